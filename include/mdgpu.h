@@ -1,0 +1,163 @@
+/*
+ * mdgpu.h — C ABI of the B200-native `MethylDackel extract` / `mbias` pileup hot path.
+ *
+ * The reference (dpryan79/MethylDackel v0.6.1) has no FFI: its seam for this path is
+ * the per-chunk body of extractCalls (extract.c:379-511) and extractMBias
+ * (MBias.c:145-218), fed by htslib callbacks (common.c:407 filter_func,
+ * overlaps.c:121 custom_overlap_constructor).  This header is the boundary a
+ * maintainer would bind instead of that body: plain pointers and sizes, no C++
+ * or torch types.  Each entry point cites the reference code it replaces.
+ *
+ * Units: a *tile* is a batch of coordinate-sorted alignments from ONE contig plus
+ * the half-open interval [beg,end) of reference positions the tile OWNS.  The
+ * caller must put into the tile every alignment that overlaps [beg,end)
+ * (exactly what sam_itr_queryi(bai,tid,beg,end) returns, extract.c:379); each
+ * position is owned by exactly one tile (extract.c:400).
+ */
+#ifndef MDGPU_H
+#define MDGPU_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDGPU_ABI_VERSION 1
+
+/* ---- options that reach the hot path: the subset of `Config`
+ *      (MethylDackel.h:90-126) read by filter_func / the per-column loop ---- */
+typedef struct md_config {
+    int32_t keepCpG, keepCHG, keepCHH;      /* extract.c:725, --noCpG/--CHG/--CHH          */
+    int32_t minMapq, minPhred;              /* extract.c:726 (-q 10, -p 5)                  */
+    int32_t keepDupes, keepSingleton, keepDiscordant; /* common.c:420,429,430             */
+    int32_t ignoreFlags, requireFlags;      /* common.c:418-419 (0xF00, 0)                  */
+    int32_t ignoreNH;                       /* common.c:421                                 */
+    int32_t minOppositeDepth;               /* extract.c:444                                */
+    double  maxVariantFrac;                 /* extract.c:446                                */
+    int32_t bounds[16];                     /* --OT/--OB/--CTOT/--CTOB, common.c:137-172    */
+    int32_t absoluteBounds[16];             /* --nOT/.., common.c:174-208                   */
+    int32_t noOverlapMerge;                 /* 1 = mbias semantics (MBias.c:160: no ctor)   */
+    int32_t reserved[7];
+} md_config;
+
+/* ---- one tile of decoded alignments, structure-of-arrays.
+ * All arrays are host pointers (pinned memory makes the copy asynchronous) for
+ * md_extract_tile()/md_mbias_tile(), or device pointers for the *_device variants.
+ * Field provenance: the BAM record fields the reference reads through htslib
+ * macros (bam1_core_t + bam_get_cigar/seq/qual, common.c:119-127,
+ * overlaps.c:27-60) and the two aux tags it scans (XG common.c:85, NH common.c:422). */
+typedef struct md_reads_soa {
+    uint32_t n_reads;
+    uint32_t n_cigar_ops;        /* total entries of cigar[]                                   */
+    uint64_t seq_words;          /* length of seq[] in 32-bit words                             */
+    uint64_t qual_words;         /* length of qual[] in 64-bit words                            */
+    const int32_t  *pos;         /* [n] 0-based leftmost reference coordinate (core.pos)        */
+    const uint16_t *flag;        /* [n] core.flag                                               */
+    const uint8_t  *mapq;        /* [n] core.qual                                               */
+    const uint8_t  *aux;         /* [n] bits0-1: XG tag (0 absent/other, 1 'C', 2 'G');
+                                        bit2: NH tag present with value > 1                     */
+    const uint32_t *l_qseq;      /* [n] query length                                            */
+    const uint32_t *cigar_off;   /* [n+1] index of the read's first op in cigar[]               */
+    const uint32_t *seq_off;     /* [n] index of the read's first 32-bit word in seq[]          */
+    const uint32_t *qual_off;    /* [n] index of the read's first 64-bit word in qual[]         */
+    const uint64_t *frag_key;    /* [n] 64-bit fingerprint of the query name (pairing key,
+                                        replaces the khash string key of overlaps.c:125)        */
+    const uint32_t *cigar;       /* BAM encoding: len<<4 | op                                   */
+    const uint32_t *seq;         /* 4-bit bases, BAM nibble order (high nibble first in each
+                                    byte), each read padded to a 32-bit word                    */
+    const uint64_t *qual;        /* phred bytes, each read padded to a 64-bit word              */
+} md_reads_soa;
+
+typedef struct md_tile_desc {
+    int32_t  tid;                /* contig id previously given to md_load_contig()              */
+    uint32_t beg, end;           /* owned reference interval [beg,end)                          */
+} md_tile_desc;
+
+/* One reported reference column (the values extract.c:420-461 hands to writeCall) */
+typedef struct md_call {
+    uint32_t pos;                /* 0-based reference position                                  */
+    uint32_t nmeth, nunmeth;     /* extract.c:438-440                                           */
+    uint32_t info;               /* bits0-1 context (0 CpG,1 CHG,2 CHH; extract.c:407-415),
+                                    bit2: reference base is G (direction<0),
+                                    bit3: column excluded as a likely variant (extract.c:444-459;
+                                          counts are then the pre-exclusion values)             */
+} md_call;
+#define MD_CALL_CTX(info)      ((info) & 3u)
+#define MD_CALL_IS_G(info)     (((info) >> 2) & 1u)
+#define MD_CALL_EXCLUDED(info) (((info) >> 3) & 1u)
+
+typedef struct md_tile_stats {
+    uint64_t n_calls;            /* records written to calls[]                                  */
+    uint64_t n_required;         /* records the tile produced (== n_calls unless capacity hit)  */
+    uint32_t n_admitted;         /* alignments that passed the filter_func tests                */
+    uint32_t n_pairs;            /* mate pairs resolved for the overlap merge                   */
+    uint32_t n_multi;            /* alignments whose query name occurred > 2 times in the tile  */
+    uint32_t reserved;
+} md_tile_stats;
+
+/* mbias histogram layout: hist[((strand*2 + read2)*lmax + qpos)*2 + {0:meth,1:unmeth}],
+ * strand 0..3 = OT,OB,CTOT,CTOB (MethylDackel.h:172-176 strandMeth, MBias.c:193-212) */
+#define MD_MBIAS_MAXLEN 1024
+
+typedef struct md_ctx md_ctx;
+
+/* Create a context on CUDA device `device` (replaces the per-thread state set up at
+ * extract.c:283-323).  Returns NULL on failure; see md_last_error(). */
+md_ctx *md_create(const md_config *cfg, int device);
+void    md_destroy(md_ctx *ctx);
+
+/* Upload one contig's bases (ASCII, case preserved, as faidx_fetch_seq returns them,
+ * extract.c:381).  The library keeps it resident in HBM until md_drop_contig(). */
+int md_load_contig(md_ctx *ctx, int32_t tid, const char *seq, uint32_t len);
+int md_drop_contig(md_ctx *ctx, int32_t tid);
+
+/* mbias only: the reference classifies context inside the per-chunk window
+ * contig[localPos..localEnd] (MBias.c:147,170-178), so context at chunk edges depends on
+ * the chunk layout.  bounds[0..n] are the n chunks' starts followed by the last end. */
+int md_set_mbias_chunks(md_ctx *ctx, int32_t tid, const uint32_t *bounds, uint32_t n_chunks);
+
+/* extract: replaces the chunk body extract.c:379-494 (pileup + per-column counting +
+ * variant test).  Writes up to `capacity` md_call records sorted by position into
+ * calls[] (host memory) and fills *stats.  Synchronous.  0 on success. */
+int md_extract_tile(md_ctx *ctx, const md_tile_desc *tile, const md_reads_soa *reads,
+                    md_call *calls, uint64_t capacity, md_tile_stats *stats);
+
+/* Asynchronous pair: md_submit_tile() enqueues copy + kernels on one of the context's
+ * streams and returns a ticket >= 0; md_collect_tile() waits for it.  The caller's input
+ * buffers must stay valid until the matching collect returns (ownership as in SURVEY 8b). */
+int md_submit_tile(md_ctx *ctx, const md_tile_desc *tile, const md_reads_soa *reads);
+int md_collect_tile(md_ctx *ctx, int ticket, md_call *calls, uint64_t capacity, md_tile_stats *stats);
+
+/* mbias: replaces MBias.c:145-218; accumulates into the context's histogram. */
+int md_mbias_tile(md_ctx *ctx, const md_tile_desc *tile, const md_reads_soa *reads, md_tile_stats *stats);
+/* Copies the accumulated histogram (uint32[4*2*MD_MBIAS_MAXLEN*2]) and the per-strand
+ * lengths `l` (MBias.c:212) to the host. */
+int md_mbias_hist(md_ctx *ctx, uint32_t *hist, int32_t lens[4]);
+int md_mbias_reset(md_ctx *ctx);
+
+/* Device-resident variants used by the benchmark's kernel-only timing: `reads` holds
+ * DEVICE pointers (e.g. from md_upload_reads) and results stay on the device. */
+typedef struct md_dev_reads md_dev_reads;
+md_dev_reads *md_upload_reads(md_ctx *ctx, const md_reads_soa *reads);
+void          md_free_reads(md_ctx *ctx, md_dev_reads *d);
+int md_extract_tile_device(md_ctx *ctx, const md_tile_desc *tile, const md_dev_reads *reads, md_tile_stats *stats);
+int md_mbias_tile_device(md_ctx *ctx, const md_tile_desc *tile, const md_dev_reads *reads, md_tile_stats *stats);
+/* Fetch the calls of the last *_device extract (for checking). */
+int md_fetch_calls(md_ctx *ctx, md_call *calls, uint64_t capacity, uint64_t *n_calls);
+
+/* CUDA-event timing of the last tile on this context, in milliseconds:
+ * out[0]=h2d, out[1]=prep+pair kernels, out[2]=count kernel, out[3]=d2h, out[4]=total. */
+int md_last_timing(md_ctx *ctx, float out[5]);
+/* Number of kernel launches issued by this context so far (for bench.py gpu_launches). */
+uint64_t md_launch_count(md_ctx *ctx);
+/* CUDA stream handle (cudaStream_t) the kernels are launched on. */
+void *md_stream(md_ctx *ctx);
+
+const char *md_last_error(void);
+int md_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

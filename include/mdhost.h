@@ -1,0 +1,73 @@
+/*
+ * mdhost.h — C ABI of the host side of the B200 MethylDackel path: the drop-in sub-command
+ * entry points and the helpers the tests and the benchmark use to decode BAM files into
+ * md_reads_soa tiles.
+ *
+ * extract_main / mbias_main have the signatures the reference exports from libMethylDackel.a
+ * (main.c:17-18, extract.c:706, MBias.c:304) and take the same argv.
+ */
+#ifndef MDHOST_H
+#define MDHOST_H
+#include "mdgpu.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* The device back end the sub-commands drive.  The shipped binary binds these slots to
+ * libmdgpu (md_create / md_load_contig / md_extract_tile / ...).  The seam exists so the host
+ * logic (option parsing, tiling, chunk replay, formatting) can be exercised by tests with a
+ * checker bound instead; the product never binds anything but libmdgpu. */
+typedef struct mdh_backend {
+    void *factory_user;
+    void *(*create)(void *factory_user, const md_config *cfg);
+    void  (*destroy)(void *be);
+    int   (*load_contig)(void *be, int32_t tid, const char *seq, uint32_t len);
+    int   (*drop_contig)(void *be, int32_t tid);
+    int   (*extract_tile)(void *be, const md_tile_desc *tile, const md_reads_soa *reads, md_call *calls, uint64_t cap, md_tile_stats *st);
+    int   (*set_mbias_chunks)(void *be, int32_t tid, const uint32_t *bounds, uint32_t n_chunks);
+    int   (*mbias_tile)(void *be, const md_tile_desc *tile, const md_reads_soa *reads, md_tile_stats *st);
+    int   (*mbias_hist)(void *be, uint32_t *hist, int32_t lens[4]);
+    const char *(*last_error)(void);
+} mdh_backend;
+
+/* Same argv conventions as the reference: argv[0] is the sub-command name. */
+int mdh_extract_main(int argc, char *argv[], const mdh_backend *be);
+int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be);
+
+/* Run statistics of the last mdh_extract_main / mdh_mbias_main call in this process */
+typedef struct mdh_run_stats {
+    uint64_t n_records;        /* alignments handed to the device (straddling reads counted once per tile) */
+    uint64_t n_tiles;
+    uint64_t n_calls;
+    double   t_decode_s, t_device_s, t_format_s, t_total_s;
+} mdh_run_stats;
+void mdh_last_run_stats(mdh_run_stats *out);
+
+/* ---- BAM -> SoA helpers (tests, bench) ---- */
+typedef struct mdh_bam mdh_bam;
+mdh_bam *mdh_bam_open(const char *path);
+void     mdh_bam_close(mdh_bam *b);
+int      mdh_bam_n_targets(const mdh_bam *b);
+const char *mdh_bam_target_name(const mdh_bam *b, int tid);
+uint32_t mdh_bam_target_len(const mdh_bam *b, int tid);
+/* Every alignment of contig `tid` overlapping [beg,end), as one tile (arrays owned by the handle and
+ * valid until the next call on it).  Scans from the start of the file (no index needed). */
+int mdh_bam_read_region(mdh_bam *b, int tid, uint32_t beg, uint32_t end, md_reads_soa *out);
+
+typedef struct mdh_fasta mdh_fasta;
+mdh_fasta *mdh_fasta_open(const char *path);
+void       mdh_fasta_close(mdh_fasta *f);
+/* whole contig; pointer owned by the handle, valid until the next fetch */
+const char *mdh_fasta_fetch(mdh_fasta *f, const char *name, uint32_t *len);
+
+/* Reference chunk layout (extract.c:325-350 + adjustBounds) of one contig, as md_set_mbias_chunks wants it:
+ * writes up to cap+1 bounds, returns the number of chunks. */
+uint32_t mdh_chunk_bounds(const char *seq, uint32_t len, unsigned long chunk_size, uint32_t reg_beg, uint32_t reg_end,
+                          uint32_t *bounds, uint32_t cap);
+
+const char *mdh_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,146 @@
+"""ctypes mirror of include/mdgpu.h and include/mdhost.h.
+
+PyTorch is not involved in the data path: the product is the C-ABI library
+``lib/libmdgpu.so`` (hand-written CUDA, sm_100a) driven by ``lib/libmdhost.so``.
+This module only describes the structs and loads the shared objects.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBDIR = os.path.join(HERE, "lib")
+MD_MBIAS_MAXLEN = 1024
+
+
+class MdConfig(C.Structure):
+    """md_config (include/mdgpu.h) — the hot-path subset of the reference's Config (MethylDackel.h:90-126)."""
+    _fields_ = [
+        ("keepCpG", C.c_int32), ("keepCHG", C.c_int32), ("keepCHH", C.c_int32),
+        ("minMapq", C.c_int32), ("minPhred", C.c_int32),
+        ("keepDupes", C.c_int32), ("keepSingleton", C.c_int32), ("keepDiscordant", C.c_int32),
+        ("ignoreFlags", C.c_int32), ("requireFlags", C.c_int32), ("ignoreNH", C.c_int32),
+        ("minOppositeDepth", C.c_int32), ("maxVariantFrac", C.c_double),
+        ("bounds", C.c_int32 * 16), ("absoluteBounds", C.c_int32 * 16),
+        ("noOverlapMerge", C.c_int32), ("reserved", C.c_int32 * 7),
+    ]
+
+
+def default_config(**kw):
+    """Defaults of extract_main (extract.c:725-746): CpG only, -q 10, -p 5, -F 0xF00."""
+    c = MdConfig()
+    c.keepCpG, c.minMapq, c.minPhred, c.ignoreFlags = 1, 10, 5, 0xF00
+    for k, v in kw.items():
+        if k in ("bounds", "absoluteBounds"):
+            for i, x in enumerate(v):
+                getattr(c, k)[i] = x
+        else:
+            setattr(c, k, v)
+    return c
+
+
+class MdReadsSoa(C.Structure):
+    _fields_ = [
+        ("n_reads", C.c_uint32), ("n_cigar_ops", C.c_uint32), ("seq_words", C.c_uint64), ("qual_words", C.c_uint64),
+        ("pos", C.POINTER(C.c_int32)), ("flag", C.POINTER(C.c_uint16)), ("mapq", C.POINTER(C.c_uint8)), ("aux", C.POINTER(C.c_uint8)),
+        ("l_qseq", C.POINTER(C.c_uint32)), ("cigar_off", C.POINTER(C.c_uint32)), ("seq_off", C.POINTER(C.c_uint32)), ("qual_off", C.POINTER(C.c_uint32)),
+        ("frag_key", C.POINTER(C.c_uint64)), ("cigar", C.POINTER(C.c_uint32)), ("seq", C.POINTER(C.c_uint32)), ("qual", C.POINTER(C.c_uint64)),
+    ]
+
+
+class MdTileDesc(C.Structure):
+    _fields_ = [("tid", C.c_int32), ("beg", C.c_uint32), ("end", C.c_uint32)]
+
+
+class MdCall(C.Structure):
+    _fields_ = [("pos", C.c_uint32), ("nmeth", C.c_uint32), ("nunmeth", C.c_uint32), ("info", C.c_uint32)]
+
+
+class MdTileStats(C.Structure):
+    _fields_ = [("n_calls", C.c_uint64), ("n_required", C.c_uint64), ("n_admitted", C.c_uint32), ("n_pairs", C.c_uint32),
+                ("n_multi", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class MdhRunStats(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("n_tiles", C.c_uint64), ("n_calls", C.c_uint64),
+                ("t_decode_s", C.c_double), ("t_device_s", C.c_double), ("t_format_s", C.c_double), ("t_total_s", C.c_double)]
+
+
+CREATE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.POINTER(MdConfig))
+DESTROY_FN = C.CFUNCTYPE(None, C.c_void_p)
+LOAD_CONTIG_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_uint32)
+DROP_CONTIG_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32)
+EXTRACT_TILE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa), C.POINTER(MdCall), C.c_uint64, C.POINTER(MdTileStats))
+SET_CHUNKS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.POINTER(C.c_uint32), C.c_uint32)
+MBIAS_TILE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa), C.POINTER(MdTileStats))
+MBIAS_HIST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32))
+LAST_ERROR_FN = C.CFUNCTYPE(C.c_char_p)
+
+
+class MdhBackend(C.Structure):
+    _fields_ = [("factory_user", C.c_void_p), ("create", CREATE_FN), ("destroy", DESTROY_FN), ("load_contig", LOAD_CONTIG_FN),
+                ("drop_contig", DROP_CONTIG_FN), ("extract_tile", EXTRACT_TILE_FN), ("set_mbias_chunks", SET_CHUNKS_FN),
+                ("mbias_tile", MBIAS_TILE_FN), ("mbias_hist", MBIAS_HIST_FN), ("last_error", LAST_ERROR_FN)]
+
+
+_host = None
+_gpu = None
+
+
+def load_host():
+    """libmdhost.so: BAM decode -> SoA, chunk replay, formatter, sub-command mains (no CUDA dependency)."""
+    global _host
+    if _host is None:
+        p = os.path.join(LIBDIR, "libmdhost.so")
+        if not os.path.exists(p):
+            raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (or make -C methyldackel_b200/csrc host)" % p)
+        h = C.CDLL(p)
+        h.mdh_extract_main.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(MdhBackend)]
+        h.mdh_mbias_main.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(MdhBackend)]
+        h.mdh_last_run_stats.argtypes = [C.POINTER(MdhRunStats)]
+        h.mdh_bam_open.restype = C.c_void_p; h.mdh_bam_open.argtypes = [C.c_char_p]
+        h.mdh_bam_close.argtypes = [C.c_void_p]
+        h.mdh_bam_n_targets.argtypes = [C.c_void_p]
+        h.mdh_bam_target_name.restype = C.c_char_p; h.mdh_bam_target_name.argtypes = [C.c_void_p, C.c_int]
+        h.mdh_bam_target_len.restype = C.c_uint32; h.mdh_bam_target_len.argtypes = [C.c_void_p, C.c_int]
+        h.mdh_bam_read_region.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(MdReadsSoa)]
+        h.mdh_fasta_open.restype = C.c_void_p; h.mdh_fasta_open.argtypes = [C.c_char_p]
+        h.mdh_fasta_close.argtypes = [C.c_void_p]
+        h.mdh_fasta_fetch.restype = C.c_void_p; h.mdh_fasta_fetch.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint32)]
+        h.mdh_chunk_bounds.restype = C.c_uint32
+        h.mdh_chunk_bounds.argtypes = [C.c_char_p, C.c_uint32, C.c_ulong, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]
+        h.mdh_last_error.restype = C.c_char_p
+        _host = h
+    return _host
+
+
+def load_gpu():
+    """libmdgpu.so: the CUDA library. Fails loudly if it has not been built — there is no CPU fallback."""
+    global _gpu
+    if _gpu is None:
+        p = os.path.join(LIBDIR, "libmdgpu.so")
+        if not os.path.exists(p):
+            raise RuntimeError("%s is missing: the CUDA extension must be built (make -C methyldackel_b200/csrc gpu); there is no CPU fallback" % p)
+        g = C.CDLL(p, mode=C.RTLD_GLOBAL)
+        g.md_create.restype = C.c_void_p; g.md_create.argtypes = [C.POINTER(MdConfig), C.c_int]
+        g.md_destroy.argtypes = [C.c_void_p]
+        g.md_load_contig.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint32]
+        g.md_drop_contig.argtypes = [C.c_void_p, C.c_int32]
+        g.md_set_mbias_chunks.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint32), C.c_uint32]
+        g.md_extract_tile.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa), C.POINTER(MdCall), C.c_uint64, C.POINTER(MdTileStats)]
+        g.md_submit_tile.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa)]
+        g.md_collect_tile.argtypes = [C.c_void_p, C.c_int, C.POINTER(MdCall), C.c_uint64, C.POINTER(MdTileStats)]
+        g.md_mbias_tile.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa), C.POINTER(MdTileStats)]
+        g.md_mbias_hist.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
+        g.md_mbias_reset.argtypes = [C.c_void_p]
+        g.md_upload_reads.restype = C.c_void_p; g.md_upload_reads.argtypes = [C.c_void_p, C.POINTER(MdReadsSoa)]
+        g.md_free_reads.argtypes = [C.c_void_p, C.c_void_p]
+        g.md_extract_tile_device.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.c_void_p, C.POINTER(MdTileStats)]
+        g.md_mbias_tile_device.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.c_void_p, C.POINTER(MdTileStats)]
+        g.md_fetch_calls.argtypes = [C.c_void_p, C.POINTER(MdCall), C.c_uint64, C.POINTER(C.c_uint64)]
+        g.md_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        g.md_launch_count.restype = C.c_uint64; g.md_launch_count.argtypes = [C.c_void_p]
+        g.md_stream.restype = C.c_void_p; g.md_stream.argtypes = [C.c_void_p]
+        g.md_last_error.restype = C.c_char_p
+        g.md_abi_version.restype = C.c_int
+        _gpu = g
+    return _gpu

@@ -1,0 +1,478 @@
+// Host driver of the B200 `MethylDackel extract` / `mbias` sub-commands (libmdhost).
+//
+// Mirrors the reference's drop-in surface for this path: the option tables and defaults of
+// extract_main (extract.c:715-946) and mbias_main (MBias.c:312-443), their validation and exit
+// codes (extract.c:979-1034, MBias.c:445-469), output file naming and headers
+// (extract.c:1344-1439), `-r` handling (extract.c:1441-1468) and the end-of-run messages
+// (extract.c:1489).  The per-chunk worker body (extract.c:379-511 / MBias.c:145-218) is NOT
+// here: alignments are decoded into SoA tiles and handed to the device back end.
+#include <getopt.h>
+#include <cstdlib>
+#include <cerrno>
+#include <climits>
+#include <chrono>
+#include <map>
+#include "tiles.hpp"
+#include "format.hpp"
+#include "mbias_report.hpp"
+#include "../../../include/mdhost.h"
+
+using namespace mdhost;
+
+#define MD_VERSION "0.6.1-b200"
+
+static thread_local std::string g_err;
+static mdh_run_stats g_stats;
+extern "C" const char *mdh_last_error(void) { return g_err.c_str(); }
+extern "C" void mdh_last_run_stats(mdh_run_stats *out) { if (out) *out = g_stats; }
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// parseBounds, common.c:11-43: four comma-separated non-negative ints into vals[4*mult..]
+static void parse_bounds(const char *s2, int *vals, int mult) {
+    std::string s(s2);
+    char *save = nullptr, *p = strtok_r(&s[0], ",", &save);
+    for (int i = 0; i < 4; ++i) {
+        char *end = nullptr; long v = -1;
+        if (p) { errno = 0; long t = strtol(p, &end, 10); if (!(errno != 0 || end == p || t > INT_MAX || t < 0)) v = t; }
+        if (v < 0) { fprintf(stderr, "Invalid bounds string, %s\n", s2); return; }
+        vals[4 * mult + i] = (int) v;
+        p = strtok_r(nullptr, ",", &save);
+    }
+}
+
+// hts_parse_reg as the reference uses it (extract.c:1446): returns length of the name part, or -1
+static int parse_region(const char *s, int *beg, int *end) {
+    const char *colon = strrchr(s, ':');
+    if (!colon) { *beg = 0; *end = INT_MAX; return (int) strlen(s); }
+    auto dec = [](const char *p, const char **e) { long long v = 0; bool neg = false; if (*p == '-') { neg = true; ++p; } while (isdigit((unsigned char) *p) || *p == ',') { if (*p != ',') v = v * 10 + (*p - '0'); ++p; } *e = p; return neg ? -v : v; };
+    const char *p; long long b = dec(colon + 1, &p) - 1, e;
+    if (b < 0) {
+        if (b != -1 && *p == '-' && colon[1] != '\0') return -1;
+        if (isdigit((unsigned char) *p) || *p == '\0' || *p == ',') { e = (b == -1) ? INT_MAX : -(b + 1); *beg = 0; *end = (int) e; return (int)(colon - s); }
+        if (b < -1) return -1;
+    }
+    if (*p == '\0' || *p == ',') e = INT_MAX;
+    else if (*p == '-') { const char *q; e = dec(p + 1, &q); if (*q != '\0' && *q != ',') return -1; }
+    else return -1;
+    if (b >= e || b > INT_MAX) return -1;
+    if (e > INT_MAX) e = INT_MAX;
+    *beg = (int) b; *end = (int) e;
+    return (int)(colon - s);
+}
+
+static void extract_usage() {
+    fprintf(stderr,
+"\nUsage: MethylDackel extract [OPTIONS] <ref.fa> <sorted_alignments.bam>\n\n"
+"B200 build of the extract hot path. Options (same names, defaults and meaning as MethylDackel 0.6.1):\n"
+"  -q INT  -p INT  -d INT  -r STR  -o/--opref STR  -@ INT  --chunkSize INT  -D INT (ignored)\n"
+"  --noCpG  --CHG  --CHH  --mergeContext  --fraction  --counts  --logit  --methylKit  --cytosine_report\n"
+"  --keepDupes  --keepSingleton  --keepDiscordant  -F/--ignoreFlags INT  -R/--requireFlags INT  --ignoreNH\n"
+"  --minOppositeDepth INT  --maxVariantFrac FLOAT\n"
+"  --OT/--OB/--CTOT/--CTOB INT,INT,INT,INT   --nOT/--nOB/--nCTOT/--nCTOB INT,INT,INT,INT\n"
+"  -h/--help  -v/--version\n"
+"Not available in this build yet: -l/--keepStrand (BED), -M/-t/-b/-O/-N/-B (mappability), --minConversionEfficiency.\n"
+"Note that --fraction, --counts, and --logit are mutually exclusive!\n");
+}
+
+static void mbias_usage() {
+    fprintf(stderr,
+"\nUsage: MethylDackel mbias [OPTIONS] <ref.fa> <sorted_alignments.bam> <output.prefix>\n\n"
+"B200 build of the mbias hot path. Options (as MethylDackel 0.6.1):\n"
+"  -q INT  -p INT  -r STR  -@ INT  --chunkSize INT  -D INT (ignored)  --noCpG  --CHG  --CHH\n"
+"  --keepDupes  --keepSingleton  --keepDiscordant  -F INT  -R INT  --ignoreNH  --txt  --noSVG\n"
+"  --nOT/--nOB/--nCTOT/--nCTOB INT,INT,INT,INT  -h/--help  -v/--version\n"
+"Not available in this build yet: -l/--keepStrand (BED), --minConversionEfficiency.\n");
+}
+
+static bool load_bai(const std::string &bam, BaiIndex &idx) {
+    if (BaiIndex::load(bam + ".bai", idx)) return true;
+    size_t n = bam.size();
+    if (n > 4 && bam.compare(n - 4, 4, ".bam") == 0) return BaiIndex::load(bam.substr(0, n - 4) + ".bai", idx);
+    return false;
+}
+
+extern "C" uint32_t mdh_chunk_bounds(const char *seq, uint32_t len, unsigned long chunk_size, uint32_t reg_beg, uint32_t reg_end, uint32_t *bounds, uint32_t cap) {
+    std::vector<uint32_t> lens{len};
+    std::string s(seq, len);
+    ChunkCursor cur(lens, chunk_size, 0, reg_beg, reg_end);
+    Chunk c; uint32_t n = 0;
+    auto fetch = [&](uint32_t) { return &s; };
+    while (cur.next(c, fetch)) {
+        if (c.tid != 0) break;
+        if (n < cap) { bounds[n] = c.beg; bounds[n + 1] = c.end; }
+        ++n;
+    }
+    return n;
+}
+
+namespace {
+struct Driver {
+    const mdh_backend *be; void *dev = nullptr;
+    std::unique_ptr<BamStream> bam; std::unique_ptr<Fasta> fa; BaiIndex bai; bool have_bai = false;
+    const BamHeader *hdr = nullptr;
+    std::string cur_seq; int cur_seq_tid = -1; bool cur_seq_ok = false;
+    const std::string *fetch(uint32_t tid) {
+        if ((int) tid != cur_seq_tid) {
+            cur_seq_tid = (int) tid; cur_seq.clear();
+            cur_seq_ok = tid < hdr->names.size() && fa->fetch(hdr->names[tid], cur_seq);
+        }
+        return cur_seq_ok ? &cur_seq : nullptr;
+    }
+    void seek_to(int tid, uint32_t beg) {
+        if (!have_bai) return;           // sequential scan: the stream only moves forward and skips earlier contigs
+        bool found; uint64_t off = bai.start_offset(tid, beg, found);
+        if (found && off) bam->seek(off);
+    }
+};
+}  // namespace
+
+extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
+    ExtractOptions o;
+    char *opref = nullptr; const char *reg = nullptr, *bedName = nullptr, *bwName = nullptr, *bbmName = nullptr;
+    int c, nThreads = 1, keepStrand = 0; double minConvEff = 0.0;
+    (void) keepStrand; (void) nThreads;
+    double t_start = now_s();
+    memset(&g_stats, 0, sizeof g_stats);
+
+    static struct option lopts[] = {
+        {"opref", 1, NULL, 'o'}, {"fraction", 0, NULL, 'f'}, {"counts", 0, NULL, 'c'}, {"logit", 0, NULL, 'm'}, {"minDepth", 1, NULL, 'd'},
+        {"noCpG", 0, NULL, 1}, {"CHG", 0, NULL, 2}, {"CHH", 0, NULL, 3}, {"keepDupes", 0, NULL, 4}, {"keepSingleton", 0, NULL, 5}, {"keepDiscordant", 0, NULL, 6},
+        {"OT", 1, NULL, 7}, {"OB", 1, NULL, 8}, {"CTOT", 1, NULL, 9}, {"CTOB", 1, NULL, 10}, {"mergeContext", 0, NULL, 11}, {"methylKit", 0, NULL, 12},
+        {"nOT", 1, NULL, 13}, {"nOB", 1, NULL, 14}, {"nCTOT", 1, NULL, 15}, {"nCTOB", 1, NULL, 16}, {"minOppositeDepth", 1, NULL, 17}, {"maxVariantFrac", 1, NULL, 18},
+        {"chunkSize", 1, NULL, 19}, {"keepStrand", 0, NULL, 20}, {"cytosine_report", 0, NULL, 21}, {"minConversionEfficiency", 1, NULL, 22}, {"ignoreNH", 0, NULL, 23},
+        {"ignoreFlags", 1, NULL, 'F'}, {"requireFlags", 1, NULL, 'R'}, {"help", 0, NULL, 'h'}, {"version", 0, NULL, 'v'},
+        {"mappability", 1, NULL, 'M'}, {"mappabilityThreshold", 1, NULL, 't'}, {"minMappableBases", 1, NULL, 'b'}, {"outputBBMFile", 1, NULL, 'O'},
+        {"outputBBMFileName", 1, NULL, 'N'}, {"mappabilityBBM", 1, NULL, 'B'}, {0, 0, NULL, 0}};
+    optind = 0;   // re-entrant use from one process
+    while ((c = getopt_long(argc, argv, "hvq:p:r:l:o:D:f:c:m:d:F:R:@:M:t:b:ON:B:", lopts, NULL)) >= 0) {
+        switch (c) {
+        case 'h': extract_usage(); return 0;
+        case 'v': printf("%s (B200 build; no HTSlib)\n", MD_VERSION); return 0;
+        case 'o': free(opref); opref = strdup(optarg); break;
+        case 'D': break;
+        case 'd': o.minDepth = atoi(optarg); if (o.minDepth < 1) { fprintf(stderr, "Error, the minimum depth must be at least 1!\n"); return 1; } break;
+        case 'r': reg = optarg; break;
+        case 'l': bedName = optarg; break;
+        case 1: o.core.keepCpG = 0; break;
+        case 2: o.core.keepCHG = 1; break;
+        case 3: o.core.keepCHH = 1; break;
+        case 4: o.core.keepDupes = 1; break;
+        case 5: o.core.keepSingleton = 1; break;
+        case 6: o.core.keepDiscordant = 1; break;
+        case 7: case 8: case 9: case 10: parse_bounds(optarg, o.core.bounds, c - 7); break;
+        case 11: o.merge = 1; break;
+        case 12: o.methylKit = 1; break;
+        case 13: case 14: case 15: case 16: parse_bounds(optarg, o.core.absoluteBounds, c - 13); break;
+        case 17: o.core.minOppositeDepth = atoi(optarg); break;
+        case 18: o.core.maxVariantFrac = atof(optarg); break;
+        case 19: o.chunkSize = strtoul(optarg, NULL, 10); if (o.chunkSize < 1) { fprintf(stderr, "Error: The chunk size must be at least 1!\n"); return 1; } break;
+        case 20: keepStrand = 1; break;
+        case 21: o.cytosine_report = 1; break;
+        case 22: minConvEff = atof(optarg); break;
+        case 23: o.core.ignoreNH = 1; break;
+        case 'M': bwName = optarg; break;
+        case 't': case 'b': case 'O': case 'N': break;
+        case 'B': bbmName = optarg; break;
+        case 'F': o.core.ignoreFlags = atoi(optarg); break;       // atoi: "0xD00" parses as 0 (tests/test.py:68)
+        case 'R': o.core.requireFlags = atoi(optarg); break;
+        case 'q': o.core.minMapq = atoi(optarg); break;
+        case 'p': o.core.minPhred = atoi(optarg); break;
+        case 'm': o.logit = 1; break;
+        case 'f': o.fraction = 1; break;
+        case 'c': o.counts = 1; break;
+        case '@': nThreads = atoi(optarg); break;
+        case '?': default: fprintf(stderr, "Invalid option '%c'\n", c); extract_usage(); return 1;
+        }
+    }
+    if (argc == 1) { extract_usage(); return 0; }
+    if (argc - optind < 2) { fprintf(stderr, "You must supply a reference genome in fasta format and an input BAM file!!!\n"); extract_usage(); return -1; }
+    if (o.core.minPhred < 1) { fprintf(stderr, "-p %i is invalid. resetting to 1, which is the lowest possible value.\n", o.core.minPhred); o.core.minPhred = 1; }
+    if (o.core.minMapq < 0) { fprintf(stderr, "-q %i is invalid. Resetting to 0, which is the lowest possible value.\n", o.core.minMapq); o.core.minMapq = 0; }
+    if (o.core.keepDupes > 0 && (o.core.ignoreFlags & 0x400)) o.core.ignoreFlags -= 0x400;
+    if (o.fraction + o.counts + o.logit + o.methylKit + o.cytosine_report > 1) {
+        fprintf(stderr, "More than one of --fraction, --counts, --methylKit, --cytosine_report and --logit were specified. These are mutually exclusive.\n"); extract_usage(); return 1; }
+    if (o.methylKit + o.merge == 2) { fprintf(stderr, "--mergeContext and --methylKit are mutually exclusive.\n"); extract_usage(); return 1; }
+    if (o.cytosine_report + o.merge == 2) { fprintf(stderr, "--mergeContext and --cytosine_report are mutually exclusive.\n"); extract_usage(); return 1; }
+    if (!(o.core.keepCpG + o.core.keepCHG + o.core.keepCHH)) {
+        fprintf(stderr, "You haven't specified any metrics to output!\nEither don't use the --noCpG option or specify --CHG and/or --CHH.\n"); return -1; }
+    if (bedName || bwName || bbmName || minConvEff > 0.0) {
+        fprintf(stderr, "This B200 build of the extract path does not implement -l, -M/-B or --minConversionEfficiency yet.\n"); return 1; }
+
+    Driver d; d.be = be;
+    const char *fastaName = argv[optind], *bamName = argv[optind + 1];
+    try { d.bam.reset(new BamStream(bamName)); }
+    catch (std::exception &e) { fprintf(stderr, "Couldn't open %s for reading!\n", bamName); return -4; }
+    d.hdr = &d.bam->header();
+    d.have_bai = load_bai(bamName, d.bai);
+    try { d.fa.reset(new Fasta(fastaName)); }
+    catch (std::exception &e) { fprintf(stderr, "Couldn't open the index for %s!\n", fastaName); return -4; }
+
+    // output files, extract.c:1344-1439
+    if (opref == NULL) {
+        opref = strdup(bamName);
+        char *p = strrchr(opref, '.');
+        if (p != NULL) *p = '\0';
+        fprintf(stderr, "writing to prefix:'%s'\n", opref);
+    }
+    FILE *fp[3] = {nullptr, nullptr, nullptr};
+    std::string pre(opref);
+    const char *mid = o.fraction ? ".meth.bedGraph" : o.counts ? ".counts.bedGraph" : o.logit ? ".logit.bedGraph" : o.methylKit ? ".methylKit" : ".bedGraph";
+    if (o.cytosine_report) {
+        fp[0] = fopen((pre + ".cytosine_report.txt").c_str(), "w"); fp[1] = fp[2] = fp[0];
+        if (!fp[0]) { fprintf(stderr, "Couldn't open the output CpG metrics file for writing! Insufficient permissions?\n"); free(opref); return -3; }
+    } else {
+        static const char *ctxName[3] = {"CpG", "CHG", "CHH"};
+        int keep[3] = {o.core.keepCpG, o.core.keepCHG, o.core.keepCHH};
+        for (int k = 0; k < 3; ++k) if (keep[k]) {
+            fp[k] = fopen((pre + "_" + ctxName[k] + mid).c_str(), "w");
+            if (!fp[k]) { fprintf(stderr, "Couldn't open the output %s metrics file for writing! Insufficient permissions?\n", ctxName[k]); free(opref); return -3; }
+            if (o.methylKit) fprintf(fp[k], "chrBase\tchr\tbase\tstrand\tcoverage\tfreqC\tfreqT\n");
+            else ExtractWriter::print_header(fp[k], ctxName[k], opref, o);
+        }
+    }
+    // -r, extract.c:1441-1468
+    uint32_t gTid = 0, gPos = 0, gEnd = 0;
+    if (reg) {
+        int s, e, nl = parse_region(reg, &s, &e);
+        if (nl < 0) { fprintf(stderr, "Could not parse the specified region!\n"); return -4; }
+        int tid = d.hdr->name2tid(std::string(reg, (size_t) nl));
+        if (tid < 0) { fprintf(stderr, "%s did not match a known chromosome/contig name!\n", reg); return -6; }
+        gTid = (uint32_t) tid;
+        if (s > 0) gPos = (uint32_t) s;
+        if (e > 0) gEnd = (uint32_t) e;
+        if (gEnd > d.hdr->lens[gTid]) gEnd = d.hdr->lens[gTid];
+    }
+
+    d.dev = be->create(be->factory_user, &o.core);
+    if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+    ExtractWriter writer(o, fp);
+    int rc = 0;
+    {
+        ChunkCursor cursor(d.hdr->lens, o.chunkSize, gTid, gPos, gEnd);
+        auto fetch = [&](uint32_t t) { return d.fetch(t); };
+        Chunk ch; bool have = cursor.next(ch, fetch);
+        SoaTile tile, carry;
+        std::vector<md_call> calls; size_t calls_head = 0;
+        std::vector<md_call> tile_calls;
+        while (have && rc == 0) {
+            // all reference chunks of this contig
+            uint32_t tid = ch.tid;
+            std::vector<Chunk> chunks;
+            while (have && ch.tid == tid) { chunks.push_back(ch); have = cursor.next(ch, fetch); }
+            // NB: cursor.next() may already have fetched the NEXT contig's bases; re-fetch ours.
+            const std::string *ref = d.fetch(tid);
+            if (!ref) {
+                fprintf(stderr, "faidx_fetch_seq returned %i while trying to fetch the sequence for tid %s:%" PRIu32 "-%" PRIu32 "!\n", -2, d.hdr->names[tid].c_str(), chunks.front().beg, chunks.front().end);
+                fprintf(stderr, "Note that the output will be truncated!\n");
+                continue;
+            }
+            uint32_t rbeg = chunks.front().beg, rend = chunks.back().end;
+            if (rend > ref->size()) rend = (uint32_t) ref->size();
+            if (be->load_contig(d.dev, (int32_t) tid, ref->data(), (uint32_t) ref->size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+            d.seek_to((int) tid, rbeg);
+            Tiler tiler(*d.bam, (int) tid, rbeg, rend, (size_t) 1 << 19);
+            calls.clear(); calls_head = 0; carry.clear();
+            size_t next_chunk = 0;
+            for (;;) {
+                double t0 = now_s();
+                bool got = tiler.next(tile, carry);
+                g_stats.t_decode_s += now_s() - t0;
+                uint32_t done_upto = rend;
+                if (got) {
+                    done_upto = tile.end;
+                    if (tile.n() > 0) {
+                        md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end}; md_tile_stats st;
+                        uint64_t cap = (uint64_t)(tile.end - tile.beg) + 16;
+                        tile_calls.resize(cap);
+                        t0 = now_s();
+                        int r = be->extract_tile(d.dev, &td, &v, tile_calls.data(), cap, &st);
+                        g_stats.t_device_s += now_s() - t0;
+                        if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+                        calls.insert(calls.end(), tile_calls.begin(), tile_calls.begin() + (ptrdiff_t) st.n_calls);
+                        g_stats.n_records += tile.n(); g_stats.n_tiles++; g_stats.n_calls += st.n_calls;
+                    }
+                }
+                t0 = now_s();
+                while (next_chunk < chunks.size() && (chunks[next_chunk].end <= done_upto || !got)) {
+                    const Chunk &k = chunks[next_chunk];
+                    size_t a = calls_head; while (a < calls.size() && calls[a].pos < k.beg) ++a;
+                    size_t b = a; while (b < calls.size() && calls[b].pos < k.end) ++b;
+                    writer.process_chunk(d.hdr->names[tid].c_str(), *ref, k.beg, k.end, calls.data() + a, b - a);
+                    calls_head = b; ++next_chunk;
+                }
+                if (calls_head > (1u << 20)) { calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
+                g_stats.t_format_s += now_s() - t0;
+                if (!got) break;
+            }
+            be->drop_contig(d.dev, (int32_t) tid);
+        }
+    }
+    be->destroy(d.dev);
+    if (writer.n_variant_positions()) printf("%" PRIu64 " positions were excluded due to likely being variants.\n", writer.n_variant_positions());
+    if (o.cytosine_report) { if (fp[0]) fclose(fp[0]); }
+    else for (int k = 0; k < 3; ++k) if (fp[k]) fclose(fp[k]);
+    free(opref);
+    g_stats.t_total_s = now_s() - t_start;
+    return rc;
+}
+
+extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
+    md_config cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.keepCpG = 1; cfg.minMapq = 10; cfg.minPhred = 5; cfg.ignoreFlags = 0xF00; cfg.noOverlapMerge = 1;   // MBias.c:312-328, :160
+    unsigned long chunkSize = 1000000;
+    const char *reg = nullptr, *bedName = nullptr; char *opref = nullptr;
+    int c, SVG = 1, txt = 0, nThreads = 1; double minConvEff = 0.0;
+    (void) nThreads;
+    double t_start = now_s();
+    memset(&g_stats, 0, sizeof g_stats);
+    static struct option lopts[] = {
+        {"noCpG", 0, NULL, 1}, {"CHG", 0, NULL, 2}, {"CHH", 0, NULL, 3}, {"keepDupes", 0, NULL, 4}, {"keepSingleton", 0, NULL, 5}, {"keepDiscordant", 0, NULL, 6},
+        {"txt", 0, NULL, 7}, {"noSVG", 0, NULL, 8}, {"nOT", 1, NULL, 9}, {"nOB", 1, NULL, 10}, {"nCTOT", 1, NULL, 11}, {"nCTOB", 1, NULL, 12},
+        {"chunkSize", 1, NULL, 13}, {"keepStrand", 0, NULL, 14}, {"minConversionEfficiency", 1, NULL, 15}, {"ignoreNH", 0, NULL, 16},
+        {"ignoreFlags", 1, NULL, 'F'}, {"requireFlags", 1, NULL, 'R'}, {"help", 0, NULL, 'h'}, {"version", 0, NULL, 'v'}, {0, 0, NULL, 0}};
+    optind = 0;
+    while ((c = getopt_long(argc, argv, "hvq:p:r:l:D:F:@:", lopts, NULL)) >= 0) {
+        switch (c) {
+        case 'h': mbias_usage(); return 0;
+        case 'v': printf("%s (B200 build; no HTSlib)\n", MD_VERSION); return 0;
+        case 'D': break;
+        case 'r': reg = optarg; break;
+        case 'l': bedName = optarg; break;
+        case 1: cfg.keepCpG = 0; break;
+        case 2: cfg.keepCHG = 1; break;
+        case 3: cfg.keepCHH = 1; break;
+        case 4: cfg.keepDupes = 1; break;
+        case 5: cfg.keepSingleton = 1; break;
+        case 6: cfg.keepDiscordant = 1; break;
+        case 7: txt = 1; break;
+        case 8: SVG = 0; txt = 1; break;
+        case 9: case 10: case 11: case 12: parse_bounds(optarg, cfg.absoluteBounds, c - 9); break;
+        case 13: chunkSize = strtoul(optarg, NULL, 10); if (chunkSize < 1) { fprintf(stderr, "Error: The chunk size must be at least 1!\n"); return 1; } break;
+        case 14: break;
+        case 15: minConvEff = atof(optarg); break;
+        case 16: cfg.ignoreNH = 1; break;
+        case 'F': cfg.ignoreFlags = atoi(optarg); break;
+        case 'R': cfg.requireFlags = atoi(optarg); break;
+        case 'q': cfg.minMapq = atoi(optarg); break;
+        case 'p': cfg.minPhred = atoi(optarg); break;
+        case '@': nThreads = atoi(optarg); break;
+        default: fprintf(stderr, "Invalid option '%c'\n", c); mbias_usage(); return 1;
+        }
+    }
+    if (argc == 1) { mbias_usage(); return 0; }
+    if ((SVG && argc - optind != 3) || (!SVG && argc - optind < 2)) {
+        fprintf(stderr, "You must supply a reference genome in fasta format, an input BAM file, and an output prefix!!!\n"); mbias_usage(); return -1; }
+    if (cfg.minPhred < 1) { fprintf(stderr, "-p %i is invalid. resetting to 1, which is the lowest possible value.\n", cfg.minPhred); cfg.minPhred = 1; }
+    if (cfg.minMapq < 0) { fprintf(stderr, "-q %i is invalid. Resetting to 0, which is the lowest possible value.\n", cfg.minMapq); cfg.minMapq = 0; }
+    if (!(cfg.keepCpG + cfg.keepCHG + cfg.keepCHH)) {
+        fprintf(stderr, "You haven't specified any metrics to output!\nEither don't use the --noCpG option or specify --CHG and/or --CHH.\n"); return -1; }
+    if (bedName || minConvEff > 0.0) { fprintf(stderr, "This B200 build of the mbias path does not implement -l or --minConversionEfficiency yet.\n"); return 1; }
+    // NB: mbias never applies the 0x400 adjustment of extract.c:1005-1007 (MBias.c has no such line)
+
+    Driver d; d.be = be;
+    const char *fastaName = argv[optind], *bamName = argv[optind + 1];
+    try { d.bam.reset(new BamStream(bamName)); }
+    catch (std::exception &e) { fprintf(stderr, "Couldn't open %s for reading!\n", bamName); return -4; }
+    d.hdr = &d.bam->header();
+    d.have_bai = load_bai(bamName, d.bai);
+    try { d.fa.reset(new Fasta(fastaName)); }
+    catch (std::exception &e) { fprintf(stderr, "Couldn't open the index for %s!\n", fastaName); return -4; }
+    if (SVG) opref = argv[optind + 2];
+    uint32_t gTid = 0, gPos = 0, gEnd = 0;
+    if (reg) {
+        int s, e, nl = parse_region(reg, &s, &e);
+        if (nl < 0) { fprintf(stderr, "Could not parse the specified region!\n"); return -4; }
+        int tid = d.hdr->name2tid(std::string(reg, (size_t) nl));
+        if (tid < 0) { fprintf(stderr, "%s did not match a known chromosome/contig name!\n", reg); return -6; }
+        gTid = (uint32_t) tid;
+        if (s > 0) gPos = (uint32_t) s;
+        if (e > 0) gEnd = (uint32_t) e;
+        if (gEnd > d.hdr->lens[gTid]) gEnd = d.hdr->lens[gTid];
+    }
+    d.dev = be->create(be->factory_user, &cfg);
+    if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+    int rc = 0;
+    {
+        ChunkCursor cursor(d.hdr->lens, chunkSize, gTid, gPos, gEnd);
+        auto fetch = [&](uint32_t t) { return d.fetch(t); };
+        Chunk ch; bool have = cursor.next(ch, fetch);
+        SoaTile tile, carry;
+        while (have && rc == 0) {
+            uint32_t tid = ch.tid;
+            std::vector<uint32_t> bounds;
+            while (have && ch.tid == tid) { if (bounds.empty()) bounds.push_back(ch.beg); bounds.push_back(ch.end); have = cursor.next(ch, fetch); }
+            const std::string *ref = d.fetch(tid);
+            if (!ref) {
+                fprintf(stderr, "faidx_fetch_seq returned %i while trying to fetch the sequence for tid %s:%" PRIu32 "-%" PRIu32 "!\n", -2, d.hdr->names[tid].c_str(), bounds.front(), bounds.back());
+                fprintf(stderr, "Note that the output will be truncated!\n");
+                break;                                             // MBias.c:152 returns from the worker
+            }
+            uint32_t rbeg = bounds.front(), rend = bounds.back();
+            if (rend > ref->size()) rend = (uint32_t) ref->size();
+            if (be->load_contig(d.dev, (int32_t) tid, ref->data(), (uint32_t) ref->size()) != 0 ||
+                be->set_mbias_chunks(d.dev, (int32_t) tid, bounds.data(), (uint32_t) bounds.size() - 1) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+            d.seek_to((int) tid, rbeg);
+            Tiler tiler(*d.bam, (int) tid, rbeg, rend, (size_t) 1 << 19);
+            carry.clear();
+            for (;;) {
+                double t0 = now_s();
+                bool got = tiler.next(tile, carry);
+                g_stats.t_decode_s += now_s() - t0;
+                if (!got) break;
+                if (tile.n() == 0) continue;
+                md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end}; md_tile_stats st;
+                t0 = now_s();
+                int r = be->mbias_tile(d.dev, &td, &v, &st);
+                g_stats.t_device_s += now_s() - t0;
+                if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+                g_stats.n_records += tile.n(); g_stats.n_tiles++;
+            }
+            be->drop_contig(d.dev, (int32_t) tid);
+        }
+    }
+    std::vector<uint32_t> hist((size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2, 0); int32_t lens[4] = {0, 0, 0, 0};
+    if (rc == 0 && be->mbias_hist(d.dev, hist.data(), lens) != 0) rc = -20;
+    be->destroy(d.dev);
+    if (rc == 0) {
+        // makeSVGs (svg.c:302-437) is where the reference prints the suggestions; the SVG drawing itself is
+        // host-only plotting outside the accelerated path and is not produced by this build.
+        if (SVG) { (void) opref; mbias_print_suggestions(stderr, hist.data(), lens); }
+        if (txt) mbias_print_txt(stdout, hist.data(), lens);
+    }
+    g_stats.t_total_s = now_s() - t_start;
+    return rc;
+}
+
+// ------------------------------------------------------------------ BAM/FASTA helpers for tests + bench
+struct mdh_bam { std::string path; BamHeader hdr; SoaTile tile; };
+extern "C" mdh_bam *mdh_bam_open(const char *path) {
+    try { BamStream s(path); mdh_bam *b = new mdh_bam(); b->path = path; b->hdr = s.header(); return b; }
+    catch (std::exception &e) { g_err = e.what(); return nullptr; }
+}
+extern "C" void mdh_bam_close(mdh_bam *b) { delete b; }
+extern "C" int mdh_bam_n_targets(const mdh_bam *b) { return (int) b->hdr.names.size(); }
+extern "C" const char *mdh_bam_target_name(const mdh_bam *b, int tid) { return b->hdr.names[(size_t) tid].c_str(); }
+extern "C" uint32_t mdh_bam_target_len(const mdh_bam *b, int tid) { return b->hdr.lens[(size_t) tid]; }
+extern "C" int mdh_bam_read_region(mdh_bam *b, int tid, uint32_t beg, uint32_t end, md_reads_soa *out) {
+    try {
+        BamStream s(b->path);
+        Tiler t(s, tid, beg, end, (size_t) -1);
+        SoaTile carry;
+        b->tile.clear();
+        t.next(b->tile, carry);
+        *out = b->tile.view();
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return -1; }
+}
+struct mdh_fasta { std::unique_ptr<Fasta> fa; std::string seq; };
+extern "C" mdh_fasta *mdh_fasta_open(const char *path) {
+    try { mdh_fasta *f = new mdh_fasta(); f->fa.reset(new Fasta(path)); return f; }
+    catch (std::exception &e) { g_err = e.what(); return nullptr; }
+}
+extern "C" void mdh_fasta_close(mdh_fasta *f) { delete f; }
+extern "C" const char *mdh_fasta_fetch(mdh_fasta *f, const char *name, uint32_t *len) {
+    if (!f->fa->fetch(name, f->seq)) { g_err = std::string("sequence not found: ") + name; return nullptr; }
+    *len = (uint32_t) f->seq.size();
+    return f->seq.data();
+}

@@ -1,0 +1,179 @@
+// BAM records -> structure-of-arrays tiles (md_reads_soa, include/mdgpu.h).
+// Replaces, for the B200 path, the record hand-off htslib does inside sam_itr_next /
+// bam_plp_push (common.c:413): the fields filter_func,
+// getStrand, the trims and the overlap code read are laid out column-wise so the
+// device can stream them with coalesced loads.
+#pragma once
+#include "hostio.hpp"
+#include "../../../include/mdgpu.h"
+#include <memory>
+#include <functional>
+
+namespace mdhost {
+
+// Allocation hooks so the CLI can back tiles with pinned (page-locked) memory obtained
+// from the CUDA library while tests use plain malloc.
+struct TileAlloc {
+    void *(*alloc)(size_t) = nullptr;
+    void (*release)(void *) = nullptr;
+};
+
+template <class T> class PodVec {   // minimal growable POD array on a TileAlloc
+public:
+    explicit PodVec(const TileAlloc *a = nullptr) : a_(a) {}
+    ~PodVec() { free_(p_); }
+    PodVec(const PodVec &) = delete;
+    PodVec &operator=(const PodVec &) = delete;
+    size_t size() const { return n_; }
+    T *data() { return p_; }
+    const T *data() const { return p_; }
+    void clear() { n_ = 0; }
+    T &operator[](size_t i) { return p_[i]; }
+    const T &operator[](size_t i) const { return p_[i]; }
+    void reserve(size_t c) {
+        if (c <= cap_) return;
+        size_t nc = std::max(c, cap_ * 2 + 1024);
+        T *q = (T *) alloc_(nc * sizeof(T));
+        if (!q) throw std::bad_alloc();
+        if (n_) memcpy(q, p_, n_ * sizeof(T));
+        free_(p_); p_ = q; cap_ = nc;
+    }
+    void push_back(const T &v) { if (n_ == cap_) reserve(n_ + 1); p_[n_++] = v; }
+    T *grow(size_t k) { reserve(n_ + k); T *r = p_ + n_; n_ += k; return r; }
+private:
+    void *alloc_(size_t b) { return (a_ && a_->alloc) ? a_->alloc(b) : malloc(b); }
+    void free_(void *p) { if (!p) return; if (a_ && a_->release) a_->release(p); else free(p); }
+    const TileAlloc *a_; T *p_ = nullptr; size_t n_ = 0, cap_ = 0;
+};
+
+struct SoaTile {
+    explicit SoaTile(const TileAlloc *a = nullptr)
+        : pos(a), flag(a), mapq(a), aux(a), l_qseq(a), cigar_off(a), seq_off(a), qual_off(a), frag_key(a), cigar(a), seq(a), qual(a), rend(nullptr) {}
+    int32_t tid = -1;
+    uint32_t beg = 0, end = 0;
+    PodVec<int32_t> pos; PodVec<uint16_t> flag; PodVec<uint8_t> mapq, aux; PodVec<uint32_t> l_qseq, cigar_off, seq_off, qual_off;
+    PodVec<uint64_t> frag_key; PodVec<uint32_t> cigar, seq; PodVec<uint64_t> qual;
+    PodVec<int32_t> rend;   // host-only: reference end of each read (for carry-over between tiles)
+    size_t n() const { return pos.size(); }
+    void clear() { pos.clear(); flag.clear(); mapq.clear(); aux.clear(); l_qseq.clear(); cigar_off.clear(); seq_off.clear(); qual_off.clear(); frag_key.clear(); cigar.clear(); seq.clear(); qual.clear(); rend.clear(); }
+    size_t bytes() const { return n() * (4 + 2 + 1 + 1 + 4 + 4 + 4 + 4 + 8) + 4 + cigar.size() * 4 + seq.size() * 4 + qual.size() * 8; }
+
+    void add(const BamRec &r) {
+        pos.push_back(r.pos); flag.push_back(r.flag); mapq.push_back(r.mapq);
+        uint8_t a = 0;
+        // getStrand (common.c:85-87): only the first value byte of XG matters
+        if (const uint8_t *xg = aux_find(r.aux, r.l_aux, 'X', 'G')) { if (xg[1] == 'C') a |= 1; else if (xg[1] == 'G') a |= 2; }
+        // filter_func (common.c:421-427): NH present and > 1
+        if (const uint8_t *nh = aux_find(r.aux, r.l_aux, 'N', 'H')) { if (aux_to_int(nh) > 1) a |= 4; }
+        aux.push_back(a);
+        l_qseq.push_back((uint32_t) r.l_qseq);
+        cigar_off.push_back((uint32_t) cigar.size());
+        int rl = 0;
+        uint32_t *c = cigar.grow(r.n_cigar);
+        for (uint32_t k = 0; k < r.n_cigar; ++k) { c[k] = le32(r.cigar + 4 * k); uint32_t op = c[k] & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rl += (int)(c[k] >> 4); }
+        rend.push_back(r.pos + rl);
+        size_t sb = ((size_t) r.l_qseq + 1) / 2, sw = (sb + 3) / 4, qw = ((size_t) r.l_qseq + 7) / 8;
+        seq_off.push_back((uint32_t) seq.size()); qual_off.push_back((uint32_t) qual.size());
+        uint32_t *s = seq.grow(sw); if (sw) { s[sw - 1] = 0; memcpy(s, r.seq, sb); }
+        uint64_t *q = qual.grow(qw); if (qw) { q[qw - 1] = 0; memcpy(q, r.qual, (size_t) r.l_qseq); }
+        frag_key.push_back(qname_key(r.qname, strnlen(r.qname, r.l_qname)));
+    }
+    // copy read i of another tile (carry-over of reads that straddle a tile boundary)
+    void add_from(const SoaTile &o, size_t i) {
+        pos.push_back(o.pos[i]); flag.push_back(o.flag[i]); mapq.push_back(o.mapq[i]); aux.push_back(o.aux[i]); l_qseq.push_back(o.l_qseq[i]);
+        uint32_t c0 = o.cigar_off[i], c1 = (i + 1 < o.n()) ? o.cigar_off[i + 1] : (uint32_t) o.cigar.size();
+        cigar_off.push_back((uint32_t) cigar.size());
+        uint32_t *c = cigar.grow(c1 - c0); memcpy(c, o.cigar.data() + c0, (c1 - c0) * 4);
+        size_t sw = (((size_t) o.l_qseq[i] + 1) / 2 + 3) / 4, qw = ((size_t) o.l_qseq[i] + 7) / 8;
+        seq_off.push_back((uint32_t) seq.size()); qual_off.push_back((uint32_t) qual.size());
+        uint32_t *s = seq.grow(sw); memcpy(s, o.seq.data() + o.seq_off[i], sw * 4);
+        uint64_t *q = qual.grow(qw); memcpy(q, o.qual.data() + o.qual_off[i], qw * 8);
+        frag_key.push_back(o.frag_key[i]); rend.push_back(o.rend[i]);
+    }
+    // Finalise (cigar_off gets its n+1'th entry) and expose as the C-ABI view.
+    md_reads_soa view() {
+        if (cigar_off.size() == n()) cigar_off.push_back((uint32_t) cigar.size());
+        else cigar_off[n()] = (uint32_t) cigar.size();
+        md_reads_soa v; memset(&v, 0, sizeof v);
+        v.n_reads = (uint32_t) n(); v.n_cigar_ops = (uint32_t) cigar.size(); v.seq_words = seq.size(); v.qual_words = qual.size();
+        v.pos = pos.data(); v.flag = flag.data(); v.mapq = mapq.data(); v.aux = aux.data(); v.l_qseq = l_qseq.data();
+        v.cigar_off = cigar_off.data(); v.seq_off = seq_off.data(); v.qual_off = qual_off.data(); v.frag_key = frag_key.data();
+        v.cigar = cigar.data(); v.seq = seq.data(); v.qual = qual.data();
+        return v;
+    }
+};
+
+// Sequential BAM record source with one-record look-ahead; records come back in file order.
+class BamStream {
+public:
+    explicit BamStream(const std::string &path) : rd_(path) { hdr_ = read_bam_header(rd_); buf_.resize(1 << 16); }
+    const BamHeader &header() const { return hdr_; }
+    void seek(uint64_t voff) { rd_.seek(voff); have_ = false; eof_ = false; }
+    // Look at the next record without consuming it; false at EOF. The view stays valid until pop().
+    bool peek(BamRec &r) {
+        if (!have_) { if (eof_ || !fetch()) { eof_ = true; return false; } have_ = true; }
+        r = cur_;
+        return true;
+    }
+    void pop() { have_ = false; }
+private:
+    bool fetch() {
+        uint8_t b[4];
+        size_t got = rd_.read(b, 4);
+        if (got == 0) return false;
+        if (got != 4) throw std::runtime_error("truncated BAM record");
+        uint32_t bs = le32(b);
+        if (bs > buf_.size()) buf_.resize(bs);
+        if (rd_.read(buf_.data(), bs) != bs) throw std::runtime_error("truncated BAM record");
+        if (!parse_bam_record(buf_.data(), bs, cur_)) throw std::runtime_error("malformed BAM record");
+        return true;
+    }
+    BgzfReader rd_;
+    BamHeader hdr_;
+    std::vector<uint8_t> buf_;
+    BamRec cur_;
+    bool have_ = false, eof_ = false;
+};
+
+// Cuts the coordinate-sorted record stream of ONE contig interval into tiles.
+//   - tile k owns [beg_k, end_k); beg_0 = region start, end_last = region end;
+//   - every record overlapping the owned interval is in the tile, so records that straddle a cut
+//     appear in both neighbours (the reference re-fetches them per chunk the same way, extract.c:379);
+//   - a cut is only placed at the start coordinate of a record, once the tile holds >= target reads.
+class Tiler {
+public:
+    Tiler(BamStream &bs, int tid, uint32_t reg_beg, uint32_t reg_end, size_t target_reads)
+        : bs_(bs), tid_(tid), reg_beg_(reg_beg), reg_end_(reg_end), target_(target_reads), cur_beg_(reg_beg) {}
+    // Fills `t` (cleared first) using `carry` (reads straddling the previous cut; updated for the next call).
+    // Returns false when the interval is exhausted.  Records of earlier contigs are skipped; the first record
+    // of a later contig / beyond the region stays un-consumed in the stream.
+    bool next(SoaTile &t, SoaTile &carry) {
+        if (done_) return false;
+        t.clear(); t.tid = tid_; t.beg = cur_beg_;
+        for (size_t i = 0; i < carry.n(); ++i) if (span_end(carry, i) > cur_beg_) t.add_from(carry, i);
+        carry.clear();
+        uint32_t cut = reg_end_;
+        bool stream_end = false;
+        BamRec r;
+        for (;;) {
+            if (!bs_.peek(r)) { stream_end = true; break; }
+            if (r.tid != tid_) { if (r.tid > tid_ || r.tid < 0) { stream_end = true; break; } bs_.pop(); continue; }
+            if ((uint32_t) r.pos >= reg_end_) { stream_end = true; break; }
+            if (t.n() >= target_ && (uint32_t) r.pos > cur_beg_ && r.pos > last_pos_) { cut = (uint32_t) r.pos; break; }
+            int rl = 0;
+            for (uint32_t k = 0; k < r.n_cigar; ++k) { uint32_t c = le32(r.cigar + 4 * k), op = c & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rl += (int)(c >> 4); }
+            if ((int64_t) r.pos + (rl ? rl : 1) > (int64_t) reg_beg_) { t.add(r); last_pos_ = r.pos; }   // index semantics: endpos > beg
+            bs_.pop();
+        }
+        t.end = cut;
+        if (stream_end) done_ = true;
+        else { for (size_t i = 0; i < t.n(); ++i) if (span_end(t, i) > cut) carry.add_from(t, i); cur_beg_ = cut; }
+        return true;
+    }
+private:
+    static uint32_t span_end(const SoaTile &t, size_t i) { return (uint32_t) std::max(t.rend[i], t.pos[i] + 1); }
+    BamStream &bs_; int tid_; uint32_t reg_beg_, reg_end_; size_t target_;
+    uint32_t cur_beg_; bool done_ = false; int32_t last_pos_ = -1;
+};
+
+}  // namespace mdhost

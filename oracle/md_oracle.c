@@ -1,0 +1,370 @@
+/* TEST INFRASTRUCTURE — see md_oracle.h.  Plain-C restatement of the reference's
+ * extract / mbias counting path on SoA tiles.  Every function cites the reference
+ * lines it follows.  The shape is deliberately simple (whole-tile dense arrays,
+ * sequential loops); it is a checker, not a fast implementation. */
+#include "md_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+/* ---- getStrand, common.c:84-116.  aux bits0-1: XG first value byte ('C' -> 1, 'G' -> 2) ---- */
+int mdo_strand(uint16_t f, uint8_t aux) {
+    int xg = aux & 3;
+    if (xg == 0) {
+        if (f & 1) {
+            if ((f & 0x50) == 0x50) return 2;
+            else if (f & 0x40) return 1;
+            else if ((f & 0x90) == 0x90) return 1;
+            else if (f & 0x80) return 2;
+            return 0;
+        }
+        return (f & 0x10) ? 2 : 1;
+    } else if (xg == 1) {
+        if ((f & 0x51) == 0x41) return 1;
+        else if ((f & 0x51) == 0x51) return 3;
+        else if ((f & 0x91) == 0x81) return 3;
+        else if ((f & 0x91) == 0x91) return 1;
+        else if (f & 0x10) return 3;
+        return 1;
+    } else {
+        if ((f & 0x51) == 0x41) return 4;
+        else if ((f & 0x51) == 0x51) return 2;
+        else if ((f & 0x91) == 0x81) return 2;
+        else if ((f & 0x91) == 0x91) return 4;
+        else if (f & 0x10) return 2;
+        return 4;
+    }
+}
+
+/* ---- filter_func, common.c:416-430 (the tests that only need flag / MAPQ / NH) ---- */
+int mdo_admit(const md_config *c, uint16_t f, uint8_t mapq, uint8_t aux) {
+    if (f & 0x4) return 0;                                             /* :416 */
+    if ((int) mapq < c->minMapq) return 0;                             /* :417 */
+    if (f & c->ignoreFlags) return 0;                                  /* :418 */
+    if (c->requireFlags && (f & c->requireFlags) != c->requireFlags) return 0; /* :419 */
+    if (!c->keepDupes && (f & 0x400)) return 0;                        /* :420 */
+    if (!c->ignoreNH && (aux & 4)) return 0;                           /* :421-427 */
+    if (!c->keepSingleton && (f & 0x9) == 0x9) return 0;               /* :429 */
+    if (!c->keepDiscordant && (f & 0x3) == 0x1) return 0;              /* :430 */
+    return 1;
+}
+
+/* ---- isCpG / isCHG / isCHH, common.c:49-82, chained as extract.c:407-418 does ---- */
+static int is_c(char b) { return b == 'C' || b == 'c'; }
+static int is_g(char b) { return b == 'G' || b == 'g'; }
+int mdo_context(const char *seq, int pos, int seqlen) {
+    if (pos < 0 || pos >= seqlen) return 0;
+    if (is_c(seq[pos])) {
+        if (pos + 1 != seqlen && is_g(seq[pos + 1])) return 1;         /* isCpG :51-54 */
+        if (!(pos + 2 >= seqlen) && is_g(seq[pos + 2])) return 2;      /* isCHG :65-68 */
+        return 3;                                                      /* isCHH :79 */
+    } else if (is_g(seq[pos])) {
+        if (pos != 0 && is_c(seq[pos - 1])) return -1;                 /* isCpG :55-58 */
+        if (!(pos <= 1) && is_c(seq[pos - 2])) return -2;              /* isCHG :69-72 */
+        return -3;                                                     /* isCHH :80 */
+    }
+    return 0;
+}
+
+/* ---- overlaps.c:103,106: `q += 0.2*q` on a uint8_t, i.e. (uint8_t)(q + 0.2*q); the conversion
+ * of an out-of-range double is what x86-64 gcc emits (truncate to int, keep the low byte) ---- */
+uint8_t mdo_boost(uint8_t q) { double v = (double) q + 0.2 * (double) q; return (uint8_t)(int) v; }
+
+static inline uint8_t seq_nib(const md_reads_soa *r, uint32_t i, uint32_t q) {
+    const uint8_t *s = (const uint8_t *)(r->seq + r->seq_off[i]);
+    return (uint8_t)((s[q >> 1] >> ((~q & 1) << 2)) & 0xf);           /* bam_seqi */
+}
+static inline uint8_t qual_at(const md_reads_soa *r, uint32_t i, uint32_t q) {
+    return ((const uint8_t *)(r->qual + r->qual_off[i]))[q];
+}
+
+typedef struct {
+    uint8_t *b, *q;     /* per-base effective base (nibble) / phred of every read, after trims + overlap */
+    uint64_t *off;      /* start of read i in b/q */
+    uint8_t *admit, *strand;
+    int32_t *rend;
+} work_t;
+
+static void free_work(work_t *w) { free(w->b); free(w->q); free(w->off); free(w->admit); free(w->strand); free(w->rend); }
+
+/* filter + strand + trimAlignment (common.c:137-172) + trimAbsoluteAlignment (common.c:174-208) */
+static int build_work(const md_config *c, const md_reads_soa *r, work_t *w, uint32_t *n_adm) {
+    uint32_t n = r->n_reads;
+    memset(w, 0, sizeof *w);
+    w->off = (uint64_t *) malloc(((size_t) n + 1) * sizeof(uint64_t));
+    w->admit = (uint8_t *) calloc((size_t) n + 1, 1);
+    w->strand = (uint8_t *) calloc((size_t) n + 1, 1);
+    w->rend = (int32_t *) calloc((size_t) n + 1, sizeof(int32_t));
+    uint64_t tot = 0;
+    for (uint32_t i = 0; i < n; ++i) { w->off[i] = tot; tot += r->l_qseq[i]; }
+    w->off[n] = tot;
+    w->b = (uint8_t *) malloc(tot + 1); w->q = (uint8_t *) malloc(tot + 1);
+    if (!w->off || !w->admit || !w->strand || !w->rend || !w->b || !w->q) return -1;
+    *n_adm = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        int rl = 0; uint32_t qlen = 0;
+        for (uint32_t k = r->cigar_off[i]; k < r->cigar_off[i + 1]; ++k) {
+            uint32_t op = r->cigar[k] & 15, len = r->cigar[k] >> 4;
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rl += (int) len;
+            if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) qlen += len;
+        }
+        w->rend[i] = r->pos[i] + rl;
+        int s = mdo_strand(r->flag[i], r->aux[i]);
+        w->strand[i] = (uint8_t) s;
+        /* a record whose CIGAR does not describe its SEQ, with no reference span, or with an
+         * undeterminable strand (the reference asserts, common.c:122-125) cannot be piled up */
+        int ok = mdo_admit(c, r->flag[i], r->mapq[i], r->aux[i]) && s != 0 && rl > 0 && qlen == r->l_qseq[i] && r->l_qseq[i] > 0;
+        w->admit[i] = (uint8_t) ok;
+        if (!ok) continue;
+        ++*n_adm;
+        int l = (int) r->l_qseq[i];
+        uint8_t *b = w->b + w->off[i], *q = w->q + w->off[i];
+        for (int j = 0; j < l; ++j) { b[j] = seq_nib(r, i, (uint32_t) j); q[j] = qual_at(r, i, (uint32_t) j); }
+        int base = 4 * (s - 1) + ((r->flag[i] & 0x80) ? 2 : 0);
+        int lb = c->bounds[base], rb = c->bounds[base + 1];
+        if (lb > l) lb = l;                                            /* common.c:151 */
+        for (int j = 0; j < lb; ++j) { q[j] = 0; b[j] = 15; }          /* :154-160 */
+        if (rb) for (int j = rb; j < l; ++j) { q[j] = 0; b[j] = 15; }  /* :163-169 */
+        lb = c->absoluteBounds[base]; rb = c->absoluteBounds[base + 1];
+        if (lb > l) lb = l;
+        if (rb > l) rb = l;                                            /* :188-189 */
+        for (int j = 0; j < lb; ++j) { q[j] = 0; b[j] = 15; }
+        for (int j = 0; j < rb; ++j) { q[l - 1 - j] = 0; b[l - 1 - j] = 15; } /* :199-205 */
+    }
+    return 0;
+}
+
+/* calculate_positions, overlaps.c:27-52 */
+static int32_t *calc_positions(const md_reads_soa *r, uint32_t i) {
+    int32_t *p = (int32_t *) malloc(sizeof(int32_t) * ((size_t) r->l_qseq[i] + 1));
+    int off = 0; int32_t prev = r->pos[i];
+    for (uint32_t k = r->cigar_off[i]; k < r->cigar_off[i + 1]; ++k) {
+        uint32_t op = r->cigar[k] & 15, len = r->cigar[k] >> 4;
+        for (uint32_t j = 0; j < len; ++j) {
+            if (op == 0 || op == 7 || op == 8) p[off++] = prev++;
+            else if (op == 1 || op == 4) p[off++] = -1;
+            else if (op == 2 || op == 3) prev++;
+        }
+    }
+    return p;
+}
+
+/* cust_tweak_overlap_quality, overlaps.c:54-119 (a = first in file order) */
+static void tweak(const md_reads_soa *r, work_t *w, uint32_t a, uint32_t b) {
+    int sa = w->strand[a], sb = w->strand[b];
+    if (((sa - sb) & 1) == 1) return;                                  /* :65 */
+    int na = (int) r->l_qseq[a], nb = (int) r->l_qseq[b], ia = 0, ib = 0;
+    int32_t *pa = calc_positions(r, a), *pb = calc_positions(r, b);
+    uint8_t *aq = w->q + w->off[a], *bq = w->q + w->off[b], *as = w->b + w->off[a], *bs = w->b + w->off[b];
+    while (ia < na && pa[ia] < 0) ia++;
+    while (ib < nb && pb[ib] < 0) ib++;
+    if (ia == na || ib == nb) goto quit;
+    if (pa[ia] < pb[ib]) { while (ia < na && pa[ia] < pb[ib]) ia++; }
+    else { while (ib < nb && pb[ib] < pa[ia]) ib++; }
+    if (ia == na || ib == nb) goto quit;
+    while (ia < na && ib < nb) {
+        if (pa[ia] < pb[ib] || pa[ia] < 0) { ia++; continue; }
+        if (pb[ib] < pa[ia] || pb[ib] < 0) { ib++; continue; }
+        if (as[ia] != bs[ib]) {
+            if (aq[ia] > bq[ib] && as[ia] != 15) { aq[ia] = (uint8_t)(aq[ia] - bq[ib]); bq[ib] = 0; }
+            else if (bq[ib] > aq[ia] && bs[ib] != 15) { bq[ib] = (uint8_t)(bq[ib] - aq[ia]); aq[ia] = 0; }
+            else { aq[ia] = 0; bq[ib] = 0; }
+        } else {
+            if (aq[ia] > bq[ib]) { aq[ia] = mdo_boost(aq[ia]); bq[ib] = 0; }
+            else { bq[ib] = mdo_boost(bq[ib]); aq[ia] = 0; }
+        }
+        ia++; ib++;
+    }
+quit:
+    free(pa); free(pb);
+}
+
+/* Emulation of the qname hash traffic generated by the pileup engine around
+ * custom_overlap_constructor / custom_overlap_destructor (overlaps.c:121-147):
+ *  - records are pushed in file order; an eligible record (paired, !(flag&12), :128) either
+ *    stores itself under its name or, if the name is present, is merged with the stored
+ *    record and the name is removed (:129-136);
+ *  - a buffered record is dropped — destructor, which removes whatever is stored under that
+ *    record's name (:141-147) — once a record starting beyond its end has been pushed.
+ * Keys are the 64-bit name fingerprints of the tile. */
+typedef struct { uint64_t key; uint32_t idx; uint8_t live; } slot_t;
+typedef struct { slot_t *s; uint32_t cap; } map_t;
+static uint32_t map_find(const map_t *m, uint64_t key) {
+    uint32_t mask = m->cap - 1, i = (uint32_t)(key * 0x9e3779b97f4a7c15ull >> 40) & mask;
+    while (m->s[i].live) { if (m->s[i].live == 1 && m->s[i].key == key) return i; i = (i + 1) & mask; }
+    return m->cap;
+}
+static void map_put(map_t *m, uint64_t key, uint32_t idx) {
+    uint32_t mask = m->cap - 1, i = (uint32_t)(key * 0x9e3779b97f4a7c15ull >> 40) & mask;
+    while (m->s[i].live == 1) i = (i + 1) & mask;   /* reuse tombstones (live==2) */
+    m->s[i].key = key; m->s[i].idx = idx; m->s[i].live = 1;
+}
+
+static int cmp_end(const void *a, const void *b) {
+    const int64_t x = *(const int64_t *) a, y = *(const int64_t *) b;
+    return (x > y) - (x < y);
+}
+
+static int pair_and_merge(const md_reads_soa *r, work_t *w, uint32_t *n_pairs, uint32_t *n_multi) {
+    uint32_t n = r->n_reads, cap = 16;
+    while (cap < 4 * (n + 1)) cap <<= 1;
+    map_t m; m.cap = cap; m.s = (slot_t *) calloc(cap, sizeof(slot_t));
+    /* eviction order: by reference end; (end<<32 | idx) sorted ascending */
+    int64_t *ev = (int64_t *) malloc(sizeof(int64_t) * ((size_t) n + 1));
+    uint32_t *occ = (uint32_t *) calloc(cap, sizeof(uint32_t));   /* name multiplicity, for stats only */
+    if (!m.s || !ev || !occ) return -1;
+    uint32_t nev = 0;
+    for (uint32_t i = 0; i < n; ++i) if (w->admit[i]) ev[nev++] = ((int64_t) w->rend[i] << 32) | i;
+    qsort(ev, nev, sizeof(int64_t), cmp_end);
+    uint32_t evp = 0;
+    *n_pairs = 0; *n_multi = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (!w->admit[i]) continue;
+        /* constructor */
+        uint16_t f = r->flag[i];
+        if ((f & 1) && !(f & 12)) {
+            uint32_t k = map_find(&m, r->frag_key[i]);
+            if (k == m.cap) map_put(&m, r->frag_key[i], i);
+            else { tweak(r, w, m.s[k].idx, i); m.s[k].live = 2; ++*n_pairs; }
+        }
+        /* this push lets the engine build every column < pos[i]; records ending at or before such a
+         * column are dropped: end <= pos[i]-1  <=>  end < pos[i] */
+        while (evp < nev && (int32_t)(ev[evp] >> 32) < r->pos[i]) {
+            uint32_t x = (uint32_t)(ev[evp] & 0xffffffff);
+            if (x < i) { uint32_t k = map_find(&m, r->frag_key[x]); if (k != m.cap) m.s[k].live = 2; }
+            ++evp;
+        }
+    }
+    /* stats: names seen more than twice among eligible admitted records */
+    {
+        uint32_t mask = cap - 1;
+        uint64_t *keys = (uint64_t *) calloc(cap, sizeof(uint64_t));
+        if (keys) {
+            for (uint32_t i = 0; i < n; ++i) {
+                if (!w->admit[i] || !(r->flag[i] & 1) || (r->flag[i] & 12)) continue;
+                uint64_t key = r->frag_key[i]; uint32_t j = (uint32_t)(key * 0x9e3779b97f4a7c15ull >> 40) & mask;
+                while (occ[j] && keys[j] != key) j = (j + 1) & mask;
+                keys[j] = key; occ[j]++;
+            }
+            for (uint32_t j = 0; j < cap; ++j) if (occ[j] > 2) *n_multi += occ[j];
+            free(keys);
+        }
+    }
+    free(m.s); free(ev); free(occ);
+    return 0;
+}
+
+int mdo_extract_tile(const md_config *c, const char *ref, uint32_t reflen, uint32_t beg, uint32_t end,
+                     const md_reads_soa *r, md_call *out, uint64_t cap, md_tile_stats *st) {
+    work_t w; uint32_t n_adm = 0, n_pairs = 0, n_multi = 0;
+    if (end > reflen) end = reflen;
+    if (beg > end) beg = end;
+    if (build_work(c, r, &w, &n_adm) < 0) { free_work(&w); return -2; }
+    if (!c->noOverlapMerge && pair_and_merge(r, &w, &n_pairs, &n_multi) < 0) { free_work(&w); return -2; }
+    size_t span = (size_t)(end - beg);
+    uint32_t *nm = (uint32_t *) calloc(span + 1, 4), *nu = (uint32_t *) calloc(span + 1, 4), *noff = (uint32_t *) calloc(span + 1, 4), *nvar = (uint32_t *) calloc(span + 1, 4);
+    if (!nm || !nu || !noff || !nvar) { free(nm); free(nu); free(noff); free(nvar); free_work(&w); return -2; }
+    /* the per-column loop of extract.c:420-441, regrouped per alignment */
+    for (uint32_t i = 0; i < r->n_reads; ++i) {
+        if (!w.admit[i]) continue;
+        int s = w.strand[i];
+        const uint8_t *b = w.b + w.off[i], *q = w.q + w.off[i];
+        int64_t p = r->pos[i]; uint32_t qi = 0;
+        for (uint32_t k = r->cigar_off[i]; k < r->cigar_off[i + 1]; ++k) {
+            uint32_t op = r->cigar[k] & 15, len = r->cigar[k] >> 4;
+            if (op == 0 || op == 7 || op == 8) {
+                for (uint32_t j = 0; j < len; ++j, ++p, ++qi) {
+                    if (p < (int64_t) beg || p >= (int64_t) end) continue;             /* extract.c:400 */
+                    char rb = ref[p];
+                    int ctx = mdo_context(ref, (int) p, (int) reflen);               /* extract.c:407-418 */
+                    if (ctx == 0) continue;
+                    int type = (ctx < 0 ? -ctx : ctx) - 1;
+                    if ((type == 0 && !c->keepCpG) || (type == 1 && !c->keepCHG) || (type == 2 && !c->keepCHH)) continue;
+                    size_t o = (size_t)(p - beg);
+                    if ((s & 1) ? !is_c(rb) : !is_g(rb)) {                              /* extract.c:427-437 */
+                        if ((int) q[qi] < c->minPhred) continue;                       /* isVariant, extract.c:229 */
+                        noff[o]++;
+                        if (s & 1) { if (b[qi] != 4 && b[qi] != 15) nvar[o]++; }        /* :232-234 */
+                        else { if (b[qi] != 2 && b[qi] != 15) nvar[o]++; }            /* :235-237 */
+                        continue;
+                    }
+                    if ((int) q[qi] < c->minPhred) continue;                           /* updateMetrics, common.c:127 */
+                    if (s & 1) { if (b[qi] == 2) nm[o]++; else if (b[qi] == 8) nu[o]++; } /* :129-130 */
+                    else { if (b[qi] == 4) nm[o]++; else if (b[qi] == 1) nu[o]++; }       /* :131-132 */
+                }
+            } else if (op == 1 || op == 4) qi += len;
+            else if (op == 2 || op == 3) p += len;                                     /* is_del / is_refskip columns: extract.c:423-424 */
+        }
+    }
+    uint64_t k = 0, need = 0;
+    for (size_t o = 0; o < span; ++o) {
+        int excluded = 0;
+        if (c->minOppositeDepth > 0 && noff[o] >= (uint32_t) c->minOppositeDepth &&
+            ((double) nvar[o]) / ((double) noff[o]) >= c->maxVariantFrac) excluded = 1;      /* extract.c:444-446 */
+        if (!excluded && nm[o] + nu[o] == 0) continue;                                      /* extract.c:461 */
+        if (excluded) {
+            /* a column only reaches the variant test if it is a kept context (extract.c:407-418) */
+            int ctx0 = mdo_context(ref, (int)(beg + o), (int) reflen);
+            int t0 = (ctx0 < 0 ? -ctx0 : ctx0) - 1;
+            if (ctx0 == 0 || (t0 == 0 && !c->keepCpG) || (t0 == 1 && !c->keepCHG) || (t0 == 2 && !c->keepCHH)) continue;
+        }
+        int ctx = mdo_context(ref, (int)(beg + o), (int) reflen);
+        ++need;
+        if (k < cap) {
+            out[k].pos = beg + (uint32_t) o; out[k].nmeth = nm[o]; out[k].nunmeth = nu[o];
+            out[k].info = (uint32_t)((ctx < 0 ? -ctx : ctx) - 1) | (ctx < 0 ? 4u : 0u) | (excluded ? 8u : 0u);
+            ++k;
+        }
+    }
+    if (st) { memset(st, 0, sizeof *st); st->n_calls = k; st->n_required = need; st->n_admitted = n_adm; st->n_pairs = n_pairs; st->n_multi = n_multi; }
+    free(nm); free(nu); free(noff); free(nvar); free_work(&w);
+    return need > cap ? -1 : 0;
+}
+
+int mdo_mbias_tile(const md_config *c, const char *ref, uint32_t reflen, uint32_t beg, uint32_t end,
+                   const uint32_t *bounds, uint32_t n_chunks,
+                   const md_reads_soa *r, uint32_t *hist, int32_t lens[4], md_tile_stats *st) {
+    work_t w; uint32_t n_adm = 0;
+    if (end > reflen) end = reflen;
+    if (build_work(c, r, &w, &n_adm) < 0) { free_work(&w); return -2; }
+    for (uint32_t i = 0; i < r->n_reads; ++i) {
+        if (!w.admit[i]) continue;
+        int s = w.strand[i];
+        int rd2 = (r->flag[i] & 0x80) ? 1 : 0;
+        const uint8_t *b = w.b + w.off[i], *q = w.q + w.off[i];
+        int64_t p = r->pos[i]; uint32_t qi = 0;
+        for (uint32_t k = r->cigar_off[i]; k < r->cigar_off[i + 1]; ++k) {
+            uint32_t op = r->cigar[k] & 15, len = r->cigar[k] >> 4;
+            if (op == 0 || op == 7 || op == 8) {
+                for (uint32_t j = 0; j < len; ++j, ++p, ++qi) {
+                    if (p < (int64_t) beg || p >= (int64_t) end) continue;             /* MBias.c:163 */
+                    /* chunk window contig[localPos..localEnd] (MBias.c:147): find the chunk that owns p */
+                    uint32_t lo = 0, hi = n_chunks;
+                    while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if (bounds[mid] <= (uint32_t) p) lo = mid; else hi = mid; }
+                    if (n_chunks == 0 || (uint32_t) p < bounds[lo] || (uint32_t) p >= bounds[lo + 1]) continue;
+                    uint32_t cs = bounds[lo], ce = bounds[lo + 1];
+                    uint32_t last = ce < reflen ? ce : reflen - 1;                      /* end-inclusive fetch, clamped */
+                    int seqlen = (int)(last - cs + 1);
+                    int ctx = mdo_context(ref + cs, (int)((uint32_t) p - cs), seqlen);  /* MBias.c:170-178 */
+                    if (ctx == 0) continue;
+                    int type = (ctx < 0 ? -ctx : ctx) - 1;
+                    if ((type == 0 && !c->keepCpG) || (type == 1 && !c->keepCHG) || (type == 2 && !c->keepCHH)) continue;
+                    char rb = ref[p];
+                    if ((s & 1) ? !is_c(rb) : !is_g(rb)) continue;                     /* MBias.c:186-190 */
+                    if ((int) q[qi] < c->minPhred) continue;
+                    int rv = 0;
+                    if (s & 1) { if (b[qi] == 2) rv = 1; else if (b[qi] == 8) rv = -1; }
+                    else { if (b[qi] == 4) rv = 1; else if (b[qi] == 1) rv = -1; }
+                    if (rv == 0) continue;
+                    if (qi >= MD_MBIAS_MAXLEN) continue;                               /* beyond the fixed histogram; counted by neither side */
+                    hist[(((size_t)(s - 1) * 2 + rd2) * MD_MBIAS_MAXLEN + qi) * 2 + (rv < 0 ? 1 : 0)]++; /* MBias.c:195-211 */
+                    if ((int32_t) qi + 1 > lens[s - 1]) lens[s - 1] = (int32_t) qi + 1;  /* MBias.c:212 */
+                }
+            } else if (op == 1 || op == 4) qi += len;
+            else if (op == 2 || op == 3) p += len;
+        }
+    }
+    if (st) { memset(st, 0, sizeof *st); st->n_admitted = n_adm; }
+    free_work(&w);
+    return 0;
+}

@@ -1,0 +1,91 @@
+"""TEST-ONLY glue: ctypes binding of oracle/libmdoracle.so (the CPU restatement) and an
+``mdh_backend`` that routes tiles to it, so the HOST logic of the product (option parsing, BAM
+decode, tiling, chunk replay, formatting) can be checked on a CPU box against oracle/_ref.
+Nothing under methyldackel_b200/ imports this."""
+import ctypes as C
+import os
+
+from methyldackel_b200 import _abi as A
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        o = C.CDLL(os.path.join(ROOT, "oracle", "libmdoracle.so"))
+        o.mdo_extract_tile.argtypes = [C.POINTER(A.MdConfig), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(A.MdReadsSoa),
+                                       C.POINTER(A.MdCall), C.c_uint64, C.POINTER(A.MdTileStats)]
+        o.mdo_mbias_tile.argtypes = [C.POINTER(A.MdConfig), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32,
+                                     C.POINTER(A.MdReadsSoa), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(A.MdTileStats)]
+        o.mdo_strand.argtypes = [C.c_uint16, C.c_uint8]
+        o.mdo_admit.argtypes = [C.POINTER(A.MdConfig), C.c_uint16, C.c_uint8, C.c_uint8]
+        o.mdo_context.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        o.mdo_boost.argtypes = [C.c_uint8]; o.mdo_boost.restype = C.c_uint8
+        _lib = o
+    return _lib
+
+
+class OracleBackend:
+    """mdh_backend whose slots call the oracle port. Keeps the callbacks alive."""
+
+    def __init__(self):
+        o = lib()
+        self.state = {}
+        st = self.state
+
+        def create(_u, cfg):
+            st["cfg"] = A.MdConfig.from_buffer_copy(cfg.contents)
+            st["contigs"] = {}
+            st["chunks"] = {}
+            st["hist"] = (C.c_uint32 * (4 * 2 * A.MD_MBIAS_MAXLEN * 2))()
+            st["lens"] = (C.c_int32 * 4)()
+            return 1
+
+        def destroy(_b):
+            return None
+
+        def load_contig(_b, tid, seq, n):
+            st["contigs"][tid] = (C.string_at(seq, n), n)
+            return 0
+
+        def drop_contig(_b, tid):
+            st["contigs"].pop(tid, None)
+            return 0
+
+        def extract_tile(_b, td, reads, calls, cap, stats):
+            seq, n = st["contigs"][td.contents.tid]
+            return o.mdo_extract_tile(C.byref(st["cfg"]), seq, n, td.contents.beg, td.contents.end, reads, calls, cap, stats)
+
+        def set_chunks(_b, tid, bounds, n):
+            st["chunks"][tid] = (C.c_uint32 * (n + 1))(*[bounds[i] for i in range(n + 1)])
+            return 0
+
+        def mbias_tile(_b, td, reads, stats):
+            seq, n = st["contigs"][td.contents.tid]
+            b = st["chunks"][td.contents.tid]
+            return o.mdo_mbias_tile(C.byref(st["cfg"]), seq, n, td.contents.beg, td.contents.end, b, len(b) - 1, reads, st["hist"], st["lens"], stats)
+
+        def mbias_hist(_b, hist, lens):
+            C.memmove(hist, st["hist"], C.sizeof(st["hist"]))
+            for i in range(4):
+                lens[i] = st["lens"][i]
+            return 0
+
+        def last_error():
+            return b"oracle backend"
+
+        self._keep = [A.CREATE_FN(create), A.DESTROY_FN(destroy), A.LOAD_CONTIG_FN(load_contig), A.DROP_CONTIG_FN(drop_contig),
+                      A.EXTRACT_TILE_FN(extract_tile), A.SET_CHUNKS_FN(set_chunks), A.MBIAS_TILE_FN(mbias_tile), A.MBIAS_HIST_FN(mbias_hist),
+                      A.LAST_ERROR_FN(last_error)]
+        self.be = A.MdhBackend(None, *self._keep)
+
+
+def run_host_main(which, argv, backend):
+    """Calls mdh_extract_main / mdh_mbias_main (argv[0] = sub-command name) with the given backend."""
+    h = A.load_host()
+    args = [which.encode()] + [a.encode() if isinstance(a, str) else a for a in argv]
+    arr = (C.c_char_p * (len(args) + 1))(*args, None)
+    fn = h.mdh_extract_main if which == "extract" else h.mdh_mbias_main
+    return fn(len(args), arr, C.byref(backend.be))
