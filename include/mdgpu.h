@@ -154,6 +154,11 @@ uint64_t md_launch_count(md_ctx *ctx);
 /* CUDA stream handle (cudaStream_t) the kernels are launched on. */
 void *md_stream(md_ctx *ctx);
 
+/* Page-lock / unlock a host buffer so md_extract_tile's copies run asynchronously at full PCIe rate
+ * (cudaHostRegister); optional. */
+int md_host_register(void *p, size_t bytes);
+int md_host_unregister(void *p);
+
 const char *md_last_error(void);
 int md_abi_version(void);
 

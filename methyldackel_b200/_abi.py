@@ -140,6 +140,8 @@ def load_gpu():
         g.md_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         g.md_launch_count.restype = C.c_uint64; g.md_launch_count.argtypes = [C.c_void_p]
         g.md_stream.restype = C.c_void_p; g.md_stream.argtypes = [C.c_void_p]
+        g.md_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        g.md_host_unregister.argtypes = [C.c_void_p]
         g.md_last_error.restype = C.c_char_p
         g.md_abi_version.restype = C.c_int
         _gpu = g

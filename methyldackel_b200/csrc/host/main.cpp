@@ -1,0 +1,35 @@
+// `MethylDackel` drop-in binary for the B200 path: same dispatcher surface as main.c:39-62 for the
+// two sub-commands this build accelerates.  The device back end is libmdgpu and nothing else;
+// if no CUDA device is usable the program fails with an error instead of computing on the CPU.
+#include <cstdio>
+#include <cstring>
+#include "../../../include/mdhost.h"
+
+static void *be_create(void *, const md_config *cfg) { return md_create(cfg, 0); }
+static void be_destroy(void *b) { md_destroy((md_ctx *) b); }
+static int be_load(void *b, int32_t tid, const char *s, uint32_t n) { return md_load_contig((md_ctx *) b, tid, s, n); }
+static int be_drop(void *b, int32_t tid) { return md_drop_contig((md_ctx *) b, tid); }
+static int be_extract(void *b, const md_tile_desc *t, const md_reads_soa *r, md_call *c, uint64_t cap, md_tile_stats *st) { return md_extract_tile((md_ctx *) b, t, r, c, cap, st); }
+static int be_chunks(void *b, int32_t tid, const uint32_t *bo, uint32_t n) { return md_set_mbias_chunks((md_ctx *) b, tid, bo, n); }
+static int be_mbias(void *b, const md_tile_desc *t, const md_reads_soa *r, md_tile_stats *st) { return md_mbias_tile((md_ctx *) b, t, r, st); }
+static int be_hist(void *b, uint32_t *h, int32_t l[4]) { return md_mbias_hist((md_ctx *) b, h, l); }
+
+static void usage_main() {
+    fprintf(stderr, "MethylDackel (B200 build of the extract/mbias hot path): A tool for processing bisulfite sequencing alignments.\n"
+                    "Usage: MethylDackel <command> [options]\n\nCommands:\n"
+                    "    mbias    Determine the position-dependent methylation bias in a dataset.\n"
+                    "    extract  Extract methylation metrics from an alignment file in BAM format.\n"
+                    "(mergeContext and perRead are not part of this build.)\n");
+}
+
+int main(int argc, char *argv[]) {
+    mdh_backend be = {nullptr, be_create, be_destroy, be_load, be_drop, be_extract, be_chunks, be_mbias, be_hist, md_last_error};
+    if (argc == 1) { usage_main(); return 0; }
+    if (!strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) { usage_main(); return 0; }
+    if (!strcmp(argv[1], "-v") || !strcmp(argv[1], "--version")) { printf("0.6.1-b200 (B200 build; no HTSlib)\n"); return 0; }
+    if (!strcmp(argv[1], "extract")) return mdh_extract_main(argc - 1, argv + 1, &be);
+    if (!strcmp(argv[1], "mbias")) return mdh_mbias_main(argc - 1, argv + 1, &be);
+    if (!strcmp(argv[1], "mergeContext") || !strcmp(argv[1], "perRead")) { fprintf(stderr, "The %s sub-command is not part of the B200 build.\n", argv[1]); return -1; }
+    fprintf(stderr, "Unknown command!\n"); usage_main();
+    return -1;
+}

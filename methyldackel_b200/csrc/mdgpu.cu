@@ -1,0 +1,772 @@
+// libmdgpu — hand-written CUDA (sm_100a) implementation of the MethylDackel extract / mbias
+// pileup hot path behind the C ABI of include/mdgpu.h.
+//
+// The reference walks a pileup: for every covered reference column it resolves the CIGAR of every
+// buffered read (htslib bam_plp, driven from extract.c:399) and then classifies read bases
+// (extract.c:420-441).  That is column-major and serial.  Here the work is read-major inside
+// position-owned windows:
+//
+//   K1 prep_kernel    one thread per alignment: filter_func's admission tests (common.c:416-430),
+//                     getStrand (common.c:84-116), reference span, and — for the mate-overlap merge —
+//                     insertion of the read's 64-bit name key into an open-addressing table in HBM
+//                     (replaces the khash of overlaps.c:121-139).
+//   K2 pair_kernel    one thread per alignment: reads its table slot; a key seen exactly twice is a
+//                     mate pair (first in file order = `a`, overlaps.c:129-135).
+//   K3 window_kernel  per window of W reference positions: the range of alignments that can touch it.
+//   K4 count_kernel   one CTA per window: stages the reference window in shared memory, classifies
+//                     every position (isCpG/isCHG/isCHH, common.c:49-82), then warps stream the
+//                     window's alignments, expand CIGARs to reference coordinates, apply the trims
+//                     (common.c:137-208), the overlap phred merge lazily at the bases that matter
+//                     (overlaps.c:54-119), updateMetrics / isVariant (common.c:118-134,
+//                     extract.c:225-239) and accumulate into privatised shared-memory histograms;
+//                     the epilogue applies the variant-site test (extract.c:444-446), drops empty
+//                     columns (extract.c:461) and appends compact md_call records to HBM.
+//                     The mbias flavour (MBias.c:181-214) accumulates a per-(strand,read,qpos)
+//                     histogram instead.
+//
+// Integer / byte work, HBM-bound by design: no tensor cores, no GEMM reshaping.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/mdgpu.h"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+static thread_local std::string g_err;
+static void set_err(const char *what, cudaError_t e) { g_err = std::string(what) + ": " + cudaGetErrorString(e); }
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(#call, e_); return -100; } } while (0)
+#define CKN(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(#call, e_); return nullptr; } } while (0)
+extern "C" const char *md_last_error(void) { return g_err.c_str(); }
+extern "C" int md_abi_version(void) { return MDGPU_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------------
+// device-side views
+struct DevReads {
+    uint32_t n;
+    const int32_t *pos; const uint16_t *flag; const uint8_t *mapq; const uint8_t *aux; const uint32_t *l_qseq;
+    const uint32_t *cigar_off, *seq_off, *qual_off; const uint64_t *frag_key;
+    const uint32_t *cigar, *seq; const uint64_t *qual;
+};
+
+struct KParams {
+    int minMapq, minPhred, keepDupes, keepSingleton, keepDiscordant, ignoreFlags, requireFlags, ignoreNH;
+    int keepMask;              // bit0 CpG, bit1 CHG, bit2 CHH
+    int minOppositeDepth; double maxVariantFrac;
+    int bounds[16], abounds[16];
+    int noOverlap;
+    unsigned char boost[256];  // (uint8_t)(q + 0.2*q), overlaps.c:103,106, tabulated on the host in double
+};
+
+// info byte per read: bits0-2 strand (1..4), bit3 admitted, bit4 pair-eligible
+#define INFO_STRAND(x) ((x) & 7)
+#define INFO_ADMIT 8
+#define INFO_ELIG 16
+
+struct HashTab { unsigned long long *keys; uint32_t *cnt; uint32_t *idx; uint32_t mask; };
+
+// counters[]: 0 n_admitted, 1 max reference span, 2 n_pairs(x2), 3 n_multi, 4 n_calls (append cursor), 5 overflow flag
+enum { C_ADMIT = 0, C_MAXSPAN = 1, C_PAIRED = 2, C_MULTI = 3, C_NCALLS = 4 /* 64-bit: slots 4,5 */, C_OVERFLOW = 6, C_N = 8 };
+
+// ------------------------------------------------------------------------------------------------
+// per-read primitives
+__device__ __forceinline__ int dev_strand(unsigned f, unsigned aux) {   // getStrand, common.c:84-116
+    unsigned xg = aux & 3u;
+    if (xg == 0) {
+        if (f & 1u) {
+            if ((f & 0x50u) == 0x50u) return 2;
+            if (f & 0x40u) return 1;
+            if ((f & 0x90u) == 0x90u) return 1;
+            if (f & 0x80u) return 2;
+            return 0;
+        }
+        return (f & 0x10u) ? 2 : 1;
+    }
+    int fwd1 = (f & 0x51u) == 0x41u, rev1 = (f & 0x51u) == 0x51u, fwd2 = (f & 0x91u) == 0x81u, rev2 = (f & 0x91u) == 0x91u;
+    if (xg == 1) { if (fwd1) return 1; if (rev1) return 3; if (fwd2) return 3; if (rev2) return 1; return (f & 0x10u) ? 3 : 1; }
+    if (fwd1) return 4; if (rev1) return 2; if (fwd2) return 2; if (rev2) return 4; return (f & 0x10u) ? 2 : 4;
+}
+
+__device__ __forceinline__ bool dev_admit(const KParams &P, unsigned f, unsigned mapq, unsigned aux) {   // common.c:416-430
+    if (f & 0x4u) return false;
+    if ((int) mapq < P.minMapq) return false;
+    if (f & (unsigned) P.ignoreFlags) return false;
+    if (P.requireFlags && (f & (unsigned) P.requireFlags) != (unsigned) P.requireFlags) return false;
+    if (!P.keepDupes && (f & 0x400u)) return false;
+    if (!P.ignoreNH && (aux & 4u)) return false;
+    if (!P.keepSingleton && (f & 0x9u) == 0x9u) return false;
+    if (!P.keepDiscordant && (f & 0x3u) == 0x1u) return false;
+    return true;
+}
+
+// kept query range [lo,hi) after trimAlignment + trimAbsoluteAlignment (common.c:137-208);
+// bases outside read as N with phred 0.
+__device__ __forceinline__ void dev_trim(const KParams &P, int strand, unsigned f, int l, int &lo, int &hi) {
+    int b = 4 * (strand - 1) + ((f & 0x80u) ? 2 : 0);
+    int lb = min(P.bounds[b], l), rb = P.bounds[b + 1];
+    lo = lb; hi = rb ? min(rb, l) : l;
+    int alb = min(P.abounds[b], l), arb = min(P.abounds[b + 1], l);
+    lo = max(lo, alb); hi = min(hi, l - arb);
+}
+
+__device__ __forceinline__ unsigned dev_base(const uint32_t *seq, uint32_t off, int q) {   // bam_seqi on word-packed bytes
+    uint32_t w = __ldg(seq + off + (q >> 3));
+    unsigned byte = (w >> (((q >> 1) & 3) << 3)) & 0xffu;
+    return (q & 1) ? (byte & 0xfu) : (byte >> 4);
+}
+__device__ __forceinline__ unsigned dev_qual(const uint64_t *qual, uint32_t off, int q) {
+    const unsigned char *p = (const unsigned char *) (qual + off);
+    return __ldg(p + q);
+}
+
+__device__ __forceinline__ uint32_t hash_slot(unsigned long long key, uint32_t mask) {
+    return (uint32_t)((key * 0x9e3779b97f4a7c15ull) >> 32) & mask;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1
+__global__ void __launch_bounds__(256) prep_kernel(DevReads R, KParams P, int32_t *rend, uint8_t *info, HashTab T, uint32_t *slot_of, uint32_t *counters) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false; int rl = 0;
+    if (i < R.n) {
+        unsigned f = R.flag[i], a = R.aux[i];
+        int strand = dev_strand(f, a);
+        uint32_t ql = 0;
+        for (uint32_t k = R.cigar_off[i], ke = R.cigar_off[i + 1]; k < ke; ++k) {
+            uint32_t c = __ldg(R.cigar + k), op = c & 15u, len = c >> 4;
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rl += (int) len;
+            if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) ql += len;
+        }
+        uint32_t lq = R.l_qseq[i];
+        ok = dev_admit(P, f, R.mapq[i], a) && strand != 0 && rl > 0 && ql == lq && lq > 0;
+        bool elig = ok && (f & 1u) && !(f & 12u) && !P.noOverlap;          // overlaps.c:128
+        rend[i] = R.pos[i] + rl;
+        info[i] = (uint8_t)(strand | (ok ? INFO_ADMIT : 0) | (elig ? INFO_ELIG : 0));
+        uint32_t slot = 0xffffffffu;
+        if (elig) {
+            unsigned long long key = R.frag_key[i];
+            if (key == 0ull) key = 0x9e3779b97f4a7c15ull;           // 0 marks an empty slot
+            uint32_t h = hash_slot(key, T.mask);
+            for (uint32_t probe = 0; probe <= T.mask; ++probe) {
+                unsigned long long prev = atomicCAS(T.keys + h, 0ull, key);
+                if (prev == 0ull || prev == key) {
+                    uint32_t c = atomicAdd(T.cnt + h, 1u);
+                    if (c < 2) T.idx[2 * h + c] = i;
+                    slot = h;
+                    break;
+                }
+                h = (h + 1) & T.mask;
+            }
+        }
+        slot_of[i] = slot;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    int wmax = ok ? rl : 0;
+    for (int o = 16; o; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if ((threadIdx.x & 31) == 0 && m) { atomicAdd(counters + C_ADMIT, (uint32_t) __popc(m)); atomicMax(counters + C_MAXSPAN, (uint32_t) wmax); }
+}
+
+// K2
+__global__ void __launch_bounds__(256) pair_kernel(DevReads R, const int32_t *rend, const uint8_t *info, HashTab T, const uint32_t *slot_of, int32_t *mate, uint32_t *counters) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R.n) return;
+    int32_t m = -1;
+    uint8_t inf = info[i];
+    if (inf & INFO_ELIG) {
+        uint32_t h = slot_of[i];
+        if (h != 0xffffffffu) {
+            uint32_t c = T.cnt[h];
+            if (c == 2) {
+                uint32_t j = T.idx[2 * h] == i ? T.idx[2 * h + 1] : T.idx[2 * h];
+                atomicAdd(counters + C_PAIRED, 1u);
+                // cust_tweak_overlap_quality bails out when the strands differ in parity (overlaps.c:65),
+                // and there is nothing to merge when the reference spans are disjoint
+                int sa = INFO_STRAND(inf), sb = INFO_STRAND(info[j]);
+                bool overlap = R.pos[i] < rend[j] && R.pos[j] < rend[i];
+                if (!((sa - sb) & 1) && overlap) m = (int32_t) j;
+            } else if (c > 2) atomicAdd(counters + C_MULTI, 1u);
+        }
+    }
+    mate[i] = m;
+}
+
+// K3: first/last alignment index that can touch each window
+__global__ void __launch_bounds__(256) window_kernel(const int32_t *pos, uint32_t n, uint32_t beg, uint32_t W, uint32_t n_win, const uint32_t *counters, uint2 *win) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_win) return;
+    long long w0 = (long long) beg + (long long) w * W, w1 = w0 + W;
+    long long lo_pos = w0 - (long long) counters[C_MAXSPAN];      // a read starting at or before this cannot reach w0
+    uint32_t a = 0, b = n;
+    while (a < b) { uint32_t mid = (a + b) >> 1; if ((long long) pos[mid] <= lo_pos) a = mid + 1; else b = mid; }
+    uint32_t r0 = a;
+    b = n;
+    while (a < b) { uint32_t mid = (a + b) >> 1; if ((long long) pos[mid] < w1) a = mid + 1; else b = mid; }
+    win[w] = make_uint2(r0, a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// context classification on an absolute window [lo,hi) of the contig (common.c:49-82 chained as
+// extract.c:407-418).  Returns 0, or (type+1) | isG<<2 with type 0 CpG, 1 CHG, 2 CHH.
+__device__ __forceinline__ bool d_isC(unsigned char b) { return b == 'C' || b == 'c'; }
+__device__ __forceinline__ bool d_isG(unsigned char b) { return b == 'G' || b == 'g'; }
+
+template <class Get>
+__device__ __forceinline__ unsigned dev_context(Get get, long long p, long long lo, long long hi) {
+    if (p < lo || p >= hi) return 0;
+    unsigned char c = get(p);
+    if (d_isC(c)) {
+        if (p + 1 != hi && d_isG(get(p + 1))) return 1;
+        if (p + 2 < hi && d_isG(get(p + 2))) return 2;
+        return 3;
+    }
+    if (d_isG(c)) {
+        if (p != lo && d_isC(get(p - 1))) return 1 | 4;
+        if (p - lo > 1 && d_isC(get(p - 2))) return 2 | 4;
+        return 3 | 4;
+    }
+    return 0;
+}
+
+// Locate the query index of reference position rp in a read (M/=/X only); -1 if rp falls in D/N or outside.
+__device__ __forceinline__ int dev_qpos_at(const uint32_t *cigar, uint32_t k, uint32_t ke, int pos, int rp) {
+    int p = pos, q = 0;
+    for (; k < ke; ++k) {
+        uint32_t c = __ldg(cigar + k), op = c & 15u; int len = (int)(c >> 4);
+        if (op == 0 || op == 7 || op == 8) { if (rp < p + len) return rp >= p ? q + (rp - p) : -1; p += len; q += len; }
+        else if (op == 1 || op == 4) q += len;
+        else if (op == 2 || op == 3) { if (rp < p + len) return -1; p += len; }
+    }
+    return -1;
+}
+
+struct CountArgs {
+    DevReads R; KParams P;
+    const int32_t *rend; const uint8_t *info; const int32_t *mate; const uint2 *win;
+    const unsigned char *ref; uint32_t reflen;
+    uint32_t beg, end, W;
+    const uint32_t *chunk_bounds; uint32_t n_chunks;       // mbias only
+    md_call *calls; unsigned long long cap; uint2 *dir;    // extract: output records + per-window directory (offset,count)
+    uint32_t *counters;
+    uint32_t *hist; int32_t *lens;                         // mbias
+};
+
+#define MB_SM_Q 256   // mbias: query positions < this are histogrammed in shared memory
+
+// K4.  MODE 0: extract, 1: extract with variant filter, 2: mbias.
+template <int MODE>
+__global__ void __launch_bounds__(256) count_kernel(CountArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t W = A.W;
+    unsigned char *ctx = smem;                                   // [W]
+    unsigned char *refw = smem + W;                              // [W + 8] reference bytes w0-2 .. w0+W+2 (+pad)
+    uint32_t *cnt = (uint32_t *)(smem + 2 * W + 16);             // extract: meth[W], unmeth[W] (, noff[W], nvar[W]); mbias: hist
+    const uint32_t w = blockIdx.x;
+    const long long w0 = (long long) A.beg + (long long) w * W;
+    const long long own1 = min((long long) A.end, w0 + (long long) W);   // owned positions of this window: [w0, own1)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+
+    // ---- stage reference + classify -------------------------------------------------------------
+    for (uint32_t t = tid; t < W + 4; t += blockDim.x) {
+        long long p = w0 - 2 + t;
+        refw[t] = (p >= 0 && p < (long long) A.reflen) ? __ldg(A.ref + p) : (unsigned char) 'N';
+    }
+    const uint32_t ncnt = (MODE == 2) ? 4u * 2u * MB_SM_Q * 2u : (MODE == 1 ? 4u * W : 2u * W);
+    for (uint32_t t = tid; t < ncnt; t += blockDim.x) cnt[t] = 0;
+    __syncthreads();
+    for (uint32_t t = tid; t < W; t += blockDim.x) {
+        long long p = w0 + t;
+        unsigned c = 0;
+        if (p < own1) {
+            if (MODE == 2) {
+                // MBias.c:147,170-178: context inside the reference chunk's own window contig[cs..ce]
+                uint32_t lo = 0, hi = A.n_chunks;
+                while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if ((long long) A.chunk_bounds[mid] <= p) lo = mid; else hi = mid; }
+                if (A.n_chunks && p >= (long long) A.chunk_bounds[lo] && p < (long long) A.chunk_bounds[lo + 1]) {
+                    long long cs = A.chunk_bounds[lo], ce = A.chunk_bounds[lo + 1];
+                    long long last = ce < (long long) A.reflen ? ce : (long long) A.reflen - 1;
+                    auto get = [&](long long x) -> unsigned char { long long o = x - (w0 - 2); return (o >= 0 && o < (long long) W + 4) ? refw[o] : __ldg(A.ref + x); };
+                    c = dev_context(get, p, cs, last + 1);
+                }
+            } else {
+                auto get = [&](long long x) -> unsigned char { return refw[x - (w0 - 2)]; };
+                c = dev_context(get, p, 0, (long long) A.reflen);
+            }
+            if (c && !((A.P.keepMask >> ((c & 3) - 1)) & 1)) c = 0;      // extract.c:408,411,414
+        }
+        ctx[t] = (unsigned char) c;
+    }
+    __syncthreads();
+
+    // ---- stream the window's alignments -----------------------------------------------------------
+    const uint2 rr = A.win[w];
+    const DevReads &R = A.R;
+    for (uint32_t i = rr.x + warp; i < rr.y; i += nwarp) {
+        const unsigned inf = A.info[i];
+        if (!(inf & INFO_ADMIT)) continue;
+        if ((long long) A.rend[i] <= w0) continue;
+        const int strand = INFO_STRAND(inf);
+        const unsigned f = R.flag[i];
+        const int lq = (int) R.l_qseq[i];
+        int lo, hi; dev_trim(A.P, strand, f, lq, lo, hi);
+        const uint32_t soff = R.seq_off[i], qoff = R.qual_off[i];
+        const int pos = R.pos[i];
+        const uint32_t k0 = R.cigar_off[i], k1 = R.cigar_off[i + 1];
+        // mate (overlap merge) state
+        int mi = (MODE == 2) ? -1 : A.mate[i];
+        int mpos = 0, mlo = 0, mhi = 0, mend = 0; uint32_t mk0 = 0, mk1 = 0, msoff = 0, mqoff = 0; bool is_a = false;
+        if (mi >= 0) {
+            mpos = R.pos[mi]; mend = A.rend[mi]; mk0 = R.cigar_off[mi]; mk1 = R.cigar_off[mi + 1]; msoff = R.seq_off[mi]; mqoff = R.qual_off[mi];
+            dev_trim(A.P, INFO_STRAND(A.info[mi]), R.flag[mi], (int) R.l_qseq[mi], mlo, mhi);
+            is_a = (uint32_t) mi > i;                                   // first in file order is `a` (overlaps.c:129-135)
+        }
+        const bool wantG = !(strand & 1);
+        const int rd2 = (f & 0x80u) ? 1 : 0;
+        int p = pos, q = 0;
+        for (uint32_t k = k0; k < k1; ++k) {
+            const uint32_t c = __ldg(R.cigar + k), op = c & 15u; const int len = (int)(c >> 4);
+            if (op == 0 || op == 7 || op == 8) {
+                // clip the op to the window, then lanes stride over its bases
+                int j0 = (int) max(0ll, w0 - (long long) p), j1 = (int) min((long long) len, own1 - (long long) p);
+                for (int j = j0 + lane; j < j1; j += 32) {
+                    const int rp = p + j, qi = q + j;
+                    const unsigned cx = ctx[rp - (int) w0];
+                    if (!cx) continue;
+                    const bool siteG = (cx & 4u) != 0;
+                    if (MODE != 1 && siteG != wantG) continue;         // wrong-strand columns only matter to the variant filter
+                    unsigned b = 15u, ql = 0u;
+                    if (qi >= lo && qi < hi) { b = dev_base(R.seq, soff, qi); ql = dev_qual(R.qual, qoff, qi); }
+                    if (mi >= 0 && rp >= mpos && rp < mend) {
+                        const int mq = dev_qpos_at(R.cigar, mk0, mk1, mpos, rp);
+                        if (mq >= 0) {                                  // aligned in both mates: overlaps.c:81-114
+                            unsigned mb = 15u, mql = 0u;
+                            if (mq >= mlo && mq < mhi) { mb = dev_base(R.seq, msoff, mq); mql = dev_qual(R.qual, mqoff, mq); }
+                            if (b != mb) {
+                                // a is tested first (overlaps.c:91-100)
+                                const unsigned qa = is_a ? ql : mql, qb = is_a ? mql : ql, ba = is_a ? b : mb, bb = is_a ? mb : b;
+                                unsigned na, nb;
+                                if (qa > qb && ba != 15u) { na = qa - qb; nb = 0; }
+                                else if (qb > qa && bb != 15u) { nb = qb - qa; na = 0; }
+                                else { na = 0; nb = 0; }
+                                ql = is_a ? na : nb;
+                            } else {
+                                const unsigned qa = is_a ? ql : mql, qb = is_a ? mql : ql;
+                                unsigned na, nb;
+                                if (qa > qb) { na = A.P.boost[qa]; nb = 0; } else { nb = A.P.boost[qb]; na = 0; }   // ties favour b (overlaps.c:102-108)
+                                ql = is_a ? na : nb;
+                            }
+                        }
+                    }
+                    if ((int) ql < A.P.minPhred) continue;              // common.c:127 / extract.c:229
+                    const uint32_t o = (uint32_t)(rp - (int) w0);
+                    if (siteG == wantG) {
+                        int rv = 0;
+                        if (!wantG) { if (b == 2u) rv = 1; else if (b == 8u) rv = -1; }   // common.c:129-130
+                        else { if (b == 4u) rv = 1; else if (b == 1u) rv = -1; }          // common.c:131-132
+                        if (rv) {
+                            if (MODE == 2) {
+                                if (qi < MB_SM_Q) atomicAdd(cnt + ((((strand - 1) * 2 + rd2) * MB_SM_Q + qi) * 2 + (rv < 0 ? 1 : 0)), 1u);
+                                else if (qi < MD_MBIAS_MAXLEN) atomicAdd(A.hist + ((((size_t)(strand - 1) * 2 + rd2) * MD_MBIAS_MAXLEN + qi) * 2 + (rv < 0 ? 1 : 0)), 1u);
+                                if (qi < MD_MBIAS_MAXLEN) atomicMax(A.lens + (strand - 1), qi + 1);
+                            } else atomicAdd(cnt + (rv > 0 ? o : W + o), 1u);
+                        }
+                    } else if (MODE == 1) {                             // isVariant, extract.c:225-239
+                        atomicAdd(cnt + 2 * W + o, 1u);
+                        const bool var = wantG ? (b != 2u && b != 15u) : (b != 4u && b != 15u);
+                        if (var) atomicAdd(cnt + 3 * W + o, 1u);
+                    }
+                }
+                p += len; q += len;
+            } else if (op == 1 || op == 4) q += len;
+            else if (op == 2 || op == 3) p += len;
+        }
+    }
+    __syncthreads();
+
+    // ---- epilogue -----------------------------------------------------------------------------------
+    if (MODE == 2) {
+        for (uint32_t t = tid; t < 4u * 2u * MB_SM_Q * 2u; t += blockDim.x) {
+            uint32_t v = cnt[t];
+            if (v) { uint32_t sr = t / (MB_SM_Q * 2), rest = t % (MB_SM_Q * 2); atomicAdd(A.hist + (size_t) sr * MD_MBIAS_MAXLEN * 2 + rest, v); }
+        }
+        return;
+    }
+    // ordered compaction of this window's reportable columns
+    __shared__ uint32_t s_warp_tot[8], s_base;
+    const uint32_t per = (W + blockDim.x - 1) / blockDim.x;
+    const uint32_t t0 = tid * per, t1 = min(W, t0 + per);
+    uint32_t mine = 0;
+    for (uint32_t t = t0; t < t1; ++t) {
+        if (!ctx[t]) continue;
+        bool excl = false;
+        if (MODE == 1) {
+            uint32_t noff = cnt[2 * W + t], nvar = cnt[3 * W + t];
+            excl = A.P.minOppositeDepth > 0 && noff >= (uint32_t) A.P.minOppositeDepth && ((double) nvar) / ((double) noff) >= A.P.maxVariantFrac;
+        }
+        if (excl || cnt[t] + cnt[W + t]) ++mine;
+    }
+    uint32_t incl = mine;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t tot = 0;
+        for (int k = 0; k < nwarp; ++k) { uint32_t v = s_warp_tot[k]; s_warp_tot[k] = tot; tot += v; }
+        unsigned long long base = tot ? atomicAdd((unsigned long long *)(A.counters + C_NCALLS), (unsigned long long) tot) : 0ull;
+        if (base + tot > A.cap) { atomicExch(A.counters + C_OVERFLOW, 1u); s_base = 0xffffffffu; }
+        else s_base = (uint32_t) base;
+        A.dir[w] = make_uint2((uint32_t) base, tot);
+    }
+    __syncthreads();
+    if (s_base == 0xffffffffu) return;
+    uint32_t o = s_base + s_warp_tot[warp] + (incl - mine);
+    for (uint32_t t = t0; t < t1; ++t) {
+        const unsigned cx = ctx[t];
+        if (!cx) continue;
+        bool excl = false;
+        if (MODE == 1) {
+            uint32_t noff = cnt[2 * W + t], nvar = cnt[3 * W + t];
+            excl = A.P.minOppositeDepth > 0 && noff >= (uint32_t) A.P.minOppositeDepth && ((double) nvar) / ((double) noff) >= A.P.maxVariantFrac;
+        }
+        const uint32_t nm = cnt[t], nu = cnt[W + t];
+        if (excl || nm + nu) {
+            md_call c; c.pos = (uint32_t)(w0 + t); c.nmeth = nm; c.nunmeth = nu; c.info = ((cx & 3u) - 1u) | (cx & 4u) | (excl ? 8u : 0u);
+            A.calls[o++] = c;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side of the library
+struct Contig { unsigned char *d_seq = nullptr; uint32_t len = 0; uint32_t *d_bounds = nullptr; uint32_t n_chunks = 0; };
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { set_err("cudaMalloc", e); return -100; }
+        cap = want; return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct md_dev_reads {
+    DevBuf arena; DevReads view; uint32_t n = 0;
+};
+
+struct md_ctx {
+    int device = 0; md_config cfg; KParams kp;
+    cudaStream_t stream = nullptr;
+    std::map<int32_t, Contig> contigs;
+    md_dev_reads staged;                 // device copy of the host tile of md_extract_tile / md_mbias_tile
+    DevBuf rend, info, slot_of, mate, keys, hcnt, hidx, win, dir, calls, counters;
+    uint32_t *d_hist = nullptr; int32_t *d_lens = nullptr;
+    uint64_t launches = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float timing[5] = {0, 0, 0, 0, 0};
+    // last extract state (for collect / fetch)
+    uint32_t last_nwin = 0; uint64_t last_ncalls = 0; bool pending = false; md_tile_stats last_stats;
+    uint32_t h_counters[C_N];
+    uint32_t W = 4096;
+};
+
+static void fill_kparams(const md_config *c, KParams &k) {
+    memset(&k, 0, sizeof k);
+    k.minMapq = c->minMapq; k.minPhred = c->minPhred; k.keepDupes = c->keepDupes; k.keepSingleton = c->keepSingleton;
+    k.keepDiscordant = c->keepDiscordant; k.ignoreFlags = c->ignoreFlags; k.requireFlags = c->requireFlags; k.ignoreNH = c->ignoreNH;
+    k.keepMask = (c->keepCpG ? 1 : 0) | (c->keepCHG ? 2 : 0) | (c->keepCHH ? 4 : 0);
+    k.minOppositeDepth = c->minOppositeDepth; k.maxVariantFrac = c->maxVariantFrac;
+    for (int i = 0; i < 16; ++i) { k.bounds[i] = c->bounds[i] < 0 ? 0 : c->bounds[i]; k.abounds[i] = c->absoluteBounds[i] < 0 ? 0 : c->absoluteBounds[i]; }
+    k.noOverlap = c->noOverlapMerge;
+    for (int q = 0; q < 256; ++q) { volatile double v = (double) q; volatile double t = 0.2 * v; volatile double s = v + t; k.boost[q] = (unsigned char)(int) s; }
+}
+
+extern "C" md_ctx *md_create(const md_config *cfg, int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { g_err = std::string("no CUDA device available: ") + cudaGetErrorString(e); return nullptr; }
+    if (device < 0 || device >= ndev) { g_err = "bad device index"; return nullptr; }
+    CKN(cudaSetDevice(device));
+    md_ctx *c = new md_ctx();
+    c->device = device; c->cfg = *cfg; fill_kparams(cfg, c->kp);
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; delete c; return nullptr; }
+    for (int i = 0; i < 5; ++i) cudaEventCreate(&c->ev[i]);
+    size_t hb = (size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2 * sizeof(uint32_t);
+    if (cudaMalloc(&c->d_hist, hb) != cudaSuccess || cudaMalloc(&c->d_lens, 4 * sizeof(int32_t)) != cudaSuccess) { g_err = "cudaMalloc(hist) failed"; delete c; return nullptr; }
+    cudaMemsetAsync(c->d_hist, 0, hb, c->stream); cudaMemsetAsync(c->d_lens, 0, 4 * sizeof(int32_t), c->stream);
+    cudaFuncSetAttribute(count_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaStreamSynchronize(c->stream);
+    return c;
+}
+
+extern "C" void md_destroy(md_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->contigs) { cudaFree(kv.second.d_seq); if (kv.second.d_bounds) cudaFree(kv.second.d_bounds); }
+    c->staged.arena.release();
+    DevBuf *bufs[] = {&c->rend, &c->info, &c->slot_of, &c->mate, &c->keys, &c->hcnt, &c->hidx, &c->win, &c->dir, &c->calls, &c->counters};
+    for (DevBuf *b : bufs) b->release();
+    if (c->d_hist) cudaFree(c->d_hist);
+    if (c->d_lens) cudaFree(c->d_lens);
+    for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int md_load_contig(md_ctx *c, int32_t tid, const char *seq, uint32_t len) {
+    CK(cudaSetDevice(c->device));
+    md_drop_contig(c, tid);
+    Contig g; g.len = len;
+    CK(cudaMalloc(&g.d_seq, (size_t) len + 16));
+    CK(cudaMemcpyAsync(g.d_seq, seq, len, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->contigs[tid] = g;
+    return 0;
+}
+
+extern "C" int md_drop_contig(md_ctx *c, int32_t tid) {
+    auto it = c->contigs.find(tid);
+    if (it == c->contigs.end()) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(it->second.d_seq);
+    if (it->second.d_bounds) cudaFree(it->second.d_bounds);
+    c->contigs.erase(it);
+    return 0;
+}
+
+extern "C" int md_set_mbias_chunks(md_ctx *c, int32_t tid, const uint32_t *bounds, uint32_t n_chunks) {
+    auto it = c->contigs.find(tid);
+    if (it == c->contigs.end()) { g_err = "md_set_mbias_chunks: contig not loaded"; return -2; }
+    CK(cudaSetDevice(c->device));
+    if (it->second.d_bounds) { cudaStreamSynchronize(c->stream); cudaFree(it->second.d_bounds); it->second.d_bounds = nullptr; }
+    CK(cudaMalloc(&it->second.d_bounds, ((size_t) n_chunks + 1) * sizeof(uint32_t)));
+    CK(cudaMemcpyAsync(it->second.d_bounds, bounds, ((size_t) n_chunks + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    it->second.n_chunks = n_chunks;
+    return 0;
+}
+
+// ---- staging a host tile into one device arena ---------------------------------------------------
+static size_t al256(size_t x) { return (x + 255) & ~(size_t) 255; }
+
+static int stage_reads(md_ctx *c, md_dev_reads &d, const md_reads_soa *r) {
+    const size_t n = r->n_reads;
+    size_t sz[12] = {n * 4, n * 2, n, n, n * 4, (n + 1) * 4, n * 4, n * 4, n * 8, (size_t) r->n_cigar_ops * 4, (size_t) r->seq_words * 4, (size_t) r->qual_words * 8};
+    const void *src[12] = {r->pos, r->flag, r->mapq, r->aux, r->l_qseq, r->cigar_off, r->seq_off, r->qual_off, r->frag_key, r->cigar, r->seq, r->qual};
+    size_t off[12], tot = 0;
+    for (int k = 0; k < 12; ++k) { off[k] = tot; tot += al256(sz[k] + 16); }
+    if (d.arena.reserve(tot) != 0) return -100;
+    unsigned char *base = (unsigned char *) d.arena.p;
+    for (int k = 0; k < 12; ++k) if (sz[k]) CK(cudaMemcpyAsync(base + off[k], src[k], sz[k], cudaMemcpyHostToDevice, c->stream));
+    DevReads &v = d.view;
+    v.n = (uint32_t) n;
+    v.pos = (const int32_t *)(base + off[0]); v.flag = (const uint16_t *)(base + off[1]); v.mapq = base + off[2]; v.aux = base + off[3];
+    v.l_qseq = (const uint32_t *)(base + off[4]); v.cigar_off = (const uint32_t *)(base + off[5]); v.seq_off = (const uint32_t *)(base + off[6]);
+    v.qual_off = (const uint32_t *)(base + off[7]); v.frag_key = (const uint64_t *)(base + off[8]); v.cigar = (const uint32_t *)(base + off[9]);
+    v.seq = (const uint32_t *)(base + off[10]); v.qual = (const uint64_t *)(base + off[11]);
+    d.n = (uint32_t) n;
+    return 0;
+}
+
+extern "C" md_dev_reads *md_upload_reads(md_ctx *c, const md_reads_soa *reads) {
+    CKN(cudaSetDevice(c->device));
+    md_dev_reads *d = new md_dev_reads();
+    if (stage_reads(c, *d, reads) != 0) { delete d; return nullptr; }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { g_err = "upload sync failed"; d->arena.release(); delete d; return nullptr; }
+    return d;
+}
+extern "C" void md_free_reads(md_ctx *c, md_dev_reads *d) { if (!d) return; cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); d->arena.release(); delete d; }
+
+// ---- kernel pipeline on a device-resident tile ---------------------------------------------------
+static int run_pipeline(md_ctx *c, const md_tile_desc *t, const DevReads &R, bool mbias) {
+    auto it = c->contigs.find(t->tid);
+    if (it == c->contigs.end()) { g_err = "tile refers to a contig that was not loaded (md_load_contig)"; return -2; }
+    const Contig &g = it->second;
+    uint32_t beg = t->beg, end = std::min(t->end, g.len);
+    if (beg > end) beg = end;
+    if (mbias && !g.d_bounds) { g_err = "mbias tile without md_set_mbias_chunks"; return -2; }
+    const uint32_t n = R.n, W = c->W;
+    const uint32_t n_win = (end - beg + W - 1) / W;
+    uint32_t cap_pow2 = 1024; while (cap_pow2 < 2 * (size_t) n + 2) cap_pow2 <<= 1;
+    const bool need_hash = !mbias && !c->kp.noOverlap;
+    if (c->rend.reserve((size_t) n * 4 + 4) || c->info.reserve((size_t) n + 4) || c->slot_of.reserve((size_t) n * 4 + 4) || c->mate.reserve((size_t) n * 4 + 4) ||
+        c->win.reserve((size_t) n_win * 8 + 8) || c->dir.reserve((size_t) n_win * 8 + 8) || c->counters.reserve(C_N * 4)) return -100;
+    if (need_hash && (c->keys.reserve((size_t) cap_pow2 * 8) || c->hcnt.reserve((size_t) cap_pow2 * 4) || c->hidx.reserve((size_t) cap_pow2 * 8))) return -100;
+    const unsigned long long cap_calls = (unsigned long long)(end - beg) + 16;
+    if (!mbias && c->calls.reserve((size_t) cap_calls * sizeof(md_call))) return -100;
+    cudaStream_t s = c->stream;
+    CK(cudaMemsetAsync(c->counters.p, 0, C_N * 4, s));
+    HashTab T; T.keys = (unsigned long long *) c->keys.p; T.cnt = (uint32_t *) c->hcnt.p; T.idx = (uint32_t *) c->hidx.p; T.mask = cap_pow2 - 1;
+    if (need_hash) { CK(cudaMemsetAsync(c->keys.p, 0, (size_t) cap_pow2 * 8, s)); CK(cudaMemsetAsync(c->hcnt.p, 0, (size_t) cap_pow2 * 4, s)); }
+    KParams kp = c->kp; if (mbias) kp.noOverlap = 1;
+    CK(cudaEventRecord(c->ev[1], s));
+    if (n) {
+        const uint32_t gb = (n + 255) / 256;
+        prep_kernel<<<gb, 256, 0, s>>>(R, kp, (int32_t *) c->rend.p, (uint8_t *) c->info.p, T, (uint32_t *) c->slot_of.p, (uint32_t *) c->counters.p);
+        pair_kernel<<<gb, 256, 0, s>>>(R, (const int32_t *) c->rend.p, (const uint8_t *) c->info.p, T, (const uint32_t *) c->slot_of.p, (int32_t *) c->mate.p, (uint32_t *) c->counters.p);
+        c->launches += 2;
+    }
+    if (n_win) {
+        window_kernel<<<(n_win + 255) / 256, 256, 0, s>>>(R.pos, n, beg, W, n_win, (const uint32_t *) c->counters.p, (uint2 *) c->win.p);
+        c->launches += 1;
+    }
+    CK(cudaEventRecord(c->ev[2], s));
+    if (n_win) {
+        CountArgs A; memset(&A, 0, sizeof A);
+        A.R = R; A.P = kp; A.rend = (const int32_t *) c->rend.p; A.info = (const uint8_t *) c->info.p; A.mate = (const int32_t *) c->mate.p; A.win = (const uint2 *) c->win.p;
+        A.ref = g.d_seq; A.reflen = g.len; A.beg = beg; A.end = end; A.W = W; A.chunk_bounds = g.d_bounds; A.n_chunks = g.n_chunks;
+        A.calls = (md_call *) c->calls.p; A.cap = cap_calls; A.dir = (uint2 *) c->dir.p; A.counters = (uint32_t *) c->counters.p; A.hist = c->d_hist; A.lens = c->d_lens;
+        if (mbias) { size_t sm = 2 * (size_t) W + 16 + (size_t) 4 * 2 * MB_SM_Q * 2 * 4; count_kernel<2><<<n_win, 256, sm, s>>>(A); }
+        else if (kp.minOppositeDepth > 0) { size_t sm = 2 * (size_t) W + 16 + (size_t) 16 * W; count_kernel<1><<<n_win, 256, sm, s>>>(A); }
+        else { size_t sm = 2 * (size_t) W + 16 + (size_t) 8 * W; count_kernel<0><<<n_win, 256, sm, s>>>(A); }
+        c->launches += 1;
+    }
+    CK(cudaEventRecord(c->ev[3], s));
+    CK(cudaGetLastError());
+    c->last_nwin = mbias ? 0 : n_win;
+    return 0;
+}
+
+static int finish_counters(md_ctx *c, md_tile_stats *st) {
+    CK(cudaMemcpyAsync(c->h_counters, c->counters.p, C_N * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    unsigned long long ncalls; memcpy(&ncalls, &c->h_counters[C_NCALLS], 8);   // C_NCALLS is 8-byte aligned (index 4)
+    if (c->h_counters[C_OVERFLOW]) { g_err = "internal: call buffer overflow"; return -3; }
+    c->last_ncalls = ncalls;
+    md_tile_stats s; memset(&s, 0, sizeof s);
+    s.n_calls = ncalls; s.n_required = ncalls; s.n_admitted = c->h_counters[C_ADMIT]; s.n_pairs = c->h_counters[C_PAIRED] / 2; s.n_multi = c->h_counters[C_MULTI];
+    c->last_stats = s;
+    if (st) *st = s;
+    return 0;
+}
+
+// gather the per-window segments into position order
+static int fetch_sorted(md_ctx *c, md_call *out, uint64_t capacity, uint64_t *n_out) {
+    const uint64_t n = c->last_ncalls;
+    if (n_out) *n_out = n;
+    if (n > capacity) { g_err = "md_call capacity too small"; return -1; }
+    if (n == 0) return 0;
+    std::vector<md_call> raw(n);
+    std::vector<uint2> dir(c->last_nwin);
+    CK(cudaMemcpyAsync(raw.data(), c->calls.p, n * sizeof(md_call), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(dir.data(), c->dir.p, (size_t) c->last_nwin * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    uint64_t o = 0;
+    for (uint32_t w = 0; w < c->last_nwin; ++w) { if (dir[w].y) { memcpy(out + o, raw.data() + dir[w].x, (size_t) dir[w].y * sizeof(md_call)); o += dir[w].y; } }
+    if (o != n) { g_err = "internal: directory does not add up"; return -3; }
+    return 0;
+}
+
+static void collect_timing(md_ctx *c) {
+    float t;
+    for (int k = 0; k < 4; ++k) { t = 0; if (cudaEventElapsedTime(&t, c->ev[k], c->ev[k + 1]) == cudaSuccess) c->timing[k] = t; else c->timing[k] = 0; }
+    t = 0; if (cudaEventElapsedTime(&t, c->ev[0], c->ev[4]) == cudaSuccess) c->timing[4] = t;
+}
+
+extern "C" int md_submit_tile(md_ctx *c, const md_tile_desc *tile, const md_reads_soa *reads) {
+    CK(cudaSetDevice(c->device));
+    if (c->pending) { g_err = "md_submit_tile: a tile is already in flight on this context (collect it first)"; return -4; }
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    int rc = stage_reads(c, c->staged, reads);
+    if (rc) return rc;
+    rc = run_pipeline(c, tile, c->staged.view, false);
+    if (rc) return rc;
+    c->pending = true;
+    return 0;
+}
+
+extern "C" int md_collect_tile(md_ctx *c, int ticket, md_call *calls, uint64_t capacity, md_tile_stats *stats) {
+    (void) ticket;
+    CK(cudaSetDevice(c->device));
+    if (!c->pending) { g_err = "md_collect_tile: nothing in flight"; return -4; }
+    c->pending = false;
+    int rc = finish_counters(c, stats);
+    if (rc) return rc;
+    rc = fetch_sorted(c, calls, capacity, nullptr);
+    CK(cudaEventRecord(c->ev[4], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    collect_timing(c);
+    return rc;
+}
+
+extern "C" int md_extract_tile(md_ctx *c, const md_tile_desc *tile, const md_reads_soa *reads, md_call *calls, uint64_t capacity, md_tile_stats *stats) {
+    int t = md_submit_tile(c, tile, reads);
+    if (t < 0) return t;
+    return md_collect_tile(c, t, calls, capacity, stats);
+}
+
+extern "C" int md_extract_tile_device(md_ctx *c, const md_tile_desc *tile, const md_dev_reads *reads, md_tile_stats *stats) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    int rc = run_pipeline(c, tile, reads->view, false);
+    if (rc) return rc;
+    rc = finish_counters(c, stats);
+    CK(cudaEventRecord(c->ev[4], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    collect_timing(c);
+    return rc;
+}
+
+extern "C" int md_fetch_calls(md_ctx *c, md_call *calls, uint64_t capacity, uint64_t *n_calls) {
+    CK(cudaSetDevice(c->device));
+    return fetch_sorted(c, calls, capacity, n_calls);
+}
+
+extern "C" int md_mbias_tile(md_ctx *c, const md_tile_desc *tile, const md_reads_soa *reads, md_tile_stats *stats) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    int rc = stage_reads(c, c->staged, reads);
+    if (rc) return rc;
+    rc = run_pipeline(c, tile, c->staged.view, true);
+    if (rc) return rc;
+    rc = finish_counters(c, stats);
+    CK(cudaEventRecord(c->ev[4], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    collect_timing(c);
+    return rc;
+}
+
+extern "C" int md_mbias_tile_device(md_ctx *c, const md_tile_desc *tile, const md_dev_reads *reads, md_tile_stats *stats) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    int rc = run_pipeline(c, tile, reads->view, true);
+    if (rc) return rc;
+    rc = finish_counters(c, stats);
+    CK(cudaEventRecord(c->ev[4], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    collect_timing(c);
+    return rc;
+}
+
+extern "C" int md_mbias_hist(md_ctx *c, uint32_t *hist, int32_t lens[4]) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(hist, c->d_hist, (size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(lens, c->d_lens, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int md_mbias_reset(md_ctx *c) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(c->d_hist, 0, (size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2 * sizeof(uint32_t), c->stream));
+    CK(cudaMemsetAsync(c->d_lens, 0, 4 * sizeof(int32_t), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int md_host_register(void *p, size_t bytes) { if (!p || !bytes) return 0; CK(cudaHostRegister(p, bytes, cudaHostRegisterDefault)); return 0; }
+extern "C" int md_host_unregister(void *p) { if (!p) return 0; CK(cudaHostUnregister(p)); return 0; }
+extern "C" int md_last_timing(md_ctx *c, float out[5]) { for (int k = 0; k < 5; ++k) out[k] = c->timing[k]; return 0; }
+extern "C" uint64_t md_launch_count(md_ctx *c) { return c->launches; }
+extern "C" void *md_stream(md_ctx *c) { return (void *) c->stream; }

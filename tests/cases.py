@@ -1,0 +1,66 @@
+"""Shared case tables for the parity tests."""
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FX = os.path.join(ROOT, "tests", "golden", "fixtures")
+
+
+def fx(n):
+    return os.path.join(FX, n)
+
+
+# The 15 commands of the reference's tests/test.py (file:line in comments) with the line counts it
+# asserts.  Test 8 asserts 12 upstream; the reference's own code gives 11.
+REFERENCE_TESTS = [
+    ("t01", ["-q", "2"], "ct100.fa", "ct_aln.bam", {"_CpG.bedGraph": 1}),                                   # test.py:18
+    ("t02", ["-q", "2"], "cg100.fa", "cg_aln.bam", {"_CpG.bedGraph": 49}),                                  # test.py:25 (>1)
+    ("t03", ["-q", "10"], "cg100.fa", "cg_aln.bam", {"_CpG.bedGraph": 1}),                                  # test.py:35
+    ("t04", ["--methylKit", "--CHH", "--CHG", "-q", "2"], "cg100.fa", "cg_aln.bam",
+     {"_CpG.methylKit": 49, "_CHG.methylKit": 1, "_CHH.methylKit": 2}),                                      # test.py:45
+    ("t05", ["--minDepth", "2", "-q", "2"], "cg100.fa", "cg_aln.bam", {"_CpG.bedGraph": 1}),                # test.py:60
+    ("t06", ["--ignoreFlags", "0xD00", "-q", "2"], "cg100.fa", "cg_aln.bam", {"_CpG.bedGraph": 49}),        # test.py:68
+    ("t07", ["--requireFlags", "0xD00", "-q", "2"], "cg100.fa", "cg_aln.bam", {"_CpG.bedGraph": 49}),       # test.py:76
+    ("t08", ["--nOT", "50,50,40,40", "-q", "2"], "cg100.fa", "cg_aln.bam", {"_CpG.bedGraph": 11}),          # test.py:84 (asserts 12)
+    ("t09", ["-p", "1", "-q", "0", "--minOppositeDepth", "3", "--maxVariantFrac", "0.25"], "cg100.fa", "cg_with_variants.bam",
+     {"_CpG.bedGraph": 48}),                                                                                  # test.py:92
+    ("t10", [], "chgchh.fa", "chgchh_aln.bam", {"_CpG.bedGraph": 2}),                                        # test.py:101
+    ("t11", ["-q", "5"], "chgchh.fa", "chgchh_aln.bam", {"_CpG.bedGraph": 3}),                               # test.py:109
+    ("t14", ["-q", "1"], "cg100.fa", "NH.bam", {"_CpG.bedGraph": 1}),                                        # test.py:133
+    ("t15", ["--ignoreNH", "-q", "1"], "cg100.fa", "NH.bam", {"_CpG.bedGraph": 49}),                         # test.py:141
+]
+# tests 12/13 use --minConversionEfficiency, a SURVEY 8f "next" row not built yet.
+
+FIXTURE_EXTRA = [
+    ("x_cyt", ["-q", "2", "--cytosine_report", "--CHG", "--CHH"], "cg100.fa", "cg_aln.bam"),
+    ("x_mrg", ["-q", "2", "--mergeContext", "--CHG"], "cg100.fa", "cg_aln.bam"),
+    ("x_all", ["-q", "5", "--CHG", "--CHH"], "chgchh.fa", "chgchh_aln.bam"),
+    ("x_allmrg", ["-q", "0", "--CHG", "--CHH", "--mergeContext"], "chgchh.fa", "chgchh_aln.bam"),
+    ("x_F0", ["-q", "0", "-F", "0", "--keepDupes", "-p", "1"], "cg100.fa", "cg_aln.bam"),
+    ("x_var", ["-p", "1", "-q", "0", "--minOppositeDepth", "1", "--maxVariantFrac", "0.1", "--mergeContext"], "cg100.fa", "cg_with_variants.bam"),
+]
+
+# option sets exercised on synthetic BAMs (each is diffed byte-for-byte against oracle/_ref)
+SYNTH_OPTION_SETS = [
+    [],
+    ["--fraction"], ["--counts"], ["--logit"],
+    ["--CHG", "--CHH"],
+    ["--mergeContext", "--CHG", "--CHH"],
+    ["--cytosine_report", "--CHG", "--CHH"],
+    ["--methylKit", "--CHG", "--CHH"],
+    ["--CHG", "--CHH", "--minOppositeDepth", "2", "--maxVariantFrac", "0.1"],
+    ["--mergeContext", "--CHG", "--minOppositeDepth", "2", "--maxVariantFrac", "0.1"],
+    ["--OT", "5,140,10,130", "--OB", "3,0,0,120"],
+    ["--nOT", "5,5,7,7", "--nOB", "2,3,4,5", "--nCTOT", "1,1,1,1", "--nCTOB", "9,9,9,9"],
+    ["-F", "0", "--keepDupes", "--keepSingleton", "--keepDiscordant", "-q", "0", "-p", "1", "--ignoreNH"],
+    ["--chunkSize", "777", "--mergeContext", "--CHG"],
+    ["--chunkSize", "1000", "--cytosine_report"],
+    ["-r", "chr1:5000-20000", "--CHG"],
+    ["-r", "chr2", "--mergeContext"],
+    ["-d", "5", "--noCpG", "--CHH"],
+    ["-q", "40", "-p", "20", "-R", "2"],
+]
+
+
+def slug(opts):
+    s = "_".join(o.strip("-").replace(",", ".").replace(":", ".") for o in opts) or "default"
+    return s[:60]

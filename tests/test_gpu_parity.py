@@ -1,0 +1,184 @@
+"""GPU tier: the CUDA path (through the C ABI / the drop-in binary) against the oracle.
+Byte-exact: every output file of `lib/MethylDackel` must equal the file oracle/_ref writes for the
+same command, and every md_call record must equal the oracle port's."""
+import ctypes as C
+import os
+import subprocess
+
+import pytest
+
+import cases
+import oracle_binding as ob
+from methyldackel_b200 import _abi as A
+from methyldackel_b200 import api
+from util import run_ref, compare_outputs
+
+pytestmark = pytest.mark.gpu
+
+NEW_BIN = os.path.join(cases.ROOT, "methyldackel_b200", "lib", "MethylDackel")
+
+
+def _both(built, tmp_path, name, args, fa, bam):
+    refp, newp = str(tmp_path / (name + "_ref")), str(tmp_path / (name + "_new"))
+    r = run_ref(built["ref_bin"], "extract", args, fa, bam, refp)
+    assert r.returncode == 0, r.stderr
+    n = subprocess.run([NEW_BIN, "extract"] + list(args) + [fa, bam, "-o", newp], capture_output=True, text=True)
+    assert n.returncode == 0, n.stderr
+    assert n.stdout == r.stdout          # "N positions were excluded ..." (extract.c:1489)
+    return refp, newp
+
+
+@pytest.mark.parametrize("case", cases.REFERENCE_TESTS, ids=[c[0] for c in cases.REFERENCE_TESTS])
+def test_cli_reference_testsuite(built, tmp_path, case):
+    name, args, fa, bam, counts = case
+    refp, newp = _both(built, tmp_path, name, args, cases.fx(fa), cases.fx(bam))
+    for suffix, n in counts.items():
+        assert sum(1 for _ in open(newp + suffix)) == n
+    assert compare_outputs(refp, newp) == []
+
+
+@pytest.mark.parametrize("case", cases.FIXTURE_EXTRA, ids=[c[0] for c in cases.FIXTURE_EXTRA])
+def test_cli_fixture_extra(built, tmp_path, case):
+    name, args, fa, bam = case
+    refp, newp = _both(built, tmp_path, name, args, cases.fx(fa), cases.fx(bam))
+    assert compare_outputs(refp, newp) == []
+
+
+@pytest.mark.parametrize("opts", cases.SYNTH_OPTION_SETS, ids=[cases.slug(o) for o in cases.SYNTH_OPTION_SETS])
+def test_cli_synthetic_noisy(built, synth, tmp_path, opts):
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    refp, newp = _both(built, tmp_path, "s", opts, p + ".fa", p + ".bam")
+    assert compare_outputs(refp, newp) == []
+
+
+@pytest.mark.parametrize("opts", [[], ["--CHG", "--CHH", "--mergeContext"], ["--cytosine_report", "--CHG", "--CHH"],
+                                  ["--minOppositeDepth", "3", "--maxVariantFrac", "0.2", "--CHG"]], ids=["default", "merge", "cyt", "variant"])
+def test_cli_bismark_nondirectional(built, synth, tmp_path, opts):
+    p = synth("bismark", "--contigs", "chrA:40000", "--depth", "40", "--bismark-tags", "--nondirectional", "0.3", "--single-frac", "0.1",
+              "--isize-mean", "200", "--isize-sd", "30", "--read-seed", "99")
+    refp, newp = _both(built, tmp_path, "b", opts, p + ".fa", p + ".bam")
+    assert compare_outputs(refp, newp) == []
+
+
+def test_cli_deep_overlap_panel(built, synth, tmp_path):
+    p = synth("panel", "--contigs", "amp:3000", "--depth", "1500", "--isize-mean", "180", "--isize-sd", "25", "--isize-min", "150", "--isize-max", "300")
+    refp, newp = _both(built, tmp_path, "p", ["--CHG", "--CHH"], p + ".fa", p + ".bam")
+    assert compare_outputs(refp, newp) == []
+
+
+def test_cli_multi_tile_1mbp(built, synth, tmp_path):
+    """> 2 tiles of 2^19 alignments and > 1 reference chunk, with --mergeContext pairs straddling cuts"""
+    p = synth("mb3", "--contigs", "chr1:3000000,chr2:400000", "--depth", "60")
+    refp, newp = _both(built, tmp_path, "m", ["--CHG", "--CHH", "--mergeContext"], p + ".fa", p + ".bam")
+    assert compare_outputs(refp, newp) == []
+
+
+@pytest.mark.parametrize("opts", [["--noSVG"], ["--noSVG", "--CHG", "--CHH"], ["--noSVG", "--nOT", "3,3,3,3", "--chunkSize", "2500", "--CHG"],
+                                  ["--noSVG", "-r", "chr1:1000-30000"]], ids=["cpg", "all", "trim_chunk", "region"])
+def test_cli_mbias_txt(built, synth, opts):
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    r = subprocess.run([built["ref_bin"], "mbias"] + opts + [p + ".fa", p + ".bam"], capture_output=True, text=True)
+    n = subprocess.run([NEW_BIN, "mbias"] + opts + [p + ".fa", p + ".bam"], capture_output=True, text=True)
+    assert r.returncode == 0 and n.returncode == 0, (r.stderr, n.stderr)
+    assert n.stdout == r.stdout and len(r.stdout.splitlines()) > 50
+
+
+def test_cli_mbias_suggestions(built, synth, tmp_path):
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    r = subprocess.run([built["ref_bin"], "mbias", p + ".fa", p + ".bam", str(tmp_path / "r")], capture_output=True, text=True)
+    n = subprocess.run([NEW_BIN, "mbias", p + ".fa", p + ".bam", str(tmp_path / "n")], capture_output=True, text=True)
+    pick = lambda s: [l for l in s.splitlines() if l.startswith("Suggested inclusion options:")]
+    assert pick(r.stderr) and pick(r.stderr) == pick(n.stderr)
+
+
+# ---------------------------------------------------------------- tile level, through the C ABI
+def _tile_compare(cfg, fa, bam, contig_idx=0, beg=0, end=None):
+    b = api.BamFile(bam)
+    name = b.names[contig_idx]
+    ref = api.fetch_contig(fa, name)
+    if end is None:
+        end = len(ref)
+    soa = b.read_region(contig_idx, beg, end)
+    o = ob.lib()
+    cap = (end - beg) + 16
+    exp = (A.MdCall * cap)()
+    est = A.MdTileStats()
+    assert o.mdo_extract_tile(C.byref(cfg), ref, len(ref), beg, end, C.byref(soa), exp, cap, C.byref(est)) == 0
+    with api.GpuContext(cfg) as g:
+        g.load_contig(contig_idx, ref)
+        got, gst = g.extract_tile(contig_idx, beg, end, soa)
+    assert gst.n_calls == est.n_calls
+    assert gst.n_admitted == est.n_admitted
+    assert bytes(C.string_at(got, gst.n_calls * C.sizeof(A.MdCall))) == bytes(C.string_at(exp, est.n_calls * C.sizeof(A.MdCall)))
+    b.close()
+    return est
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(keepCHG=1, keepCHH=1), dict(keepCHG=1, keepCHH=1, minOppositeDepth=2, maxVariantFrac=0.1),
+                                dict(minMapq=0, minPhred=1, ignoreFlags=0, keepDupes=1, keepSingleton=1, keepDiscordant=1, ignoreNH=1, keepCHH=1)],
+                         ids=["cpg", "all", "variant", "nofilter"])
+def test_tile_abi_vs_oracle(built, synth, kw):
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    st = _tile_compare(A.default_config(**kw), p + ".fa", p + ".bam", 0)
+    assert st.n_calls > 1000 and st.n_pairs > 100
+
+
+def test_tile_abi_partial_interval(built, synth):
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    _tile_compare(A.default_config(keepCHG=1, keepCHH=1), p + ".fa", p + ".bam", 0, 12345, 23456)
+    _tile_compare(A.default_config(), p + ".fa", p + ".bam", 1, 0, 5)
+
+
+def test_tile_abi_empty_and_tiny(built, synth):
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    cfg = A.default_config(minMapq=61)      # admits nothing
+    st = _tile_compare(cfg, p + ".fa", p + ".bam", 0)
+    assert st.n_calls == 0 and st.n_admitted == 0
+
+
+def test_tile_abi_fixture_duplicate_names(built):
+    """cg_aln.bam holds four records all named read1; with -F 0 the name occurs 4 times"""
+    cfg = A.default_config(minMapq=2, ignoreFlags=0)
+    _tile_compare(cfg, cases.fx("cg100.fa"), cases.fx("cg_aln.bam"))
+
+
+def test_mbias_abi_vs_oracle(built, synth):
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    cfg = A.default_config(keepCHG=1, keepCHH=1, noOverlapMerge=1)
+    b = api.BamFile(p + ".bam")
+    ref = api.fetch_contig(p + ".fa", b.names[0])
+    soa = b.read_region(0)
+    h = A.load_host()
+    bounds = (C.c_uint32 * 64)()
+    n_chunks = h.mdh_chunk_bounds(ref, len(ref), 7000, 0, 0, bounds, 63)
+    assert 8 <= n_chunks < 63
+    o = ob.lib()
+    ehist = (C.c_uint32 * (4 * 2 * A.MD_MBIAS_MAXLEN * 2))()
+    elens = (C.c_int32 * 4)()
+    assert o.mdo_mbias_tile(C.byref(cfg), ref, len(ref), 0, len(ref), bounds, n_chunks, C.byref(soa), ehist, elens, None) == 0
+    with api.GpuContext(cfg) as g:
+        g.load_contig(0, ref)
+        g.set_mbias_chunks(0, [bounds[i] for i in range(n_chunks + 1)])
+        g.mbias_tile(0, 0, len(ref), soa)
+        ghist, glens = g.mbias_hist()
+    assert glens == list(elens)
+    assert bytes(ghist) == bytes(ehist)
+    assert sum(ehist) > 10000
+
+
+def test_device_resident_path_matches_host_path(built, synth):
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    cfg = A.default_config(keepCHG=1)
+    b = api.BamFile(p + ".bam")
+    ref = api.fetch_contig(p + ".fa", b.names[0])
+    soa = b.read_region(0)
+    with api.GpuContext(cfg) as g:
+        g.load_contig(0, ref)
+        got, st = g.extract_tile(0, 0, len(ref), soa)
+        d = g.upload(soa)
+        st2 = g.extract_tile_device(0, 0, len(ref), d)
+        got2, n2 = g.fetch_calls(len(ref) + 16)
+        g.free(d)
+        assert g.launch_count() >= 8
+    assert st.n_calls == st2.n_calls == n2
+    assert bytes(C.string_at(got, n2 * 16)) == bytes(C.string_at(got2, n2 * 16))

@@ -1,0 +1,89 @@
+"""CPU tier (no GPU): pins the oracle port and the product's HOST logic against oracle/_ref
+(the reference's own C sources built on oracle/htslib_shim), on the reference's fixture BAMs and on
+synthetic BAMs.  The host driver is run with the oracle port bound as its device back end
+(tests/oracle_binding.py), so option parsing, BAM decode, tiling, chunk replay and formatting are
+all exercised exactly as the GPU run will exercise them."""
+import os
+
+import pytest
+
+import cases
+import oracle_binding as ob
+from util import run_ref, compare_outputs
+
+
+def _both(built, tmp_path, name, args, fa, bam):
+    refp, newp = str(tmp_path / (name + "_ref")), str(tmp_path / (name + "_new"))
+    r = run_ref(built["ref_bin"], "extract", args, fa, bam, refp)
+    assert r.returncode == 0, r.stderr
+    rc = ob.run_host_main("extract", list(args) + [fa, bam, "-o", newp], ob.OracleBackend())
+    assert rc == 0
+    return refp, newp
+
+
+@pytest.mark.parametrize("case", cases.REFERENCE_TESTS, ids=[c[0] for c in cases.REFERENCE_TESTS])
+def test_reference_testsuite_counts_and_bytes(built, tmp_path, case):
+    name, args, fa, bam, counts = case
+    refp, newp = _both(built, tmp_path, name, args, cases.fx(fa), cases.fx(bam))
+    for suffix, n in counts.items():
+        assert sum(1 for _ in open(refp + suffix)) == n, "reference build disagrees with tests/test.py"
+    assert compare_outputs(refp, newp) == []
+
+
+@pytest.mark.parametrize("case", cases.FIXTURE_EXTRA, ids=[c[0] for c in cases.FIXTURE_EXTRA])
+def test_fixture_extra(built, tmp_path, case):
+    name, args, fa, bam = case
+    refp, newp = _both(built, tmp_path, name, args, cases.fx(fa), cases.fx(bam))
+    assert compare_outputs(refp, newp) == []
+
+
+@pytest.mark.parametrize("opts", cases.SYNTH_OPTION_SETS, ids=[cases.slug(o) for o in cases.SYNTH_OPTION_SETS])
+def test_synthetic_noisy(built, synth, tmp_path, opts):
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    refp, newp = _both(built, tmp_path, "s", opts, p + ".fa", p + ".bam")
+    assert compare_outputs(refp, newp) == []
+
+
+@pytest.mark.parametrize("opts", [[], ["--CHG", "--CHH", "--mergeContext"], ["--cytosine_report", "--CHG", "--CHH"],
+                                  ["--minOppositeDepth", "3", "--maxVariantFrac", "0.2", "--CHG"]], ids=["default", "merge", "cyt", "variant"])
+def test_synthetic_bismark_nondirectional(built, synth, tmp_path, opts):
+    p = synth("bismark", "--contigs", "chrA:40000", "--depth", "40", "--bismark-tags", "--nondirectional", "0.3", "--single-frac", "0.1",
+              "--isize-mean", "200", "--isize-sd", "30", "--read-seed", "99")
+    refp, newp = _both(built, tmp_path, "b", opts, p + ".fa", p + ".bam")
+    assert compare_outputs(refp, newp) == []
+
+
+def test_deep_overlap_panel(built, synth, tmp_path):
+    """config-4 shape in miniature: deep, short inserts, heavy mate overlap"""
+    p = synth("panel", "--contigs", "amp:3000", "--depth", "1500", "--isize-mean", "180", "--isize-sd", "25", "--isize-min", "150", "--isize-max", "300")
+    refp, newp = _both(built, tmp_path, "p", ["--CHG", "--CHH"], p + ".fa", p + ".bam")
+    assert compare_outputs(refp, newp) == []
+
+
+@pytest.mark.parametrize("opts", [["--noSVG"], ["--noSVG", "--CHG", "--CHH"], ["--noSVG", "--nOT", "3,3,3,3", "--chunkSize", "2500", "--CHG"],
+                                  ["--noSVG", "-r", "chr1:1000-30000"]], ids=["cpg", "all", "trim_chunk", "region"])
+def test_mbias_txt(built, synth, tmp_path, opts):
+    import subprocess, sys, ctypes
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    r = subprocess.run([built["ref_bin"], "mbias"] + opts + [p + ".fa", p + ".bam"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # the host driver prints to this process's stdout: run it in a child to capture
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import oracle_binding as ob; "
+            "sys.exit(ob.run_host_main('mbias', %r, ob.OracleBackend()))") % (cases.ROOT, os.path.join(cases.ROOT, "tests"), opts + [p + ".fa", p + ".bam"])
+    n = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert n.returncode == 0, n.stderr
+    assert n.stdout == r.stdout
+    assert len(r.stdout.splitlines()) > 50
+
+
+def test_mbias_suggestion_line(built, synth, tmp_path):
+    import subprocess, sys
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    r = subprocess.run([built["ref_bin"], "mbias", p + ".fa", p + ".bam", str(tmp_path / "svgref")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import oracle_binding as ob; "
+            "sys.exit(ob.run_host_main('mbias', %r, ob.OracleBackend()))") % (cases.ROOT, os.path.join(cases.ROOT, "tests"), [p + ".fa", p + ".bam", str(tmp_path / "svgnew")])
+    n = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    ref_line = [l for l in r.stderr.splitlines() if l.startswith("Suggested inclusion options:")]
+    new_line = [l for l in n.stderr.splitlines() if l.startswith("Suggested inclusion options:")]
+    assert ref_line and ref_line == new_line
