@@ -257,13 +257,123 @@ struct CountArgs {
 #define MB_SM_Q 256   // mbias: query positions < this are histogrammed in shared memory
 
 // K4.  MODE 0: extract, 1: extract with variant filter, 2: mbias.
+//
+// Read-level state shared by the two per-read code paths
+struct ReadCtx {
+    int strand, rd2; bool wantG;
+    int lo, hi;                      // kept query range after trims
+    uint32_t soff, qoff;
+    // mate (overlap merge); mi < 0 when there is nothing to merge
+    int mi, mpos, mend, mlo, mhi; uint32_t mk0, mk1, msoff, mqoff; bool is_a, mate_simple; int mq0;
+};
+
+__device__ __forceinline__ void load_mate(const CountArgs &A, uint32_t i, int mi, ReadCtx &rc) {
+    const DevReads &R = A.R;
+    rc.mi = mi;
+    if (mi < 0) return;
+    rc.mpos = R.pos[mi]; rc.mend = A.rend[mi]; rc.mk0 = R.cigar_off[mi]; rc.mk1 = R.cigar_off[mi + 1];
+    rc.msoff = R.seq_off[mi]; rc.mqoff = R.qual_off[mi];
+    dev_trim(A.P, INFO_STRAND(A.info[mi]), R.flag[mi], (int) R.l_qseq[mi], rc.mlo, rc.mhi);
+    rc.is_a = (uint32_t) mi > i;                               // first in file order is `a` (overlaps.c:129-135)
+    // a mate whose CIGAR is a single match op maps reference -> query by subtraction
+    rc.mate_simple = false; rc.mq0 = 0;
+    if (rc.mk1 - rc.mk0 == 1) { uint32_t op = __ldg(R.cigar + rc.mk0) & 15u; rc.mate_simple = (op == 0 || op == 7 || op == 8); }
+}
+
+// One base that sits on a kept-context column: overlap merge, phred gate, call / variant evidence.
+// b / ql are the read's own base and phred AFTER trimming.  (overlaps.c:81-114, common.c:118-134, extract.c:225-239)
+template <int MODE>
+__device__ __forceinline__ void eval_hit(const CountArgs &A, const ReadCtx &rc, uint32_t *cnt, uint32_t W, int w0i, int rp, int qi, unsigned b, unsigned ql, bool siteG) {
+    const DevReads &R = A.R;
+    if (rc.mi >= 0 && rp >= rc.mpos && rp < rc.mend) {
+        const int mq = rc.mate_simple ? (rp - rc.mpos) : dev_qpos_at(R.cigar, rc.mk0, rc.mk1, rc.mpos, rp);
+        if (mq >= 0) {                                          // aligned in both mates
+            unsigned mb = 15u, mql = 0u;
+            if (mq >= rc.mlo && mq < rc.mhi) { mb = dev_base(R.seq, rc.msoff, mq); mql = dev_qual(R.qual, rc.mqoff, mq); }
+            const unsigned qa = rc.is_a ? ql : mql, qb = rc.is_a ? mql : ql;
+            unsigned na, nb;
+            if (b != mb) {                                      // a is tested first (overlaps.c:91-100)
+                const unsigned ba = rc.is_a ? b : mb, bb = rc.is_a ? mb : b;
+                if (qa > qb && ba != 15u) { na = qa - qb; nb = 0; }
+                else if (qb > qa && bb != 15u) { nb = qb - qa; na = 0; }
+                else { na = 0; nb = 0; }
+            } else if (qa > qb) { na = A.P.boost[qa]; nb = 0; }
+            else { nb = A.P.boost[qb]; na = 0; }                // ties favour b (overlaps.c:102-108)
+            ql = rc.is_a ? na : nb;
+        }
+    }
+    if ((int) ql < A.P.minPhred) return;                       // common.c:127 / extract.c:229
+    const uint32_t o = (uint32_t)(rp - w0i);
+    if (siteG == rc.wantG) {
+        int rv = 0;
+        if (!rc.wantG) { if (b == 2u) rv = 1; else if (b == 8u) rv = -1; }   // common.c:129-130
+        else { if (b == 4u) rv = 1; else if (b == 1u) rv = -1; }             // common.c:131-132
+        if (rv) {
+            if (MODE == 2) {
+                const int s1 = rc.strand - 1;
+                if (qi < MB_SM_Q) atomicAdd(cnt + (((s1 * 2 + rc.rd2) * MB_SM_Q + qi) * 2 + (rv < 0 ? 1 : 0)), 1u);
+                else if (qi < MD_MBIAS_MAXLEN) atomicAdd(A.hist + ((((size_t) s1 * 2 + rc.rd2) * MD_MBIAS_MAXLEN + qi) * 2 + (rv < 0 ? 1 : 0)), 1u);
+                if (qi < MD_MBIAS_MAXLEN) atomicMax(A.lens + s1, qi + 1);
+            } else atomicAdd(cnt + (rv > 0 ? o : W + o), 1u);
+        }
+    } else if (MODE == 1) {                                     // isVariant, extract.c:225-239
+        atomicAdd(cnt + 2 * W + o, 1u);
+        const bool var = rc.wantG ? (b != 2u && b != 15u) : (b != 4u && b != 15u);
+        if (var) atomicAdd(cnt + 3 * W + o, 1u);
+    }
+}
+
+// General path: any CIGAR.  The whole warp walks one alignment, lanes stride over the bases of each match op.
+template <int MODE>
+__device__ __forceinline__ void slow_read(const CountArgs &A, uint32_t i, unsigned inf, long long w0, long long own1, const unsigned char *ctx, uint32_t *cnt, int lane) {
+    const DevReads &R = A.R;
+    ReadCtx rc;
+    rc.strand = INFO_STRAND(inf);
+    const unsigned f = R.flag[i];
+    rc.rd2 = (f & 0x80u) ? 1 : 0; rc.wantG = !(rc.strand & 1);
+    dev_trim(A.P, rc.strand, f, (int) R.l_qseq[i], rc.lo, rc.hi);
+    rc.soff = R.seq_off[i]; rc.qoff = R.qual_off[i];
+    load_mate(A, i, (MODE == 2) ? -1 : A.mate[i], rc);
+    int p = R.pos[i], q = 0;
+    for (uint32_t k = R.cigar_off[i], k1 = R.cigar_off[i + 1]; k < k1; ++k) {
+        const uint32_t c = __ldg(R.cigar + k), op = c & 15u; const int len = (int)(c >> 4);
+        if (op == 0 || op == 7 || op == 8) {
+            const int j0 = (int) max(0ll, w0 - (long long) p), j1 = (int) min((long long) len, own1 - (long long) p);
+            for (int j = j0 + lane; j < j1; j += 32) {
+                const int rp = p + j, qi = q + j;
+                const unsigned cx = ctx[rp - (int) w0];
+                if (!cx) continue;
+                const bool siteG = (cx & 4u) != 0;
+                if (MODE != 1 && siteG != rc.wantG) continue;   // wrong-strand columns only matter to the variant filter
+                unsigned b = 15u, ql = 0u;
+                if (qi >= rc.lo && qi < rc.hi) { b = dev_base(R.seq, rc.soff, qi); ql = dev_qual(R.qual, rc.qoff, qi); }
+                eval_hit<MODE>(A, rc, cnt, A.W, (int) w0, rp, qi, b, ql, siteG);
+            }
+            p += len; q += len;
+        } else if (op == 1 || op == 4) q += len;
+        else if (op == 2 || op == 3) p += len;
+    }
+}
+
+// 16 mask bits starting at window-relative position r (any int); bits outside [0, nbits) read as 0.
+// `bm` has one zero guard word on each side (index 0 is the guard).
+__device__ __forceinline__ unsigned mask16_at(const uint32_t *bm, int r, int nwords) {
+    if (r <= -16 || r >= nwords * 32) return 0u;
+    const int wi = (r >> 5) + 1;                               // arithmetic shift: r in [-15,-1] -> word -1 -> guard
+    const uint32_t lo = bm[wi], hi = bm[wi + 1];
+    return __funnelshift_r(lo, hi, (unsigned) r & 31u) & 0xffffu;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) count_kernel(CountArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t W = A.W;
+    const int NW = (int)(W >> 5);
     unsigned char *ctx = smem;                                   // [W]
-    unsigned char *refw = smem + W;                              // [W + 8] reference bytes w0-2 .. w0+W+2 (+pad)
-    uint32_t *cnt = (uint32_t *)(smem + 2 * W + 16);             // extract: meth[W], unmeth[W] (, noff[W], nvar[W]); mbias: hist
+    unsigned char *refw = smem + W;                              // [W + 16] reference bytes w0-2 .. w0+W+2
+    uint32_t *bmC = (uint32_t *)(smem + 2 * W + 16);             // [NW + 2] C-site bitmap with guard words
+    uint32_t *bmG = bmC + NW + 2;                                // [NW + 2]
+    uint32_t *cnt = bmG + NW + 2;                                // extract: meth[W], unmeth[W] (, noff[W], nvar[W]); mbias: hist
     const uint32_t w = blockIdx.x;
     const long long w0 = (long long) A.beg + (long long) w * W;
     const long long own1 = min((long long) A.end, w0 + (long long) W);   // owned positions of this window: [w0, own1)
@@ -276,8 +386,9 @@ __global__ void __launch_bounds__(256) count_kernel(CountArgs A) {
     }
     const uint32_t ncnt = (MODE == 2) ? 4u * 2u * MB_SM_Q * 2u : (MODE == 1 ? 4u * W : 2u * W);
     for (uint32_t t = tid; t < ncnt; t += blockDim.x) cnt[t] = 0;
+    if (tid < 4) { uint32_t *g = (tid & 1) ? bmG : bmC; g[(tid & 2) ? NW + 1 : 0] = 0; }
     __syncthreads();
-    for (uint32_t t = tid; t < W; t += blockDim.x) {
+    for (uint32_t t = tid; t < W; t += blockDim.x) {             // W is a multiple of 256, so warps stay converged for the ballots
         long long p = w0 + t;
         unsigned c = 0;
         if (p < own1) {
@@ -298,90 +409,93 @@ __global__ void __launch_bounds__(256) count_kernel(CountArgs A) {
             if (c && !((A.P.keepMask >> ((c & 3) - 1)) & 1)) c = 0;      // extract.c:408,411,414
         }
         ctx[t] = (unsigned char) c;
+        const unsigned mc = __ballot_sync(0xffffffffu, c != 0 && !(c & 4u)), mg = __ballot_sync(0xffffffffu, (c & 4u) != 0);
+        if (lane == 0) { bmC[(t >> 5) + 1] = mc; bmG[(t >> 5) + 1] = mg; }
     }
     __syncthreads();
 
     // ---- stream the window's alignments -----------------------------------------------------------
+    // A warp takes 32 consecutive alignments: each lane loads one alignment's scalars (coalesced), then the two
+    // half-warps walk the batch two alignments at a time; lane l of a half-warp owns query bases [16l, 16l+16),
+    // held in registers, and meets the window through a 16-bit slice of the C- or G-site bitmap.
     const uint2 rr = A.win[w];
     const DevReads &R = A.R;
-    for (uint32_t i = rr.x + warp; i < rr.y; i += nwarp) {
-        const unsigned inf = A.info[i];
-        if (!(inf & INFO_ADMIT)) continue;
-        if ((long long) A.rend[i] <= w0) continue;
-        const int strand = INFO_STRAND(inf);
-        const unsigned f = R.flag[i];
-        const int lq = (int) R.l_qseq[i];
-        int lo, hi; dev_trim(A.P, strand, f, lq, lo, hi);
-        const uint32_t soff = R.seq_off[i], qoff = R.qual_off[i];
-        const int pos = R.pos[i];
-        const uint32_t k0 = R.cigar_off[i], k1 = R.cigar_off[i + 1];
-        // mate (overlap merge) state
-        int mi = (MODE == 2) ? -1 : A.mate[i];
-        int mpos = 0, mlo = 0, mhi = 0, mend = 0; uint32_t mk0 = 0, mk1 = 0, msoff = 0, mqoff = 0; bool is_a = false;
-        if (mi >= 0) {
-            mpos = R.pos[mi]; mend = A.rend[mi]; mk0 = R.cigar_off[mi]; mk1 = R.cigar_off[mi + 1]; msoff = R.seq_off[mi]; mqoff = R.qual_off[mi];
-            dev_trim(A.P, INFO_STRAND(A.info[mi]), R.flag[mi], (int) R.l_qseq[mi], mlo, mhi);
-            is_a = (uint32_t) mi > i;                                   // first in file order is `a` (overlaps.c:129-135)
-        }
-        const bool wantG = !(strand & 1);
-        const int rd2 = (f & 0x80u) ? 1 : 0;
-        int p = pos, q = 0;
-        for (uint32_t k = k0; k < k1; ++k) {
-            const uint32_t c = __ldg(R.cigar + k), op = c & 15u; const int len = (int)(c >> 4);
-            if (op == 0 || op == 7 || op == 8) {
-                // clip the op to the window, then lanes stride over its bases
-                int j0 = (int) max(0ll, w0 - (long long) p), j1 = (int) min((long long) len, own1 - (long long) p);
-                for (int j = j0 + lane; j < j1; j += 32) {
-                    const int rp = p + j, qi = q + j;
-                    const unsigned cx = ctx[rp - (int) w0];
-                    if (!cx) continue;
-                    const bool siteG = (cx & 4u) != 0;
-                    if (MODE != 1 && siteG != wantG) continue;         // wrong-strand columns only matter to the variant filter
-                    unsigned b = 15u, ql = 0u;
-                    if (qi >= lo && qi < hi) { b = dev_base(R.seq, soff, qi); ql = dev_qual(R.qual, qoff, qi); }
-                    if (mi >= 0 && rp >= mpos && rp < mend) {
-                        const int mq = dev_qpos_at(R.cigar, mk0, mk1, mpos, rp);
-                        if (mq >= 0) {                                  // aligned in both mates: overlaps.c:81-114
-                            unsigned mb = 15u, mql = 0u;
-                            if (mq >= mlo && mq < mhi) { mb = dev_base(R.seq, msoff, mq); mql = dev_qual(R.qual, mqoff, mq); }
-                            if (b != mb) {
-                                // a is tested first (overlaps.c:91-100)
-                                const unsigned qa = is_a ? ql : mql, qb = is_a ? mql : ql, ba = is_a ? b : mb, bb = is_a ? mb : b;
-                                unsigned na, nb;
-                                if (qa > qb && ba != 15u) { na = qa - qb; nb = 0; }
-                                else if (qb > qa && bb != 15u) { nb = qb - qa; na = 0; }
-                                else { na = 0; nb = 0; }
-                                ql = is_a ? na : nb;
-                            } else {
-                                const unsigned qa = is_a ? ql : mql, qb = is_a ? mql : ql;
-                                unsigned na, nb;
-                                if (qa > qb) { na = A.P.boost[qa]; nb = 0; } else { nb = A.P.boost[qb]; na = 0; }   // ties favour b (overlaps.c:102-108)
-                                ql = is_a ? na : nb;
-                            }
-                        }
-                    }
-                    if ((int) ql < A.P.minPhred) continue;              // common.c:127 / extract.c:229
-                    const uint32_t o = (uint32_t)(rp - (int) w0);
-                    if (siteG == wantG) {
-                        int rv = 0;
-                        if (!wantG) { if (b == 2u) rv = 1; else if (b == 8u) rv = -1; }   // common.c:129-130
-                        else { if (b == 4u) rv = 1; else if (b == 1u) rv = -1; }          // common.c:131-132
-                        if (rv) {
-                            if (MODE == 2) {
-                                if (qi < MB_SM_Q) atomicAdd(cnt + ((((strand - 1) * 2 + rd2) * MB_SM_Q + qi) * 2 + (rv < 0 ? 1 : 0)), 1u);
-                                else if (qi < MD_MBIAS_MAXLEN) atomicAdd(A.hist + ((((size_t)(strand - 1) * 2 + rd2) * MD_MBIAS_MAXLEN + qi) * 2 + (rv < 0 ? 1 : 0)), 1u);
-                                if (qi < MD_MBIAS_MAXLEN) atomicMax(A.lens + (strand - 1), qi + 1);
-                            } else atomicAdd(cnt + (rv > 0 ? o : W + o), 1u);
-                        }
-                    } else if (MODE == 1) {                             // isVariant, extract.c:225-239
-                        atomicAdd(cnt + 2 * W + o, 1u);
-                        const bool var = wantG ? (b != 2u && b != 15u) : (b != 4u && b != 15u);
-                        if (var) atomicAdd(cnt + 3 * W + o, 1u);
-                    }
+    const int half = lane >> 4, hl = lane & 15;
+    const int w0i = (int) w0;
+    for (uint32_t base = rr.x + 32u * warp; base < rr.y; base += 32u * nwarp) {
+        const uint32_t i = base + lane;
+        // -- per-lane scalars of alignment i
+        unsigned inf = 0; int pos = 0, q0 = 0, mlen = 0; uint32_t lq = 0, soff = 0, qoff = 0, f = 0; int mate = -1; bool fast = false, live = false;
+        if (i < rr.y) {
+            inf = A.info[i];
+            live = (inf & INFO_ADMIT) && (long long) A.rend[i] > w0;
+            if (live) {
+                pos = R.pos[i]; lq = R.l_qseq[i]; f = R.flag[i]; soff = R.seq_off[i]; qoff = R.qual_off[i];
+                mate = (MODE == 2) ? -1 : A.mate[i];
+                // fast shape: [S] M [S] with at most 256 query bases
+                const uint32_t k0 = R.cigar_off[i], nk = R.cigar_off[i + 1] - k0;
+                if (nk >= 1 && nk <= 3 && lq <= 256u) {
+                    uint32_t c0 = __ldg(R.cigar + k0), c1 = nk > 1 ? __ldg(R.cigar + k0 + 1) : 0u, c2 = nk > 2 ? __ldg(R.cigar + k0 + 2) : 0u;
+                    auto isM = [](uint32_t c) { uint32_t op = c & 15u; return op == 0 || op == 7 || op == 8; };
+                    auto isS = [](uint32_t c) { return (c & 15u) == 4u; };
+                    if (nk == 1 && isM(c0)) { fast = true; q0 = 0; mlen = (int)(c0 >> 4); }
+                    else if (nk == 2 && isS(c0) && isM(c1)) { fast = true; q0 = (int)(c0 >> 4); mlen = (int)(c1 >> 4); }
+                    else if (nk == 2 && isM(c0) && isS(c1)) { fast = true; q0 = 0; mlen = (int)(c0 >> 4); }
+                    else if (nk == 3 && isS(c0) && isM(c1) && isS(c2)) { fast = true; q0 = (int)(c0 >> 4); mlen = (int)(c1 >> 4); }
                 }
-                p += len; q += len;
-            } else if (op == 1 || op == 4) q += len;
-            else if (op == 2 || op == 3) p += len;
+            }
+        }
+        const unsigned live_m = __ballot_sync(0xffffffffu, live), fast_m = __ballot_sync(0xffffffffu, live && fast);
+        // -- fast alignments, two per step
+        for (int t = 0; t < 16; ++t) {
+            const int src = 2 * t + half;
+            if (!((fast_m >> (2 * t)) & 3u)) continue;            // warp-uniform: neither alignment of this step is fast
+            const bool mine = (fast_m >> src) & 1u;
+            const int rpos = __shfl_sync(0xffffffffu, pos, src), rq0 = __shfl_sync(0xffffffffu, q0, src), rmlen = __shfl_sync(0xffffffffu, mlen, src);
+            const uint32_t rlq = __shfl_sync(0xffffffffu, lq, src), rsoff = __shfl_sync(0xffffffffu, soff, src), rqoff = __shfl_sync(0xffffffffu, qoff, src);
+            const unsigned rinf = __shfl_sync(0xffffffffu, inf, src), rf = __shfl_sync(0xffffffffu, f, src);
+            const int rmate = __shfl_sync(0xffffffffu, mate, src);
+            if (!mine) continue;
+            const int b0 = 16 * hl;                               // first query base of this lane
+            if (b0 >= (int) rlq) continue;
+            ReadCtx rc;
+            rc.strand = INFO_STRAND(rinf); rc.rd2 = (rf & 0x80u) ? 1 : 0; rc.wantG = !(rc.strand & 1);
+            dev_trim(A.P, rc.strand, rf, (int) rlq, rc.lo, rc.hi);
+            rc.soff = rsoff; rc.qoff = rqoff;
+            // valid query bases of this lane: inside the match op, inside the kept range
+            const int vlo = max(max(rq0, rc.lo), b0), vhi = min(min(rq0 + rmlen, rc.hi), b0 + 16);
+            // window-relative position of query base b0
+            const int r = rpos + (b0 - rq0) - w0i;
+            unsigned mC = mask16_at(bmC, r, NW), mG = mask16_at(bmG, r, NW);
+            unsigned valid = 0u;
+            if (vhi > vlo) valid = ((1u << (vhi - b0)) - 1u) & ~((1u << (vlo - b0)) - 1u);
+            // bases outside the kept range still sit on columns (as N / phred 0) but can never pass the phred gate
+            // (minPhred >= 1) nor, for the overlap merge, win anything for THIS alignment — so they are skipped here.
+            unsigned own_m = rc.wantG ? mG : mC, opp_m = rc.wantG ? mC : mG;
+            own_m &= valid; opp_m = (MODE == 1) ? (opp_m & valid) : 0u;
+            unsigned any = own_m | opp_m;
+            if (!any) continue;
+            // this lane's 16 bases and phreds, from two 32-bit and two 64-bit loads
+            const uint32_t *sp = R.seq + rsoff + 2 * hl; const uint64_t *qp = R.qual + rqoff + 2 * hl;
+            const int nsw = (int)((((rlq + 1) >> 1) + 3) >> 2), nqw = (int)((rlq + 7) >> 3);
+            const uint32_t s0 = __ldg(sp), s1 = (2 * hl + 1 < nsw) ? __ldg(sp + 1) : 0u;
+            const uint64_t qv0 = __ldg(qp), qv1 = (2 * hl + 1 < nqw) ? __ldg(qp + 1) : 0ull;
+            load_mate(A, (uint32_t)(base + src), rmate, rc);
+            while (any) {
+                const int k = __ffs(any) - 1; any &= any - 1;
+                const uint32_t sw = (k < 8) ? s0 : s1;
+                const unsigned byte = (sw >> ((((k & 7) >> 1)) << 3)) & 0xffu;
+                const unsigned bb = (k & 1) ? (byte & 0xfu) : (byte >> 4);
+                const unsigned ql = (unsigned)(((k < 8) ? qv0 : qv1) >> ((k & 7) << 3)) & 0xffu;
+                const bool siteG = rc.wantG ? ((own_m >> k) & 1u) != 0 : ((own_m >> k) & 1u) == 0;
+                eval_hit<MODE>(A, rc, cnt, W, w0i, w0i + r + k, b0 + k, bb, ql, siteG);
+            }
+        }
+        // -- everything else (indels, reference skips, long reads): whole warp per alignment
+        unsigned slow_m = live_m & ~fast_m;
+        while (slow_m) {
+            const int src = __ffs(slow_m) - 1; slow_m &= slow_m - 1;
+            slow_read<MODE>(A, base + src, __shfl_sync(0xffffffffu, inf, src), w0, own1, ctx, cnt, lane);
         }
     }
     __syncthreads();
@@ -475,11 +589,12 @@ struct md_ctx {
     uint32_t last_nwin = 0; uint64_t last_ncalls = 0; bool pending = false; md_tile_stats last_stats;
     uint32_t h_counters[C_N];
     uint32_t W = 4096;
+    md_tile_desc last_tile; DevReads last_reads; bool last_mbias = false;
 };
 
 static void fill_kparams(const md_config *c, KParams &k) {
     memset(&k, 0, sizeof k);
-    k.minMapq = c->minMapq; k.minPhred = c->minPhred; k.keepDupes = c->keepDupes; k.keepSingleton = c->keepSingleton;
+    k.minMapq = c->minMapq; k.minPhred = c->minPhred < 1 ? 1 : c->minPhred;   /* extract.c:997-1000: -p below 1 is reset to 1 */ k.keepDupes = c->keepDupes; k.keepSingleton = c->keepSingleton;
     k.keepDiscordant = c->keepDiscordant; k.ignoreFlags = c->ignoreFlags; k.requireFlags = c->requireFlags; k.ignoreNH = c->ignoreNH;
     k.keepMask = (c->keepCpG ? 1 : 0) | (c->keepCHG ? 2 : 0) | (c->keepCHH ? 4 : 0);
     k.minOppositeDepth = c->minOppositeDepth; k.maxVariantFrac = c->maxVariantFrac;
@@ -588,6 +703,25 @@ extern "C" md_dev_reads *md_upload_reads(md_ctx *c, const md_reads_soa *reads) {
 }
 extern "C" void md_free_reads(md_ctx *c, md_dev_reads *d) { if (!d) return; cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); d->arena.release(); delete d; }
 
+
+// ---- K4 launch (also used to re-run a tile after the host resolved duplicate query names) -------
+static int launch_count(md_ctx *c, const Contig &g, const DevReads &R, const KParams &kp, uint32_t beg, uint32_t end, uint32_t n_win, unsigned long long cap_calls, bool mbias) {
+    if (!n_win) return 0;
+    const uint32_t W = c->W;
+    cudaStream_t s = c->stream;
+    CountArgs A; memset(&A, 0, sizeof A);
+    A.R = R; A.P = kp; A.rend = (const int32_t *) c->rend.p; A.info = (const uint8_t *) c->info.p; A.mate = (const int32_t *) c->mate.p; A.win = (const uint2 *) c->win.p;
+    A.ref = g.d_seq; A.reflen = g.len; A.beg = beg; A.end = end; A.W = W; A.chunk_bounds = g.d_bounds; A.n_chunks = g.n_chunks;
+    A.calls = (md_call *) c->calls.p; A.cap = cap_calls; A.dir = (uint2 *) c->dir.p; A.counters = (uint32_t *) c->counters.p; A.hist = c->d_hist; A.lens = c->d_lens;
+    const size_t bm = 2 * ((size_t)(W >> 5) + 2) * 4;
+    if (mbias) { size_t sm = 2 * (size_t) W + 16 + bm + (size_t) 4 * 2 * MB_SM_Q * 2 * 4; count_kernel<2><<<n_win, 256, sm, s>>>(A); }
+    else if (kp.minOppositeDepth > 0) { size_t sm = 2 * (size_t) W + 16 + bm + (size_t) 16 * W; count_kernel<1><<<n_win, 256, sm, s>>>(A); }
+    else { size_t sm = 2 * (size_t) W + 16 + bm + (size_t) 8 * W; count_kernel<0><<<n_win, 256, sm, s>>>(A); }
+    c->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // ---- kernel pipeline on a device-resident tile ---------------------------------------------------
 static int run_pipeline(md_ctx *c, const md_tile_desc *t, const DevReads &R, bool mbias) {
     auto it = c->contigs.find(t->tid);
@@ -622,25 +756,80 @@ static int run_pipeline(md_ctx *c, const md_tile_desc *t, const DevReads &R, boo
         c->launches += 1;
     }
     CK(cudaEventRecord(c->ev[2], s));
-    if (n_win) {
-        CountArgs A; memset(&A, 0, sizeof A);
-        A.R = R; A.P = kp; A.rend = (const int32_t *) c->rend.p; A.info = (const uint8_t *) c->info.p; A.mate = (const int32_t *) c->mate.p; A.win = (const uint2 *) c->win.p;
-        A.ref = g.d_seq; A.reflen = g.len; A.beg = beg; A.end = end; A.W = W; A.chunk_bounds = g.d_bounds; A.n_chunks = g.n_chunks;
-        A.calls = (md_call *) c->calls.p; A.cap = cap_calls; A.dir = (uint2 *) c->dir.p; A.counters = (uint32_t *) c->counters.p; A.hist = c->d_hist; A.lens = c->d_lens;
-        if (mbias) { size_t sm = 2 * (size_t) W + 16 + (size_t) 4 * 2 * MB_SM_Q * 2 * 4; count_kernel<2><<<n_win, 256, sm, s>>>(A); }
-        else if (kp.minOppositeDepth > 0) { size_t sm = 2 * (size_t) W + 16 + (size_t) 16 * W; count_kernel<1><<<n_win, 256, sm, s>>>(A); }
-        else { size_t sm = 2 * (size_t) W + 16 + (size_t) 8 * W; count_kernel<0><<<n_win, 256, sm, s>>>(A); }
-        c->launches += 1;
-    }
+    c->last_tile = *t; c->last_reads = R; c->last_mbias = mbias;
+    int rc = launch_count(c, g, R, kp, beg, end, n_win, cap_calls, mbias);
+    if (rc) return rc;
     CK(cudaEventRecord(c->ev[3], s));
     CK(cudaGetLastError());
     c->last_nwin = mbias ? 0 : n_win;
     return 0;
 }
 
+
+// ---- duplicate query names ---------------------------------------------------------------------
+// A name seen more than twice among the eligible records of a tile (secondary/supplementary records
+// admitted with -F 0, or hand-made files such as the reference's own tests/cg_aln.bam) cannot be
+// resolved by the two-slot table.  It is rare, so it is replayed on the host exactly as the pileup
+// engine drives custom_overlap_constructor / _destructor (overlaps.c:121-147): records are pushed in
+// file order; an eligible record either stores itself under its name or is merged with the stored one,
+// which removes the name; a buffered record is dropped (and whatever sits under its name with it) once
+// a record starting beyond its end has been pushed.  The count kernel is then run again.
+#include <unordered_map>
+static int resolve_duplicates_on_host(md_ctx *c) {
+    const DevReads &R = c->last_reads;
+    const uint32_t n = R.n;
+    std::vector<int32_t> pos(n), rend(n), mate(n, -1); std::vector<uint16_t> flag(n); std::vector<uint8_t> info(n); std::vector<uint64_t> key(n);
+    cudaStream_t s = c->stream;
+    CK(cudaMemcpyAsync(pos.data(), R.pos, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(rend.data(), c->rend.p, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(flag.data(), R.flag, (size_t) n * 2, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(info.data(), c->info.p, (size_t) n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(key.data(), R.frag_key, (size_t) n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<std::pair<int32_t, uint32_t>> by_end;
+    for (uint32_t i = 0; i < n; ++i) if (info[i] & INFO_ADMIT) by_end.emplace_back(rend[i], i);
+    std::sort(by_end.begin(), by_end.end());
+    std::unordered_map<uint64_t, uint32_t> stored;
+    size_t ev = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (!(info[i] & INFO_ADMIT)) continue;
+        if (info[i] & INFO_ELIG) {
+            auto it = stored.find(key[i]);
+            if (it == stored.end()) stored.emplace(key[i], i);
+            else {
+                uint32_t a = it->second;
+                stored.erase(it);
+                int sa = INFO_STRAND(info[a]), sb = INFO_STRAND(info[i]);
+                if (!((sa - sb) & 1) && pos[a] < rend[i] && pos[i] < rend[a]) { mate[a] = (int32_t) i; mate[i] = (int32_t) a; }
+            }
+        }
+        while (ev < by_end.size() && by_end[ev].first < pos[i]) { uint32_t x = by_end[ev].second; if (x < i) stored.erase(key[x]); ++ev; }
+    }
+    CK(cudaMemcpyAsync(c->mate.p, mate.data(), (size_t) n * 4, cudaMemcpyHostToDevice, s));
+    // run the count stage again from a clean output cursor
+    CK(cudaMemsetAsync((uint32_t *) c->counters.p + C_NCALLS, 0, 8, s));
+    auto it = c->contigs.find(c->last_tile.tid);
+    if (it == c->contigs.end()) { g_err = "internal: contig vanished"; return -3; }
+    const Contig &g = it->second;
+    uint32_t beg = c->last_tile.beg, end = std::min(c->last_tile.end, g.len);
+    if (beg > end) beg = end;
+    const uint32_t n_win = (end - beg + c->W - 1) / c->W;
+    KParams kp = c->kp;
+    int rc = launch_count(c, g, R, kp, beg, end, n_win, (unsigned long long)(end - beg) + 16, false);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
 static int finish_counters(md_ctx *c, md_tile_stats *st) {
     CK(cudaMemcpyAsync(c->h_counters, c->counters.p, C_N * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->h_counters[C_MULTI] && !c->last_mbias && !c->h_counters[C_OVERFLOW]) {
+        int rc = resolve_duplicates_on_host(c);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(c->h_counters, c->counters.p, C_N * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
     unsigned long long ncalls; memcpy(&ncalls, &c->h_counters[C_NCALLS], 8);   // C_NCALLS is 8-byte aligned (index 4)
     if (c->h_counters[C_OVERFLOW]) { g_err = "internal: call buffer overflow"; return -3; }
     c->last_ncalls = ncalls;
