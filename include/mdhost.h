@@ -40,6 +40,7 @@ typedef struct mdh_run_stats {
     uint64_t n_tiles;
     uint64_t n_calls;
     double   t_decode_s, t_device_s, t_format_s, t_total_s;
+    uint64_t n_variant_positions;   /* extract.c:1489 counter (summed over shards by the caller) */
 } mdh_run_stats;
 void mdh_last_run_stats(mdh_run_stats *out);
 
@@ -64,6 +65,9 @@ const char *mdh_fasta_fetch(mdh_fasta *f, const char *name, uint32_t *len);
  * writes up to cap+1 bounds, returns the number of chunks. */
 uint32_t mdh_chunk_bounds(const char *seq, uint32_t len, unsigned long chunk_size, uint32_t reg_beg, uint32_t reg_end,
                           uint32_t *bounds, uint32_t cap);
+
+/* Report stage of mbias on a summed histogram (layout of md_mbias_hist): suggestion line (svg!=0) and/or --txt table. */
+void mdh_mbias_report(const uint32_t *hist, const int32_t lens[4], int svg, int txt);
 
 const char *mdh_last_error(void);
 

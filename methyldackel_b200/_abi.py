@@ -62,7 +62,8 @@ class MdTileStats(C.Structure):
 
 class MdhRunStats(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("n_tiles", C.c_uint64), ("n_calls", C.c_uint64),
-                ("t_decode_s", C.c_double), ("t_device_s", C.c_double), ("t_format_s", C.c_double), ("t_total_s", C.c_double)]
+                ("t_decode_s", C.c_double), ("t_device_s", C.c_double), ("t_format_s", C.c_double), ("t_total_s", C.c_double),
+                ("n_variant_positions", C.c_uint64)]
 
 
 CREATE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.POINTER(MdConfig))
@@ -108,6 +109,7 @@ def load_host():
         h.mdh_fasta_fetch.restype = C.c_void_p; h.mdh_fasta_fetch.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint32)]
         h.mdh_chunk_bounds.restype = C.c_uint32
         h.mdh_chunk_bounds.argtypes = [C.c_char_p, C.c_uint32, C.c_ulong, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]
+        h.mdh_mbias_report.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.c_int, C.c_int]
         h.mdh_last_error.restype = C.c_char_p
         _host = h
     return _host

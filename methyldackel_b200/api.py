@@ -187,3 +187,116 @@ def fetch_contig(fasta_path, name):
     s = C.string_at(p, n.value)
     h.mdh_fasta_close(f)
     return s
+
+
+# ---------------------------------------------------------------------------------------------------
+# one process per GPU: the genome is partitioned into contiguous runs of reference chunks, one run per
+# rank (positions are independent, mates that straddle a cut are delivered to both sides, so
+# there is no data-path collective); rank 0 concatenates the per-rank text in genome order.
+def _output_names(argv):
+    """Output file names `extract` will write for this argv (extract.c:1344-1439)."""
+    a = list(argv)
+    flags = {x for x in a if x.startswith("-")}
+    pos = []
+    takes = {"-q", "-p", "-r", "-l", "-o", "-D", "-d", "-F", "-R", "-@", "-M", "-t", "-b", "-N", "-B", "--opref", "--minDepth", "--OT", "--OB", "--CTOT", "--CTOB",
+             "--nOT", "--nOB", "--nCTOT", "--nCTOB", "--minOppositeDepth", "--maxVariantFrac", "--chunkSize", "--minConversionEfficiency", "--ignoreFlags",
+             "--requireFlags", "--shardRank", "--shardWorld"}
+    opref, i = None, 0
+    while i < len(a):
+        if a[i] in ("-o", "--opref"):
+            opref = a[i + 1]
+        if a[i] in takes:
+            i += 2
+        elif a[i].startswith("-"):
+            i += 1
+        else:
+            pos.append(a[i]); i += 1
+    if opref is None:
+        opref = pos[1].rsplit(".", 1)[0] if "." in pos[1] else pos[1]
+    if "--cytosine_report" in flags:
+        return [opref + ".cytosine_report.txt"]
+    mid = ".meth.bedGraph" if flags & {"--fraction", "-f"} else ".counts.bedGraph" if flags & {"--counts", "-c"} else ".logit.bedGraph" if flags & {"--logit", "-m"} \
+        else ".methylKit" if "--methylKit" in flags else ".bedGraph"
+    out = []
+    if "--noCpG" not in flags:
+        out.append(opref + "_CpG" + mid)
+    if "--CHG" in flags:
+        out.append(opref + "_CHG" + mid)
+    if "--CHH" in flags:
+        out.append(opref + "_CHH" + mid)
+    return out
+
+
+def extract_sharded(argv, rank, world, run_main=None, barrier=None, allreduce_sum=None):
+    """`MethylDackel extract <argv>` with the genome split over `world` processes (one per GPU).
+
+    ``run_main(argv)`` runs the sub-command main in this process (default: the CUDA library on device
+    ``rank``); ``barrier()`` and ``allreduce_sum(int)`` come from the launcher's process group (default:
+    torch.distributed).  Returns the exit code."""
+    import sys
+    if run_main is None:
+        run_main = lambda av: extract_main(av, device=rank)[0]  # noqa: E731
+    if barrier is None or allreduce_sum is None:
+        import torch
+        import torch.distributed as dist
+
+        def barrier():
+            dist.barrier()
+
+        def allreduce_sum(x):
+            t = torch.tensor([x], dtype=torch.int64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+            dist.all_reduce(t)
+            return int(t.item())
+    rc = run_main(list(argv) + ["--shardRank", str(rank), "--shardWorld", str(world)])
+    st = A.MdhRunStats()
+    A.load_host().mdh_last_run_stats(C.byref(st))
+    nvar = allreduce_sum(int(st.n_variant_positions))
+    worst = allreduce_sum(1 if rc != 0 else 0)
+    barrier()
+    if rank == 0:
+        for name in _output_names(argv):
+            with open(name, "wb") as out:
+                for r in range(world):
+                    part = "%s.shard%d" % (name, r)
+                    with open(part, "rb") as f:
+                        while True:
+                            blk = f.read(1 << 24)
+                            if not blk:
+                                break
+                            out.write(blk)
+                    import os
+                    os.unlink(part)
+        if nvar:
+            print("%d positions were excluded due to likely being variants." % nvar)
+            sys.stdout.flush()
+    barrier()
+    return rc if rc != 0 else (-20 if worst else 0)
+
+
+def mbias_sharded(argv, rank, world, tmp_prefix, run_main=None, barrier=None):
+    """`MethylDackel mbias <argv>` over `world` processes: every rank histograms its run of chunks, rank 0 sums the
+    (<= 64 KB) histograms on the host (the analogue of mergeStrandMeth, MBias.c:42-55) and prints the report."""
+    import os
+    import numpy as np
+    if run_main is None:
+        run_main = lambda av: mbias_main(av, device=rank)[0]  # noqa: E731
+    if barrier is None:
+        import torch.distributed as dist
+        barrier = dist.barrier
+    part = "%s.hist%d" % (tmp_prefix, rank)
+    rc = run_main(list(argv) + ["--shardRank", str(rank), "--shardWorld", str(world), "--histOut", part])
+    barrier()
+    if rank == 0 and rc == 0:
+        n = 4 * 2 * A.MD_MBIAS_MAXLEN * 2
+        hist = np.zeros(n, dtype=np.uint32); lens = np.zeros(4, dtype=np.int32)
+        for r in range(world):
+            raw = np.fromfile("%s.hist%d" % (tmp_prefix, r), dtype=np.uint32)
+            lens = np.maximum(lens, raw[:4].view(np.int32))
+            hist += raw[4:4 + n]
+            os.unlink("%s.hist%d" % (tmp_prefix, r))
+        flags = set(argv)
+        svg = 0 if "--noSVG" in flags else 1
+        txt = 1 if ("--txt" in flags or "--noSVG" in flags) else 0
+        A.load_host().mdh_mbias_report(hist.ctypes.data_as(C.POINTER(C.c_uint32)), lens.ctypes.data_as(C.POINTER(C.c_int32)), svg, txt)
+    barrier()
+    return rc

@@ -143,7 +143,9 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         {"chunkSize", 1, NULL, 19}, {"keepStrand", 0, NULL, 20}, {"cytosine_report", 0, NULL, 21}, {"minConversionEfficiency", 1, NULL, 22}, {"ignoreNH", 0, NULL, 23},
         {"ignoreFlags", 1, NULL, 'F'}, {"requireFlags", 1, NULL, 'R'}, {"help", 0, NULL, 'h'}, {"version", 0, NULL, 'v'},
         {"mappability", 1, NULL, 'M'}, {"mappabilityThreshold", 1, NULL, 't'}, {"minMappableBases", 1, NULL, 'b'}, {"outputBBMFile", 1, NULL, 'O'},
-        {"outputBBMFileName", 1, NULL, 'N'}, {"mappabilityBBM", 1, NULL, 'B'}, {0, 0, NULL, 0}};
+        {"outputBBMFileName", 1, NULL, 'N'}, {"mappabilityBBM", 1, NULL, 'B'},
+        {"shardRank", 1, NULL, 200}, {"shardWorld", 1, NULL, 201}, {0, 0, NULL, 0}};   // 200/201: one process per GPU, see api.extract_sharded
+    int shardRank = 0, shardWorld = 1;
     optind = 0;   // re-entrant use from one process
     while ((c = getopt_long(argc, argv, "hvq:p:r:l:o:D:f:c:m:d:F:R:@:M:t:b:ON:B:", lopts, NULL)) >= 0) {
         switch (c) {
@@ -171,6 +173,8 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         case 21: o.cytosine_report = 1; break;
         case 22: minConvEff = atof(optarg); break;
         case 23: o.core.ignoreNH = 1; break;
+        case 200: shardRank = atoi(optarg); break;
+        case 201: shardWorld = atoi(optarg); if (shardWorld < 1) shardWorld = 1; break;
         case 'M': bwName = optarg; break;
         case 't': case 'b': case 'O': case 'N': break;
         case 'B': bbmName = optarg; break;
@@ -218,17 +222,20 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     FILE *fp[3] = {nullptr, nullptr, nullptr};
     std::string pre(opref);
     const char *mid = o.fraction ? ".meth.bedGraph" : o.counts ? ".counts.bedGraph" : o.logit ? ".logit.bedGraph" : o.methylKit ? ".methylKit" : ".bedGraph";
+    const std::string shardSuffix = shardWorld > 1 ? ".shard" + std::to_string(shardRank) : std::string();
     if (o.cytosine_report) {
-        fp[0] = fopen((pre + ".cytosine_report.txt").c_str(), "w"); fp[1] = fp[2] = fp[0];
+        fp[0] = fopen((pre + ".cytosine_report.txt" + shardSuffix).c_str(), "w"); fp[1] = fp[2] = fp[0];
         if (!fp[0]) { fprintf(stderr, "Couldn't open the output CpG metrics file for writing! Insufficient permissions?\n"); free(opref); return -3; }
     } else {
         static const char *ctxName[3] = {"CpG", "CHG", "CHH"};
         int keep[3] = {o.core.keepCpG, o.core.keepCHG, o.core.keepCHH};
         for (int k = 0; k < 3; ++k) if (keep[k]) {
-            fp[k] = fopen((pre + "_" + ctxName[k] + mid).c_str(), "w");
+            fp[k] = fopen((pre + "_" + ctxName[k] + mid + shardSuffix).c_str(), "w");
             if (!fp[k]) { fprintf(stderr, "Couldn't open the output %s metrics file for writing! Insufficient permissions?\n", ctxName[k]); free(opref); return -3; }
-            if (o.methylKit) fprintf(fp[k], "chrBase\tchr\tbase\tstrand\tcoverage\tfreqC\tfreqT\n");
-            else ExtractWriter::print_header(fp[k], ctxName[k], opref, o);
+            if (shardRank == 0) {
+                if (o.methylKit) fprintf(fp[k], "chrBase\tchr\tbase\tstrand\tcoverage\tfreqC\tfreqT\n");
+                else ExtractWriter::print_header(fp[k], ctxName[k], opref, o);
+            }
         }
     }
     // -r, extract.c:1441-1468
@@ -249,18 +256,32 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     ExtractWriter writer(o, fp);
     int rc = 0;
     {
-        ChunkCursor cursor(d.hdr->lens, o.chunkSize, gTid, gPos, gEnd);
-        auto fetch = [&](uint32_t t) { return d.fetch(t); };
-        Chunk ch; bool have = cursor.next(ch, fetch);
+        // the reference's chunk list (extract.c:325-350), enumerated up front; a shard takes a contiguous,
+        // length-balanced run of chunks (one process per GPU, no exchange between shards — SURVEY 8e)
+        std::vector<Chunk> all;
+        {
+            ChunkCursor cursor(d.hdr->lens, o.chunkSize, gTid, gPos, gEnd);
+            auto fetch = [&](uint32_t t) { return d.fetch(t); };
+            Chunk ch;
+            while (cursor.next(ch, fetch)) all.push_back(ch);
+        }
+        size_t c0 = 0, c1 = all.size();
+        if (shardWorld > 1) {
+            uint64_t total = 0; for (auto &k : all) total += k.end - k.beg;
+            uint64_t lo = total * (uint64_t) shardRank / (uint64_t) shardWorld, hi = total * (uint64_t)(shardRank + 1) / (uint64_t) shardWorld, acc = 0;
+            c0 = c1 = all.size();
+            for (size_t k = 0; k < all.size(); ++k) { if (acc >= lo && c0 == all.size()) c0 = k; if (acc >= hi) { c1 = k; break; } acc += all[k].end - all[k].beg; }
+            if (c0 > c1) c0 = c1;
+        }
         SoaTile tile, carry;
         std::vector<md_call> calls; size_t calls_head = 0;
         std::vector<md_call> tile_calls;
-        while (have && rc == 0) {
-            // all reference chunks of this contig
-            uint32_t tid = ch.tid;
+        size_t ci = c0;
+        while (ci < c1 && rc == 0) {
+            // all chunks of this shard that lie on one contig
+            uint32_t tid = all[ci].tid;
             std::vector<Chunk> chunks;
-            while (have && ch.tid == tid) { chunks.push_back(ch); have = cursor.next(ch, fetch); }
-            // NB: cursor.next() may already have fetched the NEXT contig's bases; re-fetch ours.
+            while (ci < c1 && all[ci].tid == tid) chunks.push_back(all[ci++]);
             const std::string *ref = d.fetch(tid);
             if (!ref) {
                 fprintf(stderr, "faidx_fetch_seq returned %i while trying to fetch the sequence for tid %s:%" PRIu32 "-%" PRIu32 "!\n", -2, d.hdr->names[tid].c_str(), chunks.front().beg, chunks.front().end);
@@ -309,7 +330,8 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         }
     }
     be->destroy(d.dev);
-    if (writer.n_variant_positions()) printf("%" PRIu64 " positions were excluded due to likely being variants.\n", writer.n_variant_positions());
+    g_stats.n_variant_positions = writer.n_variant_positions();
+    if (writer.n_variant_positions() && shardWorld == 1) printf("%" PRIu64 " positions were excluded due to likely being variants.\n", writer.n_variant_positions());
     if (o.cytosine_report) { if (fp[0]) fclose(fp[0]); }
     else for (int k = 0; k < 3; ++k) if (fp[k]) fclose(fp[k]);
     free(opref);
@@ -330,7 +352,9 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
         {"noCpG", 0, NULL, 1}, {"CHG", 0, NULL, 2}, {"CHH", 0, NULL, 3}, {"keepDupes", 0, NULL, 4}, {"keepSingleton", 0, NULL, 5}, {"keepDiscordant", 0, NULL, 6},
         {"txt", 0, NULL, 7}, {"noSVG", 0, NULL, 8}, {"nOT", 1, NULL, 9}, {"nOB", 1, NULL, 10}, {"nCTOT", 1, NULL, 11}, {"nCTOB", 1, NULL, 12},
         {"chunkSize", 1, NULL, 13}, {"keepStrand", 0, NULL, 14}, {"minConversionEfficiency", 1, NULL, 15}, {"ignoreNH", 0, NULL, 16},
-        {"ignoreFlags", 1, NULL, 'F'}, {"requireFlags", 1, NULL, 'R'}, {"help", 0, NULL, 'h'}, {"version", 0, NULL, 'v'}, {0, 0, NULL, 0}};
+        {"ignoreFlags", 1, NULL, 'F'}, {"requireFlags", 1, NULL, 'R'}, {"help", 0, NULL, 'h'}, {"version", 0, NULL, 'v'},
+        {"shardRank", 1, NULL, 200}, {"shardWorld", 1, NULL, 201}, {"histOut", 1, NULL, 202}, {0, 0, NULL, 0}};   // one process per GPU, see api.mbias_sharded
+    int shardRank = 0, shardWorld = 1; const char *histOut = nullptr;
     optind = 0;
     while ((c = getopt_long(argc, argv, "hvq:p:r:l:D:F:@:", lopts, NULL)) >= 0) {
         switch (c) {
@@ -352,6 +376,9 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
         case 14: break;
         case 15: minConvEff = atof(optarg); break;
         case 16: cfg.ignoreNH = 1; break;
+        case 200: shardRank = atoi(optarg); break;
+        case 201: shardWorld = atoi(optarg); if (shardWorld < 1) shardWorld = 1; break;
+        case 202: histOut = optarg; break;
         case 'F': cfg.ignoreFlags = atoi(optarg); break;
         case 'R': cfg.requireFlags = atoi(optarg); break;
         case 'q': cfg.minMapq = atoi(optarg); break;
@@ -361,6 +388,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
         }
     }
     if (argc == 1) { mbias_usage(); return 0; }
+    if (histOut) SVG = 0;
     if ((SVG && argc - optind != 3) || (!SVG && argc - optind < 2)) {
         fprintf(stderr, "You must supply a reference genome in fasta format, an input BAM file, and an output prefix!!!\n"); mbias_usage(); return -1; }
     if (cfg.minPhred < 1) { fprintf(stderr, "-p %i is invalid. resetting to 1, which is the lowest possible value.\n", cfg.minPhred); cfg.minPhred = 1; }
@@ -394,14 +422,27 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
     if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
     int rc = 0;
     {
-        ChunkCursor cursor(d.hdr->lens, chunkSize, gTid, gPos, gEnd);
-        auto fetch = [&](uint32_t t) { return d.fetch(t); };
-        Chunk ch; bool have = cursor.next(ch, fetch);
+        std::vector<Chunk> all;
+        {
+            ChunkCursor cursor(d.hdr->lens, chunkSize, gTid, gPos, gEnd);
+            auto fetch = [&](uint32_t t) { return d.fetch(t); };
+            Chunk ch;
+            while (cursor.next(ch, fetch)) all.push_back(ch);
+        }
+        size_t c0 = 0, c1 = all.size();
+        if (shardWorld > 1) {
+            uint64_t total = 0; for (auto &k : all) total += k.end - k.beg;
+            uint64_t lo = total * (uint64_t) shardRank / (uint64_t) shardWorld, hi = total * (uint64_t)(shardRank + 1) / (uint64_t) shardWorld, acc = 0;
+            c0 = c1 = all.size();
+            for (size_t k = 0; k < all.size(); ++k) { if (acc >= lo && c0 == all.size()) c0 = k; if (acc >= hi) { c1 = k; break; } acc += all[k].end - all[k].beg; }
+            if (c0 > c1) c0 = c1;
+        }
         SoaTile tile, carry;
-        while (have && rc == 0) {
-            uint32_t tid = ch.tid;
+        size_t ci = c0;
+        while (ci < c1 && rc == 0) {
+            uint32_t tid = all[ci].tid;
             std::vector<uint32_t> bounds;
-            while (have && ch.tid == tid) { if (bounds.empty()) bounds.push_back(ch.beg); bounds.push_back(ch.end); have = cursor.next(ch, fetch); }
+            while (ci < c1 && all[ci].tid == tid) { if (bounds.empty()) bounds.push_back(all[ci].beg); bounds.push_back(all[ci].end); ++ci; }
             const std::string *ref = d.fetch(tid);
             if (!ref) {
                 fprintf(stderr, "faidx_fetch_seq returned %i while trying to fetch the sequence for tid %s:%" PRIu32 "-%" PRIu32 "!\n", -2, d.hdr->names[tid].c_str(), bounds.front(), bounds.back());
@@ -434,7 +475,11 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
     std::vector<uint32_t> hist((size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2, 0); int32_t lens[4] = {0, 0, 0, 0};
     if (rc == 0 && be->mbias_hist(d.dev, hist.data(), lens) != 0) rc = -20;
     be->destroy(d.dev);
-    if (rc == 0) {
+    if (rc == 0 && histOut) {                                  // shard: hand the raw histogram to the caller, who sums the shards
+        FILE *f = fopen(histOut, "wb");
+        if (!f || fwrite(lens, sizeof(int32_t), 4, f) != 4 || fwrite(hist.data(), sizeof(uint32_t), hist.size(), f) != hist.size()) rc = -3;
+        if (f) fclose(f);
+    } else if (rc == 0) {
         // makeSVGs (svg.c:302-437) is where the reference prints the suggestions; the SVG drawing itself is
         // host-only plotting outside the accelerated path and is not produced by this build.
         if (SVG) { (void) opref; mbias_print_suggestions(stderr, hist.data(), lens); }
@@ -475,4 +520,12 @@ extern "C" const char *mdh_fasta_fetch(mdh_fasta *f, const char *name, uint32_t 
     if (!f->fa->fetch(name, f->seq)) { g_err = std::string("sequence not found: ") + name; return nullptr; }
     *len = (uint32_t) f->seq.size();
     return f->seq.data();
+}
+
+// Report stage of mbias on an (already summed) histogram: what mbias_main does after joining its threads
+// (MBias.c:557-559): the suggestion line of makeSVGs (svg.c:423-425) and/or makeTXT (svg.c:439-454).
+extern "C" void mdh_mbias_report(const uint32_t *hist, const int32_t lens[4], int svg, int txt) {
+    if (svg) mbias_print_suggestions(stderr, hist, lens);
+    if (txt) mbias_print_txt(stdout, hist, lens);
+    fflush(stdout); fflush(stderr);
 }

@@ -553,6 +553,37 @@ __global__ void __launch_bounds__(256) count_kernel(CountArgs A) {
     }
 }
 
+
+// K5/K6: put the per-window segments into position order on the device (exclusive scan of the directory
+// counts by one CTA, then a segment copy), so the D2H transfer lands in the caller's buffer already sorted.
+__global__ void __launch_bounds__(1024) dir_scan_kernel(uint2 *dir, uint32_t n_win, uint32_t *sorted_off) {
+    __shared__ uint32_t s_part[32]; __shared__ uint32_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_win; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint32_t v = i < n_win ? dir[i].y : 0u;
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_part[warp] = incl;
+        __syncthreads();
+        if (warp == 0) { uint32_t p = s_part[lane], q = p; for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, q, o); if (lane >= o) q += t; } s_part[lane] = q - p; }
+        __syncthreads();
+        const uint32_t excl = s_carry + s_part[warp] + incl - v;
+        if (i < n_win) sorted_off[i] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(128) gather_kernel(const md_call *raw, const uint2 *dir, const uint32_t *sorted_off, md_call *out) {
+    const uint2 d = dir[blockIdx.x];
+    const uint32_t o = sorted_off[blockIdx.x];
+    const uint4 *src = (const uint4 *)(raw + d.x); uint4 *dst = (uint4 *)(out + o);
+    for (uint32_t k = threadIdx.x; k < d.y; k += blockDim.x) dst[k] = src[k];
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side of the library
 struct Contig { unsigned char *d_seq = nullptr; uint32_t len = 0; uint32_t *d_bounds = nullptr; uint32_t n_chunks = 0; };
@@ -580,7 +611,7 @@ struct md_ctx {
     cudaStream_t stream = nullptr;
     std::map<int32_t, Contig> contigs;
     md_dev_reads staged;                 // device copy of the host tile of md_extract_tile / md_mbias_tile
-    DevBuf rend, info, slot_of, mate, keys, hcnt, hidx, win, dir, calls, counters;
+    DevBuf rend, info, slot_of, mate, keys, hcnt, hidx, win, dir, calls, counters, sorted, sorted_off;
     uint32_t *d_hist = nullptr; int32_t *d_lens = nullptr;
     uint64_t launches = 0;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -629,7 +660,7 @@ extern "C" void md_destroy(md_ctx *c) {
     cudaStreamSynchronize(c->stream);
     for (auto &kv : c->contigs) { cudaFree(kv.second.d_seq); if (kv.second.d_bounds) cudaFree(kv.second.d_bounds); }
     c->staged.arena.release();
-    DevBuf *bufs[] = {&c->rend, &c->info, &c->slot_of, &c->mate, &c->keys, &c->hcnt, &c->hidx, &c->win, &c->dir, &c->calls, &c->counters};
+    DevBuf *bufs[] = {&c->rend, &c->info, &c->slot_of, &c->mate, &c->keys, &c->hcnt, &c->hidx, &c->win, &c->dir, &c->calls, &c->counters, &c->sorted, &c->sorted_off};
     for (DevBuf *b : bufs) b->release();
     if (c->d_hist) cudaFree(c->d_hist);
     if (c->d_lens) cudaFree(c->d_lens);
@@ -718,6 +749,11 @@ static int launch_count(md_ctx *c, const Contig &g, const DevReads &R, const KPa
     else if (kp.minOppositeDepth > 0) { size_t sm = 2 * (size_t) W + 16 + bm + (size_t) 16 * W; count_kernel<1><<<n_win, 256, sm, s>>>(A); }
     else { size_t sm = 2 * (size_t) W + 16 + bm + (size_t) 8 * W; count_kernel<0><<<n_win, 256, sm, s>>>(A); }
     c->launches += 1;
+    if (!mbias) {
+        dir_scan_kernel<<<1, 1024, 0, s>>>((uint2 *) c->dir.p, n_win, (uint32_t *) c->sorted_off.p);
+        gather_kernel<<<n_win, 128, 0, s>>>((const md_call *) c->calls.p, (const uint2 *) c->dir.p, (const uint32_t *) c->sorted_off.p, (md_call *) c->sorted.p);
+        c->launches += 2;
+    }
     CK(cudaGetLastError());
     return 0;
 }
@@ -738,13 +774,13 @@ static int run_pipeline(md_ctx *c, const md_tile_desc *t, const DevReads &R, boo
         c->win.reserve((size_t) n_win * 8 + 8) || c->dir.reserve((size_t) n_win * 8 + 8) || c->counters.reserve(C_N * 4)) return -100;
     if (need_hash && (c->keys.reserve((size_t) cap_pow2 * 8) || c->hcnt.reserve((size_t) cap_pow2 * 4) || c->hidx.reserve((size_t) cap_pow2 * 8))) return -100;
     const unsigned long long cap_calls = (unsigned long long)(end - beg) + 16;
-    if (!mbias && c->calls.reserve((size_t) cap_calls * sizeof(md_call))) return -100;
+    if (!mbias && (c->calls.reserve((size_t) cap_calls * sizeof(md_call)) || c->sorted.reserve((size_t) cap_calls * sizeof(md_call)) || c->sorted_off.reserve((size_t) n_win * 4 + 4))) return -100;
     cudaStream_t s = c->stream;
+    CK(cudaEventRecord(c->ev[1], s));
     CK(cudaMemsetAsync(c->counters.p, 0, C_N * 4, s));
     HashTab T; T.keys = (unsigned long long *) c->keys.p; T.cnt = (uint32_t *) c->hcnt.p; T.idx = (uint32_t *) c->hidx.p; T.mask = cap_pow2 - 1;
     if (need_hash) { CK(cudaMemsetAsync(c->keys.p, 0, (size_t) cap_pow2 * 8, s)); CK(cudaMemsetAsync(c->hcnt.p, 0, (size_t) cap_pow2 * 4, s)); }
     KParams kp = c->kp; if (mbias) kp.noOverlap = 1;
-    CK(cudaEventRecord(c->ev[1], s));
     if (n) {
         const uint32_t gb = (n + 255) / 256;
         prep_kernel<<<gb, 256, 0, s>>>(R, kp, (int32_t *) c->rend.p, (uint8_t *) c->info.p, T, (uint32_t *) c->slot_of.p, (uint32_t *) c->counters.p);
@@ -840,20 +876,14 @@ static int finish_counters(md_ctx *c, md_tile_stats *st) {
     return 0;
 }
 
-// gather the per-window segments into position order
+// the records are already in position order on the device (dir_scan_kernel + gather_kernel)
 static int fetch_sorted(md_ctx *c, md_call *out, uint64_t capacity, uint64_t *n_out) {
     const uint64_t n = c->last_ncalls;
     if (n_out) *n_out = n;
     if (n > capacity) { g_err = "md_call capacity too small"; return -1; }
     if (n == 0) return 0;
-    std::vector<md_call> raw(n);
-    std::vector<uint2> dir(c->last_nwin);
-    CK(cudaMemcpyAsync(raw.data(), c->calls.p, n * sizeof(md_call), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(dir.data(), c->dir.p, (size_t) c->last_nwin * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out, c->sorted.p, n * sizeof(md_call), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    uint64_t o = 0;
-    for (uint32_t w = 0; w < c->last_nwin; ++w) { if (dir[w].y) { memcpy(out + o, raw.data() + dir[w].x, (size_t) dir[w].y * sizeof(md_call)); o += dir[w].y; } }
-    if (o != n) { g_err = "internal: directory does not add up"; return -3; }
     return 0;
 }
 

@@ -1,0 +1,60 @@
+"""CPU tier, world_size 2 over gloo: the N>1 path of the drop-in (one process per GPU, genome partitioned into
+contiguous runs of reference chunks, no data-path collective) gives byte-identical files to the single-process
+run and to oracle/_ref.  The device back end is the oracle port here (there is no GPU in this container);
+what is under test is the HOST sharding logic."""
+import os
+import subprocess
+import sys
+
+import cases
+from util import run_ref, compare_outputs
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import torch, torch.distributed as dist
+import oracle_binding as ob
+from methyldackel_b200 import api
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=world)
+def allsum(x):
+    t = torch.tensor([x], dtype=torch.int64); dist.all_reduce(t); return int(t.item())
+mode = sys.argv[1]; argv = sys.argv[2:]
+if mode == "extract":
+    rc = api.extract_sharded(argv, rank, world, run_main=lambda av: ob.run_host_main("extract", av, ob.OracleBackend()), barrier=dist.barrier, allreduce_sum=allsum)
+else:
+    rc = api.mbias_sharded(argv[1:], rank, world, argv[0], run_main=lambda av: ob.run_host_main("mbias", av, ob.OracleBackend()), barrier=dist.barrier)
+dist.destroy_process_group()
+sys.exit(rc)
+'''
+
+
+def _launch(mode, argv, port, world=2):
+    code = WORKER % {"root": cases.ROOT, "port": port}
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", code, mode] + argv, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1][-2000:] for o in outs]
+    return outs
+
+
+def test_extract_two_ranks_equals_reference(built, synth, tmp_path):
+    p = synth("shard", "--contigs", "chr1:70000,chr2:30000,chr3:9000", "--depth", "20")
+    for k, opts in enumerate([["--chunkSize", "10000", "--mergeContext", "--CHG"], ["--chunkSize", "7000", "--cytosine_report", "--CHH"],
+                              ["--chunkSize", "25000", "--minOppositeDepth", "2", "--maxVariantFrac", "0.1"]]):
+        refp, newp = str(tmp_path / ("ref%d" % k)), str(tmp_path / ("new%d" % k))
+        r = run_ref(built["ref_bin"], "extract", opts, p + ".fa", p + ".bam", refp)
+        assert r.returncode == 0
+        outs = _launch("extract", opts + [p + ".fa", p + ".bam", "-o", newp], 29511 + k)
+        assert compare_outputs(refp, newp) == []
+        assert outs[0][0] == r.stdout            # "N positions were excluded ..." summed over the shards, printed once
+
+
+def test_mbias_two_ranks_equals_reference(built, synth, tmp_path):
+    p = synth("shard", "--contigs", "chr1:70000,chr2:30000,chr3:9000", "--depth", "20")
+    opts = ["--noSVG", "--CHG", "--chunkSize", "9000"]
+    r = subprocess.run([built["ref_bin"], "mbias"] + opts + [p + ".fa", p + ".bam"], capture_output=True, text=True)
+    outs = _launch("mbias", [str(tmp_path / "mb")] + opts + [p + ".fa", p + ".bam"], 29531)
+    assert outs[0][0] == r.stdout and len(r.stdout) > 500
