@@ -156,6 +156,8 @@ void *md_stream(md_ctx *ctx);
 
 /* Page-lock / unlock a host buffer so md_extract_tile's copies run asynchronously at full PCIe rate
  * (cudaHostRegister); optional. */
+void *md_alloc_pinned(size_t bytes);   /* cudaMallocHost; NULL on failure */
+void md_free_pinned(void *p);
 int md_host_register(void *p, size_t bytes);
 int md_host_unregister(void *p);
 

@@ -28,6 +28,12 @@ typedef struct mdh_backend {
     int   (*mbias_tile)(void *be, const md_tile_desc *tile, const md_reads_soa *reads, md_tile_stats *st);
     int   (*mbias_hist)(void *be, uint32_t *hist, int32_t lens[4]);
     const char *(*last_error)(void);
+    /* optional (may be NULL): asynchronous tiles + page-locked tile memory; when present the extract driver keeps
+     * several tiles in flight so that BAM decode, H2D, kernels and D2H overlap */
+    int   (*submit_tile)(void *be, const md_tile_desc *tile, const md_reads_soa *reads);
+    int   (*collect_tile)(void *be, int ticket, md_call *calls, uint64_t cap, md_tile_stats *st);
+    void *(*pinned_alloc)(size_t bytes);
+    void  (*pinned_free)(void *p);
 } mdh_backend;
 
 /* Same argv conventions as the reference: argv[0] is the sub-command name. */
@@ -54,6 +60,12 @@ uint32_t mdh_bam_target_len(const mdh_bam *b, int tid);
 /* Every alignment of contig `tid` overlapping [beg,end), as one tile (arrays owned by the handle and
  * valid until the next call on it).  Scans from the start of the file (no index needed). */
 int mdh_bam_read_region(mdh_bam *b, int tid, uint32_t beg, uint32_t end, md_reads_soa *out);
+
+/* The same region cut into tiles of ~target_reads alignments, exactly as the sub-command driver cuts it
+ * (alignments straddling a cut are present in both neighbours). Returns the number of tiles; they stay
+ * alive (and at fixed addresses) until the next mdh_bam_make_tiles()/close. */
+int mdh_bam_make_tiles(mdh_bam *b, int tid, uint32_t beg, uint32_t end, uint64_t target_reads);
+int mdh_bam_get_tile(mdh_bam *b, int k, md_tile_desc *td, md_reads_soa *out);
 
 typedef struct mdh_fasta mdh_fasta;
 mdh_fasta *mdh_fasta_open(const char *path);

@@ -75,12 +75,17 @@ SET_CHUNKS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.POINTER(C.c_uint32
 MBIAS_TILE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa), C.POINTER(MdTileStats))
 MBIAS_HIST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32))
 LAST_ERROR_FN = C.CFUNCTYPE(C.c_char_p)
+SUBMIT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa))
+COLLECT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(MdCall), C.c_uint64, C.POINTER(MdTileStats))
+PIN_ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t)
+PIN_FREE_FN = C.CFUNCTYPE(None, C.c_void_p)
 
 
 class MdhBackend(C.Structure):
     _fields_ = [("factory_user", C.c_void_p), ("create", CREATE_FN), ("destroy", DESTROY_FN), ("load_contig", LOAD_CONTIG_FN),
                 ("drop_contig", DROP_CONTIG_FN), ("extract_tile", EXTRACT_TILE_FN), ("set_mbias_chunks", SET_CHUNKS_FN),
-                ("mbias_tile", MBIAS_TILE_FN), ("mbias_hist", MBIAS_HIST_FN), ("last_error", LAST_ERROR_FN)]
+                ("mbias_tile", MBIAS_TILE_FN), ("mbias_hist", MBIAS_HIST_FN), ("last_error", LAST_ERROR_FN),
+                ("submit_tile", SUBMIT_FN), ("collect_tile", COLLECT_FN), ("pinned_alloc", PIN_ALLOC_FN), ("pinned_free", PIN_FREE_FN)]
 
 
 _host = None
@@ -104,6 +109,8 @@ def load_host():
         h.mdh_bam_target_name.restype = C.c_char_p; h.mdh_bam_target_name.argtypes = [C.c_void_p, C.c_int]
         h.mdh_bam_target_len.restype = C.c_uint32; h.mdh_bam_target_len.argtypes = [C.c_void_p, C.c_int]
         h.mdh_bam_read_region.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(MdReadsSoa)]
+        h.mdh_bam_make_tiles.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64]
+        h.mdh_bam_get_tile.argtypes = [C.c_void_p, C.c_int, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa)]
         h.mdh_fasta_open.restype = C.c_void_p; h.mdh_fasta_open.argtypes = [C.c_char_p]
         h.mdh_fasta_close.argtypes = [C.c_void_p]
         h.mdh_fasta_fetch.restype = C.c_void_p; h.mdh_fasta_fetch.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint32)]
@@ -142,6 +149,8 @@ def load_gpu():
         g.md_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         g.md_launch_count.restype = C.c_uint64; g.md_launch_count.argtypes = [C.c_void_p]
         g.md_stream.restype = C.c_void_p; g.md_stream.argtypes = [C.c_void_p]
+        g.md_alloc_pinned.restype = C.c_void_p; g.md_alloc_pinned.argtypes = [C.c_size_t]
+        g.md_free_pinned.argtypes = [C.c_void_p]
         g.md_host_register.argtypes = [C.c_void_p, C.c_size_t]
         g.md_host_unregister.argtypes = [C.c_void_p]
         g.md_last_error.restype = C.c_char_p

@@ -119,7 +119,10 @@ class _GpuBackend:
                       A.SET_CHUNKS_FN(lambda b, t, bo, n: g.md_set_mbias_chunks(b, t, bo, n)),
                       A.MBIAS_TILE_FN(lambda b, td, r, st: g.md_mbias_tile(b, td, r, st)),
                       A.MBIAS_HIST_FN(lambda b, h, l: g.md_mbias_hist(b, h, l)),
-                      A.LAST_ERROR_FN(last_error)]
+                      A.LAST_ERROR_FN(last_error),
+                      A.SUBMIT_FN(lambda b, td, r: g.md_submit_tile(b, td, r)),
+                      A.COLLECT_FN(lambda b, t, c, cap, st: g.md_collect_tile(b, t, c, cap, st)),
+                      A.PIN_ALLOC_FN(lambda n: g.md_alloc_pinned(n)), A.PIN_FREE_FN(lambda q: g.md_free_pinned(q))]
         self.be = A.MdhBackend(None, *self._keep)
 
 
@@ -162,6 +165,20 @@ class BamFile:
         if self.h.mdh_bam_read_region(self.p, tid, beg, end, C.byref(soa)) != 0:
             raise IOError(self.h.mdh_last_error().decode())
         return soa
+
+    def make_tiles(self, tid, beg=0, end=None, target_reads=1 << 17):
+        """Cuts the region into tiles as the sub-command driver does; returns [(MdTileDesc, MdReadsSoa), ...]."""
+        if end is None:
+            end = self.lens[tid]
+        n = self.h.mdh_bam_make_tiles(self.p, tid, beg, end, target_reads)
+        if n < 0:
+            raise IOError(self.h.mdh_last_error().decode())
+        out = []
+        for k in range(n):
+            td, soa = A.MdTileDesc(), A.MdReadsSoa()
+            self.h.mdh_bam_get_tile(self.p, k, C.byref(td), C.byref(soa))
+            out.append((td, soa))
+        return out
 
     def close(self):
         if self.p:

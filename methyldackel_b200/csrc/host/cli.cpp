@@ -273,7 +273,14 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             for (size_t k = 0; k < all.size(); ++k) { if (acc >= lo && c0 == all.size()) c0 = k; if (acc >= hi) { c1 = k; break; } acc += all[k].end - all[k].beg; }
             if (c0 > c1) c0 = c1;
         }
-        SoaTile tile, carry;
+        // tile ring: with an asynchronous back end, tiles live in page-locked memory and up to two are in flight
+        // while the next one is being decoded (decode || H2D || kernels || D2H)
+        const bool use_async = be->submit_tile && be->collect_tile;
+        TileAlloc pin; if (use_async && be->pinned_alloc && be->pinned_free) { pin.alloc = be->pinned_alloc; pin.release = be->pinned_free; }
+        std::vector<std::unique_ptr<SoaTile>> ring;
+        for (int k = 0; k < (use_async ? 3 : 1); ++k) ring.emplace_back(new SoaTile(use_async ? &pin : nullptr));
+        const size_t tile_reads = use_async ? ((size_t) 1 << 17) : ((size_t) 1 << 19);
+        SoaTile carry;
         std::vector<md_call> calls; size_t calls_head = 0;
         std::vector<md_call> tile_calls;
         size_t ci = c0;
@@ -292,30 +299,13 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             if (rend > ref->size()) rend = (uint32_t) ref->size();
             if (be->load_contig(d.dev, (int32_t) tid, ref->data(), (uint32_t) ref->size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
             d.seek_to((int) tid, rbeg);
-            Tiler tiler(*d.bam, (int) tid, rbeg, rend, (size_t) 1 << 19);
+            Tiler tiler(*d.bam, (int) tid, rbeg, rend, tile_reads);
             calls.clear(); calls_head = 0; carry.clear();
             size_t next_chunk = 0;
-            for (;;) {
+            // completed tiles arrive in order; hand every finished reference chunk to the writer
+            auto absorb = [&](uint32_t done_upto, bool last) {
                 double t0 = now_s();
-                bool got = tiler.next(tile, carry);
-                g_stats.t_decode_s += now_s() - t0;
-                uint32_t done_upto = rend;
-                if (got) {
-                    done_upto = tile.end;
-                    if (tile.n() > 0) {
-                        md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end}; md_tile_stats st;
-                        uint64_t cap = (uint64_t)(tile.end - tile.beg) + 16;
-                        tile_calls.resize(cap);
-                        t0 = now_s();
-                        int r = be->extract_tile(d.dev, &td, &v, tile_calls.data(), cap, &st);
-                        g_stats.t_device_s += now_s() - t0;
-                        if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
-                        calls.insert(calls.end(), tile_calls.begin(), tile_calls.begin() + (ptrdiff_t) st.n_calls);
-                        g_stats.n_records += tile.n(); g_stats.n_tiles++; g_stats.n_calls += st.n_calls;
-                    }
-                }
-                t0 = now_s();
-                while (next_chunk < chunks.size() && (chunks[next_chunk].end <= done_upto || !got)) {
+                while (next_chunk < chunks.size() && (chunks[next_chunk].end <= done_upto || last)) {
                     const Chunk &k = chunks[next_chunk];
                     size_t a = calls_head; while (a < calls.size() && calls[a].pos < k.beg) ++a;
                     size_t b = a; while (b < calls.size() && calls[b].pos < k.end) ++b;
@@ -324,8 +314,57 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
                 }
                 if (calls_head > (1u << 20)) { calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
                 g_stats.t_format_s += now_s() - t0;
+            };
+            struct Flight { int ticket; int slot; uint32_t end; uint64_t cap; };
+            std::vector<Flight> flight;
+            auto collect_one = [&]() -> int {
+                Flight f = flight.front(); flight.erase(flight.begin());
+                tile_calls.resize(f.cap);
+                md_tile_stats st;
+                double t0 = now_s();
+                int r = be->collect_tile(d.dev, f.ticket, tile_calls.data(), f.cap, &st);
+                g_stats.t_device_s += now_s() - t0;
+                if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+                calls.insert(calls.end(), tile_calls.begin(), tile_calls.begin() + (ptrdiff_t) st.n_calls);
+                g_stats.n_calls += st.n_calls;
+                absorb(f.end, false);
+                return 0;
+            };
+            size_t rk = 0;
+            for (;;) {
+                SoaTile &tile = *ring[rk % ring.size()];
+                // the ring slot we are about to refill must have been collected
+                if (use_async) while (!flight.empty() && flight.size() >= ring.size() - 0 && rc == 0) rc = collect_one();
+                if (rc) break;
+                double t0 = now_s();
+                bool got = tiler.next(tile, carry);
+                g_stats.t_decode_s += now_s() - t0;
                 if (!got) break;
+                if (tile.n() == 0) { if (!use_async) absorb(tile.end, false); continue; }
+                md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end};
+                uint64_t cap = (uint64_t)(tile.end - tile.beg) + 16;
+                g_stats.n_records += tile.n(); g_stats.n_tiles++;
+                if (use_async) {
+                    t0 = now_s();
+                    int ticket = be->submit_tile(d.dev, &td, &v);
+                    g_stats.t_device_s += now_s() - t0;
+                    if (ticket < 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+                    flight.push_back(Flight{ticket, (int)(rk % ring.size()), tile.end, cap});
+                    ++rk;
+                } else {
+                    md_tile_stats st;
+                    tile_calls.resize(cap);
+                    t0 = now_s();
+                    int r = be->extract_tile(d.dev, &td, &v, tile_calls.data(), cap, &st);
+                    g_stats.t_device_s += now_s() - t0;
+                    if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+                    calls.insert(calls.end(), tile_calls.begin(), tile_calls.begin() + (ptrdiff_t) st.n_calls);
+                    g_stats.n_calls += st.n_calls;
+                    absorb(tile.end, false);
+                }
             }
+            while (rc == 0 && !flight.empty()) rc = collect_one();
+            if (rc == 0) absorb(rend, true);
             be->drop_contig(d.dev, (int32_t) tid);
         }
     }
@@ -490,7 +529,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
 }
 
 // ------------------------------------------------------------------ BAM/FASTA helpers for tests + bench
-struct mdh_bam { std::string path; BamHeader hdr; SoaTile tile; };
+struct mdh_bam { std::string path; BamHeader hdr; SoaTile tile; std::vector<std::unique_ptr<SoaTile>> tiles; };
 extern "C" mdh_bam *mdh_bam_open(const char *path) {
     try { BamStream s(path); mdh_bam *b = new mdh_bam(); b->path = path; b->hdr = s.header(); return b; }
     catch (std::exception &e) { g_err = e.what(); return nullptr; }
@@ -509,6 +548,30 @@ extern "C" int mdh_bam_read_region(mdh_bam *b, int tid, uint32_t beg, uint32_t e
         *out = b->tile.view();
         return 0;
     } catch (std::exception &e) { g_err = e.what(); return -1; }
+}
+// Cut [beg,end) of contig tid into tiles of ~target_reads alignments exactly as the sub-command driver does
+// (Tiler: straddling alignments are present in both neighbours). Returns the number of tiles, kept alive by the handle.
+extern "C" int mdh_bam_make_tiles(mdh_bam *b, int tid, uint32_t beg, uint32_t end, uint64_t target_reads) {
+    try {
+        BamStream s(b->path);
+        Tiler t(s, tid, beg, end, (size_t) target_reads);
+        SoaTile carry;
+        b->tiles.clear();
+        for (;;) {
+            std::unique_ptr<SoaTile> tile(new SoaTile());
+            if (!t.next(*tile, carry)) break;
+            if (tile->n() == 0) continue;
+            b->tiles.push_back(std::move(tile));
+        }
+        return (int) b->tiles.size();
+    } catch (std::exception &e) { g_err = e.what(); return -1; }
+}
+extern "C" int mdh_bam_get_tile(mdh_bam *b, int k, md_tile_desc *td, md_reads_soa *out) {
+    if (k < 0 || (size_t) k >= b->tiles.size()) return -1;
+    SoaTile &t = *b->tiles[(size_t) k];
+    td->tid = t.tid; td->beg = t.beg; td->end = t.end;
+    *out = t.view();
+    return 0;
 }
 struct mdh_fasta { std::unique_ptr<Fasta> fa; std::string seq; };
 extern "C" mdh_fasta *mdh_fasta_open(const char *path) {

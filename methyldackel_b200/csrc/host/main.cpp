@@ -13,6 +13,8 @@ static int be_extract(void *b, const md_tile_desc *t, const md_reads_soa *r, md_
 static int be_chunks(void *b, int32_t tid, const uint32_t *bo, uint32_t n) { return md_set_mbias_chunks((md_ctx *) b, tid, bo, n); }
 static int be_mbias(void *b, const md_tile_desc *t, const md_reads_soa *r, md_tile_stats *st) { return md_mbias_tile((md_ctx *) b, t, r, st); }
 static int be_hist(void *b, uint32_t *h, int32_t l[4]) { return md_mbias_hist((md_ctx *) b, h, l); }
+static int be_submit(void *b, const md_tile_desc *t, const md_reads_soa *r) { return md_submit_tile((md_ctx *) b, t, r); }
+static int be_collect(void *b, int ticket, md_call *c, uint64_t cap, md_tile_stats *st) { return md_collect_tile((md_ctx *) b, ticket, c, cap, st); }
 
 static void usage_main() {
     fprintf(stderr, "MethylDackel (B200 build of the extract/mbias hot path): A tool for processing bisulfite sequencing alignments.\n"
@@ -23,7 +25,7 @@ static void usage_main() {
 }
 
 int main(int argc, char *argv[]) {
-    mdh_backend be = {nullptr, be_create, be_destroy, be_load, be_drop, be_extract, be_chunks, be_mbias, be_hist, md_last_error};
+    mdh_backend be = {nullptr, be_create, be_destroy, be_load, be_drop, be_extract, be_chunks, be_mbias, be_hist, md_last_error, be_submit, be_collect, md_alloc_pinned, md_free_pinned};
     if (argc == 1) { usage_main(); return 0; }
     if (!strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) { usage_main(); return 0; }
     if (!strcmp(argv[1], "-v") || !strcmp(argv[1], "--version")) { printf("0.6.1-b200 (B200 build; no HTSlib)\n"); return 0; }

@@ -29,6 +29,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -47,7 +48,7 @@ extern "C" int md_abi_version(void) { return MDGPU_ABI_VERSION; }
 // ------------------------------------------------------------------------------------------------
 // device-side views
 struct DevReads {
-    uint32_t n;
+    uint32_t n; uint32_t seq_words, qual_words;   // totals of seq[] (32-bit words) / qual[] (64-bit words)
     const int32_t *pos; const uint16_t *flag; const uint8_t *mapq; const uint8_t *aux; const uint32_t *l_qseq;
     const uint32_t *cigar_off, *seq_off, *qual_off; const uint64_t *frag_key;
     const uint32_t *cigar, *seq; const uint64_t *qual;
@@ -70,7 +71,7 @@ struct KParams {
 struct HashTab { unsigned long long *keys; uint32_t *cnt; uint32_t *idx; uint32_t mask; };
 
 // counters[]: 0 n_admitted, 1 max reference span, 2 n_pairs(x2), 3 n_multi, 4 n_calls (append cursor), 5 overflow flag
-enum { C_ADMIT = 0, C_MAXSPAN = 1, C_PAIRED = 2, C_MULTI = 3, C_NCALLS = 4 /* 64-bit: slots 4,5 */, C_OVERFLOW = 6, C_N = 8 };
+enum { C_ADMIT = 0, C_MAXSPAN = 1, C_PAIRED = 2, C_MULTI = 3, C_NCALLS = 4 /* 64-bit: slots 4,5 */, C_OVERFLOW = 6, C_MAXLQ = 7, C_N = 8 };
 
 // ------------------------------------------------------------------------------------------------
 // per-read primitives
@@ -166,8 +167,12 @@ __global__ void __launch_bounds__(256) prep_kernel(DevReads R, KParams P, int32_
     }
     unsigned m = __ballot_sync(0xffffffffu, ok);
     int wmax = ok ? rl : 0;
-    for (int o = 16; o; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if ((threadIdx.x & 31) == 0 && m) { atomicAdd(counters + C_ADMIT, (uint32_t) __popc(m)); atomicMax(counters + C_MAXSPAN, (uint32_t) wmax); }
+    uint32_t lqmax = (i < R.n) ? R.l_qseq[i] : 0u;
+    for (int o = 16; o; o >>= 1) { wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o)); lqmax = max(lqmax, __shfl_xor_sync(0xffffffffu, lqmax, o)); }
+    if ((threadIdx.x & 31) == 0) {
+        if (m) { atomicAdd(counters + C_ADMIT, (uint32_t) __popc(m)); atomicMax(counters + C_MAXSPAN, (uint32_t) wmax); }
+        atomicMax(counters + C_MAXLQ, lqmax);
+    }
 }
 
 // K2
@@ -324,8 +329,8 @@ __device__ __forceinline__ void eval_hit(const CountArgs &A, const ReadCtx &rc, 
 }
 
 // General path: any CIGAR.  The whole warp walks one alignment, lanes stride over the bases of each match op.
-template <int MODE>
-__device__ __forceinline__ void slow_read(const CountArgs &A, uint32_t i, unsigned inf, long long w0, long long own1, const unsigned char *ctx, uint32_t *cnt, int lane) {
+template <int MODE, class Ctx>
+__device__ __forceinline__ void slow_read(const CountArgs &A, uint32_t i, unsigned inf, long long w0, long long own1, Ctx ctx, uint32_t *cnt, int lane) {
     const DevReads &R = A.R;
     ReadCtx rc;
     rc.strand = INFO_STRAND(inf);
@@ -341,7 +346,7 @@ __device__ __forceinline__ void slow_read(const CountArgs &A, uint32_t i, unsign
             const int j0 = (int) max(0ll, w0 - (long long) p), j1 = (int) min((long long) len, own1 - (long long) p);
             for (int j = j0 + lane; j < j1; j += 32) {
                 const int rp = p + j, qi = q + j;
-                const unsigned cx = ctx[rp - (int) w0];
+                const unsigned cx = ctx(rp - (int) w0);
                 if (!cx) continue;
                 const bool siteG = (cx & 4u) != 0;
                 if (MODE != 1 && siteG != rc.wantG) continue;   // wrong-strand columns only matter to the variant filter
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(256) count_kernel(CountArgs A) {
         unsigned slow_m = live_m & ~fast_m;
         while (slow_m) {
             const int src = __ffs(slow_m) - 1; slow_m &= slow_m - 1;
-            slow_read<MODE>(A, base + src, __shfl_sync(0xffffffffu, inf, src), w0, own1, ctx, cnt, lane);
+            slow_read<MODE>(A, base + src, __shfl_sync(0xffffffffu, inf, src), w0, own1, [&](int rel) -> unsigned { return ctx[rel]; }, cnt, lane);
         }
     }
     __syncthreads();
@@ -554,6 +559,294 @@ __global__ void __launch_bounds__(256) count_kernel(CountArgs A) {
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// K4s — the streaming count kernel (default).  Same contract as count_kernel, different machine mapping:
+//
+//   * one CTA per window of W = 4096 reference positions, 256 threads, two CTAs resident per SM;
+//   * the window's alignments are taken in batches of up to 256; the batch's packed bases and phreds are ONE
+//     contiguous byte range each (tiles are laid out in read order), so thread 0 streams them into shared memory
+//     with two cp.async.bulk copies (TMA, completion on an mbarrier) while every thread fetches the scalars of
+//     "its" alignment; the co-resident CTA computes meanwhile, so HBM and the SM overlap;
+//   * then ONE THREAD PER ALIGNMENT walks its CIGAR against bitmaps of the kept C- and G-sites of the window
+//     (built bit-parallel from the staged reference: CpG / CHG / CHH are three shifts and a few ANDs), so only
+//     bases that can produce a call are ever touched — base and phred come from shared memory;
+//   * counts go to shared-memory histograms with atomicAdd, the epilogue is the same ordered compaction.
+//
+// Against the warp-per-alignment mapping this removes the idle lanes (an alignment has ~9 CpG hits for 150
+// bases) and cuts the warp-instruction count per alignment by more than an order of magnitude.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+#define ST_THREADS 256
+#define ST_SEQ_BYTES (20 * 1024)     // staged packed bases per batch  (256 alignments x 76 B for 150-mers, + slack)
+#define ST_QUAL_BYTES (40 * 1024)    // staged phreds per batch        (256 x 152 B, + slack)
+
+struct StreamLayout { uint32_t off_bm, off_ref, off_cnt, off_seq, off_qual, total; };
+__host__ __device__ inline StreamLayout stream_layout(uint32_t W, int mode) {
+    StreamLayout L; uint32_t NW = W >> 5;
+    auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
+    L.off_bm = 128;                                            // [0,128): mbarrier + batch descriptor
+    L.off_ref = up(L.off_bm + 4u * (NW + 2u) * 4u);
+    L.off_cnt = up(L.off_ref + W + 32u);
+    uint32_t ncnt = mode == 2 ? 4u * 2u * MB_SM_Q * 2u : (mode == 1 ? 4u * W : 2u * W);
+    L.off_seq = up(L.off_cnt + ncnt * 4u);
+    L.off_qual = up(L.off_seq + ST_SEQ_BYTES + 64u);
+    L.total = up(L.off_qual + ST_QUAL_BYTES + 64u);
+    return L;
+}
+
+struct StageDesc { uint32_t sw0, sw1, qw0, qw1; };             // staged word ranges: seq words [sw0,sw1), qual dwords [qw0,qw1)
+
+template <int MODE>
+__global__ void __launch_bounds__(ST_THREADS, 2) count_stream(CountArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t W = A.W, NW = W >> 5;
+    const StreamLayout SL = stream_layout(W, MODE);
+    uint64_t *bar = (uint64_t *) smem;
+    StageDesc *sd = (StageDesc *)(smem + 16);
+    uint32_t *bmC = (uint32_t *)(smem + SL.off_bm), *bmG = bmC + NW + 2, *bmT0 = bmG + NW + 2, *bmT1 = bmT0 + NW + 2;   // one guard word each side
+    unsigned char *refw = smem + SL.off_ref;
+    uint32_t *cnt = (uint32_t *)(smem + SL.off_cnt);
+    const unsigned char *sseq = smem + SL.off_seq, *squal = smem + SL.off_qual;
+    const uint32_t w = blockIdx.x;
+    const long long w0 = (long long) A.beg + (long long) w * W;
+    const long long own1 = min((long long) A.end, w0 + (long long) W);
+    const int own = (int)(own1 - w0), w0i = (int) w0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DevReads &R = A.R;
+    const uint2 rr = A.win[w];
+
+    // ---- prologue: barrier, reference window, site bitmaps -------------------------------------------
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    for (uint32_t t = tid; t < W + 4; t += ST_THREADS) {
+        long long p = w0 - 2 + t;
+        refw[t] = (p >= 0 && p < (long long) A.reflen) ? __ldg(A.ref + p) : (unsigned char) 'N';
+    }
+    const uint32_t ncnt = (MODE == 2) ? 4u * 2u * MB_SM_Q * 2u : (MODE == 1 ? 4u * W : 2u * W);
+    for (uint32_t t = tid; t < ncnt; t += ST_THREADS) cnt[t] = 0;
+    if (tid < 8) { uint32_t *g = bmC + (tid >> 1) * (NW + 2); g[(tid & 1) ? NW + 1 : 0] = 0; }
+    __syncthreads();
+    for (uint32_t base = 0; base < W; base += 16u * ST_THREADS) {         // 16 positions per thread per pass (one pass when W = 4096)
+        const uint32_t t16 = base + 16u * tid;                            // window offset of this thread's first position
+        unsigned sC = 0, sG = 0, t0 = 0, t1 = 0;
+        if (MODE == 2) {
+            // MBias.c:147,170-178: context inside the reference chunk's own window contig[cs..ce]; per position
+            for (int j = 0; j < 16; ++j) {
+                long long p = w0 + t16 + j; unsigned c = 0;
+                if (p < own1 && A.n_chunks) {
+                    uint32_t lo = 0, hi = A.n_chunks;
+                    while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if ((long long) A.chunk_bounds[mid] <= p) lo = mid; else hi = mid; }
+                    if (p >= (long long) A.chunk_bounds[lo] && p < (long long) A.chunk_bounds[lo + 1]) {
+                        long long cs = A.chunk_bounds[lo], ce = A.chunk_bounds[lo + 1];
+                        long long last = ce < (long long) A.reflen ? ce : (long long) A.reflen - 1;
+                        auto get = [&](long long x) -> unsigned char { long long o = x - (w0 - 2); return (o >= 0 && o < (long long) W + 4) ? refw[o] : __ldg(A.ref + x); };
+                        c = dev_context(get, p, cs, last + 1);
+                    }
+                }
+                if (c && !((A.P.keepMask >> ((c & 3) - 1)) & 1)) c = 0;
+                if (c) { if (c & 4u) sG |= 1u << j; else sC |= 1u << j; if ((c & 3u) == 1u) t0 |= 1u << j; else if ((c & 3u) == 2u) t1 |= 1u << j; }
+            }
+        } else if (t16 < W) {
+            // bit j of C / G <-> reference position w0 + t16 - 2 + j  (j = 0..19); bases outside the contig are staged as 'N',
+            // which reproduces the end-of-sequence rules of common.c:50-57,64-71
+            unsigned C = 0, G = 0;
+            #pragma unroll
+            for (int j = 0; j < 20; ++j) { unsigned ch = refw[t16 + j] | 0x20u; C |= (ch == 'c' ? 1u : 0u) << j; G |= (ch == 'g' ? 1u : 0u) << j; }
+            const unsigned cpgC = C & (G >> 1), cpgG = G & (C << 1);
+            const unsigned chgC = C & ~cpgC & (G >> 2), chgG = G & ~cpgG & (C << 2);
+            const unsigned chhC = C & ~cpgC & ~chgC, chhG = G & ~cpgG & ~chgG;
+            const unsigned k0 = (A.P.keepMask & 1) ? ~0u : 0u, k1 = (A.P.keepMask & 2) ? ~0u : 0u, k2 = (A.P.keepMask & 4) ? ~0u : 0u;
+            int nown = own - (int) t16; nown = nown < 0 ? 0 : (nown > 16 ? 16 : nown);
+            const unsigned ownm = nown >= 16 ? 0xffffu : ((1u << nown) - 1u);
+            sC = (((cpgC & k0) | (chgC & k1) | (chhC & k2)) >> 2) & ownm;
+            sG = (((cpgG & k0) | (chgG & k1) | (chhG & k2)) >> 2) & ownm;
+            t0 = (((cpgC | cpgG) & k0) >> 2) & ownm;
+            t1 = (((chgC | chgG) & k1) >> 2) & ownm;
+        }
+        // two threads share a bitmap word
+        const unsigned pC = __shfl_down_sync(0xffffffffu, sC, 1), pG = __shfl_down_sync(0xffffffffu, sG, 1), p0 = __shfl_down_sync(0xffffffffu, t0, 1), p1 = __shfl_down_sync(0xffffffffu, t1, 1);
+        if (!(tid & 1) && t16 < W) {
+            const uint32_t wi = (t16 >> 5) + 1;
+            bmC[wi] = sC | (pC << 16); bmG[wi] = sG | (pG << 16); bmT0[wi] = t0 | (p0 << 16); bmT1[wi] = t1 | (p1 << 16);
+        }
+    }
+    __syncthreads();
+
+    // ---- batches --------------------------------------------------------------------------------------
+    // batch size: as many alignments as are guaranteed to fit the staging buffers given the longest read of the tile
+    const uint32_t maxlq = A.counters[C_MAXLQ];
+    const uint32_t seqw_max = ((((maxlq + 1u) >> 1) + 3u) >> 2), qualw_max = (maxlq + 7u) >> 3;
+    uint32_t nb = ST_THREADS;
+    if (seqw_max) nb = min(nb, (uint32_t)(ST_SEQ_BYTES / 4u - 4u) / seqw_max);
+    if (qualw_max) nb = min(nb, (uint32_t)(ST_QUAL_BYTES / 8u - 2u) / qualw_max);
+    auto ctx_code = [&](int rel) -> unsigned {                        // byte code of count_kernel's ctx[] from the bitmaps
+        const uint32_t wi = ((uint32_t) rel >> 5) + 1, b = 1u << (rel & 31);
+        const bool c = bmC[wi] & b, g = bmG[wi] & b;
+        if (!c && !g) return 0u;
+        return ((bmT0[wi] & b) ? 1u : (bmT1[wi] & b) ? 2u : 3u) | (g ? 4u : 0u);
+    };
+    if (nb == 0) {
+        // reads too long to stage: whole warp per alignment, straight from global memory
+        for (uint32_t i = rr.x + warp; i < rr.y; i += ST_THREADS / 32) {
+            const unsigned inf = A.info[i];
+            if ((inf & INFO_ADMIT) && (long long) A.rend[i] > w0) slow_read<MODE>(A, i, inf, w0, own1, ctx_code, cnt, lane);
+        }
+    } else {
+        uint32_t phase = 0;
+        for (uint32_t s = rr.x; s < rr.y; s += nb) {
+            const uint32_t e = min(s + nb, rr.y), i = s + tid;
+            // -- thread 0 streams the batch's bases and phreds into shared memory
+            if (tid == 0) {
+                StageDesc d;
+                d.sw0 = R.seq_off[s] & ~3u; d.qw0 = R.qual_off[s] & ~1u;
+                const uint32_t lql = R.l_qseq[e - 1];
+                uint32_t sw_end = R.seq_off[e - 1] + ((((lql + 1u) >> 1) + 3u) >> 2), qw_end = R.qual_off[e - 1] + ((lql + 7u) >> 3);
+                sw_end = min(sw_end, R.seq_words); qw_end = min(qw_end, R.qual_words);
+                uint32_t sbytes = sw_end > d.sw0 ? (sw_end - d.sw0) * 4u : 0u, qbytes = qw_end > d.qw0 ? (qw_end - d.qw0) * 8u : 0u;
+                sbytes = min((sbytes + 15u) & ~15u, (uint32_t) ST_SEQ_BYTES); qbytes = min((qbytes + 15u) & ~15u, (uint32_t) ST_QUAL_BYTES);
+                d.sw1 = d.sw0 + sbytes / 4u; d.qw1 = d.qw0 + qbytes / 8u;
+                *sd = d;
+                mbar_arrive_expect_tx(bar, sbytes + qbytes);
+                if (sbytes) bulk_copy_g2s((void *) sseq, R.seq + d.sw0, sbytes, bar);
+                if (qbytes) bulk_copy_g2s((void *) squal, R.qual + d.qw0, qbytes, bar);
+            }
+            // -- meanwhile every thread fetches the scalars of its alignment
+            unsigned inf = 0; bool live = false;
+            int pos = 0, lq = 0, mate = -1; unsigned f = 0; uint32_t soff = 0, qoff = 0, k0 = 0, k1 = 0, c0 = 0;
+            if (i < e) {
+                inf = A.info[i];
+                live = (inf & INFO_ADMIT) && (long long) A.rend[i] > w0;
+                if (live) {
+                    pos = R.pos[i]; lq = (int) R.l_qseq[i]; f = R.flag[i]; soff = R.seq_off[i]; qoff = R.qual_off[i];
+                    k0 = R.cigar_off[i]; k1 = R.cigar_off[i + 1];
+                    mate = (MODE == 2) ? -1 : A.mate[i];
+                    c0 = __ldg(R.cigar + k0);
+                }
+            }
+            __syncthreads();                                           // descriptor visible
+            const StageDesc d = *sd;
+            { uint32_t spins = 0; while (!mbar_try_wait(bar, phase)) { if (++spins > (1u << 26)) { atomicExch(A.counters + C_OVERFLOW, 2u); break; } } }
+            phase ^= 1u;
+            if (live) {
+                ReadCtx rc;
+                rc.strand = INFO_STRAND(inf); rc.rd2 = (f & 0x80u) ? 1 : 0; rc.wantG = !(rc.strand & 1);
+                dev_trim(A.P, rc.strand, f, lq, rc.lo, rc.hi);
+                rc.soff = soff; rc.qoff = qoff;
+                load_mate(A, i, mate, rc);
+                // is this alignment's data inside the staged ranges?  (always, for tiles laid out in read order)
+                const uint32_t sw_need = ((((uint32_t) lq + 1u) >> 1) + 3u) >> 2, qw_need = ((uint32_t) lq + 7u) >> 3;
+                const bool staged = soff >= d.sw0 && soff + sw_need <= d.sw1 && qoff >= d.qw0 && qoff + qw_need <= d.qw1;
+                const unsigned char *sb = sseq + (size_t)(soff - d.sw0) * 4u, *qb = squal + (size_t)(qoff - d.qw0) * 8u;
+                const uint32_t *own_bm = rc.wantG ? bmG : bmC, *opp_bm = rc.wantG ? bmC : bmG;
+                int p = pos, q = 0;
+                for (uint32_t k = k0; k < k1; ++k) {
+                    const uint32_t c = (k == k0) ? c0 : __ldg(R.cigar + k), op = c & 15u; const int len = (int)(c >> 4);
+                    if (op == 0 || op == 7 || op == 8) {
+                        // reference interval of this op clipped to the window and to the kept query range
+                        const int a = max(max(p, w0i), p + (rc.lo - q)), b = min(min(p + len, w0i + own), p + (rc.hi - q));
+                        if (b > a) {
+                            const int ra = a - w0i, rb = b - w0i;
+                            for (int wi = ra >> 5; wi <= (rb - 1) >> 5; ++wi) {
+                                unsigned m = own_bm[wi + 1], mo = (MODE == 1) ? opp_bm[wi + 1] : 0u;
+                                unsigned keep = 0xffffffffu;
+                                if (wi == (ra >> 5)) keep &= 0xffffffffu << (ra & 31);
+                                if (wi == ((rb - 1) >> 5)) keep &= 0xffffffffu >> (31 - ((rb - 1) & 31));
+                                m &= keep; mo &= keep;
+                                unsigned any = m | mo;
+                                while (any) {
+                                    const int bit = __ffs(any) - 1; any &= any - 1;
+                                    const int rp = w0i + (wi << 5) + bit, qi = q + (rp - p);
+                                    unsigned bb, ql;
+                                    if (staged) { const unsigned byte = sb[qi >> 1]; bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4); ql = qb[qi]; }
+                                    else { bb = dev_base(R.seq, soff, qi); ql = dev_qual(R.qual, qoff, qi); }
+                                    const bool is_own = (m >> bit) & 1u;
+                                    eval_hit<MODE>(A, rc, cnt, W, w0i, rp, qi, bb, ql, is_own ? rc.wantG : !rc.wantG);
+                                }
+                            }
+                        }
+                        p += len; q += len;
+                    } else if (op == 1 || op == 4) q += len;
+                    else if (op == 2 || op == 3) p += len;
+                }
+            }
+            __syncthreads();                                           // staging buffers free for the next batch
+        }
+    }
+    __syncthreads();
+
+    // ---- epilogue -------------------------------------------------------------------------------------
+    if (MODE == 2) {
+        for (uint32_t t = tid; t < 4u * 2u * MB_SM_Q * 2u; t += ST_THREADS) {
+            uint32_t v = cnt[t];
+            if (v) { uint32_t sr = t / (MB_SM_Q * 2), rest = t % (MB_SM_Q * 2); atomicAdd(A.hist + (size_t) sr * MD_MBIAS_MAXLEN * 2 + rest, v); }
+        }
+        return;
+    }
+    __shared__ uint32_t s_warp_tot[ST_THREADS / 32], s_base;
+    uint32_t total_mine = 0;
+    // this thread owns window offsets [16*tid + 4096*pass, +16)
+    auto reportable = [&](uint32_t t16) -> unsigned {                   // 16-bit mask of columns to report
+        const uint32_t wi = (t16 >> 5) + 1, sh = t16 & 31u;
+        unsigned sites = ((bmC[wi] | bmG[wi]) >> sh) & 0xffffu, out = 0;
+        while (sites) {
+            const int k = __ffs(sites) - 1; sites &= sites - 1;
+            const uint32_t t = t16 + k;
+            bool excl = false;
+            if (MODE == 1) {
+                const uint32_t noff = cnt[2 * W + t], nvar = cnt[3 * W + t];
+                excl = A.P.minOppositeDepth > 0 && noff >= (uint32_t) A.P.minOppositeDepth && ((double) nvar) / ((double) noff) >= A.P.maxVariantFrac;
+            }
+            if (excl) out |= 0x10000u << k;
+            if (excl || cnt[t] + cnt[W + t]) out |= 1u << k;
+        }
+        return out;
+    };
+    unsigned rep = 0;                                                   // W = 4096: a single pass; kept general with a loop below
+    const uint32_t npass = (W + 16u * ST_THREADS - 1) / (16u * ST_THREADS);
+    for (uint32_t pass = 0; pass < npass; ++pass) { const uint32_t t16 = pass * 16u * ST_THREADS + 16u * tid; if (t16 < W) total_mine += __popc(reportable(t16) & 0xffffu); }
+    uint32_t incl = total_mine;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t tot = 0;
+        for (int k = 0; k < ST_THREADS / 32; ++k) { uint32_t v = s_warp_tot[k]; s_warp_tot[k] = tot; tot += v; }
+        unsigned long long base = tot ? atomicAdd((unsigned long long *)(A.counters + C_NCALLS), (unsigned long long) tot) : 0ull;
+        if (base + tot > A.cap) { atomicExch(A.counters + C_OVERFLOW, 1u); s_base = 0xffffffffu; }
+        else s_base = (uint32_t) base;
+        A.dir[w] = make_uint2((uint32_t) base, tot);
+    }
+    __syncthreads();
+    if (s_base == 0xffffffffu) return;
+    // NB: with more than one pass the per-thread order would interleave passes; W is fixed at 16 * ST_THREADS by the host
+    uint32_t o = s_base + s_warp_tot[warp] + (incl - total_mine);
+    {
+        const uint32_t t16 = 16u * tid;
+        rep = reportable(t16);
+        const uint32_t wi = (t16 >> 5) + 1, sh = t16 & 31u;
+        const unsigned g16 = (bmG[wi] >> sh) & 0xffffu, a16 = (bmT0[wi] >> sh) & 0xffffu, b16 = (bmT1[wi] >> sh) & 0xffffu;
+        unsigned r16 = rep & 0xffffu;
+        while (r16) {
+            const int k = __ffs(r16) - 1; r16 &= r16 - 1;
+            const uint32_t t = t16 + k;
+            md_call c; c.pos = (uint32_t)(w0 + t); c.nmeth = cnt[t]; c.nunmeth = cnt[W + t];
+            c.info = (((a16 >> k) & 1u) ? 0u : ((b16 >> k) & 1u) ? 1u : 2u) | (((g16 >> k) & 1u) ? 4u : 0u) | (((rep >> (16 + k)) & 1u) ? 8u : 0u);
+            A.calls[o++] = c;
+        }
+    }
+}
+
 // K5/K6: put the per-window segments into position order on the device (exclusive scan of the directory
 // counts by one CTA, then a segment copy), so the D2H transfer lands in the caller's buffer already sorted.
 __global__ void __launch_bounds__(1024) dir_scan_kernel(uint2 *dir, uint32_t n_win, uint32_t *sorted_off) {
@@ -606,22 +899,31 @@ struct md_dev_reads {
     DevBuf arena; DevReads view; uint32_t n = 0;
 };
 
-struct md_ctx {
-    int device = 0; md_config cfg; KParams kp;
+#define MD_NLANES 3
+// One lane = one stream with its own staging arena, scratch and output buffers, so that the copy of tile k+1,
+// the kernels of tile k and the read-back of tile k-1 overlap (md_submit_tile / md_collect_tile).
+struct Lane {
     cudaStream_t stream = nullptr;
-    std::map<int32_t, Contig> contigs;
-    md_dev_reads staged;                 // device copy of the host tile of md_extract_tile / md_mbias_tile
+    md_dev_reads staged;                 // device copy of the host tile
     DevBuf rend, info, slot_of, mate, keys, hcnt, hidx, win, dir, calls, counters, sorted, sorted_off;
-    uint32_t *d_hist = nullptr; int32_t *d_lens = nullptr;
-    uint64_t launches = 0;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float timing[5] = {0, 0, 0, 0, 0};
-    // last extract state (for collect / fetch)
     uint32_t last_nwin = 0; uint64_t last_ncalls = 0; bool pending = false; md_tile_stats last_stats;
-    uint32_t h_counters[C_N];
-    uint32_t W = 4096;
+    uint32_t *h_counters = nullptr;      // page-locked
     md_tile_desc last_tile; DevReads last_reads; bool last_mbias = false;
 };
+
+struct md_ctx {
+    int device = 0; md_config cfg; KParams kp;
+    std::map<int32_t, Contig> contigs;
+    Lane lanes[MD_NLANES]; int rr = 0; Lane *last = nullptr;
+    uint32_t *d_hist = nullptr; int32_t *d_lens = nullptr;
+    uint64_t launches = 0;
+    uint32_t W = 4096;
+    int count_variant = 3;               // 3: count_stream (TMA-staged, thread per alignment); 2: count_kernel (warp / half-warp per alignment)
+};
+
+static void sync_all(md_ctx *c) { for (int k = 0; k < MD_NLANES; ++k) if (c->lanes[k].stream) cudaStreamSynchronize(c->lanes[k].stream); }
 
 static void fill_kparams(const md_config *c, KParams &k) {
     memset(&k, 0, sizeof k);
@@ -642,40 +944,54 @@ extern "C" md_ctx *md_create(const md_config *cfg, int device) {
     CKN(cudaSetDevice(device));
     md_ctx *c = new md_ctx();
     c->device = device; c->cfg = *cfg; fill_kparams(cfg, c->kp);
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; delete c; return nullptr; }
-    for (int i = 0; i < 5; ++i) cudaEventCreate(&c->ev[i]);
+    if (const char *v = getenv("MD_COUNT_KERNEL")) { int k = atoi(v); if (k == 2 || k == 3) c->count_variant = k; }
+    for (int k = 0; k < MD_NLANES; ++k) {
+        Lane *L = &c->lanes[k];
+        if (cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; delete c; return nullptr; }
+        for (int i = 0; i < 5; ++i) cudaEventCreate(&L->ev[i]);
+        if (cudaMallocHost((void **) &L->h_counters, C_N * 4) != cudaSuccess) { g_err = "cudaMallocHost failed"; delete c; return nullptr; }
+    }
+    Lane *L = &c->lanes[0]; c->last = L;
     size_t hb = (size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2 * sizeof(uint32_t);
     if (cudaMalloc(&c->d_hist, hb) != cudaSuccess || cudaMalloc(&c->d_lens, 4 * sizeof(int32_t)) != cudaSuccess) { g_err = "cudaMalloc(hist) failed"; delete c; return nullptr; }
-    cudaMemsetAsync(c->d_hist, 0, hb, c->stream); cudaMemsetAsync(c->d_lens, 0, 4 * sizeof(int32_t), c->stream);
+    cudaMemsetAsync(c->d_hist, 0, hb, L->stream); cudaMemsetAsync(c->d_lens, 0, 4 * sizeof(int32_t), L->stream);
     cudaFuncSetAttribute(count_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaStreamSynchronize(c->stream);
+    cudaFuncSetAttribute(count_stream<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) stream_layout(4096, 0).total);
+    cudaFuncSetAttribute(count_stream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) stream_layout(4096, 1).total);
+    cudaFuncSetAttribute(count_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) stream_layout(4096, 2).total);
+    cudaStreamSynchronize(L->stream);
     return c;
 }
 
 extern "C" void md_destroy(md_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    sync_all(c);
     for (auto &kv : c->contigs) { cudaFree(kv.second.d_seq); if (kv.second.d_bounds) cudaFree(kv.second.d_bounds); }
-    c->staged.arena.release();
-    DevBuf *bufs[] = {&c->rend, &c->info, &c->slot_of, &c->mate, &c->keys, &c->hcnt, &c->hidx, &c->win, &c->dir, &c->calls, &c->counters, &c->sorted, &c->sorted_off};
-    for (DevBuf *b : bufs) b->release();
+    for (int k = 0; k < MD_NLANES; ++k) {
+        Lane *L = &c->lanes[k];
+        L->staged.arena.release();
+        DevBuf *bufs[] = {&L->rend, &L->info, &L->slot_of, &L->mate, &L->keys, &L->hcnt, &L->hidx, &L->win, &L->dir, &L->calls, &L->counters, &L->sorted, &L->sorted_off};
+        for (DevBuf *b : bufs) b->release();
+        for (int i = 0; i < 5; ++i) if (L->ev[i]) cudaEventDestroy(L->ev[i]);
+        if (L->h_counters) cudaFreeHost(L->h_counters);
+        if (L->stream) cudaStreamDestroy(L->stream);
+    }
     if (c->d_hist) cudaFree(c->d_hist);
     if (c->d_lens) cudaFree(c->d_lens);
-    for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
 extern "C" int md_load_contig(md_ctx *c, int32_t tid, const char *seq, uint32_t len) {
     CK(cudaSetDevice(c->device));
     md_drop_contig(c, tid);
+    Lane *L = &c->lanes[0];
     Contig g; g.len = len;
     CK(cudaMalloc(&g.d_seq, (size_t) len + 16));
-    CK(cudaMemcpyAsync(g.d_seq, seq, len, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpyAsync(g.d_seq, seq, len, cudaMemcpyHostToDevice, L->stream));
+    CK(cudaStreamSynchronize(L->stream));
     c->contigs[tid] = g;
     return 0;
 }
@@ -684,7 +1000,7 @@ extern "C" int md_drop_contig(md_ctx *c, int32_t tid) {
     auto it = c->contigs.find(tid);
     if (it == c->contigs.end()) return 0;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    sync_all(c);
     cudaFree(it->second.d_seq);
     if (it->second.d_bounds) cudaFree(it->second.d_bounds);
     c->contigs.erase(it);
@@ -695,10 +1011,11 @@ extern "C" int md_set_mbias_chunks(md_ctx *c, int32_t tid, const uint32_t *bound
     auto it = c->contigs.find(tid);
     if (it == c->contigs.end()) { g_err = "md_set_mbias_chunks: contig not loaded"; return -2; }
     CK(cudaSetDevice(c->device));
-    if (it->second.d_bounds) { cudaStreamSynchronize(c->stream); cudaFree(it->second.d_bounds); it->second.d_bounds = nullptr; }
+    Lane *L = &c->lanes[0];
+    if (it->second.d_bounds) { sync_all(c); cudaFree(it->second.d_bounds); it->second.d_bounds = nullptr; }
     CK(cudaMalloc(&it->second.d_bounds, ((size_t) n_chunks + 1) * sizeof(uint32_t)));
-    CK(cudaMemcpyAsync(it->second.d_bounds, bounds, ((size_t) n_chunks + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpyAsync(it->second.d_bounds, bounds, ((size_t) n_chunks + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, L->stream));
+    CK(cudaStreamSynchronize(L->stream));
     it->second.n_chunks = n_chunks;
     return 0;
 }
@@ -706,7 +1023,8 @@ extern "C" int md_set_mbias_chunks(md_ctx *c, int32_t tid, const uint32_t *bound
 // ---- staging a host tile into one device arena ---------------------------------------------------
 static size_t al256(size_t x) { return (x + 255) & ~(size_t) 255; }
 
-static int stage_reads(md_ctx *c, md_dev_reads &d, const md_reads_soa *r) {
+static int stage_reads(md_ctx *c, Lane *L, md_dev_reads &d, const md_reads_soa *r) {
+    (void) c;
     const size_t n = r->n_reads;
     size_t sz[12] = {n * 4, n * 2, n, n, n * 4, (n + 1) * 4, n * 4, n * 4, n * 8, (size_t) r->n_cigar_ops * 4, (size_t) r->seq_words * 4, (size_t) r->qual_words * 8};
     const void *src[12] = {r->pos, r->flag, r->mapq, r->aux, r->l_qseq, r->cigar_off, r->seq_off, r->qual_off, r->frag_key, r->cigar, r->seq, r->qual};
@@ -714,9 +1032,9 @@ static int stage_reads(md_ctx *c, md_dev_reads &d, const md_reads_soa *r) {
     for (int k = 0; k < 12; ++k) { off[k] = tot; tot += al256(sz[k] + 16); }
     if (d.arena.reserve(tot) != 0) return -100;
     unsigned char *base = (unsigned char *) d.arena.p;
-    for (int k = 0; k < 12; ++k) if (sz[k]) CK(cudaMemcpyAsync(base + off[k], src[k], sz[k], cudaMemcpyHostToDevice, c->stream));
+    for (int k = 0; k < 12; ++k) if (sz[k]) CK(cudaMemcpyAsync(base + off[k], src[k], sz[k], cudaMemcpyHostToDevice, L->stream));
     DevReads &v = d.view;
-    v.n = (uint32_t) n;
+    v.n = (uint32_t) n; v.seq_words = (uint32_t) r->seq_words; v.qual_words = (uint32_t) r->qual_words;
     v.pos = (const int32_t *)(base + off[0]); v.flag = (const uint16_t *)(base + off[1]); v.mapq = base + off[2]; v.aux = base + off[3];
     v.l_qseq = (const uint32_t *)(base + off[4]); v.cigar_off = (const uint32_t *)(base + off[5]); v.seq_off = (const uint32_t *)(base + off[6]);
     v.qual_off = (const uint32_t *)(base + off[7]); v.frag_key = (const uint64_t *)(base + off[8]); v.cigar = (const uint32_t *)(base + off[9]);
@@ -728,30 +1046,35 @@ static int stage_reads(md_ctx *c, md_dev_reads &d, const md_reads_soa *r) {
 extern "C" md_dev_reads *md_upload_reads(md_ctx *c, const md_reads_soa *reads) {
     CKN(cudaSetDevice(c->device));
     md_dev_reads *d = new md_dev_reads();
-    if (stage_reads(c, *d, reads) != 0) { delete d; return nullptr; }
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { g_err = "upload sync failed"; d->arena.release(); delete d; return nullptr; }
+    Lane *L = &c->lanes[0];
+    if (stage_reads(c, L, *d, reads) != 0) { delete d; return nullptr; }
+    if (cudaStreamSynchronize(L->stream) != cudaSuccess) { g_err = "upload sync failed"; d->arena.release(); delete d; return nullptr; }
     return d;
 }
-extern "C" void md_free_reads(md_ctx *c, md_dev_reads *d) { if (!d) return; cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); d->arena.release(); delete d; }
+extern "C" void md_free_reads(md_ctx *c, md_dev_reads *d) { if (!d) return; cudaSetDevice(c->device); sync_all(c); d->arena.release(); delete d; }
 
 
 // ---- K4 launch (also used to re-run a tile after the host resolved duplicate query names) -------
-static int launch_count(md_ctx *c, const Contig &g, const DevReads &R, const KParams &kp, uint32_t beg, uint32_t end, uint32_t n_win, unsigned long long cap_calls, bool mbias) {
+static int launch_count(md_ctx *c, Lane *L, const Contig &g, const DevReads &R, const KParams &kp, uint32_t beg, uint32_t end, uint32_t n_win, unsigned long long cap_calls, bool mbias) {
     if (!n_win) return 0;
     const uint32_t W = c->W;
-    cudaStream_t s = c->stream;
+    cudaStream_t s = L->stream;
     CountArgs A; memset(&A, 0, sizeof A);
-    A.R = R; A.P = kp; A.rend = (const int32_t *) c->rend.p; A.info = (const uint8_t *) c->info.p; A.mate = (const int32_t *) c->mate.p; A.win = (const uint2 *) c->win.p;
+    A.R = R; A.P = kp; A.rend = (const int32_t *) L->rend.p; A.info = (const uint8_t *) L->info.p; A.mate = (const int32_t *) L->mate.p; A.win = (const uint2 *) L->win.p;
     A.ref = g.d_seq; A.reflen = g.len; A.beg = beg; A.end = end; A.W = W; A.chunk_bounds = g.d_bounds; A.n_chunks = g.n_chunks;
-    A.calls = (md_call *) c->calls.p; A.cap = cap_calls; A.dir = (uint2 *) c->dir.p; A.counters = (uint32_t *) c->counters.p; A.hist = c->d_hist; A.lens = c->d_lens;
+    A.calls = (md_call *) L->calls.p; A.cap = cap_calls; A.dir = (uint2 *) L->dir.p; A.counters = (uint32_t *) L->counters.p; A.hist = c->d_hist; A.lens = c->d_lens;
     const size_t bm = 2 * ((size_t)(W >> 5) + 2) * 4;
-    if (mbias) { size_t sm = 2 * (size_t) W + 16 + bm + (size_t) 4 * 2 * MB_SM_Q * 2 * 4; count_kernel<2><<<n_win, 256, sm, s>>>(A); }
+    if (c->count_variant == 3 && W == 16 * ST_THREADS) {
+        if (mbias) count_stream<2><<<n_win, ST_THREADS, stream_layout(W, 2).total, s>>>(A);
+        else if (kp.minOppositeDepth > 0) count_stream<1><<<n_win, ST_THREADS, stream_layout(W, 1).total, s>>>(A);
+        else count_stream<0><<<n_win, ST_THREADS, stream_layout(W, 0).total, s>>>(A);
+    } else if (mbias) { size_t sm = 2 * (size_t) W + 16 + bm + (size_t) 4 * 2 * MB_SM_Q * 2 * 4; count_kernel<2><<<n_win, 256, sm, s>>>(A); }
     else if (kp.minOppositeDepth > 0) { size_t sm = 2 * (size_t) W + 16 + bm + (size_t) 16 * W; count_kernel<1><<<n_win, 256, sm, s>>>(A); }
     else { size_t sm = 2 * (size_t) W + 16 + bm + (size_t) 8 * W; count_kernel<0><<<n_win, 256, sm, s>>>(A); }
     c->launches += 1;
     if (!mbias) {
-        dir_scan_kernel<<<1, 1024, 0, s>>>((uint2 *) c->dir.p, n_win, (uint32_t *) c->sorted_off.p);
-        gather_kernel<<<n_win, 128, 0, s>>>((const md_call *) c->calls.p, (const uint2 *) c->dir.p, (const uint32_t *) c->sorted_off.p, (md_call *) c->sorted.p);
+        dir_scan_kernel<<<1, 1024, 0, s>>>((uint2 *) L->dir.p, n_win, (uint32_t *) L->sorted_off.p);
+        gather_kernel<<<n_win, 128, 0, s>>>((const md_call *) L->calls.p, (const uint2 *) L->dir.p, (const uint32_t *) L->sorted_off.p, (md_call *) L->sorted.p);
         c->launches += 2;
     }
     CK(cudaGetLastError());
@@ -759,7 +1082,7 @@ static int launch_count(md_ctx *c, const Contig &g, const DevReads &R, const KPa
 }
 
 // ---- kernel pipeline on a device-resident tile ---------------------------------------------------
-static int run_pipeline(md_ctx *c, const md_tile_desc *t, const DevReads &R, bool mbias) {
+static int run_pipeline(md_ctx *c, Lane *L, const md_tile_desc *t, const DevReads &R, bool mbias) {
     auto it = c->contigs.find(t->tid);
     if (it == c->contigs.end()) { g_err = "tile refers to a contig that was not loaded (md_load_contig)"; return -2; }
     const Contig &g = it->second;
@@ -770,34 +1093,34 @@ static int run_pipeline(md_ctx *c, const md_tile_desc *t, const DevReads &R, boo
     const uint32_t n_win = (end - beg + W - 1) / W;
     uint32_t cap_pow2 = 1024; while (cap_pow2 < 2 * (size_t) n + 2) cap_pow2 <<= 1;
     const bool need_hash = !mbias && !c->kp.noOverlap;
-    if (c->rend.reserve((size_t) n * 4 + 4) || c->info.reserve((size_t) n + 4) || c->slot_of.reserve((size_t) n * 4 + 4) || c->mate.reserve((size_t) n * 4 + 4) ||
-        c->win.reserve((size_t) n_win * 8 + 8) || c->dir.reserve((size_t) n_win * 8 + 8) || c->counters.reserve(C_N * 4)) return -100;
-    if (need_hash && (c->keys.reserve((size_t) cap_pow2 * 8) || c->hcnt.reserve((size_t) cap_pow2 * 4) || c->hidx.reserve((size_t) cap_pow2 * 8))) return -100;
+    if (L->rend.reserve((size_t) n * 4 + 4) || L->info.reserve((size_t) n + 4) || L->slot_of.reserve((size_t) n * 4 + 4) || L->mate.reserve((size_t) n * 4 + 4) ||
+        L->win.reserve((size_t) n_win * 8 + 8) || L->dir.reserve((size_t) n_win * 8 + 8) || L->counters.reserve(C_N * 4)) return -100;
+    if (need_hash && (L->keys.reserve((size_t) cap_pow2 * 8) || L->hcnt.reserve((size_t) cap_pow2 * 4) || L->hidx.reserve((size_t) cap_pow2 * 8))) return -100;
     const unsigned long long cap_calls = (unsigned long long)(end - beg) + 16;
-    if (!mbias && (c->calls.reserve((size_t) cap_calls * sizeof(md_call)) || c->sorted.reserve((size_t) cap_calls * sizeof(md_call)) || c->sorted_off.reserve((size_t) n_win * 4 + 4))) return -100;
-    cudaStream_t s = c->stream;
-    CK(cudaEventRecord(c->ev[1], s));
-    CK(cudaMemsetAsync(c->counters.p, 0, C_N * 4, s));
-    HashTab T; T.keys = (unsigned long long *) c->keys.p; T.cnt = (uint32_t *) c->hcnt.p; T.idx = (uint32_t *) c->hidx.p; T.mask = cap_pow2 - 1;
-    if (need_hash) { CK(cudaMemsetAsync(c->keys.p, 0, (size_t) cap_pow2 * 8, s)); CK(cudaMemsetAsync(c->hcnt.p, 0, (size_t) cap_pow2 * 4, s)); }
+    if (!mbias && (L->calls.reserve((size_t) cap_calls * sizeof(md_call)) || L->sorted.reserve((size_t) cap_calls * sizeof(md_call)) || L->sorted_off.reserve((size_t) n_win * 4 + 4))) return -100;
+    cudaStream_t s = L->stream;
+    CK(cudaEventRecord(L->ev[1], s));
+    CK(cudaMemsetAsync(L->counters.p, 0, C_N * 4, s));
+    HashTab T; T.keys = (unsigned long long *) L->keys.p; T.cnt = (uint32_t *) L->hcnt.p; T.idx = (uint32_t *) L->hidx.p; T.mask = cap_pow2 - 1;
+    if (need_hash) { CK(cudaMemsetAsync(L->keys.p, 0, (size_t) cap_pow2 * 8, s)); CK(cudaMemsetAsync(L->hcnt.p, 0, (size_t) cap_pow2 * 4, s)); }
     KParams kp = c->kp; if (mbias) kp.noOverlap = 1;
     if (n) {
         const uint32_t gb = (n + 255) / 256;
-        prep_kernel<<<gb, 256, 0, s>>>(R, kp, (int32_t *) c->rend.p, (uint8_t *) c->info.p, T, (uint32_t *) c->slot_of.p, (uint32_t *) c->counters.p);
-        pair_kernel<<<gb, 256, 0, s>>>(R, (const int32_t *) c->rend.p, (const uint8_t *) c->info.p, T, (const uint32_t *) c->slot_of.p, (int32_t *) c->mate.p, (uint32_t *) c->counters.p);
+        prep_kernel<<<gb, 256, 0, s>>>(R, kp, (int32_t *) L->rend.p, (uint8_t *) L->info.p, T, (uint32_t *) L->slot_of.p, (uint32_t *) L->counters.p);
+        pair_kernel<<<gb, 256, 0, s>>>(R, (const int32_t *) L->rend.p, (const uint8_t *) L->info.p, T, (const uint32_t *) L->slot_of.p, (int32_t *) L->mate.p, (uint32_t *) L->counters.p);
         c->launches += 2;
     }
     if (n_win) {
-        window_kernel<<<(n_win + 255) / 256, 256, 0, s>>>(R.pos, n, beg, W, n_win, (const uint32_t *) c->counters.p, (uint2 *) c->win.p);
+        window_kernel<<<(n_win + 255) / 256, 256, 0, s>>>(R.pos, n, beg, W, n_win, (const uint32_t *) L->counters.p, (uint2 *) L->win.p);
         c->launches += 1;
     }
-    CK(cudaEventRecord(c->ev[2], s));
-    c->last_tile = *t; c->last_reads = R; c->last_mbias = mbias;
-    int rc = launch_count(c, g, R, kp, beg, end, n_win, cap_calls, mbias);
+    CK(cudaEventRecord(L->ev[2], s));
+    L->last_tile = *t; L->last_reads = R; L->last_mbias = mbias;
+    int rc = launch_count(c, L, g, R, kp, beg, end, n_win, cap_calls, mbias);
     if (rc) return rc;
-    CK(cudaEventRecord(c->ev[3], s));
+    CK(cudaEventRecord(L->ev[3], s));
     CK(cudaGetLastError());
-    c->last_nwin = mbias ? 0 : n_win;
+    L->last_nwin = mbias ? 0 : n_win;
     return 0;
 }
 
@@ -811,15 +1134,15 @@ static int run_pipeline(md_ctx *c, const md_tile_desc *t, const DevReads &R, boo
 // which removes the name; a buffered record is dropped (and whatever sits under its name with it) once
 // a record starting beyond its end has been pushed.  The count kernel is then run again.
 #include <unordered_map>
-static int resolve_duplicates_on_host(md_ctx *c) {
-    const DevReads &R = c->last_reads;
+static int resolve_duplicates_on_host(md_ctx *c, Lane *L) {
+    const DevReads &R = L->last_reads;
     const uint32_t n = R.n;
     std::vector<int32_t> pos(n), rend(n), mate(n, -1); std::vector<uint16_t> flag(n); std::vector<uint8_t> info(n); std::vector<uint64_t> key(n);
-    cudaStream_t s = c->stream;
+    cudaStream_t s = L->stream;
     CK(cudaMemcpyAsync(pos.data(), R.pos, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(rend.data(), c->rend.p, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(rend.data(), L->rend.p, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(flag.data(), R.flag, (size_t) n * 2, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(info.data(), c->info.p, (size_t) n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(info.data(), L->info.p, (size_t) n, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(key.data(), R.frag_key, (size_t) n * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     std::vector<std::pair<int32_t, uint32_t>> by_end;
@@ -841,81 +1164,97 @@ static int resolve_duplicates_on_host(md_ctx *c) {
         }
         while (ev < by_end.size() && by_end[ev].first < pos[i]) { uint32_t x = by_end[ev].second; if (x < i) stored.erase(key[x]); ++ev; }
     }
-    CK(cudaMemcpyAsync(c->mate.p, mate.data(), (size_t) n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(L->mate.p, mate.data(), (size_t) n * 4, cudaMemcpyHostToDevice, s));
     // run the count stage again from a clean output cursor
-    CK(cudaMemsetAsync((uint32_t *) c->counters.p + C_NCALLS, 0, 8, s));
-    auto it = c->contigs.find(c->last_tile.tid);
+    CK(cudaMemsetAsync((uint32_t *) L->counters.p + C_NCALLS, 0, 8, s));
+    auto it = c->contigs.find(L->last_tile.tid);
     if (it == c->contigs.end()) { g_err = "internal: contig vanished"; return -3; }
     const Contig &g = it->second;
-    uint32_t beg = c->last_tile.beg, end = std::min(c->last_tile.end, g.len);
+    uint32_t beg = L->last_tile.beg, end = std::min(L->last_tile.end, g.len);
     if (beg > end) beg = end;
     const uint32_t n_win = (end - beg + c->W - 1) / c->W;
     KParams kp = c->kp;
-    int rc = launch_count(c, g, R, kp, beg, end, n_win, (unsigned long long)(end - beg) + 16, false);
+    int rc = launch_count(c, L, g, R, kp, beg, end, n_win, (unsigned long long)(end - beg) + 16, false);
     if (rc) return rc;
     CK(cudaStreamSynchronize(s));
     return 0;
 }
 
-static int finish_counters(md_ctx *c, md_tile_stats *st) {
-    CK(cudaMemcpyAsync(c->h_counters, c->counters.p, C_N * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (c->h_counters[C_MULTI] && !c->last_mbias && !c->h_counters[C_OVERFLOW]) {
-        int rc = resolve_duplicates_on_host(c);
+static int finish_counters(md_ctx *c, Lane *L, md_tile_stats *st) {
+    CK(cudaMemcpyAsync(L->h_counters, L->counters.p, C_N * 4, cudaMemcpyDeviceToHost, L->stream));
+    CK(cudaStreamSynchronize(L->stream));
+    if (L->h_counters[C_MULTI] && !L->last_mbias && !L->h_counters[C_OVERFLOW]) {
+        int rc = resolve_duplicates_on_host(c, L);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(c->h_counters, c->counters.p, C_N * 4, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemcpyAsync(L->h_counters, L->counters.p, C_N * 4, cudaMemcpyDeviceToHost, L->stream));
+        CK(cudaStreamSynchronize(L->stream));
     }
-    unsigned long long ncalls; memcpy(&ncalls, &c->h_counters[C_NCALLS], 8);   // C_NCALLS is 8-byte aligned (index 4)
-    if (c->h_counters[C_OVERFLOW]) { g_err = "internal: call buffer overflow"; return -3; }
-    c->last_ncalls = ncalls;
+    unsigned long long ncalls; memcpy(&ncalls, &L->h_counters[C_NCALLS], 8);   // C_NCALLS is 8-byte aligned (index 4)
+    if (L->h_counters[C_OVERFLOW]) { g_err = "internal: call buffer overflow"; return -3; }
+    L->last_ncalls = ncalls;
     md_tile_stats s; memset(&s, 0, sizeof s);
-    s.n_calls = ncalls; s.n_required = ncalls; s.n_admitted = c->h_counters[C_ADMIT]; s.n_pairs = c->h_counters[C_PAIRED] / 2; s.n_multi = c->h_counters[C_MULTI];
-    c->last_stats = s;
+    s.n_calls = ncalls; s.n_required = ncalls; s.n_admitted = L->h_counters[C_ADMIT]; s.n_pairs = L->h_counters[C_PAIRED] / 2; s.n_multi = L->h_counters[C_MULTI];
+    L->last_stats = s;
     if (st) *st = s;
     return 0;
 }
 
 // the records are already in position order on the device (dir_scan_kernel + gather_kernel)
-static int fetch_sorted(md_ctx *c, md_call *out, uint64_t capacity, uint64_t *n_out) {
-    const uint64_t n = c->last_ncalls;
+static int fetch_sorted(md_ctx *c, Lane *L, md_call *out, uint64_t capacity, uint64_t *n_out) {
+    (void) c;
+    const uint64_t n = L->last_ncalls;
     if (n_out) *n_out = n;
     if (n > capacity) { g_err = "md_call capacity too small"; return -1; }
     if (n == 0) return 0;
-    CK(cudaMemcpyAsync(out, c->sorted.p, n * sizeof(md_call), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpyAsync(out, L->sorted.p, n * sizeof(md_call), cudaMemcpyDeviceToHost, L->stream));
+    CK(cudaStreamSynchronize(L->stream));
     return 0;
 }
 
-static void collect_timing(md_ctx *c) {
+static void collect_timing(Lane *L) {
     float t;
-    for (int k = 0; k < 4; ++k) { t = 0; if (cudaEventElapsedTime(&t, c->ev[k], c->ev[k + 1]) == cudaSuccess) c->timing[k] = t; else c->timing[k] = 0; }
-    t = 0; if (cudaEventElapsedTime(&t, c->ev[0], c->ev[4]) == cudaSuccess) c->timing[4] = t;
+    for (int k = 0; k < 4; ++k) { t = 0; if (cudaEventElapsedTime(&t, L->ev[k], L->ev[k + 1]) == cudaSuccess) L->timing[k] = t; else L->timing[k] = 0; }
+    t = 0; if (cudaEventElapsedTime(&t, L->ev[0], L->ev[4]) == cudaSuccess) L->timing[4] = t;
+}
+
+// Lane selection: round-robin over the lanes that have nothing in flight.
+static Lane *free_lane(md_ctx *c, int *ticket) {
+    for (int k = 0; k < MD_NLANES; ++k) {
+        int idx = (c->rr + k) % MD_NLANES;
+        if (!c->lanes[idx].pending) { c->rr = (idx + 1) % MD_NLANES; *ticket = idx; return &c->lanes[idx]; }
+    }
+    return nullptr;
 }
 
 extern "C" int md_submit_tile(md_ctx *c, const md_tile_desc *tile, const md_reads_soa *reads) {
     CK(cudaSetDevice(c->device));
-    if (c->pending) { g_err = "md_submit_tile: a tile is already in flight on this context (collect it first)"; return -4; }
-    CK(cudaEventRecord(c->ev[0], c->stream));
-    int rc = stage_reads(c, c->staged, reads);
+    int ticket = -1;
+    Lane *L = free_lane(c, &ticket);
+    if (!L) { g_err = "md_submit_tile: all lanes are busy (collect a ticket first)"; return -4; }
+    CK(cudaEventRecord(L->ev[0], L->stream));
+    int rc = stage_reads(c, L, L->staged, reads);
     if (rc) return rc;
-    rc = run_pipeline(c, tile, c->staged.view, false);
+    rc = run_pipeline(c, L, tile, L->staged.view, false);
     if (rc) return rc;
-    c->pending = true;
-    return 0;
+    // queue the small read-backs now so that collect only has to wait
+    CK(cudaMemcpyAsync(L->h_counters, L->counters.p, C_N * 4, cudaMemcpyDeviceToHost, L->stream));
+    L->pending = true;
+    c->last = L;
+    return ticket;
 }
 
 extern "C" int md_collect_tile(md_ctx *c, int ticket, md_call *calls, uint64_t capacity, md_tile_stats *stats) {
-    (void) ticket;
     CK(cudaSetDevice(c->device));
-    if (!c->pending) { g_err = "md_collect_tile: nothing in flight"; return -4; }
-    c->pending = false;
-    int rc = finish_counters(c, stats);
+    if (ticket < 0 || ticket >= MD_NLANES || !c->lanes[ticket].pending) { g_err = "md_collect_tile: bad ticket / nothing in flight"; return -4; }
+    Lane *L = &c->lanes[ticket];
+    L->pending = false;
+    int rc = finish_counters(c, L, stats);
     if (rc) return rc;
-    rc = fetch_sorted(c, calls, capacity, nullptr);
-    CK(cudaEventRecord(c->ev[4], c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    collect_timing(c);
+    rc = fetch_sorted(c, L, calls, capacity, nullptr);
+    CK(cudaEventRecord(L->ev[4], L->stream));
+    CK(cudaStreamSynchronize(L->stream));
+    collect_timing(L);
+    c->last = L;
     return rc;
 }
 
@@ -927,65 +1266,80 @@ extern "C" int md_extract_tile(md_ctx *c, const md_tile_desc *tile, const md_rea
 
 extern "C" int md_extract_tile_device(md_ctx *c, const md_tile_desc *tile, const md_dev_reads *reads, md_tile_stats *stats) {
     CK(cudaSetDevice(c->device));
-    CK(cudaEventRecord(c->ev[0], c->stream));
-    int rc = run_pipeline(c, tile, reads->view, false);
+    Lane *L = &c->lanes[0];
+    if (L->pending) { g_err = "md_extract_tile_device: lane 0 has a tile in flight"; return -4; }
+    CK(cudaEventRecord(L->ev[0], L->stream));
+    int rc = run_pipeline(c, L, tile, reads->view, false);
     if (rc) return rc;
-    rc = finish_counters(c, stats);
-    CK(cudaEventRecord(c->ev[4], c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    collect_timing(c);
+    rc = finish_counters(c, L, stats);
+    CK(cudaEventRecord(L->ev[4], L->stream));
+    CK(cudaStreamSynchronize(L->stream));
+    collect_timing(L);
+    c->last = L;
     return rc;
 }
 
 extern "C" int md_fetch_calls(md_ctx *c, md_call *calls, uint64_t capacity, uint64_t *n_calls) {
     CK(cudaSetDevice(c->device));
-    return fetch_sorted(c, calls, capacity, n_calls);
+    return fetch_sorted(c, c->last, calls, capacity, n_calls);
 }
 
 extern "C" int md_mbias_tile(md_ctx *c, const md_tile_desc *tile, const md_reads_soa *reads, md_tile_stats *stats) {
     CK(cudaSetDevice(c->device));
-    CK(cudaEventRecord(c->ev[0], c->stream));
-    int rc = stage_reads(c, c->staged, reads);
+    int ticket = -1;
+    Lane *L = free_lane(c, &ticket);
+    if (!L) { g_err = "md_mbias_tile: all lanes are busy"; return -4; }
+    CK(cudaEventRecord(L->ev[0], L->stream));
+    int rc = stage_reads(c, L, L->staged, reads);
     if (rc) return rc;
-    rc = run_pipeline(c, tile, c->staged.view, true);
+    rc = run_pipeline(c, L, tile, L->staged.view, true);
     if (rc) return rc;
-    rc = finish_counters(c, stats);
-    CK(cudaEventRecord(c->ev[4], c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    collect_timing(c);
+    rc = finish_counters(c, L, stats);
+    CK(cudaEventRecord(L->ev[4], L->stream));
+    CK(cudaStreamSynchronize(L->stream));
+    collect_timing(L);
+    c->last = L;
     return rc;
 }
 
 extern "C" int md_mbias_tile_device(md_ctx *c, const md_tile_desc *tile, const md_dev_reads *reads, md_tile_stats *stats) {
     CK(cudaSetDevice(c->device));
-    CK(cudaEventRecord(c->ev[0], c->stream));
-    int rc = run_pipeline(c, tile, reads->view, true);
+    Lane *L = &c->lanes[0];
+    CK(cudaEventRecord(L->ev[0], L->stream));
+    int rc = run_pipeline(c, L, tile, reads->view, true);
     if (rc) return rc;
-    rc = finish_counters(c, stats);
-    CK(cudaEventRecord(c->ev[4], c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    collect_timing(c);
+    rc = finish_counters(c, L, stats);
+    CK(cudaEventRecord(L->ev[4], L->stream));
+    CK(cudaStreamSynchronize(L->stream));
+    collect_timing(L);
+    c->last = L;
     return rc;
 }
 
 extern "C" int md_mbias_hist(md_ctx *c, uint32_t *hist, int32_t lens[4]) {
     CK(cudaSetDevice(c->device));
-    CK(cudaMemcpyAsync(hist, c->d_hist, (size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(lens, c->d_lens, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    sync_all(c);
+    Lane *L = &c->lanes[0];
+    CK(cudaMemcpyAsync(hist, c->d_hist, (size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, L->stream));
+    CK(cudaMemcpyAsync(lens, c->d_lens, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, L->stream));
+    CK(cudaStreamSynchronize(L->stream));
     return 0;
 }
 
 extern "C" int md_mbias_reset(md_ctx *c) {
     CK(cudaSetDevice(c->device));
-    CK(cudaMemsetAsync(c->d_hist, 0, (size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2 * sizeof(uint32_t), c->stream));
-    CK(cudaMemsetAsync(c->d_lens, 0, 4 * sizeof(int32_t), c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    sync_all(c);
+    Lane *L = &c->lanes[0];
+    CK(cudaMemsetAsync(c->d_hist, 0, (size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2 * sizeof(uint32_t), L->stream));
+    CK(cudaMemsetAsync(c->d_lens, 0, 4 * sizeof(int32_t), L->stream));
+    CK(cudaStreamSynchronize(L->stream));
     return 0;
 }
 
+extern "C" void *md_alloc_pinned(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { g_err = "cudaMallocHost failed"; return nullptr; } return p; }
+extern "C" void md_free_pinned(void *p) { if (p) cudaFreeHost(p); }
 extern "C" int md_host_register(void *p, size_t bytes) { if (!p || !bytes) return 0; CK(cudaHostRegister(p, bytes, cudaHostRegisterDefault)); return 0; }
 extern "C" int md_host_unregister(void *p) { if (!p) return 0; CK(cudaHostUnregister(p)); return 0; }
-extern "C" int md_last_timing(md_ctx *c, float out[5]) { for (int k = 0; k < 5; ++k) out[k] = c->timing[k]; return 0; }
+extern "C" int md_last_timing(md_ctx *c, float out[5]) { for (int k = 0; k < 5; ++k) out[k] = c->last->timing[k]; return 0; }
 extern "C" uint64_t md_launch_count(md_ctx *c) { return c->launches; }
-extern "C" void *md_stream(md_ctx *c) { return (void *) c->stream; }
+extern "C" void *md_stream(md_ctx *c) { return (void *) c->lanes[0].stream; }

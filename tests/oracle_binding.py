@@ -79,7 +79,7 @@ class OracleBackend:
         self._keep = [A.CREATE_FN(create), A.DESTROY_FN(destroy), A.LOAD_CONTIG_FN(load_contig), A.DROP_CONTIG_FN(drop_contig),
                       A.EXTRACT_TILE_FN(extract_tile), A.SET_CHUNKS_FN(set_chunks), A.MBIAS_TILE_FN(mbias_tile), A.MBIAS_HIST_FN(mbias_hist),
                       A.LAST_ERROR_FN(last_error)]
-        self.be = A.MdhBackend(None, *self._keep)
+        self.be = A.MdhBackend(None, *self._keep)      # async slots stay NULL: the driver then runs tile by tile
 
 
 def run_host_main(which, argv, backend):
