@@ -10,8 +10,8 @@
 //                     getStrand (common.c:84-116), reference span, and — for the mate-overlap merge —
 //                     insertion of the read's 64-bit name key into an open-addressing table in HBM
 //                     (replaces the khash of overlaps.c:121-139).
-//   K2 pair_kernel    one thread per alignment: reads its table slot; a key seen exactly twice is a
-//                     mate pair (first in file order = `a`, overlaps.c:129-135).
+//                     (a later record with the same name claims the stored one as its mate with one atomicCAS;
+//                     a third record of a name flags the tile for an exact host replay).
 //   K3 window_kernel  per window of W reference positions: the range of alignments that can touch it.
 //   K4 count_kernel   one CTA per window: stages the reference window in shared memory, classifies
 //                     every position (isCpG/isCHG/isCHH, common.c:49-82), then warps stream the
@@ -68,9 +68,11 @@ struct KParams {
 #define INFO_ADMIT 8
 #define INFO_ELIG 16
 
-struct HashTab { unsigned long long *keys; uint32_t *cnt; uint32_t *idx; uint32_t mask; };
+// Pairing table: one 32-bit slot per name = index of the first record seen with that name (0xffffffff = empty);
+// the name itself is checked against frag_key[] of that record, so the table stays small enough to live in L2.
+struct HashTab { uint32_t *tab; uint32_t cap; };
 
-// counters[]: 0 n_admitted, 1 max reference span, 2 n_pairs(x2), 3 n_multi, 4 n_calls (append cursor), 5 overflow flag
+// counters[]: 0 n_admitted, 1 max reference span, 2 n_pairs, 3 n_multi, 4-5 n_calls (64-bit append cursor), 6 overflow flag, 7 max l_qseq
 enum { C_ADMIT = 0, C_MAXSPAN = 1, C_PAIRED = 2, C_MULTI = 3, C_NCALLS = 4 /* 64-bit: slots 4,5 */, C_OVERFLOW = 6, C_MAXLQ = 7, C_N = 8 };
 
 // ------------------------------------------------------------------------------------------------
@@ -124,15 +126,19 @@ __device__ __forceinline__ unsigned dev_qual(const uint64_t *qual, uint32_t off,
     return __ldg(p + q);
 }
 
-__device__ __forceinline__ uint32_t hash_slot(unsigned long long key, uint32_t mask) {
-    return (uint32_t)((key * 0x9e3779b97f4a7c15ull) >> 32) & mask;
+__device__ __forceinline__ uint32_t hash_slot(unsigned long long key, uint32_t cap) {
+    const uint32_t h = (uint32_t)((key * 0x9e3779b97f4a7c15ull) >> 32);
+    return (uint32_t)(((unsigned long long) h * cap) >> 32);               // multiply-shift range reduction, any cap
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1
-__global__ void __launch_bounds__(256) prep_kernel(DevReads R, KParams P, int32_t *rend, uint8_t *info, HashTab T, uint32_t *slot_of, uint32_t *counters) {
+// K1.  Besides admission / strand / span, resolves mate pairs: the first record of a name claims a table slot with its
+// index (atomicCAS); a later record with the same name finds it, and claims it as its mate with one atomicCAS on mate[]
+// (overlaps.c:129-135: the stored record is `a`).  A third record of the same name cannot claim anything: the tile is
+// then flagged (C_MULTI) and replayed exactly on the host.  mate[] must be preset to -1 and tab[] to 0xffffffff.
+__global__ void __launch_bounds__(256) prep_kernel(DevReads R, KParams P, int32_t *rend, uint8_t *info, HashTab T, int32_t *mate, uint32_t *counters) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool ok = false; int rl = 0;
+    bool ok = false, paired = false, multi = false; int rl = 0;
     if (i < R.n) {
         unsigned f = R.flag[i], a = R.aux[i];
         int strand = dev_strand(f, a);
@@ -147,56 +153,31 @@ __global__ void __launch_bounds__(256) prep_kernel(DevReads R, KParams P, int32_
         bool elig = ok && (f & 1u) && !(f & 12u) && !P.noOverlap;          // overlaps.c:128
         rend[i] = R.pos[i] + rl;
         info[i] = (uint8_t)(strand | (ok ? INFO_ADMIT : 0) | (elig ? INFO_ELIG : 0));
-        uint32_t slot = 0xffffffffu;
         if (elig) {
-            unsigned long long key = R.frag_key[i];
-            if (key == 0ull) key = 0x9e3779b97f4a7c15ull;           // 0 marks an empty slot
-            uint32_t h = hash_slot(key, T.mask);
-            for (uint32_t probe = 0; probe <= T.mask; ++probe) {
-                unsigned long long prev = atomicCAS(T.keys + h, 0ull, key);
-                if (prev == 0ull || prev == key) {
-                    uint32_t c = atomicAdd(T.cnt + h, 1u);
-                    if (c < 2) T.idx[2 * h + c] = i;
-                    slot = h;
+            const unsigned long long key = R.frag_key[i];
+            uint32_t h = hash_slot(key, T.cap);
+            for (uint32_t probe = 0; probe < T.cap; ++probe) {
+                const uint32_t old = atomicCAS(T.tab + h, 0xffffffffu, i);
+                if (old == 0xffffffffu) break;                                 // first record of this name
+                if (R.frag_key[old] == key) {                                  // same name: pair up, or detect a third record
+                    if (atomicCAS((int *) mate + old, -1, (int) i) == -1) { mate[i] = (int32_t) old; paired = true; }
+                    else multi = true;
                     break;
                 }
-                h = (h + 1) & T.mask;
+                if (++h == T.cap) h = 0;
             }
         }
-        slot_of[i] = slot;
     }
-    unsigned m = __ballot_sync(0xffffffffu, ok);
+    const unsigned m = __ballot_sync(0xffffffffu, ok), mp = __ballot_sync(0xffffffffu, paired), mm = __ballot_sync(0xffffffffu, multi);
     int wmax = ok ? rl : 0;
     uint32_t lqmax = (i < R.n) ? R.l_qseq[i] : 0u;
     for (int o = 16; o; o >>= 1) { wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o)); lqmax = max(lqmax, __shfl_xor_sync(0xffffffffu, lqmax, o)); }
     if ((threadIdx.x & 31) == 0) {
         if (m) { atomicAdd(counters + C_ADMIT, (uint32_t) __popc(m)); atomicMax(counters + C_MAXSPAN, (uint32_t) wmax); }
+        if (mp) atomicAdd(counters + C_PAIRED, (uint32_t) __popc(mp));
+        if (mm) atomicAdd(counters + C_MULTI, (uint32_t) __popc(mm));
         atomicMax(counters + C_MAXLQ, lqmax);
     }
-}
-
-// K2
-__global__ void __launch_bounds__(256) pair_kernel(DevReads R, const int32_t *rend, const uint8_t *info, HashTab T, const uint32_t *slot_of, int32_t *mate, uint32_t *counters) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R.n) return;
-    int32_t m = -1;
-    uint8_t inf = info[i];
-    if (inf & INFO_ELIG) {
-        uint32_t h = slot_of[i];
-        if (h != 0xffffffffu) {
-            uint32_t c = T.cnt[h];
-            if (c == 2) {
-                uint32_t j = T.idx[2 * h] == i ? T.idx[2 * h + 1] : T.idx[2 * h];
-                atomicAdd(counters + C_PAIRED, 1u);
-                // cust_tweak_overlap_quality bails out when the strands differ in parity (overlaps.c:65),
-                // and there is nothing to merge when the reference spans are disjoint
-                int sa = INFO_STRAND(inf), sb = INFO_STRAND(info[j]);
-                bool overlap = R.pos[i] < rend[j] && R.pos[j] < rend[i];
-                if (!((sa - sb) & 1) && overlap) m = (int32_t) j;
-            } else if (c > 2) atomicAdd(counters + C_MULTI, 1u);
-        }
-    }
-    mate[i] = m;
 }
 
 // K3: first/last alignment index that can touch each window
@@ -276,9 +257,13 @@ __device__ __forceinline__ void load_mate(const CountArgs &A, uint32_t i, int mi
     const DevReads &R = A.R;
     rc.mi = mi;
     if (mi < 0) return;
-    rc.mpos = R.pos[mi]; rc.mend = A.rend[mi]; rc.mk0 = R.cigar_off[mi]; rc.mk1 = R.cigar_off[mi + 1];
+    rc.mpos = R.pos[mi]; rc.mend = A.rend[mi];
+    const int ms = INFO_STRAND(A.info[mi]);
+    // cust_tweak_overlap_quality bails out when the strands differ in parity (overlaps.c:65); disjoint spans have nothing to merge
+    if (((rc.strand - ms) & 1) || !(R.pos[i] < rc.mend && rc.mpos < A.rend[i])) { rc.mi = -1; return; }
+    rc.mk0 = R.cigar_off[mi]; rc.mk1 = R.cigar_off[mi + 1];
     rc.msoff = R.seq_off[mi]; rc.mqoff = R.qual_off[mi];
-    dev_trim(A.P, INFO_STRAND(A.info[mi]), R.flag[mi], (int) R.l_qseq[mi], rc.mlo, rc.mhi);
+    dev_trim(A.P, ms, R.flag[mi], (int) R.l_qseq[mi], rc.mlo, rc.mhi);
     rc.is_a = (uint32_t) mi > i;                               // first in file order is `a` (overlaps.c:129-135)
     // a mate whose CIGAR is a single match op maps reference -> query by subtraction
     rc.mate_simple = false; rc.mq0 = 0;
@@ -847,6 +832,343 @@ __global__ void __launch_bounds__(ST_THREADS, 2) count_stream(CountArgs A) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K4w — warp-streaming count kernel (default).  Same contract as count_kernel / count_stream.
+//
+//   * one CTA (8 warps) per window of 4096 reference positions, two CTAs resident per SM;
+//   * the window's alignments are consumed in batches of 32, handed out dynamically to the CTA's warps
+//     (shared-memory ticket), so there is no CTA-wide barrier in the streaming phase and no tail imbalance;
+//   * each warp owns a staging buffer and an mbarrier: lane 0 streams the batch's packed bases and phreds into
+//     shared memory with two cp.async.bulk copies (TMA) while all lanes fetch the scalars of "their" alignment;
+//   * GENERATE: every lane walks its alignment's CIGAR against the C-/G-site bitmaps of the window and emits one
+//     candidate base per iteration; a warp ballot compacts the candidates into a shared-memory queue;
+//   * EVALUATE: as soon as 32 candidates are queued, every lane takes one — all 32 lanes busy — and runs trims,
+//     overlap merge, phred gate, call / variant evidence and the shared-memory atomicAdd.
+//
+// This is the "warp-ballot branch flattening" of the north star: the divergent part (how many cytosines an
+// alignment covers) is reduced to a cheap iterator, the expensive part runs converged.
+#define WS_SEQ_BYTES 2560          // 32 alignments x 76 B (150-mers) + alignment slack
+#define WS_QUAL_BYTES 5120         // 32 x 152 B + slack
+#define WS_CTX_WORDS 12
+#define WS_QUEUE 128               // candidate queue entries per warp (>= 64: up to 31 left over + 32 new)
+#define WS_WARPS 8
+
+struct WarpLayout { uint32_t off_bm, off_cnt, off_warp, warp_stride, off_seq, off_qual, off_ctx, off_queue, total; };
+__host__ __device__ inline WarpLayout warp_layout(uint32_t W, int mode) {
+    WarpLayout L; const uint32_t NW = W >> 5;
+    auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
+    L.off_bm = 128;                                              // [0,128): 8 mbarriers + ticket counter
+    L.off_cnt = up(L.off_bm + 4u * (NW + 2u) * 4u);
+    const uint32_t ncnt = mode == 2 ? 4u * 2u * MB_SM_Q * 2u : (mode == 1 ? 4u * W : 2u * W);
+    L.off_warp = up(L.off_cnt + ncnt * 4u);
+    L.off_seq = 0; L.off_qual = up(WS_SEQ_BYTES + 32u); L.off_ctx = L.off_qual + up(WS_QUAL_BYTES + 32u);
+    L.off_queue = L.off_ctx + WS_CTX_WORDS * 32u * 4u;
+    L.warp_stride = up(L.off_queue + WS_QUEUE * 4u);
+    L.total = L.off_warp + WS_WARPS * L.warp_stride;
+    return L;
+}
+
+// per-alignment context words in shared memory
+//  0: staged seq byte offset | staged qual byte offset << 16
+//  1: flags: bit0 wantG, bit1 rd2, bit2 has mate, bit3 is_a, bit4 mate_simple, bits8-10 strand
+//  2: mpos   3: mend   4: msoff   5: mqoff   6: mlo | mhi << 16   7: mk0   8: mk1
+template <int MODE>
+__global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t W = A.W, NW = W >> 5;
+    const WarpLayout SL = warp_layout(W, MODE);
+    uint64_t *bars = (uint64_t *) smem;                                   // [8]
+    uint32_t *ticket = (uint32_t *)(smem + 64);
+    uint32_t *bmC = (uint32_t *)(smem + SL.off_bm), *bmG = bmC + NW + 2, *bmT0 = bmG + NW + 2, *bmT1 = bmT0 + NW + 2;
+    uint32_t *cnt = (uint32_t *)(smem + SL.off_cnt);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char *wbase = smem + SL.off_warp + (size_t) warp * SL.warp_stride;
+    unsigned char *sseq = wbase + SL.off_seq, *squal = wbase + SL.off_qual;
+    uint32_t *rctx = (uint32_t *)(wbase + SL.off_ctx), *queue = (uint32_t *)(wbase + SL.off_queue);
+    unsigned char *refw = smem + SL.off_warp;                             // prologue only: overlays the warps' staging area
+    const uint32_t w = blockIdx.x;
+    const long long w0 = (long long) A.beg + (long long) w * W;
+    const long long own1 = min((long long) A.end, w0 + (long long) W);
+    const int own = (int)(own1 - w0), w0i = (int) w0;
+    const DevReads &R = A.R;
+    const uint2 rr = A.win[w];
+
+    // ---- prologue: barriers, reference window, site bitmaps (as count_stream) --------------------------
+    if (tid == 0) { for (int kk = 0; kk < WS_WARPS; ++kk) mbar_init(bars + kk, 1); *ticket = 0; mbar_fence_init(); }
+    for (uint32_t t = tid; t < W + 4; t += WS_WARPS * 32) {
+        long long p = w0 - 2 + t;
+        refw[t] = (p >= 0 && p < (long long) A.reflen) ? __ldg(A.ref + p) : (unsigned char) 'N';
+    }
+    const uint32_t ncnt = (MODE == 2) ? 4u * 2u * MB_SM_Q * 2u : (MODE == 1 ? 4u * W : 2u * W);
+    for (uint32_t t = tid; t < ncnt; t += WS_WARPS * 32) cnt[t] = 0;
+    if (tid < 8) { uint32_t *g = bmC + (tid >> 1) * (NW + 2); g[(tid & 1) ? NW + 1 : 0] = 0; }
+    __syncthreads();
+    {
+        const uint32_t t16 = 16u * tid;
+        unsigned sC = 0, sG = 0, t0 = 0, t1 = 0;
+        if (MODE == 2) {
+            for (int j = 0; j < 16; ++j) {                                // MBias.c:147,170-178: context inside the chunk's own window
+                long long p = w0 + t16 + j; unsigned c = 0;
+                if (p < own1 && A.n_chunks) {
+                    uint32_t lo = 0, hi = A.n_chunks;
+                    while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if ((long long) A.chunk_bounds[mid] <= p) lo = mid; else hi = mid; }
+                    if (p >= (long long) A.chunk_bounds[lo] && p < (long long) A.chunk_bounds[lo + 1]) {
+                        long long cs = A.chunk_bounds[lo], ce = A.chunk_bounds[lo + 1];
+                        long long last = ce < (long long) A.reflen ? ce : (long long) A.reflen - 1;
+                        auto get = [&](long long x) -> unsigned char { long long o = x - (w0 - 2); return (o >= 0 && o < (long long) W + 4) ? refw[o] : __ldg(A.ref + x); };
+                        c = dev_context(get, p, cs, last + 1);
+                    }
+                }
+                if (c && !((A.P.keepMask >> ((c & 3) - 1)) & 1)) c = 0;
+                if (c) { if (c & 4u) sG |= 1u << j; else sC |= 1u << j; if ((c & 3u) == 1u) t0 |= 1u << j; else if ((c & 3u) == 2u) t1 |= 1u << j; }
+            }
+        } else {
+            unsigned C = 0, G = 0;
+            #pragma unroll
+            for (int j = 0; j < 20; ++j) { unsigned ch = refw[t16 + j] | 0x20u; C |= (ch == 'c' ? 1u : 0u) << j; G |= (ch == 'g' ? 1u : 0u) << j; }
+            const unsigned cpgC = C & (G >> 1), cpgG = G & (C << 1);
+            const unsigned chgC = C & ~cpgC & (G >> 2), chgG = G & ~cpgG & (C << 2);
+            const unsigned chhC = C & ~cpgC & ~chgC, chhG = G & ~cpgG & ~chgG;
+            const unsigned k0 = (A.P.keepMask & 1) ? ~0u : 0u, k1 = (A.P.keepMask & 2) ? ~0u : 0u, k2 = (A.P.keepMask & 4) ? ~0u : 0u;
+            int nown = own - (int) t16; nown = nown < 0 ? 0 : (nown > 16 ? 16 : nown);
+            const unsigned ownm = nown >= 16 ? 0xffffu : ((1u << nown) - 1u);
+            sC = (((cpgC & k0) | (chgC & k1) | (chhC & k2)) >> 2) & ownm;
+            sG = (((cpgG & k0) | (chgG & k1) | (chhG & k2)) >> 2) & ownm;
+            t0 = (((cpgC | cpgG) & k0) >> 2) & ownm;
+            t1 = (((chgC | chgG) & k1) >> 2) & ownm;
+        }
+        const unsigned pC = __shfl_down_sync(0xffffffffu, sC, 1), pG = __shfl_down_sync(0xffffffffu, sG, 1), p0 = __shfl_down_sync(0xffffffffu, t0, 1), p1 = __shfl_down_sync(0xffffffffu, t1, 1);
+        if (!(tid & 1)) {
+            const uint32_t wi = (t16 >> 5) + 1;
+            bmC[wi] = sC | (pC << 16); bmG[wi] = sG | (pG << 16); bmT0[wi] = t0 | (p0 << 16); bmT1[wi] = t1 | (p1 << 16);
+        }
+    }
+    __syncthreads();                                                      // bitmaps complete; refw (overlay) no longer needed
+
+    // ---- streaming phase: every warp on its own -----------------------------------------------------------
+    const uint32_t maxlq = A.counters[C_MAXLQ];
+    const uint32_t seqb_max = ((((maxlq + 1u) >> 1) + 3u) >> 2) * 4u, qualb_max = ((maxlq + 7u) >> 3) * 8u;
+    uint32_t nb = 32;
+    if (seqb_max) nb = min(nb, (uint32_t)(WS_SEQ_BYTES - 32u) / seqb_max);
+    if (qualb_max) nb = min(nb, (uint32_t)(WS_QUAL_BYTES - 32u) / qualb_max);
+    if (maxlq >= (1u << 14)) nb = 0;                                      // query index must fit the queue entry
+    auto ctx_code = [&](int rel) -> unsigned {
+        const uint32_t wi = ((uint32_t) rel >> 5) + 1, b = 1u << (rel & 31);
+        const bool c = bmC[wi] & b, g = bmG[wi] & b;
+        if (!c && !g) return 0u;
+        return ((bmT0[wi] & b) ? 1u : (bmT1[wi] & b) ? 2u : 3u) | (g ? 4u : 0u);
+    };
+    if (nb == 0) {
+        for (uint32_t i = rr.x + warp; i < rr.y; i += WS_WARPS) {         // reads too long to stage: whole warp per alignment, from global memory
+            const unsigned inf = A.info[i];
+            if ((inf & INFO_ADMIT) && (long long) A.rend[i] > w0) slow_read<MODE>(A, i, inf, w0, own1, ctx_code, cnt, lane);
+        }
+    } else {
+        uint64_t *bar = bars + warp;
+        uint32_t phase = 0;
+        for (;;) {
+            uint32_t b = 0;
+            if (lane == 0) b = atomicAdd(ticket, 1u);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            const uint64_t s64 = (uint64_t) rr.x + (uint64_t) b * nb;
+            if (s64 >= rr.y) break;
+            const uint32_t s = (uint32_t) s64, e = min(s + nb, rr.y), i = s + lane;
+            // -- lane 0 streams the batch's bases and phreds (TMA); the descriptor goes to the other lanes by shuffle
+            uint32_t sw0 = 0, sw1 = 0, qw0 = 0, qw1 = 0;
+            if (lane == 0) {
+                sw0 = R.seq_off[s] & ~3u; qw0 = R.qual_off[s] & ~1u;
+                const uint32_t lql = R.l_qseq[e - 1];
+                uint32_t sw_end = min(R.seq_off[e - 1] + ((((lql + 1u) >> 1) + 3u) >> 2), R.seq_words), qw_end = min(R.qual_off[e - 1] + ((lql + 7u) >> 3), R.qual_words);
+                uint32_t sbytes = sw_end > sw0 ? (sw_end - sw0) * 4u : 0u, qbytes = qw_end > qw0 ? (qw_end - qw0) * 8u : 0u;
+                sbytes = min((sbytes + 15u) & ~15u, (uint32_t) WS_SEQ_BYTES); qbytes = min((qbytes + 15u) & ~15u, (uint32_t) WS_QUAL_BYTES);
+                sw1 = sw0 + sbytes / 4u; qw1 = qw0 + qbytes / 8u;
+                mbar_arrive_expect_tx(bar, sbytes + qbytes);
+                if (sbytes) bulk_copy_g2s(sseq, R.seq + sw0, sbytes, bar);
+                if (qbytes) bulk_copy_g2s(squal, R.qual + qw0, qbytes, bar);
+            }
+            // -- every lane: scalars of its alignment, kept range, mate
+            unsigned inf = 0; bool live = false;
+            int pos = 0, lq = 0, mate = -1; unsigned f = 0; uint32_t soff = 0, qoff = 0, k0 = 0, k1 = 0, c0 = 0;
+            if (i < e) {
+                inf = A.info[i];
+                live = (inf & INFO_ADMIT) && (long long) A.rend[i] > w0;
+                if (live) {
+                    pos = R.pos[i]; lq = (int) R.l_qseq[i]; f = R.flag[i]; soff = R.seq_off[i]; qoff = R.qual_off[i];
+                    k0 = R.cigar_off[i]; k1 = R.cigar_off[i + 1];
+                    mate = (MODE == 2) ? -1 : A.mate[i];
+                    c0 = __ldg(R.cigar + k0);
+                }
+            }
+            sw0 = __shfl_sync(0xffffffffu, sw0, 0); sw1 = __shfl_sync(0xffffffffu, sw1, 0); qw0 = __shfl_sync(0xffffffffu, qw0, 0); qw1 = __shfl_sync(0xffffffffu, qw1, 0);
+            ReadCtx rc; rc.mi = -1; rc.lo = 0; rc.hi = 0; rc.strand = 1; rc.wantG = false; rc.rd2 = 0;
+            bool staged = false;
+            if (live) {
+                rc.strand = INFO_STRAND(inf); rc.rd2 = (f & 0x80u) ? 1 : 0; rc.wantG = !(rc.strand & 1);
+                dev_trim(A.P, rc.strand, f, lq, rc.lo, rc.hi);
+                rc.soff = soff; rc.qoff = qoff;
+                load_mate(A, i, mate, rc);
+                const uint32_t sw_need = ((((uint32_t) lq + 1u) >> 1) + 3u) >> 2, qw_need = ((uint32_t) lq + 7u) >> 3;
+                staged = soff >= sw0 && soff + sw_need <= sw1 && qoff >= qw0 && qoff + qw_need <= qw1;
+                uint32_t *cx = rctx + WS_CTX_WORDS * lane;
+                cx[0] = ((soff - sw0) * 4u) | (((qoff - qw0) * 8u) << 16);
+                cx[1] = (rc.wantG ? 1u : 0u) | (rc.rd2 ? 2u : 0u) | (rc.mi >= 0 ? 4u : 0u) | (rc.is_a ? 8u : 0u) | (rc.mate_simple ? 16u : 0u) | ((unsigned) rc.strand << 8);
+                if (rc.mi >= 0) { cx[2] = (uint32_t) rc.mpos; cx[3] = (uint32_t) rc.mend; cx[4] = rc.msoff; cx[5] = rc.mqoff; cx[6] = (uint32_t) rc.mlo | ((uint32_t) rc.mhi << 16); cx[7] = rc.mk0; cx[8] = rc.mk1; }
+            }
+            // alignments that cannot use the queue (not inside the staged range, trims beyond 16 bits) go the direct way below
+            const bool direct = live && (!staged || (rc.mi >= 0 && rc.mhi > 0xffff));
+            { uint32_t spins = 0; while (!mbar_try_wait(bar, phase)) { if (++spins > (1u << 26)) { atomicExch(A.counters + C_OVERFLOW, 2u); break; } } }
+            phase ^= 1u;
+            __syncwarp();                                              // context words visible to the whole warp
+
+            // -- GENERATE / EVALUATE
+            // iterator over this lane's candidate bases: current match op [a,b) (clipped), bitmap word wi, remaining bits cur
+            const uint32_t *own_bm = rc.wantG ? bmG : bmC, *opp_bm = rc.wantG ? bmC : bmG;
+            uint32_t k = k0; int p = pos, q = 0, opq = 0, opp_ = 0, ra = 0, rb = 0, wi = 0; unsigned cur = 0, curo = 0; bool in_op = false;
+            bool done = !(live && !direct);
+            uint32_t qn = 0;                                            // queued candidates (warp-uniform)
+            for (;;) {
+                // advance to the next candidate (divergent, cheap)
+                bool has = false; uint32_t ent = 0;
+                while (!done) {
+                    if (cur | curo) {
+                        const unsigned any = cur | curo; const int bit = __ffs(any) - 1;
+                        const bool is_own = (cur >> bit) & 1u;
+                        cur &= ~(1u << bit); curo &= ~(1u << bit);
+                        const int rel = (wi << 5) + bit, qi = opq + (w0i + rel - opp_);
+                        ent = (uint32_t) lane | ((uint32_t) rel << 5) | ((uint32_t) qi << 17) | (is_own ? 0u : 0x80000000u);
+                        has = true; break;
+                    }
+                    if (in_op && wi < ((rb - 1) >> 5)) {
+                        ++wi;
+                        unsigned keep = 0xffffffffu;
+                        if (wi == ((rb - 1) >> 5)) keep &= 0xffffffffu >> (31 - ((rb - 1) & 31));
+                        cur = own_bm[wi + 1] & keep; curo = (MODE == 1) ? (opp_bm[wi + 1] & keep) : 0u;
+                        continue;
+                    }
+                    in_op = false;
+                    if (k >= k1) { done = true; break; }
+                    const uint32_t c = (k == k0) ? c0 : __ldg(R.cigar + k), op = c & 15u; const int len = (int)(c >> 4);
+                    ++k;
+                    if (op == 0 || op == 7 || op == 8) {
+                        const int a = max(max(p, w0i), p + (rc.lo - q)), bnd = min(min(p + len, w0i + own), p + (rc.hi - q));
+                        if (bnd > a) {
+                            ra = a - w0i; rb = bnd - w0i; wi = ra >> 5; in_op = true; opq = q; opp_ = p;
+                            unsigned keep = 0xffffffffu << (ra & 31);
+                            if (wi == ((rb - 1) >> 5)) keep &= 0xffffffffu >> (31 - ((rb - 1) & 31));
+                            cur = own_bm[wi + 1] & keep; curo = (MODE == 1) ? (opp_bm[wi + 1] & keep) : 0u;
+                        }
+                        p += len; q += len;
+                    } else if (op == 1 || op == 4) q += len;
+                    else if (op == 2 || op == 3) p += len;
+                }
+                const unsigned hm = __ballot_sync(0xffffffffu, has);
+                if (has) queue[qn + __popc(hm & ((1u << lane) - 1u))] = ent;
+                qn += __popc(hm);
+                const bool all_done = hm == 0u;                           // no lane produced anything: every iterator is exhausted
+                __syncwarp();
+                while (qn >= 32u || (all_done && qn > 0u)) {
+                    const uint32_t take = min(qn, 32u);
+                    if ((uint32_t) lane < take) {
+                        const uint32_t en = queue[qn - take + lane];
+                        const int src = en & 31u, rel = (en >> 5) & 0xfffu, qi = (en >> 17) & 0x3fffu; const bool is_opp = en >> 31;
+                        const uint32_t *cx = rctx + WS_CTX_WORDS * src;
+                        const uint32_t c0w = cx[0], c1w = cx[1];
+                        ReadCtx hc;
+                        hc.wantG = c1w & 1u; hc.rd2 = (c1w >> 1) & 1u; hc.strand = (c1w >> 8) & 7u; hc.mi = (c1w & 4u) ? 0 : -1;
+                        if (hc.mi >= 0) {
+                            hc.is_a = (c1w & 8u) != 0; hc.mate_simple = (c1w & 16u) != 0;
+                            hc.mpos = (int) cx[2]; hc.mend = (int) cx[3]; hc.msoff = cx[4]; hc.mqoff = cx[5]; hc.mlo = (int)(cx[6] & 0xffffu); hc.mhi = (int)(cx[6] >> 16); hc.mk0 = cx[7]; hc.mk1 = cx[8];
+                        }
+                        const unsigned byte = sseq[(c0w & 0xffffu) + (qi >> 1)];
+                        const unsigned bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4), ql = squal[(c0w >> 16) + qi];
+                        eval_hit<MODE>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
+                    }
+                    qn -= take;
+                    __syncwarp();
+                }
+                if (all_done) break;
+            }
+            // -- alignments outside the staged range: the lane walks it alone, from global memory
+            if (direct) {
+                int p2 = pos, q2 = 0;
+                for (uint32_t kk = k0; kk < k1; ++kk) {
+                    const uint32_t c = __ldg(R.cigar + kk), op = c & 15u; const int len = (int)(c >> 4);
+                    if (op == 0 || op == 7 || op == 8) {
+                        const int a = max(max(p2, w0i), p2 + (rc.lo - q2)), bnd = min(min(p2 + len, w0i + own), p2 + (rc.hi - q2));
+                        for (int x = a; x < bnd; ++x) {
+                            const unsigned cxc = ctx_code(x - w0i);
+                            if (!cxc) continue;
+                            const bool siteG = (cxc & 4u) != 0;
+                            if (MODE != 1 && siteG != rc.wantG) continue;
+                            const int qi = q2 + (x - p2);
+                            eval_hit<MODE>(A, rc, cnt, W, w0i, x, qi, dev_base(R.seq, soff, qi), dev_qual(R.qual, qoff, qi), siteG);
+                        }
+                        p2 += len; q2 += len;
+                    } else if (op == 1 || op == 4) q2 += len;
+                    else if (op == 2 || op == 3) p2 += len;
+                }
+            }
+            __syncwarp();                                              // staging buffer and context free for the next batch
+        }
+    }
+    __syncthreads();
+
+    // ---- epilogue (as count_stream) ---------------------------------------------------------------------
+    if (MODE == 2) {
+        for (uint32_t t = tid; t < 4u * 2u * MB_SM_Q * 2u; t += WS_WARPS * 32) {
+            uint32_t v = cnt[t];
+            if (v) { uint32_t sr = t / (MB_SM_Q * 2), rest = t % (MB_SM_Q * 2); atomicAdd(A.hist + (size_t) sr * MD_MBIAS_MAXLEN * 2 + rest, v); }
+        }
+        return;
+    }
+    __shared__ uint32_t s_warp_tot[WS_WARPS], s_base;
+    const uint32_t t16 = 16u * tid;
+    unsigned rep = 0;
+    {
+        const uint32_t wi = (t16 >> 5) + 1, sh = t16 & 31u;
+        unsigned sites = ((bmC[wi] | bmG[wi]) >> sh) & 0xffffu;
+        while (sites) {
+            const int kbit = __ffs(sites) - 1; sites &= sites - 1;
+            const uint32_t t = t16 + kbit;
+            bool excl = false;
+            if (MODE == 1) {
+                const uint32_t noff = cnt[2 * W + t], nvar = cnt[3 * W + t];
+                excl = A.P.minOppositeDepth > 0 && noff >= (uint32_t) A.P.minOppositeDepth && ((double) nvar) / ((double) noff) >= A.P.maxVariantFrac;
+            }
+            if (excl) rep |= 0x10000u << kbit;
+            if (excl || cnt[t] + cnt[W + t]) rep |= 1u << kbit;
+        }
+    }
+    const uint32_t mine = __popc(rep & 0xffffu);
+    uint32_t incl = mine;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t tot = 0;
+        for (int kk = 0; kk < WS_WARPS; ++kk) { uint32_t v = s_warp_tot[kk]; s_warp_tot[kk] = tot; tot += v; }
+        unsigned long long base = tot ? atomicAdd((unsigned long long *)(A.counters + C_NCALLS), (unsigned long long) tot) : 0ull;
+        if (base + tot > A.cap) { atomicExch(A.counters + C_OVERFLOW, 1u); s_base = 0xffffffffu; }
+        else s_base = (uint32_t) base;
+        A.dir[w] = make_uint2((uint32_t) base, tot);
+    }
+    __syncthreads();
+    if (s_base == 0xffffffffu) return;
+    uint32_t o = s_base + s_warp_tot[warp] + (incl - mine);
+    {
+        const uint32_t wi = (t16 >> 5) + 1, sh = t16 & 31u;
+        const unsigned g16 = (bmG[wi] >> sh) & 0xffffu, a16 = (bmT0[wi] >> sh) & 0xffffu, b16 = (bmT1[wi] >> sh) & 0xffffu;
+        unsigned r16 = rep & 0xffffu;
+        while (r16) {
+            const int kbit = __ffs(r16) - 1; r16 &= r16 - 1;
+            const uint32_t t = t16 + kbit;
+            md_call c; c.pos = (uint32_t)(w0 + t); c.nmeth = cnt[t]; c.nunmeth = cnt[W + t];
+            c.info = (((a16 >> kbit) & 1u) ? 0u : ((b16 >> kbit) & 1u) ? 1u : 2u) | (((g16 >> kbit) & 1u) ? 4u : 0u) | (((rep >> (16 + kbit)) & 1u) ? 8u : 0u);
+            A.calls[o++] = c;
+        }
+    }
+}
+
 // K5/K6: put the per-window segments into position order on the device (exclusive scan of the directory
 // counts by one CTA, then a segment copy), so the D2H transfer lands in the caller's buffer already sorted.
 __global__ void __launch_bounds__(1024) dir_scan_kernel(uint2 *dir, uint32_t n_win, uint32_t *sorted_off) {
@@ -905,7 +1227,7 @@ struct md_dev_reads {
 struct Lane {
     cudaStream_t stream = nullptr;
     md_dev_reads staged;                 // device copy of the host tile
-    DevBuf rend, info, slot_of, mate, keys, hcnt, hidx, win, dir, calls, counters, sorted, sorted_off;
+    DevBuf rend, info, mate, tab, win, dir, calls, counters, sorted, sorted_off;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float timing[5] = {0, 0, 0, 0, 0};
     uint32_t last_nwin = 0; uint64_t last_ncalls = 0; bool pending = false; md_tile_stats last_stats;
@@ -920,7 +1242,7 @@ struct md_ctx {
     uint32_t *d_hist = nullptr; int32_t *d_lens = nullptr;
     uint64_t launches = 0;
     uint32_t W = 4096;
-    int count_variant = 3;               // 3: count_stream (TMA-staged, thread per alignment); 2: count_kernel (warp / half-warp per alignment)
+    int count_variant = 4;               // 4: count_warp (per-warp TMA streaming + ballot queue); 3: count_stream; 2: count_kernel
 };
 
 static void sync_all(md_ctx *c) { for (int k = 0; k < MD_NLANES; ++k) if (c->lanes[k].stream) cudaStreamSynchronize(c->lanes[k].stream); }
@@ -944,7 +1266,7 @@ extern "C" md_ctx *md_create(const md_config *cfg, int device) {
     CKN(cudaSetDevice(device));
     md_ctx *c = new md_ctx();
     c->device = device; c->cfg = *cfg; fill_kparams(cfg, c->kp);
-    if (const char *v = getenv("MD_COUNT_KERNEL")) { int k = atoi(v); if (k == 2 || k == 3) c->count_variant = k; }
+    if (const char *v = getenv("MD_COUNT_KERNEL")) { int k = atoi(v); if (k >= 2 && k <= 4) c->count_variant = k; }
     for (int k = 0; k < MD_NLANES; ++k) {
         Lane *L = &c->lanes[k];
         if (cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; delete c; return nullptr; }
@@ -958,6 +1280,9 @@ extern "C" md_ctx *md_create(const md_config *cfg, int device) {
     cudaFuncSetAttribute(count_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(count_warp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0).total);
+    cudaFuncSetAttribute(count_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1).total);
+    cudaFuncSetAttribute(count_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2).total);
     cudaFuncSetAttribute(count_stream<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) stream_layout(4096, 0).total);
     cudaFuncSetAttribute(count_stream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) stream_layout(4096, 1).total);
     cudaFuncSetAttribute(count_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) stream_layout(4096, 2).total);
@@ -973,7 +1298,7 @@ extern "C" void md_destroy(md_ctx *c) {
     for (int k = 0; k < MD_NLANES; ++k) {
         Lane *L = &c->lanes[k];
         L->staged.arena.release();
-        DevBuf *bufs[] = {&L->rend, &L->info, &L->slot_of, &L->mate, &L->keys, &L->hcnt, &L->hidx, &L->win, &L->dir, &L->calls, &L->counters, &L->sorted, &L->sorted_off};
+        DevBuf *bufs[] = {&L->rend, &L->info, &L->mate, &L->tab, &L->win, &L->dir, &L->calls, &L->counters, &L->sorted, &L->sorted_off};
         for (DevBuf *b : bufs) b->release();
         for (int i = 0; i < 5; ++i) if (L->ev[i]) cudaEventDestroy(L->ev[i]);
         if (L->h_counters) cudaFreeHost(L->h_counters);
@@ -1064,7 +1389,11 @@ static int launch_count(md_ctx *c, Lane *L, const Contig &g, const DevReads &R, 
     A.ref = g.d_seq; A.reflen = g.len; A.beg = beg; A.end = end; A.W = W; A.chunk_bounds = g.d_bounds; A.n_chunks = g.n_chunks;
     A.calls = (md_call *) L->calls.p; A.cap = cap_calls; A.dir = (uint2 *) L->dir.p; A.counters = (uint32_t *) L->counters.p; A.hist = c->d_hist; A.lens = c->d_lens;
     const size_t bm = 2 * ((size_t)(W >> 5) + 2) * 4;
-    if (c->count_variant == 3 && W == 16 * ST_THREADS) {
+    if (c->count_variant == 4 && W == 16 * WS_WARPS * 32) {
+        if (mbias) count_warp<2><<<n_win, WS_WARPS * 32, warp_layout(W, 2).total, s>>>(A);
+        else if (kp.minOppositeDepth > 0) count_warp<1><<<n_win, WS_WARPS * 32, warp_layout(W, 1).total, s>>>(A);
+        else count_warp<0><<<n_win, WS_WARPS * 32, warp_layout(W, 0).total, s>>>(A);
+    } else if (c->count_variant >= 3 && W == 16 * ST_THREADS) {
         if (mbias) count_stream<2><<<n_win, ST_THREADS, stream_layout(W, 2).total, s>>>(A);
         else if (kp.minOppositeDepth > 0) count_stream<1><<<n_win, ST_THREADS, stream_layout(W, 1).total, s>>>(A);
         else count_stream<0><<<n_win, ST_THREADS, stream_layout(W, 0).total, s>>>(A);
@@ -1091,24 +1420,24 @@ static int run_pipeline(md_ctx *c, Lane *L, const md_tile_desc *t, const DevRead
     if (mbias && !g.d_bounds) { g_err = "mbias tile without md_set_mbias_chunks"; return -2; }
     const uint32_t n = R.n, W = c->W;
     const uint32_t n_win = (end - beg + W - 1) / W;
-    uint32_t cap_pow2 = 1024; while (cap_pow2 < 2 * (size_t) n + 2) cap_pow2 <<= 1;
+    const uint32_t tab_cap = n + n / 4 + 1024;                         // names <= eligible records <= n  ->  load factor <= 0.8, ~0.4 for paired data
     const bool need_hash = !mbias && !c->kp.noOverlap;
-    if (L->rend.reserve((size_t) n * 4 + 4) || L->info.reserve((size_t) n + 4) || L->slot_of.reserve((size_t) n * 4 + 4) || L->mate.reserve((size_t) n * 4 + 4) ||
+    if (L->rend.reserve((size_t) n * 4 + 4) || L->info.reserve((size_t) n + 4) || L->mate.reserve((size_t) n * 4 + 4) ||
         L->win.reserve((size_t) n_win * 8 + 8) || L->dir.reserve((size_t) n_win * 8 + 8) || L->counters.reserve(C_N * 4)) return -100;
-    if (need_hash && (L->keys.reserve((size_t) cap_pow2 * 8) || L->hcnt.reserve((size_t) cap_pow2 * 4) || L->hidx.reserve((size_t) cap_pow2 * 8))) return -100;
+    if (need_hash && L->tab.reserve((size_t) tab_cap * 4)) return -100;
     const unsigned long long cap_calls = (unsigned long long)(end - beg) + 16;
     if (!mbias && (L->calls.reserve((size_t) cap_calls * sizeof(md_call)) || L->sorted.reserve((size_t) cap_calls * sizeof(md_call)) || L->sorted_off.reserve((size_t) n_win * 4 + 4))) return -100;
     cudaStream_t s = L->stream;
     CK(cudaEventRecord(L->ev[1], s));
     CK(cudaMemsetAsync(L->counters.p, 0, C_N * 4, s));
-    HashTab T; T.keys = (unsigned long long *) L->keys.p; T.cnt = (uint32_t *) L->hcnt.p; T.idx = (uint32_t *) L->hidx.p; T.mask = cap_pow2 - 1;
-    if (need_hash) { CK(cudaMemsetAsync(L->keys.p, 0, (size_t) cap_pow2 * 8, s)); CK(cudaMemsetAsync(L->hcnt.p, 0, (size_t) cap_pow2 * 4, s)); }
+    HashTab T; T.tab = (uint32_t *) L->tab.p; T.cap = tab_cap;
+    if (need_hash) CK(cudaMemsetAsync(L->tab.p, 0xff, (size_t) tab_cap * 4, s));
+    if (n) CK(cudaMemsetAsync(L->mate.p, 0xff, (size_t) n * 4, s));
     KParams kp = c->kp; if (mbias) kp.noOverlap = 1;
     if (n) {
         const uint32_t gb = (n + 255) / 256;
-        prep_kernel<<<gb, 256, 0, s>>>(R, kp, (int32_t *) L->rend.p, (uint8_t *) L->info.p, T, (uint32_t *) L->slot_of.p, (uint32_t *) L->counters.p);
-        pair_kernel<<<gb, 256, 0, s>>>(R, (const int32_t *) L->rend.p, (const uint8_t *) L->info.p, T, (const uint32_t *) L->slot_of.p, (int32_t *) L->mate.p, (uint32_t *) L->counters.p);
-        c->launches += 2;
+        prep_kernel<<<gb, 256, 0, s>>>(R, kp, (int32_t *) L->rend.p, (uint8_t *) L->info.p, T, (int32_t *) L->mate.p, (uint32_t *) L->counters.p);
+        c->launches += 1;
     }
     if (n_win) {
         window_kernel<<<(n_win + 255) / 256, 256, 0, s>>>(R.pos, n, beg, W, n_win, (const uint32_t *) L->counters.p, (uint2 *) L->win.p);
@@ -1193,7 +1522,7 @@ static int finish_counters(md_ctx *c, Lane *L, md_tile_stats *st) {
     if (L->h_counters[C_OVERFLOW]) { g_err = "internal: call buffer overflow"; return -3; }
     L->last_ncalls = ncalls;
     md_tile_stats s; memset(&s, 0, sizeof s);
-    s.n_calls = ncalls; s.n_required = ncalls; s.n_admitted = L->h_counters[C_ADMIT]; s.n_pairs = L->h_counters[C_PAIRED] / 2; s.n_multi = L->h_counters[C_MULTI];
+    s.n_calls = ncalls; s.n_required = ncalls; s.n_admitted = L->h_counters[C_ADMIT]; s.n_pairs = L->h_counters[C_PAIRED]; s.n_multi = L->h_counters[C_MULTI];
     L->last_stats = s;
     if (st) *st = s;
     return 0;
