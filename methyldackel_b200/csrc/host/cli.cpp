@@ -13,6 +13,7 @@
 #include <chrono>
 #include <map>
 #include "tiles.hpp"
+#include "pardecode.hpp"
 #include "format.hpp"
 #include "mbias_report.hpp"
 #include "../../../include/mdhost.h"
@@ -106,10 +107,20 @@ extern "C" uint32_t mdh_chunk_bounds(const char *seq, uint32_t len, unsigned lon
     return n;
 }
 
+// -@ N is the number of host decode threads here (the reference uses it for its pileup workers, extract.c:607).
+// Without -@ the decode pool uses the machine (capped), because the GPU otherwise starves behind one inflate thread.
+static int decode_threads(int n, bool given) {
+    if (given) return n < 1 ? 1 : n;
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char *e = getenv("MD_DECODE_THREADS")) { int v = atoi(e); if (v > 0) return v; }
+    return (int) std::min<unsigned>(hw ? hw : 1, 32);
+}
+
 namespace {
 struct Driver {
     const mdh_backend *be; void *dev = nullptr;
-    std::unique_ptr<BamStream> bam; std::unique_ptr<Fasta> fa; BaiIndex bai; bool have_bai = false;
+    std::unique_ptr<ParallelBam> bam; std::unique_ptr<Fasta> fa; BaiIndex bai; bool have_bai = false;
+    std::unique_ptr<Fragment> frag; size_t frag_i = 0;      // decode cursor shared by consecutive FragTilers
     const BamHeader *hdr = nullptr;
     std::string cur_seq; int cur_seq_tid = -1; bool cur_seq_ok = false;
     const std::string *fetch(uint32_t tid) {
@@ -122,7 +133,7 @@ struct Driver {
     void seek_to(int tid, uint32_t beg) {
         if (!have_bai) return;           // sequential scan: the stream only moves forward and skips earlier contigs
         bool found; uint64_t off = bai.start_offset(tid, beg, found);
-        if (found && off) bam->seek(off);
+        if (found && off) { bam->seek(off); frag.reset(); frag_i = 0; }
     }
 };
 }  // namespace
@@ -130,8 +141,8 @@ struct Driver {
 extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     ExtractOptions o;
     char *opref = nullptr; const char *reg = nullptr, *bedName = nullptr, *bwName = nullptr, *bbmName = nullptr;
-    int c, nThreads = 1, keepStrand = 0; double minConvEff = 0.0;
-    (void) keepStrand; (void) nThreads;
+    int c, nThreads = 1, keepStrand = 0; double minConvEff = 0.0; bool threads_given = false;
+    (void) keepStrand;
     double t_start = now_s();
     memset(&g_stats, 0, sizeof g_stats);
 
@@ -185,7 +196,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         case 'm': o.logit = 1; break;
         case 'f': o.fraction = 1; break;
         case 'c': o.counts = 1; break;
-        case '@': nThreads = atoi(optarg); break;
+        case '@': nThreads = atoi(optarg); threads_given = true; break;
         case '?': default: fprintf(stderr, "Invalid option '%c'\n", c); extract_usage(); return 1;
         }
     }
@@ -205,7 +216,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
 
     Driver d; d.be = be;
     const char *fastaName = argv[optind], *bamName = argv[optind + 1];
-    try { d.bam.reset(new BamStream(bamName)); }
+    try { d.bam.reset(new ParallelBam(bamName, decode_threads(nThreads, threads_given))); }
     catch (std::exception &e) { fprintf(stderr, "Couldn't open %s for reading!\n", bamName); return -4; }
     d.hdr = &d.bam->header();
     d.have_bai = load_bai(bamName, d.bai);
@@ -299,7 +310,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             if (rend > ref->size()) rend = (uint32_t) ref->size();
             if (be->load_contig(d.dev, (int32_t) tid, ref->data(), (uint32_t) ref->size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
             d.seek_to((int) tid, rbeg);
-            Tiler tiler(*d.bam, (int) tid, rbeg, rend, tile_reads);
+            FragTiler tiler(*d.bam, d.frag, d.frag_i, (int) tid, rbeg, rend, tile_reads);
             calls.clear(); calls_head = 0; carry.clear();
             size_t next_chunk = 0;
             // completed tiles arrive in order; hand every finished reference chunk to the writer
@@ -383,8 +394,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
     cfg.keepCpG = 1; cfg.minMapq = 10; cfg.minPhred = 5; cfg.ignoreFlags = 0xF00; cfg.noOverlapMerge = 1;   // MBias.c:312-328, :160
     unsigned long chunkSize = 1000000;
     const char *reg = nullptr, *bedName = nullptr; char *opref = nullptr;
-    int c, SVG = 1, txt = 0, nThreads = 1; double minConvEff = 0.0;
-    (void) nThreads;
+    int c, SVG = 1, txt = 0, nThreads = 1; double minConvEff = 0.0; bool threads_given = false;
     double t_start = now_s();
     memset(&g_stats, 0, sizeof g_stats);
     static struct option lopts[] = {
@@ -422,7 +432,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
         case 'R': cfg.requireFlags = atoi(optarg); break;
         case 'q': cfg.minMapq = atoi(optarg); break;
         case 'p': cfg.minPhred = atoi(optarg); break;
-        case '@': nThreads = atoi(optarg); break;
+        case '@': nThreads = atoi(optarg); threads_given = true; break;
         default: fprintf(stderr, "Invalid option '%c'\n", c); mbias_usage(); return 1;
         }
     }
@@ -439,7 +449,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
 
     Driver d; d.be = be;
     const char *fastaName = argv[optind], *bamName = argv[optind + 1];
-    try { d.bam.reset(new BamStream(bamName)); }
+    try { d.bam.reset(new ParallelBam(bamName, decode_threads(nThreads, threads_given))); }
     catch (std::exception &e) { fprintf(stderr, "Couldn't open %s for reading!\n", bamName); return -4; }
     d.hdr = &d.bam->header();
     d.have_bai = load_bai(bamName, d.bai);
@@ -493,7 +503,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
             if (be->load_contig(d.dev, (int32_t) tid, ref->data(), (uint32_t) ref->size()) != 0 ||
                 be->set_mbias_chunks(d.dev, (int32_t) tid, bounds.data(), (uint32_t) bounds.size() - 1) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
             d.seek_to((int) tid, rbeg);
-            Tiler tiler(*d.bam, (int) tid, rbeg, rend, (size_t) 1 << 19);
+            FragTiler tiler(*d.bam, d.frag, d.frag_i, (int) tid, rbeg, rend, (size_t) 1 << 19);
             carry.clear();
             for (;;) {
                 double t0 = now_s();

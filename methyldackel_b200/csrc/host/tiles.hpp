@@ -90,6 +90,24 @@ struct SoaTile {
         uint64_t *q = qual.grow(qw); memcpy(q, o.qual.data() + o.qual_off[i], qw * 8);
         frag_key.push_back(o.frag_key[i]); rend.push_back(o.rend[i]);
     }
+    // bulk copy of reads [a,b) of another tile whose blobs are laid out in read order (as add() produces them)
+    void add_range_from(const SoaTile &o, size_t a, size_t b) {
+        if (b <= a) return;
+        const size_t k = b - a, on = o.n();
+        memcpy(pos.grow(k), o.pos.data() + a, k * 4); memcpy(flag.grow(k), o.flag.data() + a, k * 2);
+        memcpy(mapq.grow(k), o.mapq.data() + a, k); memcpy(aux.grow(k), o.aux.data() + a, k);
+        memcpy(l_qseq.grow(k), o.l_qseq.data() + a, k * 4); memcpy(frag_key.grow(k), o.frag_key.data() + a, k * 8);
+        memcpy(rend.grow(k), o.rend.data() + a, k * 4);
+        const uint32_t c0 = o.cigar_off[a], c1 = b < on ? o.cigar_off[b] : (uint32_t) o.cigar.size();
+        const uint32_t s0 = o.seq_off[a], s1 = b < on ? o.seq_off[b] : (uint32_t) o.seq.size();
+        const uint32_t q0 = o.qual_off[a], q1 = b < on ? o.qual_off[b] : (uint32_t) o.qual.size();
+        const uint32_t cb = (uint32_t) cigar.size(), sb = (uint32_t) seq.size(), qb = (uint32_t) qual.size();
+        uint32_t *co = cigar_off.grow(k), *so = seq_off.grow(k), *qo = qual_off.grow(k);
+        for (size_t i = 0; i < k; ++i) { co[i] = cb + (o.cigar_off[a + i] - c0); so[i] = sb + (o.seq_off[a + i] - s0); qo[i] = qb + (o.qual_off[a + i] - q0); }
+        memcpy(cigar.grow(c1 - c0), o.cigar.data() + c0, (size_t)(c1 - c0) * 4);
+        memcpy(seq.grow(s1 - s0), o.seq.data() + s0, (size_t)(s1 - s0) * 4);
+        memcpy(qual.grow(q1 - q0), o.qual.data() + q0, (size_t)(q1 - q0) * 8);
+    }
     // Finalise (cigar_off gets its n+1'th entry) and expose as the C-ABI view.
     md_reads_soa view() {
         if (cigar_off.size() == n()) cigar_off.push_back((uint32_t) cigar.size());

@@ -87,3 +87,19 @@ def test_mbias_suggestion_line(built, synth, tmp_path):
     ref_line = [l for l in r.stderr.splitlines() if l.startswith("Suggested inclusion options:")]
     new_line = [l for l in n.stderr.splitlines() if l.startswith("Suggested inclusion options:")]
     assert ref_line and ref_line == new_line
+
+
+def test_parallel_decode_many_small_jobs(built, synth, tmp_path):
+    """forces the multi-threaded decoder to cut the BAM into one job per BGZF block, so that records straddle
+    nearly every job boundary (stitch path), with 5 decode threads"""
+    import subprocess, sys
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    refp, newp = str(tmp_path / "ref"), str(tmp_path / "new")
+    r = run_ref(built["ref_bin"], "extract", ["--CHG", "--mergeContext"], p + ".fa", p + ".bam", refp)
+    assert r.returncode == 0
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import oracle_binding as ob; "
+            "sys.exit(ob.run_host_main('extract', %r, ob.OracleBackend()))") % (cases.ROOT, os.path.join(cases.ROOT, "tests"),
+                                                                               ["--CHG", "--mergeContext", "-@", "5", p + ".fa", p + ".bam", "-o", newp])
+    n = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, MD_DECODE_JOB_BYTES="1"))
+    assert n.returncode == 0, n.stderr
+    assert compare_outputs(refp, newp) == []
