@@ -113,7 +113,7 @@ static int decode_threads(int n, bool given) {
     if (given) return n < 1 ? 1 : n;
     unsigned hw = std::thread::hardware_concurrency();
     if (const char *e = getenv("MD_DECODE_THREADS")) { int v = atoi(e); if (v > 0) return v; }
-    return (int) std::min<unsigned>(hw ? hw : 1, 32);
+    return (int) std::min<unsigned>(hw ? hw : 1, 64);
 }
 
 namespace {

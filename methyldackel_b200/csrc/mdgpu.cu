@@ -137,22 +137,25 @@ __device__ __forceinline__ uint32_t hash_slot(unsigned long long key, uint32_t c
 // (overlaps.c:129-135: the stored record is `a`).  A third record of the same name cannot claim anything: the tile is
 // then flagged (C_MULTI) and replayed exactly on the host.  mate[] must be preset to -1 and tab[] to 0xffffffff.
 __global__ void __launch_bounds__(256) prep_kernel(DevReads R, KParams P, int32_t *rend, uint8_t *info, HashTab T, int32_t *mate, uint32_t *counters) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool ok = false, paired = false, multi = false; int rl = 0;
-    if (i < R.n) {
-        unsigned f = R.flag[i], a = R.aux[i];
-        int strand = dev_strand(f, a);
-        uint32_t ql = 0;
+    // grid-stride over the alignments; the five tile-wide statistics are reduced per thread, then per CTA, so the
+    // global counters see one atomic per CTA instead of one per warp (same-address L2 atomics serialise)
+    uint32_t n_ok = 0, n_paired = 0, n_multi = 0, span_max = 0, lq_max = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R.n; i += gridDim.x * blockDim.x) {
+        const unsigned f = R.flag[i], a = R.aux[i];
+        const int strand = dev_strand(f, a);
+        uint32_t ql = 0; int rl = 0;
         for (uint32_t k = R.cigar_off[i], ke = R.cigar_off[i + 1]; k < ke; ++k) {
-            uint32_t c = __ldg(R.cigar + k), op = c & 15u, len = c >> 4;
+            const uint32_t c = __ldg(R.cigar + k), op = c & 15u, len = c >> 4;
             if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rl += (int) len;
             if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) ql += len;
         }
-        uint32_t lq = R.l_qseq[i];
-        ok = dev_admit(P, f, R.mapq[i], a) && strand != 0 && rl > 0 && ql == lq && lq > 0;
-        bool elig = ok && (f & 1u) && !(f & 12u) && !P.noOverlap;          // overlaps.c:128
+        const uint32_t lq = R.l_qseq[i];
+        const bool ok = dev_admit(P, f, R.mapq[i], a) && strand != 0 && rl > 0 && ql == lq && lq > 0;
+        const bool elig = ok && (f & 1u) && !(f & 12u) && !P.noOverlap;      // overlaps.c:128
         rend[i] = R.pos[i] + rl;
         info[i] = (uint8_t)(strand | (ok ? INFO_ADMIT : 0) | (elig ? INFO_ELIG : 0));
+        lq_max = max(lq_max, lq);
+        if (ok) { ++n_ok; span_max = max(span_max, (uint32_t) rl); }
         if (elig) {
             const unsigned long long key = R.frag_key[i];
             uint32_t h = hash_slot(key, T.cap);
@@ -160,23 +163,30 @@ __global__ void __launch_bounds__(256) prep_kernel(DevReads R, KParams P, int32_
                 const uint32_t old = atomicCAS(T.tab + h, 0xffffffffu, i);
                 if (old == 0xffffffffu) break;                                 // first record of this name
                 if (R.frag_key[old] == key) {                                  // same name: pair up, or detect a third record
-                    if (atomicCAS((int *) mate + old, -1, (int) i) == -1) { mate[i] = (int32_t) old; paired = true; }
-                    else multi = true;
+                    if (atomicCAS((int *) mate + old, -1, (int) i) == -1) { mate[i] = (int32_t) old; ++n_paired; }
+                    else ++n_multi;
                     break;
                 }
                 if (++h == T.cap) h = 0;
             }
         }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, ok), mp = __ballot_sync(0xffffffffu, paired), mm = __ballot_sync(0xffffffffu, multi);
-    int wmax = ok ? rl : 0;
-    uint32_t lqmax = (i < R.n) ? R.l_qseq[i] : 0u;
-    for (int o = 16; o; o >>= 1) { wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o)); lqmax = max(lqmax, __shfl_xor_sync(0xffffffffu, lqmax, o)); }
-    if ((threadIdx.x & 31) == 0) {
-        if (m) { atomicAdd(counters + C_ADMIT, (uint32_t) __popc(m)); atomicMax(counters + C_MAXSPAN, (uint32_t) wmax); }
-        if (mp) atomicAdd(counters + C_PAIRED, (uint32_t) __popc(mp));
-        if (mm) atomicAdd(counters + C_MULTI, (uint32_t) __popc(mm));
-        atomicMax(counters + C_MAXLQ, lqmax);
+    __shared__ uint32_t red[5][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 16; o; o >>= 1) {
+        n_ok += __shfl_xor_sync(0xffffffffu, n_ok, o); n_paired += __shfl_xor_sync(0xffffffffu, n_paired, o); n_multi += __shfl_xor_sync(0xffffffffu, n_multi, o);
+        span_max = max(span_max, __shfl_xor_sync(0xffffffffu, span_max, o)); lq_max = max(lq_max, __shfl_xor_sync(0xffffffffu, lq_max, o));
+    }
+    if (lane == 0) { red[0][warp] = n_ok; red[1][warp] = n_paired; red[2][warp] = n_multi; red[3][warp] = span_max; red[4][warp] = lq_max; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+        for (int k = 0; k < 8; ++k) { a0 += red[0][k]; a1 += red[1][k]; a2 += red[2][k]; a3 = max(a3, red[3][k]); a4 = max(a4, red[4][k]); }
+        if (a0) atomicAdd(counters + C_ADMIT, a0);
+        if (a1) atomicAdd(counters + C_PAIRED, a1);
+        if (a2) atomicAdd(counters + C_MULTI, a2);
+        if (a3) atomicMax(counters + C_MAXSPAN, a3);
+        if (a4) atomicMax(counters + C_MAXLQ, a4);
     }
 }
 
@@ -272,10 +282,10 @@ __device__ __forceinline__ void load_mate(const CountArgs &A, uint32_t i, int mi
 
 // One base that sits on a kept-context column: overlap merge, phred gate, call / variant evidence.
 // b / ql are the read's own base and phred AFTER trimming.  (overlaps.c:81-114, common.c:118-134, extract.c:225-239)
-template <int MODE>
+template <int MODE, bool MATE = true>
 __device__ __forceinline__ void eval_hit(const CountArgs &A, const ReadCtx &rc, uint32_t *cnt, uint32_t W, int w0i, int rp, int qi, unsigned b, unsigned ql, bool siteG) {
     const DevReads &R = A.R;
-    if (rc.mi >= 0 && rp >= rc.mpos && rp < rc.mend) {
+    if (MATE && rc.mi >= 0 && rp >= rc.mpos && rp < rc.mend) {
         const int mq = rc.mate_simple ? (rp - rc.mpos) : dev_qpos_at(R.cigar, rc.mk0, rc.mk1, rc.mpos, rp);
         if (mq >= 0) {                                          // aligned in both mates
             unsigned mb = 15u, mql = 0u;
@@ -973,33 +983,34 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
             const uint64_t s64 = (uint64_t) rr.x + (uint64_t) b * nb;
             if (s64 >= rr.y) break;
             const uint32_t s = (uint32_t) s64, e = min(s + nb, rr.y), i = s + lane;
-            // -- lane 0 streams the batch's bases and phreds (TMA); the descriptor goes to the other lanes by shuffle
-            uint32_t sw0 = 0, sw1 = 0, qw0 = 0, qw1 = 0;
-            if (lane == 0) {
-                sw0 = R.seq_off[s] & ~3u; qw0 = R.qual_off[s] & ~1u;
-                const uint32_t lql = R.l_qseq[e - 1];
-                uint32_t sw_end = min(R.seq_off[e - 1] + ((((lql + 1u) >> 1) + 3u) >> 2), R.seq_words), qw_end = min(R.qual_off[e - 1] + ((lql + 7u) >> 3), R.qual_words);
-                uint32_t sbytes = sw_end > sw0 ? (sw_end - sw0) * 4u : 0u, qbytes = qw_end > qw0 ? (qw_end - qw0) * 8u : 0u;
-                sbytes = min((sbytes + 15u) & ~15u, (uint32_t) WS_SEQ_BYTES); qbytes = min((qbytes + 15u) & ~15u, (uint32_t) WS_QUAL_BYTES);
-                sw1 = sw0 + sbytes / 4u; qw1 = qw0 + qbytes / 8u;
-                mbar_arrive_expect_tx(bar, sbytes + qbytes);
-                if (sbytes) bulk_copy_g2s(sseq, R.seq + sw0, sbytes, bar);
-                if (qbytes) bulk_copy_g2s(squal, R.qual + qw0, qbytes, bar);
-            }
-            // -- every lane: scalars of its alignment, kept range, mate
+            // -- every lane: scalars of its alignment (the first and last lanes' offsets also delimit the batch's byte ranges)
             unsigned inf = 0; bool live = false;
             int pos = 0, lq = 0, mate = -1; unsigned f = 0; uint32_t soff = 0, qoff = 0, k0 = 0, k1 = 0, c0 = 0;
             if (i < e) {
+                soff = R.seq_off[i]; qoff = R.qual_off[i]; lq = (int) R.l_qseq[i];
                 inf = A.info[i];
                 live = (inf & INFO_ADMIT) && (long long) A.rend[i] > w0;
                 if (live) {
-                    pos = R.pos[i]; lq = (int) R.l_qseq[i]; f = R.flag[i]; soff = R.seq_off[i]; qoff = R.qual_off[i];
+                    pos = R.pos[i]; f = R.flag[i];
                     k0 = R.cigar_off[i]; k1 = R.cigar_off[i + 1];
                     mate = (MODE == 2) ? -1 : A.mate[i];
                     c0 = __ldg(R.cigar + k0);
                 }
             }
-            sw0 = __shfl_sync(0xffffffffu, sw0, 0); sw1 = __shfl_sync(0xffffffffu, sw1, 0); qw0 = __shfl_sync(0xffffffffu, qw0, 0); qw1 = __shfl_sync(0xffffffffu, qw1, 0);
+            // -- lane 0 streams the batch's bases and phreds into the warp's staging buffer (TMA, completion on the warp's mbarrier)
+            const int last = (int)(e - 1 - s);
+            uint32_t sw0 = __shfl_sync(0xffffffffu, soff, 0) & ~3u, qw0 = __shfl_sync(0xffffffffu, qoff, 0) & ~1u;
+            const uint32_t lql = (uint32_t) __shfl_sync(0xffffffffu, lq, last);
+            uint32_t sw_end = min(__shfl_sync(0xffffffffu, soff, last) + ((((lql + 1u) >> 1) + 3u) >> 2), R.seq_words);
+            uint32_t qw_end = min(__shfl_sync(0xffffffffu, qoff, last) + ((lql + 7u) >> 3), R.qual_words);
+            uint32_t sbytes = sw_end > sw0 ? (sw_end - sw0) * 4u : 0u, qbytes = qw_end > qw0 ? (qw_end - qw0) * 8u : 0u;
+            sbytes = min((sbytes + 15u) & ~15u, (uint32_t) WS_SEQ_BYTES); qbytes = min((qbytes + 15u) & ~15u, (uint32_t) WS_QUAL_BYTES);
+            const uint32_t sw1 = sw0 + sbytes / 4u, qw1 = qw0 + qbytes / 8u;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar, sbytes + qbytes);
+                if (sbytes) bulk_copy_g2s(sseq, R.seq + sw0, sbytes, bar);
+                if (qbytes) bulk_copy_g2s(squal, R.qual + qw0, qbytes, bar);
+            }
             ReadCtx rc; rc.mi = -1; rc.lo = 0; rc.hi = 0; rc.strand = 1; rc.wantG = false; rc.rd2 = 0;
             bool staged = false;
             if (live) {
@@ -1025,10 +1036,11 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
             const uint32_t *own_bm = rc.wantG ? bmG : bmC, *opp_bm = rc.wantG ? bmC : bmG;
             uint32_t k = k0; int p = pos, q = 0, opq = 0, opp_ = 0, ra = 0, rb = 0, wi = 0; unsigned cur = 0, curo = 0; bool in_op = false;
             bool done = !(live && !direct);
-            uint32_t qn = 0;                                            // queued candidates (warp-uniform)
+            uint32_t qa = 0, qb2 = 0;                                   // queued candidates: plain / inside the mate's span (warp-uniform)
+            uint32_t *queueB = queue + WS_QUEUE / 2;
             for (;;) {
                 // advance to the next candidate (divergent, cheap)
-                bool has = false; uint32_t ent = 0;
+                bool has = false; uint32_t ent = 0; bool inmate = false;
                 while (!done) {
                     if (cur | curo) {
                         const unsigned any = cur | curo; const int bit = __ffs(any) - 1;
@@ -1036,6 +1048,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
                         cur &= ~(1u << bit); curo &= ~(1u << bit);
                         const int rel = (wi << 5) + bit, qi = opq + (w0i + rel - opp_);
                         ent = (uint32_t) lane | ((uint32_t) rel << 5) | ((uint32_t) qi << 17) | (is_own ? 0u : 0x80000000u);
+                        inmate = rc.mi >= 0 && (w0i + rel) >= rc.mpos && (w0i + rel) < rc.mend;
                         has = true; break;
                     }
                     if (in_op && wi < ((rb - 1) >> 5)) {
@@ -1061,29 +1074,45 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
                     } else if (op == 1 || op == 4) q += len;
                     else if (op == 2 || op == 3) p += len;
                 }
-                const unsigned hm = __ballot_sync(0xffffffffu, has);
-                if (has) queue[qn + __popc(hm & ((1u << lane) - 1u))] = ent;
-                qn += __popc(hm);
-                const bool all_done = hm == 0u;                           // no lane produced anything: every iterator is exhausted
+                // candidates that need the mate's base/phred (global-memory look-ups) are queued apart, so that their latency
+                // is paid once per 32 look-ups instead of once per round
+                const unsigned hmA = __ballot_sync(0xffffffffu, has && !inmate), hmB = __ballot_sync(0xffffffffu, has && inmate);
+                if (has) { if (inmate) queueB[qb2 + __popc(hmB & ((1u << lane) - 1u))] = ent; else queue[qa + __popc(hmA & ((1u << lane) - 1u))] = ent; }
+                qa += __popc(hmA); qb2 += __popc(hmB);
+                const bool all_done = (hmA | hmB) == 0u;                  // no lane produced anything: every iterator is exhausted
                 __syncwarp();
-                while (qn >= 32u || (all_done && qn > 0u)) {
-                    const uint32_t take = min(qn, 32u);
+                while (qa >= 32u || (all_done && qa > 0u)) {
+                    const uint32_t take = min(qa, 32u);
                     if ((uint32_t) lane < take) {
-                        const uint32_t en = queue[qn - take + lane];
+                        const uint32_t en = queue[qa - take + lane];
                         const int src = en & 31u, rel = (en >> 5) & 0xfffu, qi = (en >> 17) & 0x3fffu; const bool is_opp = en >> 31;
                         const uint32_t *cx = rctx + WS_CTX_WORDS * src;
                         const uint32_t c0w = cx[0], c1w = cx[1];
                         ReadCtx hc;
-                        hc.wantG = c1w & 1u; hc.rd2 = (c1w >> 1) & 1u; hc.strand = (c1w >> 8) & 7u; hc.mi = (c1w & 4u) ? 0 : -1;
-                        if (hc.mi >= 0) {
-                            hc.is_a = (c1w & 8u) != 0; hc.mate_simple = (c1w & 16u) != 0;
-                            hc.mpos = (int) cx[2]; hc.mend = (int) cx[3]; hc.msoff = cx[4]; hc.mqoff = cx[5]; hc.mlo = (int)(cx[6] & 0xffffu); hc.mhi = (int)(cx[6] >> 16); hc.mk0 = cx[7]; hc.mk1 = cx[8];
-                        }
+                        hc.wantG = c1w & 1u; hc.rd2 = (c1w >> 1) & 1u; hc.strand = (c1w >> 8) & 7u; hc.mi = -1;
                         const unsigned byte = sseq[(c0w & 0xffffu) + (qi >> 1)];
                         const unsigned bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4), ql = squal[(c0w >> 16) + qi];
-                        eval_hit<MODE>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
+                        eval_hit<MODE, false>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
                     }
-                    qn -= take;
+                    qa -= take;
+                    __syncwarp();
+                }
+                while (qb2 >= 32u || (all_done && qb2 > 0u)) {
+                    const uint32_t take = min(qb2, 32u);
+                    if ((uint32_t) lane < take) {
+                        const uint32_t en = queueB[qb2 - take + lane];
+                        const int src = en & 31u, rel = (en >> 5) & 0xfffu, qi = (en >> 17) & 0x3fffu; const bool is_opp = en >> 31;
+                        const uint32_t *cx = rctx + WS_CTX_WORDS * src;
+                        const uint32_t c0w = cx[0], c1w = cx[1];
+                        ReadCtx hc;
+                        hc.wantG = c1w & 1u; hc.rd2 = (c1w >> 1) & 1u; hc.strand = (c1w >> 8) & 7u; hc.mi = 0;
+                        hc.is_a = (c1w & 8u) != 0; hc.mate_simple = (c1w & 16u) != 0;
+                        hc.mpos = (int) cx[2]; hc.mend = (int) cx[3]; hc.msoff = cx[4]; hc.mqoff = cx[5]; hc.mlo = (int)(cx[6] & 0xffffu); hc.mhi = (int)(cx[6] >> 16); hc.mk0 = cx[7]; hc.mk1 = cx[8];
+                        const unsigned byte = sseq[(c0w & 0xffffu) + (qi >> 1)];
+                        const unsigned bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4), ql = squal[(c0w >> 16) + qi];
+                        eval_hit<MODE, true>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
+                    }
+                    qb2 -= take;
                     __syncwarp();
                 }
                 if (all_done) break;
@@ -1435,7 +1464,7 @@ static int run_pipeline(md_ctx *c, Lane *L, const md_tile_desc *t, const DevRead
     if (n) CK(cudaMemsetAsync(L->mate.p, 0xff, (size_t) n * 4, s));
     KParams kp = c->kp; if (mbias) kp.noOverlap = 1;
     if (n) {
-        const uint32_t gb = (n + 255) / 256;
+        const uint32_t gb = std::min<uint32_t>((n + 255) / 256, 148u * 8u);     // 8 CTAs of 256 threads per SM, grid-stride
         prep_kernel<<<gb, 256, 0, s>>>(R, kp, (int32_t *) L->rend.p, (uint8_t *) L->info.p, T, (int32_t *) L->mate.p, (uint32_t *) L->counters.p);
         c->launches += 1;
     }
