@@ -9,7 +9,7 @@ Contract (see the task brief): `python bench.py --gpus N --steps K --warmup W` p
   * value     : alignments / s with the SoA batch already resident in HBM (CUDA-event timed, max over ranks).
   * e2e       : the same through md_extract_tile() with HOST (page-locked) SoA buffers: H2D copy of the batch,
                 kernels, D2H of the compact call records, every step.
-  * roofline  : count_kernel, algorithmic bytes (249 B per 150M alignment + 1 B per reference
+  * roofline  : count_warp (the dominant kernel), algorithmic bytes (249 B per 150M alignment + 1 B per reference
                 base + 8 B per reported cytosine) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
   * cpu_baseline : oracle/_ref/MethylDackel (the reference's own C sources, see oracle/Makefile) with -@ <all cores>
                 on a bounded region of the same BAM.
@@ -311,9 +311,22 @@ def main():
     alg = algorithmic_bytes(soa, reflen, st.n_calls)
     count_ms = ev_count / args.steps
     achieved = alg / (count_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "count_kernel<0>", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+    roofline = {"bound": "hbm", "kernel": "count_warp<0>", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 (of fallback)",
                 "algorithmic_bytes_per_launch": int(alg), "kernel_ms": round(count_ms, 4), "prep_pair_window_ms": round(ev_prep / args.steps, 4), "traffic": None}
+
+    # ------------------------------------------------------------ the drop-in binary from the BAM file (informational)
+    cli = None
+    if world == 1:
+        binp = os.path.join(ROOT, "methyldackel_b200", "lib", "MethylDackel")
+        outp = os.path.join(tmpdir, "cli_out")
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            subprocess.run([binp, "extract", prefix + ".fa", prefix + ".bam", "-o", outp], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            ts.append(time.perf_counter() - t0)
+        cli = {"value": round(n / min(ts) / 1e6, 3), "unit": UNIT, "seconds": round(min(ts), 3),
+               "what": "lib/MethylDackel extract <fa> <bam> (process start, CUDA context, multi-threaded BGZF inflate + decode, H2D, kernels, D2H, text output), best of 3"}
 
     # ------------------------------------------------------------ CPU baseline (reference build, all host threads, bounded sample)
     cpu = None
@@ -326,7 +339,7 @@ def main():
 
     out = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
-           "config": {"workload": workload, "alignments_per_gpu": n, "contig_bp": reflen, "options": "extract defaults (-q 10 -p 5 -F 0xF00, CpG only)",
+           "config": {"workload": workload, "alignments_per_gpu": n, "contig_bp": reflen, "soa_phred_bits": int(soa.qual_bits) or 8, "options": "extract defaults (-q 10 -p 5 -F 0xF00, CpG only)",
                       "parallelism": "contig interval per GPU, no collective", "l2": "inputs (%.0f MB SoA per GPU) larger than the 126 MB L2" % (soa_bytes(soa) / 1e6)},
            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(n_e2e_calls * 16 + 32 * len(tiles)),
                    "ms_per_step": round(e2e_s * 1e3, 3), "tiles_per_step": len(tiles), "lanes": NL,
@@ -334,6 +347,8 @@ def main():
                    "path": "md_submit_tile()/md_collect_tile(): page-locked host SoA tiles -> H2D -> kernels -> D2H md_call records, 3 lanes in flight, every step"},
            "gpu_launches": int(launches), "wall_ms_per_step_device_resident": round(1e3 * wall_dev / args.steps, 3),
            "roofline": roofline, "clocks": sampler.summary(), "calls_per_step": int(st.n_calls), "pairs_per_step": int(st.n_pairs)}
+    if cli is not None:
+        out["cli_from_bam"] = cli
     if cpu is not None:
         out["cpu_baseline"] = cpu
     print(json.dumps(out))

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MDGPU_ABI_VERSION 1
+#define MDGPU_ABI_VERSION 2
 
 /* ---- options that reach the hot path: the subset of `Config`
  *      (MethylDackel.h:90-126) read by filter_func / the per-column loop ---- */
@@ -66,7 +66,16 @@ typedef struct md_reads_soa {
     const uint32_t *cigar;       /* BAM encoding: len<<4 | op                                   */
     const uint32_t *seq;         /* 4-bit bases, BAM nibble order (high nibble first in each
                                     byte), each read padded to a 32-bit word                    */
-    const uint64_t *qual;        /* phred bytes, each read padded to a 64-bit word              */
+    const uint64_t *qual;        /* phreds, each read padded to a 64-bit word: plain bytes when
+                                    qual_bits is 8 (or 0), else qual_bits-wide codes, base j of a
+                                    read at bit j*qual_bits of its words (little endian)          */
+    uint32_t qual_bits;          /* 8, 4 or 2 (0 means 8).  Sequencers emit few distinct phreds
+                                    (4 on current Illumina instruments), so a tile whose alphabet
+                                    fits is shipped as codes + table: the PCIe and HBM bytes of the
+                                    largest column shrink 2-4x.  Lossless: qual_lut[code] is the
+                                    phred byte the reference would read with bam_get_qual()        */
+    uint8_t  qual_lut[16];
+    uint8_t  reserved_[12];
 } md_reads_soa;
 
 typedef struct md_tile_desc {

@@ -44,6 +44,7 @@ class MdReadsSoa(C.Structure):
         ("pos", C.POINTER(C.c_int32)), ("flag", C.POINTER(C.c_uint16)), ("mapq", C.POINTER(C.c_uint8)), ("aux", C.POINTER(C.c_uint8)),
         ("l_qseq", C.POINTER(C.c_uint32)), ("cigar_off", C.POINTER(C.c_uint32)), ("seq_off", C.POINTER(C.c_uint32)), ("qual_off", C.POINTER(C.c_uint32)),
         ("frag_key", C.POINTER(C.c_uint64)), ("cigar", C.POINTER(C.c_uint32)), ("seq", C.POINTER(C.c_uint32)), ("qual", C.POINTER(C.c_uint64)),
+        ("qual_bits", C.c_uint32), ("qual_lut", C.c_uint8 * 16), ("reserved_", C.c_uint8 * 12),
     ]
 
 

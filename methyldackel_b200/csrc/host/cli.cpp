@@ -116,6 +116,8 @@ static int decode_threads(int n, bool given) {
     return (int) std::min<unsigned>(hw ? hw : 1, 64);
 }
 
+static bool pack_quals_enabled() { const char *e = getenv("MD_QUAL_PACK"); return !(e && e[0] == '0'); }
+
 namespace {
 struct Driver {
     const mdh_backend *be; void *dev = nullptr;
@@ -291,6 +293,10 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         std::vector<std::unique_ptr<SoaTile>> ring;
         for (int k = 0; k < (use_async ? 3 : 1); ++k) ring.emplace_back(new SoaTile(use_async ? &pin : nullptr));
         const size_t tile_reads = use_async ? ((size_t) 1 << 17) : ((size_t) 1 << 19);
+        // phred column re-encoded as 2/4-bit codes when the tile's alphabet allows (md_reads_soa::qual_bits)
+        const bool pack_q = pack_quals_enabled();
+        std::vector<std::unique_ptr<PodVec<uint64_t>>> qscratch; std::vector<std::unique_ptr<PodVec<uint32_t>>> qoffscratch;
+        for (size_t k = 0; k < ring.size(); ++k) { qscratch.emplace_back(new PodVec<uint64_t>(use_async ? &pin : nullptr)); qoffscratch.emplace_back(new PodVec<uint32_t>(use_async ? &pin : nullptr)); }
         SoaTile carry;
         std::vector<md_call> calls; size_t calls_head = 0;
         std::vector<md_call> tile_calls;
@@ -352,6 +358,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
                 g_stats.t_decode_s += now_s() - t0;
                 if (!got) break;
                 if (tile.n() == 0) { if (!use_async) absorb(tile.end, false); continue; }
+                if (pack_q) tile.pack_quals(*qscratch[rk % ring.size()], *qoffscratch[rk % ring.size()]);
                 md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end};
                 uint64_t cap = (uint64_t)(tile.end - tile.beg) + 16;
                 g_stats.n_records += tile.n(); g_stats.n_tiles++;
@@ -487,6 +494,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
             if (c0 > c1) c0 = c1;
         }
         SoaTile tile, carry;
+        PodVec<uint64_t> mb_qscratch; PodVec<uint32_t> mb_qoffscratch;
         size_t ci = c0;
         while (ci < c1 && rc == 0) {
             uint32_t tid = all[ci].tid;
@@ -511,6 +519,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
                 g_stats.t_decode_s += now_s() - t0;
                 if (!got) break;
                 if (tile.n() == 0) continue;
+                if (pack_quals_enabled()) tile.pack_quals(mb_qscratch, mb_qoffscratch);
                 md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end}; md_tile_stats st;
                 t0 = now_s();
                 int r = be->mbias_tile(d.dev, &td, &v, &st);
@@ -555,6 +564,7 @@ extern "C" int mdh_bam_read_region(mdh_bam *b, int tid, uint32_t beg, uint32_t e
         SoaTile carry;
         b->tile.clear();
         t.next(b->tile, carry);
+        if (pack_quals_enabled()) { PodVec<uint64_t> sq; PodVec<uint32_t> so; b->tile.pack_quals(sq, so); }
         *out = b->tile.view();
         return 0;
     } catch (std::exception &e) { g_err = e.what(); return -1; }
@@ -571,6 +581,7 @@ extern "C" int mdh_bam_make_tiles(mdh_bam *b, int tid, uint32_t beg, uint32_t en
             std::unique_ptr<SoaTile> tile(new SoaTile());
             if (!t.next(*tile, carry)) break;
             if (tile->n() == 0) continue;
+            if (pack_quals_enabled()) { PodVec<uint64_t> sq; PodVec<uint32_t> so; tile->pack_quals(sq, so); }
             b->tiles.push_back(std::move(tile));
         }
         return (int) b->tiles.size();

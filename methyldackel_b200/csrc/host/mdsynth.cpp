@@ -6,6 +6,7 @@
 //           [--isize-mean 300 --isize-sd 60 --isize-min 150 --isize-max 800]
 //           [--genome-seed 1234] [--read-seed 5678] [--level 1]
 //           [--bismark-tags] [--nondirectional F] [--single-frac F] [--lower-frac F] [--n-frac F]
+//           [--quals N]  (N distinct phred values instead of the 4 binned ones)
 //           [--clean]   (no flag noise / indels / clips: every record is a plain properly paired 150M)
 #include "hostio.hpp"
 #include <cmath>
@@ -36,6 +37,7 @@ struct Opts {
     int level = 1;
     bool bismark_tags = false, clean = false;
     double nondirectional = 0.0, single_frac = 0.0, lower_frac = 0.0, n_frac = 0.0;
+    int quals = 4;          // distinct phred values: 4 = binned Illumina-like; more = uniform over [2, 2+quals)
 };
 
 struct Rec { int32_t pos; uint64_t order; std::vector<uint8_t> data; int32_t end; };
@@ -69,6 +71,7 @@ int main(int argc, char **argv) {
         else if (a == "--single-frac") o.single_frac = atof(val().c_str());
         else if (a == "--lower-frac") o.lower_frac = atof(val().c_str());
         else if (a == "--n-frac") o.n_frac = atof(val().c_str());
+        else if (a == "--quals") o.quals = atoi(val().c_str());
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
     }
     if (o.out.empty()) { fprintf(stderr, "usage: mdsynth --out PREFIX [options]\n"); return 1; }
@@ -219,6 +222,7 @@ int main(int argc, char **argv) {
                 if (end > G) continue;
                 for (int j = 0; j < L; ++j) {
                     double u = r.uni(); uint8_t ql = u < 0.75 ? 37 : u < 0.90 ? 25 : u < 0.98 ? 11 : 2;
+                    if (o.quals != 4) ql = (uint8_t)(2 + r.below((uint32_t) o.quals));
                     quals[(size_t) j] = ql;
                     if (r.uni() < std::pow(10.0, -ql / 10.0)) { char c; do c = "ACGT"[r.next() >> 62]; while (c == (char) bases[(size_t) j]); bases[(size_t) j] = (uint8_t) c; }
                 }

@@ -40,6 +40,7 @@ public:
     }
     void push_back(const T &v) { if (n_ == cap_) reserve(n_ + 1); p_[n_++] = v; }
     T *grow(size_t k) { reserve(n_ + k); T *r = p_ + n_; n_ += k; return r; }
+    void swap(PodVec &o) { std::swap(a_, o.a_); std::swap(p_, o.p_); std::swap(n_, o.n_); std::swap(cap_, o.cap_); }
 private:
     void *alloc_(size_t b) { return (a_ && a_->alloc) ? a_->alloc(b) : malloc(b); }
     void free_(void *p) { if (!p) return; if (a_ && a_->release) a_->release(p); else free(p); }
@@ -51,11 +52,12 @@ struct SoaTile {
         : pos(a), flag(a), mapq(a), aux(a), l_qseq(a), cigar_off(a), seq_off(a), qual_off(a), frag_key(a), cigar(a), seq(a), qual(a), rend(nullptr) {}
     int32_t tid = -1;
     uint32_t beg = 0, end = 0;
+    uint32_t qual_bits = 8; uint8_t qual_lut[16] = {0};      // phred encoding of qual[] (include/mdgpu.h)
     PodVec<int32_t> pos; PodVec<uint16_t> flag; PodVec<uint8_t> mapq, aux; PodVec<uint32_t> l_qseq, cigar_off, seq_off, qual_off;
     PodVec<uint64_t> frag_key; PodVec<uint32_t> cigar, seq; PodVec<uint64_t> qual;
     PodVec<int32_t> rend;   // host-only: reference end of each read (for carry-over between tiles)
     size_t n() const { return pos.size(); }
-    void clear() { pos.clear(); flag.clear(); mapq.clear(); aux.clear(); l_qseq.clear(); cigar_off.clear(); seq_off.clear(); qual_off.clear(); frag_key.clear(); cigar.clear(); seq.clear(); qual.clear(); rend.clear(); }
+    void clear() { qual_bits = 8; pos.clear(); flag.clear(); mapq.clear(); aux.clear(); l_qseq.clear(); cigar_off.clear(); seq_off.clear(); qual_off.clear(); frag_key.clear(); cigar.clear(); seq.clear(); qual.clear(); rend.clear(); }
     size_t bytes() const { return n() * (4 + 2 + 1 + 1 + 4 + 4 + 4 + 4 + 8) + 4 + cigar.size() * 4 + seq.size() * 4 + qual.size() * 8; }
 
     void add(const BamRec &r) {
@@ -108,6 +110,30 @@ struct SoaTile {
         memcpy(seq.grow(s1 - s0), o.seq.data() + s0, (size_t)(s1 - s0) * 4);
         memcpy(qual.grow(q1 - q0), o.qual.data() + q0, (size_t)(q1 - q0) * 8);
     }
+    // Re-encode the phred column as 2- or 4-bit codes when the tile's alphabet allows it (lossless; see md_reads_soa).
+    // `scratch` receives the packed words and is swapped in, so a ring of tiles re-uses its allocations.
+    void pack_quals(PodVec<uint64_t> &scratch, PodVec<uint32_t> &scratch_off) {
+        if (qual_bits != 8 || n() == 0) return;
+        bool seen[256] = {false};
+        for (size_t i = 0; i < n(); ++i) { const uint8_t *q = (const uint8_t *)(qual.data() + qual_off[i]); for (uint32_t j = 0, l = l_qseq[i]; j < l; ++j) seen[q[j]] = true; }
+        uint8_t code[256]; int na = 0;
+        for (int v = 0; v < 256; ++v) if (seen[v]) { if (na < 16) { qual_lut[na] = (uint8_t) v; code[v] = (uint8_t) na; } ++na; }
+        if (na > 16) return;
+        const uint32_t bits = na <= 4 ? 2 : 4;
+        for (int k = na; k < 16; ++k) qual_lut[k] = 0;
+        scratch.clear(); scratch_off.clear();
+        for (size_t i = 0; i < n(); ++i) {
+            const uint32_t l = l_qseq[i]; const size_t words = ((size_t) l * bits + 63) / 64;
+            scratch_off.push_back((uint32_t) scratch.size());
+            uint64_t *w = scratch.grow(words);
+            const uint8_t *q = (const uint8_t *)(qual.data() + qual_off[i]);
+            for (size_t k = 0; k < words; ++k) w[k] = 0;
+            if (bits == 2) for (uint32_t j = 0; j < l; ++j) w[j >> 5] |= (uint64_t) code[q[j]] << ((j & 31) * 2);
+            else for (uint32_t j = 0; j < l; ++j) w[j >> 4] |= (uint64_t) code[q[j]] << ((j & 15) * 4);
+        }
+        qual.swap(scratch); qual_off.swap(scratch_off);
+        qual_bits = bits;
+    }
     // Finalise (cigar_off gets its n+1'th entry) and expose as the C-ABI view.
     md_reads_soa view() {
         if (cigar_off.size() == n()) cigar_off.push_back((uint32_t) cigar.size());
@@ -117,6 +143,7 @@ struct SoaTile {
         v.pos = pos.data(); v.flag = flag.data(); v.mapq = mapq.data(); v.aux = aux.data(); v.l_qseq = l_qseq.data();
         v.cigar_off = cigar_off.data(); v.seq_off = seq_off.data(); v.qual_off = qual_off.data(); v.frag_key = frag_key.data();
         v.cigar = cigar.data(); v.seq = seq.data(); v.qual = qual.data();
+        v.qual_bits = qual_bits; memcpy(v.qual_lut, qual_lut, 16);
         return v;
     }
 };

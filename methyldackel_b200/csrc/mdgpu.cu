@@ -49,6 +49,7 @@ extern "C" int md_abi_version(void) { return MDGPU_ABI_VERSION; }
 // device-side views
 struct DevReads {
     uint32_t n; uint32_t seq_words, qual_words;   // totals of seq[] (32-bit words) / qual[] (64-bit words)
+    uint32_t qbits; unsigned char qlut[16];       // phred encoding of qual[]: 8 = bytes, 2/4 = codes through qlut (md_reads_soa::qual_bits)
     const int32_t *pos; const uint16_t *flag; const uint8_t *mapq; const uint8_t *aux; const uint32_t *l_qseq;
     const uint32_t *cigar_off, *seq_off, *qual_off; const uint64_t *frag_key;
     const uint32_t *cigar, *seq; const uint64_t *qual;
@@ -121,10 +122,19 @@ __device__ __forceinline__ unsigned dev_base(const uint32_t *seq, uint32_t off, 
     unsigned byte = (w >> (((q >> 1) & 3) << 3)) & 0xffu;
     return (q & 1) ? (byte & 0xfu) : (byte >> 4);
 }
-__device__ __forceinline__ unsigned dev_qual(const uint64_t *qual, uint32_t off, int q) {
-    const unsigned char *p = (const unsigned char *) (qual + off);
-    return __ldg(p + q);
+__device__ __forceinline__ unsigned dev_qual(const DevReads &R, uint32_t off, int q) {
+    const unsigned char *p = (const unsigned char *) (R.qual + off);
+    if (R.qbits == 8u) return __ldg(p + q);
+    const unsigned bit = (unsigned) q * R.qbits;                        // 2- or 4-bit codes never straddle a byte
+    return R.qlut[(__ldg(p + (bit >> 3)) >> (bit & 7u)) & ((1u << R.qbits) - 1u)];
 }
+// same, from the staged copy in shared memory
+__device__ __forceinline__ unsigned staged_qual(const DevReads &R, const unsigned char *p, int q) {
+    if (R.qbits == 8u) return p[q];
+    const unsigned bit = (unsigned) q * R.qbits;
+    return R.qlut[(p[bit >> 3] >> (bit & 7u)) & ((1u << R.qbits) - 1u)];
+}
+__device__ __forceinline__ uint32_t qual_words_of(const DevReads &R, uint32_t lq) { return (lq * R.qbits + 63u) >> 6; }
 
 __device__ __forceinline__ uint32_t hash_slot(unsigned long long key, uint32_t cap) {
     const uint32_t h = (uint32_t)((key * 0x9e3779b97f4a7c15ull) >> 32);
@@ -289,7 +299,7 @@ __device__ __forceinline__ void eval_hit(const CountArgs &A, const ReadCtx &rc, 
         const int mq = rc.mate_simple ? (rp - rc.mpos) : dev_qpos_at(R.cigar, rc.mk0, rc.mk1, rc.mpos, rp);
         if (mq >= 0) {                                          // aligned in both mates
             unsigned mb = 15u, mql = 0u;
-            if (mq >= rc.mlo && mq < rc.mhi) { mb = dev_base(R.seq, rc.msoff, mq); mql = dev_qual(R.qual, rc.mqoff, mq); }
+            if (mq >= rc.mlo && mq < rc.mhi) { mb = dev_base(R.seq, rc.msoff, mq); mql = dev_qual(R, rc.mqoff, mq); }
             const unsigned qa = rc.is_a ? ql : mql, qb = rc.is_a ? mql : ql;
             unsigned na, nb;
             if (b != mb) {                                      // a is tested first (overlaps.c:91-100)
@@ -346,7 +356,7 @@ __device__ __forceinline__ void slow_read(const CountArgs &A, uint32_t i, unsign
                 const bool siteG = (cx & 4u) != 0;
                 if (MODE != 1 && siteG != rc.wantG) continue;   // wrong-strand columns only matter to the variant filter
                 unsigned b = 15u, ql = 0u;
-                if (qi >= rc.lo && qi < rc.hi) { b = dev_base(R.seq, rc.soff, qi); ql = dev_qual(R.qual, rc.qoff, qi); }
+                if (qi >= rc.lo && qi < rc.hi) { b = dev_base(R.seq, rc.soff, qi); ql = dev_qual(R, rc.qoff, qi); }
                 eval_hit<MODE>(A, rc, cnt, A.W, (int) w0, rp, qi, b, ql, siteG);
             }
             p += len; q += len;
@@ -355,220 +365,9 @@ __device__ __forceinline__ void slow_read(const CountArgs &A, uint32_t i, unsign
     }
 }
 
-// 16 mask bits starting at window-relative position r (any int); bits outside [0, nbits) read as 0.
-// `bm` has one zero guard word on each side (index 0 is the guard).
-__device__ __forceinline__ unsigned mask16_at(const uint32_t *bm, int r, int nwords) {
-    if (r <= -16 || r >= nwords * 32) return 0u;
-    const int wi = (r >> 5) + 1;                               // arithmetic shift: r in [-15,-1] -> word -1 -> guard
-    const uint32_t lo = bm[wi], hi = bm[wi + 1];
-    return __funnelshift_r(lo, hi, (unsigned) r & 31u) & 0xffffu;
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(256) count_kernel(CountArgs A) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t W = A.W;
-    const int NW = (int)(W >> 5);
-    unsigned char *ctx = smem;                                   // [W]
-    unsigned char *refw = smem + W;                              // [W + 16] reference bytes w0-2 .. w0+W+2
-    uint32_t *bmC = (uint32_t *)(smem + 2 * W + 16);             // [NW + 2] C-site bitmap with guard words
-    uint32_t *bmG = bmC + NW + 2;                                // [NW + 2]
-    uint32_t *cnt = bmG + NW + 2;                                // extract: meth[W], unmeth[W] (, noff[W], nvar[W]); mbias: hist
-    const uint32_t w = blockIdx.x;
-    const long long w0 = (long long) A.beg + (long long) w * W;
-    const long long own1 = min((long long) A.end, w0 + (long long) W);   // owned positions of this window: [w0, own1)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-
-    // ---- stage reference + classify -------------------------------------------------------------
-    for (uint32_t t = tid; t < W + 4; t += blockDim.x) {
-        long long p = w0 - 2 + t;
-        refw[t] = (p >= 0 && p < (long long) A.reflen) ? __ldg(A.ref + p) : (unsigned char) 'N';
-    }
-    const uint32_t ncnt = (MODE == 2) ? 4u * 2u * MB_SM_Q * 2u : (MODE == 1 ? 4u * W : 2u * W);
-    for (uint32_t t = tid; t < ncnt; t += blockDim.x) cnt[t] = 0;
-    if (tid < 4) { uint32_t *g = (tid & 1) ? bmG : bmC; g[(tid & 2) ? NW + 1 : 0] = 0; }
-    __syncthreads();
-    for (uint32_t t = tid; t < W; t += blockDim.x) {             // W is a multiple of 256, so warps stay converged for the ballots
-        long long p = w0 + t;
-        unsigned c = 0;
-        if (p < own1) {
-            if (MODE == 2) {
-                // MBias.c:147,170-178: context inside the reference chunk's own window contig[cs..ce]
-                uint32_t lo = 0, hi = A.n_chunks;
-                while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if ((long long) A.chunk_bounds[mid] <= p) lo = mid; else hi = mid; }
-                if (A.n_chunks && p >= (long long) A.chunk_bounds[lo] && p < (long long) A.chunk_bounds[lo + 1]) {
-                    long long cs = A.chunk_bounds[lo], ce = A.chunk_bounds[lo + 1];
-                    long long last = ce < (long long) A.reflen ? ce : (long long) A.reflen - 1;
-                    auto get = [&](long long x) -> unsigned char { long long o = x - (w0 - 2); return (o >= 0 && o < (long long) W + 4) ? refw[o] : __ldg(A.ref + x); };
-                    c = dev_context(get, p, cs, last + 1);
-                }
-            } else {
-                auto get = [&](long long x) -> unsigned char { return refw[x - (w0 - 2)]; };
-                c = dev_context(get, p, 0, (long long) A.reflen);
-            }
-            if (c && !((A.P.keepMask >> ((c & 3) - 1)) & 1)) c = 0;      // extract.c:408,411,414
-        }
-        ctx[t] = (unsigned char) c;
-        const unsigned mc = __ballot_sync(0xffffffffu, c != 0 && !(c & 4u)), mg = __ballot_sync(0xffffffffu, (c & 4u) != 0);
-        if (lane == 0) { bmC[(t >> 5) + 1] = mc; bmG[(t >> 5) + 1] = mg; }
-    }
-    __syncthreads();
-
-    // ---- stream the window's alignments -----------------------------------------------------------
-    // A warp takes 32 consecutive alignments: each lane loads one alignment's scalars (coalesced), then the two
-    // half-warps walk the batch two alignments at a time; lane l of a half-warp owns query bases [16l, 16l+16),
-    // held in registers, and meets the window through a 16-bit slice of the C- or G-site bitmap.
-    const uint2 rr = A.win[w];
-    const DevReads &R = A.R;
-    const int half = lane >> 4, hl = lane & 15;
-    const int w0i = (int) w0;
-    for (uint32_t base = rr.x + 32u * warp; base < rr.y; base += 32u * nwarp) {
-        const uint32_t i = base + lane;
-        // -- per-lane scalars of alignment i
-        unsigned inf = 0; int pos = 0, q0 = 0, mlen = 0; uint32_t lq = 0, soff = 0, qoff = 0, f = 0; int mate = -1; bool fast = false, live = false;
-        if (i < rr.y) {
-            inf = A.info[i];
-            live = (inf & INFO_ADMIT) && (long long) A.rend[i] > w0;
-            if (live) {
-                pos = R.pos[i]; lq = R.l_qseq[i]; f = R.flag[i]; soff = R.seq_off[i]; qoff = R.qual_off[i];
-                mate = (MODE == 2) ? -1 : A.mate[i];
-                // fast shape: [S] M [S] with at most 256 query bases
-                const uint32_t k0 = R.cigar_off[i], nk = R.cigar_off[i + 1] - k0;
-                if (nk >= 1 && nk <= 3 && lq <= 256u) {
-                    uint32_t c0 = __ldg(R.cigar + k0), c1 = nk > 1 ? __ldg(R.cigar + k0 + 1) : 0u, c2 = nk > 2 ? __ldg(R.cigar + k0 + 2) : 0u;
-                    auto isM = [](uint32_t c) { uint32_t op = c & 15u; return op == 0 || op == 7 || op == 8; };
-                    auto isS = [](uint32_t c) { return (c & 15u) == 4u; };
-                    if (nk == 1 && isM(c0)) { fast = true; q0 = 0; mlen = (int)(c0 >> 4); }
-                    else if (nk == 2 && isS(c0) && isM(c1)) { fast = true; q0 = (int)(c0 >> 4); mlen = (int)(c1 >> 4); }
-                    else if (nk == 2 && isM(c0) && isS(c1)) { fast = true; q0 = 0; mlen = (int)(c0 >> 4); }
-                    else if (nk == 3 && isS(c0) && isM(c1) && isS(c2)) { fast = true; q0 = (int)(c0 >> 4); mlen = (int)(c1 >> 4); }
-                }
-            }
-        }
-        const unsigned live_m = __ballot_sync(0xffffffffu, live), fast_m = __ballot_sync(0xffffffffu, live && fast);
-        // -- fast alignments, two per step
-        for (int t = 0; t < 16; ++t) {
-            const int src = 2 * t + half;
-            if (!((fast_m >> (2 * t)) & 3u)) continue;            // warp-uniform: neither alignment of this step is fast
-            const bool mine = (fast_m >> src) & 1u;
-            const int rpos = __shfl_sync(0xffffffffu, pos, src), rq0 = __shfl_sync(0xffffffffu, q0, src), rmlen = __shfl_sync(0xffffffffu, mlen, src);
-            const uint32_t rlq = __shfl_sync(0xffffffffu, lq, src), rsoff = __shfl_sync(0xffffffffu, soff, src), rqoff = __shfl_sync(0xffffffffu, qoff, src);
-            const unsigned rinf = __shfl_sync(0xffffffffu, inf, src), rf = __shfl_sync(0xffffffffu, f, src);
-            const int rmate = __shfl_sync(0xffffffffu, mate, src);
-            if (!mine) continue;
-            const int b0 = 16 * hl;                               // first query base of this lane
-            if (b0 >= (int) rlq) continue;
-            ReadCtx rc;
-            rc.strand = INFO_STRAND(rinf); rc.rd2 = (rf & 0x80u) ? 1 : 0; rc.wantG = !(rc.strand & 1);
-            dev_trim(A.P, rc.strand, rf, (int) rlq, rc.lo, rc.hi);
-            rc.soff = rsoff; rc.qoff = rqoff;
-            // valid query bases of this lane: inside the match op, inside the kept range
-            const int vlo = max(max(rq0, rc.lo), b0), vhi = min(min(rq0 + rmlen, rc.hi), b0 + 16);
-            // window-relative position of query base b0
-            const int r = rpos + (b0 - rq0) - w0i;
-            unsigned mC = mask16_at(bmC, r, NW), mG = mask16_at(bmG, r, NW);
-            unsigned valid = 0u;
-            if (vhi > vlo) valid = ((1u << (vhi - b0)) - 1u) & ~((1u << (vlo - b0)) - 1u);
-            // bases outside the kept range still sit on columns (as N / phred 0) but can never pass the phred gate
-            // (minPhred >= 1) nor, for the overlap merge, win anything for THIS alignment — so they are skipped here.
-            unsigned own_m = rc.wantG ? mG : mC, opp_m = rc.wantG ? mC : mG;
-            own_m &= valid; opp_m = (MODE == 1) ? (opp_m & valid) : 0u;
-            unsigned any = own_m | opp_m;
-            if (!any) continue;
-            // this lane's 16 bases and phreds, from two 32-bit and two 64-bit loads
-            const uint32_t *sp = R.seq + rsoff + 2 * hl; const uint64_t *qp = R.qual + rqoff + 2 * hl;
-            const int nsw = (int)((((rlq + 1) >> 1) + 3) >> 2), nqw = (int)((rlq + 7) >> 3);
-            const uint32_t s0 = __ldg(sp), s1 = (2 * hl + 1 < nsw) ? __ldg(sp + 1) : 0u;
-            const uint64_t qv0 = __ldg(qp), qv1 = (2 * hl + 1 < nqw) ? __ldg(qp + 1) : 0ull;
-            load_mate(A, (uint32_t)(base + src), rmate, rc);
-            while (any) {
-                const int k = __ffs(any) - 1; any &= any - 1;
-                const uint32_t sw = (k < 8) ? s0 : s1;
-                const unsigned byte = (sw >> ((((k & 7) >> 1)) << 3)) & 0xffu;
-                const unsigned bb = (k & 1) ? (byte & 0xfu) : (byte >> 4);
-                const unsigned ql = (unsigned)(((k < 8) ? qv0 : qv1) >> ((k & 7) << 3)) & 0xffu;
-                const bool siteG = rc.wantG ? ((own_m >> k) & 1u) != 0 : ((own_m >> k) & 1u) == 0;
-                eval_hit<MODE>(A, rc, cnt, W, w0i, w0i + r + k, b0 + k, bb, ql, siteG);
-            }
-        }
-        // -- everything else (indels, reference skips, long reads): whole warp per alignment
-        unsigned slow_m = live_m & ~fast_m;
-        while (slow_m) {
-            const int src = __ffs(slow_m) - 1; slow_m &= slow_m - 1;
-            slow_read<MODE>(A, base + src, __shfl_sync(0xffffffffu, inf, src), w0, own1, [&](int rel) -> unsigned { return ctx[rel]; }, cnt, lane);
-        }
-    }
-    __syncthreads();
-
-    // ---- epilogue -----------------------------------------------------------------------------------
-    if (MODE == 2) {
-        for (uint32_t t = tid; t < 4u * 2u * MB_SM_Q * 2u; t += blockDim.x) {
-            uint32_t v = cnt[t];
-            if (v) { uint32_t sr = t / (MB_SM_Q * 2), rest = t % (MB_SM_Q * 2); atomicAdd(A.hist + (size_t) sr * MD_MBIAS_MAXLEN * 2 + rest, v); }
-        }
-        return;
-    }
-    // ordered compaction of this window's reportable columns
-    __shared__ uint32_t s_warp_tot[8], s_base;
-    const uint32_t per = (W + blockDim.x - 1) / blockDim.x;
-    const uint32_t t0 = tid * per, t1 = min(W, t0 + per);
-    uint32_t mine = 0;
-    for (uint32_t t = t0; t < t1; ++t) {
-        if (!ctx[t]) continue;
-        bool excl = false;
-        if (MODE == 1) {
-            uint32_t noff = cnt[2 * W + t], nvar = cnt[3 * W + t];
-            excl = A.P.minOppositeDepth > 0 && noff >= (uint32_t) A.P.minOppositeDepth && ((double) nvar) / ((double) noff) >= A.P.maxVariantFrac;
-        }
-        if (excl || cnt[t] + cnt[W + t]) ++mine;
-    }
-    uint32_t incl = mine;
-    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) s_warp_tot[warp] = incl;
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t tot = 0;
-        for (int k = 0; k < nwarp; ++k) { uint32_t v = s_warp_tot[k]; s_warp_tot[k] = tot; tot += v; }
-        unsigned long long base = tot ? atomicAdd((unsigned long long *)(A.counters + C_NCALLS), (unsigned long long) tot) : 0ull;
-        if (base + tot > A.cap) { atomicExch(A.counters + C_OVERFLOW, 1u); s_base = 0xffffffffu; }
-        else s_base = (uint32_t) base;
-        A.dir[w] = make_uint2((uint32_t) base, tot);
-    }
-    __syncthreads();
-    if (s_base == 0xffffffffu) return;
-    uint32_t o = s_base + s_warp_tot[warp] + (incl - mine);
-    for (uint32_t t = t0; t < t1; ++t) {
-        const unsigned cx = ctx[t];
-        if (!cx) continue;
-        bool excl = false;
-        if (MODE == 1) {
-            uint32_t noff = cnt[2 * W + t], nvar = cnt[3 * W + t];
-            excl = A.P.minOppositeDepth > 0 && noff >= (uint32_t) A.P.minOppositeDepth && ((double) nvar) / ((double) noff) >= A.P.maxVariantFrac;
-        }
-        const uint32_t nm = cnt[t], nu = cnt[W + t];
-        if (excl || nm + nu) {
-            md_call c; c.pos = (uint32_t)(w0 + t); c.nmeth = nm; c.nunmeth = nu; c.info = ((cx & 3u) - 1u) | (cx & 4u) | (excl ? 8u : 0u);
-            A.calls[o++] = c;
-        }
-    }
-}
-
-
 // ------------------------------------------------------------------------------------------------
-// K4s — the streaming count kernel (default).  Same contract as count_kernel, different machine mapping:
-//
-//   * one CTA per window of W = 4096 reference positions, 256 threads, two CTAs resident per SM;
-//   * the window's alignments are taken in batches of up to 256; the batch's packed bases and phreds are ONE
-//     contiguous byte range each (tiles are laid out in read order), so thread 0 streams them into shared memory
-//     with two cp.async.bulk copies (TMA, completion on an mbarrier) while every thread fetches the scalars of
-//     "its" alignment; the co-resident CTA computes meanwhile, so HBM and the SM overlap;
-//   * then ONE THREAD PER ALIGNMENT walks its CIGAR against bitmaps of the kept C- and G-sites of the window
-//     (built bit-parallel from the staged reference: CpG / CHG / CHH are three shifts and a few ANDs), so only
-//     bases that can produce a call are ever touched — base and phred come from shared memory;
-//   * counts go to shared-memory histograms with atomicAdd, the epilogue is the same ordered compaction.
-//
-// Against the warp-per-alignment mapping this removes the idle lanes (an alignment has ~9 CpG hits for 150
-// bases) and cuts the warp-instruction count per alignment by more than an order of magnitude.
+// async-copy primitives (sm_90+ / sm_100a): mbarrier + cp.async.bulk, i.e. the TMA engine in its 1-D "bulk" form
+// (SASS: UBLKCP for the copy, SYNCS for the barrier)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -583,264 +382,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     return ok != 0;
 }
 
-#define ST_THREADS 256
-#define ST_SEQ_BYTES (20 * 1024)     // staged packed bases per batch  (256 alignments x 76 B for 150-mers, + slack)
-#define ST_QUAL_BYTES (40 * 1024)    // staged phreds per batch        (256 x 152 B, + slack)
-
-struct StreamLayout { uint32_t off_bm, off_ref, off_cnt, off_seq, off_qual, total; };
-__host__ __device__ inline StreamLayout stream_layout(uint32_t W, int mode) {
-    StreamLayout L; uint32_t NW = W >> 5;
-    auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
-    L.off_bm = 128;                                            // [0,128): mbarrier + batch descriptor
-    L.off_ref = up(L.off_bm + 4u * (NW + 2u) * 4u);
-    L.off_cnt = up(L.off_ref + W + 32u);
-    uint32_t ncnt = mode == 2 ? 4u * 2u * MB_SM_Q * 2u : (mode == 1 ? 4u * W : 2u * W);
-    L.off_seq = up(L.off_cnt + ncnt * 4u);
-    L.off_qual = up(L.off_seq + ST_SEQ_BYTES + 64u);
-    L.total = up(L.off_qual + ST_QUAL_BYTES + 64u);
-    return L;
-}
-
-struct StageDesc { uint32_t sw0, sw1, qw0, qw1; };             // staged word ranges: seq words [sw0,sw1), qual dwords [qw0,qw1)
-
-template <int MODE>
-__global__ void __launch_bounds__(ST_THREADS, 2) count_stream(CountArgs A) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t W = A.W, NW = W >> 5;
-    const StreamLayout SL = stream_layout(W, MODE);
-    uint64_t *bar = (uint64_t *) smem;
-    StageDesc *sd = (StageDesc *)(smem + 16);
-    uint32_t *bmC = (uint32_t *)(smem + SL.off_bm), *bmG = bmC + NW + 2, *bmT0 = bmG + NW + 2, *bmT1 = bmT0 + NW + 2;   // one guard word each side
-    unsigned char *refw = smem + SL.off_ref;
-    uint32_t *cnt = (uint32_t *)(smem + SL.off_cnt);
-    const unsigned char *sseq = smem + SL.off_seq, *squal = smem + SL.off_qual;
-    const uint32_t w = blockIdx.x;
-    const long long w0 = (long long) A.beg + (long long) w * W;
-    const long long own1 = min((long long) A.end, w0 + (long long) W);
-    const int own = (int)(own1 - w0), w0i = (int) w0;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const DevReads &R = A.R;
-    const uint2 rr = A.win[w];
-
-    // ---- prologue: barrier, reference window, site bitmaps -------------------------------------------
-    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    for (uint32_t t = tid; t < W + 4; t += ST_THREADS) {
-        long long p = w0 - 2 + t;
-        refw[t] = (p >= 0 && p < (long long) A.reflen) ? __ldg(A.ref + p) : (unsigned char) 'N';
-    }
-    const uint32_t ncnt = (MODE == 2) ? 4u * 2u * MB_SM_Q * 2u : (MODE == 1 ? 4u * W : 2u * W);
-    for (uint32_t t = tid; t < ncnt; t += ST_THREADS) cnt[t] = 0;
-    if (tid < 8) { uint32_t *g = bmC + (tid >> 1) * (NW + 2); g[(tid & 1) ? NW + 1 : 0] = 0; }
-    __syncthreads();
-    for (uint32_t base = 0; base < W; base += 16u * ST_THREADS) {         // 16 positions per thread per pass (one pass when W = 4096)
-        const uint32_t t16 = base + 16u * tid;                            // window offset of this thread's first position
-        unsigned sC = 0, sG = 0, t0 = 0, t1 = 0;
-        if (MODE == 2) {
-            // MBias.c:147,170-178: context inside the reference chunk's own window contig[cs..ce]; per position
-            for (int j = 0; j < 16; ++j) {
-                long long p = w0 + t16 + j; unsigned c = 0;
-                if (p < own1 && A.n_chunks) {
-                    uint32_t lo = 0, hi = A.n_chunks;
-                    while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if ((long long) A.chunk_bounds[mid] <= p) lo = mid; else hi = mid; }
-                    if (p >= (long long) A.chunk_bounds[lo] && p < (long long) A.chunk_bounds[lo + 1]) {
-                        long long cs = A.chunk_bounds[lo], ce = A.chunk_bounds[lo + 1];
-                        long long last = ce < (long long) A.reflen ? ce : (long long) A.reflen - 1;
-                        auto get = [&](long long x) -> unsigned char { long long o = x - (w0 - 2); return (o >= 0 && o < (long long) W + 4) ? refw[o] : __ldg(A.ref + x); };
-                        c = dev_context(get, p, cs, last + 1);
-                    }
-                }
-                if (c && !((A.P.keepMask >> ((c & 3) - 1)) & 1)) c = 0;
-                if (c) { if (c & 4u) sG |= 1u << j; else sC |= 1u << j; if ((c & 3u) == 1u) t0 |= 1u << j; else if ((c & 3u) == 2u) t1 |= 1u << j; }
-            }
-        } else if (t16 < W) {
-            // bit j of C / G <-> reference position w0 + t16 - 2 + j  (j = 0..19); bases outside the contig are staged as 'N',
-            // which reproduces the end-of-sequence rules of common.c:50-57,64-71
-            unsigned C = 0, G = 0;
-            #pragma unroll
-            for (int j = 0; j < 20; ++j) { unsigned ch = refw[t16 + j] | 0x20u; C |= (ch == 'c' ? 1u : 0u) << j; G |= (ch == 'g' ? 1u : 0u) << j; }
-            const unsigned cpgC = C & (G >> 1), cpgG = G & (C << 1);
-            const unsigned chgC = C & ~cpgC & (G >> 2), chgG = G & ~cpgG & (C << 2);
-            const unsigned chhC = C & ~cpgC & ~chgC, chhG = G & ~cpgG & ~chgG;
-            const unsigned k0 = (A.P.keepMask & 1) ? ~0u : 0u, k1 = (A.P.keepMask & 2) ? ~0u : 0u, k2 = (A.P.keepMask & 4) ? ~0u : 0u;
-            int nown = own - (int) t16; nown = nown < 0 ? 0 : (nown > 16 ? 16 : nown);
-            const unsigned ownm = nown >= 16 ? 0xffffu : ((1u << nown) - 1u);
-            sC = (((cpgC & k0) | (chgC & k1) | (chhC & k2)) >> 2) & ownm;
-            sG = (((cpgG & k0) | (chgG & k1) | (chhG & k2)) >> 2) & ownm;
-            t0 = (((cpgC | cpgG) & k0) >> 2) & ownm;
-            t1 = (((chgC | chgG) & k1) >> 2) & ownm;
-        }
-        // two threads share a bitmap word
-        const unsigned pC = __shfl_down_sync(0xffffffffu, sC, 1), pG = __shfl_down_sync(0xffffffffu, sG, 1), p0 = __shfl_down_sync(0xffffffffu, t0, 1), p1 = __shfl_down_sync(0xffffffffu, t1, 1);
-        if (!(tid & 1) && t16 < W) {
-            const uint32_t wi = (t16 >> 5) + 1;
-            bmC[wi] = sC | (pC << 16); bmG[wi] = sG | (pG << 16); bmT0[wi] = t0 | (p0 << 16); bmT1[wi] = t1 | (p1 << 16);
-        }
-    }
-    __syncthreads();
-
-    // ---- batches --------------------------------------------------------------------------------------
-    // batch size: as many alignments as are guaranteed to fit the staging buffers given the longest read of the tile
-    const uint32_t maxlq = A.counters[C_MAXLQ];
-    const uint32_t seqw_max = ((((maxlq + 1u) >> 1) + 3u) >> 2), qualw_max = (maxlq + 7u) >> 3;
-    uint32_t nb = ST_THREADS;
-    if (seqw_max) nb = min(nb, (uint32_t)(ST_SEQ_BYTES / 4u - 4u) / seqw_max);
-    if (qualw_max) nb = min(nb, (uint32_t)(ST_QUAL_BYTES / 8u - 2u) / qualw_max);
-    auto ctx_code = [&](int rel) -> unsigned {                        // byte code of count_kernel's ctx[] from the bitmaps
-        const uint32_t wi = ((uint32_t) rel >> 5) + 1, b = 1u << (rel & 31);
-        const bool c = bmC[wi] & b, g = bmG[wi] & b;
-        if (!c && !g) return 0u;
-        return ((bmT0[wi] & b) ? 1u : (bmT1[wi] & b) ? 2u : 3u) | (g ? 4u : 0u);
-    };
-    if (nb == 0) {
-        // reads too long to stage: whole warp per alignment, straight from global memory
-        for (uint32_t i = rr.x + warp; i < rr.y; i += ST_THREADS / 32) {
-            const unsigned inf = A.info[i];
-            if ((inf & INFO_ADMIT) && (long long) A.rend[i] > w0) slow_read<MODE>(A, i, inf, w0, own1, ctx_code, cnt, lane);
-        }
-    } else {
-        uint32_t phase = 0;
-        for (uint32_t s = rr.x; s < rr.y; s += nb) {
-            const uint32_t e = min(s + nb, rr.y), i = s + tid;
-            // -- thread 0 streams the batch's bases and phreds into shared memory
-            if (tid == 0) {
-                StageDesc d;
-                d.sw0 = R.seq_off[s] & ~3u; d.qw0 = R.qual_off[s] & ~1u;
-                const uint32_t lql = R.l_qseq[e - 1];
-                uint32_t sw_end = R.seq_off[e - 1] + ((((lql + 1u) >> 1) + 3u) >> 2), qw_end = R.qual_off[e - 1] + ((lql + 7u) >> 3);
-                sw_end = min(sw_end, R.seq_words); qw_end = min(qw_end, R.qual_words);
-                uint32_t sbytes = sw_end > d.sw0 ? (sw_end - d.sw0) * 4u : 0u, qbytes = qw_end > d.qw0 ? (qw_end - d.qw0) * 8u : 0u;
-                sbytes = min((sbytes + 15u) & ~15u, (uint32_t) ST_SEQ_BYTES); qbytes = min((qbytes + 15u) & ~15u, (uint32_t) ST_QUAL_BYTES);
-                d.sw1 = d.sw0 + sbytes / 4u; d.qw1 = d.qw0 + qbytes / 8u;
-                *sd = d;
-                mbar_arrive_expect_tx(bar, sbytes + qbytes);
-                if (sbytes) bulk_copy_g2s((void *) sseq, R.seq + d.sw0, sbytes, bar);
-                if (qbytes) bulk_copy_g2s((void *) squal, R.qual + d.qw0, qbytes, bar);
-            }
-            // -- meanwhile every thread fetches the scalars of its alignment
-            unsigned inf = 0; bool live = false;
-            int pos = 0, lq = 0, mate = -1; unsigned f = 0; uint32_t soff = 0, qoff = 0, k0 = 0, k1 = 0, c0 = 0;
-            if (i < e) {
-                inf = A.info[i];
-                live = (inf & INFO_ADMIT) && (long long) A.rend[i] > w0;
-                if (live) {
-                    pos = R.pos[i]; lq = (int) R.l_qseq[i]; f = R.flag[i]; soff = R.seq_off[i]; qoff = R.qual_off[i];
-                    k0 = R.cigar_off[i]; k1 = R.cigar_off[i + 1];
-                    mate = (MODE == 2) ? -1 : A.mate[i];
-                    c0 = __ldg(R.cigar + k0);
-                }
-            }
-            __syncthreads();                                           // descriptor visible
-            const StageDesc d = *sd;
-            { uint32_t spins = 0; while (!mbar_try_wait(bar, phase)) { if (++spins > (1u << 26)) { atomicExch(A.counters + C_OVERFLOW, 2u); break; } } }
-            phase ^= 1u;
-            if (live) {
-                ReadCtx rc;
-                rc.strand = INFO_STRAND(inf); rc.rd2 = (f & 0x80u) ? 1 : 0; rc.wantG = !(rc.strand & 1);
-                dev_trim(A.P, rc.strand, f, lq, rc.lo, rc.hi);
-                rc.soff = soff; rc.qoff = qoff;
-                load_mate(A, i, mate, rc);
-                // is this alignment's data inside the staged ranges?  (always, for tiles laid out in read order)
-                const uint32_t sw_need = ((((uint32_t) lq + 1u) >> 1) + 3u) >> 2, qw_need = ((uint32_t) lq + 7u) >> 3;
-                const bool staged = soff >= d.sw0 && soff + sw_need <= d.sw1 && qoff >= d.qw0 && qoff + qw_need <= d.qw1;
-                const unsigned char *sb = sseq + (size_t)(soff - d.sw0) * 4u, *qb = squal + (size_t)(qoff - d.qw0) * 8u;
-                const uint32_t *own_bm = rc.wantG ? bmG : bmC, *opp_bm = rc.wantG ? bmC : bmG;
-                int p = pos, q = 0;
-                for (uint32_t k = k0; k < k1; ++k) {
-                    const uint32_t c = (k == k0) ? c0 : __ldg(R.cigar + k), op = c & 15u; const int len = (int)(c >> 4);
-                    if (op == 0 || op == 7 || op == 8) {
-                        // reference interval of this op clipped to the window and to the kept query range
-                        const int a = max(max(p, w0i), p + (rc.lo - q)), b = min(min(p + len, w0i + own), p + (rc.hi - q));
-                        if (b > a) {
-                            const int ra = a - w0i, rb = b - w0i;
-                            for (int wi = ra >> 5; wi <= (rb - 1) >> 5; ++wi) {
-                                unsigned m = own_bm[wi + 1], mo = (MODE == 1) ? opp_bm[wi + 1] : 0u;
-                                unsigned keep = 0xffffffffu;
-                                if (wi == (ra >> 5)) keep &= 0xffffffffu << (ra & 31);
-                                if (wi == ((rb - 1) >> 5)) keep &= 0xffffffffu >> (31 - ((rb - 1) & 31));
-                                m &= keep; mo &= keep;
-                                unsigned any = m | mo;
-                                while (any) {
-                                    const int bit = __ffs(any) - 1; any &= any - 1;
-                                    const int rp = w0i + (wi << 5) + bit, qi = q + (rp - p);
-                                    unsigned bb, ql;
-                                    if (staged) { const unsigned byte = sb[qi >> 1]; bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4); ql = qb[qi]; }
-                                    else { bb = dev_base(R.seq, soff, qi); ql = dev_qual(R.qual, qoff, qi); }
-                                    const bool is_own = (m >> bit) & 1u;
-                                    eval_hit<MODE>(A, rc, cnt, W, w0i, rp, qi, bb, ql, is_own ? rc.wantG : !rc.wantG);
-                                }
-                            }
-                        }
-                        p += len; q += len;
-                    } else if (op == 1 || op == 4) q += len;
-                    else if (op == 2 || op == 3) p += len;
-                }
-            }
-            __syncthreads();                                           // staging buffers free for the next batch
-        }
-    }
-    __syncthreads();
-
-    // ---- epilogue -------------------------------------------------------------------------------------
-    if (MODE == 2) {
-        for (uint32_t t = tid; t < 4u * 2u * MB_SM_Q * 2u; t += ST_THREADS) {
-            uint32_t v = cnt[t];
-            if (v) { uint32_t sr = t / (MB_SM_Q * 2), rest = t % (MB_SM_Q * 2); atomicAdd(A.hist + (size_t) sr * MD_MBIAS_MAXLEN * 2 + rest, v); }
-        }
-        return;
-    }
-    __shared__ uint32_t s_warp_tot[ST_THREADS / 32], s_base;
-    uint32_t total_mine = 0;
-    // this thread owns window offsets [16*tid + 4096*pass, +16)
-    auto reportable = [&](uint32_t t16) -> unsigned {                   // 16-bit mask of columns to report
-        const uint32_t wi = (t16 >> 5) + 1, sh = t16 & 31u;
-        unsigned sites = ((bmC[wi] | bmG[wi]) >> sh) & 0xffffu, out = 0;
-        while (sites) {
-            const int k = __ffs(sites) - 1; sites &= sites - 1;
-            const uint32_t t = t16 + k;
-            bool excl = false;
-            if (MODE == 1) {
-                const uint32_t noff = cnt[2 * W + t], nvar = cnt[3 * W + t];
-                excl = A.P.minOppositeDepth > 0 && noff >= (uint32_t) A.P.minOppositeDepth && ((double) nvar) / ((double) noff) >= A.P.maxVariantFrac;
-            }
-            if (excl) out |= 0x10000u << k;
-            if (excl || cnt[t] + cnt[W + t]) out |= 1u << k;
-        }
-        return out;
-    };
-    unsigned rep = 0;                                                   // W = 4096: a single pass; kept general with a loop below
-    const uint32_t npass = (W + 16u * ST_THREADS - 1) / (16u * ST_THREADS);
-    for (uint32_t pass = 0; pass < npass; ++pass) { const uint32_t t16 = pass * 16u * ST_THREADS + 16u * tid; if (t16 < W) total_mine += __popc(reportable(t16) & 0xffffu); }
-    uint32_t incl = total_mine;
-    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) s_warp_tot[warp] = incl;
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t tot = 0;
-        for (int k = 0; k < ST_THREADS / 32; ++k) { uint32_t v = s_warp_tot[k]; s_warp_tot[k] = tot; tot += v; }
-        unsigned long long base = tot ? atomicAdd((unsigned long long *)(A.counters + C_NCALLS), (unsigned long long) tot) : 0ull;
-        if (base + tot > A.cap) { atomicExch(A.counters + C_OVERFLOW, 1u); s_base = 0xffffffffu; }
-        else s_base = (uint32_t) base;
-        A.dir[w] = make_uint2((uint32_t) base, tot);
-    }
-    __syncthreads();
-    if (s_base == 0xffffffffu) return;
-    // NB: with more than one pass the per-thread order would interleave passes; W is fixed at 16 * ST_THREADS by the host
-    uint32_t o = s_base + s_warp_tot[warp] + (incl - total_mine);
-    {
-        const uint32_t t16 = 16u * tid;
-        rep = reportable(t16);
-        const uint32_t wi = (t16 >> 5) + 1, sh = t16 & 31u;
-        const unsigned g16 = (bmG[wi] >> sh) & 0xffffu, a16 = (bmT0[wi] >> sh) & 0xffffu, b16 = (bmT1[wi] >> sh) & 0xffffu;
-        unsigned r16 = rep & 0xffffu;
-        while (r16) {
-            const int k = __ffs(r16) - 1; r16 &= r16 - 1;
-            const uint32_t t = t16 + k;
-            md_call c; c.pos = (uint32_t)(w0 + t); c.nmeth = cnt[t]; c.nunmeth = cnt[W + t];
-            c.info = (((a16 >> k) & 1u) ? 0u : ((b16 >> k) & 1u) ? 1u : 2u) | (((g16 >> k) & 1u) ? 4u : 0u) | (((rep >> (16 + k)) & 1u) ? 8u : 0u);
-            A.calls[o++] = c;
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // K4w — warp-streaming count kernel (default).  Same contract as count_kernel / count_stream.
@@ -957,7 +498,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
 
     // ---- streaming phase: every warp on its own -----------------------------------------------------------
     const uint32_t maxlq = A.counters[C_MAXLQ];
-    const uint32_t seqb_max = ((((maxlq + 1u) >> 1) + 3u) >> 2) * 4u, qualb_max = ((maxlq + 7u) >> 3) * 8u;
+    const uint32_t seqb_max = ((((maxlq + 1u) >> 1) + 3u) >> 2) * 4u, qualb_max = qual_words_of(R, maxlq) * 8u;
     uint32_t nb = 32;
     if (seqb_max) nb = min(nb, (uint32_t)(WS_SEQ_BYTES - 32u) / seqb_max);
     if (qualb_max) nb = min(nb, (uint32_t)(WS_QUAL_BYTES - 32u) / qualb_max);
@@ -1002,7 +543,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
             uint32_t sw0 = __shfl_sync(0xffffffffu, soff, 0) & ~3u, qw0 = __shfl_sync(0xffffffffu, qoff, 0) & ~1u;
             const uint32_t lql = (uint32_t) __shfl_sync(0xffffffffu, lq, last);
             uint32_t sw_end = min(__shfl_sync(0xffffffffu, soff, last) + ((((lql + 1u) >> 1) + 3u) >> 2), R.seq_words);
-            uint32_t qw_end = min(__shfl_sync(0xffffffffu, qoff, last) + ((lql + 7u) >> 3), R.qual_words);
+            uint32_t qw_end = min(__shfl_sync(0xffffffffu, qoff, last) + qual_words_of(R, lql), R.qual_words);
             uint32_t sbytes = sw_end > sw0 ? (sw_end - sw0) * 4u : 0u, qbytes = qw_end > qw0 ? (qw_end - qw0) * 8u : 0u;
             sbytes = min((sbytes + 15u) & ~15u, (uint32_t) WS_SEQ_BYTES); qbytes = min((qbytes + 15u) & ~15u, (uint32_t) WS_QUAL_BYTES);
             const uint32_t sw1 = sw0 + sbytes / 4u, qw1 = qw0 + qbytes / 8u;
@@ -1018,7 +559,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
                 dev_trim(A.P, rc.strand, f, lq, rc.lo, rc.hi);
                 rc.soff = soff; rc.qoff = qoff;
                 load_mate(A, i, mate, rc);
-                const uint32_t sw_need = ((((uint32_t) lq + 1u) >> 1) + 3u) >> 2, qw_need = ((uint32_t) lq + 7u) >> 3;
+                const uint32_t sw_need = ((((uint32_t) lq + 1u) >> 1) + 3u) >> 2, qw_need = qual_words_of(R, (uint32_t) lq);
                 staged = soff >= sw0 && soff + sw_need <= sw1 && qoff >= qw0 && qoff + qw_need <= qw1;
                 uint32_t *cx = rctx + WS_CTX_WORDS * lane;
                 cx[0] = ((soff - sw0) * 4u) | (((qoff - qw0) * 8u) << 16);
@@ -1091,7 +632,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
                         ReadCtx hc;
                         hc.wantG = c1w & 1u; hc.rd2 = (c1w >> 1) & 1u; hc.strand = (c1w >> 8) & 7u; hc.mi = -1;
                         const unsigned byte = sseq[(c0w & 0xffffu) + (qi >> 1)];
-                        const unsigned bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4), ql = squal[(c0w >> 16) + qi];
+                        const unsigned bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4), ql = staged_qual(R, squal + (c0w >> 16), qi);
                         eval_hit<MODE, false>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
                     }
                     qa -= take;
@@ -1109,7 +650,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
                         hc.is_a = (c1w & 8u) != 0; hc.mate_simple = (c1w & 16u) != 0;
                         hc.mpos = (int) cx[2]; hc.mend = (int) cx[3]; hc.msoff = cx[4]; hc.mqoff = cx[5]; hc.mlo = (int)(cx[6] & 0xffffu); hc.mhi = (int)(cx[6] >> 16); hc.mk0 = cx[7]; hc.mk1 = cx[8];
                         const unsigned byte = sseq[(c0w & 0xffffu) + (qi >> 1)];
-                        const unsigned bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4), ql = squal[(c0w >> 16) + qi];
+                        const unsigned bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4), ql = staged_qual(R, squal + (c0w >> 16), qi);
                         eval_hit<MODE, true>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
                     }
                     qb2 -= take;
@@ -1130,7 +671,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
                             const bool siteG = (cxc & 4u) != 0;
                             if (MODE != 1 && siteG != rc.wantG) continue;
                             const int qi = q2 + (x - p2);
-                            eval_hit<MODE>(A, rc, cnt, W, w0i, x, qi, dev_base(R.seq, soff, qi), dev_qual(R.qual, qoff, qi), siteG);
+                            eval_hit<MODE>(A, rc, cnt, W, w0i, x, qi, dev_base(R.seq, soff, qi), dev_qual(R, qoff, qi), siteG);
                         }
                         p2 += len; q2 += len;
                     } else if (op == 1 || op == 4) q2 += len;
@@ -1271,7 +812,6 @@ struct md_ctx {
     uint32_t *d_hist = nullptr; int32_t *d_lens = nullptr;
     uint64_t launches = 0;
     uint32_t W = 4096;
-    int count_variant = 4;               // 4: count_warp (per-warp TMA streaming + ballot queue); 3: count_stream; 2: count_kernel
 };
 
 static void sync_all(md_ctx *c) { for (int k = 0; k < MD_NLANES; ++k) if (c->lanes[k].stream) cudaStreamSynchronize(c->lanes[k].stream); }
@@ -1295,7 +835,6 @@ extern "C" md_ctx *md_create(const md_config *cfg, int device) {
     CKN(cudaSetDevice(device));
     md_ctx *c = new md_ctx();
     c->device = device; c->cfg = *cfg; fill_kparams(cfg, c->kp);
-    if (const char *v = getenv("MD_COUNT_KERNEL")) { int k = atoi(v); if (k >= 2 && k <= 4) c->count_variant = k; }
     for (int k = 0; k < MD_NLANES; ++k) {
         Lane *L = &c->lanes[k];
         if (cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; delete c; return nullptr; }
@@ -1306,15 +845,9 @@ extern "C" md_ctx *md_create(const md_config *cfg, int device) {
     size_t hb = (size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2 * sizeof(uint32_t);
     if (cudaMalloc(&c->d_hist, hb) != cudaSuccess || cudaMalloc(&c->d_lens, 4 * sizeof(int32_t)) != cudaSuccess) { g_err = "cudaMalloc(hist) failed"; delete c; return nullptr; }
     cudaMemsetAsync(c->d_hist, 0, hb, L->stream); cudaMemsetAsync(c->d_lens, 0, 4 * sizeof(int32_t), L->stream);
-    cudaFuncSetAttribute(count_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(count_warp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0).total);
     cudaFuncSetAttribute(count_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1).total);
     cudaFuncSetAttribute(count_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2).total);
-    cudaFuncSetAttribute(count_stream<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) stream_layout(4096, 0).total);
-    cudaFuncSetAttribute(count_stream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) stream_layout(4096, 1).total);
-    cudaFuncSetAttribute(count_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) stream_layout(4096, 2).total);
     cudaStreamSynchronize(L->stream);
     return c;
 }
@@ -1389,6 +922,8 @@ static int stage_reads(md_ctx *c, Lane *L, md_dev_reads &d, const md_reads_soa *
     for (int k = 0; k < 12; ++k) if (sz[k]) CK(cudaMemcpyAsync(base + off[k], src[k], sz[k], cudaMemcpyHostToDevice, L->stream));
     DevReads &v = d.view;
     v.n = (uint32_t) n; v.seq_words = (uint32_t) r->seq_words; v.qual_words = (uint32_t) r->qual_words;
+    v.qbits = (r->qual_bits == 2 || r->qual_bits == 4) ? r->qual_bits : 8u; memcpy(v.qlut, r->qual_lut, 16);
+    if (r->qual_bits != 0 && r->qual_bits != 2 && r->qual_bits != 4 && r->qual_bits != 8) { g_err = "md_reads_soa.qual_bits must be 0, 2, 4 or 8"; return -2; }
     v.pos = (const int32_t *)(base + off[0]); v.flag = (const uint16_t *)(base + off[1]); v.mapq = base + off[2]; v.aux = base + off[3];
     v.l_qseq = (const uint32_t *)(base + off[4]); v.cigar_off = (const uint32_t *)(base + off[5]); v.seq_off = (const uint32_t *)(base + off[6]);
     v.qual_off = (const uint32_t *)(base + off[7]); v.frag_key = (const uint64_t *)(base + off[8]); v.cigar = (const uint32_t *)(base + off[9]);
@@ -1417,18 +952,10 @@ static int launch_count(md_ctx *c, Lane *L, const Contig &g, const DevReads &R, 
     A.R = R; A.P = kp; A.rend = (const int32_t *) L->rend.p; A.info = (const uint8_t *) L->info.p; A.mate = (const int32_t *) L->mate.p; A.win = (const uint2 *) L->win.p;
     A.ref = g.d_seq; A.reflen = g.len; A.beg = beg; A.end = end; A.W = W; A.chunk_bounds = g.d_bounds; A.n_chunks = g.n_chunks;
     A.calls = (md_call *) L->calls.p; A.cap = cap_calls; A.dir = (uint2 *) L->dir.p; A.counters = (uint32_t *) L->counters.p; A.hist = c->d_hist; A.lens = c->d_lens;
-    const size_t bm = 2 * ((size_t)(W >> 5) + 2) * 4;
-    if (c->count_variant == 4 && W == 16 * WS_WARPS * 32) {
-        if (mbias) count_warp<2><<<n_win, WS_WARPS * 32, warp_layout(W, 2).total, s>>>(A);
-        else if (kp.minOppositeDepth > 0) count_warp<1><<<n_win, WS_WARPS * 32, warp_layout(W, 1).total, s>>>(A);
-        else count_warp<0><<<n_win, WS_WARPS * 32, warp_layout(W, 0).total, s>>>(A);
-    } else if (c->count_variant >= 3 && W == 16 * ST_THREADS) {
-        if (mbias) count_stream<2><<<n_win, ST_THREADS, stream_layout(W, 2).total, s>>>(A);
-        else if (kp.minOppositeDepth > 0) count_stream<1><<<n_win, ST_THREADS, stream_layout(W, 1).total, s>>>(A);
-        else count_stream<0><<<n_win, ST_THREADS, stream_layout(W, 0).total, s>>>(A);
-    } else if (mbias) { size_t sm = 2 * (size_t) W + 16 + bm + (size_t) 4 * 2 * MB_SM_Q * 2 * 4; count_kernel<2><<<n_win, 256, sm, s>>>(A); }
-    else if (kp.minOppositeDepth > 0) { size_t sm = 2 * (size_t) W + 16 + bm + (size_t) 16 * W; count_kernel<1><<<n_win, 256, sm, s>>>(A); }
-    else { size_t sm = 2 * (size_t) W + 16 + bm + (size_t) 8 * W; count_kernel<0><<<n_win, 256, sm, s>>>(A); }
+    if (W != 16 * WS_WARPS * 32) { g_err = "internal: window size must be 4096"; return -3; }
+    if (mbias) count_warp<2><<<n_win, WS_WARPS * 32, warp_layout(W, 2).total, s>>>(A);
+    else if (kp.minOppositeDepth > 0) count_warp<1><<<n_win, WS_WARPS * 32, warp_layout(W, 1).total, s>>>(A);
+    else count_warp<0><<<n_win, WS_WARPS * 32, warp_layout(W, 0).total, s>>>(A);
     c->launches += 1;
     if (!mbias) {
         dir_scan_kernel<<<1, 1024, 0, s>>>((uint2 *) L->dir.p, n_win, (uint32_t *) L->sorted_off.p);

@@ -75,7 +75,11 @@ static inline uint8_t seq_nib(const md_reads_soa *r, uint32_t i, uint32_t q) {
     return (uint8_t)((s[q >> 1] >> ((~q & 1) << 2)) & 0xf);           /* bam_seqi */
 }
 static inline uint8_t qual_at(const md_reads_soa *r, uint32_t i, uint32_t q) {
-    return ((const uint8_t *)(r->qual + r->qual_off[i]))[q];
+    const uint8_t *b = (const uint8_t *)(r->qual + r->qual_off[i]);
+    if (r->qual_bits == 0 || r->qual_bits == 8) return b[q];
+    /* packed tile (include/mdgpu.h): qual_bits-wide codes, base q at bit q*qual_bits; the table gives back the phred byte */
+    const uint32_t bit = q * r->qual_bits;
+    return r->qual_lut[(b[bit >> 3] >> (bit & 7)) & ((1u << r->qual_bits) - 1u)];
 }
 
 typedef struct {

@@ -182,3 +182,50 @@ def test_device_resident_path_matches_host_path(built, synth):
         assert g.launch_count() >= 8
     assert st.n_calls == st2.n_calls == n2
     assert bytes(C.string_at(got, n2 * 16)) == bytes(C.string_at(got2, n2 * 16))
+
+
+# ---------------------------------------------------------------- read-length regimes of the streaming kernel
+@pytest.mark.parametrize("name,args", [
+    ("len250", ["--contigs", "chr1:80000", "--depth", "20", "--readlen", "250", "--isize-mean", "400", "--isize-sd", "80", "--isize-min", "250", "--isize-max", "900"]),
+    ("len75", ["--contigs", "chr1:50000", "--depth", "25", "--readlen", "75", "--isize-mean", "160", "--isize-sd", "40", "--isize-min", "75", "--isize-max", "400"]),
+    ("len600", ["--contigs", "chr1:90000", "--depth", "15", "--readlen", "600", "--isize-mean", "900", "--isize-sd", "150", "--isize-min", "600", "--isize-max", "2000"]),
+    ("len20000", ["--contigs", "chr1:300000", "--depth", "6", "--readlen", "20000", "--isize-mean", "30000", "--isize-sd", "4000", "--isize-min", "20000", "--isize-max", "45000"]),
+], ids=["250bp_batch19", "75bp", "600bp_batch7", "20kb_unstaged"])
+def test_cli_read_lengths(built, synth, tmp_path, name, args):
+    """250/600-mers shrink the per-warp batch (staging buffer holds fewer alignments), 20 kb reads exceed the queue's query-index
+    field and take the whole-warp path from global memory"""
+    p = synth(name, *args)
+    for k, opts in enumerate([["--CHG", "--CHH"], ["--mergeContext", "--minOppositeDepth", "2", "--maxVariantFrac", "0.2"]]):
+        refp, newp = _both(built, tmp_path, "%s_%d" % (name, k), opts, p + ".fa", p + ".bam")
+        assert compare_outputs(refp, newp) == []
+
+
+def test_cli_mbias_long_reads(built, synth):
+    """query positions beyond the shared-memory histogram (>= 256) go to the global one; beyond MD_MBIAS_MAXLEN they are dropped by both sides... so stay below"""
+    p = synth("len600", "--contigs", "chr1:90000", "--depth", "15", "--readlen", "600", "--isize-mean", "900", "--isize-sd", "150", "--isize-min", "600", "--isize-max", "2000")
+    r = subprocess.run([built["ref_bin"], "mbias", "--noSVG", "--CHH", p + ".fa", p + ".bam"], capture_output=True, text=True)
+    n = subprocess.run([NEW_BIN, "mbias", "--noSVG", "--CHH", p + ".fa", p + ".bam"], capture_output=True, text=True)
+    assert r.returncode == 0 and n.returncode == 0, (r.stderr, n.stderr)
+    assert n.stdout == r.stdout and len(r.stdout.splitlines()) > 1000
+
+
+# ---------------------------------------------------------------- phred encodings of the tile (md_reads_soa::qual_bits)
+@pytest.mark.parametrize("nq,env", [(4, {}), (12, {}), (40, {}), (4, {"MD_QUAL_PACK": "0"})], ids=["2bit", "4bit", "8bit_alphabet_too_large", "packing_off"])
+def test_cli_phred_encodings(built, synth, tmp_path, nq, env):
+    """4 distinct phreds ship as 2-bit codes, 12 as 4-bit codes, 40 stay bytes; all three must give the reference's bytes"""
+    p = synth("q%d" % nq, "--contigs", "chr1:50000", "--depth", "25", "--quals", str(nq))
+    refp, newp = str(tmp_path / "ref"), str(tmp_path / "new")
+    r = run_ref(built["ref_bin"], "extract", ["--CHG", "--CHH", "-p", "9"], p + ".fa", p + ".bam", refp)
+    assert r.returncode == 0, r.stderr
+    n = subprocess.run([NEW_BIN, "extract", "--CHG", "--CHH", "-p", "9", p + ".fa", p + ".bam", "-o", newp], capture_output=True, text=True, env=dict(os.environ, **env))
+    assert n.returncode == 0, n.stderr
+    assert compare_outputs(refp, newp) == []
+
+
+def test_tile_abi_reports_encoding(built, synth):
+    p = synth("q12", "--contigs", "chr1:50000", "--depth", "25", "--quals", "12")
+    b = api.BamFile(p + ".bam")
+    soa = b.read_region(0)
+    assert soa.qual_bits == 4 and sorted(soa.qual_lut[:12]) == list(range(2, 14))
+    _tile_compare(A.default_config(keepCHG=1), p + ".fa", p + ".bam", 0)
+    b.close()

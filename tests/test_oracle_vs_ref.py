@@ -103,3 +103,21 @@ def test_parallel_decode_many_small_jobs(built, synth, tmp_path):
     n = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, MD_DECODE_JOB_BYTES="1"))
     assert n.returncode == 0, n.stderr
     assert compare_outputs(refp, newp) == []
+
+
+@pytest.mark.parametrize("name,args", [
+    ("len250", ["--contigs", "chr1:80000", "--depth", "20", "--readlen", "250", "--isize-mean", "400", "--isize-sd", "80", "--isize-min", "250", "--isize-max", "900"]),
+    ("len20000", ["--contigs", "chr1:300000", "--depth", "6", "--readlen", "20000", "--isize-mean", "30000", "--isize-sd", "4000", "--isize-min", "20000", "--isize-max", "45000"]),
+], ids=["250bp", "20kb"])
+def test_synthetic_read_lengths(built, synth, tmp_path, name, args):
+    p = synth(name, *args)
+    refp, newp = _both(built, tmp_path, name, ["--CHG", "--CHH"], p + ".fa", p + ".bam")
+    assert compare_outputs(refp, newp) == []
+
+
+@pytest.mark.parametrize("nq", [4, 12, 40], ids=["2bit", "4bit", "8bit"])
+def test_phred_encodings_cpu(built, synth, tmp_path, nq):
+    """host packer + oracle port: 2-bit / 4-bit / plain phred tiles all reproduce the reference"""
+    p = synth("q%d" % nq, "--contigs", "chr1:50000", "--depth", "25", "--quals", str(nq))
+    refp, newp = _both(built, tmp_path, "q", ["--CHG", "--CHH", "-p", "9"], p + ".fa", p + ".bam")
+    assert compare_outputs(refp, newp) == []
