@@ -224,6 +224,10 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     d.have_bai = load_bai(bamName, d.bai);
     try { d.fa.reset(new Fasta(fastaName)); }
     catch (std::exception &e) { fprintf(stderr, "Couldn't open the index for %s!\n", fastaName); return -4; }
+    // the device context takes a noticeable fraction of a second to come up: create it while the host opens files,
+    // loads the first contig and starts decoding
+    std::future<void *> dev_future = std::async(std::launch::async, [be, &o] { return be->create(be->factory_user, &o.core); });
+    struct DevJoin { std::future<void *> &f; const mdh_backend *be; bool taken = false; ~DevJoin() { if (!taken && f.valid()) { void *p = f.get(); if (p) be->destroy(p); } } } dev_join{dev_future, be};
 
     // output files, extract.c:1344-1439
     if (opref == NULL) {
@@ -264,8 +268,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         if (gEnd > d.hdr->lens[gTid]) gEnd = d.hdr->lens[gTid];
     }
 
-    d.dev = be->create(be->factory_user, &o.core);
-    if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+    for (int k = 0; k < 3; ++k) if (fp[k] && (k == 0 || fp[k] != fp[0])) setvbuf(fp[k], nullptr, _IOFBF, 4 << 20);
     ExtractWriter writer(o, fp);
     int rc = 0;
     {
@@ -293,6 +296,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         std::vector<std::unique_ptr<SoaTile>> ring;
         for (int k = 0; k < (use_async ? 3 : 1); ++k) ring.emplace_back(new SoaTile(use_async ? &pin : nullptr));
         const size_t tile_reads = use_async ? ((size_t) 1 << 17) : ((size_t) 1 << 19);
+        if (use_async) for (auto &t : ring) t->reserve_for(tile_reads + tile_reads / 8, 160);
         // phred column re-encoded as 2/4-bit codes when the tile's alphabet allows (md_reads_soa::qual_bits)
         const bool pack_q = pack_quals_enabled();
         std::vector<std::unique_ptr<PodVec<uint64_t>>> qscratch; std::vector<std::unique_ptr<PodVec<uint32_t>>> qoffscratch;
@@ -300,6 +304,8 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         SoaTile carry;
         std::vector<md_call> calls; size_t calls_head = 0;
         std::vector<md_call> tile_calls;
+        d.dev = dev_future.get(); dev_join.taken = true;
+        if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
         size_t ci = c0;
         while (ci < c1 && rc == 0) {
             // all chunks of this shard that lie on one contig

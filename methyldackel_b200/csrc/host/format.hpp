@@ -172,13 +172,24 @@ private:
         return rv;
     }
     static double logit(double p) { return log(p) - log(1 - p); }
+    static char *put_uint(char *w, uint32_t v) { char t[12]; int n = 0; do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) *w++ = t[--n]; return w; }
+    static char *put_int(char *w, int32_t v) { if (v < 0) { *w++ = '-'; return put_uint(w, (uint32_t)(-(int64_t) v)); } return put_uint(w, (uint32_t) v); }
 
     // writeCall, extract.c:39-99
     void write_call(FILE *f, const char *chrom, int32_t pos, int32_t width, uint32_t nm, uint32_t nu, char base, const char *context, const char *tnc) {
         char strand = (base == 'C' || base == 'c') ? 'F' : 'R';
         if ((nm + nu) < (uint32_t) o_.minDepth && !o_.cytosine_report) return;   // unsigned compare, as in C
-        if (!o_.fraction && !o_.logit && !o_.counts && !o_.methylKit && !o_.cytosine_report)
-            fprintf(f, "%s\t%i\t%i\t%i\t%" PRIu32 "\t%" PRIu32 "\n", chrom, pos, pos + width, (int)(100.0 * ((double) nm) / (nm + nu)), nm, nu);
+        if (!o_.fraction && !o_.logit && !o_.counts && !o_.methylKit && !o_.cytosine_report) {
+            // "%s\t%i\t%i\t%i\t%u\t%u\n" (extract.c:45-52) assembled by hand: this line is written ~10^9 times on a genome
+            char buf[512]; char *w = buf;
+            size_t cl = strlen(chrom);
+            if (cl > 400) { fprintf(f, "%s\t%i\t%i\t%i\t%" PRIu32 "\t%" PRIu32 "\n", chrom, pos, pos + width, (int)(100.0 * ((double) nm) / (nm + nu)), nm, nu); return; }
+            memcpy(w, chrom, cl); w += cl; *w++ = '\t';
+            w = put_int(w, pos); *w++ = '\t'; w = put_int(w, pos + width); *w++ = '\t';
+            w = put_int(w, (int)(100.0 * ((double) nm) / (nm + nu))); *w++ = '\t';
+            w = put_uint(w, nm); *w++ = '\t'; w = put_uint(w, nu); *w++ = '\n';
+            fwrite(buf, 1, (size_t)(w - buf), f);
+        }
         else if (o_.fraction) fprintf(f, "%s\t%i\t%i\t%f\n", chrom, pos, pos + width, ((double) nm) / (nm + nu));
         else if (o_.counts) fprintf(f, "%s\t%i\t%i\t%i\n", chrom, pos, pos + width, nm + nu);
         else if (o_.logit) fprintf(f, "%s\t%i\t%i\t%f\n", chrom, pos, pos + width, logit(((double) nm) / (nm + nu)));

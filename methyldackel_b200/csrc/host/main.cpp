@@ -3,6 +3,8 @@
 // if no CUDA device is usable the program fails with an error instead of computing on the CPU.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <chrono>
 #include "../../../include/mdhost.h"
 
 static void *be_create(void *, const md_config *cfg) { return md_create(cfg, 0); }
@@ -29,8 +31,18 @@ int main(int argc, char *argv[]) {
     if (argc == 1) { usage_main(); return 0; }
     if (!strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) { usage_main(); return 0; }
     if (!strcmp(argv[1], "-v") || !strcmp(argv[1], "--version")) { printf("0.6.1-b200 (B200 build; no HTSlib)\n"); return 0; }
-    if (!strcmp(argv[1], "extract")) return mdh_extract_main(argc - 1, argv + 1, &be);
-    if (!strcmp(argv[1], "mbias")) return mdh_mbias_main(argc - 1, argv + 1, &be);
+    if (!strcmp(argv[1], "extract") || !strcmp(argv[1], "mbias")) {
+        auto t0 = std::chrono::steady_clock::now();
+        int rc = !strcmp(argv[1], "extract") ? mdh_extract_main(argc - 1, argv + 1, &be) : mdh_mbias_main(argc - 1, argv + 1, &be);
+        if (getenv("MD_TIMING")) {      // where the wall clock went (stderr), for tuning
+            mdh_run_stats st; mdh_last_run_stats(&st);
+            double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            fprintf(stderr, "[md-timing] wall %.3f s: setup %.3f, decode-wait %.3f, device-wait %.3f, format %.3f; %llu alignments in %llu tiles, %llu calls\n",
+                    wall, st.t_total_s - st.t_decode_s - st.t_device_s - st.t_format_s, st.t_decode_s, st.t_device_s, st.t_format_s,
+                    (unsigned long long) st.n_records, (unsigned long long) st.n_tiles, (unsigned long long) st.n_calls);
+        }
+        return rc;
+    }
     if (!strcmp(argv[1], "mergeContext") || !strcmp(argv[1], "perRead")) { fprintf(stderr, "The %s sub-command is not part of the B200 build.\n", argv[1]); return -1; }
     fprintf(stderr, "Unknown command!\n"); usage_main();
     return -1;

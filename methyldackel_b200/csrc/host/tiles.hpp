@@ -57,6 +57,11 @@ struct SoaTile {
     PodVec<uint64_t> frag_key; PodVec<uint32_t> cigar, seq; PodVec<uint64_t> qual;
     PodVec<int32_t> rend;   // host-only: reference end of each read (for carry-over between tiles)
     size_t n() const { return pos.size(); }
+    // one allocation per column up front (page-locked allocations are expensive; growth stays possible)
+    void reserve_for(size_t reads, size_t read_len) {
+        pos.reserve(reads); flag.reserve(reads); mapq.reserve(reads); aux.reserve(reads); l_qseq.reserve(reads); cigar_off.reserve(reads + 1); seq_off.reserve(reads); qual_off.reserve(reads);
+        frag_key.reserve(reads); rend.reserve(reads); cigar.reserve(reads * 2); seq.reserve(reads * ((read_len / 2 + 3) / 4 + 1)); qual.reserve(reads * ((read_len + 7) / 8 + 1));
+    }
     void clear() { qual_bits = 8; pos.clear(); flag.clear(); mapq.clear(); aux.clear(); l_qseq.clear(); cigar_off.clear(); seq_off.clear(); qual_off.clear(); frag_key.clear(); cigar.clear(); seq.clear(); qual.clear(); rend.clear(); }
     size_t bytes() const { return n() * (4 + 2 + 1 + 1 + 4 + 4 + 4 + 4 + 8) + 4 + cigar.size() * 4 + seq.size() * 4 + qual.size() * 8; }
 

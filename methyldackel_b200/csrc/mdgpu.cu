@@ -400,8 +400,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 // alignment covers) is reduced to a cheap iterator, the expensive part runs converged.
 #define WS_SEQ_BYTES 2560          // 32 alignments x 76 B (150-mers) + alignment slack
 #define WS_QUAL_BYTES 5120         // 32 x 152 B + slack
-#define WS_CTX_WORDS 12
-#define WS_QUEUE 128               // candidate queue entries per warp (>= 64: up to 31 left over + 32 new)
+#define WS_CTX_WORDS 10
+#define WS_QUEUE 192               // two candidate queues of 96 entries per warp (up to 63 left over + 32 new)
 #define WS_WARPS 8
 
 struct WarpLayout { uint32_t off_bm, off_cnt, off_warp, warp_stride, off_seq, off_qual, off_ctx, off_queue, total; };
@@ -423,7 +423,7 @@ __host__ __device__ inline WarpLayout warp_layout(uint32_t W, int mode) {
 //  0: staged seq byte offset | staged qual byte offset << 16
 //  1: flags: bit0 wantG, bit1 rd2, bit2 has mate, bit3 is_a, bit4 mate_simple, bits8-10 strand
 //  2: mpos   3: mend   4: msoff   5: mqoff   6: mlo | mhi << 16   7: mk0   8: mk1
-template <int MODE>
+template <int MODE, int EV>
 __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t W = A.W, NW = W >> 5;
@@ -622,37 +622,33 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
                 qa += __popc(hmA); qb2 += __popc(hmB);
                 const bool all_done = (hmA | hmB) == 0u;                  // no lane produced anything: every iterator is exhausted
                 __syncwarp();
-                while (qa >= 32u || (all_done && qa > 0u)) {
-                    const uint32_t take = min(qa, 32u);
-                    if ((uint32_t) lane < take) {
-                        const uint32_t en = queue[qa - take + lane];
-                        const int src = en & 31u, rel = (en >> 5) & 0xfffu, qi = (en >> 17) & 0x3fffu; const bool is_opp = en >> 31;
-                        const uint32_t *cx = rctx + WS_CTX_WORDS * src;
-                        const uint32_t c0w = cx[0], c1w = cx[1];
-                        ReadCtx hc;
-                        hc.wantG = c1w & 1u; hc.rd2 = (c1w >> 1) & 1u; hc.strand = (c1w >> 8) & 7u; hc.mi = -1;
-                        const unsigned byte = sseq[(c0w & 0xffffu) + (qi >> 1)];
-                        const unsigned bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4), ql = staged_qual(R, squal + (c0w >> 16), qi);
-                        eval_hit<MODE, false>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
+                // one queued candidate -> call / evidence.  MATE candidates carry the mate descriptor of their alignment.
+                auto eval_entry = [&](uint32_t en, bool with_mate) {
+                    const int src = en & 31u, rel = (en >> 5) & 0xfffu, qi = (en >> 17) & 0x3fffu; const bool is_opp = en >> 31;
+                    const uint32_t *cx = rctx + WS_CTX_WORDS * src;
+                    const uint32_t c0w = cx[0], c1w = cx[1];
+                    ReadCtx hc;
+                    hc.wantG = c1w & 1u; hc.rd2 = (c1w >> 1) & 1u; hc.strand = (c1w >> 8) & 7u; hc.mi = with_mate ? 0 : -1;
+                    if (with_mate) {
+                        hc.is_a = (c1w & 8u) != 0; hc.mate_simple = (c1w & 16u) != 0;
+                        hc.mpos = (int) cx[2]; hc.mend = (int) cx[3]; hc.msoff = cx[4]; hc.mqoff = cx[5]; hc.mlo = (int)(cx[6] & 0xffffu); hc.mhi = (int)(cx[6] >> 16); hc.mk0 = cx[7]; hc.mk1 = cx[8];
                     }
+                    const unsigned byte = sseq[(c0w & 0xffffu) + (qi >> 1)];
+                    const unsigned bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4), ql = staged_qual(R, squal + (c0w >> 16), qi);
+                    if (with_mate) eval_hit<MODE, true>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
+                    else eval_hit<MODE, false>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
+                };
+                while (qa >= 32u * EV || (all_done && qa > 0u)) {
+                    const uint32_t take = min(qa, 32u * EV);
+                    #pragma unroll
+                    for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take) eval_entry(queue[qa - take + lane + 32 * r], false);
                     qa -= take;
                     __syncwarp();
                 }
-                while (qb2 >= 32u || (all_done && qb2 > 0u)) {
-                    const uint32_t take = min(qb2, 32u);
-                    if ((uint32_t) lane < take) {
-                        const uint32_t en = queueB[qb2 - take + lane];
-                        const int src = en & 31u, rel = (en >> 5) & 0xfffu, qi = (en >> 17) & 0x3fffu; const bool is_opp = en >> 31;
-                        const uint32_t *cx = rctx + WS_CTX_WORDS * src;
-                        const uint32_t c0w = cx[0], c1w = cx[1];
-                        ReadCtx hc;
-                        hc.wantG = c1w & 1u; hc.rd2 = (c1w >> 1) & 1u; hc.strand = (c1w >> 8) & 7u; hc.mi = 0;
-                        hc.is_a = (c1w & 8u) != 0; hc.mate_simple = (c1w & 16u) != 0;
-                        hc.mpos = (int) cx[2]; hc.mend = (int) cx[3]; hc.msoff = cx[4]; hc.mqoff = cx[5]; hc.mlo = (int)(cx[6] & 0xffffu); hc.mhi = (int)(cx[6] >> 16); hc.mk0 = cx[7]; hc.mk1 = cx[8];
-                        const unsigned byte = sseq[(c0w & 0xffffu) + (qi >> 1)];
-                        const unsigned bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4), ql = staged_qual(R, squal + (c0w >> 16), qi);
-                        eval_hit<MODE, true>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
-                    }
+                while (qb2 >= 32u * EV || (all_done && qb2 > 0u)) {
+                    const uint32_t take = min(qb2, 32u * EV);
+                    #pragma unroll
+                    for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take) eval_entry(queueB[qb2 - take + lane + 32 * r], true);
                     qb2 -= take;
                     __syncwarp();
                 }
@@ -812,6 +808,7 @@ struct md_ctx {
     uint32_t *d_hist = nullptr; int32_t *d_lens = nullptr;
     uint64_t launches = 0;
     uint32_t W = 4096;
+    int ev = 1;                          // candidates per lane per evaluate round (count_warp<MODE, EV>)
 };
 
 static void sync_all(md_ctx *c) { for (int k = 0; k < MD_NLANES; ++k) if (c->lanes[k].stream) cudaStreamSynchronize(c->lanes[k].stream); }
@@ -845,9 +842,13 @@ extern "C" md_ctx *md_create(const md_config *cfg, int device) {
     size_t hb = (size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2 * sizeof(uint32_t);
     if (cudaMalloc(&c->d_hist, hb) != cudaSuccess || cudaMalloc(&c->d_lens, 4 * sizeof(int32_t)) != cudaSuccess) { g_err = "cudaMalloc(hist) failed"; delete c; return nullptr; }
     cudaMemsetAsync(c->d_hist, 0, hb, L->stream); cudaMemsetAsync(c->d_lens, 0, 4 * sizeof(int32_t), L->stream);
-    cudaFuncSetAttribute(count_warp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0).total);
-    cudaFuncSetAttribute(count_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1).total);
-    cudaFuncSetAttribute(count_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2).total);
+    cudaFuncSetAttribute(count_warp<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0).total);
+    cudaFuncSetAttribute(count_warp<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1).total);
+    cudaFuncSetAttribute(count_warp<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2).total);
+    cudaFuncSetAttribute(count_warp<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0).total);
+    cudaFuncSetAttribute(count_warp<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1).total);
+    cudaFuncSetAttribute(count_warp<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2).total);
+    if (const char *v = getenv("MD_EV")) { int e = atoi(v); if (e == 1 || e == 2) c->ev = e; }
     cudaStreamSynchronize(L->stream);
     return c;
 }
@@ -953,9 +954,17 @@ static int launch_count(md_ctx *c, Lane *L, const Contig &g, const DevReads &R, 
     A.ref = g.d_seq; A.reflen = g.len; A.beg = beg; A.end = end; A.W = W; A.chunk_bounds = g.d_bounds; A.n_chunks = g.n_chunks;
     A.calls = (md_call *) L->calls.p; A.cap = cap_calls; A.dir = (uint2 *) L->dir.p; A.counters = (uint32_t *) L->counters.p; A.hist = c->d_hist; A.lens = c->d_lens;
     if (W != 16 * WS_WARPS * 32) { g_err = "internal: window size must be 4096"; return -3; }
-    if (mbias) count_warp<2><<<n_win, WS_WARPS * 32, warp_layout(W, 2).total, s>>>(A);
-    else if (kp.minOppositeDepth > 0) count_warp<1><<<n_win, WS_WARPS * 32, warp_layout(W, 1).total, s>>>(A);
-    else count_warp<0><<<n_win, WS_WARPS * 32, warp_layout(W, 0).total, s>>>(A);
+    const int mode = mbias ? 2 : (kp.minOppositeDepth > 0 ? 1 : 0);
+    const size_t sm = warp_layout(W, mode).total;
+    if (c->ev == 2) {
+        if (mode == 2) count_warp<2, 2><<<n_win, WS_WARPS * 32, sm, s>>>(A);
+        else if (mode == 1) count_warp<1, 2><<<n_win, WS_WARPS * 32, sm, s>>>(A);
+        else count_warp<0, 2><<<n_win, WS_WARPS * 32, sm, s>>>(A);
+    } else {
+        if (mode == 2) count_warp<2, 1><<<n_win, WS_WARPS * 32, sm, s>>>(A);
+        else if (mode == 1) count_warp<1, 1><<<n_win, WS_WARPS * 32, sm, s>>>(A);
+        else count_warp<0, 1><<<n_win, WS_WARPS * 32, sm, s>>>(A);
+    }
     c->launches += 1;
     if (!mbias) {
         dir_scan_kernel<<<1, 1024, 0, s>>>((uint2 *) L->dir.p, n_win, (uint32_t *) L->sorted_off.p);

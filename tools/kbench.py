@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Kernel A/B bench (development aid): device-resident pipeline timings per count-kernel variant and workload.
-usage: python tools/kbench.py [--variants 2,3,4] [--steps 10] [--panel]"""
+usage: python tools/kbench.py [--variants 1,2] [--steps 10] [--panel]   (variants = MD_EV values: candidates per lane per evaluate round)"""
 import argparse
 import json
 import os
@@ -24,7 +24,7 @@ def dataset(name, args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--variants", default="2,3,4")
+    ap.add_argument("--variants", default="1,2")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--panel", action="store_true")
     a = ap.parse_args()
@@ -40,7 +40,7 @@ def main():
         for cname, cfg in cfgs:
             base = None
             for v in a.variants.split(","):
-                os.environ["MD_COUNT_KERNEL"] = v
+                os.environ["MD_EV"] = v
                 g = api.GpuContext(cfg)
                 g.load_contig(0, ref)
                 d = g.upload(soa)
