@@ -808,7 +808,7 @@ struct md_ctx {
     uint32_t *d_hist = nullptr; int32_t *d_lens = nullptr;
     uint64_t launches = 0;
     uint32_t W = 4096;
-    int ev = 1;                          // candidates per lane per evaluate round (count_warp<MODE, EV>)
+    int ev = 2;                          // candidates per lane per evaluate round (count_warp<MODE, EV>); 2 measured ~2 % faster than 1
 };
 
 static void sync_all(md_ctx *c) { for (int k = 0; k < MD_NLANES; ++k) if (c->lanes[k].stream) cudaStreamSynchronize(c->lanes[k].stream); }
