@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MDGPU_ABI_VERSION 2
+#define MDGPU_ABI_VERSION 3
 
 /* ---- options that reach the hot path: the subset of `Config`
  *      (MethylDackel.h:90-126) read by filter_func / the per-column loop ---- */
@@ -38,7 +38,8 @@ typedef struct md_config {
     int32_t bounds[16];                     /* --OT/--OB/--CTOT/--CTOB, common.c:137-172    */
     int32_t absoluteBounds[16];             /* --nOT/.., common.c:174-208                   */
     int32_t noOverlapMerge;                 /* 1 = mbias semantics (MBias.c:160: no ctor)   */
-    int32_t reserved[7];
+    float   minConversionEfficiency;        /* common.c:442-444; 0 = off                     */
+    int32_t reserved[6];
 } md_config;
 
 /* ---- one tile of decoded alignments, structure-of-arrays.
@@ -81,6 +82,12 @@ typedef struct md_reads_soa {
 typedef struct md_tile_desc {
     int32_t  tid;                /* contig id previously given to md_load_contig()              */
     uint32_t beg, end;           /* owned reference interval [beg,end)                          */
+    uint32_t ce_beg, ce_end;     /* only read when minConversionEfficiency > 0: the reference window
+                                    contig[ce_beg, ce_end) of the chunk the tile lies in, i.e.
+                                    [localPos-2, localEnd+11) clipped to the contig (extract.c:369-381,
+                                    common.c:363): computeConversionEfficiency only sees this window,
+                                    so the verdict on a read depends on the chunk; ce_end = 0 means
+                                    the whole contig                                               */
 } md_tile_desc;
 
 /* One reported reference column (the values extract.c:420-461 hands to writeCall) */

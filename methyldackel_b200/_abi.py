@@ -21,7 +21,7 @@ class MdConfig(C.Structure):
         ("ignoreFlags", C.c_int32), ("requireFlags", C.c_int32), ("ignoreNH", C.c_int32),
         ("minOppositeDepth", C.c_int32), ("maxVariantFrac", C.c_double),
         ("bounds", C.c_int32 * 16), ("absoluteBounds", C.c_int32 * 16),
-        ("noOverlapMerge", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("noOverlapMerge", C.c_int32), ("minConversionEfficiency", C.c_float), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -49,7 +49,7 @@ class MdReadsSoa(C.Structure):
 
 
 class MdTileDesc(C.Structure):
-    _fields_ = [("tid", C.c_int32), ("beg", C.c_uint32), ("end", C.c_uint32)]
+    _fields_ = [("tid", C.c_int32), ("beg", C.c_uint32), ("end", C.c_uint32), ("ce_beg", C.c_uint32), ("ce_end", C.c_uint32)]
 
 
 class MdCall(C.Structure):

@@ -72,7 +72,8 @@ static void extract_usage() {
 "  --minOppositeDepth INT  --maxVariantFrac FLOAT\n"
 "  --OT/--OB/--CTOT/--CTOB INT,INT,INT,INT   --nOT/--nOB/--nCTOT/--nCTOB INT,INT,INT,INT\n"
 "  -h/--help  -v/--version\n"
-"Not available in this build yet: -l/--keepStrand (BED), -M/-t/-b/-O/-N/-B (mappability), --minConversionEfficiency.\n"
+"  --minConversionEfficiency FLOAT\n"
+"Not available in this build yet: -l/--keepStrand (BED), -M/-t/-b/-O/-N/-B (mappability).\n"
 "Note that --fraction, --counts, and --logit are mutually exclusive!\n");
 }
 
@@ -213,8 +214,9 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     if (o.cytosine_report + o.merge == 2) { fprintf(stderr, "--mergeContext and --cytosine_report are mutually exclusive.\n"); extract_usage(); return 1; }
     if (!(o.core.keepCpG + o.core.keepCHG + o.core.keepCHH)) {
         fprintf(stderr, "You haven't specified any metrics to output!\nEither don't use the --noCpG option or specify --CHG and/or --CHH.\n"); return -1; }
-    if (bedName || bwName || bbmName || minConvEff > 0.0) {
-        fprintf(stderr, "This B200 build of the extract path does not implement -l, -M/-B or --minConversionEfficiency yet.\n"); return 1; }
+    if (bedName || bwName || bbmName) {
+        fprintf(stderr, "This B200 build of the extract path does not implement -l or -M/-B yet.\n"); return 1; }
+    o.core.minConversionEfficiency = (float) minConvEff;            // Config.minConversionEfficiency is a float (MethylDackel.h:110)
 
     Driver d; d.be = be;
     const char *fastaName = argv[optind], *bamName = argv[optind + 1];
@@ -322,9 +324,14 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             if (rend > ref->size()) rend = (uint32_t) ref->size();
             if (be->load_contig(d.dev, (int32_t) tid, ref->data(), (uint32_t) ref->size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
             d.seek_to((int) tid, rbeg);
-            FragTiler tiler(*d.bam, d.frag, d.frag_i, (int) tid, rbeg, rend, tile_reads);
             calls.clear(); calls_head = 0; carry.clear();
             size_t next_chunk = 0;
+            // With --minConversionEfficiency the verdict on an alignment depends on the reference chunk it is looked at in
+            // (computeConversionEfficiency only sees that chunk's window, common.c:363,378), so tiles are cut at chunk ends
+            // and carry the chunk window; otherwise the whole run of chunks is one region.
+            const bool per_chunk = o.core.minConversionEfficiency > 0.0f;
+            std::vector<Chunk> regions;
+            if (per_chunk) regions = chunks; else regions.push_back(Chunk{tid, rbeg, rend});
             // completed tiles arrive in order; hand every finished reference chunk to the writer
             auto absorb = [&](uint32_t done_upto, bool last) {
                 double t0 = now_s();
@@ -354,6 +361,10 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
                 return 0;
             };
             size_t rk = 0;
+            for (size_t ri = 0; ri < regions.size() && rc == 0; ++ri) {
+            const uint32_t gbeg = regions[ri].beg, gend = std::min<uint32_t>(regions[ri].end, (uint32_t) ref->size());
+            const uint32_t ce_beg = per_chunk ? (gbeg > 1 ? gbeg - 2 : 0) : 0, ce_end = per_chunk ? (uint32_t) std::min<uint64_t>((uint64_t) regions[ri].end + 11, ref->size()) : 0;
+            FragTiler tiler(*d.bam, d.frag, d.frag_i, (int) tid, gbeg, gend, tile_reads);
             for (;;) {
                 SoaTile &tile = *ring[rk % ring.size()];
                 // the ring slot we are about to refill must have been collected
@@ -365,7 +376,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
                 if (!got) break;
                 if (tile.n() == 0) { if (!use_async) absorb(tile.end, false); continue; }
                 if (pack_q) tile.pack_quals(*qscratch[rk % ring.size()], *qoffscratch[rk % ring.size()]);
-                md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end};
+                md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end, ce_beg, ce_end};
                 uint64_t cap = (uint64_t)(tile.end - tile.beg) + 16;
                 g_stats.n_records += tile.n(); g_stats.n_tiles++;
                 if (use_async) {
@@ -387,6 +398,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
                     absorb(tile.end, false);
                 }
             }
+            }   // regions
             while (rc == 0 && !flight.empty()) rc = collect_one();
             if (rc == 0) absorb(rend, true);
             be->drop_contig(d.dev, (int32_t) tid);
@@ -526,7 +538,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
                 if (!got) break;
                 if (tile.n() == 0) continue;
                 if (pack_quals_enabled()) tile.pack_quals(mb_qscratch, mb_qoffscratch);
-                md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end}; md_tile_stats st;
+                md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end, 0, 0}; md_tile_stats st;
                 t0 = now_s();
                 int r = be->mbias_tile(d.dev, &td, &v, &st);
                 g_stats.t_device_s += now_s() - t0;
@@ -596,7 +608,7 @@ extern "C" int mdh_bam_make_tiles(mdh_bam *b, int tid, uint32_t beg, uint32_t en
 extern "C" int mdh_bam_get_tile(mdh_bam *b, int k, md_tile_desc *td, md_reads_soa *out) {
     if (k < 0 || (size_t) k >= b->tiles.size()) return -1;
     SoaTile &t = *b->tiles[(size_t) k];
-    td->tid = t.tid; td->beg = t.beg; td->end = t.end;
+    td->tid = t.tid; td->beg = t.beg; td->end = t.end; td->ce_beg = 0; td->ce_end = 0;
     *out = t.view();
     return 0;
 }

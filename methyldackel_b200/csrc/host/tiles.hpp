@@ -216,8 +216,9 @@ public:
             bs_.pop();
         }
         t.end = cut;
-        if (stream_end) done_ = true;
-        else { for (size_t i = 0; i < t.n(); ++i) if (span_end(t, i) > cut) carry.add_from(t, i); cur_beg_ = cut; }
+        // reads reaching beyond the cut (or beyond the region end) are handed on: to the next tile, or to the tiler of the adjacent region
+        for (size_t i = 0; i < t.n(); ++i) if (span_end(t, i) > cut) carry.add_from(t, i);
+        if (stream_end) done_ = true; else cur_beg_ = cut;
         return true;
     }
 private:

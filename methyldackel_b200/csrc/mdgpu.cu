@@ -61,6 +61,7 @@ struct KParams {
     int minOppositeDepth; double maxVariantFrac;
     int bounds[16], abounds[16];
     int noOverlap;
+    float minCE;               // --minConversionEfficiency (common.c:442-444); 0 = off
     unsigned char boost[256];  // (uint8_t)(q + 0.2*q), overlaps.c:103,106, tabulated on the host in double
 };
 
@@ -146,7 +147,60 @@ __device__ __forceinline__ uint32_t hash_slot(unsigned long long key, uint32_t c
 // index (atomicCAS); a later record with the same name finds it, and claims it as its mate with one atomicCAS on mate[]
 // (overlaps.c:129-135: the stored record is `a`).  A third record of the same name cannot claim anything: the tile is
 // then flagged (C_MULTI) and replayed exactly on the host.  mate[] must be preset to -1 and tab[] to 0xffffffff.
-__global__ void __launch_bounds__(256) prep_kernel(DevReads R, KParams P, int32_t *rend, uint8_t *info, HashTab T, int32_t *mate, uint32_t *counters) {
+// context classification on an absolute window [lo,hi) of the contig (common.c:49-82 chained as
+// extract.c:407-418).  Returns 0, or (type+1) | isG<<2 with type 0 CpG, 1 CHG, 2 CHH.
+__device__ __forceinline__ bool d_isC(unsigned char b) { return b == 'C' || b == 'c'; }
+__device__ __forceinline__ bool d_isG(unsigned char b) { return b == 'G' || b == 'g'; }
+
+template <class Get>
+__device__ __forceinline__ unsigned dev_context(Get get, long long p, long long lo, long long hi) {
+    if (p < lo || p >= hi) return 0;
+    unsigned char c = get(p);
+    if (d_isC(c)) {
+        if (p + 1 != hi && d_isG(get(p + 1))) return 1;
+        if (p + 2 < hi && d_isG(get(p + 2))) return 2;
+        return 3;
+    }
+    if (d_isG(c)) {
+        if (p != lo && d_isC(get(p - 1))) return 1 | 4;
+        if (p - lo > 1 && d_isC(get(p - 2))) return 2 | 4;
+        return 3 | 4;
+    }
+    return 0;
+}
+
+// computeConversionEfficiency (common.c:361-404) of one alignment inside the chunk window contig[ce_beg, ce_end).
+// Quirks kept: the reference position is not advanced after a match op (no `pos += opLen` at common.c:373-391); CpG
+// positions are skipped; the walk ends at the window end (:378).  Window indices below 0 — a read that starts before
+// the window, where the reference reads out of bounds — count as "no context".
+__device__ float dev_conversion_efficiency(const DevReads &R, const KParams &P, uint32_t i, int strand, const unsigned char *ref, uint32_t ce_beg, uint32_t ce_end) {
+    unsigned nM = 0, nU = 0;
+    long long pos = R.pos[i]; int seqPos = 0;
+    const uint32_t soff = R.seq_off[i], qoff = R.qual_off[i];
+    auto get = [&](long long x) -> unsigned char { return __ldg(ref + x); };
+    for (uint32_t k = R.cigar_off[i], ke = R.cigar_off[i + 1]; k < ke; ++k) {
+        const uint32_t c = __ldg(R.cigar + k), op = c & 15u; const int len = (int)(c >> 4);
+        if (op == 0 || op == 7 || op == 8) {
+            for (int j = 0; j < len; ++j, ++seqPos) {
+                if (pos + j >= (long long) ce_end) goto done;
+                if (pos + j < (long long) ce_beg) continue;
+                const unsigned cx = dev_context(get, pos + j, (long long) ce_beg, (long long) ce_end);
+                if (cx == 0 || (cx & 3u) == 1u) continue;                        // not a cytosine column, or CpG
+                if ((int) dev_qual(R, qoff, seqPos) < P.minPhred) continue;      // getMethylState, common.c:347
+                const unsigned b = dev_base(R.seq, soff, seqPos);
+                if (strand & 1) { if (b == 2u) ++nM; else if (b == 8u) ++nU; }
+                else { if (b == 4u) ++nM; else if (b == 1u) ++nU; }
+            }
+        } else if (op == 1 || op == 4) seqPos += len;
+        else if (op == 2 || op == 3) pos += len;
+    }
+done:
+    if (nM + nU == 0) return 1.0f;
+    return __fdiv_rn((float) nU, (float)(nM + nU));
+}
+
+__global__ void __launch_bounds__(256) prep_kernel(DevReads R, KParams P, int32_t *rend, uint8_t *info, HashTab T, int32_t *mate, uint32_t *counters,
+                                                   const unsigned char *ref, uint32_t ce_beg, uint32_t ce_end) {
     // grid-stride over the alignments; the five tile-wide statistics are reduced per thread, then per CTA, so the
     // global counters see one atomic per CTA instead of one per warp (same-address L2 atomics serialise)
     uint32_t n_ok = 0, n_paired = 0, n_multi = 0, span_max = 0, lq_max = 0;
@@ -160,7 +214,8 @@ __global__ void __launch_bounds__(256) prep_kernel(DevReads R, KParams P, int32_
             if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) ql += len;
         }
         const uint32_t lq = R.l_qseq[i];
-        const bool ok = dev_admit(P, f, R.mapq[i], a) && strand != 0 && rl > 0 && ql == lq && lq > 0;
+        bool ok = dev_admit(P, f, R.mapq[i], a) && strand != 0 && rl > 0 && ql == lq && lq > 0;
+        if (ok && P.minCE > 0.0f && dev_conversion_efficiency(R, P, i, strand, ref, ce_beg, ce_end) < P.minCE) ok = false;   // common.c:442-444
         const bool elig = ok && (f & 1u) && !(f & 12u) && !P.noOverlap;      // overlaps.c:128
         rend[i] = R.pos[i] + rl;
         info[i] = (uint8_t)(strand | (ok ? INFO_ADMIT : 0) | (elig ? INFO_ELIG : 0));
@@ -215,28 +270,6 @@ __global__ void __launch_bounds__(256) window_kernel(const int32_t *pos, uint32_
 }
 
 // ------------------------------------------------------------------------------------------------
-// context classification on an absolute window [lo,hi) of the contig (common.c:49-82 chained as
-// extract.c:407-418).  Returns 0, or (type+1) | isG<<2 with type 0 CpG, 1 CHG, 2 CHH.
-__device__ __forceinline__ bool d_isC(unsigned char b) { return b == 'C' || b == 'c'; }
-__device__ __forceinline__ bool d_isG(unsigned char b) { return b == 'G' || b == 'g'; }
-
-template <class Get>
-__device__ __forceinline__ unsigned dev_context(Get get, long long p, long long lo, long long hi) {
-    if (p < lo || p >= hi) return 0;
-    unsigned char c = get(p);
-    if (d_isC(c)) {
-        if (p + 1 != hi && d_isG(get(p + 1))) return 1;
-        if (p + 2 < hi && d_isG(get(p + 2))) return 2;
-        return 3;
-    }
-    if (d_isG(c)) {
-        if (p != lo && d_isC(get(p - 1))) return 1 | 4;
-        if (p - lo > 1 && d_isC(get(p - 2))) return 2 | 4;
-        return 3 | 4;
-    }
-    return 0;
-}
-
 // Locate the query index of reference position rp in a read (M/=/X only); -1 if rp falls in D/N or outside.
 __device__ __forceinline__ int dev_qpos_at(const uint32_t *cigar, uint32_t k, uint32_t ke, int pos, int rp) {
     int p = pos, q = 0;
@@ -820,7 +853,7 @@ static void fill_kparams(const md_config *c, KParams &k) {
     k.keepMask = (c->keepCpG ? 1 : 0) | (c->keepCHG ? 2 : 0) | (c->keepCHH ? 4 : 0);
     k.minOppositeDepth = c->minOppositeDepth; k.maxVariantFrac = c->maxVariantFrac;
     for (int i = 0; i < 16; ++i) { k.bounds[i] = c->bounds[i] < 0 ? 0 : c->bounds[i]; k.abounds[i] = c->absoluteBounds[i] < 0 ? 0 : c->absoluteBounds[i]; }
-    k.noOverlap = c->noOverlapMerge;
+    k.noOverlap = c->noOverlapMerge; k.minCE = c->minConversionEfficiency;
     for (int q = 0; q < 256; ++q) { volatile double v = (double) q; volatile double t = 0.2 * v; volatile double s = v + t; k.boost[q] = (unsigned char)(int) s; }
 }
 
@@ -1001,7 +1034,9 @@ static int run_pipeline(md_ctx *c, Lane *L, const md_tile_desc *t, const DevRead
     KParams kp = c->kp; if (mbias) kp.noOverlap = 1;
     if (n) {
         const uint32_t gb = std::min<uint32_t>((n + 255) / 256, 148u * 8u);     // 8 CTAs of 256 threads per SM, grid-stride
-        prep_kernel<<<gb, 256, 0, s>>>(R, kp, (int32_t *) L->rend.p, (uint8_t *) L->info.p, T, (int32_t *) L->mate.p, (uint32_t *) L->counters.p);
+        uint32_t ce_beg = t->ce_beg, ce_end = (t->ce_end == 0 || t->ce_end > g.len) ? g.len : t->ce_end;
+        if (ce_beg > ce_end) ce_beg = ce_end;
+        prep_kernel<<<gb, 256, 0, s>>>(R, kp, (int32_t *) L->rend.p, (uint8_t *) L->info.p, T, (int32_t *) L->mate.p, (uint32_t *) L->counters.p, g.d_seq, ce_beg, ce_end);
         c->launches += 1;
     }
     if (n_win) {

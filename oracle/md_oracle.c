@@ -91,8 +91,41 @@ typedef struct {
 
 static void free_work(work_t *w) { free(w->b); free(w->q); free(w->off); free(w->admit); free(w->strand); free(w->rend); }
 
+/* computeConversionEfficiency, common.c:361-404, on the window contig[ce_beg, ce_end) of the chunk.
+ * Restated with its quirks: the reference position is NOT advanced after a match op (common.c:373-391 has no
+ * `pos += opLen`), CpG positions are skipped, the walk stops at the window end (:378).  Window indices below 0
+ * (a read starting before the window) read out of bounds in the reference; they are treated as "no context" here. */
+static float conversion_efficiency(const md_config *c, const md_reads_soa *r, uint32_t i, int strand, const char *ref, uint32_t ce_beg, uint32_t ce_end) {
+    unsigned nMethyl = 0, nUMethyl = 0;
+    int64_t pos = r->pos[i]; uint32_t seqPos = 0;
+    const int lseq = (int)(ce_end - ce_beg);
+    for (uint32_t k = r->cigar_off[i]; k < r->cigar_off[i + 1]; ++k) {
+        uint32_t op = r->cigar[k] & 15, len = r->cigar[k] >> 4;
+        if (op == 0 || op == 7 || op == 8) {
+            for (uint32_t j = 0; j < len; ++j, ++seqPos) {
+                if (pos + j >= (int64_t) ce_end) goto done;                                     /* :378 */
+                int64_t idx = pos + j - (int64_t) ce_beg;
+                if (idx < 0) continue;
+                int ctx = mdo_context(ref + ce_beg, (int) idx, lseq);
+                if (ctx == 0 || ctx == 1 || ctx == -1) continue;                               /* :379-380: CpG skipped */
+                /* getMethylState, common.c:338-354: raw base and phred (trims come later, :458) */
+                int state = 0; uint8_t b = seq_nib(r, i, seqPos);
+                if ((int) qual_at(r, i, seqPos) >= c->minPhred) {
+                    if (b == 2 && (strand & 1)) state = 1; else if (b == 8 && (strand & 1)) state = -1;
+                    else if (b == 4 && !(strand & 1)) state = 1; else if (b == 1 && !(strand & 1)) state = -1;
+                }
+                if (state > 0) nMethyl++; else if (state < 0) nUMethyl++;
+            }
+        } else if (op == 1 || op == 4) seqPos += len;
+        else if (op == 2 || op == 3) pos += len;
+    }
+done:
+    if (nMethyl + nUMethyl == 0) return 1.0f;                                                   /* :357 */
+    return nUMethyl / ((float)(nMethyl + nUMethyl));                                            /* :358 */
+}
+
 /* filter + strand + trimAlignment (common.c:137-172) + trimAbsoluteAlignment (common.c:174-208) */
-static int build_work(const md_config *c, const md_reads_soa *r, work_t *w, uint32_t *n_adm) {
+static int build_work(const md_config *c, const md_reads_soa *r, work_t *w, uint32_t *n_adm, const char *ref, uint32_t ce_beg, uint32_t ce_end) {
     uint32_t n = r->n_reads;
     memset(w, 0, sizeof *w);
     w->off = (uint64_t *) malloc(((size_t) n + 1) * sizeof(uint64_t));
@@ -118,6 +151,7 @@ static int build_work(const md_config *c, const md_reads_soa *r, work_t *w, uint
         /* a record whose CIGAR does not describe its SEQ, with no reference span, or with an
          * undeterminable strand (the reference asserts, common.c:122-125) cannot be piled up */
         int ok = mdo_admit(c, r->flag[i], r->mapq[i], r->aux[i]) && s != 0 && rl > 0 && qlen == r->l_qseq[i] && r->l_qseq[i] > 0;
+        if (ok && c->minConversionEfficiency > 0.0f && conversion_efficiency(c, r, i, s, ref, ce_beg, ce_end) < c->minConversionEfficiency) ok = 0;   /* common.c:442-444 */
         w->admit[i] = (uint8_t) ok;
         if (!ok) continue;
         ++*n_adm;
@@ -260,10 +294,17 @@ static int pair_and_merge(const md_reads_soa *r, work_t *w, uint32_t *n_pairs, u
 
 int mdo_extract_tile(const md_config *c, const char *ref, uint32_t reflen, uint32_t beg, uint32_t end,
                      const md_reads_soa *r, md_call *out, uint64_t cap, md_tile_stats *st) {
+    return mdo_extract_tile_ce(c, ref, reflen, beg, end, 0, 0, r, out, cap, st);
+}
+
+int mdo_extract_tile_ce(const md_config *c, const char *ref, uint32_t reflen, uint32_t beg, uint32_t end, uint32_t ce_beg, uint32_t ce_end,
+                        const md_reads_soa *r, md_call *out, uint64_t cap, md_tile_stats *st) {
     work_t w; uint32_t n_adm = 0, n_pairs = 0, n_multi = 0;
     if (end > reflen) end = reflen;
     if (beg > end) beg = end;
-    if (build_work(c, r, &w, &n_adm) < 0) { free_work(&w); return -2; }
+    if (ce_end == 0 || ce_end > reflen) ce_end = reflen;
+    if (ce_beg > ce_end) ce_beg = ce_end;
+    if (build_work(c, r, &w, &n_adm, ref, ce_beg, ce_end) < 0) { free_work(&w); return -2; }
     if (!c->noOverlapMerge && pair_and_merge(r, &w, &n_pairs, &n_multi) < 0) { free_work(&w); return -2; }
     size_t span = (size_t)(end - beg);
     uint32_t *nm = (uint32_t *) calloc(span + 1, 4), *nu = (uint32_t *) calloc(span + 1, 4), *noff = (uint32_t *) calloc(span + 1, 4), *nvar = (uint32_t *) calloc(span + 1, 4);
@@ -330,7 +371,7 @@ int mdo_mbias_tile(const md_config *c, const char *ref, uint32_t reflen, uint32_
                    const md_reads_soa *r, uint32_t *hist, int32_t lens[4], md_tile_stats *st) {
     work_t w; uint32_t n_adm = 0;
     if (end > reflen) end = reflen;
-    if (build_work(c, r, &w, &n_adm) < 0) { free_work(&w); return -2; }
+    if (build_work(c, r, &w, &n_adm, ref, 0, reflen) < 0) { free_work(&w); return -2; }
     for (uint32_t i = 0; i < r->n_reads; ++i) {
         if (!w.admit[i]) continue;
         int s = w.strand[i];

@@ -21,6 +21,9 @@ extern "C" {
  * (info bit3).  Returns 0, or -1 if `cap` was too small (stats->n_required tells how many). */
 int mdo_extract_tile(const md_config *cfg, const char *ref, uint32_t reflen, uint32_t beg, uint32_t end,
                      const md_reads_soa *reads, md_call *out, uint64_t cap, md_tile_stats *stats);
+/* same with the conversion-efficiency window of the tile's chunk (md_tile_desc::ce_beg/ce_end; 0,0 = whole contig) */
+int mdo_extract_tile_ce(const md_config *cfg, const char *ref, uint32_t reflen, uint32_t beg, uint32_t end, uint32_t ce_beg, uint32_t ce_end,
+                        const md_reads_soa *reads, md_call *out, uint64_t cap, md_tile_stats *stats);
 
 /* mbias accumulation (MBias.c:145-218). `bounds`/`n_chunks` as md_set_mbias_chunks();
  * hist is uint32[4*2*MD_MBIAS_MAXLEN*2] and is ADDED to; lens[] is max-updated. */

@@ -25,10 +25,11 @@ REFERENCE_TESTS = [
      {"_CpG.bedGraph": 48}),                                                                                  # test.py:92
     ("t10", [], "chgchh.fa", "chgchh_aln.bam", {"_CpG.bedGraph": 2}),                                        # test.py:101
     ("t11", ["-q", "5"], "chgchh.fa", "chgchh_aln.bam", {"_CpG.bedGraph": 3}),                               # test.py:109
+    ("t12", ["-q", "5", "--minConversionEfficiency", "0.9"], "chgchh.fa", "chgchh_aln.bam", {"_CpG.bedGraph": 2}),         # test.py:117
+    ("t13", ["-q", "5", "--minConversionEfficiency", "1.0"], "chgchh.fa", "chgchh_aln.bam", {"_CpG.bedGraph": 1}),         # test.py:125
     ("t14", ["-q", "1"], "cg100.fa", "NH.bam", {"_CpG.bedGraph": 1}),                                        # test.py:133
     ("t15", ["--ignoreNH", "-q", "1"], "cg100.fa", "NH.bam", {"_CpG.bedGraph": 49}),                         # test.py:141
 ]
-# tests 12/13 use --minConversionEfficiency, a SURVEY 8f "next" row not built yet.
 
 FIXTURE_EXTRA = [
     ("x_cyt", ["-q", "2", "--cytosine_report", "--CHG", "--CHH"], "cg100.fa", "cg_aln.bam"),
@@ -58,6 +59,10 @@ SYNTH_OPTION_SETS = [
     ["-r", "chr2", "--mergeContext"],
     ["-d", "5", "--noCpG", "--CHH"],
     ["-q", "40", "-p", "20", "-R", "2"],
+    # the conversion-efficiency filter is only well defined in the reference for reads that start inside the chunk window
+    # (it indexes the window with pos - offset, common.c:379); one chunk per contig keeps every read inside
+    ["--minConversionEfficiency", "0.97", "--CHH"],
+    ["--minConversionEfficiency", "0.9", "--mergeContext", "--OT", "3,140,3,140"],
 ]
 
 

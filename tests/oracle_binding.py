@@ -17,6 +17,8 @@ def lib():
         o = C.CDLL(os.path.join(ROOT, "oracle", "libmdoracle.so"))
         o.mdo_extract_tile.argtypes = [C.POINTER(A.MdConfig), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(A.MdReadsSoa),
                                        C.POINTER(A.MdCall), C.c_uint64, C.POINTER(A.MdTileStats)]
+        o.mdo_extract_tile_ce.argtypes = [C.POINTER(A.MdConfig), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(A.MdReadsSoa),
+                                          C.POINTER(A.MdCall), C.c_uint64, C.POINTER(A.MdTileStats)]
         o.mdo_mbias_tile.argtypes = [C.POINTER(A.MdConfig), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32,
                                      C.POINTER(A.MdReadsSoa), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(A.MdTileStats)]
         o.mdo_strand.argtypes = [C.c_uint16, C.c_uint8]
@@ -56,7 +58,7 @@ class OracleBackend:
 
         def extract_tile(_b, td, reads, calls, cap, stats):
             seq, n = st["contigs"][td.contents.tid]
-            return o.mdo_extract_tile(C.byref(st["cfg"]), seq, n, td.contents.beg, td.contents.end, reads, calls, cap, stats)
+            return o.mdo_extract_tile_ce(C.byref(st["cfg"]), seq, n, td.contents.beg, td.contents.end, td.contents.ce_beg, td.contents.ce_end, reads, calls, cap, stats)
 
         def set_chunks(_b, tid, bounds, n):
             st["chunks"][tid] = (C.c_uint32 * (n + 1))(*[bounds[i] for i in range(n + 1)])
