@@ -6,23 +6,20 @@
 // (extract.c:420-441).  That is column-major and serial.  Here the work is read-major inside
 // position-owned windows:
 //
-//   K1 prep_kernel    one thread per alignment: filter_func's admission tests (common.c:416-430),
-//                     getStrand (common.c:84-116), reference span, and — for the mate-overlap merge —
-//                     insertion of the read's 64-bit name key into an open-addressing table in HBM
-//                     (replaces the khash of overlaps.c:121-139).
-//                     (a later record with the same name claims the stored one as its mate with one atomicCAS;
-//                     a third record of a name flags the tile for an exact host replay).
-//   K3 window_kernel  per window of W reference positions: the range of alignments that can touch it.
-//   K4 count_kernel   one CTA per window: stages the reference window in shared memory, classifies
-//                     every position (isCpG/isCHG/isCHH, common.c:49-82), then warps stream the
-//                     window's alignments, expand CIGARs to reference coordinates, apply the trims
-//                     (common.c:137-208), the overlap phred merge lazily at the bases that matter
-//                     (overlaps.c:54-119), updateMetrics / isVariant (common.c:118-134,
-//                     extract.c:225-239) and accumulate into privatised shared-memory histograms;
-//                     the epilogue applies the variant-site test (extract.c:444-446), drops empty
-//                     columns (extract.c:461) and appends compact md_call records to HBM.
-//                     The mbias flavour (MBias.c:181-214) accumulates a per-(strand,read,qpos)
-//                     histogram instead.
+//   K1 prep_kernel    grid-stride, one thread per alignment: filter_func's admission tests (common.c:416-430),
+//                     getStrand (common.c:84-116), reference span, the optional conversion-efficiency filter
+//                     (common.c:361-404) and mate pairing through a 4-byte-per-slot open-addressing table that stays
+//                     in L2 (replaces the khash of overlaps.c:121-139).
+//   K2 count_warp     one CTA per window of 4096 reference positions: stages the reference window in shared memory and
+//                     classifies every position bit-parallel (isCpG/isCHG/isCHH, common.c:49-82); then every warp
+//                     streams batches of 32 alignments through TMA bulk copies into its own shared-memory staging
+//                     buffer, walks the CIGARs against bitmaps of the kept C-/G-sites, queues candidate bases with
+//                     warp ballots and evaluates them 32 at a time: trims (common.c:137-208), the overlap phred merge
+//                     (overlaps.c:54-119), updateMetrics / isVariant (common.c:118-134, extract.c:225-239), shared-memory
+//                     atomicAdd; the epilogue applies the variant-site test (extract.c:444-446), drops empty columns
+//                     (extract.c:461) and appends compact md_call records to HBM.  count_warp<2> is the mbias flavour
+//                     (MBias.c:181-214: a per-(strand,read,qpos) histogram).
+//   K3 dir_scan + gather   put the per-window segments into position order.
 //
 // Integer / byte work, HBM-bound by design: no tensor cores, no GEMM reshaping.
 #include <cuda_runtime.h>
@@ -255,21 +252,21 @@ __global__ void __launch_bounds__(256) prep_kernel(DevReads R, KParams P, int32_
     }
 }
 
-// K3: first/last alignment index that can touch each window
-__global__ void __launch_bounds__(256) window_kernel(const int32_t *pos, uint32_t n, uint32_t beg, uint32_t W, uint32_t n_win, const uint32_t *counters, uint2 *win) {
-    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_win) return;
-    long long w0 = (long long) beg + (long long) w * W, w1 = w0 + W;
-    long long lo_pos = w0 - (long long) counters[C_MAXSPAN];      // a read starting at or before this cannot reach w0
-    uint32_t a = 0, b = n;
-    while (a < b) { uint32_t mid = (a + b) >> 1; if ((long long) pos[mid] <= lo_pos) a = mid + 1; else b = mid; }
-    uint32_t r0 = a;
-    b = n;
-    while (a < b) { uint32_t mid = (a + b) >> 1; if ((long long) pos[mid] < w1) a = mid + 1; else b = mid; }
-    win[w] = make_uint2(r0, a);
+// First index in [0,n) whose pos is > key (pos ascending), found by the whole warp: 32 probes per step, ~log32(n) dependent loads.
+__device__ __forceinline__ uint32_t warp_upper_bound(const int32_t *pos, uint32_t n, long long key, int lane) {
+    uint32_t lo = 0, hi = n;
+    while (hi > lo) {
+        const uint32_t span = hi - lo, step = (span + 31u) / 32u;
+        const uint32_t idx = lo + (uint32_t) lane * step;
+        const bool le = idx < hi && (long long) __ldg(pos + idx) <= key;        // monotone: true for every index below the answer
+        const unsigned k = (unsigned) __popc(__ballot_sync(0xffffffffu, le));
+        if (k == 0) { hi = lo; break; }
+        const uint32_t nlo = lo + (k - 1u) * step + 1u, nhi = min(lo + k * step, hi);
+        lo = nlo; hi = nhi;
+    }
+    return lo;
 }
 
-// ------------------------------------------------------------------------------------------------
 // Locate the query index of reference position rp in a read (M/=/X only); -1 if rp falls in D/N or outside.
 __device__ __forceinline__ int dev_qpos_at(const uint32_t *cigar, uint32_t k, uint32_t ke, int pos, int rp) {
     int p = pos, q = 0;
@@ -291,6 +288,8 @@ struct CountArgs {
     md_call *calls; unsigned long long cap; uint2 *dir;    // extract: output records + per-window directory (offset,count)
     uint32_t *counters;
     uint32_t *hist; int32_t *lens;                         // mbias
+    uint32_t st_seq, st_qual;                              // per-warp staging capacities in bytes (count_warp)
+    uint32_t wide;                                         // 1: 32-bit window counters; 0: 16-bit pairs packed in one word (overflow -> rerun wide)
 };
 
 #define MB_SM_Q 256   // mbias: query positions < this are histogrammed in shared memory
@@ -357,12 +356,19 @@ __device__ __forceinline__ void eval_hit(const CountArgs &A, const ReadCtx &rc, 
                 if (qi < MB_SM_Q) atomicAdd(cnt + (((s1 * 2 + rc.rd2) * MB_SM_Q + qi) * 2 + (rv < 0 ? 1 : 0)), 1u);
                 else if (qi < MD_MBIAS_MAXLEN) atomicAdd(A.hist + ((((size_t) s1 * 2 + rc.rd2) * MD_MBIAS_MAXLEN + qi) * 2 + (rv < 0 ? 1 : 0)), 1u);
                 if (qi < MD_MBIAS_MAXLEN) atomicMax(A.lens + s1, qi + 1);
-            } else atomicAdd(cnt + (rv > 0 ? o : W + o), 1u);
+            } else if (A.wide) atomicAdd(cnt + (rv > 0 ? o : W + o), 1u);
+            else {                                                // meth in the low half, unmeth in the high half of one word
+                const uint32_t old = atomicAdd(cnt + o, rv > 0 ? 1u : 0x10000u);
+                if ((rv > 0 ? (old & 0xffffu) : (old >> 16)) == 0xffffu) atomicExch(A.counters + C_OVERFLOW, 3u);   // a 16-bit field wrapped: the host reruns the tile wide
+            }
         }
     } else if (MODE == 1) {                                     // isVariant, extract.c:225-239
-        atomicAdd(cnt + 2 * W + o, 1u);
         const bool var = rc.wantG ? (b != 2u && b != 15u) : (b != 4u && b != 15u);
-        if (var) atomicAdd(cnt + 3 * W + o, 1u);
+        if (A.wide) { atomicAdd(cnt + 2 * W + o, 1u); if (var) atomicAdd(cnt + 3 * W + o, 1u); }
+        else {                                                    // nOff low half, nVariant high half
+            const uint32_t old = atomicAdd(cnt + W + o, var ? 0x10001u : 1u);
+            if ((old & 0xffffu) == 0xffffu) atomicExch(A.counters + C_OVERFLOW, 3u);
+        }
     }
 }
 
@@ -431,21 +437,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 //
 // This is the "warp-ballot branch flattening" of the north star: the divergent part (how many cytosines an
 // alignment covers) is reduced to a cheap iterator, the expensive part runs converged.
-#define WS_SEQ_BYTES 2560          // 32 alignments x 76 B (150-mers) + alignment slack
-#define WS_QUAL_BYTES 5120         // 32 x 152 B + slack
+#define WS_SEQ_BYTES 2560          // default per-warp staging: 32 alignments x 76 B (150-mers) + alignment slack
+#define WS_QUAL_BYTES 5120         // upper bound for the phred staging (32 x 152 B + slack for plain bytes); 2-/4-bit tiles use less
 #define WS_CTX_WORDS 10
 #define WS_QUEUE 192               // two candidate queues of 96 entries per warp (up to 63 left over + 32 new)
 #define WS_WARPS 8
 
 struct WarpLayout { uint32_t off_bm, off_cnt, off_warp, warp_stride, off_seq, off_qual, off_ctx, off_queue, total; };
-__host__ __device__ inline WarpLayout warp_layout(uint32_t W, int mode) {
+__host__ __device__ inline WarpLayout warp_layout(uint32_t W, int mode, uint32_t wide, uint32_t st_seq, uint32_t st_qual) {
     WarpLayout L; const uint32_t NW = W >> 5;
     auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
     L.off_bm = 128;                                              // [0,128): 8 mbarriers + ticket counter
     L.off_cnt = up(L.off_bm + 4u * (NW + 2u) * 4u);
-    const uint32_t ncnt = mode == 2 ? 4u * 2u * MB_SM_Q * 2u : (mode == 1 ? 4u * W : 2u * W);
+    const uint32_t ncnt = mode == 2 ? 4u * 2u * MB_SM_Q * 2u : ((mode == 1 ? 4u * W : 2u * W) >> (wide ? 0 : 1));
     L.off_warp = up(L.off_cnt + ncnt * 4u);
-    L.off_seq = 0; L.off_qual = up(WS_SEQ_BYTES + 32u); L.off_ctx = L.off_qual + up(WS_QUAL_BYTES + 32u);
+    L.off_seq = 0; L.off_qual = up(st_seq + 32u); L.off_ctx = L.off_qual + up(st_qual + 32u);
     L.off_queue = L.off_ctx + WS_CTX_WORDS * 32u * 4u;
     L.warp_stride = up(L.off_queue + WS_QUEUE * 4u);
     L.total = L.off_warp + WS_WARPS * L.warp_stride;
@@ -457,10 +463,10 @@ __host__ __device__ inline WarpLayout warp_layout(uint32_t W, int mode) {
 //  1: flags: bit0 wantG, bit1 rd2, bit2 has mate, bit3 is_a, bit4 mate_simple, bits8-10 strand
 //  2: mpos   3: mend   4: msoff   5: mqoff   6: mlo | mhi << 16   7: mk0   8: mk1
 template <int MODE, int EV>
-__global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
+__global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t W = A.W, NW = W >> 5;
-    const WarpLayout SL = warp_layout(W, MODE);
+    const WarpLayout SL = warp_layout(W, MODE, A.wide, A.st_seq, A.st_qual);
     uint64_t *bars = (uint64_t *) smem;                                   // [8]
     uint32_t *ticket = (uint32_t *)(smem + 64);
     uint32_t *bmC = (uint32_t *)(smem + SL.off_bm), *bmG = bmC + NW + 2, *bmT0 = bmG + NW + 2, *bmT1 = bmT0 + NW + 2;
@@ -475,15 +481,19 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
     const long long own1 = min((long long) A.end, w0 + (long long) W);
     const int own = (int)(own1 - w0), w0i = (int) w0;
     const DevReads &R = A.R;
-    const uint2 rr = A.win[w];
+    __shared__ uint32_t s_rr[2];
 
-    // ---- prologue: barriers, reference window, site bitmaps (as count_stream) --------------------------
+    // ---- prologue: barriers, reference window, site bitmaps --------------------------
     if (tid == 0) { for (int kk = 0; kk < WS_WARPS; ++kk) mbar_init(bars + kk, 1); *ticket = 0; mbar_fence_init(); }
+    // the window's alignment range: warp 0 finds the first alignment that can reach w0 (a read starting at or before w0 - maxspan
+    // cannot), warp 1 the first one starting at or beyond the window end — replaces a separate launch with two 32-ary searches
+    if (warp == 0) { const uint32_t r0 = warp_upper_bound(R.pos, R.n, w0 - (long long) A.counters[C_MAXSPAN], lane); if (lane == 0) s_rr[0] = r0; }
+    else if (warp == 1) { const uint32_t r1 = warp_upper_bound(R.pos, R.n, w0 + (long long) W - 1, lane); if (lane == 0) s_rr[1] = r1; }
     for (uint32_t t = tid; t < W + 4; t += WS_WARPS * 32) {
         long long p = w0 - 2 + t;
         refw[t] = (p >= 0 && p < (long long) A.reflen) ? __ldg(A.ref + p) : (unsigned char) 'N';
     }
-    const uint32_t ncnt = (MODE == 2) ? 4u * 2u * MB_SM_Q * 2u : (MODE == 1 ? 4u * W : 2u * W);
+    const uint32_t ncnt = (MODE == 2) ? 4u * 2u * MB_SM_Q * 2u : ((MODE == 1 ? 4u * W : 2u * W) >> (A.wide ? 0 : 1));
     for (uint32_t t = tid; t < ncnt; t += WS_WARPS * 32) cnt[t] = 0;
     if (tid < 8) { uint32_t *g = bmC + (tid >> 1) * (NW + 2); g[(tid & 1) ? NW + 1 : 0] = 0; }
     __syncthreads();
@@ -528,13 +538,14 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
         }
     }
     __syncthreads();                                                      // bitmaps complete; refw (overlay) no longer needed
+    const uint2 rr = make_uint2(s_rr[0], max(s_rr[0], s_rr[1]));
 
     // ---- streaming phase: every warp on its own -----------------------------------------------------------
     const uint32_t maxlq = A.counters[C_MAXLQ];
     const uint32_t seqb_max = ((((maxlq + 1u) >> 1) + 3u) >> 2) * 4u, qualb_max = qual_words_of(R, maxlq) * 8u;
     uint32_t nb = 32;
-    if (seqb_max) nb = min(nb, (uint32_t)(WS_SEQ_BYTES - 32u) / seqb_max);
-    if (qualb_max) nb = min(nb, (uint32_t)(WS_QUAL_BYTES - 32u) / qualb_max);
+    if (seqb_max) nb = min(nb, (A.st_seq - 32u) / seqb_max);
+    if (qualb_max) nb = min(nb, (A.st_qual - 32u) / qualb_max);
     if (maxlq >= (1u << 14)) nb = 0;                                      // query index must fit the queue entry
     auto ctx_code = [&](int rel) -> unsigned {
         const uint32_t wi = ((uint32_t) rel >> 5) + 1, b = 1u << (rel & 31);
@@ -578,7 +589,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
             uint32_t sw_end = min(__shfl_sync(0xffffffffu, soff, last) + ((((lql + 1u) >> 1) + 3u) >> 2), R.seq_words);
             uint32_t qw_end = min(__shfl_sync(0xffffffffu, qoff, last) + qual_words_of(R, lql), R.qual_words);
             uint32_t sbytes = sw_end > sw0 ? (sw_end - sw0) * 4u : 0u, qbytes = qw_end > qw0 ? (qw_end - qw0) * 8u : 0u;
-            sbytes = min((sbytes + 15u) & ~15u, (uint32_t) WS_SEQ_BYTES); qbytes = min((qbytes + 15u) & ~15u, (uint32_t) WS_QUAL_BYTES);
+            sbytes = min((sbytes + 15u) & ~15u, A.st_seq); qbytes = min((qbytes + 15u) & ~15u, A.st_qual);
             const uint32_t sw1 = sw0 + sbytes / 4u, qw1 = qw0 + qbytes / 8u;
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar, sbytes + qbytes);
@@ -731,11 +742,11 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
             const uint32_t t = t16 + kbit;
             bool excl = false;
             if (MODE == 1) {
-                const uint32_t noff = cnt[2 * W + t], nvar = cnt[3 * W + t];
+                const uint32_t noff = A.wide ? cnt[2 * W + t] : (cnt[W + t] & 0xffffu), nvar = A.wide ? cnt[3 * W + t] : (cnt[W + t] >> 16);
                 excl = A.P.minOppositeDepth > 0 && noff >= (uint32_t) A.P.minOppositeDepth && ((double) nvar) / ((double) noff) >= A.P.maxVariantFrac;
             }
             if (excl) rep |= 0x10000u << kbit;
-            if (excl || cnt[t] + cnt[W + t]) rep |= 1u << kbit;
+            if (excl || (A.wide ? cnt[t] + cnt[W + t] : cnt[t])) rep |= 1u << kbit;
         }
     }
     const uint32_t mine = __popc(rep & 0xffffu);
@@ -761,7 +772,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 2) count_warp(CountArgs A) {
         while (r16) {
             const int kbit = __ffs(r16) - 1; r16 &= r16 - 1;
             const uint32_t t = t16 + kbit;
-            md_call c; c.pos = (uint32_t)(w0 + t); c.nmeth = cnt[t]; c.nunmeth = cnt[W + t];
+            md_call c; c.pos = (uint32_t)(w0 + t); c.nmeth = A.wide ? cnt[t] : (cnt[t] & 0xffffu); c.nunmeth = A.wide ? cnt[W + t] : (cnt[t] >> 16);
             c.info = (((a16 >> kbit) & 1u) ? 0u : ((b16 >> kbit) & 1u) ? 1u : 2u) | (((g16 >> kbit) & 1u) ? 4u : 0u) | (((rep >> (16 + kbit)) & 1u) ? 8u : 0u);
             A.calls[o++] = c;
         }
@@ -875,12 +886,12 @@ extern "C" md_ctx *md_create(const md_config *cfg, int device) {
     size_t hb = (size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2 * sizeof(uint32_t);
     if (cudaMalloc(&c->d_hist, hb) != cudaSuccess || cudaMalloc(&c->d_lens, 4 * sizeof(int32_t)) != cudaSuccess) { g_err = "cudaMalloc(hist) failed"; delete c; return nullptr; }
     cudaMemsetAsync(c->d_hist, 0, hb, L->stream); cudaMemsetAsync(c->d_lens, 0, 4 * sizeof(int32_t), L->stream);
-    cudaFuncSetAttribute(count_warp<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0).total);
-    cudaFuncSetAttribute(count_warp<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1).total);
-    cudaFuncSetAttribute(count_warp<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2).total);
-    cudaFuncSetAttribute(count_warp<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0).total);
-    cudaFuncSetAttribute(count_warp<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1).total);
-    cudaFuncSetAttribute(count_warp<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2).total);
+    cudaFuncSetAttribute(count_warp<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
+    cudaFuncSetAttribute(count_warp<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
+    cudaFuncSetAttribute(count_warp<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
+    cudaFuncSetAttribute(count_warp<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
+    cudaFuncSetAttribute(count_warp<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
+    cudaFuncSetAttribute(count_warp<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
     if (const char *v = getenv("MD_EV")) { int e = atoi(v); if (e == 1 || e == 2) c->ev = e; }
     cudaStreamSynchronize(L->stream);
     return c;
@@ -978,7 +989,7 @@ extern "C" void md_free_reads(md_ctx *c, md_dev_reads *d) { if (!d) return; cuda
 
 
 // ---- K4 launch (also used to re-run a tile after the host resolved duplicate query names) -------
-static int launch_count(md_ctx *c, Lane *L, const Contig &g, const DevReads &R, const KParams &kp, uint32_t beg, uint32_t end, uint32_t n_win, unsigned long long cap_calls, bool mbias) {
+static int launch_count(md_ctx *c, Lane *L, const Contig &g, const DevReads &R, const KParams &kp, uint32_t beg, uint32_t end, uint32_t n_win, unsigned long long cap_calls, bool mbias, bool wide) {
     if (!n_win) return 0;
     const uint32_t W = c->W;
     cudaStream_t s = L->stream;
@@ -988,7 +999,11 @@ static int launch_count(md_ctx *c, Lane *L, const Contig &g, const DevReads &R, 
     A.calls = (md_call *) L->calls.p; A.cap = cap_calls; A.dir = (uint2 *) L->dir.p; A.counters = (uint32_t *) L->counters.p; A.hist = c->d_hist; A.lens = c->d_lens;
     if (W != 16 * WS_WARPS * 32) { g_err = "internal: window size must be 4096"; return -3; }
     const int mode = mbias ? 2 : (kp.minOppositeDepth > 0 ? 1 : 0);
-    const size_t sm = warp_layout(W, mode).total;
+    // staging sized for 32 alignments of up to 160 bases in the tile's phred encoding (longer reads shrink the batch in the kernel);
+    // 2-bit tiles with packed counters fit three CTAs per SM, everything else two
+    A.st_seq = WS_SEQ_BYTES; A.st_qual = std::min<uint32_t>(WS_QUAL_BYTES, 32u * (((160u * R.qbits + 63u) >> 6) * 8u) + 32u);
+    A.wide = wide ? 1u : 0u;
+    const size_t sm = warp_layout(W, mode, A.wide, A.st_seq, A.st_qual).total;
     if (c->ev == 2) {
         if (mode == 2) count_warp<2, 2><<<n_win, WS_WARPS * 32, sm, s>>>(A);
         else if (mode == 1) count_warp<1, 2><<<n_win, WS_WARPS * 32, sm, s>>>(A);
@@ -1039,13 +1054,9 @@ static int run_pipeline(md_ctx *c, Lane *L, const md_tile_desc *t, const DevRead
         prep_kernel<<<gb, 256, 0, s>>>(R, kp, (int32_t *) L->rend.p, (uint8_t *) L->info.p, T, (int32_t *) L->mate.p, (uint32_t *) L->counters.p, g.d_seq, ce_beg, ce_end);
         c->launches += 1;
     }
-    if (n_win) {
-        window_kernel<<<(n_win + 255) / 256, 256, 0, s>>>(R.pos, n, beg, W, n_win, (const uint32_t *) L->counters.p, (uint2 *) L->win.p);
-        c->launches += 1;
-    }
     CK(cudaEventRecord(L->ev[2], s));
     L->last_tile = *t; L->last_reads = R; L->last_mbias = mbias;
-    int rc = launch_count(c, L, g, R, kp, beg, end, n_win, cap_calls, mbias);
+    int rc = launch_count(c, L, g, R, kp, beg, end, n_win, cap_calls, mbias, /*wide=*/false);
     if (rc) return rc;
     CK(cudaEventRecord(L->ev[3], s));
     CK(cudaGetLastError());
@@ -1094,8 +1105,16 @@ static int resolve_duplicates_on_host(md_ctx *c, Lane *L) {
         while (ev < by_end.size() && by_end[ev].first < pos[i]) { uint32_t x = by_end[ev].second; if (x < i) stored.erase(key[x]); ++ev; }
     }
     CK(cudaMemcpyAsync(L->mate.p, mate.data(), (size_t) n * 4, cudaMemcpyHostToDevice, s));
-    // run the count stage again from a clean output cursor
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// Run the count stage of the lane's last tile again from a clean output cursor (after the host fixed mate[], or with
+// 32-bit window counters after a 16-bit one wrapped).
+static int rerun_count(md_ctx *c, Lane *L, bool wide) {
+    cudaStream_t s = L->stream;
     CK(cudaMemsetAsync((uint32_t *) L->counters.p + C_NCALLS, 0, 8, s));
+    CK(cudaMemsetAsync((uint32_t *) L->counters.p + C_OVERFLOW, 0, 4, s));
     auto it = c->contigs.find(L->last_tile.tid);
     if (it == c->contigs.end()) { g_err = "internal: contig vanished"; return -3; }
     const Contig &g = it->second;
@@ -1103,8 +1122,9 @@ static int resolve_duplicates_on_host(md_ctx *c, Lane *L) {
     if (beg > end) beg = end;
     const uint32_t n_win = (end - beg + c->W - 1) / c->W;
     KParams kp = c->kp;
-    int rc = launch_count(c, L, g, R, kp, beg, end, n_win, (unsigned long long)(end - beg) + 16, false);
+    int rc = launch_count(c, L, g, L->last_reads, kp, beg, end, n_win, (unsigned long long)(end - beg) + 16, false, wide);
     if (rc) return rc;
+    CK(cudaMemcpyAsync(L->h_counters, L->counters.p, C_N * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return 0;
 }
@@ -1112,14 +1132,17 @@ static int resolve_duplicates_on_host(md_ctx *c, Lane *L) {
 static int finish_counters(md_ctx *c, Lane *L, md_tile_stats *st) {
     CK(cudaMemcpyAsync(L->h_counters, L->counters.p, C_N * 4, cudaMemcpyDeviceToHost, L->stream));
     CK(cudaStreamSynchronize(L->stream));
-    if (L->h_counters[C_MULTI] && !L->last_mbias && !L->h_counters[C_OVERFLOW]) {
+    if (L->h_counters[C_MULTI] && !L->last_mbias && L->h_counters[C_OVERFLOW] != 1u && L->h_counters[C_OVERFLOW] != 2u) {
         int rc = resolve_duplicates_on_host(c, L);
+        if (!rc) rc = rerun_count(c, L, false);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(L->h_counters, L->counters.p, C_N * 4, cudaMemcpyDeviceToHost, L->stream));
-        CK(cudaStreamSynchronize(L->stream));
+    }
+    if (L->h_counters[C_OVERFLOW] == 3u && !L->last_mbias) {      // a packed 16-bit window counter wrapped (depth >= 65536): count again, wide
+        int rc = rerun_count(c, L, true);
+        if (rc) return rc;
     }
     unsigned long long ncalls; memcpy(&ncalls, &L->h_counters[C_NCALLS], 8);   // C_NCALLS is 8-byte aligned (index 4)
-    if (L->h_counters[C_OVERFLOW]) { g_err = "internal: call buffer overflow"; return -3; }
+    if (L->h_counters[C_OVERFLOW]) { g_err = L->h_counters[C_OVERFLOW] == 2u ? "internal: staging copy did not complete" : "internal: call buffer overflow"; return -3; }
     L->last_ncalls = ncalls;
     md_tile_stats s; memset(&s, 0, sizeof s);
     s.n_calls = ncalls; s.n_required = ncalls; s.n_admitted = L->h_counters[C_ADMIT]; s.n_pairs = L->h_counters[C_PAIRED]; s.n_multi = L->h_counters[C_MULTI];

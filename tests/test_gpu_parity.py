@@ -229,3 +229,12 @@ def test_tile_abi_reports_encoding(built, synth):
     assert soa.qual_bits == 4 and sorted(soa.qual_lut[:12]) == list(range(2, 14))
     _tile_compare(A.default_config(keepCHG=1), p + ".fa", p + ".bam", 0)
     b.close()
+
+
+def test_cli_ultra_deep_switches_to_wide_counters(built, synth, tmp_path):
+    """> 65535 calls on one column: the packed 16-bit window counters wrap, the tile is counted again with 32-bit ones"""
+    p = synth("ultradeep", "--contigs", "amp:700", "--depth", "260000", "--isize-mean", "170", "--isize-sd", "10", "--isize-min", "150", "--isize-max", "200", "--clean")
+    refp, newp = _both(built, tmp_path, "ud", ["--CHG", "--CHH"], p + ".fa", p + ".bam")
+    assert compare_outputs(refp, newp) == []
+    top = max(int(l.split("\t")[4]) + int(l.split("\t")[5]) for l in open(refp + "_CHH.bedGraph").read().splitlines()[1:])
+    assert top > 70000
