@@ -375,7 +375,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
                 g_stats.t_decode_s += now_s() - t0;
                 if (!got) break;
                 if (tile.n() == 0) { if (!use_async) absorb(tile.end, false); continue; }
-                if (pack_q) tile.pack_quals(*qscratch[rk % ring.size()], *qoffscratch[rk % ring.size()]);
+                if (pack_q) tile.pack_quals(*qscratch[rk % ring.size()], *qoffscratch[rk % ring.size()], [&](size_t n, const std::function<void(size_t)> &fn) { d.bam->parallel_for(n, fn); });
                 md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end, ce_beg, ce_end};
                 uint64_t cap = (uint64_t)(tile.end - tile.beg) + 16;
                 g_stats.n_records += tile.n(); g_stats.n_tiles++;
@@ -537,7 +537,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
                 g_stats.t_decode_s += now_s() - t0;
                 if (!got) break;
                 if (tile.n() == 0) continue;
-                if (pack_quals_enabled()) tile.pack_quals(mb_qscratch, mb_qoffscratch);
+                if (pack_quals_enabled()) tile.pack_quals(mb_qscratch, mb_qoffscratch, [&](size_t n, const std::function<void(size_t)> &fn) { d.bam->parallel_for(n, fn); });
                 md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end, 0, 0}; md_tile_stats st;
                 t0 = now_s();
                 int r = be->mbias_tile(d.dev, &td, &v, &st);

@@ -75,6 +75,13 @@ public:
     }
     const BamHeader &header() const { return hdr_; }
     uint64_t first_record_voffset() const { return start_voff_; }
+    // run fn(0..n-1) on the decode pool and wait (used for tile-level work such as phred packing)
+    void parallel_for(size_t n, const std::function<void(size_t)> &fn) {
+        std::vector<std::future<void>> fs;
+        for (size_t k = 1; k < n; ++k) fs.push_back(pool_.submit([&fn, k] { fn(k); }));
+        if (n) fn(0);
+        for (auto &f : fs) f.get();
+    }
 
     // Restart decoding at a BGZF virtual offset that points at a record start (from a BAI, or first_record_voffset()).
     void seek(uint64_t voff) {

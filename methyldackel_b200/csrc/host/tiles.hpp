@@ -8,6 +8,7 @@
 #include "../../../include/mdgpu.h"
 #include <memory>
 #include <functional>
+#include <array>
 
 namespace mdhost {
 
@@ -116,28 +117,46 @@ struct SoaTile {
         memcpy(qual.grow(q1 - q0), o.qual.data() + q0, (size_t)(q1 - q0) * 8);
     }
     // Re-encode the phred column as 2- or 4-bit codes when the tile's alphabet allows it (lossless; see md_reads_soa).
-    // `scratch` receives the packed words and is swapped in, so a ring of tiles re-uses its allocations.
-    void pack_quals(PodVec<uint64_t> &scratch, PodVec<uint32_t> &scratch_off) {
+    // `scratch` receives the packed words and is swapped in, so a ring of tiles re-uses its allocations.  `par(n, fn)` runs
+    // fn(k) for k in [0,n) — the driver passes its decode pool, so a 2^17-alignment tile is packed in about a millisecond.
+    template <class Par>
+    void pack_quals(PodVec<uint64_t> &scratch, PodVec<uint32_t> &scratch_off, Par &&par) {
         if (qual_bits != 8 || n() == 0) return;
-        bool seen[256] = {false};
-        for (size_t i = 0; i < n(); ++i) { const uint8_t *q = (const uint8_t *)(qual.data() + qual_off[i]); for (uint32_t j = 0, l = l_qseq[i]; j < l; ++j) seen[q[j]] = true; }
+        const size_t N = n(), parts = std::min<size_t>(16, (N + 4095) / 4096);
+        std::vector<std::array<bool, 256>> seen(parts);
+        for (auto &a : seen) a.fill(false);
+        par(parts, [&](size_t k) {
+            const size_t i0 = N * k / parts, i1 = N * (k + 1) / parts;
+            auto &sk = seen[k];
+            for (size_t i = i0; i < i1; ++i) { const uint8_t *q = (const uint8_t *)(qual.data() + qual_off[i]); for (uint32_t j = 0, l = l_qseq[i]; j < l; ++j) sk[q[j]] = true; }
+        });
         uint8_t code[256]; int na = 0;
-        for (int v = 0; v < 256; ++v) if (seen[v]) { if (na < 16) { qual_lut[na] = (uint8_t) v; code[v] = (uint8_t) na; } ++na; }
+        for (int v = 0; v < 256; ++v) { bool any = false; for (auto &a : seen) any = any || a[(size_t) v]; if (any) { if (na < 16) { qual_lut[na] = (uint8_t) v; code[v] = (uint8_t) na; } ++na; } }
         if (na > 16) return;
         const uint32_t bits = na <= 4 ? 2 : 4;
         for (int k = na; k < 16; ++k) qual_lut[k] = 0;
-        scratch.clear(); scratch_off.clear();
-        for (size_t i = 0; i < n(); ++i) {
-            const uint32_t l = l_qseq[i]; const size_t words = ((size_t) l * bits + 63) / 64;
-            scratch_off.push_back((uint32_t) scratch.size());
-            uint64_t *w = scratch.grow(words);
-            const uint8_t *q = (const uint8_t *)(qual.data() + qual_off[i]);
-            for (size_t k = 0; k < words; ++k) w[k] = 0;
-            if (bits == 2) for (uint32_t j = 0; j < l; ++j) w[j >> 5] |= (uint64_t) code[q[j]] << ((j & 31) * 2);
-            else for (uint32_t j = 0; j < l; ++j) w[j >> 4] |= (uint64_t) code[q[j]] << ((j & 15) * 4);
-        }
+        // offsets first (serial, trivial), then the ranges pack independently
+        scratch_off.clear(); scratch.clear();
+        uint32_t *off = scratch_off.grow(N);
+        size_t tot = 0;
+        for (size_t i = 0; i < N; ++i) { off[i] = (uint32_t) tot; tot += ((size_t) l_qseq[i] * bits + 63) / 64; }
+        uint64_t *dst = scratch.grow(tot);
+        par(parts, [&](size_t k) {
+            const size_t i0 = N * k / parts, i1 = N * (k + 1) / parts;
+            for (size_t i = i0; i < i1; ++i) {
+                const uint32_t l = l_qseq[i]; const size_t words = ((size_t) l * bits + 63) / 64;
+                uint64_t *w = dst + off[i];
+                const uint8_t *q = (const uint8_t *)(qual.data() + qual_off[i]);
+                for (size_t x = 0; x < words; ++x) w[x] = 0;
+                if (bits == 2) for (uint32_t j = 0; j < l; ++j) w[j >> 5] |= (uint64_t) code[q[j]] << ((j & 31) * 2);
+                else for (uint32_t j = 0; j < l; ++j) w[j >> 4] |= (uint64_t) code[q[j]] << ((j & 15) * 4);
+            }
+        });
         qual.swap(scratch); qual_off.swap(scratch_off);
         qual_bits = bits;
+    }
+    void pack_quals(PodVec<uint64_t> &scratch, PodVec<uint32_t> &scratch_off) {
+        pack_quals(scratch, scratch_off, [](size_t n, const std::function<void(size_t)> &fn) { for (size_t k = 0; k < n; ++k) fn(k); });
     }
     // Finalise (cigar_off gets its n+1'th entry) and expose as the C-ABI view.
     md_reads_soa view() {
