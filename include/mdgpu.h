@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MDGPU_ABI_VERSION 3
+#define MDGPU_ABI_VERSION 4
 
 /* ---- options that reach the hot path: the subset of `Config`
  *      (MethylDackel.h:90-126) read by filter_func / the per-column loop ---- */
@@ -147,6 +147,9 @@ int md_collect_tile(md_ctx *ctx, int ticket, md_call *calls, uint64_t capacity, 
 
 /* mbias: replaces MBias.c:145-218; accumulates into the context's histogram. */
 int md_mbias_tile(md_ctx *ctx, const md_tile_desc *tile, const md_reads_soa *reads, md_tile_stats *stats);
+/* Asynchronous form: returns a ticket for md_collect_tile() (calls = NULL, capacity = 0); tiles in flight on different
+ * streams add into the same histogram. */
+int md_submit_mbias_tile(md_ctx *ctx, const md_tile_desc *tile, const md_reads_soa *reads);
 /* Copies the accumulated histogram (uint32[4*2*MD_MBIAS_MAXLEN*2]) and the per-strand
  * lengths `l` (MBias.c:212) to the host. */
 int md_mbias_hist(md_ctx *ctx, uint32_t *hist, int32_t lens[4]);

@@ -34,6 +34,7 @@ typedef struct mdh_backend {
     int   (*collect_tile)(void *be, int ticket, md_call *calls, uint64_t cap, md_tile_stats *st);
     void *(*pinned_alloc)(size_t bytes);
     void  (*pinned_free)(void *p);
+    int   (*submit_mbias_tile)(void *be, const md_tile_desc *tile, const md_reads_soa *reads);   /* optional; collected with collect_tile(calls = NULL) */
 } mdh_backend;
 
 /* Same argv conventions as the reference: argv[0] is the sub-command name. */

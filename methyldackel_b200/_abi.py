@@ -86,7 +86,8 @@ class MdhBackend(C.Structure):
     _fields_ = [("factory_user", C.c_void_p), ("create", CREATE_FN), ("destroy", DESTROY_FN), ("load_contig", LOAD_CONTIG_FN),
                 ("drop_contig", DROP_CONTIG_FN), ("extract_tile", EXTRACT_TILE_FN), ("set_mbias_chunks", SET_CHUNKS_FN),
                 ("mbias_tile", MBIAS_TILE_FN), ("mbias_hist", MBIAS_HIST_FN), ("last_error", LAST_ERROR_FN),
-                ("submit_tile", SUBMIT_FN), ("collect_tile", COLLECT_FN), ("pinned_alloc", PIN_ALLOC_FN), ("pinned_free", PIN_FREE_FN)]
+                ("submit_tile", SUBMIT_FN), ("collect_tile", COLLECT_FN), ("pinned_alloc", PIN_ALLOC_FN), ("pinned_free", PIN_FREE_FN),
+                ("submit_mbias_tile", SUBMIT_FN)]
 
 
 _host = None
@@ -138,6 +139,7 @@ def load_gpu():
         g.md_set_mbias_chunks.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint32), C.c_uint32]
         g.md_extract_tile.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa), C.POINTER(MdCall), C.c_uint64, C.POINTER(MdTileStats)]
         g.md_submit_tile.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa)]
+        g.md_submit_mbias_tile.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa)]
         g.md_collect_tile.argtypes = [C.c_void_p, C.c_int, C.POINTER(MdCall), C.c_uint64, C.POINTER(MdTileStats)]
         g.md_mbias_tile.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa), C.POINTER(MdTileStats)]
         g.md_mbias_hist.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]

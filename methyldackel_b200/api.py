@@ -122,7 +122,8 @@ class _GpuBackend:
                       A.LAST_ERROR_FN(last_error),
                       A.SUBMIT_FN(lambda b, td, r: g.md_submit_tile(b, td, r)),
                       A.COLLECT_FN(lambda b, t, c, cap, st: g.md_collect_tile(b, t, c, cap, st)),
-                      A.PIN_ALLOC_FN(lambda n: g.md_alloc_pinned(n)), A.PIN_FREE_FN(lambda q: g.md_free_pinned(q))]
+                      A.PIN_ALLOC_FN(lambda n: g.md_alloc_pinned(n)), A.PIN_FREE_FN(lambda q: g.md_free_pinned(q)),
+                      A.SUBMIT_FN(lambda b, t, r: g.md_submit_mbias_tile(b, t, r))]
         self.be = A.MdhBackend(None, *self._keep)
 
 

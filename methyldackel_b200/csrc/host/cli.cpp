@@ -12,6 +12,8 @@
 #include <climits>
 #include <chrono>
 #include <map>
+#include <future>
+#include <malloc.h>
 #include "tiles.hpp"
 #include "pardecode.hpp"
 #include "format.hpp"
@@ -28,6 +30,9 @@ extern "C" const char *mdh_last_error(void) { return g_err.c_str(); }
 extern "C" void mdh_last_run_stats(mdh_run_stats *out) { if (out) *out = g_stats; }
 
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+// MD_TIMING=1: phase marks on stderr (seconds since the sub-command started)
+static double g_t0 = 0; static bool g_marks = false;
+static void mark(const char *what) { if (g_marks) fprintf(stderr, "[md-timing] %8.3f  %s\n", now_s() - g_t0, what); }
 
 // parseBounds, common.c:11-43: four comma-separated non-negative ints into vals[4*mult..]
 static void parse_bounds(const char *s2, int *vals, int mult) {
@@ -119,11 +124,46 @@ static int decode_threads(int n, bool given) {
 
 static bool pack_quals_enabled() { const char *e = getenv("MD_QUAL_PACK"); return !(e && e[0] == '0'); }
 
+// The decode workers allocate and free multi-megabyte buffers at a high rate; glibc's default turns each of those into an
+// mmap/munmap pair plus a page fault per 4 KB, all serialised on the process's address-space lock (which also slows the CUDA
+// context creation running beside them).  Keep such blocks in the arenas instead.
+static void tune_allocator() {
+    static bool done = false; if (done) return; done = true;
+    mallopt(M_MMAP_THRESHOLD, 32 << 20); mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_TOP_PAD, 16 << 20);
+}
+
 namespace {
+// The text formatter runs on its own thread, chunk after chunk in genome order (the analogue of the reference's ordered
+// output bins, extract.c:514-535), so the caller's thread is free to keep tiles moving.  A bounded queue applies back-pressure.
+class SerialWorker {
+public:
+    SerialWorker() : th_([this] { run(); }) {}
+    ~SerialWorker() { { std::lock_guard<std::mutex> g(m_); stop_ = true; } cv_.notify_all(); th_.join(); }
+    void post(std::function<void()> fn) {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return q_.size() < 16; });
+        q_.push_back(std::move(fn)); cv_.notify_all();
+    }
+    void drain() { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return q_.empty() && !busy_; }); }
+    double busy_seconds() { std::lock_guard<std::mutex> g(m_); return busy_s_; }
+private:
+    void run() {
+        for (;;) {
+            std::function<void()> fn;
+            { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return stop_ || !q_.empty(); }); if (q_.empty()) return; fn = std::move(q_.front()); q_.pop_front(); busy_ = true; cv_.notify_all(); }
+            double t0 = now_s();
+            fn();
+            { std::lock_guard<std::mutex> g(m_); busy_ = false; busy_s_ += now_s() - t0; cv_.notify_all(); }
+        }
+    }
+    std::deque<std::function<void()>> q_; std::mutex m_; std::condition_variable cv_; bool stop_ = false, busy_ = false; double busy_s_ = 0;
+    std::thread th_;
+};
+
 struct Driver {
     const mdh_backend *be; void *dev = nullptr;
     std::unique_ptr<ParallelBam> bam; std::unique_ptr<Fasta> fa; BaiIndex bai; bool have_bai = false;
-    std::unique_ptr<Fragment> frag; size_t frag_i = 0;      // decode cursor shared by consecutive FragTilers
+    std::shared_ptr<Fragment> frag; size_t frag_i = 0;      // decode cursor shared by consecutive FragTilers
     const BamHeader *hdr = nullptr;
     std::string cur_seq; int cur_seq_tid = -1; bool cur_seq_ok = false;
     const std::string *fetch(uint32_t tid) {
@@ -133,10 +173,13 @@ struct Driver {
         }
         return cur_seq_ok ? &cur_seq : nullptr;
     }
+    bool sought = false;
     void seek_to(int tid, uint32_t beg) {
-        if (!have_bai) return;           // sequential scan: the stream only moves forward and skips earlier contigs
+        // One index jump to where this run starts; after that contigs and regions are visited in file order, so the decode
+        // stream simply continues (its read-ahead into the next contig is kept) and the tilers skip what lies between.
+        if (!have_bai || sought) return;           // no index: sequential scan, the stream only moves forward and skips earlier contigs
         bool found; uint64_t off = bai.start_offset(tid, beg, found);
-        if (found && off) { bam->seek(off); frag.reset(); frag_i = 0; }
+        if (found && off) { bam->seek(off); frag.reset(); frag_i = 0; sought = true; }
     }
 };
 }  // namespace
@@ -146,7 +189,8 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     char *opref = nullptr; const char *reg = nullptr, *bedName = nullptr, *bwName = nullptr, *bbmName = nullptr;
     int c, nThreads = 1, keepStrand = 0; double minConvEff = 0.0; bool threads_given = false;
     (void) keepStrand;
-    double t_start = now_s();
+    double t_start = now_s(); g_t0 = t_start; g_marks = getenv("MD_TIMING") != nullptr;
+    tune_allocator();
     memset(&g_stats, 0, sizeof g_stats);
 
     static struct option lopts[] = {
@@ -228,7 +272,8 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     catch (std::exception &e) { fprintf(stderr, "Couldn't open the index for %s!\n", fastaName); return -4; }
     // the device context takes a noticeable fraction of a second to come up: create it while the host opens files,
     // loads the first contig and starts decoding
-    std::future<void *> dev_future = std::async(std::launch::async, [be, &o] { return be->create(be->factory_user, &o.core); });
+    mark("files open");
+    std::future<void *> dev_future = std::async(std::launch::async, [be, &o] { void *p = be->create(be->factory_user, &o.core); mark("device context ready"); return p; });
     struct DevJoin { std::future<void *> &f; const mdh_backend *be; bool taken = false; ~DevJoin() { if (!taken && f.valid()) { void *p = f.get(); if (p) be->destroy(p); } } } dev_join{dev_future, be};
 
     // output files, extract.c:1344-1439
@@ -272,6 +317,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
 
     for (int k = 0; k < 3; ++k) if (fp[k] && (k == 0 || fp[k] != fp[0])) setvbuf(fp[k], nullptr, _IOFBF, 4 << 20);
     ExtractWriter writer(o, fp);
+    SerialWorker out_thread;
     int rc = 0;
     {
         // the reference's chunk list (extract.c:325-350), enumerated up front; a shard takes a contiguous,
@@ -306,7 +352,9 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         SoaTile carry;
         std::vector<md_call> calls; size_t calls_head = 0;
         std::vector<md_call> tile_calls;
+        mark("tile ring reserved");
         d.dev = dev_future.get(); dev_join.taken = true;
+        mark("device joined");
         if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
         size_t ci = c0;
         while (ci < c1 && rc == 0) {
@@ -323,6 +371,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             uint32_t rbeg = chunks.front().beg, rend = chunks.back().end;
             if (rend > ref->size()) rend = (uint32_t) ref->size();
             if (be->load_contig(d.dev, (int32_t) tid, ref->data(), (uint32_t) ref->size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+            mark("contig loaded");
             d.seek_to((int) tid, rbeg);
             calls.clear(); calls_head = 0; carry.clear();
             size_t next_chunk = 0;
@@ -334,16 +383,16 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             if (per_chunk) regions = chunks; else regions.push_back(Chunk{tid, rbeg, rend});
             // completed tiles arrive in order; hand every finished reference chunk to the writer
             auto absorb = [&](uint32_t done_upto, bool last) {
-                double t0 = now_s();
                 while (next_chunk < chunks.size() && (chunks[next_chunk].end <= done_upto || last)) {
-                    const Chunk &k = chunks[next_chunk];
+                    const Chunk k = chunks[next_chunk];
                     size_t a = calls_head; while (a < calls.size() && calls[a].pos < k.beg) ++a;
                     size_t b = a; while (b < calls.size() && calls[b].pos < k.end) ++b;
-                    writer.process_chunk(d.hdr->names[tid].c_str(), *ref, k.beg, k.end, calls.data() + a, b - a);
+                    auto part = std::make_shared<std::vector<md_call>>(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b);
+                    const char *cname = d.hdr->names[tid].c_str();
+                    out_thread.post([&writer, cname, ref, k, part] { writer.process_chunk(cname, *ref, k.beg, k.end, part->data(), part->size()); });
                     calls_head = b; ++next_chunk;
                 }
                 if (calls_head > (1u << 20)) { calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
-                g_stats.t_format_s += now_s() - t0;
             };
             struct Flight { int ticket; int slot; uint32_t end; uint64_t cap; };
             std::vector<Flight> flight;
@@ -399,12 +448,18 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
                 }
             }
             }   // regions
+            mark("last tile submitted");
             while (rc == 0 && !flight.empty()) rc = collect_one();
             if (rc == 0) absorb(rend, true);
+            out_thread.drain();                                     // the next contig replaces *ref
+            mark("contig written");
             be->drop_contig(d.dev, (int32_t) tid);
         }
     }
+    out_thread.drain();
+    g_stats.t_format_s = out_thread.busy_seconds();
     be->destroy(d.dev);
+    mark("device destroyed");
     g_stats.n_variant_positions = writer.n_variant_positions();
     if (writer.n_variant_positions() && shardWorld == 1) printf("%" PRIu64 " positions were excluded due to likely being variants.\n", writer.n_variant_positions());
     if (o.cytosine_report) { if (fp[0]) fclose(fp[0]); }
@@ -420,7 +475,8 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
     unsigned long chunkSize = 1000000;
     const char *reg = nullptr, *bedName = nullptr; char *opref = nullptr;
     int c, SVG = 1, txt = 0, nThreads = 1; double minConvEff = 0.0; bool threads_given = false;
-    double t_start = now_s();
+    double t_start = now_s(); g_t0 = t_start; g_marks = getenv("MD_TIMING") != nullptr;
+    tune_allocator();
     memset(&g_stats, 0, sizeof g_stats);
     static struct option lopts[] = {
         {"noCpG", 0, NULL, 1}, {"CHG", 0, NULL, 2}, {"CHH", 0, NULL, 3}, {"keepDupes", 0, NULL, 4}, {"keepSingleton", 0, NULL, 5}, {"keepDiscordant", 0, NULL, 6},
@@ -492,8 +548,9 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
         if (e > 0) gEnd = (uint32_t) e;
         if (gEnd > d.hdr->lens[gTid]) gEnd = d.hdr->lens[gTid];
     }
-    d.dev = be->create(be->factory_user, &cfg);
-    if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+    // as in extract: the device context comes up while the host opens files and starts decoding
+    std::future<void *> dev_future = std::async(std::launch::async, [be, &cfg] { void *p = be->create(be->factory_user, &cfg); mark("device context ready"); return p; });
+    struct DevJoin { std::future<void *> &f; const mdh_backend *be; bool taken = false; ~DevJoin() { if (!taken && f.valid()) { void *p = f.get(); if (p) be->destroy(p); } } } dev_join{dev_future, be};
     int rc = 0;
     {
         std::vector<Chunk> all;
@@ -511,8 +568,30 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
             for (size_t k = 0; k < all.size(); ++k) { if (acc >= lo && c0 == all.size()) c0 = k; if (acc >= hi) { c1 = k; break; } acc += all[k].end - all[k].beg; }
             if (c0 > c1) c0 = c1;
         }
-        SoaTile tile, carry;
-        PodVec<uint64_t> mb_qscratch; PodVec<uint32_t> mb_qoffscratch;
+        // tile ring as in extract: page-locked tiles, up to three in flight when the back end is asynchronous
+        const bool use_async = be->submit_mbias_tile && be->collect_tile;
+        TileAlloc pin; if (use_async && be->pinned_alloc && be->pinned_free) { pin.alloc = be->pinned_alloc; pin.release = be->pinned_free; }
+        std::vector<std::unique_ptr<SoaTile>> ring;
+        for (int k = 0; k < (use_async ? 3 : 1); ++k) ring.emplace_back(new SoaTile(use_async ? &pin : nullptr));
+        const size_t tile_reads = use_async ? ((size_t) 1 << 17) : ((size_t) 1 << 19);
+        if (use_async) for (auto &t : ring) t->reserve_for(tile_reads + tile_reads / 8, 160);
+        std::vector<std::unique_ptr<PodVec<uint64_t>>> qscratch; std::vector<std::unique_ptr<PodVec<uint32_t>>> qoffscratch;
+        for (size_t k = 0; k < ring.size(); ++k) { qscratch.emplace_back(new PodVec<uint64_t>(use_async ? &pin : nullptr)); qoffscratch.emplace_back(new PodVec<uint32_t>(use_async ? &pin : nullptr)); }
+        SoaTile carry;
+        mark("tile ring reserved");
+        d.dev = dev_future.get(); dev_join.taken = true;
+        if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+        std::vector<int> flight;
+        auto collect_one = [&]() -> int {
+            int ticket = flight.front(); flight.erase(flight.begin());
+            md_tile_stats st;
+            double t0 = now_s();
+            int r = be->collect_tile(d.dev, ticket, nullptr, 0, &st);
+            g_stats.t_device_s += now_s() - t0;
+            if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+            return 0;
+        };
+        size_t rk = 0;
         size_t ci = c0;
         while (ci < c1 && rc == 0) {
             uint32_t tid = all[ci].tid;
@@ -529,22 +608,33 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
             if (be->load_contig(d.dev, (int32_t) tid, ref->data(), (uint32_t) ref->size()) != 0 ||
                 be->set_mbias_chunks(d.dev, (int32_t) tid, bounds.data(), (uint32_t) bounds.size() - 1) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
             d.seek_to((int) tid, rbeg);
-            FragTiler tiler(*d.bam, d.frag, d.frag_i, (int) tid, rbeg, rend, (size_t) 1 << 19);
+            FragTiler tiler(*d.bam, d.frag, d.frag_i, (int) tid, rbeg, rend, tile_reads);
             carry.clear();
             for (;;) {
+                SoaTile &tile = *ring[rk % ring.size()];
+                if (use_async) while (flight.size() >= ring.size() && rc == 0) rc = collect_one();
+                if (rc) break;
                 double t0 = now_s();
                 bool got = tiler.next(tile, carry);
                 g_stats.t_decode_s += now_s() - t0;
                 if (!got) break;
                 if (tile.n() == 0) continue;
-                if (pack_quals_enabled()) tile.pack_quals(mb_qscratch, mb_qoffscratch, [&](size_t n, const std::function<void(size_t)> &fn) { d.bam->parallel_for(n, fn); });
+                if (pack_quals_enabled()) tile.pack_quals(*qscratch[rk % ring.size()], *qoffscratch[rk % ring.size()], [&](size_t n, const std::function<void(size_t)> &fn) { d.bam->parallel_for(n, fn); });
                 md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end, 0, 0}; md_tile_stats st;
-                t0 = now_s();
-                int r = be->mbias_tile(d.dev, &td, &v, &st);
-                g_stats.t_device_s += now_s() - t0;
-                if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
                 g_stats.n_records += tile.n(); g_stats.n_tiles++;
+                t0 = now_s();
+                if (use_async) {
+                    int ticket = be->submit_mbias_tile(d.dev, &td, &v);
+                    g_stats.t_device_s += now_s() - t0;
+                    if (ticket < 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+                    flight.push_back(ticket); ++rk;
+                } else {
+                    int r = be->mbias_tile(d.dev, &td, &v, &st);
+                    g_stats.t_device_s += now_s() - t0;
+                    if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+                }
             }
+            while (rc == 0 && !flight.empty()) rc = collect_one();       // the contig (and its chunk table) is dropped next
             be->drop_contig(d.dev, (int32_t) tid);
         }
     }

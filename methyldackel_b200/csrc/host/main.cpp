@@ -17,6 +17,7 @@ static int be_mbias(void *b, const md_tile_desc *t, const md_reads_soa *r, md_ti
 static int be_hist(void *b, uint32_t *h, int32_t l[4]) { return md_mbias_hist((md_ctx *) b, h, l); }
 static int be_submit(void *b, const md_tile_desc *t, const md_reads_soa *r) { return md_submit_tile((md_ctx *) b, t, r); }
 static int be_collect(void *b, int ticket, md_call *c, uint64_t cap, md_tile_stats *st) { return md_collect_tile((md_ctx *) b, ticket, c, cap, st); }
+static int be_submit_mbias(void *b, const md_tile_desc *t, const md_reads_soa *r) { return md_submit_mbias_tile((md_ctx *) b, t, r); }
 
 static void usage_main() {
     fprintf(stderr, "MethylDackel (B200 build of the extract/mbias hot path): A tool for processing bisulfite sequencing alignments.\n"
@@ -27,7 +28,7 @@ static void usage_main() {
 }
 
 int main(int argc, char *argv[]) {
-    mdh_backend be = {nullptr, be_create, be_destroy, be_load, be_drop, be_extract, be_chunks, be_mbias, be_hist, md_last_error, be_submit, be_collect, md_alloc_pinned, md_free_pinned};
+    mdh_backend be = {nullptr, be_create, be_destroy, be_load, be_drop, be_extract, be_chunks, be_mbias, be_hist, md_last_error, be_submit, be_collect, md_alloc_pinned, md_free_pinned, be_submit_mbias};
     if (argc == 1) { usage_main(); return 0; }
     if (!strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) { usage_main(); return 0; }
     if (!strcmp(argv[1], "-v") || !strcmp(argv[1], "--version")) { printf("0.6.1-b200 (B200 build; no HTSlib)\n"); return 0; }
@@ -37,8 +38,8 @@ int main(int argc, char *argv[]) {
         if (getenv("MD_TIMING")) {      // where the wall clock went (stderr), for tuning
             mdh_run_stats st; mdh_last_run_stats(&st);
             double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            fprintf(stderr, "[md-timing] wall %.3f s: setup %.3f, decode-wait %.3f, device-wait %.3f, format %.3f; %llu alignments in %llu tiles, %llu calls\n",
-                    wall, st.t_total_s - st.t_decode_s - st.t_device_s - st.t_format_s, st.t_decode_s, st.t_device_s, st.t_format_s,
+            fprintf(stderr, "[md-timing] wall %.3f s: tiler (decode wait + assembly) %.3f, device calls %.3f, other %.3f on the calling thread; writer thread busy %.3f; %llu alignments in %llu tiles, %llu calls\n",
+                    wall, st.t_decode_s, st.t_device_s, st.t_total_s - st.t_decode_s - st.t_device_s, st.t_format_s,
                     (unsigned long long) st.n_records, (unsigned long long) st.n_tiles, (unsigned long long) st.n_calls);
         }
         return rc;

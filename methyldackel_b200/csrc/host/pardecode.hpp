@@ -18,6 +18,10 @@
 #include <deque>
 #include <future>
 #include <atomic>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 
 namespace mdhost {
 
@@ -32,12 +36,10 @@ public:
         cv_.notify_all();
         for (auto &t : th_) t.join();
     }
-    std::future<void> submit(std::function<void()> fn) {
-        auto task = std::make_shared<std::packaged_task<void()>>(std::move(fn));
-        std::future<void> f = task->get_future();
-        { std::lock_guard<std::mutex> g(m_); q_.emplace_back([task] { (*task)(); }); }
+    // fire-and-forget; `urgent` tasks overtake the queued decode work (tile-level helpers the caller waits on)
+    void post(std::function<void()> fn, bool urgent = false) {
+        { std::lock_guard<std::mutex> g(m_); if (urgent) q_.emplace_front(std::move(fn)); else q_.emplace_back(std::move(fn)); }
         cv_.notify_one();
-        return f;
     }
     int size() const { return (int) th_.size(); }
 private:
@@ -57,80 +59,89 @@ struct Fragment {
     std::vector<int32_t> tid;
 };
 
+// The compressed file is mapped, not read: jobs point into the mapping, so the only bytes the caller's thread touches are
+// the 18-byte block headers.  Inflate -> stitch -> parse advance by continuation on the pool (the worker that completes the
+// inflate of the oldest unstitched job walks the record-length chain for it and every inflated successor, then queues
+// their parses), so decoding runs ahead of the consumer — in particular while the CUDA context is still coming up.
 class ParallelBam {
 public:
-    ParallelBam(const std::string &path, int nthreads) : pool_(nthreads) {
+    ParallelBam(const std::string &path, int nthreads) : pool_(nthreads), aux_(std::max(1, std::min(16, nthreads))) {
         // header through the sequential reader; remember where the records start
         BgzfReader rd(path);
         hdr_ = read_bam_header(rd);
         start_voff_ = rd.tell();
-        fp_ = fopen(path.c_str(), "rb");
-        if (!fp_) throw std::runtime_error("Couldn't open " + path + " for reading!");
-        setvbuf(fp_, nullptr, _IOFBF, 8 << 20);
+        fd_ = ::open(path.c_str(), O_RDONLY);
+        if (fd_ < 0) throw std::runtime_error("Couldn't open " + path + " for reading!");
+        struct stat st;
+        if (fstat(fd_, &st) != 0 || st.st_size <= 0) { ::close(fd_); throw std::runtime_error("Couldn't stat " + path); }
+        size_ = (size_t) st.st_size;
+        void *m = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+        if (m == MAP_FAILED) { ::close(fd_); throw std::runtime_error("Couldn't map " + path); }
+        map_ = (const uint8_t *) m;
+        madvise((void *) map_, size_, MADV_SEQUENTIAL);
         seek(start_voff_);
     }
     ~ParallelBam() {
-        for (auto &j : jobs_) { if (j->f_inflate.valid()) j->f_inflate.wait(); if (j->f_parse.valid()) j->f_parse.wait(); }
-        if (fp_) fclose(fp_);
+        quiesce();
+        if (map_) munmap((void *) map_, size_);
+        if (fd_ >= 0) ::close(fd_);
     }
     const BamHeader &header() const { return hdr_; }
     uint64_t first_record_voffset() const { return start_voff_; }
-    // run fn(0..n-1) on the decode pool and wait (used for tile-level work such as phred packing)
+    // run fn(0..n-1) and wait (tile-level work the caller is blocked on: column copies, phred packing).  These go to a small
+    // pool of their own: the decode pool's workers sit in ~10 ms inflate/parse jobs, which would be the latency of every call.
     void parallel_for(size_t n, const std::function<void(size_t)> &fn) {
-        std::vector<std::future<void>> fs;
-        for (size_t k = 1; k < n; ++k) fs.push_back(pool_.submit([&fn, k] { fn(k); }));
-        if (n) fn(0);
-        for (auto &f : fs) f.get();
+        if (n <= 1) { if (n) fn(0); return; }
+        std::mutex m; std::condition_variable cv; size_t left = n - 1;
+        for (size_t k = 1; k < n; ++k) aux_.post([&, k] { fn(k); std::lock_guard<std::mutex> g(m); if (--left == 0) cv.notify_one(); });
+        fn(0);
+        std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return left == 0; });
     }
 
     // Restart decoding at a BGZF virtual offset that points at a record start (from a BAI, or first_record_voffset()).
     void seek(uint64_t voff) {
-        for (auto &j : jobs_) { if (j->f_inflate.valid()) j->f_inflate.wait(); if (j->f_parse.valid()) j->f_parse.wait(); }
-        jobs_.clear(); pending_.clear();
-        file_off_ = (int64_t)(voff >> 16); skip_ = (size_t)(voff & 0xffff); eof_ = false; file_eof_ = false; rolling_.clear(); rpos_ = 0; rolling_base_ = file_off_;
-        if (fseeko(fp_, file_off_, SEEK_SET) != 0) throw std::runtime_error("seek failed");
+        quiesce();
+        std::lock_guard<std::mutex> g(m_);
+        jobs_.clear(); pending_.clear(); stitch_next_ = 0; cancel_ = false;
+        file_off_ = (size_t)(voff >> 16); skip_ = (size_t)(voff & 0xffff); eof_ = false;
+        if (file_off_ > size_) throw std::runtime_error("seek failed");
+        top_up_locked();
     }
 
     // Next fragment in file order; nullptr at end of file.
     std::unique_ptr<Fragment> next() {
+        std::unique_lock<std::mutex> l(m_);
         for (;;) {
-            top_up();
+            top_up_locked();
             if (jobs_.empty()) return nullptr;
-            // stitch + launch the parse of every inflated job, in order
-            for (auto &j : jobs_) {
-                if (j->stitched) continue;
-                if (j->f_inflate.wait_for(std::chrono::seconds(0)) != std::future_status::ready && &j != &jobs_.front()) break;
-                j->f_inflate.get();
-                stitch(*j);
-                Job *jp = j.get();
-                j->f_parse = pool_.submit([jp] { jp->parse(); });
-            }
             Job &head = *jobs_.front();
-            if (!head.stitched) continue;
-            head.f_parse.get();
+            cv_.wait(l, [&] { return head.state == PARSED || head.state == FAILED; });
+            if (head.state == FAILED) throw std::runtime_error(head.err);
             std::unique_ptr<Fragment> out = std::move(head.frag);
-            jobs_.pop_front();
+            jobs_.pop_front(); if (stitch_next_) --stitch_next_;
             if (out->soa.n() == 0 && !(jobs_.empty() && eof_)) continue;   // a job that only completed a straddling record elsewhere
+            top_up_locked();
             return out;
         }
     }
 
 private:
+    enum State { QUEUED = 0, INFLATED, STITCHED, PARSED, FAILED };
     struct Job {
-        std::vector<uint8_t> comp; std::vector<std::pair<uint32_t, uint32_t>> blocks;   // (offset in comp, total block size)
+        const uint8_t *base = nullptr; std::vector<std::pair<uint32_t, uint32_t>> blocks;   // (offset from base, total block size)
         std::vector<uint8_t> ubuf; std::vector<uint8_t> head_rec;                         // head_rec: a record completed from the previous job's tail
         std::vector<uint32_t> rec_off;                                                     // starts of whole records in ubuf (pointing at the length prefix)
-        std::future<void> f_inflate, f_parse; bool stitched = false;
+        State state = QUEUED; std::string err;
         std::unique_ptr<Fragment> frag;
         void inflate_all() {
             // sizes first (ISIZE trailer), then inflate block by block into place
             size_t tot = 0; std::vector<size_t> uoff(blocks.size());
-            for (size_t b = 0; b < blocks.size(); ++b) { const uint8_t *p = comp.data() + blocks[b].first; uint32_t bs = blocks[b].second; uoff[b] = tot; tot += le32(p + bs - 4); }
+            for (size_t b = 0; b < blocks.size(); ++b) { const uint8_t *p = base + blocks[b].first; uint32_t bs = blocks[b].second; uoff[b] = tot; tot += le32(p + bs - 4); }
             ubuf.resize(tot);
             z_stream zs; memset(&zs, 0, sizeof zs);
             if (inflateInit2(&zs, -15) != Z_OK) throw std::runtime_error("inflateInit2");
             for (size_t b = 0; b < blocks.size(); ++b) {
-                const uint8_t *p = comp.data() + blocks[b].first; uint32_t bs = blocks[b].second;
+                const uint8_t *p = base + blocks[b].first; uint32_t bs = blocks[b].second;
                 int xlen = p[10] | (p[11] << 8);
                 uint32_t isize = le32(p + bs - 4);
                 if (isize == 0) continue;
@@ -140,11 +151,12 @@ private:
                 if (inflate(&zs, Z_FINISH) != Z_STREAM_END || zs.total_out != isize) { inflateEnd(&zs); throw std::runtime_error("BGZF inflate failed"); }
             }
             inflateEnd(&zs);
-            std::vector<uint8_t>().swap(comp);
         }
         void parse() {
             frag.reset(new Fragment());
             BamRec r;
+            const size_t nrec = rec_off.size() + (head_rec.empty() ? 0 : 1);
+            frag->tid.reserve(nrec);
             auto add = [&](const uint8_t *p) {
                 uint32_t bs = le32(p);
                 if (!parse_bam_record(p + 4, bs, r)) throw std::runtime_error("malformed BAM record");
@@ -156,53 +168,74 @@ private:
         }
     };
 
-    // read compressed bytes and cut jobs at block boundaries
-    void top_up() {
+    // wait until no pool task of this reader is running or queued
+    void quiesce() {
+        std::unique_lock<std::mutex> l(m_);
+        cancel_ = true;
+        cv_.wait(l, [&] { return tasks_ == 0; });
+    }
+    // cut jobs of whole BGZF blocks from the mapping (header scan only) and queue their inflates; m_ held
+    void top_up_locked() {
         const size_t want_jobs = (size_t) pool_.size() * 3 + 2;
+        static const size_t target = [] { const char *e = getenv("MD_DECODE_JOB_BYTES"); size_t v = e ? (size_t) atol(e) : 0; return v ? v : (size_t) 1 << 20; }();   // ~1 MB of compressed blocks per job
         while (!eof_ && jobs_.size() < want_jobs) {
-            std::unique_ptr<Job> j(new Job());
-            static const size_t target = [] { const char *e = getenv("MD_DECODE_JOB_BYTES"); size_t v = e ? (size_t) atol(e) : 0; return v ? v : (size_t) 1 << 20; }();   // ~1 MB of compressed blocks per job
+            std::shared_ptr<Job> j(new Job());
+            j->base = map_ + file_off_;
             size_t used = 0;
-            for (;;) {
-                // make sure a whole block header + block is in the rolling buffer
-                if (rolling_.size() - rpos_ < 18) { if (!fill()) break; if (rolling_.size() - rpos_ < 18) break; }
-                const uint8_t *p = rolling_.data() + rpos_;
+            while (file_off_ + used + 18 <= size_) {
+                const uint8_t *p = map_ + file_off_ + used;
                 if (p[0] != 31 || p[1] != 139 || !(p[3] & 4)) throw std::runtime_error("not a BGZF block");
                 int xlen = p[10] | (p[11] << 8), bsize = -1;
-                if (rolling_.size() - rpos_ < (size_t) 12 + xlen) { if (!fill()) throw std::runtime_error("truncated BGZF header"); continue; }
+                if (file_off_ + used + 12 + (size_t) xlen > size_) throw std::runtime_error("truncated BGZF header");
                 for (int off = 0; off + 4 <= xlen;) { int slen = p[12 + off + 2] | (p[12 + off + 3] << 8); if (p[12 + off] == 'B' && p[12 + off + 1] == 'C' && slen == 2) bsize = p[12 + off + 4] | (p[12 + off + 5] << 8); off += 4 + slen; }
                 if (bsize < 0) throw std::runtime_error("BGZF block without BC field");
                 const size_t bs = (size_t) bsize + 1;
-                if (rolling_.size() - rpos_ < bs) { if (!fill()) throw std::runtime_error("truncated BGZF block"); continue; }
-                j->blocks.emplace_back((uint32_t) j->comp.size(), (uint32_t) bs);
-                j->comp.insert(j->comp.end(), rolling_.begin() + (ptrdiff_t) rpos_, rolling_.begin() + (ptrdiff_t)(rpos_ + bs));
-                rpos_ += bs; used += bs;
+                if (file_off_ + used + bs > size_) throw std::runtime_error("truncated BGZF block");
+                j->blocks.emplace_back((uint32_t) used, (uint32_t) bs);
+                used += bs;
                 if (used >= target) break;
             }
             if (j->blocks.empty()) { eof_ = true; break; }
-            Job *jp = j.get();
-            j->f_inflate = pool_.submit([jp] { jp->inflate_all(); });
-            jobs_.push_back(std::move(j));
+            file_off_ += used;
+            jobs_.push_back(j);
+            ++tasks_;
+            pool_.post([this, j] { run_inflate(j); });
         }
     }
-    bool fill() {
-        if (file_eof_) return false;
-        if (rpos_ > 0) { rolling_.erase(rolling_.begin(), rolling_.begin() + (ptrdiff_t) rpos_); rpos_ = 0; }
-        size_t old = rolling_.size();
-        rolling_.resize(old + (4 << 20));
-        size_t got = fread(rolling_.data() + old, 1, 4 << 20, fp_);
-        rolling_.resize(old + got);
-        if (got == 0) file_eof_ = true;
-        return got > 0;
+    void run_inflate(const std::shared_ptr<Job> &j) {
+        bool ok = true; std::string err;
+        if (!cancel_) { try { j->inflate_all(); } catch (std::exception &e) { ok = false; err = e.what(); } }
+        std::lock_guard<std::mutex> g(m_);
+        if (cancel_) { --tasks_; cv_.notify_all(); return; }
+        if (!ok) { j->state = FAILED; j->err = err; } else j->state = INFLATED;
+        // advance the stitch chain as far as the inflated prefix reaches
+        while (stitch_next_ < jobs_.size()) {
+            std::shared_ptr<Job> k = jobs_[stitch_next_];
+            if (k->state == FAILED) break;
+            if (k->state != INFLATED) break;
+            try { stitch(*k); } catch (std::exception &e) { k->state = FAILED; k->err = e.what(); break; }
+            k->state = STITCHED; ++stitch_next_;
+            ++tasks_;
+            pool_.post([this, k] { run_parse(k); });
+        }
+        --tasks_; cv_.notify_all();
     }
-    // record boundaries of one job; completes the previous job's straddling record
+    void run_parse(const std::shared_ptr<Job> &j) {
+        bool ok = true; std::string err;
+        if (!cancel_) { try { j->parse(); } catch (std::exception &e) { ok = false; err = e.what(); } }
+        std::lock_guard<std::mutex> g(m_);
+        if (!cancel_) { if (ok) j->state = PARSED; else { j->state = FAILED; j->err = err; } }
+        --tasks_; cv_.notify_all();
+    }
+    // record boundaries of one job; completes the previous job's straddling record; m_ held
     void stitch(Job &j) {
         size_t off = skip_; skip_ = 0;
         const size_t U = j.ubuf.size();
+        if (off > U) throw std::runtime_error("BGZF seek past block end");
         if (!pending_.empty()) {
             // pending_ holds the first bytes of a record that began in an earlier job
             size_t have = pending_.size();
-            if (have < 4) { size_t take = std::min(4 - have, U - std::min(off, U)); pending_.insert(pending_.end(), j.ubuf.begin() + (ptrdiff_t) off, j.ubuf.begin() + (ptrdiff_t)(off + take)); off += take; have = pending_.size(); }
+            if (have < 4) { size_t take = std::min(4 - have, U - off); pending_.insert(pending_.end(), j.ubuf.begin() + (ptrdiff_t) off, j.ubuf.begin() + (ptrdiff_t)(off + take)); off += take; have = pending_.size(); }
             if (have >= 4) {
                 size_t need = 4 + (size_t) le32(pending_.data()) - have;
                 size_t take = std::min(need, U - off);
@@ -211,30 +244,35 @@ private:
             }
         }
         if (pending_.empty()) {
+            const uint8_t *u = j.ubuf.data();
+            size_t nest = 0;
+            if (U > off + 4) { size_t l0 = 4 + (size_t) le32(u + off); nest = l0 ? (U - off) / l0 + 16 : 0; }
+            j.rec_off.reserve(std::min<size_t>(nest, (size_t) 1 << 22));
             while (off + 4 <= U) {
-                size_t len = 4 + (size_t) le32(j.ubuf.data() + off);
+                size_t len = 4 + (size_t) le32(u + off);
                 if (off + len > U) break;
                 j.rec_off.push_back((uint32_t) off); off += len;
             }
             if (off < U) pending_.assign(j.ubuf.begin() + (ptrdiff_t) off, j.ubuf.end());
         }
-        j.stitched = true;
     }
 
-    ThreadPool pool_;
+    ThreadPool pool_, aux_;
     BamHeader hdr_;
-    FILE *fp_ = nullptr;
+    int fd_ = -1; const uint8_t *map_ = nullptr; size_t size_ = 0;
     uint64_t start_voff_ = 0;
-    int64_t file_off_ = 0, rolling_base_ = 0; size_t skip_ = 0; bool eof_ = false, file_eof_ = false;
-    std::vector<uint8_t> rolling_; size_t rpos_ = 0;
+    std::mutex m_; std::condition_variable cv_;
+    size_t file_off_ = 0, skip_ = 0; bool eof_ = false; std::atomic<bool> cancel_{false};
+    size_t tasks_ = 0, stitch_next_ = 0;
     std::vector<uint8_t> pending_;
-    std::deque<std::unique_ptr<Job>> jobs_;
+    std::deque<std::shared_ptr<Job>> jobs_;
 };
 
-// Same contract as Tiler (tiles.hpp), fed by fragments.
+// Same contract as Tiler (tiles.hpp), fed by fragments.  The caller's thread only scans positions to decide which runs of
+// records belong to the tile; the column copies of those runs are done on the decode pool.
 class FragTiler {
 public:
-    FragTiler(ParallelBam &pb, std::unique_ptr<Fragment> &cur, size_t &cur_i, int tid, uint32_t reg_beg, uint32_t reg_end, size_t target_reads)
+    FragTiler(ParallelBam &pb, std::shared_ptr<Fragment> &cur, size_t &cur_i, int tid, uint32_t reg_beg, uint32_t reg_end, size_t target_reads)
         : pb_(pb), cur_(cur), i_(cur_i), tid_(tid), reg_beg_(reg_beg), reg_end_(reg_end), target_(target_reads), cur_beg_(reg_beg) {}
     bool next(SoaTile &t, SoaTile &carry) {
         if (done_) return false;
@@ -243,16 +281,19 @@ public:
         carry.clear();
         uint32_t cut = reg_end_;
         bool stream_end = false;
+        struct Run { std::shared_ptr<Fragment> f; size_t a, b; SoaTile::Extent at; };
+        std::vector<Run> plan; size_t have = t.n();
+        SoaTile::Extent total;
         for (;;) {
             if (!cur_ || i_ >= cur_->soa.n()) { cur_ = pb_.next(); i_ = 0; if (!cur_) { stream_end = true; break; } if (cur_->soa.n() == 0) continue; }
             const SoaTile &f = cur_->soa;
             const int32_t rt = cur_->tid[i_];
             if (rt != tid_) { if (rt > tid_ || rt < 0) { stream_end = true; break; } ++i_; continue; }
             if ((uint32_t) f.pos[i_] >= reg_end_) { stream_end = true; break; }
-            if (t.n() >= target_ && (uint32_t) f.pos[i_] > cur_beg_ && f.pos[i_] > last_pos_) { cut = (uint32_t) f.pos[i_]; break; }
+            if (have >= target_ && (uint32_t) f.pos[i_] > cur_beg_ && f.pos[i_] > last_pos_) { cut = (uint32_t) f.pos[i_]; break; }
             // take a run of records of this contig that stays below the region end (and, once the tile is full, at one position)
             size_t j = i_;
-            const size_t room = t.n() >= target_ ? 1 : target_ - t.n();
+            const size_t room = std::min<size_t>(have >= target_ ? 1 : target_ - have, 8192);
             while (j < f.n() && j - i_ < room && cur_->tid[j] == tid_ && (uint32_t) f.pos[j] < reg_end_) ++j;
             // records entirely left of the region start are dropped (index semantics: endpos > beg)
             size_t a = i_;
@@ -260,10 +301,23 @@ public:
                 while (a < j && !((int64_t) std::max(f.rend[a], f.pos[a] + 1) > (int64_t) reg_beg_)) ++a;
                 size_t b = a;
                 while (b < j && (int64_t) std::max(f.rend[b], f.pos[b] + 1) > (int64_t) reg_beg_) ++b;
-                if (b > a) { t.add_range_from(f, a, b); last_pos_ = f.pos[b - 1]; }
+                if (b > a) {
+                    Run r{cur_, a, b, total};
+                    const SoaTile::Extent e = SoaTile::extent_of(f, a, b);
+                    total.n += e.n; total.c += e.c; total.s += e.s; total.q += e.q;
+                    plan.push_back(std::move(r)); have += b - a; last_pos_ = f.pos[b - 1];
+                }
                 a = b;
             }
             i_ = j;
+        }
+        if (!plan.empty()) {
+            const SoaTile::Extent base = t.extend(total);
+            pb_.parallel_for(plan.size(), [&](size_t k) {
+                const Run &r = plan[k];
+                SoaTile::Extent at; at.n = base.n + r.at.n; at.c = base.c + r.at.c; at.s = base.s + r.at.s; at.q = base.q + r.at.q;
+                t.copy_range_at(r.f->soa, r.a, r.b, at);
+            });
         }
         t.end = cut;
         // reads reaching beyond the cut (or beyond the region end) are handed on: to the next tile, or to the tiler of the adjacent region
@@ -273,7 +327,7 @@ public:
     }
 private:
     static uint32_t span_end(const SoaTile &t, size_t i) { return (uint32_t) std::max(t.rend[i], t.pos[i] + 1); }
-    ParallelBam &pb_; std::unique_ptr<Fragment> &cur_; size_t &i_;
+    ParallelBam &pb_; std::shared_ptr<Fragment> &cur_; size_t &i_;
     int tid_; uint32_t reg_beg_, reg_end_; size_t target_; uint32_t cur_beg_; bool done_ = false; int32_t last_pos_ = -1;
 };
 

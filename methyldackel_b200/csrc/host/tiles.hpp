@@ -116,6 +116,37 @@ struct SoaTile {
         memcpy(seq.grow(s1 - s0), o.seq.data() + s0, (size_t)(s1 - s0) * 4);
         memcpy(qual.grow(q1 - q0), o.qual.data() + q0, (size_t)(q1 - q0) * 8);
     }
+    // Planned assembly: the caller sums the sizes of the ranges it wants, grows every column once with extend(), and then the
+    // ranges are copied into place independently (copy_range_at), e.g. on a thread pool.
+    struct Extent { size_t n = 0, c = 0, s = 0, q = 0; };
+    static Extent extent_of(const SoaTile &o, size_t a, size_t b) {
+        Extent e; const size_t on = o.n();
+        e.n = b - a;
+        e.c = (b < on ? o.cigar_off[b] : (uint32_t) o.cigar.size()) - o.cigar_off[a];
+        e.s = (b < on ? o.seq_off[b] : (uint32_t) o.seq.size()) - o.seq_off[a];
+        e.q = (b < on ? o.qual_off[b] : (uint32_t) o.qual.size()) - o.qual_off[a];
+        return e;
+    }
+    Extent extend(const Extent &by) {
+        Extent at; at.n = n(); at.c = cigar.size(); at.s = seq.size(); at.q = qual.size();
+        pos.grow(by.n); flag.grow(by.n); mapq.grow(by.n); aux.grow(by.n); l_qseq.grow(by.n); frag_key.grow(by.n); rend.grow(by.n);
+        cigar_off.grow(by.n); seq_off.grow(by.n); qual_off.grow(by.n); cigar.grow(by.c); seq.grow(by.s); qual.grow(by.q);
+        return at;
+    }
+    void copy_range_at(const SoaTile &o, size_t a, size_t b, const Extent &at) {
+        const size_t k = b - a; if (!k) return;
+        const Extent e = extent_of(o, a, b);
+        memcpy(pos.data() + at.n, o.pos.data() + a, k * 4); memcpy(flag.data() + at.n, o.flag.data() + a, k * 2);
+        memcpy(mapq.data() + at.n, o.mapq.data() + a, k); memcpy(aux.data() + at.n, o.aux.data() + a, k);
+        memcpy(l_qseq.data() + at.n, o.l_qseq.data() + a, k * 4); memcpy(frag_key.data() + at.n, o.frag_key.data() + a, k * 8);
+        memcpy(rend.data() + at.n, o.rend.data() + a, k * 4);
+        const uint32_t c0 = o.cigar_off[a], s0 = o.seq_off[a], q0 = o.qual_off[a];
+        uint32_t *co = cigar_off.data() + at.n, *so = seq_off.data() + at.n, *qo = qual_off.data() + at.n;
+        for (size_t i = 0; i < k; ++i) { co[i] = (uint32_t) at.c + (o.cigar_off[a + i] - c0); so[i] = (uint32_t) at.s + (o.seq_off[a + i] - s0); qo[i] = (uint32_t) at.q + (o.qual_off[a + i] - q0); }
+        memcpy(cigar.data() + at.c, o.cigar.data() + c0, e.c * 4);
+        memcpy(seq.data() + at.s, o.seq.data() + s0, e.s * 4);
+        memcpy(qual.data() + at.q, o.qual.data() + q0, e.q * 8);
+    }
     // Re-encode the phred column as 2- or 4-bit codes when the tile's alphabet allows it (lossless; see md_reads_soa).
     // `scratch` receives the packed words and is swapped in, so a ring of tiles re-uses its allocations.  `par(n, fn)` runs
     // fn(k) for k in [0,n) — the driver passes its decode pool, so a 2^17-alignment tile is packed in about a millisecond.

@@ -1178,7 +1178,7 @@ static Lane *free_lane(md_ctx *c, int *ticket) {
     return nullptr;
 }
 
-extern "C" int md_submit_tile(md_ctx *c, const md_tile_desc *tile, const md_reads_soa *reads) {
+static int submit_common(md_ctx *c, const md_tile_desc *tile, const md_reads_soa *reads, bool mbias) {
     CK(cudaSetDevice(c->device));
     int ticket = -1;
     Lane *L = free_lane(c, &ticket);
@@ -1186,7 +1186,7 @@ extern "C" int md_submit_tile(md_ctx *c, const md_tile_desc *tile, const md_read
     CK(cudaEventRecord(L->ev[0], L->stream));
     int rc = stage_reads(c, L, L->staged, reads);
     if (rc) return rc;
-    rc = run_pipeline(c, L, tile, L->staged.view, false);
+    rc = run_pipeline(c, L, tile, L->staged.view, mbias);
     if (rc) return rc;
     // queue the small read-backs now so that collect only has to wait
     CK(cudaMemcpyAsync(L->h_counters, L->counters.p, C_N * 4, cudaMemcpyDeviceToHost, L->stream));
@@ -1194,6 +1194,8 @@ extern "C" int md_submit_tile(md_ctx *c, const md_tile_desc *tile, const md_read
     c->last = L;
     return ticket;
 }
+extern "C" int md_submit_tile(md_ctx *c, const md_tile_desc *tile, const md_reads_soa *reads) { return submit_common(c, tile, reads, false); }
+extern "C" int md_submit_mbias_tile(md_ctx *c, const md_tile_desc *tile, const md_reads_soa *reads) { return submit_common(c, tile, reads, true); }
 
 extern "C" int md_collect_tile(md_ctx *c, int ticket, md_call *calls, uint64_t capacity, md_tile_stats *stats) {
     CK(cudaSetDevice(c->device));
@@ -1202,7 +1204,7 @@ extern "C" int md_collect_tile(md_ctx *c, int ticket, md_call *calls, uint64_t c
     L->pending = false;
     int rc = finish_counters(c, L, stats);
     if (rc) return rc;
-    rc = fetch_sorted(c, L, calls, capacity, nullptr);
+    if (!L->last_mbias) rc = fetch_sorted(c, L, calls, capacity, nullptr);
     CK(cudaEventRecord(L->ev[4], L->stream));
     CK(cudaStreamSynchronize(L->stream));
     collect_timing(L);
@@ -1237,21 +1239,9 @@ extern "C" int md_fetch_calls(md_ctx *c, md_call *calls, uint64_t capacity, uint
 }
 
 extern "C" int md_mbias_tile(md_ctx *c, const md_tile_desc *tile, const md_reads_soa *reads, md_tile_stats *stats) {
-    CK(cudaSetDevice(c->device));
-    int ticket = -1;
-    Lane *L = free_lane(c, &ticket);
-    if (!L) { g_err = "md_mbias_tile: all lanes are busy"; return -4; }
-    CK(cudaEventRecord(L->ev[0], L->stream));
-    int rc = stage_reads(c, L, L->staged, reads);
-    if (rc) return rc;
-    rc = run_pipeline(c, L, tile, L->staged.view, true);
-    if (rc) return rc;
-    rc = finish_counters(c, L, stats);
-    CK(cudaEventRecord(L->ev[4], L->stream));
-    CK(cudaStreamSynchronize(L->stream));
-    collect_timing(L);
-    c->last = L;
-    return rc;
+    int t = md_submit_mbias_tile(c, tile, reads);
+    if (t < 0) return t;
+    return md_collect_tile(c, t, nullptr, 0, stats);
 }
 
 extern "C" int md_mbias_tile_device(md_ctx *c, const md_tile_desc *tile, const md_dev_reads *reads, md_tile_stats *stats) {
