@@ -32,6 +32,8 @@ extern "C" void mdh_last_run_stats(mdh_run_stats *out) { if (out) *out = g_stats
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 // MD_TIMING=1: phase marks on stderr (seconds since the sub-command started)
 static double g_t0 = 0; static bool g_marks = false;
+static double g_acc[8];   // pack, contig load, absorb, drain, ring wait
+struct Acc { int k; double t0; explicit Acc(int k_) : k(k_), t0(now_s()) {} ~Acc() { g_acc[k] += now_s() - t0; } };
 static void mark(const char *what) { if (g_marks) fprintf(stderr, "[md-timing] %8.3f  %s\n", now_s() - g_t0, what); }
 
 // parseBounds, common.c:11-43: four comma-separated non-negative ints into vals[4*mult..]
@@ -121,6 +123,13 @@ static int decode_threads(int n, bool given) {
     if (const char *e = getenv("MD_DECODE_THREADS")) { int v = atoi(e); if (v > 0) return v; }
     return (int) std::min<unsigned>(hw ? hw : 1, 64);
 }
+
+// While the CUDA context is being created, full-speed decoding on every core makes that creation several times slower (both
+// sides fight over the process's address-space lock); a handful of decode threads run ahead until the device is up.
+static int warm_threads(int nthreads) { const char *e = getenv("MD_WARM_THREADS"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > nthreads ? nthreads : v); }
+
+// alignments per device tile (testing knob: small values exercise tile cuts and carried reads on small inputs)
+static size_t tile_reads_default(bool async) { if (const char *e = getenv("MD_TILE_READS")) { long v = atol(e); if (v > 0) return (size_t) v; } return async ? ((size_t) 1 << 17) : ((size_t) 1 << 19); }
 
 static bool pack_quals_enabled() { const char *e = getenv("MD_QUAL_PACK"); return !(e && e[0] == '0'); }
 
@@ -264,7 +273,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
 
     Driver d; d.be = be;
     const char *fastaName = argv[optind], *bamName = argv[optind + 1];
-    try { d.bam.reset(new ParallelBam(bamName, decode_threads(nThreads, threads_given))); }
+    try { { const int nt = decode_threads(nThreads, threads_given); d.bam.reset(new ParallelBam(bamName, nt, warm_threads(nt))); } }
     catch (std::exception &e) { fprintf(stderr, "Couldn't open %s for reading!\n", bamName); return -4; }
     d.hdr = &d.bam->header();
     d.have_bai = load_bai(bamName, d.bai);
@@ -343,17 +352,16 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         TileAlloc pin; if (use_async && be->pinned_alloc && be->pinned_free) { pin.alloc = be->pinned_alloc; pin.release = be->pinned_free; }
         std::vector<std::unique_ptr<SoaTile>> ring;
         for (int k = 0; k < (use_async ? 3 : 1); ++k) ring.emplace_back(new SoaTile(use_async ? &pin : nullptr));
-        const size_t tile_reads = use_async ? ((size_t) 1 << 17) : ((size_t) 1 << 19);
+        const size_t tile_reads = tile_reads_default(use_async);
         if (use_async) for (auto &t : ring) t->reserve_for(tile_reads + tile_reads / 8, 160);
         // phred column re-encoded as 2/4-bit codes when the tile's alphabet allows (md_reads_soa::qual_bits)
         const bool pack_q = pack_quals_enabled();
-        std::vector<std::unique_ptr<PodVec<uint64_t>>> qscratch; std::vector<std::unique_ptr<PodVec<uint32_t>>> qoffscratch;
-        for (size_t k = 0; k < ring.size(); ++k) { qscratch.emplace_back(new PodVec<uint64_t>(use_async ? &pin : nullptr)); qoffscratch.emplace_back(new PodVec<uint32_t>(use_async ? &pin : nullptr)); }
         SoaTile carry;
         std::vector<md_call> calls; size_t calls_head = 0;
-        std::vector<md_call> tile_calls;
+        PodVec<md_call> tile_calls;                              // collect target (plain capacity, never value-initialised)
         mark("tile ring reserved");
         d.dev = dev_future.get(); dev_join.taken = true;
+        d.bam->set_active_threads(d.bam->threads());
         mark("device joined");
         if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
         size_t ci = c0;
@@ -362,6 +370,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             uint32_t tid = all[ci].tid;
             std::vector<Chunk> chunks;
             while (ci < c1 && all[ci].tid == tid) chunks.push_back(all[ci++]);
+            double t_ld = now_s();
             const std::string *ref = d.fetch(tid);
             if (!ref) {
                 fprintf(stderr, "faidx_fetch_seq returned %i while trying to fetch the sequence for tid %s:%" PRIu32 "-%" PRIu32 "!\n", -2, d.hdr->names[tid].c_str(), chunks.front().beg, chunks.front().end);
@@ -371,6 +380,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             uint32_t rbeg = chunks.front().beg, rend = chunks.back().end;
             if (rend > ref->size()) rend = (uint32_t) ref->size();
             if (be->load_contig(d.dev, (int32_t) tid, ref->data(), (uint32_t) ref->size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+            g_acc[1] += now_s() - t_ld;
             mark("contig loaded");
             d.seek_to((int) tid, rbeg);
             calls.clear(); calls_head = 0; carry.clear();
@@ -398,22 +408,22 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             std::vector<Flight> flight;
             auto collect_one = [&]() -> int {
                 Flight f = flight.front(); flight.erase(flight.begin());
-                tile_calls.resize(f.cap);
+                { Acc a_(4); tile_calls.clear(); tile_calls.grow(f.cap); }
                 md_tile_stats st;
                 double t0 = now_s();
                 int r = be->collect_tile(d.dev, f.ticket, tile_calls.data(), f.cap, &st);
                 g_stats.t_device_s += now_s() - t0;
                 if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
-                calls.insert(calls.end(), tile_calls.begin(), tile_calls.begin() + (ptrdiff_t) st.n_calls);
+                { Acc a_(2); calls.insert(calls.end(), tile_calls.data(), tile_calls.data() + (ptrdiff_t) st.n_calls);
                 g_stats.n_calls += st.n_calls;
-                absorb(f.end, false);
+                absorb(f.end, false); }
                 return 0;
             };
             size_t rk = 0;
             for (size_t ri = 0; ri < regions.size() && rc == 0; ++ri) {
             const uint32_t gbeg = regions[ri].beg, gend = std::min<uint32_t>(regions[ri].end, (uint32_t) ref->size());
             const uint32_t ce_beg = per_chunk ? (gbeg > 1 ? gbeg - 2 : 0) : 0, ce_end = per_chunk ? (uint32_t) std::min<uint64_t>((uint64_t) regions[ri].end + 11, ref->size()) : 0;
-            FragTiler tiler(*d.bam, d.frag, d.frag_i, (int) tid, gbeg, gend, tile_reads);
+            FragTiler tiler(*d.bam, d.frag, d.frag_i, (int) tid, gbeg, gend, tile_reads); tiler.set_pack_quals(pack_q);
             for (;;) {
                 SoaTile &tile = *ring[rk % ring.size()];
                 // the ring slot we are about to refill must have been collected
@@ -424,7 +434,6 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
                 g_stats.t_decode_s += now_s() - t0;
                 if (!got) break;
                 if (tile.n() == 0) { if (!use_async) absorb(tile.end, false); continue; }
-                if (pack_q) tile.pack_quals(*qscratch[rk % ring.size()], *qoffscratch[rk % ring.size()], [&](size_t n, const std::function<void(size_t)> &fn) { d.bam->parallel_for(n, fn); });
                 md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end, ce_beg, ce_end};
                 uint64_t cap = (uint64_t)(tile.end - tile.beg) + 16;
                 g_stats.n_records += tile.n(); g_stats.n_tiles++;
@@ -437,12 +446,12 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
                     ++rk;
                 } else {
                     md_tile_stats st;
-                    tile_calls.resize(cap);
+                    tile_calls.clear(); tile_calls.grow(cap);
                     t0 = now_s();
                     int r = be->extract_tile(d.dev, &td, &v, tile_calls.data(), cap, &st);
                     g_stats.t_device_s += now_s() - t0;
                     if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
-                    calls.insert(calls.end(), tile_calls.begin(), tile_calls.begin() + (ptrdiff_t) st.n_calls);
+                    calls.insert(calls.end(), tile_calls.data(), tile_calls.data() + (ptrdiff_t) st.n_calls);
                     g_stats.n_calls += st.n_calls;
                     absorb(tile.end, false);
                 }
@@ -451,13 +460,15 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             mark("last tile submitted");
             while (rc == 0 && !flight.empty()) rc = collect_one();
             if (rc == 0) absorb(rend, true);
-            out_thread.drain();                                     // the next contig replaces *ref
+            { Acc a_(3); out_thread.drain(); }                      // the next contig replaces *ref
             mark("contig written");
             be->drop_contig(d.dev, (int32_t) tid);
         }
     }
     out_thread.drain();
     g_stats.t_format_s = out_thread.busy_seconds();
+    if (g_marks) fprintf(stderr, "[md-timing] calling thread: phred packing %.3f, contig load %.3f, call hand-over %.3f, writer drain %.3f, result buffer %.3f\n", g_acc[0], g_acc[1], g_acc[2], g_acc[3], g_acc[4]);
+    if (g_marks) fprintf(stderr, "[md-timing] record chains: %zu jobs adopted from the inflating worker, %zu walked by the stitcher\n", d.bam->jobs_adopted(), d.bam->jobs_walked());
     be->destroy(d.dev);
     mark("device destroyed");
     g_stats.n_variant_positions = writer.n_variant_positions();
@@ -530,7 +541,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
 
     Driver d; d.be = be;
     const char *fastaName = argv[optind], *bamName = argv[optind + 1];
-    try { d.bam.reset(new ParallelBam(bamName, decode_threads(nThreads, threads_given))); }
+    try { { const int nt = decode_threads(nThreads, threads_given); d.bam.reset(new ParallelBam(bamName, nt, warm_threads(nt))); } }
     catch (std::exception &e) { fprintf(stderr, "Couldn't open %s for reading!\n", bamName); return -4; }
     d.hdr = &d.bam->header();
     d.have_bai = load_bai(bamName, d.bai);
@@ -573,13 +584,12 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
         TileAlloc pin; if (use_async && be->pinned_alloc && be->pinned_free) { pin.alloc = be->pinned_alloc; pin.release = be->pinned_free; }
         std::vector<std::unique_ptr<SoaTile>> ring;
         for (int k = 0; k < (use_async ? 3 : 1); ++k) ring.emplace_back(new SoaTile(use_async ? &pin : nullptr));
-        const size_t tile_reads = use_async ? ((size_t) 1 << 17) : ((size_t) 1 << 19);
+        const size_t tile_reads = tile_reads_default(use_async);
         if (use_async) for (auto &t : ring) t->reserve_for(tile_reads + tile_reads / 8, 160);
-        std::vector<std::unique_ptr<PodVec<uint64_t>>> qscratch; std::vector<std::unique_ptr<PodVec<uint32_t>>> qoffscratch;
-        for (size_t k = 0; k < ring.size(); ++k) { qscratch.emplace_back(new PodVec<uint64_t>(use_async ? &pin : nullptr)); qoffscratch.emplace_back(new PodVec<uint32_t>(use_async ? &pin : nullptr)); }
         SoaTile carry;
         mark("tile ring reserved");
         d.dev = dev_future.get(); dev_join.taken = true;
+        d.bam->set_active_threads(d.bam->threads());
         if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
         std::vector<int> flight;
         auto collect_one = [&]() -> int {
@@ -608,7 +618,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
             if (be->load_contig(d.dev, (int32_t) tid, ref->data(), (uint32_t) ref->size()) != 0 ||
                 be->set_mbias_chunks(d.dev, (int32_t) tid, bounds.data(), (uint32_t) bounds.size() - 1) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
             d.seek_to((int) tid, rbeg);
-            FragTiler tiler(*d.bam, d.frag, d.frag_i, (int) tid, rbeg, rend, tile_reads);
+            FragTiler tiler(*d.bam, d.frag, d.frag_i, (int) tid, rbeg, rend, tile_reads); tiler.set_pack_quals(pack_quals_enabled());
             carry.clear();
             for (;;) {
                 SoaTile &tile = *ring[rk % ring.size()];
@@ -619,7 +629,6 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
                 g_stats.t_decode_s += now_s() - t0;
                 if (!got) break;
                 if (tile.n() == 0) continue;
-                if (pack_quals_enabled()) tile.pack_quals(*qscratch[rk % ring.size()], *qoffscratch[rk % ring.size()], [&](size_t n, const std::function<void(size_t)> &fn) { d.bam->parallel_for(n, fn); });
                 md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end, 0, 0}; md_tile_stats st;
                 g_stats.n_records += tile.n(); g_stats.n_tiles++;
                 t0 = now_s();

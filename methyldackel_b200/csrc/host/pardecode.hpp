@@ -29,7 +29,7 @@ class ThreadPool {
 public:
     explicit ThreadPool(int n) {
         if (n < 1) n = 1;
-        for (int i = 0; i < n; ++i) th_.emplace_back([this] { run(); });
+        for (int i = 0; i < n; ++i) th_.emplace_back([this, i] { run(i); });
     }
     ~ThreadPool() {
         { std::lock_guard<std::mutex> g(m_); stop_ = true; }
@@ -38,19 +38,21 @@ public:
     }
     // fire-and-forget; `urgent` tasks overtake the queued decode work (tile-level helpers the caller waits on)
     void post(std::function<void()> fn, bool urgent = false) {
-        { std::lock_guard<std::mutex> g(m_); if (urgent) q_.emplace_front(std::move(fn)); else q_.emplace_back(std::move(fn)); }
-        cv_.notify_one();
+        bool all; { std::lock_guard<std::mutex> g(m_); if (urgent) q_.emplace_front(std::move(fn)); else q_.emplace_back(std::move(fn)); all = active_ < (int) th_.size(); }
+        if (all) cv_.notify_all(); else cv_.notify_one();
     }
     int size() const { return (int) th_.size(); }
+    // only the first n workers take tasks (the rest sleep) until the limit is raised again
+    void set_active(int n) { { std::lock_guard<std::mutex> g(m_); active_ = n; } cv_.notify_all(); }
 private:
-    void run() {
+    void run(int me) {
         for (;;) {
             std::function<void()> fn;
-            { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [this] { return stop_ || !q_.empty(); }); if (stop_ && q_.empty()) return; fn = std::move(q_.front()); q_.pop_front(); }
+            { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return stop_ || (!q_.empty() && me < active_); }); if (stop_ && (q_.empty() || me >= active_)) return; fn = std::move(q_.front()); q_.pop_front(); }
             fn();
         }
     }
-    std::vector<std::thread> th_; std::deque<std::function<void()>> q_; std::mutex m_; std::condition_variable cv_; bool stop_ = false;
+    std::vector<std::thread> th_; std::deque<std::function<void()>> q_; std::mutex m_; std::condition_variable cv_; bool stop_ = false; int active_ = 1 << 30;
 };
 
 // A decoded run of consecutive records: SoA columns + the contig id of each record.
@@ -65,7 +67,9 @@ struct Fragment {
 // their parses), so decoding runs ahead of the consumer — in particular while the CUDA context is still coming up.
 class ParallelBam {
 public:
-    ParallelBam(const std::string &path, int nthreads) : pool_(nthreads), aux_(std::max(1, std::min(16, nthreads))) {
+    // `warm_threads` > 0 keeps all but that many decode workers asleep until set_active_threads() raises the limit
+    ParallelBam(const std::string &path, int nthreads, int warm_threads = 0) : pool_(nthreads), aux_(std::max(1, std::min(16, nthreads))) {
+        if (warm_threads > 0) pool_.set_active(warm_threads);
         // header through the sequential reader; remember where the records start
         BgzfReader rd(path);
         hdr_ = read_bam_header(rd);
@@ -88,6 +92,10 @@ public:
     }
     const BamHeader &header() const { return hdr_; }
     uint64_t first_record_voffset() const { return start_voff_; }
+    int threads() const { return pool_.size(); }
+    size_t jobs_adopted() const { return n_adopted_; }
+    size_t jobs_walked() const { return n_walked_; }
+    void set_active_threads(int n) { pool_.set_active(n); }
     // run fn(0..n-1) and wait (tile-level work the caller is blocked on: column copies, phred packing).  These go to a small
     // pool of their own: the decode pool's workers sit in ~10 ms inflate/parse jobs, which would be the latency of every call.
     void parallel_for(size_t n, const std::function<void(size_t)> &fn) {
@@ -133,6 +141,40 @@ private:
         std::vector<uint32_t> rec_off;                                                     // starts of whole records in ubuf (pointing at the length prefix)
         State state = QUEUED; std::string err;
         std::unique_ptr<Fragment> frag;
+        // Speculative record chain, built by the inflating worker while the bytes are hot in its cache: the first offset
+        // from which a few consecutive plausible record headers follow, and the chain walked from there.  The ordered
+        // stitch step adopts it when the true first record start (known from the predecessor) is that offset — then the
+        // serial work per job is O(1) — and otherwise walks the chain itself.
+        size_t guess_start = (size_t) -1, guess_tail = 0; std::vector<uint32_t> guess_off;
+        int32_t n_targets = 0;
+        bool plausible(size_t o, int depth) const {
+            const size_t U = ubuf.size(); const uint8_t *u = ubuf.data();
+            for (int d = 0; d < depth; ++d) {
+                if (o + 36 > U) return d > 0;                         // ran off the end after at least one full header
+                const uint32_t bs = le32(u + o);
+                if (bs < 32 || bs > (1u << 28)) return false;
+                const int32_t tid = (int32_t) le32(u + o + 4), pos = (int32_t) le32(u + o + 8);
+                const uint32_t lq = u[o + 12], ncig = le32(u + o + 16) & 0xffffu; const int32_t lseq = (int32_t) le32(u + o + 20);
+                const int32_t mtid = (int32_t) le32(u + o + 24);
+                if (tid < -1 || tid >= n_targets || mtid < -1 || mtid >= n_targets || pos < -1 || lq < 1 || lseq < 0) return false;
+                const size_t need = 32 + (size_t) lq + 4 * (size_t) ncig + ((size_t) lseq + 1) / 2 + (size_t) lseq;
+                if (need > bs) return false;
+                if (o + 36 + lq <= U && u[o + 36 + lq - 1] != 0) return false;   // query name is NUL-terminated
+                o += 4 + (size_t) bs;
+                if (o == U) return true;
+            }
+            return true;
+        }
+        void speculate() {
+            const size_t U = ubuf.size(); const uint8_t *u = ubuf.data();
+            const size_t limit = std::min<size_t>(U, (size_t) 1 << 16);   // a first record start further in than this: leave it to the stitcher
+            for (size_t o = 0; o + 36 <= limit; ++o) if (plausible(o, 4)) { guess_start = o; break; }
+            if (guess_start == (size_t) -1) return;
+            size_t off = guess_start;
+            guess_off.reserve((U - off) / (4 + (size_t) le32(u + off)) + 16);
+            while (off + 4 <= U) { const size_t len = 4 + (size_t) le32(u + off); if (off + len > U) break; guess_off.push_back((uint32_t) off); off += len; }
+            guess_tail = off;
+        }
         void inflate_all() {
             // sizes first (ISIZE trailer), then inflate block by block into place
             size_t tot = 0; std::vector<size_t> uoff(blocks.size());
@@ -151,6 +193,7 @@ private:
                 if (inflate(&zs, Z_FINISH) != Z_STREAM_END || zs.total_out != isize) { inflateEnd(&zs); throw std::runtime_error("BGZF inflate failed"); }
             }
             inflateEnd(&zs);
+            speculate();
         }
         void parse() {
             frag.reset(new Fragment());
@@ -180,7 +223,7 @@ private:
         static const size_t target = [] { const char *e = getenv("MD_DECODE_JOB_BYTES"); size_t v = e ? (size_t) atol(e) : 0; return v ? v : (size_t) 1 << 20; }();   // ~1 MB of compressed blocks per job
         while (!eof_ && jobs_.size() < want_jobs) {
             std::shared_ptr<Job> j(new Job());
-            j->base = map_ + file_off_;
+            j->base = map_ + file_off_; j->n_targets = (int32_t) hdr_.names.size();
             size_t used = 0;
             while (file_off_ + used + 18 <= size_) {
                 const uint8_t *p = map_ + file_off_ + used;
@@ -243,7 +286,11 @@ private:
                 if (take == need) { j.head_rec.swap(pending_); pending_.clear(); }
             }
         }
-        if (pending_.empty()) {
+        if (pending_.empty() && off == j.guess_start) {
+            j.rec_off.swap(j.guess_off); off = j.guess_tail; ++n_adopted_;
+            if (off < U) pending_.assign(j.ubuf.begin() + (ptrdiff_t) off, j.ubuf.end());
+        } else if (pending_.empty()) {
+            ++n_walked_;
             const uint8_t *u = j.ubuf.data();
             size_t nest = 0;
             if (U > off + 4) { size_t l0 = 4 + (size_t) le32(u + off); nest = l0 ? (U - off) / l0 + 16 : 0; }
@@ -263,7 +310,7 @@ private:
     uint64_t start_voff_ = 0;
     std::mutex m_; std::condition_variable cv_;
     size_t file_off_ = 0, skip_ = 0; bool eof_ = false; std::atomic<bool> cancel_{false};
-    size_t tasks_ = 0, stitch_next_ = 0;
+    size_t tasks_ = 0, stitch_next_ = 0, n_adopted_ = 0, n_walked_ = 0;
     std::vector<uint8_t> pending_;
     std::deque<std::shared_ptr<Job>> jobs_;
 };
@@ -274,16 +321,17 @@ class FragTiler {
 public:
     FragTiler(ParallelBam &pb, std::shared_ptr<Fragment> &cur, size_t &cur_i, int tid, uint32_t reg_beg, uint32_t reg_end, size_t target_reads)
         : pb_(pb), cur_(cur), i_(cur_i), tid_(tid), reg_beg_(reg_beg), reg_end_(reg_end), target_(target_reads), cur_beg_(reg_beg) {}
+    // phred columns of the tiles are written as 2/4-bit codes when the tile's alphabet allows (md_reads_soa::qual_bits)
+    void set_pack_quals(bool on) { pack_ = on; }
     bool next(SoaTile &t, SoaTile &carry) {
         if (done_) return false;
         t.clear(); t.tid = tid_; t.beg = cur_beg_;
-        for (size_t i = 0; i < carry.n(); ++i) if (span_end(carry, i) > cur_beg_) t.add_from(carry, i);
-        carry.clear();
+        std::vector<size_t> keep;
+        for (size_t i = 0; i < carry.n(); ++i) if (span_end(carry, i) > cur_beg_) keep.push_back(i);
         uint32_t cut = reg_end_;
         bool stream_end = false;
         struct Run { std::shared_ptr<Fragment> f; size_t a, b; SoaTile::Extent at; };
-        std::vector<Run> plan; size_t have = t.n();
-        SoaTile::Extent total;
+        std::vector<Run> plan; size_t have = keep.size();
         for (;;) {
             if (!cur_ || i_ >= cur_->soa.n()) { cur_ = pb_.next(); i_ = 0; if (!cur_) { stream_end = true; break; } if (cur_->soa.n() == 0) continue; }
             const SoaTile &f = cur_->soa;
@@ -301,17 +349,26 @@ public:
                 while (a < j && !((int64_t) std::max(f.rend[a], f.pos[a] + 1) > (int64_t) reg_beg_)) ++a;
                 size_t b = a;
                 while (b < j && (int64_t) std::max(f.rend[b], f.pos[b] + 1) > (int64_t) reg_beg_) ++b;
-                if (b > a) {
-                    Run r{cur_, a, b, total};
-                    const SoaTile::Extent e = SoaTile::extent_of(f, a, b);
-                    total.n += e.n; total.c += e.c; total.s += e.s; total.q += e.q;
-                    plan.push_back(std::move(r)); have += b - a; last_pos_ = f.pos[b - 1];
-                }
+                if (b > a) { plan.push_back(Run{cur_, a, b, SoaTile::Extent()}); have += b - a; last_pos_ = f.pos[b - 1]; }
                 a = b;
             }
             i_ = j;
         }
+        // the tile's phred alphabet: what the contributing fragments saw while they were parsed, plus the carried reads
+        if (pack_) {
+            uint8_t seen[256] = {0};
+            const Fragment *lastf = nullptr;
+            for (const Run &r : plan) if (r.f.get() != lastf) { lastf = r.f.get(); for (int v = 0; v < 256; ++v) seen[v] |= r.f->soa.qseen[v]; }
+            for (size_t i : keep) for (uint32_t j = 0, l = carry.l_qseq[i]; j < l; ++j) seen[carry.qual_value(i, j)] = 1;
+            uint8_t lut[16]; int na = 0;
+            for (int v = 0; v < 256; ++v) if (seen[v]) { if (na < 16) lut[na] = (uint8_t) v; ++na; }
+            if (na <= 16) t.set_encoding(na <= 4 ? 2 : 4, lut, na);
+        }
+        for (size_t i : keep) t.add_from(carry, i);
+        carry.clear();
         if (!plan.empty()) {
+            SoaTile::Extent total;
+            for (Run &r : plan) { r.at = total; const SoaTile::Extent e = t.extent_of(r.f->soa, r.a, r.b); total.n += e.n; total.c += e.c; total.s += e.s; total.q += e.q; }
             const SoaTile::Extent base = t.extend(total);
             pb_.parallel_for(plan.size(), [&](size_t k) {
                 const Run &r = plan[k];
@@ -328,7 +385,7 @@ public:
 private:
     static uint32_t span_end(const SoaTile &t, size_t i) { return (uint32_t) std::max(t.rend[i], t.pos[i] + 1); }
     ParallelBam &pb_; std::shared_ptr<Fragment> &cur_; size_t &i_;
-    int tid_; uint32_t reg_beg_, reg_end_; size_t target_; uint32_t cur_beg_; bool done_ = false; int32_t last_pos_ = -1;
+    int tid_; uint32_t reg_beg_, reg_end_; size_t target_; uint32_t cur_beg_; bool done_ = false; int32_t last_pos_ = -1; bool pack_ = false;
 };
 
 }  // namespace mdhost

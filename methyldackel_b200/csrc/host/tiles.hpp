@@ -54,6 +54,8 @@ struct SoaTile {
     int32_t tid = -1;
     uint32_t beg = 0, end = 0;
     uint32_t qual_bits = 8; uint8_t qual_lut[16] = {0};      // phred encoding of qual[] (include/mdgpu.h)
+    uint8_t qual_code[256] = {0};                             // inverse of qual_lut while qual_bits < 8
+    uint8_t qseen[256] = {0};                                 // phred values add() has stored (alphabet of an 8-bit tile)
     PodVec<int32_t> pos; PodVec<uint16_t> flag; PodVec<uint8_t> mapq, aux; PodVec<uint32_t> l_qseq, cigar_off, seq_off, qual_off;
     PodVec<uint64_t> frag_key; PodVec<uint32_t> cigar, seq; PodVec<uint64_t> qual;
     PodVec<int32_t> rend;   // host-only: reference end of each read (for carry-over between tiles)
@@ -63,7 +65,7 @@ struct SoaTile {
         pos.reserve(reads); flag.reserve(reads); mapq.reserve(reads); aux.reserve(reads); l_qseq.reserve(reads); cigar_off.reserve(reads + 1); seq_off.reserve(reads); qual_off.reserve(reads);
         frag_key.reserve(reads); rend.reserve(reads); cigar.reserve(reads * 2); seq.reserve(reads * ((read_len / 2 + 3) / 4 + 1)); qual.reserve(reads * ((read_len + 7) / 8 + 1));
     }
-    void clear() { qual_bits = 8; pos.clear(); flag.clear(); mapq.clear(); aux.clear(); l_qseq.clear(); cigar_off.clear(); seq_off.clear(); qual_off.clear(); frag_key.clear(); cigar.clear(); seq.clear(); qual.clear(); rend.clear(); }
+    void clear() { qual_bits = 8; memset(qseen, 0, sizeof qseen); pos.clear(); flag.clear(); mapq.clear(); aux.clear(); l_qseq.clear(); cigar_off.clear(); seq_off.clear(); qual_off.clear(); frag_key.clear(); cigar.clear(); seq.clear(); qual.clear(); rend.clear(); }
     size_t bytes() const { return n() * (4 + 2 + 1 + 1 + 4 + 4 + 4 + 4 + 8) + 4 + cigar.size() * 4 + seq.size() * 4 + qual.size() * 8; }
 
     void add(const BamRec &r) {
@@ -83,19 +85,49 @@ struct SoaTile {
         size_t sb = ((size_t) r.l_qseq + 1) / 2, sw = (sb + 3) / 4, qw = ((size_t) r.l_qseq + 7) / 8;
         seq_off.push_back((uint32_t) seq.size()); qual_off.push_back((uint32_t) qual.size());
         uint32_t *s = seq.grow(sw); if (sw) { s[sw - 1] = 0; memcpy(s, r.seq, sb); }
-        uint64_t *q = qual.grow(qw); if (qw) { q[qw - 1] = 0; memcpy(q, r.qual, (size_t) r.l_qseq); }
+        uint64_t *q = qual.grow(qw); if (qw) { q[qw - 1] = 0; uint8_t *qb = (uint8_t *) q; for (int32_t j = 0; j < r.l_qseq; ++j) { const uint8_t v = r.qual[j]; qb[j] = v; qseen[v] = 1; } }
         frag_key.push_back(qname_key(r.qname, strnlen(r.qname, r.l_qname)));
     }
-    // copy read i of another tile (carry-over of reads that straddle a tile boundary)
+    // phred encoding of this tile: 8 = plain bytes; 2/4 = codes into `lut` (at most 4/16 distinct values, ascending)
+    void set_encoding(uint32_t bits, const uint8_t *lut, int n_lut) {
+        qual_bits = bits; memset(qual_lut, 0, 16); memset(qual_code, 0, 256);
+        if (bits < 8) for (int k = 0; k < n_lut; ++k) { qual_lut[k] = lut[k]; qual_code[lut[k]] = (uint8_t) k; }
+    }
+    size_t qual_words_for(uint32_t l) const { return ((size_t) l * qual_bits + 63) / 64; }
+    uint8_t qual_value(size_t i, uint32_t j) const {
+        const uint64_t *w = qual.data() + qual_off[i];
+        if (qual_bits == 8) return ((const uint8_t *) w)[j];
+        if (qual_bits == 4) return qual_lut[(w[j >> 4] >> ((j & 15) * 4)) & 15];
+        return qual_lut[(w[j >> 5] >> ((j & 31) * 2)) & 3];
+    }
+    // write l phred values (plain bytes) at w in this tile's encoding; w has qual_words_for(l) words
+    void encode_quals(uint64_t *w, const uint8_t *q, uint32_t l) const {
+        const size_t words = qual_words_for(l);
+        if (!words) return;
+        if (qual_bits == 8) { w[words - 1] = 0; memcpy(w, q, l); return; }
+        if (qual_bits == 2) {
+            uint32_t j = 0;
+            for (size_t x = 0; x < words; ++x) { uint64_t v = 0; const uint32_t e = std::min<uint32_t>(l, j + 32); for (int sh = 0; j < e; ++j, sh += 2) v |= (uint64_t) qual_code[q[j]] << sh; w[x] = v; }
+        } else {
+            uint32_t j = 0;
+            for (size_t x = 0; x < words; ++x) { uint64_t v = 0; const uint32_t e = std::min<uint32_t>(l, j + 16); for (int sh = 0; j < e; ++j, sh += 4) v |= (uint64_t) qual_code[q[j]] << sh; w[x] = v; }
+        }
+    }
+    // copy read i of another tile (carry-over of reads that straddle a tile boundary); the phreds are re-encoded if the two
+    // tiles differ in encoding (every value must exist in this tile's alphabet)
     void add_from(const SoaTile &o, size_t i) {
         pos.push_back(o.pos[i]); flag.push_back(o.flag[i]); mapq.push_back(o.mapq[i]); aux.push_back(o.aux[i]); l_qseq.push_back(o.l_qseq[i]);
         uint32_t c0 = o.cigar_off[i], c1 = (i + 1 < o.n()) ? o.cigar_off[i + 1] : (uint32_t) o.cigar.size();
         cigar_off.push_back((uint32_t) cigar.size());
         uint32_t *c = cigar.grow(c1 - c0); memcpy(c, o.cigar.data() + c0, (c1 - c0) * 4);
-        size_t sw = (((size_t) o.l_qseq[i] + 1) / 2 + 3) / 4, qw = ((size_t) o.l_qseq[i] + 7) / 8;
+        const uint32_t l = o.l_qseq[i];
+        size_t sw = (((size_t) l + 1) / 2 + 3) / 4, qw = qual_words_for(l);
         seq_off.push_back((uint32_t) seq.size()); qual_off.push_back((uint32_t) qual.size());
         uint32_t *s = seq.grow(sw); memcpy(s, o.seq.data() + o.seq_off[i], sw * 4);
-        uint64_t *q = qual.grow(qw); memcpy(q, o.qual.data() + o.qual_off[i], qw * 8);
+        uint64_t *q = qual.grow(qw);
+        if (o.qual_bits == 8) { const uint8_t *src = (const uint8_t *)(o.qual.data() + o.qual_off[i]); if (qual_bits == 8) for (uint32_t j = 0; j < l; ++j) qseen[src[j]] = 1; encode_quals(q, src, l); }
+        else if (o.qual_bits == qual_bits && !memcmp(o.qual_lut, qual_lut, 16)) memcpy(q, o.qual.data() + o.qual_off[i], qw * 8);
+        else { std::vector<uint8_t> tmp(l); for (uint32_t j = 0; j < l; ++j) { tmp[j] = o.qual_value(i, j); if (qual_bits == 8) qseen[tmp[j]] = 1; } encode_quals(q, tmp.data(), l); }
         frag_key.push_back(o.frag_key[i]); rend.push_back(o.rend[i]);
     }
     // bulk copy of reads [a,b) of another tile whose blobs are laid out in read order (as add() produces them)
@@ -115,16 +147,19 @@ struct SoaTile {
         memcpy(cigar.grow(c1 - c0), o.cigar.data() + c0, (size_t)(c1 - c0) * 4);
         memcpy(seq.grow(s1 - s0), o.seq.data() + s0, (size_t)(s1 - s0) * 4);
         memcpy(qual.grow(q1 - q0), o.qual.data() + q0, (size_t)(q1 - q0) * 8);
+        for (int v = 0; v < 256; ++v) qseen[v] |= o.qseen[v];
     }
     // Planned assembly: the caller sums the sizes of the ranges it wants, grows every column once with extend(), and then the
     // ranges are copied into place independently (copy_range_at), e.g. on a thread pool.
     struct Extent { size_t n = 0, c = 0, s = 0, q = 0; };
-    static Extent extent_of(const SoaTile &o, size_t a, size_t b) {
+    // sizes of reads [a,b) of an 8-bit tile `o` once stored in this tile's encoding
+    Extent extent_of(const SoaTile &o, size_t a, size_t b) const {
         Extent e; const size_t on = o.n();
         e.n = b - a;
         e.c = (b < on ? o.cigar_off[b] : (uint32_t) o.cigar.size()) - o.cigar_off[a];
         e.s = (b < on ? o.seq_off[b] : (uint32_t) o.seq.size()) - o.seq_off[a];
-        e.q = (b < on ? o.qual_off[b] : (uint32_t) o.qual.size()) - o.qual_off[a];
+        if (qual_bits == 8) e.q = (b < on ? o.qual_off[b] : (uint32_t) o.qual.size()) - o.qual_off[a];
+        else for (size_t i = a; i < b; ++i) e.q += qual_words_for(o.l_qseq[i]);
         return e;
     }
     Extent extend(const Extent &by) {
@@ -133,19 +168,32 @@ struct SoaTile {
         cigar_off.grow(by.n); seq_off.grow(by.n); qual_off.grow(by.n); cigar.grow(by.c); seq.grow(by.s); qual.grow(by.q);
         return at;
     }
+    // `o` holds plain 8-bit phreds (a decoded fragment); they are written in this tile's encoding
     void copy_range_at(const SoaTile &o, size_t a, size_t b, const Extent &at) {
         const size_t k = b - a; if (!k) return;
-        const Extent e = extent_of(o, a, b);
         memcpy(pos.data() + at.n, o.pos.data() + a, k * 4); memcpy(flag.data() + at.n, o.flag.data() + a, k * 2);
         memcpy(mapq.data() + at.n, o.mapq.data() + a, k); memcpy(aux.data() + at.n, o.aux.data() + a, k);
         memcpy(l_qseq.data() + at.n, o.l_qseq.data() + a, k * 4); memcpy(frag_key.data() + at.n, o.frag_key.data() + a, k * 8);
         memcpy(rend.data() + at.n, o.rend.data() + a, k * 4);
+        const size_t on = o.n();
         const uint32_t c0 = o.cigar_off[a], s0 = o.seq_off[a], q0 = o.qual_off[a];
+        const uint32_t c1 = b < on ? o.cigar_off[b] : (uint32_t) o.cigar.size(), s1 = b < on ? o.seq_off[b] : (uint32_t) o.seq.size(), q1 = b < on ? o.qual_off[b] : (uint32_t) o.qual.size();
         uint32_t *co = cigar_off.data() + at.n, *so = seq_off.data() + at.n, *qo = qual_off.data() + at.n;
-        for (size_t i = 0; i < k; ++i) { co[i] = (uint32_t) at.c + (o.cigar_off[a + i] - c0); so[i] = (uint32_t) at.s + (o.seq_off[a + i] - s0); qo[i] = (uint32_t) at.q + (o.qual_off[a + i] - q0); }
-        memcpy(cigar.data() + at.c, o.cigar.data() + c0, e.c * 4);
-        memcpy(seq.data() + at.s, o.seq.data() + s0, e.s * 4);
-        memcpy(qual.data() + at.q, o.qual.data() + q0, e.q * 8);
+        for (size_t i = 0; i < k; ++i) { co[i] = (uint32_t) at.c + (o.cigar_off[a + i] - c0); so[i] = (uint32_t) at.s + (o.seq_off[a + i] - s0); }
+        memcpy(cigar.data() + at.c, o.cigar.data() + c0, (size_t)(c1 - c0) * 4);
+        memcpy(seq.data() + at.s, o.seq.data() + s0, (size_t)(s1 - s0) * 4);
+        if (qual_bits == 8) {
+            for (size_t i = 0; i < k; ++i) qo[i] = (uint32_t) at.q + (o.qual_off[a + i] - q0);
+            memcpy(qual.data() + at.q, o.qual.data() + q0, (size_t)(q1 - q0) * 8);
+        } else {
+            size_t w = at.q;
+            for (size_t i = 0; i < k; ++i) {
+                const uint32_t l = o.l_qseq[a + i];
+                qo[i] = (uint32_t) w;
+                encode_quals(qual.data() + w, (const uint8_t *)(o.qual.data() + o.qual_off[a + i]), l);
+                w += qual_words_for(l);
+            }
+        }
     }
     // Re-encode the phred column as 2- or 4-bit codes when the tile's alphabet allows it (lossless; see md_reads_soa).
     // `scratch` receives the packed words and is swapped in, so a ring of tiles re-uses its allocations.  `par(n, fn)` runs
@@ -184,7 +232,7 @@ struct SoaTile {
             }
         });
         qual.swap(scratch); qual_off.swap(scratch_off);
-        qual_bits = bits;
+        qual_bits = bits; memset(qual_code, 0, 256); for (int k = 0; k < na; ++k) qual_code[qual_lut[k]] = (uint8_t) k;
     }
     void pack_quals(PodVec<uint64_t> &scratch, PodVec<uint32_t> &scratch_off) {
         pack_quals(scratch, scratch_off, [](size_t n, const std::function<void(size_t)> &fn) { for (size_t k = 0; k < n; ++k) fn(k); });

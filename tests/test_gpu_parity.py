@@ -238,3 +238,25 @@ def test_cli_ultra_deep_switches_to_wide_counters(built, synth, tmp_path):
     assert compare_outputs(refp, newp) == []
     top = max(int(l.split("\t")[4]) + int(l.split("\t")[5]) for l in open(refp + "_CHH.bedGraph").read().splitlines()[1:])
     assert top > 70000
+
+
+@pytest.mark.parametrize("sub", ["extract", "mbias"])
+@pytest.mark.parametrize("nq", [4, 12, 40], ids=["2bit", "4bit", "8bit"])
+def test_cli_small_tiles_three_in_flight(built, synth, tmp_path, nq, sub):
+    """tiles of 300 alignments through the asynchronous ring (3 lanes): carried reads re-encoded per tile, results of tiles
+    in flight on different streams land in genome order (extract) / in one histogram (mbias)"""
+    p = synth("st%d" % nq, "--contigs", "chr1:40000,chr2:9000", "--depth", "30", "--quals", str(nq), "--lower-frac", "0.02")
+    env = dict(os.environ, MD_DECODE_JOB_BYTES="1", MD_TILE_READS="300")
+    if sub == "extract":
+        refp, newp = str(tmp_path / "ref"), str(tmp_path / "new")
+        opts = ["--CHG", "--CHH", "--mergeContext"]
+        r = run_ref(built["ref_bin"], "extract", opts, p + ".fa", p + ".bam", refp)
+        n = subprocess.run([NEW_BIN, "extract"] + opts + ["-@", "3", p + ".fa", p + ".bam", "-o", newp], capture_output=True, text=True, env=env)
+        assert r.returncode == 0 and n.returncode == 0, (r.stderr, n.stderr)
+        assert compare_outputs(refp, newp) == []
+    else:
+        opts = ["--CHH", "--txt", "--noSVG"]
+        r = subprocess.run([built["ref_bin"], "mbias"] + opts + [p + ".fa", p + ".bam"], capture_output=True, text=True)
+        n = subprocess.run([NEW_BIN, "mbias"] + opts + ["-@", "3", p + ".fa", p + ".bam"], capture_output=True, text=True, env=env)
+        assert r.returncode == 0 and n.returncode == 0, (r.stderr, n.stderr)
+        assert n.stdout == r.stdout and len(r.stdout.splitlines()) > 10

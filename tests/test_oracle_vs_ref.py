@@ -105,6 +105,34 @@ def test_parallel_decode_many_small_jobs(built, synth, tmp_path):
     assert compare_outputs(refp, newp) == []
 
 
+@pytest.mark.parametrize("sub", ["extract", "mbias"])
+@pytest.mark.parametrize("nq", [4, 12, 40], ids=["2bit", "4bit", "8bit"])
+def test_small_tiles_carry_and_encodings(built, synth, tmp_path, nq, sub):
+    """tiles of 300 alignments: every tile cut carries straddling reads into the next tile, re-encoded into that tile's
+    phred alphabet; jobs of one BGZF block each (speculative record chains adopted or re-walked)"""
+    import subprocess, sys
+    p = synth("st%d" % nq, "--contigs", "chr1:40000,chr2:9000", "--depth", "30", "--quals", str(nq), "--lower-frac", "0.02")
+    refp, newp = str(tmp_path / "ref"), str(tmp_path / "new")
+    opts = ["--CHG", "--CHH", "--mergeContext"] if sub == "extract" else ["--CHH", "--txt", "--noSVG"]
+    tail_ref = [p + ".fa", p + ".bam"] + ([] if sub == "mbias" else [])
+    if sub == "extract":
+        r = run_ref(built["ref_bin"], "extract", opts, p + ".fa", p + ".bam", refp)
+        assert r.returncode == 0
+        argv = opts + ["-@", "3", p + ".fa", p + ".bam", "-o", newp]
+    else:
+        r = subprocess.run([built["ref_bin"], "mbias"] + opts + tail_ref, capture_output=True, text=True)
+        assert r.returncode == 0
+        argv = opts + ["-@", "3", p + ".fa", p + ".bam"]
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import oracle_binding as ob; "
+            "sys.exit(ob.run_host_main(%r, %r, ob.OracleBackend()))") % (cases.ROOT, os.path.join(cases.ROOT, "tests"), sub, argv)
+    n = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, MD_DECODE_JOB_BYTES="1", MD_TILE_READS="300"))
+    assert n.returncode == 0, n.stderr
+    if sub == "extract":
+        assert compare_outputs(refp, newp) == []
+    else:
+        assert r.stdout == n.stdout and len(r.stdout.splitlines()) > 10
+
+
 @pytest.mark.parametrize("name,args", [
     ("len250", ["--contigs", "chr1:80000", "--depth", "20", "--readlen", "250", "--isize-mean", "400", "--isize-sd", "80", "--isize-min", "250", "--isize-max", "900"]),
     ("len20000", ["--contigs", "chr1:300000", "--depth", "6", "--readlen", "20000", "--isize-mean", "30000", "--isize-sd", "4000", "--isize-min", "20000", "--isize-max", "45000"]),
