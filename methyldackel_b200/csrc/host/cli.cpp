@@ -103,10 +103,9 @@ static bool load_bai(const std::string &bam, BaiIndex &idx) {
 
 extern "C" uint32_t mdh_chunk_bounds(const char *seq, uint32_t len, unsigned long chunk_size, uint32_t reg_beg, uint32_t reg_end, uint32_t *bounds, uint32_t cap) {
     std::vector<uint32_t> lens{len};
-    std::string s(seq, len);
     ChunkCursor cur(lens, chunk_size, 0, reg_beg, reg_end);
     Chunk c; uint32_t n = 0;
-    auto fetch = [&](uint32_t) { return &s; };
+    auto fetch = [&](uint32_t, int64_t start, int64_t cnt, std::string &w) { w.clear(); if (start < (int64_t) len) w.assign(seq + start, (size_t) std::min<int64_t>(cnt, (int64_t) len - start)); return (int64_t) len; };
     while (cur.next(c, fetch)) {
         if (c.tid != 0) break;
         if (n < cap) { bounds[n] = c.beg; bounds[n + 1] = c.end; }
@@ -175,12 +174,30 @@ struct Driver {
     std::shared_ptr<Fragment> frag; size_t frag_i = 0;      // decode cursor shared by consecutive FragTilers
     const BamHeader *hdr = nullptr;
     std::string cur_seq; int cur_seq_tid = -1; bool cur_seq_ok = false;
+    std::future<bool> next_ready; std::string next_seq; int next_tid = -1;
+    // whole contig for the device and the writer; the one announced with prefetch() was read in the background meanwhile
     const std::string *fetch(uint32_t tid) {
         if ((int) tid != cur_seq_tid) {
-            cur_seq_tid = (int) tid; cur_seq.clear();
-            cur_seq_ok = tid < hdr->names.size() && fa->fetch(hdr->names[tid], cur_seq);
+            cur_seq_tid = (int) tid;
+            if (next_ready.valid() && next_tid == (int) tid) { cur_seq_ok = next_ready.get(); cur_seq.swap(next_seq); }
+            else { if (next_ready.valid()) next_ready.get(); cur_seq.clear(); cur_seq_ok = tid < hdr->names.size() && fa->fetch(hdr->names[tid], cur_seq); }
         }
         return cur_seq_ok ? &cur_seq : nullptr;
+    }
+    void prefetch(uint32_t tid) {
+        if (next_ready.valid() || (int) tid == cur_seq_tid || tid >= hdr->names.size()) return;
+        next_tid = (int) tid;
+        next_ready = std::async(std::launch::async, [this, tid] { return fa->fetch(hdr->names[tid], next_seq); });
+    }
+    ~Driver() { if (next_ready.valid()) next_ready.wait(); }
+    // a few bases around a chunk end (adjustBounds, common.c:477) without loading the contig; returns the contig's length
+    int64_t window(uint32_t tid, int64_t start, int64_t n, std::string &w) {
+        w.clear();
+        if (tid >= hdr->names.size()) return 0;
+        const FaiEntry *e = fa->find(hdr->names[tid]);
+        if (!e) return 0;
+        fa->fetch_range(*e, start, n, w);
+        return e->len;
     }
     bool sought = false;
     void seek_to(int tid, uint32_t beg) {
@@ -334,7 +351,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         std::vector<Chunk> all;
         {
             ChunkCursor cursor(d.hdr->lens, o.chunkSize, gTid, gPos, gEnd);
-            auto fetch = [&](uint32_t t) { return d.fetch(t); };
+            auto fetch = [&](uint32_t t, int64_t start, int64_t cnt, std::string &w) { return d.window(t, start, cnt, w); };
             Chunk ch;
             while (cursor.next(ch, fetch)) all.push_back(ch);
         }
@@ -372,6 +389,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             while (ci < c1 && all[ci].tid == tid) chunks.push_back(all[ci++]);
             double t_ld = now_s();
             const std::string *ref = d.fetch(tid);
+            if (ci < c1) d.prefetch(all[ci].tid);                  // the next contig is read from the FASTA while this one is processed
             if (!ref) {
                 fprintf(stderr, "faidx_fetch_seq returned %i while trying to fetch the sequence for tid %s:%" PRIu32 "-%" PRIu32 "!\n", -2, d.hdr->names[tid].c_str(), chunks.front().beg, chunks.front().end);
                 fprintf(stderr, "Note that the output will be truncated!\n");
@@ -567,7 +585,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
         std::vector<Chunk> all;
         {
             ChunkCursor cursor(d.hdr->lens, chunkSize, gTid, gPos, gEnd);
-            auto fetch = [&](uint32_t t) { return d.fetch(t); };
+            auto fetch = [&](uint32_t t, int64_t start, int64_t cnt, std::string &w) { return d.window(t, start, cnt, w); };
             Chunk ch;
             while (cursor.next(ch, fetch)) all.push_back(ch);
         }
@@ -608,6 +626,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
             std::vector<uint32_t> bounds;
             while (ci < c1 && all[ci].tid == tid) { if (bounds.empty()) bounds.push_back(all[ci].beg); bounds.push_back(all[ci].end); ++ci; }
             const std::string *ref = d.fetch(tid);
+            if (ci < c1) d.prefetch(all[ci].tid);                  // the next contig is read from the FASTA while this one is processed
             if (!ref) {
                 fprintf(stderr, "faidx_fetch_seq returned %i while trying to fetch the sequence for tid %s:%" PRIu32 "-%" PRIu32 "!\n", -2, d.hdr->names[tid].c_str(), bounds.front(), bounds.back());
                 fprintf(stderr, "Note that the output will be truncated!\n");

@@ -67,15 +67,16 @@ public:
         if (gEnd_ && localEnd > gEnd_) localEnd = gEnd_;
         // adjustBounds, common.c:466-493: look at contig[localEnd-1 .. localEnd+1]
         {
-            const std::string *s = fetch(localTid);
-            int64_t L = s ? (int64_t) s->size() : 0;
+            // fetch(tid, start, n, out) -> length of the contig in the FASTA (0 if absent), out = bases [start, start+n) clamped
             int64_t start = localEnd > 0 ? (int64_t) localEnd - 1 : 0, end = (int64_t) localEnd + 1;
+            std::string w;
+            const int64_t L = fetch(localTid, start, (int64_t) 3, w);
             // faidx_fetch_seq clamping (end inclusive)
             if (start >= L) start = L;
             if (end >= L) end = L - 1;
             int64_t seqlen = end + 1 - start; if (seqlen < 0) seqlen = 0;
-            if (s && seqlen > 1) {
-                const char *q = s->data() + start;
+            if (L > 0 && seqlen > 1 && (int64_t) w.size() >= seqlen) {
+                const char *q = w.data();
                 if (seqlen > 2 && (q[0] & 0x5F) == 'C' && (q[2] & 0x5F) == 'G') localEnd += 2;
                 else if ((q[1] & 0x5F) == 'G') localEnd += 1;
             }

@@ -12,6 +12,7 @@
 #include <stdexcept>
 #include <algorithm>
 #include <zlib.h>
+#include <unistd.h>
 
 namespace mdhost {
 
@@ -398,16 +399,37 @@ public:
     bool fetch(const std::string &name, std::string &out) const {
         const FaiEntry *e = find(name);
         if (!e) return false;
-        out.clear(); out.reserve((size_t) e->len);
-        if (e->len == 0) return true;
-        int64_t nlines = (e->len + e->line_blen - 1) / e->line_blen;
-        int64_t nbytes = (nlines - 1) * e->line_len + (e->len - (nlines - 1) * e->line_blen);
-        std::vector<char> raw((size_t) nbytes);
-        if (fseeko(fp_, e->offset, SEEK_SET) != 0) return false;
-        size_t got = fread(raw.data(), 1, (size_t) nbytes, fp_);
-        for (size_t i = 0; i < got; ++i) { unsigned char c = (unsigned char) raw[i]; if (c > 32 && c < 127) out.push_back((char) c); }
-        if ((int64_t) out.size() > e->len) out.resize((size_t) e->len);
-        return (int64_t) out.size() == e->len;
+        return fetch_range(*e, 0, e->len, out) && (int64_t) out.size() == e->len;
+    }
+    // bases [beg, beg+n) of a contig (clamped to its end), as faidx_fetch_seq returns them.  Reads through its own descriptor
+    // position (pread), so concurrent calls are fine.
+    bool fetch_range(const FaiEntry &e, int64_t beg, int64_t n, std::string &out) const {
+        out.clear();
+        if (beg < 0) beg = 0;
+        if (beg >= e.len || n <= 0) return true;
+        if (beg + n > e.len) n = e.len - beg;
+        const int64_t lb = e.line_blen > 0 ? e.line_blen : e.len, ll = e.line_len >= lb ? e.line_len : lb;
+        const int64_t first_line = beg / lb, last_line = (beg + n - 1) / lb;
+        const int64_t off0 = e.offset + first_line * ll + beg % lb;
+        const int64_t off1 = e.offset + last_line * ll + (beg + n - 1) % lb + 1;
+        std::vector<char> raw((size_t)(off1 - off0));
+        size_t got = 0;
+        while (got < raw.size()) { ssize_t r = pread(fileno(fp_), raw.data() + got, raw.size() - got, (off_t)(off0 + (int64_t) got)); if (r <= 0) break; got += (size_t) r; }
+        out.resize((size_t) n);
+        // fast path: uniform lines — copy line by line, then make sure nothing but sequence characters came along
+        bool clean = got == raw.size();
+        if (clean) {
+            int64_t src = 0, dst = 0, col = beg % lb;
+            while (dst < n) { const int64_t take = std::min<int64_t>(lb - col, n - dst); memcpy(&out[(size_t) dst], raw.data() + src, (size_t) take); dst += take; src += take + (ll - lb); col = 0; }
+            unsigned char bad = 0;
+            for (size_t i = 0; i < out.size(); ++i) { const unsigned char c = (unsigned char) out[i]; bad |= (unsigned char)((c <= 32) | (c >= 127)); }
+            clean = !bad;
+        }
+        if (!clean) {          // irregular file: drop everything that is not a printable character, as the reference's fetch does
+            out.clear();
+            for (size_t i = 0; i < got && (int64_t) out.size() < n; ++i) { unsigned char c = (unsigned char) raw[i]; if (c > 32 && c < 127) out.push_back((char) c); }
+        }
+        return true;
     }
 private:
     void build() {
