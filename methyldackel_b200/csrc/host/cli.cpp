@@ -125,7 +125,7 @@ static int decode_threads(int n, bool given) {
 
 // While the CUDA context is being created, full-speed decoding on every core makes that creation several times slower (both
 // sides fight over the process's address-space lock); a handful of decode threads run ahead until the device is up.
-static int warm_threads(int nthreads) { const char *e = getenv("MD_WARM_THREADS"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > nthreads ? nthreads : v); }
+static int warm_threads(int nthreads) { const char *e = getenv("MD_WARM_THREADS"); int v = e ? atoi(e) : 8; return v < 0 ? 0 : (v > nthreads ? nthreads : v); }
 
 // alignments per device tile (testing knob: small values exercise tile cuts and carried reads on small inputs)
 static size_t tile_reads_default(bool async) { if (const char *e = getenv("MD_TILE_READS")) { long v = atol(e); if (v > 0) return (size_t) v; } return async ? ((size_t) 1 << 17) : ((size_t) 1 << 19); }
@@ -137,6 +137,7 @@ static bool pack_quals_enabled() { const char *e = getenv("MD_QUAL_PACK"); retur
 // context creation running beside them).  Keep such blocks in the arenas instead.
 static void tune_allocator() {
     static bool done = false; if (done) return; done = true;
+    if (getenv("MD_NO_MALLOPT")) return;
     mallopt(M_MMAP_THRESHOLD, 32 << 20); mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_TOP_PAD, 16 << 20);
 }
 

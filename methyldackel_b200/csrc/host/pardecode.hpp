@@ -67,9 +67,9 @@ struct Fragment {
 // their parses), so decoding runs ahead of the consumer — in particular while the CUDA context is still coming up.
 class ParallelBam {
 public:
-    // `warm_threads` > 0 keeps all but that many decode workers asleep until set_active_threads() raises the limit
-    ParallelBam(const std::string &path, int nthreads, int warm_threads = 0) : pool_(nthreads), aux_(std::max(1, std::min(16, nthreads))) {
-        if (warm_threads > 0) pool_.set_active(warm_threads);
+    // `warm_threads` >= 0 keeps all but that many decode workers asleep until set_active_threads() raises the limit
+    ParallelBam(const std::string &path, int nthreads, int warm_threads = -1) : pool_(nthreads), aux_(std::max(1, std::min(16, nthreads))) {
+        if (warm_threads >= 0) pool_.set_active(warm_threads);
         // header through the sequential reader; remember where the records start
         BgzfReader rd(path);
         hdr_ = read_bam_header(rd);
