@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MDGPU_ABI_VERSION 4
+#define MDGPU_ABI_VERSION 5
 
 /* ---- options that reach the hot path: the subset of `Config`
  *      (MethylDackel.h:90-126) read by filter_func / the per-column loop ---- */
@@ -179,6 +179,38 @@ void *md_alloc_pinned(size_t bytes);   /* cudaMallocHost; NULL on failure */
 void md_free_pinned(void *p);
 int md_host_register(void *p, size_t bytes);
 int md_host_unregister(void *p);
+
+/* ---- Device-side BAM decode -------------------------------------------------------------------
+ * Replaces the work inside sam_itr_next (common.c:413; htslib bgzf_read + bam_read1): BGZF block inflate, record framing
+ * and field extraction happen in HBM, and the resulting tiles never exist on the host.  The caller cuts the compressed
+ * file into SEGMENTS of whole BGZF blocks (scanning the 18-byte block headers) and pushes them in file order; each push
+ * reports the runs of records per contig, and the caller asks for one tile per run.  Reads that reach beyond a tile's end
+ * are carried into the next tile of the same contig on the device (the reference re-fetches them per chunk, extract.c:379). */
+typedef struct md_bgzf_block {
+    uint64_t comp_off;     /* offset of the raw-deflate payload (after the 12+XLEN byte header) in the pushed buffer */
+    uint32_t comp_len;     /* payload bytes (block size - header - 8 byte trailer) */
+    uint32_t isize;        /* uncompressed size (BGZF trailer ISIZE) */
+} md_bgzf_block;
+typedef struct md_bam_run {  /* records [start, start+n) of the pushed segment lie on contig `tid`, positions first_pos..last_pos */
+    int32_t tid; uint32_t start, n; int32_t first_pos, last_pos, prev_last_pos;
+} md_bam_run;
+typedef struct md_bam_summary { uint32_t n_records, n_runs; uint64_t inflated_bytes, leftover_bytes; } md_bam_summary;
+typedef struct md_bam_stream md_bam_stream;
+md_bam_stream *md_bam_open(md_ctx *ctx, int32_t n_targets);
+void md_bam_close(md_bam_stream *s);
+void md_bam_reset(md_bam_stream *s);      /* after a seek in the file */
+/* `skip`: offset of the first record in the segment's inflated bytes (only after open/reset: the in-block part of a BAI
+ * virtual offset, or the end of the BAM header); later segments continue the record that straddled in. */
+int md_bam_push(md_bam_stream *s, const void *comp, uint64_t comp_bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip, md_bam_summary *out);
+int md_bam_get_runs(md_bam_stream *s, md_bam_run *runs, uint32_t cap);
+/* One tile = reads carried from the previous tile of this contig (if that tile ended where this one begins) + run `run`
+ * of the last segment (run < 0: carried reads only, to close a contig), restricted to records with pos < keep_hi; then
+ * the extract / mbias pipeline over the owned interval [tile->beg, tile->end) as md_extract_tile / md_mbias_tile. */
+int md_bam_extract_run(md_bam_stream *s, int run, const md_tile_desc *tile, uint32_t keep_hi, md_call *calls, uint64_t capacity, md_tile_stats *stats);
+int md_bam_mbias_run(md_bam_stream *s, int run, const md_tile_desc *tile, uint32_t keep_hi, md_tile_stats *stats);
+/* the tile built last, copied back (for tests: must equal the tile the host decoder builds from the same records) */
+int md_bam_tile_shape(md_bam_stream *s, md_reads_soa *shape);
+int md_bam_tile_fetch(md_bam_stream *s, md_reads_soa *dst, int32_t *rend);
 
 const char *md_last_error(void);
 int md_abi_version(void);

@@ -35,6 +35,15 @@ typedef struct mdh_backend {
     void *(*pinned_alloc)(size_t bytes);
     void  (*pinned_free)(void *p);
     int   (*submit_mbias_tile)(void *be, const md_tile_desc *tile, const md_reads_soa *reads);   /* optional; collected with collect_tile(calls = NULL) */
+    /* optional: device-side BGZF inflate + BAM decode (md_bam_* in mdgpu.h).  When present (and MD_DEVICE_DECODE is not 0)
+     * the sub-commands ship the compressed file in segments of whole BGZF blocks instead of decoding it on host cores. */
+    void *(*bam_open)(void *be, int32_t n_targets);
+    void  (*bam_close)(void *s);
+    void  (*bam_reset)(void *s);
+    int   (*bam_push)(void *s, const void *comp, uint64_t bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip, md_bam_summary *out);
+    int   (*bam_get_runs)(void *s, md_bam_run *runs, uint32_t cap);
+    int   (*bam_extract_run)(void *s, int run, const md_tile_desc *tile, uint32_t keep_hi, md_call *calls, uint64_t cap, md_tile_stats *st);
+    int   (*bam_mbias_run)(void *s, int run, const md_tile_desc *tile, uint32_t keep_hi, md_tile_stats *st);
 } mdh_backend;
 
 /* Same argv conventions as the reference: argv[0] is the sub-command name. */

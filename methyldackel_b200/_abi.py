@@ -82,12 +82,34 @@ PIN_ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t)
 PIN_FREE_FN = C.CFUNCTYPE(None, C.c_void_p)
 
 
+class MdBgzfBlock(C.Structure):
+    _fields_ = [("comp_off", C.c_uint64), ("comp_len", C.c_uint32), ("isize", C.c_uint32)]
+
+
+class MdBamRun(C.Structure):
+    _fields_ = [("tid", C.c_int32), ("start", C.c_uint32), ("n", C.c_uint32), ("first_pos", C.c_int32), ("last_pos", C.c_int32), ("prev_last_pos", C.c_int32)]
+
+
+class MdBamSummary(C.Structure):
+    _fields_ = [("n_records", C.c_uint32), ("n_runs", C.c_uint32), ("inflated_bytes", C.c_uint64), ("leftover_bytes", C.c_uint64)]
+
+
+BAM_OPEN_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int32)
+BAM_CLOSE_FN = C.CFUNCTYPE(None, C.c_void_p)
+BAM_PUSH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(MdBgzfBlock), C.c_uint32, C.c_uint32, C.POINTER(MdBamSummary))
+BAM_RUNS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(MdBamRun), C.c_uint32)
+BAM_EXTRACT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(MdTileDesc), C.c_uint32, C.POINTER(MdCall), C.c_uint64, C.POINTER(MdTileStats))
+BAM_MBIAS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(MdTileDesc), C.c_uint32, C.POINTER(MdTileStats))
+
+
 class MdhBackend(C.Structure):
     _fields_ = [("factory_user", C.c_void_p), ("create", CREATE_FN), ("destroy", DESTROY_FN), ("load_contig", LOAD_CONTIG_FN),
                 ("drop_contig", DROP_CONTIG_FN), ("extract_tile", EXTRACT_TILE_FN), ("set_mbias_chunks", SET_CHUNKS_FN),
                 ("mbias_tile", MBIAS_TILE_FN), ("mbias_hist", MBIAS_HIST_FN), ("last_error", LAST_ERROR_FN),
                 ("submit_tile", SUBMIT_FN), ("collect_tile", COLLECT_FN), ("pinned_alloc", PIN_ALLOC_FN), ("pinned_free", PIN_FREE_FN),
-                ("submit_mbias_tile", SUBMIT_FN)]
+                ("submit_mbias_tile", SUBMIT_FN),
+                ("bam_open", BAM_OPEN_FN), ("bam_close", BAM_CLOSE_FN), ("bam_reset", BAM_CLOSE_FN), ("bam_push", BAM_PUSH_FN),
+                ("bam_get_runs", BAM_RUNS_FN), ("bam_extract_run", BAM_EXTRACT_FN), ("bam_mbias_run", BAM_MBIAS_FN)]
 
 
 _host = None
@@ -156,6 +178,15 @@ def load_gpu():
         g.md_free_pinned.argtypes = [C.c_void_p]
         g.md_host_register.argtypes = [C.c_void_p, C.c_size_t]
         g.md_host_unregister.argtypes = [C.c_void_p]
+        g.md_bam_open.restype = C.c_void_p; g.md_bam_open.argtypes = [C.c_void_p, C.c_int32]
+        g.md_bam_close.argtypes = [C.c_void_p]; g.md_bam_close.restype = None
+        g.md_bam_reset.argtypes = [C.c_void_p]; g.md_bam_reset.restype = None
+        g.md_bam_push.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(MdBgzfBlock), C.c_uint32, C.c_uint32, C.POINTER(MdBamSummary)]
+        g.md_bam_get_runs.argtypes = [C.c_void_p, C.POINTER(MdBamRun), C.c_uint32]
+        g.md_bam_extract_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(MdTileDesc), C.c_uint32, C.POINTER(MdCall), C.c_uint64, C.POINTER(MdTileStats)]
+        g.md_bam_mbias_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(MdTileDesc), C.c_uint32, C.POINTER(MdTileStats)]
+        g.md_bam_tile_shape.argtypes = [C.c_void_p, C.POINTER(MdReadsSoa)]
+        g.md_bam_tile_fetch.argtypes = [C.c_void_p, C.POINTER(MdReadsSoa), C.POINTER(C.c_int32)]
         g.md_last_error.restype = C.c_char_p
         g.md_abi_version.restype = C.c_int
         _gpu = g

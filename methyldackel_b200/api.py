@@ -123,7 +123,12 @@ class _GpuBackend:
                       A.SUBMIT_FN(lambda b, td, r: g.md_submit_tile(b, td, r)),
                       A.COLLECT_FN(lambda b, t, c, cap, st: g.md_collect_tile(b, t, c, cap, st)),
                       A.PIN_ALLOC_FN(lambda n: g.md_alloc_pinned(n)), A.PIN_FREE_FN(lambda q: g.md_free_pinned(q)),
-                      A.SUBMIT_FN(lambda b, t, r: g.md_submit_mbias_tile(b, t, r))]
+                      A.SUBMIT_FN(lambda b, t, r: g.md_submit_mbias_tile(b, t, r)),
+                      A.BAM_OPEN_FN(lambda b, nt: g.md_bam_open(b, nt)), A.BAM_CLOSE_FN(lambda s: g.md_bam_close(s)), A.BAM_CLOSE_FN(lambda s: g.md_bam_reset(s)),
+                      A.BAM_PUSH_FN(lambda s, c, n, bl, nb, sk, o: g.md_bam_push(s, c, n, bl, nb, sk, o)),
+                      A.BAM_RUNS_FN(lambda s, r, cap: g.md_bam_get_runs(s, r, cap)),
+                      A.BAM_EXTRACT_FN(lambda s, run, td, kh, c, cap, st: g.md_bam_extract_run(s, run, td, kh, c, cap, st)),
+                      A.BAM_MBIAS_FN(lambda s, run, td, kh, st: g.md_bam_mbias_run(s, run, td, kh, st))]
         self.be = A.MdhBackend(None, *self._keep)
 
 

@@ -130,6 +130,14 @@ static int warm_threads(int nthreads) { const char *e = getenv("MD_WARM_THREADS"
 // alignments per device tile (testing knob: small values exercise tile cuts and carried reads on small inputs)
 static size_t tile_reads_default(bool async) { if (const char *e = getenv("MD_TILE_READS")) { long v = atol(e); if (v > 0) return (size_t) v; } return async ? ((size_t) 1 << 17) : ((size_t) 1 << 19); }
 
+// Device-side BGZF inflate + BAM decode (md_bam_*): opt-in with MD_DEVICE_DECODE=1 while it is new.
+static bool device_decode_enabled(const mdh_backend *be) {
+    if (!(be->bam_open && be->bam_close && be->bam_reset && be->bam_push && be->bam_get_runs && be->bam_extract_run && be->bam_mbias_run)) return false;
+    const char *e = getenv("MD_DEVICE_DECODE");
+    return e && e[0] == '1';
+}
+static size_t device_segment_bytes() { if (const char *e = getenv("MD_SEGMENT_BYTES")) { long v = atol(e); if (v > 0) return (size_t) v; } return (size_t) 128 << 20; }
+
 static bool pack_quals_enabled() { const char *e = getenv("MD_QUAL_PACK"); return !(e && e[0] == '0'); }
 
 // The decode workers allocate and free multi-megabyte buffers at a high rate; glibc's default turns each of those into an
@@ -172,6 +180,7 @@ private:
 struct Driver {
     const mdh_backend *be; void *dev = nullptr;
     std::unique_ptr<ParallelBam> bam; std::unique_ptr<Fasta> fa; BaiIndex bai; bool have_bai = false;
+    BamHeader own_hdr; uint64_t start_voff = 0;              // device-decode mode: no host decoder, just the header
     std::shared_ptr<Fragment> frag; size_t frag_i = 0;      // decode cursor shared by consecutive FragTilers
     const BamHeader *hdr = nullptr;
     std::string cur_seq; int cur_seq_tid = -1; bool cur_seq_ok = false;
@@ -210,6 +219,198 @@ struct Driver {
     }
 };
 }  // namespace
+
+
+// ---- device-decode drivers --------------------------------------------------------------------------------------
+// The compressed file goes to the device in segments of whole BGZF blocks (md_bam_push); every push reports the runs of
+// records per contig and one tile is requested per run.  A contig that may continue in the next segment is cut at the
+// position of the run's last record (those reads, and every read reaching beyond the cut, are carried into the next tile on
+// the device); a contig that ends inside the segment gets its final tile.  The reference's chunks are replayed over the
+// returned md_call records exactly as in the host-decode path.
+namespace {
+struct ContigJob { uint32_t tid, rbeg, rend; std::vector<Chunk> chunks; };
+
+template <class OpenContig, class Tile, class CloseContig>
+int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamName, const std::vector<ContigJob> &jobs, OpenContig &&open_contig, Tile &&tile, CloseContig &&close_contig) {
+    if (jobs.empty()) return 0;
+    BgzfSegmenter seg(bamName);
+    uint64_t voff = d.start_voff;
+    if (d.have_bai) { bool found; uint64_t o = d.bai.start_offset((int) jobs[0].tid, jobs[0].rbeg, found); if (found && o) voff = o; }
+    seg.seek(voff >> 16);
+    uint32_t skip = (uint32_t)(voff & 0xffff);
+    be->bam_reset(bs);
+    const size_t target = device_segment_bytes();
+    size_t cj = 0; bool open = false; uint32_t open_beg = 0; int rc = 0;
+    std::vector<md_bgzf_block> blocks; std::vector<md_bam_run> runs;
+    // finish job cj: its last tile comes from carried reads only (run -1); a contig that never had a record just gets its chunks written
+    auto finish = [&]() -> int {
+        const ContigJob &J = jobs[cj];
+        int r = 0;
+        if (!open) { r = open_contig(J); if (r) return r; open_beg = J.rbeg; }
+        md_tile_desc td{(int32_t) J.tid, open_beg, J.rend, 0, 0};
+        r = tile(J, -1, td, open);                       // nothing to compute if the contig was never opened on the device
+        if (r) return r;
+        r = close_contig(J);
+        open = false; ++cj;
+        return r;
+    };
+    bool done = false;
+    while (!done && rc == 0) {
+        const uint8_t *base; size_t bytes;
+        double t0 = now_s();
+        if (!seg.next(target, base, bytes, blocks)) break;
+        md_bam_summary sum;
+        int r = be->bam_push(bs, base, bytes, blocks.data(), (uint32_t) blocks.size(), skip, &sum);
+        skip = 0;
+        g_stats.t_decode_s += now_s() - t0;
+        if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+        g_stats.n_records += sum.n_records;
+        runs.resize(sum.n_runs);
+        if (sum.n_runs) be->bam_get_runs(bs, runs.data(), sum.n_runs);
+        const bool file_end = seg.eof();
+        for (size_t k = 0; k < runs.size() && !done && rc == 0; ++k) {
+            const md_bam_run &run = runs[k];
+            if (run.tid < 0) { done = true; break; }                                   // unmapped records close a sorted file
+            while (cj < jobs.size() && (int32_t) jobs[cj].tid < run.tid && rc == 0) rc = finish();
+            if (rc || cj >= jobs.size()) { done = true; break; }
+            const ContigJob &J = jobs[cj];
+            if ((int32_t) J.tid > run.tid) continue;                                   // a contig this run does not cover
+            if ((int64_t) run.first_pos >= (int64_t) J.rend) { rc = finish(); if (cj >= jobs.size()) done = true; continue; }
+            if (!open) { rc = open_contig(J); if (rc) break; open = true; open_beg = J.rbeg; }
+            const bool may_continue = (k + 1 == runs.size()) && !file_end && (int64_t) run.last_pos < (int64_t) J.rend;
+            if (may_continue) {
+                uint32_t cut = (uint32_t) std::max<int64_t>(run.last_pos, (int64_t) open_beg);
+                md_tile_desc td{(int32_t) J.tid, open_beg, cut, 0, 0};
+                rc = tile(J, (int) k, td, true);
+                open_beg = cut;
+            } else {
+                md_tile_desc td{(int32_t) J.tid, open_beg, J.rend, 0, 0};
+                rc = tile(J, (int) k, td, true);
+                if (!rc) rc = close_contig(J);
+                open = false; ++cj;
+                if (cj >= jobs.size()) done = true;
+            }
+        }
+    }
+    while (rc == 0 && cj < jobs.size()) rc = finish();
+    return rc;
+}
+
+std::vector<ContigJob> contig_jobs(const std::vector<Chunk> &all, size_t c0, size_t c1) {
+    std::vector<ContigJob> jobs;
+    for (size_t ci = c0; ci < c1; ++ci) {
+        if (jobs.empty() || jobs.back().tid != all[ci].tid) { ContigJob j; j.tid = all[ci].tid; j.rbeg = all[ci].beg; j.rend = all[ci].end; jobs.push_back(j); }
+        jobs.back().chunks.push_back(all[ci]); jobs.back().rend = all[ci].end;
+    }
+    return jobs;
+}
+}  // namespace
+
+static int extract_device_decode(Driver &d, const mdh_backend *be, const char *bamName, const std::vector<Chunk> &all, size_t c0, size_t c1, ExtractWriter &writer, SerialWorker &out_thread) {
+    void *bs = be->bam_open(d.dev, (int32_t) d.hdr->names.size());
+    if (!bs) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+    std::vector<ContigJob> jobs = contig_jobs(all, c0, c1);
+    const std::string *ref = nullptr; bool loaded = false;
+    std::vector<md_call> calls; size_t calls_head = 0, next_chunk = 0;
+    PodVec<md_call> tile_calls;
+    auto absorb = [&](const ContigJob &J, uint32_t done_upto, bool last) {
+        while (next_chunk < J.chunks.size() && (J.chunks[next_chunk].end <= done_upto || last)) {
+            const Chunk k = J.chunks[next_chunk];
+            size_t a = calls_head; while (a < calls.size() && calls[a].pos < k.beg) ++a;
+            size_t b = a; while (b < calls.size() && calls[b].pos < k.end) ++b;
+            auto part = std::make_shared<std::vector<md_call>>(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b);
+            const char *cname = d.hdr->names[J.tid].c_str();
+            const std::string *rp = ref;
+            out_thread.post([&writer, cname, rp, k, part] { writer.process_chunk(cname, *rp, k.beg, k.end, part->data(), part->size()); });
+            calls_head = b; ++next_chunk;
+        }
+        if (calls_head > (1u << 20)) { calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
+    };
+    size_t job_i = 0;
+    auto open_contig = [&](const ContigJob &J) -> int {
+        ref = d.fetch(J.tid);
+        while (job_i < jobs.size() && jobs[job_i].tid != J.tid) ++job_i;
+        if (job_i + 1 < jobs.size()) d.prefetch(jobs[job_i + 1].tid);
+        calls.clear(); calls_head = 0; next_chunk = 0; loaded = false;
+        if (!ref) {
+            fprintf(stderr, "faidx_fetch_seq returned %i while trying to fetch the sequence for tid %s:%" PRIu32 "-%" PRIu32 "!\n", -2, d.hdr->names[J.tid].c_str(), J.chunks.front().beg, J.chunks.front().end);
+            fprintf(stderr, "Note that the output will be truncated!\n");
+            return 0;
+        }
+        return 0;
+    };
+    auto tile = [&](const ContigJob &J, int run, const md_tile_desc &td, bool on_device) -> int {
+        if (!ref) return 0;
+        if (on_device) {
+            if (!loaded) { if (be->load_contig(d.dev, (int32_t) J.tid, ref->data(), (uint32_t) ref->size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; } loaded = true; }
+            md_tile_desc t = td; if (t.end > ref->size()) t.end = (uint32_t) ref->size(); if (t.beg > t.end) t.beg = t.end;
+            const uint64_t cap = (uint64_t)(t.end - t.beg) + 16;
+            tile_calls.clear(); tile_calls.grow(cap);
+            md_tile_stats st;
+            double t0 = now_s();
+            int r = be->bam_extract_run(bs, run, &t, J.rend, tile_calls.data(), cap, &st);
+            g_stats.t_device_s += now_s() - t0;
+            if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+            calls.insert(calls.end(), tile_calls.data(), tile_calls.data() + (ptrdiff_t) st.n_calls);
+            g_stats.n_calls += st.n_calls; g_stats.n_tiles++;
+        }
+        absorb(J, td.end, false);
+        return 0;
+    };
+    auto close_contig = [&](const ContigJob &J) -> int {
+        if (ref) absorb(J, J.rend, true);
+        out_thread.drain();                                     // the next contig replaces *ref
+        if (loaded) be->drop_contig(d.dev, (int32_t) J.tid);
+        loaded = false;
+        return 0;
+    };
+    int rc = drive_segments(d, be, bs, bamName, jobs, open_contig, tile, close_contig);
+    be->bam_close(bs);
+    return rc;
+}
+
+
+static int mbias_device_decode(Driver &d, const mdh_backend *be, const char *bamName, const std::vector<Chunk> &all, size_t c0, size_t c1) {
+    void *bs = be->bam_open(d.dev, (int32_t) d.hdr->names.size());
+    if (!bs) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+    std::vector<ContigJob> jobs = contig_jobs(all, c0, c1);
+    const std::string *ref = nullptr; bool loaded = false; bool truncated = false;
+    size_t job_i = 0;
+    auto open_contig = [&](const ContigJob &J) -> int {
+        if (truncated) { ref = nullptr; return 0; }
+        ref = d.fetch(J.tid);
+        while (job_i < jobs.size() && jobs[job_i].tid != J.tid) ++job_i;
+        if (job_i + 1 < jobs.size()) d.prefetch(jobs[job_i + 1].tid);
+        loaded = false;
+        if (!ref) {
+            fprintf(stderr, "faidx_fetch_seq returned %i while trying to fetch the sequence for tid %s:%" PRIu32 "-%" PRIu32 "!\n", -2, d.hdr->names[J.tid].c_str(), J.chunks.front().beg, J.chunks.front().end);
+            fprintf(stderr, "Note that the output will be truncated!\n");
+            truncated = true;                                  // MBias.c:152 returns from the worker
+        }
+        return 0;
+    };
+    auto tile = [&](const ContigJob &J, int run, const md_tile_desc &td, bool on_device) -> int {
+        if (!ref || !on_device) return 0;
+        if (!loaded) {
+            std::vector<uint32_t> bounds; bounds.push_back(J.chunks.front().beg); for (auto &k : J.chunks) bounds.push_back(k.end);
+            if (be->load_contig(d.dev, (int32_t) J.tid, ref->data(), (uint32_t) ref->size()) != 0 ||
+                be->set_mbias_chunks(d.dev, (int32_t) J.tid, bounds.data(), (uint32_t) bounds.size() - 1) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+            loaded = true;
+        }
+        md_tile_desc t = td; if (t.end > ref->size()) t.end = (uint32_t) ref->size(); if (t.beg > t.end) t.beg = t.end;
+        md_tile_stats st;
+        double t0 = now_s();
+        int r = be->bam_mbias_run(bs, run, &t, J.rend, &st);
+        g_stats.t_device_s += now_s() - t0;
+        if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+        g_stats.n_tiles++;
+        return 0;
+    };
+    auto close_contig = [&](const ContigJob &J) -> int { if (loaded) be->drop_contig(d.dev, (int32_t) J.tid); loaded = false; return 0; };
+    int rc = drive_segments(d, be, bs, bamName, jobs, open_contig, tile, close_contig);
+    be->bam_close(bs);
+    return rc;
+}
 
 extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     ExtractOptions o;
@@ -291,9 +492,11 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
 
     Driver d; d.be = be;
     const char *fastaName = argv[optind], *bamName = argv[optind + 1];
-    try { { const int nt = decode_threads(nThreads, threads_given); d.bam.reset(new ParallelBam(bamName, nt, warm_threads(nt))); } }
-    catch (std::exception &e) { fprintf(stderr, "Couldn't open %s for reading!\n", bamName); return -4; }
-    d.hdr = &d.bam->header();
+    const bool dev_decode = device_decode_enabled(be) && !(minConvEff > 0.0);
+    try {
+        if (dev_decode) { BgzfReader rd(bamName); d.own_hdr = read_bam_header(rd); d.start_voff = rd.tell(); d.hdr = &d.own_hdr; }
+        else { const int nt = decode_threads(nThreads, threads_given); d.bam.reset(new ParallelBam(bamName, nt, warm_threads(nt))); d.hdr = &d.bam->header(); }
+    } catch (std::exception &e) { fprintf(stderr, "Couldn't open %s for reading!\n", bamName); return -4; }
     d.have_bai = load_bai(bamName, d.bai);
     try { d.fa.reset(new Fasta(fastaName)); }
     catch (std::exception &e) { fprintf(stderr, "Couldn't open the index for %s!\n", fastaName); return -4; }
@@ -364,6 +567,12 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             for (size_t k = 0; k < all.size(); ++k) { if (acc >= lo && c0 == all.size()) c0 = k; if (acc >= hi) { c1 = k; break; } acc += all[k].end - all[k].beg; }
             if (c0 > c1) c0 = c1;
         }
+        if (dev_decode) {
+            d.dev = dev_future.get(); dev_join.taken = true;
+            mark("device joined");
+            if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+            rc = extract_device_decode(d, be, bamName, all, c0, c1, writer, out_thread);
+        } else {
         // tile ring: with an asynchronous back end, tiles live in page-locked memory and up to two are in flight
         // while the next one is being decoded (decode || H2D || kernels || D2H)
         const bool use_async = be->submit_tile && be->collect_tile;
@@ -379,7 +588,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         PodVec<md_call> tile_calls;                              // collect target (plain capacity, never value-initialised)
         mark("tile ring reserved");
         d.dev = dev_future.get(); dev_join.taken = true;
-        d.bam->set_active_threads(d.bam->threads());
+        if (d.bam) d.bam->set_active_threads(d.bam->threads());
         mark("device joined");
         if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
         size_t ci = c0;
@@ -483,11 +692,12 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             mark("contig written");
             be->drop_contig(d.dev, (int32_t) tid);
         }
+        }   // host decode
     }
     out_thread.drain();
     g_stats.t_format_s = out_thread.busy_seconds();
     if (g_marks) fprintf(stderr, "[md-timing] calling thread: phred packing %.3f, contig load %.3f, call hand-over %.3f, writer drain %.3f, result buffer %.3f\n", g_acc[0], g_acc[1], g_acc[2], g_acc[3], g_acc[4]);
-    if (g_marks) fprintf(stderr, "[md-timing] record chains: %zu jobs adopted from the inflating worker, %zu walked by the stitcher\n", d.bam->jobs_adopted(), d.bam->jobs_walked());
+    if (g_marks && d.bam) fprintf(stderr, "[md-timing] record chains: %zu jobs adopted from the inflating worker, %zu walked by the stitcher\n", d.bam->jobs_adopted(), d.bam->jobs_walked());
     be->destroy(d.dev);
     mark("device destroyed");
     g_stats.n_variant_positions = writer.n_variant_positions();
@@ -560,9 +770,11 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
 
     Driver d; d.be = be;
     const char *fastaName = argv[optind], *bamName = argv[optind + 1];
-    try { { const int nt = decode_threads(nThreads, threads_given); d.bam.reset(new ParallelBam(bamName, nt, warm_threads(nt))); } }
-    catch (std::exception &e) { fprintf(stderr, "Couldn't open %s for reading!\n", bamName); return -4; }
-    d.hdr = &d.bam->header();
+    const bool dev_decode = device_decode_enabled(be) && !(false);
+    try {
+        if (dev_decode) { BgzfReader rd(bamName); d.own_hdr = read_bam_header(rd); d.start_voff = rd.tell(); d.hdr = &d.own_hdr; }
+        else { const int nt = decode_threads(nThreads, threads_given); d.bam.reset(new ParallelBam(bamName, nt, warm_threads(nt))); d.hdr = &d.bam->header(); }
+    } catch (std::exception &e) { fprintf(stderr, "Couldn't open %s for reading!\n", bamName); return -4; }
     d.have_bai = load_bai(bamName, d.bai);
     try { d.fa.reset(new Fasta(fastaName)); }
     catch (std::exception &e) { fprintf(stderr, "Couldn't open the index for %s!\n", fastaName); return -4; }
@@ -598,6 +810,11 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
             for (size_t k = 0; k < all.size(); ++k) { if (acc >= lo && c0 == all.size()) c0 = k; if (acc >= hi) { c1 = k; break; } acc += all[k].end - all[k].beg; }
             if (c0 > c1) c0 = c1;
         }
+        if (dev_decode) {
+            d.dev = dev_future.get(); dev_join.taken = true;
+            if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+            rc = mbias_device_decode(d, be, bamName, all, c0, c1);
+        } else {
         // tile ring as in extract: page-locked tiles, up to three in flight when the back end is asynchronous
         const bool use_async = be->submit_mbias_tile && be->collect_tile;
         TileAlloc pin; if (use_async && be->pinned_alloc && be->pinned_free) { pin.alloc = be->pinned_alloc; pin.release = be->pinned_free; }
@@ -608,7 +825,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
         SoaTile carry;
         mark("tile ring reserved");
         d.dev = dev_future.get(); dev_join.taken = true;
-        d.bam->set_active_threads(d.bam->threads());
+        if (d.bam) d.bam->set_active_threads(d.bam->threads());
         if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
         std::vector<int> flight;
         auto collect_one = [&]() -> int {
@@ -666,6 +883,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
             while (rc == 0 && !flight.empty()) rc = collect_one();       // the contig (and its chunk table) is dropped next
             be->drop_contig(d.dev, (int32_t) tid);
         }
+        }   // host decode
     }
     std::vector<uint32_t> hist((size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2, 0); int32_t lens[4] = {0, 0, 0, 0};
     if (rc == 0 && be->mbias_hist(d.dev, hist.data(), lens) != 0) rc = -20;

@@ -315,6 +315,49 @@ private:
     std::deque<std::shared_ptr<Job>> jobs_;
 };
 
+// Cuts the mapped BAM into segments of whole BGZF blocks for the device decoder (md_bam_push): only the 18-byte block
+// headers are read on the host.
+class BgzfSegmenter {
+public:
+    explicit BgzfSegmenter(const std::string &path) {
+        fd_ = ::open(path.c_str(), O_RDONLY);
+        if (fd_ < 0) throw std::runtime_error("Couldn't open " + path + " for reading!");
+        struct stat st;
+        if (fstat(fd_, &st) != 0 || st.st_size <= 0) { ::close(fd_); throw std::runtime_error("Couldn't stat " + path); }
+        size_ = (size_t) st.st_size;
+        void *m = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+        if (m == MAP_FAILED) { ::close(fd_); throw std::runtime_error("Couldn't map " + path); }
+        map_ = (const uint8_t *) m;
+        madvise((void *) map_, size_, MADV_SEQUENTIAL);
+    }
+    ~BgzfSegmenter() { if (map_) munmap((void *) map_, size_); if (fd_ >= 0) ::close(fd_); }
+    void seek(uint64_t file_off) { off_ = (size_t) file_off; }
+    bool eof() const { return off_ + 18 > size_; }
+    // next segment of about `target` compressed bytes: pointer + length, block table with payload offsets relative to it
+    bool next(size_t target, const uint8_t *&base, size_t &bytes, std::vector<md_bgzf_block> &blocks) {
+        blocks.clear();
+        base = map_ + off_; size_t used = 0;
+        while (off_ + used + 18 <= size_) {
+            const uint8_t *p = map_ + off_ + used;
+            if (p[0] != 31 || p[1] != 139 || !(p[3] & 4)) throw std::runtime_error("not a BGZF block");
+            int xlen = p[10] | (p[11] << 8), bsize = -1;
+            if (off_ + used + 12 + (size_t) xlen > size_) throw std::runtime_error("truncated BGZF header");
+            for (int o = 0; o + 4 <= xlen;) { int slen = p[12 + o + 2] | (p[12 + o + 3] << 8); if (p[12 + o] == 'B' && p[12 + o + 1] == 'C' && slen == 2) bsize = p[12 + o + 4] | (p[12 + o + 5] << 8); o += 4 + slen; }
+            if (bsize < 0) throw std::runtime_error("BGZF block without BC field");
+            const size_t bs = (size_t) bsize + 1;
+            if (off_ + used + bs > size_ || bs < (size_t) 12 + xlen + 8) throw std::runtime_error("truncated BGZF block");
+            md_bgzf_block b; b.comp_off = used + 12 + (size_t) xlen; b.comp_len = (uint32_t)(bs - 12 - (size_t) xlen - 8); b.isize = le32(p + bs - 4);
+            blocks.push_back(b);
+            used += bs;
+            if (used >= target) break;
+        }
+        bytes = used; off_ += used;
+        return !blocks.empty();
+    }
+private:
+    int fd_ = -1; const uint8_t *map_ = nullptr; size_t size_ = 0, off_ = 0;
+};
+
 // Same contract as Tiler (tiles.hpp), fed by fragments.  The caller's thread only scans positions to decide which runs of
 // records belong to the tile; the column copies of those runs are done on the decode pool.
 class FragTiler {

@@ -1285,3 +1285,5 @@ extern "C" int md_host_unregister(void *p) { if (!p) return 0; CK(cudaHostUnregi
 extern "C" int md_last_timing(md_ctx *c, float out[5]) { for (int k = 0; k < 5; ++k) out[k] = c->last->timing[k]; return 0; }
 extern "C" uint64_t md_launch_count(md_ctx *c) { return c->launches; }
 extern "C" void *md_stream(md_ctx *c) { return (void *) c->lanes[0].stream; }
+
+#include "bamdev.cu"

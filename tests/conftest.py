@@ -26,6 +26,7 @@ def built():
     _run(["make", "-s", "-C", os.path.join(ROOT, "methyldackel_b200", "csrc"), "host"])
     _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
     _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    _run(["make", "-s", "-C", os.path.join(ROOT, "tests", "native")])
     return {
         "ref_bin": os.path.join(ROOT, "oracle", "_ref", "MethylDackel"),
         "mdsynth": os.path.join(ROOT, "methyldackel_b200", "lib", "mdsynth"),

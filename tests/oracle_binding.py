@@ -29,10 +29,32 @@ def lib():
     return _lib
 
 
+_emu = None
+
+
+def emu():
+    """tests/native/libmdemu.so — CPU emulation of md_bam_* (built by the `built` fixture / __graft_entry__.build())."""
+    global _emu
+    if _emu is None:
+        e = C.CDLL(os.path.join(ROOT, "tests", "native", "libmdemu.so"))
+        e.emu_bam_open.restype = C.c_void_p; e.emu_bam_open.argtypes = [C.c_int32, A.EXTRACT_TILE_FN, A.MBIAS_TILE_FN, C.c_void_p]
+        e.emu_bam_close.argtypes = [C.c_void_p]; e.emu_bam_close.restype = None
+        e.emu_bam_reset.argtypes = [C.c_void_p]; e.emu_bam_reset.restype = None
+        e.emu_bam_push.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(A.MdBgzfBlock), C.c_uint32, C.c_uint32, C.POINTER(A.MdBamSummary)]
+        e.emu_bam_get_runs.argtypes = [C.c_void_p, C.POINTER(A.MdBamRun), C.c_uint32]
+        e.emu_bam_extract_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(A.MdTileDesc), C.c_uint32, C.POINTER(A.MdCall), C.c_uint64, C.POINTER(A.MdTileStats)]
+        e.emu_bam_mbias_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(A.MdTileDesc), C.c_uint32, C.POINTER(A.MdTileStats)]
+        e.emu_bam_tile_view.argtypes = [C.c_void_p, C.POINTER(A.MdReadsSoa)]
+        e.emu_bam_fixups.restype = C.c_uint64; e.emu_bam_fixups.argtypes = [C.c_void_p]
+        e.emu_last_error.restype = C.c_char_p
+        _emu = e
+    return _emu
+
+
 class OracleBackend:
     """mdh_backend whose slots call the oracle port. Keeps the callbacks alive."""
 
-    def __init__(self):
+    def __init__(self, device_decode=False):
         o = lib()
         self.state = {}
         st = self.state
@@ -82,6 +104,18 @@ class OracleBackend:
                       A.EXTRACT_TILE_FN(extract_tile), A.SET_CHUNKS_FN(set_chunks), A.MBIAS_TILE_FN(mbias_tile), A.MBIAS_HIST_FN(mbias_hist),
                       A.LAST_ERROR_FN(last_error)]
         self.be = A.MdhBackend(None, *self._keep)      # async slots stay NULL: the driver then runs tile by tile
+        if device_decode:
+            # md_bam_* emulated on the CPU (tests/native/mdemu.cpp: the kernels' own per-thread bodies in plain loops); the
+            # tiles it assembles go to the oracle through the two callbacks above
+            e = emu()
+            ex_cb, mb_cb = self._keep[4], self._keep[6]
+            extra = [A.BAM_OPEN_FN(lambda b, nt: e.emu_bam_open(nt, ex_cb, mb_cb, b)), A.BAM_CLOSE_FN(lambda s_: e.emu_bam_close(s_)), A.BAM_CLOSE_FN(lambda s_: e.emu_bam_reset(s_)),
+                     A.BAM_PUSH_FN(lambda s_, c, n, bl, nb, sk, o_: e.emu_bam_push(s_, c, n, bl, nb, sk, o_)),
+                     A.BAM_RUNS_FN(lambda s_, r, cap: e.emu_bam_get_runs(s_, r, cap)),
+                     A.BAM_EXTRACT_FN(lambda s_, run, td, kh, c, cap, st_: e.emu_bam_extract_run(s_, run, td, kh, c, cap, st_)),
+                     A.BAM_MBIAS_FN(lambda s_, run, td, kh, st_: e.emu_bam_mbias_run(s_, run, td, kh, st_))]
+            self._keep += extra
+            self.be.bam_open, self.be.bam_close, self.be.bam_reset, self.be.bam_push, self.be.bam_get_runs, self.be.bam_extract_run, self.be.bam_mbias_run = extra
 
 
 def run_host_main(which, argv, backend):
