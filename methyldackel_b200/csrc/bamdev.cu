@@ -96,6 +96,7 @@ struct md_bam_stream {
     // page-locked mailbox: [0] n_runs, [1] inflate/parse error, [2] chain-check flag, [3] last_pos, [4..5] final exit, [6..7] n_records(total)
     uint32_t *h_small = nullptr;
     Sz4 *h_tot = nullptr;
+    double t_push[8] = {0}, t_tile[8] = {0}; uint64_t n_push = 0, n_tiles = 0, comp_total = 0, infl_total = 0, rec_total = 0;
 };
 
 extern "C" md_bam_stream *md_bam_open(md_ctx *c, int32_t n_targets) {
@@ -110,6 +111,9 @@ extern "C" md_bam_stream *md_bam_open(md_ctx *c, int32_t n_targets) {
 extern "C" void md_bam_close(md_bam_stream *s) {
     if (!s) return;
     cudaSetDevice(s->c->device); sync_all(s->c);
+    if (getenv("MD_TIMING"))
+        fprintf(stderr, "[md-timing] device decode: %llu segments, %.1f MB compressed -> %.1f MB, %llu records; H2D %.2f ms, inflate %.2f ms, record chains %.2f ms, offsets+heads+runs %.2f ms; %llu tiles: sizes+scan %.2f ms, gather %.2f ms\n",
+                (unsigned long long) s->n_push, s->comp_total / 1e6, s->infl_total / 1e6, (unsigned long long) s->rec_total, s->t_push[0], s->t_push[1], s->t_push[2], s->t_push[3], (unsigned long long) s->n_tiles, s->t_tile[0], s->t_tile[1]);
     DevBuf *bufs[] = {&s->comp, &s->blk, &s->uoff, &s->ubuf, &s->scan, &s->cnt, &s->base, &s->rec_off, &s->tid, &s->pos, &s->rend, &s->runs, &s->small, &s->cub_tmp, &s->sz, &s->off, &s->tile[0].buf, &s->tile[1].buf};
     for (DevBuf *b : bufs) b->release();
     if (s->h_small) cudaFreeHost(s->h_small);
@@ -121,6 +125,15 @@ extern "C" void md_bam_reset(md_bam_stream *s) {       // after a seek: forget t
 }
 
 static const uint32_t BAM_MAX_RUNS = 1u << 16;
+
+// MD_TIMING=1: per-stage device times of the decode (CUDA events on the lane's stream), accumulated per stream object
+struct BamTimer {
+    bool on; cudaStream_t st; cudaEvent_t ev[8]; int n = 0;
+    explicit BamTimer(cudaStream_t s) : on(getenv("MD_TIMING") != nullptr), st(s) { if (on) for (auto &e : ev) cudaEventCreate(&e); }
+    ~BamTimer() { if (on) for (auto &e : ev) cudaEventDestroy(e); }
+    void tick() { if (on && n < 8) cudaEventRecord(ev[n++], st); }
+    void add(double *acc) { if (!on) return; cudaEventSynchronize(ev[n - 1]); for (int k = 0; k + 1 < n; ++k) { float ms = 0; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); acc[k] += ms; } }
+};
 
 extern "C" int md_bam_push(md_bam_stream *s, const void *comp, uint64_t comp_bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip, md_bam_summary *out) {
     md_ctx *c = s->c;
@@ -150,6 +163,7 @@ extern "C" int md_bam_push(md_bam_stream *s, const void *comp, uint64_t comp_byt
     if (s->comp.reserve(comp_bytes + 64) || s->blk.reserve((size_t) n_blocks * sizeof(md_bgzf_block) + 16) || s->uoff.reserve((size_t)(n_blocks + 1) * 8) ||
         s->ubuf.reserve(U + 64) || s->scan.reserve((size_t) n_blocks * sizeof(BlockScan) + 16) || s->cnt.reserve((size_t) n_blocks * 4 + 16) || s->base.reserve((size_t) n_blocks * 4 + 16) ||
         s->runs.reserve((size_t) BAM_MAX_RUNS * sizeof(md_bam_run))) { keep.release(); return -100; }
+    BamTimer tm(st); tm.tick();
     if (s->leftover) { CK(cudaMemcpyAsync((uint8_t *) s->ubuf.p + D0, keep.p, s->leftover, cudaMemcpyDeviceToDevice, st)); }
     CK(cudaMemcpyAsync(s->comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync((uint8_t *) s->comp.p + comp_bytes, 0, 64, st));
@@ -159,8 +173,10 @@ extern "C" int md_bam_push(md_bam_stream *s, const void *comp, uint64_t comp_byt
     uint32_t *d_small = (uint32_t *) s->small.p;       // [0] n_runs [1] err [2] bad [3] last_pos [4,5] final_exit
     const uint8_t *u = (const uint8_t *) s->ubuf.p;
     const unsigned long long first = D0 + (s->leftover ? 0 : skip);
+    tm.tick();
     if (n_blocks) {
         inflate_kernel<<<(n_blocks + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, 0, st>>>((const uint8_t *) s->comp.p, (const md_bgzf_block *) s->blk.p, (const unsigned long long *) s->uoff.p, (uint8_t *) s->ubuf.p, n_blocks, (int *)(d_small + 1));
+        tm.tick();
         const uint32_t g = (n_blocks + 127) / 128;
         // block 0's slice starts at D0 so that the straddling record is part of its chain
         unsigned long long d0 = D0;
@@ -175,6 +191,7 @@ extern "C" int md_bam_push(md_bam_stream *s, const void *comp, uint64_t comp_byt
         cub::DeviceScan::ExclusiveSum(s->cub_tmp.p, tmp, (const uint32_t *) s->cnt.p, (uint32_t *) s->base.p, (int) n_blocks, st);
         c->launches += 6;
     }
+    tm.tick();
     // number of records = base[last] + cnt[last]
     uint32_t last2[2] = {0, 0};
     if (n_blocks) {
@@ -198,6 +215,7 @@ extern "C" int md_bam_push(md_bam_stream *s, const void *comp, uint64_t comp_byt
         head_kernel<<<gr, 256, 0, st>>>(u, (const unsigned long long *) s->rec_off.p, n, (int32_t *) s->tid.p, (int32_t *) s->pos.p, (int32_t *) s->rend.p, (int *)(d_small + 1));
         runs_kernel<<<gr, 256, 0, st>>>((const int32_t *) s->tid.p, (const int32_t *) s->pos.p, n, (md_bam_run *) s->runs.p, BAM_MAX_RUNS, d_small, (int32_t *)(d_small + 3));
         c->launches += 3;
+        tm.tick();
         CK(cudaMemcpyAsync(s->h_small, d_small, 32, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (s->h_small[1]) { g_err = "malformed BAM record"; return -5; }
@@ -213,6 +231,7 @@ extern "C" int md_bam_push(md_bam_stream *s, const void *comp, uint64_t comp_byt
             r.last_pos = k + 1 < nr ? s->runs_host[k + 1].prev_last_pos : (int32_t) s->h_small[3];
         }
     }
+    tm.add(s->t_push); s->n_push++; s->comp_total += comp_bytes; s->infl_total += tot; s->rec_total += n;
     CK(cudaGetLastError());
     out->n_records = n; out->n_runs = (uint32_t) s->runs_host.size(); out->inflated_bytes = tot; out->leftover_bytes = s->leftover;
     return 0;
@@ -246,6 +265,7 @@ static int bam_build_tile(md_bam_stream *s, int run, const md_tile_desc *t, uint
     S.keep_lo = t->beg; S.keep_hi = keep_hi;
     const uint32_t m = S.n_prev + S.n_own;
     N.valid = false; N.n = 0;
+    BamTimer tm(st); tm.tick();
     Sz4 tot; tot.x = tot.y = tot.z = tot.w = 0;
     const Sz4 zero4 = tot;
     if (m) {
@@ -261,6 +281,7 @@ static int bam_build_tile(md_bam_stream *s, int run, const md_tile_desc *t, uint
         tot = U4Sum()(s->h_tot[0], s->h_tot[1]);
         c->launches += 2;
     }
+    tm.tick();
     const size_t n = tot.x;
     size_t szs[13] = {n * 4, n * 2, n, n, n * 4, (n + 1) * 4, n * 4, n * 4, n * 8, n * 4, (size_t) tot.y * 4, (size_t) tot.z * 4, (size_t) tot.w * 8};
     size_t offs[13], total = 0;
@@ -277,6 +298,7 @@ static int bam_build_tile(md_bam_stream *s, int run, const md_tile_desc *t, uint
     v.n = (uint32_t) n; v.seq_words = tot.z; v.qual_words = tot.w; v.qbits = 8;
     v.pos = D.pos; v.flag = D.flag; v.mapq = D.mapq; v.aux = D.aux; v.l_qseq = D.l_qseq; v.cigar_off = D.cigar_off; v.seq_off = D.seq_off; v.qual_off = D.qual_off;
     v.frag_key = D.frag_key; v.cigar = D.cigar; v.seq = D.seq; v.qual = D.qual;
+    tm.tick(); tm.add(s->t_tile); s->n_tiles++;
     N.rend = D.rend; N.n = (uint32_t) n; N.tid = t->tid; N.cut = t->end; N.valid = true;
     s->cur ^= 1;
     CK(cudaGetLastError());

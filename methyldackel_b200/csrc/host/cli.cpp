@@ -130,11 +130,12 @@ static int warm_threads(int nthreads) { const char *e = getenv("MD_WARM_THREADS"
 // alignments per device tile (testing knob: small values exercise tile cuts and carried reads on small inputs)
 static size_t tile_reads_default(bool async) { if (const char *e = getenv("MD_TILE_READS")) { long v = atol(e); if (v > 0) return (size_t) v; } return async ? ((size_t) 1 << 17) : ((size_t) 1 << 19); }
 
-// Device-side BGZF inflate + BAM decode (md_bam_*): opt-in with MD_DEVICE_DECODE=1 while it is new.
+// Device-side BGZF inflate + BAM decode (md_bam_*) is the default when the back end offers it; MD_DEVICE_DECODE=0 selects the
+// multi-threaded host decoder (also used for --minConversionEfficiency, whose tiles follow the reference's chunks).
 static bool device_decode_enabled(const mdh_backend *be) {
     if (!(be->bam_open && be->bam_close && be->bam_reset && be->bam_push && be->bam_get_runs && be->bam_extract_run && be->bam_mbias_run)) return false;
     const char *e = getenv("MD_DEVICE_DECODE");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
 }
 static size_t device_segment_bytes() { if (const char *e = getenv("MD_SEGMENT_BYTES")) { long v = atol(e); if (v > 0) return (size_t) v; } return (size_t) 128 << 20; }
 

@@ -217,7 +217,7 @@ def test_cli_phred_encodings(built, synth, tmp_path, nq, env):
     refp, newp = str(tmp_path / "ref"), str(tmp_path / "new")
     r = run_ref(built["ref_bin"], "extract", ["--CHG", "--CHH", "-p", "9"], p + ".fa", p + ".bam", refp)
     assert r.returncode == 0, r.stderr
-    n = subprocess.run([NEW_BIN, "extract", "--CHG", "--CHH", "-p", "9", p + ".fa", p + ".bam", "-o", newp], capture_output=True, text=True, env=dict(os.environ, **env))
+    n = subprocess.run([NEW_BIN, "extract", "--CHG", "--CHH", "-p", "9", p + ".fa", p + ".bam", "-o", newp], capture_output=True, text=True, env=dict(os.environ, MD_DEVICE_DECODE="0", **env))   # host decoder: it is the one that packs phreds
     assert n.returncode == 0, n.stderr
     assert compare_outputs(refp, newp) == []
 
@@ -246,7 +246,7 @@ def test_cli_small_tiles_three_in_flight(built, synth, tmp_path, nq, sub):
     """tiles of 300 alignments through the asynchronous ring (3 lanes): carried reads re-encoded per tile, results of tiles
     in flight on different streams land in genome order (extract) / in one histogram (mbias)"""
     p = synth("st%d" % nq, "--contigs", "chr1:40000,chr2:9000", "--depth", "30", "--quals", str(nq), "--lower-frac", "0.02")
-    env = dict(os.environ, MD_DECODE_JOB_BYTES="1", MD_TILE_READS="300")
+    env = dict(os.environ, MD_DECODE_JOB_BYTES="1", MD_TILE_READS="300", MD_DEVICE_DECODE="0")      # the host decoder's tile ring
     if sub == "extract":
         refp, newp = str(tmp_path / "ref"), str(tmp_path / "new")
         opts = ["--CHG", "--CHH", "--mergeContext"]
