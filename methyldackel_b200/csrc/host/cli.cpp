@@ -151,32 +151,55 @@ static void tune_allocator() {
 }
 
 namespace {
-// The text formatter runs on its own thread, chunk after chunk in genome order (the analogue of the reference's ordered
-// output bins, extract.c:514-535), so the caller's thread is free to keep tiles moving.  A bounded queue applies back-pressure.
-class SerialWorker {
+// Text formatting: reference chunks are independent (extract.c:496-507 flushes the merge state at every chunk end), so a few
+// threads format chunks concurrently, each into memory, and the finished texts are appended to the output files strictly
+// in chunk order (the analogue of the reference's ordered output bins, extract.c:514-535).  post() applies back-pressure.
+class OrderedFormatter {
 public:
-    SerialWorker() : th_([this] { run(); }) {}
-    ~SerialWorker() { { std::lock_guard<std::mutex> g(m_); stop_ = true; } cv_.notify_all(); th_.join(); }
-    void post(std::function<void()> fn) {
-        std::unique_lock<std::mutex> l(m_);
-        cv_.wait(l, [&] { return q_.size() < 16; });
-        q_.push_back(std::move(fn)); cv_.notify_all();
+    OrderedFormatter(int nthreads, const ExtractOptions &o, FILE *fp[3]) : o_(o) {
+        fp_[0] = fp[0]; fp_[1] = fp[1]; fp_[2] = fp[2];
+        for (int i = 0; i < std::max(1, nthreads); ++i) th_.emplace_back([this] { run(); });
     }
-    void drain() { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return q_.empty() && !busy_; }); }
+    ~OrderedFormatter() { { std::lock_guard<std::mutex> g(m_); stop_ = true; } cv_.notify_all(); for (auto &t : th_) t.join(); }
+    void post(const char *chrom, const std::string *ref, Chunk k, std::shared_ptr<std::vector<md_call>> part) {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return next_seq_ - next_write_ < 64; });
+        q_.push_back(Job{next_seq_++, chrom, ref, k, std::move(part)}); cv_.notify_all();
+    }
+    void drain() { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return next_write_ == next_seq_; }); }
     double busy_seconds() { std::lock_guard<std::mutex> g(m_); return busy_s_; }
+    uint64_t n_variant_positions() { std::lock_guard<std::mutex> g(m_); return n_variant_; }
 private:
+    struct Job { uint64_t seq; const char *chrom; const std::string *ref; Chunk k; std::shared_ptr<std::vector<md_call>> part; };
+    struct Done { char *buf[3] = {nullptr, nullptr, nullptr}; size_t len[3] = {0, 0, 0}; };
     void run() {
         for (;;) {
-            std::function<void()> fn;
-            { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return stop_ || !q_.empty(); }); if (q_.empty()) return; fn = std::move(q_.front()); q_.pop_front(); busy_ = true; cv_.notify_all(); }
-            double t0 = now_s();
-            fn();
-            { std::lock_guard<std::mutex> g(m_); busy_ = false; busy_s_ += now_s() - t0; cv_.notify_all(); }
+            Job j;
+            { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return stop_ || !q_.empty(); }); if (q_.empty()) return; j = std::move(q_.front()); q_.pop_front(); }
+            const double t0 = now_s();
+            Done d; FILE *m[3] = {nullptr, nullptr, nullptr};
+            const bool one_file = fp_[0] && fp_[1] == fp_[0];                  // cytosine_report: the contexts interleave in one file
+            for (int k = 0; k < 3; ++k) if (fp_[k]) { if (one_file && k) m[k] = m[0]; else m[k] = open_memstream(&d.buf[k], &d.len[k]); }
+            uint64_t nvar;
+            { ExtractWriter w(o_, m); w.process_chunk(j.chrom, *j.ref, j.k.beg, j.k.end, j.part->data(), j.part->size()); nvar = w.n_variant_positions(); }
+            for (int k = 0; k < 3; ++k) if (m[k] && !(one_file && k)) fclose(m[k]);
+            j.part.reset();
+            std::lock_guard<std::mutex> g(m_);
+            busy_s_ += now_s() - t0; n_variant_ += nvar;
+            ready_.emplace(j.seq, d);
+            for (auto it = ready_.find(next_write_); it != ready_.end(); it = ready_.find(next_write_)) {
+                for (int k = 0; k < 3; ++k) if (it->second.buf[k]) { if (it->second.len[k]) fwrite(it->second.buf[k], 1, it->second.len[k], fp_[k]); free(it->second.buf[k]); }
+                ready_.erase(it); ++next_write_;
+            }
+            cv_.notify_all();
         }
     }
-    std::deque<std::function<void()>> q_; std::mutex m_; std::condition_variable cv_; bool stop_ = false, busy_ = false; double busy_s_ = 0;
-    std::thread th_;
+    const ExtractOptions &o_; FILE *fp_[3];
+    std::deque<Job> q_; std::map<uint64_t, Done> ready_; uint64_t next_seq_ = 0, next_write_ = 0, n_variant_ = 0;
+    std::mutex m_; std::condition_variable cv_; bool stop_ = false; double busy_s_ = 0;
+    std::vector<std::thread> th_;
 };
+static int format_threads() { if (const char *e = getenv("MD_FORMAT_THREADS")) { int v = atoi(e); if (v > 0) return v; } unsigned hw = std::thread::hardware_concurrency(); return (int) std::max(1u, std::min(8u, hw / 4)); }
 
 struct Driver {
     const mdh_backend *be; void *dev = nullptr;
@@ -307,7 +330,7 @@ std::vector<ContigJob> contig_jobs(const std::vector<Chunk> &all, size_t c0, siz
 }
 }  // namespace
 
-static int extract_device_decode(Driver &d, const mdh_backend *be, const char *bamName, const std::vector<Chunk> &all, size_t c0, size_t c1, ExtractWriter &writer, SerialWorker &out_thread) {
+static int extract_device_decode(Driver &d, const mdh_backend *be, const char *bamName, const std::vector<Chunk> &all, size_t c0, size_t c1, OrderedFormatter &out_thread) {
     void *bs = be->bam_open(d.dev, (int32_t) d.hdr->names.size());
     if (!bs) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
     std::vector<ContigJob> jobs = contig_jobs(all, c0, c1);
@@ -322,7 +345,7 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
             auto part = std::make_shared<std::vector<md_call>>(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b);
             const char *cname = d.hdr->names[J.tid].c_str();
             const std::string *rp = ref;
-            out_thread.post([&writer, cname, rp, k, part] { writer.process_chunk(cname, *rp, k.beg, k.end, part->data(), part->size()); });
+            out_thread.post(cname, rp, k, part);
             calls_head = b; ++next_chunk;
         }
         if (calls_head > (1u << 20)) { calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
@@ -547,8 +570,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     }
 
     for (int k = 0; k < 3; ++k) if (fp[k] && (k == 0 || fp[k] != fp[0])) setvbuf(fp[k], nullptr, _IOFBF, 4 << 20);
-    ExtractWriter writer(o, fp);
-    SerialWorker out_thread;
+    OrderedFormatter out_thread(format_threads(), o, fp);
     int rc = 0;
     {
         // the reference's chunk list (extract.c:325-350), enumerated up front; a shard takes a contiguous,
@@ -572,7 +594,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             d.dev = dev_future.get(); dev_join.taken = true;
             mark("device joined");
             if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
-            rc = extract_device_decode(d, be, bamName, all, c0, c1, writer, out_thread);
+            rc = extract_device_decode(d, be, bamName, all, c0, c1, out_thread);
         } else {
         // tile ring: with an asynchronous back end, tiles live in page-locked memory and up to two are in flight
         // while the next one is being decoded (decode || H2D || kernels || D2H)
@@ -628,7 +650,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
                     size_t b = a; while (b < calls.size() && calls[b].pos < k.end) ++b;
                     auto part = std::make_shared<std::vector<md_call>>(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b);
                     const char *cname = d.hdr->names[tid].c_str();
-                    out_thread.post([&writer, cname, ref, k, part] { writer.process_chunk(cname, *ref, k.beg, k.end, part->data(), part->size()); });
+                    out_thread.post(cname, ref, k, part);
                     calls_head = b; ++next_chunk;
                 }
                 if (calls_head > (1u << 20)) { calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
@@ -701,8 +723,8 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     if (g_marks && d.bam) fprintf(stderr, "[md-timing] record chains: %zu jobs adopted from the inflating worker, %zu walked by the stitcher\n", d.bam->jobs_adopted(), d.bam->jobs_walked());
     be->destroy(d.dev);
     mark("device destroyed");
-    g_stats.n_variant_positions = writer.n_variant_positions();
-    if (writer.n_variant_positions() && shardWorld == 1) printf("%" PRIu64 " positions were excluded due to likely being variants.\n", writer.n_variant_positions());
+    g_stats.n_variant_positions = out_thread.n_variant_positions();
+    if (g_stats.n_variant_positions && shardWorld == 1) printf("%" PRIu64 " positions were excluded due to likely being variants.\n", (uint64_t) g_stats.n_variant_positions);
     if (o.cytosine_report) { if (fp[0]) fclose(fp[0]); }
     else for (int k = 0; k < 3; ++k) if (fp[k]) fclose(fp[k]);
     free(opref);
