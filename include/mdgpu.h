@@ -202,6 +202,12 @@ void md_bam_reset(md_bam_stream *s);      /* after a seek in the file */
 /* `skip`: offset of the first record in the segment's inflated bytes (only after open/reset: the in-block part of a BAI
  * virtual offset, or the end of the BAM header); later segments continue the record that straddled in. */
 int md_bam_push(md_bam_stream *s, const void *comp, uint64_t comp_bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip, md_bam_summary *out);
+/* The same in two halves: _begin() starts the copy + decode of the segment on a helper thread and its own stream and returns
+ * at once; _end() waits for it, after which runs and tiles refer to that segment.  Between the two the caller may request
+ * tiles of the PREVIOUS segment, so the transfer and inflate of segment k+1 overlap the counting of segment k.  The
+ * compressed bytes and the block table must stay valid until _end(). */
+int md_bam_push_begin(md_bam_stream *s, const void *comp, uint64_t comp_bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip);
+int md_bam_push_end(md_bam_stream *s, md_bam_summary *out);
 int md_bam_get_runs(md_bam_stream *s, md_bam_run *runs, uint32_t cap);
 /* One tile = reads carried from the previous tile of this contig (if that tile ended where this one begins) + run `run`
  * of the last segment (run < 0: carried reads only, to close a contig), restricted to records with pos < keep_hi; then

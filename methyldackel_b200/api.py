@@ -128,7 +128,9 @@ class _GpuBackend:
                       A.BAM_PUSH_FN(lambda s, c, n, bl, nb, sk, o: g.md_bam_push(s, c, n, bl, nb, sk, o)),
                       A.BAM_RUNS_FN(lambda s, r, cap: g.md_bam_get_runs(s, r, cap)),
                       A.BAM_EXTRACT_FN(lambda s, run, td, kh, c, cap, st: g.md_bam_extract_run(s, run, td, kh, c, cap, st)),
-                      A.BAM_MBIAS_FN(lambda s, run, td, kh, st: g.md_bam_mbias_run(s, run, td, kh, st))]
+                      A.BAM_MBIAS_FN(lambda s, run, td, kh, st: g.md_bam_mbias_run(s, run, td, kh, st)),
+                      A.BAM_PUSH_BEGIN_FN(lambda s, c, n, bl, nb, sk: g.md_bam_push_begin(s, c, n, bl, nb, sk)),
+                      A.BAM_PUSH_END_FN(lambda s, o: g.md_bam_push_end(s, o))]
         self.be = A.MdhBackend(None, *self._keep)
 
 

@@ -17,6 +17,7 @@
 //
 // after which the tile goes through prep_kernel / count_warp / gather exactly like a host-supplied one.
 #include <cub/device/device_scan.cuh>
+#include <thread>
 #include "bamdev_hd.h"
 
 namespace {
@@ -85,16 +86,25 @@ static const size_t BAM_HEADROOM = (size_t) 64 << 20;      // room in front of a
 
 struct TileArena { DevBuf buf; DevReads view; int32_t *rend = nullptr; uint32_t n = 0; int32_t tid = -1; uint32_t cut = 0; bool valid = false; };
 
+// One pushed segment: its compressed bytes, inflated stream, record table and the per-contig runs.  Two slots alternate so
+// that segment k+1 is copied and decoded (on its own stream, driven by a helper thread) while the tiles of segment k are
+// assembled and counted on the lane's stream.
+struct BamSlot {
+    DevBuf comp, blk, uoff, ubuf, scan, cnt, base, rec_off, tid, pos, rend, runs, small, cub_tmp;
+    uint32_t *h_small = nullptr;        // page-locked mailbox: [0] n_runs, [1] inflate/parse error, [2] chain-check flag, [3] last_pos, [4..5] final exit
+    uint64_t U = 0, D0 = 0, leftover_from = 0, leftover = 0;
+    uint32_t n_records = 0;
+    std::vector<md_bam_run> runs_host;
+    md_bam_summary sum; int rc = 0; std::string err; uint64_t launches = 0;
+};
+
 struct md_bam_stream {
     md_ctx *c = nullptr; int32_t n_targets = 0;
-    DevBuf comp, blk, uoff, ubuf, scan, cnt, base, rec_off, tid, pos, rend, runs, small, cub_tmp, sz, off;
-    uint64_t U = 0, D0 = 0;             // current segment: data is ubuf[D0, U)
-    uint64_t leftover_from = 0, leftover = 0;
-    uint32_t n_records = 0; bool have_segment = false;
-    std::vector<md_bam_run> runs_host;
+    BamSlot slot[2]; int cur_slot = 0; bool have_segment = false;
+    cudaStream_t sd = nullptr;          // decode stream
+    std::thread worker; bool inflight = false; int target = 0;
+    DevBuf cub_tmp, sz, off;
     TileArena tile[2]; int cur = 0;
-    // page-locked mailbox: [0] n_runs, [1] inflate/parse error, [2] chain-check flag, [3] last_pos, [4..5] final exit, [6..7] n_records(total)
-    uint32_t *h_small = nullptr;
     Sz4 *h_tot = nullptr;
     double t_push[8] = {0}, t_tile[8] = {0}; uint64_t n_push = 0, n_tiles = 0, comp_total = 0, infl_total = 0, rec_total = 0;
 };
@@ -104,142 +114,175 @@ extern "C" md_bam_stream *md_bam_open(md_ctx *c, int32_t n_targets) {
     CKN(cudaSetDevice(c->device));
     md_bam_stream *s = new md_bam_stream();
     s->c = c; s->n_targets = n_targets;
-    if (cudaMallocHost((void **) &s->h_small, 64) != cudaSuccess || cudaMallocHost((void **) &s->h_tot, 2 * sizeof(Sz4)) != cudaSuccess) { g_err = "cudaMallocHost failed"; delete s; return nullptr; }
-    if (s->small.reserve(256)) { delete s; return nullptr; }
+    bool ok = cudaStreamCreateWithFlags(&s->sd, cudaStreamNonBlocking) == cudaSuccess && cudaMallocHost((void **) &s->h_tot, 2 * sizeof(Sz4)) == cudaSuccess;
+    for (int k = 0; k < 2 && ok; ++k) ok = cudaMallocHost((void **) &s->slot[k].h_small, 64) == cudaSuccess && s->slot[k].small.reserve(256) == 0;
+    if (!ok) { g_err = "md_bam_open: allocation failed"; delete s; return nullptr; }
     return s;
 }
+static void bam_join(md_bam_stream *s) { if (s->worker.joinable()) s->worker.join(); }
 extern "C" void md_bam_close(md_bam_stream *s) {
     if (!s) return;
-    cudaSetDevice(s->c->device); sync_all(s->c);
+    bam_join(s);
+    cudaSetDevice(s->c->device); sync_all(s->c); if (s->sd) cudaStreamSynchronize(s->sd);
     if (getenv("MD_TIMING"))
         fprintf(stderr, "[md-timing] device decode: %llu segments, %.1f MB compressed -> %.1f MB, %llu records; H2D %.2f ms, inflate %.2f ms, record chains %.2f ms, offsets+heads+runs %.2f ms; %llu tiles: sizes+scan %.2f ms, gather %.2f ms\n",
                 (unsigned long long) s->n_push, s->comp_total / 1e6, s->infl_total / 1e6, (unsigned long long) s->rec_total, s->t_push[0], s->t_push[1], s->t_push[2], s->t_push[3], (unsigned long long) s->n_tiles, s->t_tile[0], s->t_tile[1]);
-    DevBuf *bufs[] = {&s->comp, &s->blk, &s->uoff, &s->ubuf, &s->scan, &s->cnt, &s->base, &s->rec_off, &s->tid, &s->pos, &s->rend, &s->runs, &s->small, &s->cub_tmp, &s->sz, &s->off, &s->tile[0].buf, &s->tile[1].buf};
+    for (int k = 0; k < 2; ++k) {
+        BamSlot &S = s->slot[k];
+        DevBuf *bufs[] = {&S.comp, &S.blk, &S.uoff, &S.ubuf, &S.scan, &S.cnt, &S.base, &S.rec_off, &S.tid, &S.pos, &S.rend, &S.runs, &S.small, &S.cub_tmp};
+        for (DevBuf *b : bufs) b->release();
+        if (S.h_small) cudaFreeHost(S.h_small);
+    }
+    DevBuf *bufs[] = {&s->cub_tmp, &s->sz, &s->off, &s->tile[0].buf, &s->tile[1].buf};
     for (DevBuf *b : bufs) b->release();
-    if (s->h_small) cudaFreeHost(s->h_small);
     if (s->h_tot) cudaFreeHost(s->h_tot);
+    if (s->sd) cudaStreamDestroy(s->sd);
     delete s;
 }
 extern "C" void md_bam_reset(md_bam_stream *s) {       // after a seek: forget the straddling record and the carried reads
-    s->leftover = 0; s->have_segment = false; s->tile[0].valid = s->tile[1].valid = false; s->n_records = 0; s->runs_host.clear();
+    bam_join(s); s->inflight = false;
+    s->have_segment = false; s->slot[0].leftover = s->slot[1].leftover = 0; s->tile[0].valid = s->tile[1].valid = false;
 }
 
 static const uint32_t BAM_MAX_RUNS = 1u << 16;
 
-// MD_TIMING=1: per-stage device times of the decode (CUDA events on the lane's stream), accumulated per stream object
+// MD_TIMING=1: per-stage device times of the decode (CUDA events on the stream the work is queued on)
 struct BamTimer {
     bool on; cudaStream_t st; cudaEvent_t ev[8]; int n = 0;
     explicit BamTimer(cudaStream_t s) : on(getenv("MD_TIMING") != nullptr), st(s) { if (on) for (auto &e : ev) cudaEventCreate(&e); }
     ~BamTimer() { if (on) for (auto &e : ev) cudaEventDestroy(e); }
     void tick() { if (on && n < 8) cudaEventRecord(ev[n++], st); }
-    void add(double *acc) { if (!on) return; cudaEventSynchronize(ev[n - 1]); for (int k = 0; k + 1 < n; ++k) { float ms = 0; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); acc[k] += ms; } }
+    void add(double *acc) { if (!on || n < 2) return; cudaEventSynchronize(ev[n - 1]); for (int k = 0; k + 1 < n; ++k) { float ms = 0; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); acc[k] += ms; } }
 };
 
-extern "C" int md_bam_push(md_bam_stream *s, const void *comp, uint64_t comp_bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip, md_bam_summary *out) {
+#define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { S.err = std::string(#call) + ": " + cudaGetErrorString(e_); return -100; } } while (0)
+// Everything one segment needs, queued on the decode stream; runs on the helper thread.  `P` (may be null) is the slot of
+// the previous segment: the record that straddles in is copied from its inflated bytes.
+static int bam_push_impl(md_bam_stream *s, BamSlot &S, const BamSlot *P, const void *comp, uint64_t comp_bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip) {
     md_ctx *c = s->c;
-    CK(cudaSetDevice(c->device));
-    Lane *L = &c->lanes[0];
-    cudaStream_t st = L->stream;
-    sync_all(c);                                              // v1: one segment at a time; tiles of the previous segment are complete
-    memset(out, 0, sizeof *out);
-    // stream layout of this segment
+    PCK(cudaSetDevice(c->device));
+    cudaStream_t st = s->sd;
+    memset(&S.sum, 0, sizeof S.sum); S.runs_host.clear(); S.n_records = 0; S.launches = 0;
+    const uint64_t carry_in = P ? P->leftover : 0;
     std::vector<unsigned long long> uoff(n_blocks + 1);
     uint64_t tot = 0;
     for (uint32_t b = 0; b < n_blocks; ++b) {
-        if (blocks[b].comp_off + blocks[b].comp_len > comp_bytes) { g_err = "md_bam_push: block outside the buffer"; return -2; }
+        if (blocks[b].comp_off + blocks[b].comp_len > comp_bytes) { S.err = "md_bam_push: block outside the buffer"; return -2; }
         uoff[b] = BAM_HEADROOM + tot; tot += blocks[b].isize;
     }
     uoff[n_blocks] = BAM_HEADROOM + tot;
-    if (s->leftover > BAM_HEADROOM) { g_err = "md_bam_push: a record larger than 64 MB straddles two segments"; return -2; }
-    const uint64_t D0 = BAM_HEADROOM - s->leftover, U = BAM_HEADROOM + tot;
-    if (tot + s->leftover >= ((uint64_t) 1 << 32) - BAM_HEADROOM) { g_err = "md_bam_push: segment inflates to more than 4 GB"; return -2; }
-    // the straddling record's first bytes move in front of the new data (before ubuf may be re-allocated)
-    DevBuf keep;
-    if (s->leftover) {
-        if (keep.reserve(s->leftover)) return -100;
-        CK(cudaMemcpyAsync(keep.p, (uint8_t *) s->ubuf.p + s->leftover_from, s->leftover, cudaMemcpyDeviceToDevice, st));
-        CK(cudaStreamSynchronize(st));
-    }
-    if (s->comp.reserve(comp_bytes + 64) || s->blk.reserve((size_t) n_blocks * sizeof(md_bgzf_block) + 16) || s->uoff.reserve((size_t)(n_blocks + 1) * 8) ||
-        s->ubuf.reserve(U + 64) || s->scan.reserve((size_t) n_blocks * sizeof(BlockScan) + 16) || s->cnt.reserve((size_t) n_blocks * 4 + 16) || s->base.reserve((size_t) n_blocks * 4 + 16) ||
-        s->runs.reserve((size_t) BAM_MAX_RUNS * sizeof(md_bam_run))) { keep.release(); return -100; }
+    if (carry_in > BAM_HEADROOM) { S.err = "md_bam_push: a record larger than 64 MB straddles two segments"; return -2; }
+    const uint64_t D0 = BAM_HEADROOM - carry_in, U = BAM_HEADROOM + tot;
+    if (tot + carry_in >= ((uint64_t) 1 << 32) - BAM_HEADROOM) { S.err = "md_bam_push: segment inflates to more than 4 GB"; return -2; }
+    if (S.comp.reserve(comp_bytes + 64) || S.blk.reserve((size_t) n_blocks * sizeof(md_bgzf_block) + 16) || S.uoff.reserve((size_t)(n_blocks + 1) * 8) ||
+        S.ubuf.reserve(U + 64) || S.scan.reserve((size_t) n_blocks * sizeof(BlockScan) + 16) || S.cnt.reserve((size_t) n_blocks * 4 + 16) || S.base.reserve((size_t) n_blocks * 4 + 16) ||
+        S.runs.reserve((size_t) BAM_MAX_RUNS * sizeof(md_bam_run))) { S.err = "md_bam_push: out of device memory"; return -100; }
     BamTimer tm(st); tm.tick();
-    if (s->leftover) { CK(cudaMemcpyAsync((uint8_t *) s->ubuf.p + D0, keep.p, s->leftover, cudaMemcpyDeviceToDevice, st)); }
-    CK(cudaMemcpyAsync(s->comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync((uint8_t *) s->comp.p + comp_bytes, 0, 64, st));
-    CK(cudaMemcpyAsync(s->blk.p, blocks, (size_t) n_blocks * sizeof(md_bgzf_block), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->uoff.p, uoff.data(), (size_t)(n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(s->small.p, 0, 256, st));
-    uint32_t *d_small = (uint32_t *) s->small.p;       // [0] n_runs [1] err [2] bad [3] last_pos [4,5] final_exit
-    const uint8_t *u = (const uint8_t *) s->ubuf.p;
-    const unsigned long long first = D0 + (s->leftover ? 0 : skip);
+    // the straddling record's first bytes go in front of the new data
+    if (carry_in) PCK(cudaMemcpyAsync((uint8_t *) S.ubuf.p + D0, (const uint8_t *) P->ubuf.p + P->leftover_from, carry_in, cudaMemcpyDeviceToDevice, st));
+    PCK(cudaMemcpyAsync(S.comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, st));
+    PCK(cudaMemsetAsync((uint8_t *) S.comp.p + comp_bytes, 0, 64, st));
+    PCK(cudaMemcpyAsync(S.blk.p, blocks, (size_t) n_blocks * sizeof(md_bgzf_block), cudaMemcpyHostToDevice, st));
+    PCK(cudaMemcpyAsync(S.uoff.p, uoff.data(), (size_t)(n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
+    PCK(cudaMemsetAsync(S.small.p, 0, 256, st));
+    uint32_t *d_small = (uint32_t *) S.small.p;       // [0] n_runs [1] err [2] bad [3] last_pos [4,5] final_exit
+    const uint8_t *u = (const uint8_t *) S.ubuf.p;
+    const unsigned long long first = D0 + (carry_in ? 0 : skip);
     tm.tick();
     if (n_blocks) {
-        inflate_kernel<<<(n_blocks + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, 0, st>>>((const uint8_t *) s->comp.p, (const md_bgzf_block *) s->blk.p, (const unsigned long long *) s->uoff.p, (uint8_t *) s->ubuf.p, n_blocks, (int *)(d_small + 1));
+        inflate_kernel<<<(n_blocks + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, 0, st>>>((const uint8_t *) S.comp.p, (const md_bgzf_block *) S.blk.p, (const unsigned long long *) S.uoff.p, (uint8_t *) S.ubuf.p, n_blocks, (int *)(d_small + 1));
         tm.tick();
         const uint32_t g = (n_blocks + 127) / 128;
         // block 0's slice starts at D0 so that the straddling record is part of its chain
         unsigned long long d0 = D0;
-        CK(cudaMemcpyAsync(s->uoff.p, &d0, 8, cudaMemcpyHostToDevice, st));
-        scan_blocks_kernel<<<g, 128, 0, st>>>(u, (const unsigned long long *) s->uoff.p, n_blocks, first, U, s->n_targets, (BlockScan *) s->scan.p);
-        check_chain_kernel<<<g, 128, 0, st>>>((const unsigned long long *) s->uoff.p, n_blocks, first, (const BlockScan *) s->scan.p, (int *)(d_small + 2));
-        fix_chain_kernel<<<1, 32, 0, st>>>(u, (const unsigned long long *) s->uoff.p, n_blocks, first, U, (BlockScan *) s->scan.p, (const int *)(d_small + 2), (unsigned long long *)(d_small + 4));
-        counts_kernel<<<g, 128, 0, st>>>((const BlockScan *) s->scan.p, n_blocks, (uint32_t *) s->cnt.p);
+        PCK(cudaMemcpyAsync(S.uoff.p, &d0, 8, cudaMemcpyHostToDevice, st));
+        scan_blocks_kernel<<<g, 128, 0, st>>>(u, (const unsigned long long *) S.uoff.p, n_blocks, first, U, s->n_targets, (BlockScan *) S.scan.p);
+        check_chain_kernel<<<g, 128, 0, st>>>((const unsigned long long *) S.uoff.p, n_blocks, first, (const BlockScan *) S.scan.p, (int *)(d_small + 2));
+        fix_chain_kernel<<<1, 32, 0, st>>>(u, (const unsigned long long *) S.uoff.p, n_blocks, first, U, (BlockScan *) S.scan.p, (const int *)(d_small + 2), (unsigned long long *)(d_small + 4));
+        counts_kernel<<<g, 128, 0, st>>>((const BlockScan *) S.scan.p, n_blocks, (uint32_t *) S.cnt.p);
         size_t tmp = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const uint32_t *) s->cnt.p, (uint32_t *) s->base.p, (int) n_blocks, st);
-        if (s->cub_tmp.reserve(tmp + 256)) { keep.release(); return -100; }
-        cub::DeviceScan::ExclusiveSum(s->cub_tmp.p, tmp, (const uint32_t *) s->cnt.p, (uint32_t *) s->base.p, (int) n_blocks, st);
-        c->launches += 6;
-    }
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const uint32_t *) S.cnt.p, (uint32_t *) S.base.p, (int) n_blocks, st);
+        if (S.cub_tmp.reserve(tmp + 256)) { S.err = "md_bam_push: out of device memory"; return -100; }
+        cub::DeviceScan::ExclusiveSum(S.cub_tmp.p, tmp, (const uint32_t *) S.cnt.p, (uint32_t *) S.base.p, (int) n_blocks, st);
+        S.launches += 6;
+    } else tm.tick();
     tm.tick();
     // number of records = base[last] + cnt[last]
     uint32_t last2[2] = {0, 0};
     if (n_blocks) {
-        CK(cudaMemcpyAsync(&last2[0], (uint32_t *) s->base.p + (n_blocks - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&last2[1], (uint32_t *) s->cnt.p + (n_blocks - 1), 4, cudaMemcpyDeviceToHost, st));
+        PCK(cudaMemcpyAsync(&last2[0], (uint32_t *) S.base.p + (n_blocks - 1), 4, cudaMemcpyDeviceToHost, st));
+        PCK(cudaMemcpyAsync(&last2[1], (uint32_t *) S.cnt.p + (n_blocks - 1), 4, cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaMemcpyAsync(s->h_small, d_small, 32, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    keep.release();
-    if (s->h_small[1]) { char msg[128]; snprintf(msg, sizeof msg, "BGZF inflate failed on the device (block %u, code -%u)", s->h_small[1] >> 4, s->h_small[1] & 15u); g_err = msg; return -5; }
+    PCK(cudaMemcpyAsync(S.h_small, d_small, 32, cudaMemcpyDeviceToHost, st));
+    PCK(cudaStreamSynchronize(st));
+    if (S.h_small[1]) { char msg[128]; snprintf(msg, sizeof msg, "BGZF inflate failed on the device (block %u, code -%u)", S.h_small[1] >> 4, S.h_small[1] & 15u); S.err = msg; return -5; }
     const uint32_t n = last2[0] + last2[1];
-    unsigned long long final_exit; memcpy(&final_exit, s->h_small + 4, 8);
+    unsigned long long final_exit; memcpy(&final_exit, S.h_small + 4, 8);
     if (!n_blocks) final_exit = first;
-    s->U = U; s->D0 = D0; s->n_records = n; s->have_segment = true;
-    s->leftover_from = final_exit; s->leftover = U - final_exit;
-    s->runs_host.clear();
+    S.U = U; S.D0 = D0; S.n_records = n;
+    S.leftover_from = final_exit; S.leftover = U - final_exit;
     if (n) {
-        if (s->rec_off.reserve((size_t) n * 8 + 16) || s->tid.reserve((size_t) n * 4 + 16) || s->pos.reserve((size_t) n * 4 + 16) || s->rend.reserve((size_t) n * 4 + 16)) return -100;
+        if (S.rec_off.reserve((size_t) n * 8 + 16) || S.tid.reserve((size_t) n * 4 + 16) || S.pos.reserve((size_t) n * 4 + 16) || S.rend.reserve((size_t) n * 4 + 16)) { S.err = "md_bam_push: out of device memory"; return -100; }
         const uint32_t g = (n_blocks + 127) / 128, gr = (n + 255) / 256;
-        fill_offsets_kernel<<<g, 128, 0, st>>>(u, (const unsigned long long *) s->uoff.p, n_blocks, U, (const BlockScan *) s->scan.p, (const uint32_t *) s->base.p, (unsigned long long *) s->rec_off.p);
-        head_kernel<<<gr, 256, 0, st>>>(u, (const unsigned long long *) s->rec_off.p, n, (int32_t *) s->tid.p, (int32_t *) s->pos.p, (int32_t *) s->rend.p, (int *)(d_small + 1));
-        runs_kernel<<<gr, 256, 0, st>>>((const int32_t *) s->tid.p, (const int32_t *) s->pos.p, n, (md_bam_run *) s->runs.p, BAM_MAX_RUNS, d_small, (int32_t *)(d_small + 3));
-        c->launches += 3;
+        fill_offsets_kernel<<<g, 128, 0, st>>>(u, (const unsigned long long *) S.uoff.p, n_blocks, U, (const BlockScan *) S.scan.p, (const uint32_t *) S.base.p, (unsigned long long *) S.rec_off.p);
+        head_kernel<<<gr, 256, 0, st>>>(u, (const unsigned long long *) S.rec_off.p, n, (int32_t *) S.tid.p, (int32_t *) S.pos.p, (int32_t *) S.rend.p, (int *)(d_small + 1));
+        runs_kernel<<<gr, 256, 0, st>>>((const int32_t *) S.tid.p, (const int32_t *) S.pos.p, n, (md_bam_run *) S.runs.p, BAM_MAX_RUNS, d_small, (int32_t *)(d_small + 3));
+        S.launches += 3;
         tm.tick();
-        CK(cudaMemcpyAsync(s->h_small, d_small, 32, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (s->h_small[1]) { g_err = "malformed BAM record"; return -5; }
-        const uint32_t nr = s->h_small[0];
-        if (nr > BAM_MAX_RUNS) { g_err = "md_bam_push: more than 65536 contig runs in one segment"; return -2; }
-        s->runs_host.resize(nr);
-        CK(cudaMemcpy(s->runs_host.data(), s->runs.p, (size_t) nr * sizeof(md_bam_run), cudaMemcpyDeviceToHost));
-        std::sort(s->runs_host.begin(), s->runs_host.end(), [](const md_bam_run &a, const md_bam_run &b) { return a.start < b.start; });
+        PCK(cudaMemcpyAsync(S.h_small, d_small, 32, cudaMemcpyDeviceToHost, st));
+        PCK(cudaStreamSynchronize(st));
+        if (S.h_small[1]) { S.err = "malformed BAM record"; return -5; }
+        const uint32_t nr = S.h_small[0];
+        if (nr > BAM_MAX_RUNS) { S.err = "md_bam_push: more than 65536 contig runs in one segment"; return -2; }
+        S.runs_host.resize(nr);
+        PCK(cudaMemcpyAsync(S.runs_host.data(), S.runs.p, (size_t) nr * sizeof(md_bam_run), cudaMemcpyDeviceToHost, st));
+        PCK(cudaStreamSynchronize(st));
+        std::sort(S.runs_host.begin(), S.runs_host.end(), [](const md_bam_run &a, const md_bam_run &b) { return a.start < b.start; });
         for (uint32_t k = 0; k < nr; ++k) {
-            md_bam_run &r = s->runs_host[k];
-            const uint32_t nxt = k + 1 < nr ? s->runs_host[k + 1].start : n;
+            md_bam_run &r = S.runs_host[k];
+            const uint32_t nxt = k + 1 < nr ? S.runs_host[k + 1].start : n;
             r.n = nxt - r.start;
-            r.last_pos = k + 1 < nr ? s->runs_host[k + 1].prev_last_pos : (int32_t) s->h_small[3];
+            r.last_pos = k + 1 < nr ? S.runs_host[k + 1].prev_last_pos : (int32_t) S.h_small[3];
         }
     }
     tm.add(s->t_push); s->n_push++; s->comp_total += comp_bytes; s->infl_total += tot; s->rec_total += n;
-    CK(cudaGetLastError());
-    out->n_records = n; out->n_runs = (uint32_t) s->runs_host.size(); out->inflated_bytes = tot; out->leftover_bytes = s->leftover;
+    PCK(cudaGetLastError());
+    S.sum.n_records = n; S.sum.n_runs = (uint32_t) S.runs_host.size(); S.sum.inflated_bytes = tot; S.sum.leftover_bytes = S.leftover;
     return 0;
 }
+
+// Start copying + decoding a segment in the background; the caller's buffers must stay valid until md_bam_push_end().
+extern "C" int md_bam_push_begin(md_bam_stream *s, const void *comp, uint64_t comp_bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip) {
+    if (s->inflight) { g_err = "md_bam_push_begin: a push is already in flight"; return -4; }
+    bam_join(s);
+    const int tgt = s->have_segment ? (s->cur_slot ^ 1) : 0;
+    BamSlot *S = &s->slot[tgt]; const BamSlot *P = s->have_segment ? &s->slot[s->cur_slot] : nullptr;
+    s->target = tgt; s->inflight = true;
+    S->rc = 0; S->err.clear();
+    s->worker = std::thread([=] { S->rc = bam_push_impl(s, *S, P, comp, comp_bytes, blocks, n_blocks, skip); });
+    return 0;
+}
+// Wait for it; from here on the runs / tiles refer to that segment.
+extern "C" int md_bam_push_end(md_bam_stream *s, md_bam_summary *out) {
+    if (!s->inflight) { g_err = "md_bam_push_end: nothing in flight"; return -4; }
+    bam_join(s); s->inflight = false;
+    BamSlot &S = s->slot[s->target];
+    s->c->launches += S.launches;
+    if (S.rc) { g_err = S.err.empty() ? "md_bam_push failed" : S.err; return S.rc; }
+    s->cur_slot = s->target; s->have_segment = true;
+    if (out) *out = S.sum;
+    return 0;
+}
+extern "C" int md_bam_push(md_bam_stream *s, const void *comp, uint64_t comp_bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip, md_bam_summary *out) {
+    int rc = md_bam_push_begin(s, comp, comp_bytes, blocks, n_blocks, skip);
+    if (rc) return rc;
+    return md_bam_push_end(s, out);
+}
 extern "C" int md_bam_get_runs(md_bam_stream *s, md_bam_run *runs, uint32_t cap) {
-    const uint32_t n = (uint32_t) s->runs_host.size();
-    for (uint32_t k = 0; k < n && k < cap; ++k) runs[k] = s->runs_host[k];
-    return (int) n;
+    if (!s->have_segment) return 0;
+    const std::vector<md_bam_run> &R = s->slot[s->cur_slot].runs_host;
+    for (uint32_t k = 0; k < R.size() && k < cap; ++k) runs[k] = R[k];
+    return (int) R.size();
 }
 
 // Build the tile (carried reads of the previous tile of this contig + records [run.start, run.start+run.n) of the last segment)
@@ -248,10 +291,11 @@ static int bam_build_tile(md_bam_stream *s, int run, const md_tile_desc *t, uint
     md_ctx *c = s->c; Lane *L = &c->lanes[0]; cudaStream_t st = L->stream;
     TileArena &P = s->tile[s->cur], &N = s->tile[s->cur ^ 1];
     TileSrc S; memset(&S, 0, sizeof S);
-    S.u = (const uint8_t *) s->ubuf.p; S.rec_off = (const unsigned long long *) s->rec_off.p; S.pos = (const int32_t *) s->pos.p; S.rend = (const int32_t *) s->rend.p;
+    const BamSlot &B = s->slot[s->cur_slot];
+    S.u = (const uint8_t *) B.ubuf.p; S.rec_off = (const unsigned long long *) B.rec_off.p; S.pos = (const int32_t *) B.pos.p; S.rend = (const int32_t *) B.rend.p;
     if (run >= 0) {
-        if (!s->have_segment || (size_t) run >= s->runs_host.size()) { g_err = "md_bam: no such run"; return -2; }
-        const md_bam_run &r = s->runs_host[(size_t) run];
+        if (!s->have_segment || (size_t) run >= B.runs_host.size()) { g_err = "md_bam: no such run"; return -2; }
+        const md_bam_run &r = B.runs_host[(size_t) run];
         if (r.tid != t->tid) { g_err = "md_bam: tile and run are on different contigs"; return -2; }
         S.r0 = r.start; S.n_own = r.n;
     }

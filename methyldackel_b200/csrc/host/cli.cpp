@@ -265,7 +265,7 @@ int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamNa
     be->bam_reset(bs);
     const size_t target = device_segment_bytes();
     size_t cj = 0; bool open = false; uint32_t open_beg = 0; int rc = 0;
-    std::vector<md_bgzf_block> blocks; std::vector<md_bam_run> runs;
+    std::vector<md_bam_run> runs;
     // finish job cj: its last tile comes from carried reads only (run -1); a contig that never had a record just gets its chunks written
     auto finish = [&]() -> int {
         const ContigJob &J = jobs[cj];
@@ -278,20 +278,30 @@ int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamNa
         open = false; ++cj;
         return r;
     };
+    // Segment k+1 is handed to the device (copy + inflate + record tables, on a helper thread and its own stream) before
+    // the tiles of segment k are requested, when the back end offers the two-phase push.
+    const bool overlapped = be->bam_push_begin && be->bam_push_end;
+    std::vector<md_bgzf_block> blk[2]; int cur = 0;
+    const uint8_t *base[2] = {nullptr, nullptr}; size_t bytes[2] = {0, 0};
+    bool have_cur = seg.next(target, base[0], bytes[0], blk[0]);
+    bool pushed = false;
+    if (have_cur && overlapped) { if (be->bam_push_begin(bs, base[0], bytes[0], blk[0].data(), (uint32_t) blk[0].size(), skip) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; } pushed = true; }
     bool done = false;
-    while (!done && rc == 0) {
-        const uint8_t *base; size_t bytes;
+    while (have_cur && !done && rc == 0) {
         double t0 = now_s();
-        if (!seg.next(target, base, bytes, blocks)) break;
         md_bam_summary sum;
-        int r = be->bam_push(bs, base, bytes, blocks.data(), (uint32_t) blocks.size(), skip, &sum);
-        skip = 0;
+        int r = overlapped ? be->bam_push_end(bs, &sum) : be->bam_push(bs, base[cur], bytes[cur], blk[cur].data(), (uint32_t) blk[cur].size(), skip, &sum);
+        pushed = false; skip = 0;
         g_stats.t_decode_s += now_s() - t0;
-        if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+        if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+        // cut the next segment now: whether the file ends here decides how this segment's last run is closed
+        const int nxt = cur ^ 1;
+        const bool have_next = seg.next(target, base[nxt], bytes[nxt], blk[nxt]);
+        const bool file_end = !have_next;
+        if (have_next && overlapped) { if (be->bam_push_begin(bs, base[nxt], bytes[nxt], blk[nxt].data(), (uint32_t) blk[nxt].size(), 0) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; } pushed = true; }
         g_stats.n_records += sum.n_records;
         runs.resize(sum.n_runs);
         if (sum.n_runs) be->bam_get_runs(bs, runs.data(), sum.n_runs);
-        const bool file_end = seg.eof();
         for (size_t k = 0; k < runs.size() && !done && rc == 0; ++k) {
             const md_bam_run &run = runs[k];
             if (run.tid < 0) { done = true; break; }                                   // unmapped records close a sorted file
@@ -315,7 +325,9 @@ int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamNa
                 if (cj >= jobs.size()) done = true;
             }
         }
+        have_cur = have_next; cur = nxt;
     }
+    if (pushed) { md_bam_summary dummy; be->bam_push_end(bs, &dummy); }            // a segment beyond the region was already on its way
     while (rc == 0 && cj < jobs.size()) rc = finish();
     return rc;
 }

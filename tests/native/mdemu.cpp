@@ -21,10 +21,14 @@ struct Tile {
     std::vector<int32_t> pos, rend; std::vector<uint16_t> flag; std::vector<uint8_t> mapq, aux; std::vector<uint32_t> l_qseq, cigar_off, seq_off, qual_off, cigar, seq;
     std::vector<uint64_t> frag_key, qual; uint32_t n = 0; int32_t tid = -1; uint32_t cut = 0; bool valid = false;
 };
+struct Seg {
+    std::vector<uint8_t> ubuf; uint64_t U = 0, D0 = 0, leftover_from = 0, leftover = 0;
+    std::vector<unsigned long long> rec_off; std::vector<int32_t> tid, pos, rend; std::vector<md_bam_run> runs;
+};
 struct Emu {
     int32_t n_targets; emu_extract_cb ex; emu_mbias_cb mb; void *be;
-    std::vector<uint8_t> ubuf; uint64_t U = 0, D0 = 0, leftover_from = 0, leftover = 0; bool have = false;
-    std::vector<unsigned long long> rec_off; std::vector<int32_t> tid, pos, rend; std::vector<md_bam_run> runs;
+    Seg seg[2]; int cur_seg = 0; bool have = false;          // two slots, as the device library: tiles read seg[cur_seg]
+    bool pending = false; int pending_rc = 0, target = 0; md_bam_summary pending_sum;
     Tile tile[2]; int cur = 0; std::string err;
     uint64_t n_fix = 0;
 };
@@ -34,21 +38,20 @@ std::string g_emu_err;
 extern "C" const char *emu_last_error() { return g_emu_err.c_str(); }
 extern "C" void *emu_bam_open(int32_t n_targets, emu_extract_cb ex, emu_mbias_cb mb, void *be) { Emu *e = new Emu(); e->n_targets = n_targets; e->ex = ex; e->mb = mb; e->be = be; return e; }
 extern "C" void emu_bam_close(void *s) { delete (Emu *) s; }
-extern "C" void emu_bam_reset(void *s) { Emu *e = (Emu *) s; e->leftover = 0; e->have = false; e->tile[0].valid = e->tile[1].valid = false; e->runs.clear(); }
+extern "C" void emu_bam_reset(void *s) { Emu *e = (Emu *) s; e->seg[0].leftover = e->seg[1].leftover = 0; e->have = false; e->pending = false; e->tile[0].valid = e->tile[1].valid = false; }
 extern "C" uint64_t emu_bam_fixups(void *s) { return ((Emu *) s)->n_fix; }
 
-extern "C" int emu_bam_push(void *sv, const void *comp, uint64_t comp_bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip, md_bam_summary *out) {
-    Emu *s = (Emu *) sv;
+static int push_impl(Emu *e, Seg *s, const Seg *P, const void *comp, uint64_t comp_bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip, md_bam_summary *out) {
     memset(out, 0, sizeof *out);
+    const uint64_t carry_in = P ? P->leftover : 0;
     std::vector<unsigned long long> uoff(n_blocks + 1);
     uint64_t tot = 0;
     for (uint32_t b = 0; b < n_blocks; ++b) { if (blocks[b].comp_off + blocks[b].comp_len > comp_bytes) { g_emu_err = "block outside the buffer"; return -2; } uoff[b] = HEADROOM + tot; tot += blocks[b].isize; }
     uoff[n_blocks] = HEADROOM + tot;
-    if (s->leftover > HEADROOM) { g_emu_err = "straddling record too large for the emulation"; return -2; }
-    const uint64_t D0 = HEADROOM - s->leftover, U = HEADROOM + tot;
-    std::vector<uint8_t> keep(s->ubuf.begin() + (ptrdiff_t) s->leftover_from, s->ubuf.begin() + (ptrdiff_t)(s->leftover_from + s->leftover));
+    if (carry_in > HEADROOM) { g_emu_err = "straddling record too large for the emulation"; return -2; }
+    const uint64_t D0 = HEADROOM - carry_in, U = HEADROOM + tot;
     s->ubuf.assign(U + 64, 0);
-    if (!keep.empty()) memcpy(s->ubuf.data() + D0, keep.data(), keep.size());
+    if (carry_in) memcpy(s->ubuf.data() + D0, P->ubuf.data() + P->leftover_from, carry_in);
     // 4-byte aligned, padded copy of the compressed bytes (the device buffer is)
     std::vector<uint32_t> cal((comp_bytes + 64 + 3) / 4, 0); memcpy(cal.data(), comp, comp_bytes);
     mdinflate::Tables T;
@@ -58,22 +61,22 @@ extern "C" int emu_bam_push(void *sv, const void *comp, uint64_t comp_bytes, con
         if (rc) { g_emu_err = "inflate failed in block " + std::to_string(b) + " code " + std::to_string(rc); return -5; }
     }
     const uint8_t *u = s->ubuf.data();
-    const unsigned long long first = D0 + (s->leftover ? 0 : skip);
+    const unsigned long long first = D0 + (carry_in ? 0 : skip);
     std::vector<mdbam::BlockScan> sc(n_blocks);
     unsigned long long final_exit = first;
     std::vector<uint32_t> base(n_blocks, 0);
     uint32_t n = 0;
     if (n_blocks) {
         uoff[0] = D0;
-        for (uint32_t b = 0; b < n_blocks; ++b) mdbam::scan_block_body(b, u, uoff.data(), first, U, s->n_targets, sc.data());
+        for (uint32_t b = 0; b < n_blocks; ++b) mdbam::scan_block_body(b, u, uoff.data(), first, U, e->n_targets, sc.data());
         int bad = 0;
         for (uint32_t b = 0; b < n_blocks; ++b) if (!mdbam::check_block_body(b, uoff.data(), first, sc.data())) bad = 1;
         if (getenv("MDEMU_FORCE_FIX")) { bad = 1; for (uint32_t b = 1; b < n_blocks; b += 3) if (sc[b].guess != mdbam::NONE) { sc[b].guess += 1; } }   // sabotage guesses: the repair must restore them
-        s->n_fix += (uint64_t) bad;
+        e->n_fix += (uint64_t) bad;
         mdbam::fix_chain_body(u, uoff.data(), n_blocks, first, U, sc.data(), bad, &final_exit);
         for (uint32_t b = 0; b < n_blocks; ++b) { base[b] = n; n += sc[b].guess != mdbam::NONE ? sc[b].count : 0u; }
     }
-    s->U = U; s->D0 = D0; s->have = true; s->leftover_from = final_exit; s->leftover = U - final_exit;
+    s->U = U; s->D0 = D0; s->leftover_from = final_exit; s->leftover = U - final_exit;
     s->rec_off.assign(n, 0); s->tid.assign(n, 0); s->pos.assign(n, 0); s->rend.assign(n, 0); s->runs.clear();
     for (uint32_t b = 0; b < n_blocks; ++b) mdbam::fill_offsets_body(b, u, uoff.data(), U, sc.data(), base.data(), s->rec_off.data());
     for (uint32_t i = 0; i < n; ++i) if (!mdbam::head_body(i, u, s->rec_off.data(), s->tid.data(), s->pos.data(), s->rend.data())) { g_emu_err = "malformed BAM record"; return -5; }
@@ -82,15 +85,37 @@ extern "C" int emu_bam_push(void *sv, const void *comp, uint64_t comp_bytes, con
     out->n_records = n; out->n_runs = (uint32_t) s->runs.size(); out->inflated_bytes = tot; out->leftover_bytes = s->leftover;
     return 0;
 }
-extern "C" int emu_bam_get_runs(void *sv, md_bam_run *runs, uint32_t cap) { Emu *s = (Emu *) sv; for (size_t k = 0; k < s->runs.size() && k < cap; ++k) runs[k] = s->runs[k]; return (int) s->runs.size(); }
+extern "C" int emu_bam_push_begin(void *sv, const void *comp, uint64_t comp_bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip) {
+    Emu *e = (Emu *) sv;
+    if (e->pending) { g_emu_err = "a push is already in flight"; return -4; }
+    e->target = e->have ? (e->cur_seg ^ 1) : 0;
+    e->pending_rc = push_impl(e, &e->seg[e->target], e->have ? &e->seg[e->cur_seg] : nullptr, comp, comp_bytes, blocks, n_blocks, skip, &e->pending_sum);
+    e->pending = true;
+    return 0;
+}
+extern "C" int emu_bam_push_end(void *sv, md_bam_summary *out) {
+    Emu *e = (Emu *) sv;
+    if (!e->pending) { g_emu_err = "nothing in flight"; return -4; }
+    e->pending = false;
+    if (e->pending_rc) return e->pending_rc;
+    e->cur_seg = e->target; e->have = true;
+    if (out) *out = e->pending_sum;
+    return 0;
+}
+extern "C" int emu_bam_push(void *sv, const void *comp, uint64_t comp_bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip, md_bam_summary *out) {
+    int rc = emu_bam_push_begin(sv, comp, comp_bytes, blocks, n_blocks, skip);
+    return rc ? rc : emu_bam_push_end(sv, out);
+}
+extern "C" int emu_bam_get_runs(void *sv, md_bam_run *runs, uint32_t cap) { Emu *e = (Emu *) sv; if (!e->have) return 0; const Seg &s = e->seg[e->cur_seg]; for (size_t k = 0; k < s.runs.size() && k < cap; ++k) runs[k] = s.runs[k]; return (int) s.runs.size(); }
 
 static int build(Emu *s, int run, const md_tile_desc *t, uint32_t keep_hi) {
     Tile &P = s->tile[s->cur], &N = s->tile[s->cur ^ 1];
     mdbam::TileSrc S; memset(&S, 0, sizeof S);
-    S.u = s->ubuf.data(); S.rec_off = s->rec_off.data(); S.pos = s->pos.data(); S.rend = s->rend.data();
+    const Seg &G = s->seg[s->cur_seg];
+    S.u = G.ubuf.data(); S.rec_off = G.rec_off.data(); S.pos = G.pos.data(); S.rend = G.rend.data();
     if (run >= 0) {
-        if (!s->have || (size_t) run >= s->runs.size()) { g_emu_err = "no such run"; return -2; }
-        const md_bam_run &r = s->runs[(size_t) run];
+        if (!s->have || (size_t) run >= G.runs.size()) { g_emu_err = "no such run"; return -2; }
+        const md_bam_run &r = G.runs[(size_t) run];
         if (r.tid != t->tid) { g_emu_err = "tile and run are on different contigs"; return -2; }
         S.r0 = r.start; S.n_own = r.n;
     }

@@ -42,6 +42,8 @@ def emu():
         e.emu_bam_reset.argtypes = [C.c_void_p]; e.emu_bam_reset.restype = None
         e.emu_bam_push.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(A.MdBgzfBlock), C.c_uint32, C.c_uint32, C.POINTER(A.MdBamSummary)]
         e.emu_bam_get_runs.argtypes = [C.c_void_p, C.POINTER(A.MdBamRun), C.c_uint32]
+        e.emu_bam_push_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(A.MdBgzfBlock), C.c_uint32, C.c_uint32]
+        e.emu_bam_push_end.argtypes = [C.c_void_p, C.POINTER(A.MdBamSummary)]
         e.emu_bam_extract_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(A.MdTileDesc), C.c_uint32, C.POINTER(A.MdCall), C.c_uint64, C.POINTER(A.MdTileStats)]
         e.emu_bam_mbias_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(A.MdTileDesc), C.c_uint32, C.POINTER(A.MdTileStats)]
         e.emu_bam_tile_view.argtypes = [C.c_void_p, C.POINTER(A.MdReadsSoa)]
@@ -54,7 +56,7 @@ def emu():
 class OracleBackend:
     """mdh_backend whose slots call the oracle port. Keeps the callbacks alive."""
 
-    def __init__(self, device_decode=False):
+    def __init__(self, device_decode=False, overlapped=True):
         o = lib()
         self.state = {}
         st = self.state
@@ -116,6 +118,10 @@ class OracleBackend:
                      A.BAM_MBIAS_FN(lambda s_, run, td, kh, st_: e.emu_bam_mbias_run(s_, run, td, kh, st_))]
             self._keep += extra
             self.be.bam_open, self.be.bam_close, self.be.bam_reset, self.be.bam_push, self.be.bam_get_runs, self.be.bam_extract_run, self.be.bam_mbias_run = extra
+            if overlapped:
+                two = [A.BAM_PUSH_BEGIN_FN(lambda s_, c, n, bl, nb, sk: e.emu_bam_push_begin(s_, c, n, bl, nb, sk)), A.BAM_PUSH_END_FN(lambda s_, o_: e.emu_bam_push_end(s_, o_))]
+                self._keep += two
+                self.be.bam_push_begin, self.be.bam_push_end = two
 
 
 def run_host_main(which, argv, backend):

@@ -15,8 +15,9 @@ from util import run_ref, compare_outputs
 
 
 def _host_main(sub, argv, env):
+    overlapped = env.pop("OVERLAPPED", "1") == "1"           # two-phase push (segment k+1 decoded while segment k's tiles are built) or the plain one
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import oracle_binding as ob; "
-            "sys.exit(ob.run_host_main(%r, %r, ob.OracleBackend(device_decode=True)))") % (cases.ROOT, os.path.join(cases.ROOT, "tests"), sub, argv)
+            "sys.exit(ob.run_host_main(%r, %r, ob.OracleBackend(device_decode=True, overlapped=%r)))") % (cases.ROOT, os.path.join(cases.ROOT, "tests"), sub, argv, overlapped)
     return subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, MD_DEVICE_DECODE="1", **env))
 
 
@@ -36,6 +37,12 @@ def _extract_both(built, tmp_path, opts, fa, bam, env):
 def test_extract_noisy(built, synth, tmp_path, opts, seg):
     p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
     assert _extract_both(built, tmp_path, opts, p + ".fa", p + ".bam", {"MD_SEGMENT_BYTES": seg}) == []
+
+
+def test_plain_push(built, synth, tmp_path):
+    """back ends without the two-phase push are driven segment by segment"""
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    assert _extract_both(built, tmp_path, ["--CHG", "--mergeContext"], p + ".fa", p + ".bam", {"MD_SEGMENT_BYTES": "70000", "OVERLAPPED": "0"}) == []
 
 
 def test_wrong_guesses_are_repaired(built, synth, tmp_path):
