@@ -199,7 +199,7 @@ static int bam_push_impl(md_bam_stream *s, BamSlot &S, const BamSlot *P, const v
     if (n_blocks) {
         {
             // decoders per warp (MD_INFLATE_DPW: 1, 2, 4, 8, 16 or 32) and warps per CTA chosen so that a CTA's tables stay below 64 KB
-            static const int dpw = [] { const char *e = getenv("MD_INFLATE_DPW"); int v = e ? atoi(e) : 8; return (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 8; }();
+            static const int dpw = [] { const char *e = getenv("MD_INFLATE_DPW"); int v = e ? atoi(e) : 1; return (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 1; }();
             const int warps = std::max(1, std::min(8, (int)(65536 / (sizeof(mdinflate::Tables) * (size_t) dpw))));
             const int dec = dpw * warps; const size_t smem = sizeof(mdinflate::Tables) * (size_t) dec;
             static bool attr_set = false;
