@@ -23,22 +23,17 @@
 namespace {
 using mdbam::BlockScan; using mdbam::TileSrc; using mdbam::TileDst; using mdbam::Sz4;
 
-// One decoder = one thread running inflate_hd.h:inflate_block with its own tables in shared memory.  Deflate decoding is a
-// serial bit-stream walk, so a warp with a single decoder wastes 31/32 of every issued instruction — and issue slots are
-// what this kernel is bound by.  Several decoders per warp (every `stride`-th lane, each on its own BGZF block) share the
-// instruction stream whenever they are in the same phase (literal after literal is the common case) and diverge only for
-// matches and table builds.  `dec_per_cta` decoders, tables in dynamic shared memory.
-__global__ void inflate_kernel(const uint8_t *comp, const md_bgzf_block *blk, const unsigned long long *uoff, uint8_t *ubuf, uint32_t n_blocks, int *err, int stride, int dec_per_cta) {
-    extern __shared__ __align__(16) unsigned char inf_smem[];
-    mdinflate::Tables *T = (mdinflate::Tables *) inf_smem;
-    if (threadIdx.x % stride) return;
-    const int d = threadIdx.x / stride;
-    const uint32_t b = blockIdx.x * dec_per_cta + d;
+// One warp per BGZF block, INF_WARPS blocks per CTA, decoding tables in shared memory.  Deflate decoding is a serial bit-stream
+// walk; all 32 lanes run it redundantly (see inflate_hd.h:inflate_block) and split the match copies between them.
+constexpr int INF_WARPS = 8;
+__global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const uint8_t *comp, const md_bgzf_block *blk, const unsigned long long *uoff, uint8_t *ubuf, uint32_t n_blocks, int *err) {
+    __shared__ mdinflate::Tables T[INF_WARPS];
+    const uint32_t b = blockIdx.x * INF_WARPS + (threadIdx.x >> 5);
     if (b >= n_blocks) return;
-    const md_bgzf_block bd = blk[b];
-    if (bd.isize == 0) return;
-    const int rc = mdinflate::inflate_block(comp, bd.comp_off, bd.comp_len, ubuf + uoff[b], bd.isize, T[d]);
-    if (rc) atomicCAS(err, 0, (int)((b << 4) | (uint32_t)(-rc)));
+    const md_bgzf_block d = blk[b];
+    if (d.isize == 0) return;
+    const int rc = mdinflate::inflate_block(comp, d.comp_off, d.comp_len, ubuf + uoff[b], d.isize, T[threadIdx.x >> 5], (int)(threadIdx.x & 31), 32);
+    if (rc && !(threadIdx.x & 31)) atomicCAS(err, 0, (int)((b << 4) | (uint32_t)(-rc)));
 }
 __global__ void scan_blocks_kernel(const uint8_t *u, const unsigned long long *uoff, uint32_t n_blocks, unsigned long long first, unsigned long long U, int32_t n_targets, BlockScan *out) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -197,15 +192,7 @@ static int bam_push_impl(md_bam_stream *s, BamSlot &S, const BamSlot *P, const v
     const unsigned long long first = D0 + (carry_in ? 0 : skip);
     tm.tick();
     if (n_blocks) {
-        {
-            // decoders per warp (MD_INFLATE_DPW: 1, 2, 4, 8, 16 or 32) and warps per CTA chosen so that a CTA's tables stay below 64 KB
-            static const int dpw = [] { const char *e = getenv("MD_INFLATE_DPW"); int v = e ? atoi(e) : 1; return (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 1; }();
-            const int warps = std::max(1, std::min(8, (int)(65536 / (sizeof(mdinflate::Tables) * (size_t) dpw))));
-            const int dec = dpw * warps; const size_t smem = sizeof(mdinflate::Tables) * (size_t) dec;
-            static bool attr_set = false;
-            if (!attr_set) { cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-            inflate_kernel<<<(n_blocks + dec - 1) / dec, warps * 32, smem, st>>>((const uint8_t *) S.comp.p, (const md_bgzf_block *) S.blk.p, (const unsigned long long *) S.uoff.p, (uint8_t *) S.ubuf.p, n_blocks, (int *)(d_small + 1), 32 / dpw, dec);
-        }
+        inflate_kernel<<<(n_blocks + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, 0, st>>>((const uint8_t *) S.comp.p, (const md_bgzf_block *) S.blk.p, (const unsigned long long *) S.uoff.p, (uint8_t *) S.ubuf.p, n_blocks, (int *)(d_small + 1));
         tm.tick();
         const uint32_t g = (n_blocks + 127) / 128;
         // block 0's slice starts at D0 so that the straddling record is part of its chain

@@ -18,6 +18,11 @@
 #else
 #define MD_HD inline
 #endif
+#if defined(__CUDA_ARCH__)
+#define MD_SYNCWARP() __syncwarp()
+#else
+#define MD_SYNCWARP() ((void) 0)
+#endif
 
 namespace mdinflate {
 
@@ -66,26 +71,37 @@ MD_HD uint32_t bit_reverse(uint32_t v, int n) {
 }
 
 // Canonical Huffman set from code lengths (RFC 1951 3.2.2).  Returns false for an over-subscribed set.
-MD_HD bool build_table(const uint8_t *lens, int n, uint16_t *primary, int root, uint16_t *sorted, uint16_t *count) {
-    for (int i = 0; i < 16; ++i) count[i] = 0;
-    for (int i = 0; i < n; ++i) count[lens[i]]++;
-    count[0] = 0;
+// All lanes of a warp run this with the same arguments; only lane 0 stores to the (shared) tables, with a warp barrier
+// between the phases, so no lane reads a table entry another lane is still writing.
+MD_HD bool build_table(const uint8_t *lens, int n, uint16_t *primary, int root, uint16_t *sorted, uint16_t *count, int lane) {
+    uint16_t cnt[16];
+    for (int i = 0; i < 16; ++i) cnt[i] = 0;
+    for (int i = 0; i < n; ++i) cnt[lens[i]]++;
+    cnt[0] = 0;
     int left = 1;
-    for (int l = 1; l < 16; ++l) { left <<= 1; left -= count[l]; if (left < 0) return false; }
+    for (int l = 1; l < 16; ++l) { left <<= 1; left -= cnt[l]; if (left < 0) return false; }
     uint16_t offs[16]; offs[1] = 0;
-    for (int l = 1; l < 15; ++l) offs[l + 1] = (uint16_t)(offs[l] + count[l]);
-    for (int i = 0; i < n; ++i) if (lens[i]) sorted[offs[lens[i]]++] = (uint16_t) i;
-    for (int i = 0; i < (1 << root); ++i) primary[i] = 0;
-    // assign codes in (length, symbol) order and spread the short ones over the primary table
-    uint32_t code = 0; int idx = 0;
-    for (int l = 1; l <= root; ++l) {
-        for (int k = 0; k < count[l]; ++k, ++idx, ++code) {
-            const uint32_t rev = bit_reverse(code, l);
-            const uint16_t e = (uint16_t)((sorted[idx] << 4) | l);
-            for (uint32_t x = rev; x < (1u << root); x += (1u << l)) primary[x] = e;
-        }
-        code <<= 1;
+    for (int l = 1; l < 15; ++l) offs[l + 1] = (uint16_t)(offs[l] + cnt[l]);
+    MD_SYNCWARP();                                       // nobody is still decoding with the previous tables
+    if (lane == 0) {
+        for (int i = 0; i < 16; ++i) count[i] = cnt[i];
+        for (int i = 0; i < n; ++i) if (lens[i]) sorted[offs[lens[i]]++] = (uint16_t) i;
+        if (root) for (int i = 0; i < (1 << root); ++i) primary[i] = 0;
     }
+    MD_SYNCWARP();
+    // assign codes in (length, symbol) order and spread the short ones over the primary table
+    if (root && lane == 0) {
+        uint32_t code = 0; int idx = 0;
+        for (int l = 1; l <= root; ++l) {
+            for (int k = 0; k < cnt[l]; ++k, ++idx, ++code) {
+                const uint32_t rev = bit_reverse(code, l);
+                const uint16_t e = (uint16_t)((sorted[idx] << 4) | l);
+                for (uint32_t x = rev; x < (1u << root); x += (1u << l)) primary[x] = e;
+            }
+            code <<= 1;
+        }
+    }
+    MD_SYNCWARP();
     return true;
 }
 
@@ -110,7 +126,12 @@ MD_HD int decode_sym(BitReader &b, const uint16_t *primary, int root, const uint
 // Inflate one raw-deflate stream of `in_len` bytes at base+in_off into out[0..out_len).  The stream must produce exactly
 // out_len bytes.  Returns 0, or a negative code: -1 bad block type / stored length, -2 bad code lengths, -3 bad symbol,
 // -4 output overrun, -5 distance before start, -6 output short.
-MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_len, uint8_t *out, uint32_t out_len, Tables &T) {
+//
+// `lane` / `nl`: on the device all 32 lanes of a warp run this function REDUNDANTLY on the same block (identical control
+// flow and register state, so the warp never diverges and the cost is that of one lane); what they share out is the
+// output: lane 0 stores literals, and a match of `len` bytes is copied by all lanes at once (one round of memory latency
+// per 32 bytes instead of one per byte — the byte-serial copy is what bounds a single-lane decoder).  Host: lane 0 of 1.
+MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_len, uint8_t *out, uint32_t out_len, Tables &T, int lane = 0, int nl = 1) {
     BitReader b; br_init(b, base_aligned, in_off, in_len);
     uint32_t op = 0;
     const uint16_t len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -127,7 +148,7 @@ MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_l
             const uint32_t nlen = br_take(b, 16);
             if ((len ^ 0xffffu) != nlen) return -1;
             if (op + len > out_len) return -4;
-            for (uint32_t i = 0; i < len; ++i) { br_fill(b); out[op++] = (uint8_t) br_take(b, 8); }
+            for (uint32_t i = 0; i < len; ++i) { br_fill(b); const uint8_t v = (uint8_t) br_take(b, 8); if (lane == 0) out[op] = v; ++op; }
         } else if (type == 1 || type == 2) {
             uint8_t lens[320];
             int nlit, ndist;
@@ -145,19 +166,9 @@ MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_l
                 uint8_t cl[19];
                 for (int i = 0; i < 19; ++i) cl[i] = 0;
                 for (int i = 0; i < ncl; ++i) { br_fill(b); cl[cl_order[i]] = (uint8_t) br_take(b, 3); }
-                // the code-length alphabet is decoded with the canonical walk only (19 symbols, <= 7 bits);
-                // T.dist_sorted / T.dist_count serve as its scratch until the real distance set is built
-                {
-                    uint16_t *cnt = T.dist_count, *srt = T.dist_sorted;
-                    for (int i = 0; i < 16; ++i) cnt[i] = 0;
-                    for (int i = 0; i < 19; ++i) cnt[cl[i]]++;
-                    cnt[0] = 0;
-                    int left = 1;
-                    for (int l = 1; l < 16; ++l) { left <<= 1; left -= cnt[l]; if (left < 0) return -2; }
-                    uint16_t offs[16]; offs[1] = 0;
-                    for (int l = 1; l < 15; ++l) offs[l + 1] = (uint16_t)(offs[l] + cnt[l]);
-                    for (int i = 0; i < 19; ++i) if (cl[i]) srt[offs[cl[i]]++] = (uint16_t) i;
-                }
+                // the code-length alphabet is decoded with the canonical walk only (19 symbols, <= 7 bits; root 0 = no primary
+                // table); T.dist_sorted / T.dist_count serve as its scratch until the real distance set is built
+                if (!build_table(cl, 19, T.dist, 0, T.dist_sorted, T.dist_count, lane)) return -2;
                 int i = 0;
                 while (i < nlit + ndist) {
                     br_fill(b);
@@ -178,13 +189,13 @@ MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_l
                 // distance lengths follow the literal/length ones; move them to a fixed offset
                 for (int k = ndist - 1; k >= 0; --k) lens[288 + k] = lens[nlit + k];
             }
-            if (!build_table(lens, nlit, T.lit, LIT_ROOT, T.lit_sorted, T.lit_count)) return -2;
-            if (!build_table(lens + 288, ndist, T.dist, DIST_ROOT, T.dist_sorted, T.dist_count)) return -2;
+            if (!build_table(lens, nlit, T.lit, LIT_ROOT, T.lit_sorted, T.lit_count, lane)) return -2;
+            if (!build_table(lens + 288, ndist, T.dist, DIST_ROOT, T.dist_sorted, T.dist_count, lane)) return -2;
             for (;;) {
                 br_fill(b);
                 int sym = decode_sym(b, T.lit, LIT_ROOT, T.lit_sorted, T.lit_count);
                 if (sym < 0) return -3;
-                if (sym < 256) { if (op >= out_len) return -4; out[op++] = (uint8_t) sym; continue; }
+                if (sym < 256) { if (op >= out_len) return -4; if (lane == 0) out[op] = (uint8_t) sym; ++op; continue; }
                 if (sym == 256) break;
                 sym -= 257;
                 if (sym >= 29) return -3;
@@ -196,7 +207,10 @@ MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_l
                 if (dist > op) return -5;
                 if (op + len > out_len) return -4;
                 const uint8_t *src = out + op - dist; uint8_t *dst = out + op;
-                for (uint32_t k = 0; k < len; ++k) dst[k] = src[k];
+                MD_SYNCWARP();                                   // the bytes being copied were stored by other lanes
+                if (dist >= len) { for (uint32_t k = (uint32_t) lane; k < len; k += (uint32_t) nl) dst[k] = src[k]; }
+                else if (nl == 1) { for (uint32_t k = 0; k < len; ++k) dst[k] = src[k]; }
+                else { for (uint32_t k = (uint32_t) lane; k < len; k += (uint32_t) nl) dst[k] = src[k % dist]; }   // overlapping match = the last `dist` bytes repeated
                 op += len;
             }
         } else return -1;
