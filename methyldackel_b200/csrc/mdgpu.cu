@@ -347,9 +347,8 @@ __device__ __forceinline__ void eval_hit(const CountArgs &A, const ReadCtx &rc, 
     if ((int) ql < A.P.minPhred) return;                       // common.c:127 / extract.c:229
     const uint32_t o = (uint32_t)(rp - w0i);
     if (siteG == rc.wantG) {
-        int rv = 0;
-        if (!rc.wantG) { if (b == 2u) rv = 1; else if (b == 8u) rv = -1; }   // common.c:129-130
-        else { if (b == 4u) rv = 1; else if (b == 1u) rv = -1; }             // common.c:131-132
+        // OT/CTOT: C (2) methylated, T (8) unmethylated; OB/CTOB: G (4) methylated, A (1) unmethylated (common.c:129-132)
+        const int rv = (b == (rc.wantG ? 4u : 2u)) ? 1 : ((b == (rc.wantG ? 1u : 8u)) ? -1 : 0);
         if (rv) {
             if (MODE == 2) {
                 const int s1 = rc.strand - 1;
@@ -440,7 +439,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 #define WS_SEQ_BYTES 2560          // default per-warp staging: 32 alignments x 76 B (150-mers) + alignment slack
 #define WS_QUAL_BYTES 5120         // upper bound for the phred staging (32 x 152 B + slack for plain bytes); 2-/4-bit tiles use less
 #define WS_CTX_WORDS 10
-#define WS_QUEUE 192               // two candidate queues of 96 entries per warp (up to 63 left over + 32 new)
+#define WS_QUEUE 448               // candidate queue entries per warp: plain candidates grow from the bottom, in-mate-span ones from the top
+#define WS_EV 2                    // candidates per lane per evaluate round
 #define WS_WARPS 8
 
 struct WarpLayout { uint32_t off_bm, off_cnt, off_warp, warp_stride, off_seq, off_qual, off_ctx, off_queue, total; };
@@ -462,8 +462,9 @@ __host__ __device__ inline WarpLayout warp_layout(uint32_t W, int mode, uint32_t
 //  0: staged seq byte offset | staged qual byte offset << 16
 //  1: flags: bit0 wantG, bit1 rd2, bit2 has mate, bit3 is_a, bit4 mate_simple, bits8-10 strand
 //  2: mpos   3: mend   4: msoff   5: mqoff   6: mlo | mhi << 16   7: mk0   8: mk1
-template <int MODE, int EV>
+template <int MODE, int GEN>
 __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
+    constexpr int EV = WS_EV;
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t W = A.W, NW = W >> 5;
     const WarpLayout SL = warp_layout(W, MODE, A.wide, A.st_seq, A.st_qual);
@@ -561,6 +562,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
     } else {
         uint64_t *bar = bars + warp;
         uint32_t phase = 0;
+        int maxbits = 256;                                                // GEN 1: longest segment a lane takes per round (adapts to the site density)
         for (;;) {
             uint32_t b = 0;
             if (lane == 0) b = atomicAdd(ticket, 1u);
@@ -617,86 +619,180 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
             __syncwarp();                                              // context words visible to the whole warp
 
             // -- GENERATE / EVALUATE
-            // iterator over this lane's candidate bases: current match op [a,b) (clipped), bitmap word wi, remaining bits cur
+            // one queued candidate -> call / evidence.  MATE candidates carry the mate descriptor of their alignment.
+            auto eval_entry = [&](uint32_t en, bool with_mate) {
+                const int src = en & 31u, rel = (en >> 5) & 0xfffu, qi = (en >> 17) & 0x3fffu; const bool is_opp = en >> 31;
+                const uint32_t *cx = rctx + WS_CTX_WORDS * src;
+                const uint32_t c0w = cx[0], c1w = cx[1];
+                ReadCtx hc;
+                hc.wantG = c1w & 1u; hc.rd2 = (c1w >> 1) & 1u; hc.strand = (c1w >> 8) & 7u; hc.mi = with_mate ? 0 : -1;
+                if (with_mate) {
+                    hc.is_a = (c1w & 8u) != 0; hc.mate_simple = (c1w & 16u) != 0;
+                    hc.mpos = (int) cx[2]; hc.mend = (int) cx[3]; hc.msoff = cx[4]; hc.mqoff = cx[5]; hc.mlo = (int)(cx[6] & 0xffffu); hc.mhi = (int)(cx[6] >> 16); hc.mk0 = cx[7]; hc.mk1 = cx[8];
+                }
+                const unsigned byte = sseq[(c0w & 0xffffu) + (qi >> 1)];
+                const unsigned bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4), ql = staged_qual(R, squal + (c0w >> 16), qi);
+                if (with_mate) eval_hit<MODE, true>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
+                else eval_hit<MODE, false>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
+            };
+            // iterator over this lane's candidate bases: current match op [ra,rb) (clipped, window-relative), bitmap word wi, remaining bits cur
             const uint32_t *own_bm = rc.wantG ? bmG : bmC, *opp_bm = rc.wantG ? bmC : bmG;
-            uint32_t k = k0; int p = pos, q = 0, opq = 0, opp_ = 0, ra = 0, rb = 0, wi = 0; unsigned cur = 0, curo = 0; bool in_op = false;
+            uint32_t k = k0; int p = pos, q = 0, ra = 0, rb = 0, wi = 0; unsigned cur = 0, curo = 0; bool in_op = false;
             bool done = !(live && !direct);
-            uint32_t qa = 0, qb2 = 0;                                   // queued candidates: plain / inside the mate's span (warp-uniform)
-            uint32_t *queueB = queue + WS_QUEUE / 2;
-            for (;;) {
-                // advance to the next candidate (divergent, cheap)
-                bool has = false; uint32_t ent = 0; bool inmate = false;
-                while (!done) {
-                    if (cur | curo) {
-                        const unsigned any = cur | curo; const int bit = __ffs(any) - 1;
-                        const bool is_own = (cur >> bit) & 1u;
-                        cur &= ~(1u << bit); curo &= ~(1u << bit);
-                        const int rel = (wi << 5) + bit, qi = opq + (w0i + rel - opp_);
-                        ent = (uint32_t) lane | ((uint32_t) rel << 5) | ((uint32_t) qi << 17) | (is_own ? 0u : 0x80000000u);
-                        inmate = rc.mi >= 0 && (w0i + rel) >= rc.mpos && (w0i + rel) < rc.mend;
-                        has = true; break;
+            if constexpr (GEN == 1) {
+                // Segment-at-a-time generator.  A round: every lane holds ONE segment of its current match op — a run of reference
+                // positions that lies entirely outside or entirely inside the mate's span, at most `maxbits` long.  The lanes count the
+                // kept sites of their segment in the window bitmaps (popc per word), the counts (plain | in-mate-span, packed in one
+                // register) are prefix-summed across the warp, and every lane then writes its candidates to its own slice of the queue:
+                // no ballot per candidate, and the divergent CIGAR walk runs once per op instead of once per base.
+                // Plain candidates are stacked from the bottom of the queue, in-mate-span ones (global look-ups) from the top.
+                int qrel = 0;                                              // query index = window-relative position + qrel inside the current op
+                uint32_t qa = 0, qb2 = 0;
+                const bool has_mate = rc.mi >= 0;
+                const int mrel0 = has_mate ? rc.mpos - w0i : 0, mrel1 = has_mate ? rc.mend - w0i : 0;
+                for (;;) {
+                    while (!done && !in_op) {
+                        if (k >= k1) { done = true; break; }
+                        const uint32_t c = (k == k0) ? c0 : __ldg(R.cigar + k), op = c & 15u; const int len = (int)(c >> 4);
+                        ++k;
+                        if (op == 0 || op == 7 || op == 8) {
+                            const int a = max(max(p, w0i), p + (rc.lo - q)), bnd = min(min(p + len, w0i + own), p + (rc.hi - q));
+                            if (bnd > a) { ra = a - w0i; rb = bnd - w0i; qrel = q - (p - w0i); in_op = true; }
+                            p += len; q += len;
+                        } else if (op == 1 || op == 4) q += len;
+                        else if (op == 2 || op == 3) p += len;
                     }
-                    if (in_op && wi < ((rb - 1) >> 5)) {
-                        ++wi;
-                        unsigned keep = 0xffffffffu;
-                        if (wi == ((rb - 1) >> 5)) keep &= 0xffffffffu >> (31 - ((rb - 1) & 31));
-                        cur = own_bm[wi + 1] & keep; curo = (MODE == 1) ? (opp_bm[wi + 1] & keep) : 0u;
-                        continue;
+                    const bool all_done = !__any_sync(0xffffffffu, in_op);     // every lane ran out of match ops: the batch is exhausted
+                    // this round's segment [ra, se)
+                    int sb = ra; bool tB = false;
+                    if (in_op) {
+                        sb = rb;
+                        if (has_mate) { if (ra < mrel0) sb = min(rb, mrel0); else if (ra < mrel1) { sb = min(rb, mrel1); tB = true; } }
                     }
-                    in_op = false;
-                    if (k >= k1) { done = true; break; }
-                    const uint32_t c = (k == k0) ? c0 : __ldg(R.cigar + k), op = c & 15u; const int len = (int)(c >> 4);
-                    ++k;
-                    if (op == 0 || op == 7 || op == 8) {
-                        const int a = max(max(p, w0i), p + (rc.lo - q)), bnd = min(min(p + len, w0i + own), p + (rc.hi - q));
-                        if (bnd > a) {
-                            ra = a - w0i; rb = bnd - w0i; wi = ra >> 5; in_op = true; opq = q; opp_ = p;
-                            unsigned keep = 0xffffffffu << (ra & 31);
+                    const uint32_t room = WS_QUEUE - qa - qb2;
+                    int se; uint32_t v, inc, tot;
+                    for (;;) {
+                        se = min(sb, ra + maxbits);
+                        uint32_t n = 0;
+                        if (se > ra) {
+                            const int wa = ra >> 5, wb = (se - 1) >> 5;
+                            for (int w = wa; w <= wb; ++w) {
+                                unsigned m = own_bm[w + 1]; if (MODE == 1) m |= opp_bm[w + 1];
+                                if (w == wa) m &= 0xffffffffu << (ra & 31);
+                                if (w == wb) m &= 0xffffffffu >> (31 - ((se - 1) & 31));
+                                n += (uint32_t) __popc(m);
+                            }
+                        }
+                        v = tB ? (n << 16) : n;
+                        inc = v;
+                        #pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                        tot = __shfl_sync(0xffffffffu, inc, 31);
+                        if ((tot & 0xffffu) + (tot >> 16) <= room || maxbits <= 8) break;
+                        maxbits >>= 1;                                        // unusually site-dense: shorter segments (8 positions per lane always fit)
+                    }
+                    if (((tot & 0xffffu) + (tot >> 16)) * 4u < room && maxbits < 256) maxbits <<= 1;
+                    if (se > ra) {
+                        const uint32_t ex = inc - v;
+                        uint32_t *dst = tB ? queue + (WS_QUEUE - 1u - (qb2 + (ex >> 16))) : queue + (qa + (ex & 0xffffu));
+                        const int dir = tB ? -1 : 1;
+                        const uint32_t base = (uint32_t) lane + ((uint32_t) qrel << 17);
+                        const int wa = ra >> 5, wb = (se - 1) >> 5;
+                        for (int w = wa; w <= wb; ++w) {
+                            const unsigned mo = own_bm[w + 1]; unsigned m = mo; if (MODE == 1) m |= opp_bm[w + 1];
+                            if (w == wa) m &= 0xffffffffu << (ra & 31);
+                            if (w == wb) m &= 0xffffffffu >> (31 - ((se - 1) & 31));
+                            const uint32_t entw = base + (uint32_t)(w << 5) * 0x20020u;
+                            while (m) {
+                                const int bit = __ffs(m) - 1; m &= m - 1u;
+                                uint32_t ent = entw + (uint32_t) bit * 0x20020u;
+                                if (MODE == 1) ent |= ((mo >> bit) & 1u) ? 0u : 0x80000000u;
+                                *dst = ent; dst += dir;
+                            }
+                        }
+                        ra = se; if (ra >= rb) in_op = false;
+                    }
+                    qa += tot & 0xffffu; qb2 += tot >> 16;
+                    __syncwarp();
+                    while (qa >= 32u * EV || (all_done && qa > 0u)) {
+                        const uint32_t take = min(qa, 32u * EV);
+                        #pragma unroll
+                        for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take) eval_entry(queue[qa - take + lane + 32 * r], false);
+                        qa -= take;
+                        __syncwarp();
+                    }
+                    while (qb2 >= 32u * EV || (all_done && qb2 > 0u)) {
+                        const uint32_t take = min(qb2, 32u * EV);
+                        #pragma unroll
+                        for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take) eval_entry(queue[WS_QUEUE - qb2 + lane + 32 * r], true);
+                        qb2 -= take;
+                        __syncwarp();
+                    }
+                    if (all_done) break;
+                }
+            } else {
+                int opq = 0, opp_ = 0;
+                uint32_t qa = 0, qb2 = 0;                                   // queued candidates: plain / inside the mate's span (warp-uniform)
+                uint32_t *queueB = queue + WS_QUEUE / 2;
+                for (;;) {
+                    // advance to the next candidate (divergent, cheap)
+                    bool has = false; uint32_t ent = 0; bool inmate = false;
+                    while (!done) {
+                        if (cur | curo) {
+                            const unsigned any = cur | curo; const int bit = __ffs(any) - 1;
+                            const bool is_own = (cur >> bit) & 1u;
+                            cur &= ~(1u << bit); curo &= ~(1u << bit);
+                            const int rel = (wi << 5) + bit, qi = opq + (w0i + rel - opp_);
+                            ent = (uint32_t) lane | ((uint32_t) rel << 5) | ((uint32_t) qi << 17) | (is_own ? 0u : 0x80000000u);
+                            inmate = rc.mi >= 0 && (w0i + rel) >= rc.mpos && (w0i + rel) < rc.mend;
+                            has = true; break;
+                        }
+                        if (in_op && wi < ((rb - 1) >> 5)) {
+                            ++wi;
+                            unsigned keep = 0xffffffffu;
                             if (wi == ((rb - 1) >> 5)) keep &= 0xffffffffu >> (31 - ((rb - 1) & 31));
                             cur = own_bm[wi + 1] & keep; curo = (MODE == 1) ? (opp_bm[wi + 1] & keep) : 0u;
+                            continue;
                         }
-                        p += len; q += len;
-                    } else if (op == 1 || op == 4) q += len;
-                    else if (op == 2 || op == 3) p += len;
-                }
-                // candidates that need the mate's base/phred (global-memory look-ups) are queued apart, so that their latency
-                // is paid once per 32 look-ups instead of once per round
-                const unsigned hmA = __ballot_sync(0xffffffffu, has && !inmate), hmB = __ballot_sync(0xffffffffu, has && inmate);
-                if (has) { if (inmate) queueB[qb2 + __popc(hmB & ((1u << lane) - 1u))] = ent; else queue[qa + __popc(hmA & ((1u << lane) - 1u))] = ent; }
-                qa += __popc(hmA); qb2 += __popc(hmB);
-                const bool all_done = (hmA | hmB) == 0u;                  // no lane produced anything: every iterator is exhausted
-                __syncwarp();
-                // one queued candidate -> call / evidence.  MATE candidates carry the mate descriptor of their alignment.
-                auto eval_entry = [&](uint32_t en, bool with_mate) {
-                    const int src = en & 31u, rel = (en >> 5) & 0xfffu, qi = (en >> 17) & 0x3fffu; const bool is_opp = en >> 31;
-                    const uint32_t *cx = rctx + WS_CTX_WORDS * src;
-                    const uint32_t c0w = cx[0], c1w = cx[1];
-                    ReadCtx hc;
-                    hc.wantG = c1w & 1u; hc.rd2 = (c1w >> 1) & 1u; hc.strand = (c1w >> 8) & 7u; hc.mi = with_mate ? 0 : -1;
-                    if (with_mate) {
-                        hc.is_a = (c1w & 8u) != 0; hc.mate_simple = (c1w & 16u) != 0;
-                        hc.mpos = (int) cx[2]; hc.mend = (int) cx[3]; hc.msoff = cx[4]; hc.mqoff = cx[5]; hc.mlo = (int)(cx[6] & 0xffffu); hc.mhi = (int)(cx[6] >> 16); hc.mk0 = cx[7]; hc.mk1 = cx[8];
+                        in_op = false;
+                        if (k >= k1) { done = true; break; }
+                        const uint32_t c = (k == k0) ? c0 : __ldg(R.cigar + k), op = c & 15u; const int len = (int)(c >> 4);
+                        ++k;
+                        if (op == 0 || op == 7 || op == 8) {
+                            const int a = max(max(p, w0i), p + (rc.lo - q)), bnd = min(min(p + len, w0i + own), p + (rc.hi - q));
+                            if (bnd > a) {
+                                ra = a - w0i; rb = bnd - w0i; wi = ra >> 5; in_op = true; opq = q; opp_ = p;
+                                unsigned keep = 0xffffffffu << (ra & 31);
+                                if (wi == ((rb - 1) >> 5)) keep &= 0xffffffffu >> (31 - ((rb - 1) & 31));
+                                cur = own_bm[wi + 1] & keep; curo = (MODE == 1) ? (opp_bm[wi + 1] & keep) : 0u;
+                            }
+                            p += len; q += len;
+                        } else if (op == 1 || op == 4) q += len;
+                        else if (op == 2 || op == 3) p += len;
                     }
-                    const unsigned byte = sseq[(c0w & 0xffffu) + (qi >> 1)];
-                    const unsigned bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4), ql = staged_qual(R, squal + (c0w >> 16), qi);
-                    if (with_mate) eval_hit<MODE, true>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
-                    else eval_hit<MODE, false>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
-                };
-                while (qa >= 32u * EV || (all_done && qa > 0u)) {
-                    const uint32_t take = min(qa, 32u * EV);
-                    #pragma unroll
-                    for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take) eval_entry(queue[qa - take + lane + 32 * r], false);
-                    qa -= take;
+                    // candidates that need the mate's base/phred (global-memory look-ups) are queued apart, so that their latency
+                    // is paid once per 32 look-ups instead of once per round
+                    const unsigned hmA = __ballot_sync(0xffffffffu, has && !inmate), hmB = __ballot_sync(0xffffffffu, has && inmate);
+                    if (has) { if (inmate) queueB[qb2 + __popc(hmB & ((1u << lane) - 1u))] = ent; else queue[qa + __popc(hmA & ((1u << lane) - 1u))] = ent; }
+                    qa += __popc(hmA); qb2 += __popc(hmB);
+                    const bool all_done = (hmA | hmB) == 0u;                  // no lane produced anything: every iterator is exhausted
                     __syncwarp();
+                    while (qa >= 32u * EV || (all_done && qa > 0u)) {
+                        const uint32_t take = min(qa, 32u * EV);
+                        #pragma unroll
+                        for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take) eval_entry(queue[qa - take + lane + 32 * r], false);
+                        qa -= take;
+                        __syncwarp();
+                    }
+                    while (qb2 >= 32u * EV || (all_done && qb2 > 0u)) {
+                        const uint32_t take = min(qb2, 32u * EV);
+                        #pragma unroll
+                        for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take) eval_entry(queueB[qb2 - take + lane + 32 * r], true);
+                        qb2 -= take;
+                        __syncwarp();
+                    }
+                    if (all_done) break;
                 }
-                while (qb2 >= 32u * EV || (all_done && qb2 > 0u)) {
-                    const uint32_t take = min(qb2, 32u * EV);
-                    #pragma unroll
-                    for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take) eval_entry(queueB[qb2 - take + lane + 32 * r], true);
-                    qb2 -= take;
-                    __syncwarp();
-                }
-                if (all_done) break;
             }
             // -- alignments outside the staged range: the lane walks it alone, from global memory
             if (direct) {
@@ -852,7 +948,7 @@ struct md_ctx {
     uint32_t *d_hist = nullptr; int32_t *d_lens = nullptr;
     uint64_t launches = 0;
     uint32_t W = 4096;
-    int ev = 2;                          // candidates per lane per evaluate round (count_warp<MODE, EV>); 2 measured ~2 % faster than 1
+    int gen = 1;                         // count_warp<MODE, GEN>: 1 = word-at-a-time candidate generator, 0 = one candidate per lane per ballot (kept for A/B runs)
 };
 
 static void sync_all(md_ctx *c) { for (int k = 0; k < MD_NLANES; ++k) if (c->lanes[k].stream) cudaStreamSynchronize(c->lanes[k].stream); }
@@ -889,10 +985,10 @@ extern "C" md_ctx *md_create(const md_config *cfg, int device) {
     cudaFuncSetAttribute(count_warp<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
     cudaFuncSetAttribute(count_warp<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
     cudaFuncSetAttribute(count_warp<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
-    cudaFuncSetAttribute(count_warp<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
-    cudaFuncSetAttribute(count_warp<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
-    cudaFuncSetAttribute(count_warp<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
-    if (const char *v = getenv("MD_EV")) { int e = atoi(v); if (e == 1 || e == 2) c->ev = e; }
+    cudaFuncSetAttribute(count_warp<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
+    cudaFuncSetAttribute(count_warp<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
+    cudaFuncSetAttribute(count_warp<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
+    if (const char *v = getenv("MD_GEN")) { int e = atoi(v); if (e == 0 || e == 1) c->gen = e; }
     cudaStreamSynchronize(L->stream);
     return c;
 }
@@ -1004,14 +1100,14 @@ static int launch_count(md_ctx *c, Lane *L, const Contig &g, const DevReads &R, 
     A.st_seq = WS_SEQ_BYTES; A.st_qual = std::min<uint32_t>(WS_QUAL_BYTES, 32u * (((160u * R.qbits + 63u) >> 6) * 8u) + 32u);
     A.wide = wide ? 1u : 0u;
     const size_t sm = warp_layout(W, mode, A.wide, A.st_seq, A.st_qual).total;
-    if (c->ev == 2) {
-        if (mode == 2) count_warp<2, 2><<<n_win, WS_WARPS * 32, sm, s>>>(A);
-        else if (mode == 1) count_warp<1, 2><<<n_win, WS_WARPS * 32, sm, s>>>(A);
-        else count_warp<0, 2><<<n_win, WS_WARPS * 32, sm, s>>>(A);
-    } else {
+    if (c->gen == 1) {
         if (mode == 2) count_warp<2, 1><<<n_win, WS_WARPS * 32, sm, s>>>(A);
         else if (mode == 1) count_warp<1, 1><<<n_win, WS_WARPS * 32, sm, s>>>(A);
         else count_warp<0, 1><<<n_win, WS_WARPS * 32, sm, s>>>(A);
+    } else {
+        if (mode == 2) count_warp<2, 0><<<n_win, WS_WARPS * 32, sm, s>>>(A);
+        else if (mode == 1) count_warp<1, 0><<<n_win, WS_WARPS * 32, sm, s>>>(A);
+        else count_warp<0, 0><<<n_win, WS_WARPS * 32, sm, s>>>(A);
     }
     c->launches += 1;
     if (!mbias) {

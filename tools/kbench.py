@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Kernel A/B bench (development aid): device-resident pipeline timings per count-kernel variant and workload.
-usage: python tools/kbench.py [--variants 1,2] [--steps 10] [--panel]   (variants = MD_EV values: candidates per lane per evaluate round)"""
+usage: python tools/kbench.py [--variants 1,2] [--steps 10] [--panel]   (variants = MD_GEN values: candidate generator of count_warp)"""
 import argparse
 import json
 import os
@@ -24,9 +24,10 @@ def dataset(name, args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--variants", default="1,2")
+    ap.add_argument("--variants", default="0,1")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--panel", action="store_true")
+    ap.add_argument("--only", default="", help="comma list of option-set names (cpg,all,var) to run")
     a = ap.parse_args()
     sets = [("c2", ["--contigs", "chr1:10000000", "--depth", "30"], "chr1")]
     if a.panel:
@@ -38,9 +39,11 @@ def main():
         ref = api.fetch_contig(p + ".fa", contig)
         soa = b.read_region(0)
         for cname, cfg in cfgs:
+            if a.only and cname not in a.only.split(","):
+                continue
             base = None
             for v in a.variants.split(","):
-                os.environ["MD_EV"] = v
+                os.environ["MD_GEN"] = v
                 g = api.GpuContext(cfg)
                 g.load_contig(0, ref)
                 d = g.upload(soa)
