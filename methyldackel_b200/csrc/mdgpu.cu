@@ -290,9 +290,18 @@ struct CountArgs {
     uint32_t *hist; int32_t *lens;                         // mbias
     uint32_t st_seq, st_qual;                              // per-warp staging capacities in bytes (count_warp)
     uint32_t wide;                                         // 1: 32-bit window counters; 0: 16-bit pairs packed in one word (overflow -> rerun wide)
+    uint32_t ablate;                                       // timing experiments only (MD_ABLATE): 1 skip evaluation, 2 skip generation, 4 skip staging copies
+    uint32_t okmask;                                       // 2-/4-bit phred tiles: bit c set when code c decodes to a phred >= minPhred
 };
 
 #define MB_SM_Q 256   // mbias: query positions < this are histogrammed in shared memory
+
+// phred gate (common.c:127) on a staged phred column without decoding the value: packed codes are looked up in okmask
+__device__ __forceinline__ bool staged_pass(const CountArgs &A, const unsigned char *p, int q) {
+    if (A.R.qbits == 8u) return (int) p[q] >= A.P.minPhred;
+    if (A.R.qbits == 2u) return (A.okmask >> ((p[q >> 2] >> ((q & 3) << 1)) & 3u)) & 1u;
+    return (A.okmask >> ((p[q >> 1] >> ((q & 1) << 2)) & 15u)) & 1u;
+}
 
 // K4.  MODE 0: extract, 1: extract with variant filter, 2: mbias.
 //
@@ -322,6 +331,35 @@ __device__ __forceinline__ void load_mate(const CountArgs &A, uint32_t i, int mi
     if (rc.mk1 - rc.mk0 == 1) { uint32_t op = __ldg(R.cigar + rc.mk0) & 15u; rc.mate_simple = (op == 0 || op == 7 || op == 8); }
 }
 
+// A base that passed the phred gate on a kept-context column: call (common.c:118-134) or variant evidence (extract.c:225-239).
+// ovf: the window holds enough alignments for a packed 16-bit counter to wrap, so the wrap test is needed.
+template <int MODE>
+__device__ __forceinline__ void eval_plain(const CountArgs &A, int strand, int rd2, bool wantG, uint32_t *cnt, uint32_t W, uint32_t o, int qi, unsigned b, bool siteG, bool ovf) {
+    if (siteG == wantG) {
+        // OT/CTOT: C (2) methylated, T (8) unmethylated; OB/CTOB: G (4) methylated, A (1) unmethylated (common.c:129-132)
+        const int rv = (b == (wantG ? 4u : 2u)) ? 1 : ((b == (wantG ? 1u : 8u)) ? -1 : 0);
+        if (rv) {
+            if (MODE == 2) {
+                const int s1 = strand - 1;
+                if (qi < MB_SM_Q) atomicAdd(cnt + (((s1 * 2 + rd2) * MB_SM_Q + qi) * 2 + (rv < 0 ? 1 : 0)), 1u);
+                else if (qi < MD_MBIAS_MAXLEN) atomicAdd(A.hist + ((((size_t) s1 * 2 + rd2) * MD_MBIAS_MAXLEN + qi) * 2 + (rv < 0 ? 1 : 0)), 1u);
+                if (qi < MD_MBIAS_MAXLEN) atomicMax(A.lens + s1, qi + 1);
+            } else if (A.wide) atomicAdd(cnt + (rv > 0 ? o : W + o), 1u);
+            else {                                                // meth in the low half, unmeth in the high half of one word
+                const uint32_t old = atomicAdd(cnt + o, rv > 0 ? 1u : 0x10000u);
+                if (ovf && (rv > 0 ? (old & 0xffffu) : (old >> 16)) == 0xffffu) atomicExch(A.counters + C_OVERFLOW, 3u);   // a 16-bit field wrapped: the host reruns the tile wide
+            }
+        }
+    } else if (MODE == 1) {                                     // isVariant, extract.c:225-239
+        const bool var = wantG ? (b != 2u && b != 15u) : (b != 4u && b != 15u);
+        if (A.wide) { atomicAdd(cnt + 2 * W + o, 1u); if (var) atomicAdd(cnt + 3 * W + o, 1u); }
+        else {                                                    // nOff low half, nVariant high half
+            const uint32_t old = atomicAdd(cnt + W + o, var ? 0x10001u : 1u);
+            if (ovf && (old & 0xffffu) == 0xffffu) atomicExch(A.counters + C_OVERFLOW, 3u);
+        }
+    }
+}
+
 // One base that sits on a kept-context column: overlap merge, phred gate, call / variant evidence.
 // b / ql are the read's own base and phred AFTER trimming.  (overlaps.c:81-114, common.c:118-134, extract.c:225-239)
 template <int MODE, bool MATE = true>
@@ -345,30 +383,7 @@ __device__ __forceinline__ void eval_hit(const CountArgs &A, const ReadCtx &rc, 
         }
     }
     if ((int) ql < A.P.minPhred) return;                       // common.c:127 / extract.c:229
-    const uint32_t o = (uint32_t)(rp - w0i);
-    if (siteG == rc.wantG) {
-        // OT/CTOT: C (2) methylated, T (8) unmethylated; OB/CTOB: G (4) methylated, A (1) unmethylated (common.c:129-132)
-        const int rv = (b == (rc.wantG ? 4u : 2u)) ? 1 : ((b == (rc.wantG ? 1u : 8u)) ? -1 : 0);
-        if (rv) {
-            if (MODE == 2) {
-                const int s1 = rc.strand - 1;
-                if (qi < MB_SM_Q) atomicAdd(cnt + (((s1 * 2 + rc.rd2) * MB_SM_Q + qi) * 2 + (rv < 0 ? 1 : 0)), 1u);
-                else if (qi < MD_MBIAS_MAXLEN) atomicAdd(A.hist + ((((size_t) s1 * 2 + rc.rd2) * MD_MBIAS_MAXLEN + qi) * 2 + (rv < 0 ? 1 : 0)), 1u);
-                if (qi < MD_MBIAS_MAXLEN) atomicMax(A.lens + s1, qi + 1);
-            } else if (A.wide) atomicAdd(cnt + (rv > 0 ? o : W + o), 1u);
-            else {                                                // meth in the low half, unmeth in the high half of one word
-                const uint32_t old = atomicAdd(cnt + o, rv > 0 ? 1u : 0x10000u);
-                if ((rv > 0 ? (old & 0xffffu) : (old >> 16)) == 0xffffu) atomicExch(A.counters + C_OVERFLOW, 3u);   // a 16-bit field wrapped: the host reruns the tile wide
-            }
-        }
-    } else if (MODE == 1) {                                     // isVariant, extract.c:225-239
-        const bool var = rc.wantG ? (b != 2u && b != 15u) : (b != 4u && b != 15u);
-        if (A.wide) { atomicAdd(cnt + 2 * W + o, 1u); if (var) atomicAdd(cnt + 3 * W + o, 1u); }
-        else {                                                    // nOff low half, nVariant high half
-            const uint32_t old = atomicAdd(cnt + W + o, var ? 0x10001u : 1u);
-            if ((old & 0xffffu) == 0xffffu) atomicExch(A.counters + C_OVERFLOW, 3u);
-        }
-    }
+    eval_plain<MODE>(A, rc.strand, rc.rd2, rc.wantG, cnt, W, (uint32_t)(rp - w0i), qi, b, siteG, true);
 }
 
 // General path: any CIGAR.  The whole warp walks one alignment, lanes stride over the bases of each match op.
@@ -462,6 +477,7 @@ __host__ __device__ inline WarpLayout warp_layout(uint32_t W, int mode, uint32_t
 //  0: staged seq byte offset | staged qual byte offset << 16
 //  1: flags: bit0 wantG, bit1 rd2, bit2 has mate, bit3 is_a, bit4 mate_simple, bits8-10 strand
 //  2: mpos   3: mend   4: msoff   5: mqoff   6: mlo | mhi << 16   7: mk0   8: mk1
+//  9: all a plain candidate needs: staged seq word offset | staged qual 8-byte offset << 10 | wantG << 20 | rd2 << 21 | strand << 22
 template <int MODE, int GEN>
 __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
     constexpr int EV = WS_EV;
@@ -592,6 +608,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
             uint32_t qw_end = min(__shfl_sync(0xffffffffu, qoff, last) + qual_words_of(R, lql), R.qual_words);
             uint32_t sbytes = sw_end > sw0 ? (sw_end - sw0) * 4u : 0u, qbytes = qw_end > qw0 ? (qw_end - qw0) * 8u : 0u;
             sbytes = min((sbytes + 15u) & ~15u, A.st_seq); qbytes = min((qbytes + 15u) & ~15u, A.st_qual);
+            if (A.ablate & 4u) { sbytes = 0; qbytes = 0; }
             const uint32_t sw1 = sw0 + sbytes / 4u, qw1 = qw0 + qbytes / 8u;
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar, sbytes + qbytes);
@@ -609,6 +626,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
                 staged = soff >= sw0 && soff + sw_need <= sw1 && qoff >= qw0 && qoff + qw_need <= qw1;
                 uint32_t *cx = rctx + WS_CTX_WORDS * lane;
                 cx[0] = ((soff - sw0) * 4u) | (((qoff - qw0) * 8u) << 16);
+                cx[9] = ((soff - sw0) & 1023u) | (((qoff - qw0) & 1023u) << 10) | (rc.wantG ? 1u << 20 : 0u) | (rc.rd2 ? 1u << 21 : 0u) | ((unsigned) rc.strand << 22);
                 cx[1] = (rc.wantG ? 1u : 0u) | (rc.rd2 ? 2u : 0u) | (rc.mi >= 0 ? 4u : 0u) | (rc.is_a ? 8u : 0u) | (rc.mate_simple ? 16u : 0u) | ((unsigned) rc.strand << 8);
                 if (rc.mi >= 0) { cx[2] = (uint32_t) rc.mpos; cx[3] = (uint32_t) rc.mend; cx[4] = rc.msoff; cx[5] = rc.mqoff; cx[6] = (uint32_t) rc.mlo | ((uint32_t) rc.mhi << 16); cx[7] = rc.mk0; cx[8] = rc.mk1; }
             }
@@ -620,20 +638,26 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
 
             // -- GENERATE / EVALUATE
             // one queued candidate -> call / evidence.  MATE candidates carry the mate descriptor of their alignment.
+            const bool ovf = rr.y - rr.x >= 0xffffu;                   // only a window this deep can wrap a packed 16-bit counter
             auto eval_entry = [&](uint32_t en, bool with_mate) {
                 const int src = en & 31u, rel = (en >> 5) & 0xfffu, qi = (en >> 17) & 0x3fffu; const bool is_opp = en >> 31;
                 const uint32_t *cx = rctx + WS_CTX_WORDS * src;
+                if (!with_mate) {
+                    const uint32_t d = cx[9];
+                    const bool wg = (d >> 20) & 1u;
+                    if (!staged_pass(A, squal + ((d >> 10) & 1023u) * 8u, qi)) return;
+                    const unsigned byte = sseq[(d & 1023u) * 4u + (qi >> 1)];
+                    eval_plain<MODE>(A, (int)(d >> 22), (int)((d >> 21) & 1u), wg, cnt, W, (uint32_t) rel, qi, (qi & 1) ? (byte & 0xfu) : (byte >> 4), is_opp ? !wg : wg, ovf);
+                    return;
+                }
                 const uint32_t c0w = cx[0], c1w = cx[1];
                 ReadCtx hc;
-                hc.wantG = c1w & 1u; hc.rd2 = (c1w >> 1) & 1u; hc.strand = (c1w >> 8) & 7u; hc.mi = with_mate ? 0 : -1;
-                if (with_mate) {
-                    hc.is_a = (c1w & 8u) != 0; hc.mate_simple = (c1w & 16u) != 0;
-                    hc.mpos = (int) cx[2]; hc.mend = (int) cx[3]; hc.msoff = cx[4]; hc.mqoff = cx[5]; hc.mlo = (int)(cx[6] & 0xffffu); hc.mhi = (int)(cx[6] >> 16); hc.mk0 = cx[7]; hc.mk1 = cx[8];
-                }
+                hc.wantG = c1w & 1u; hc.rd2 = (c1w >> 1) & 1u; hc.strand = (c1w >> 8) & 7u; hc.mi = 0;
+                hc.is_a = (c1w & 8u) != 0; hc.mate_simple = (c1w & 16u) != 0;
+                hc.mpos = (int) cx[2]; hc.mend = (int) cx[3]; hc.msoff = cx[4]; hc.mqoff = cx[5]; hc.mlo = (int)(cx[6] & 0xffffu); hc.mhi = (int)(cx[6] >> 16); hc.mk0 = cx[7]; hc.mk1 = cx[8];
                 const unsigned byte = sseq[(c0w & 0xffffu) + (qi >> 1)];
                 const unsigned bb = (qi & 1) ? (byte & 0xfu) : (byte >> 4), ql = staged_qual(R, squal + (c0w >> 16), qi);
-                if (with_mate) eval_hit<MODE, true>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
-                else eval_hit<MODE, false>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
+                eval_hit<MODE, true>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
             };
             // iterator over this lane's candidate bases: current match op [ra,rb) (clipped, window-relative), bitmap word wi, remaining bits cur
             const uint32_t *own_bm = rc.wantG ? bmG : bmC, *opp_bm = rc.wantG ? bmC : bmG;
@@ -650,6 +674,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
                 uint32_t qa = 0, qb2 = 0;
                 const bool has_mate = rc.mi >= 0;
                 const int mrel0 = has_mate ? rc.mpos - w0i : 0, mrel1 = has_mate ? rc.mend - w0i : 0;
+                if (A.ablate & 2u) done = true;
                 for (;;) {
                     while (!done && !in_op) {
                         if (k >= k1) { done = true; break; }
@@ -717,14 +742,14 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
                     while (qa >= 32u * EV || (all_done && qa > 0u)) {
                         const uint32_t take = min(qa, 32u * EV);
                         #pragma unroll
-                        for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take) eval_entry(queue[qa - take + lane + 32 * r], false);
+                        for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take && !(A.ablate & 1u)) eval_entry(queue[qa - take + lane + 32 * r], false);
                         qa -= take;
                         __syncwarp();
                     }
                     while (qb2 >= 32u * EV || (all_done && qb2 > 0u)) {
                         const uint32_t take = min(qb2, 32u * EV);
                         #pragma unroll
-                        for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take) eval_entry(queue[WS_QUEUE - qb2 + lane + 32 * r], true);
+                        for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take && !(A.ablate & 1u)) eval_entry(queue[WS_QUEUE - qb2 + lane + 32 * r], true);
                         qb2 -= take;
                         __syncwarp();
                     }
@@ -948,7 +973,8 @@ struct md_ctx {
     uint32_t *d_hist = nullptr; int32_t *d_lens = nullptr;
     uint64_t launches = 0;
     uint32_t W = 4096;
-    int gen = 1;                         // count_warp<MODE, GEN>: 1 = word-at-a-time candidate generator, 0 = one candidate per lane per ballot (kept for A/B runs)
+    uint32_t ablate = 0;                 // MD_ABLATE: timing experiments (results are wrong when set)
+    int gen = 1;                         // count_warp<MODE, GEN>: 1 = segment-at-a-time candidate generator, 0 = one candidate per lane per ballot (kept for A/B runs, MD_GEN=0)
 };
 
 static void sync_all(md_ctx *c) { for (int k = 0; k < MD_NLANES; ++k) if (c->lanes[k].stream) cudaStreamSynchronize(c->lanes[k].stream); }
@@ -988,6 +1014,7 @@ extern "C" md_ctx *md_create(const md_config *cfg, int device) {
     cudaFuncSetAttribute(count_warp<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
     cudaFuncSetAttribute(count_warp<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
     cudaFuncSetAttribute(count_warp<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
+    if (const char *v = getenv("MD_ABLATE")) c->ablate = (uint32_t) atoi(v);
     if (const char *v = getenv("MD_GEN")) { int e = atoi(v); if (e == 0 || e == 1) c->gen = e; }
     cudaStreamSynchronize(L->stream);
     return c;
@@ -1099,6 +1126,8 @@ static int launch_count(md_ctx *c, Lane *L, const Contig &g, const DevReads &R, 
     // 2-bit tiles with packed counters fit three CTAs per SM, everything else two
     A.st_seq = WS_SEQ_BYTES; A.st_qual = std::min<uint32_t>(WS_QUAL_BYTES, 32u * (((160u * R.qbits + 63u) >> 6) * 8u) + 32u);
     A.wide = wide ? 1u : 0u;
+    A.ablate = c->ablate;
+    A.okmask = 0; for (int cde = 0; cde < 16; ++cde) if ((int) R.qlut[cde] >= kp.minPhred) A.okmask |= 1u << cde;
     const size_t sm = warp_layout(W, mode, A.wide, A.st_seq, A.st_qual).total;
     if (c->gen == 1) {
         if (mode == 2) count_warp<2, 1><<<n_win, WS_WARPS * 32, sm, s>>>(A);

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--variants", default="0,1")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--panel", action="store_true")
+    ap.add_argument("--envs", default="", help="semicolon list of extra env settings to sweep, e.g. 'MD_PREFETCH=0;MD_PREFETCH=1'")
     ap.add_argument("--only", default="", help="comma list of option-set names (cpg,all,var) to run")
     a = ap.parse_args()
     sets = [("c2", ["--contigs", "chr1:10000000", "--depth", "30"], "chr1")]
@@ -42,8 +43,10 @@ def main():
             if a.only and cname not in a.only.split(","):
                 continue
             base = None
-            for v in a.variants.split(","):
+            for v, envset in [(v, e) for v in a.variants.split(",") for e in (a.envs.split(";") if a.envs else [""])]:
                 os.environ["MD_GEN"] = v
+                for kv in filter(None, envset.split(",")):
+                    os.environ[kv.split("=")[0]] = kv.split("=")[1]
                 g = api.GpuContext(cfg)
                 g.load_contig(0, ref)
                 d = g.upload(soa)
@@ -58,7 +61,7 @@ def main():
                 sig = hash(bytes(C.string_at(calls, n * 16)))
                 if base is None:
                     base = sig
-                print(json.dumps({"set": name, "cfg": cname, "variant": int(v), "reads": soa.n_reads, "prep_ms": round(tp / a.steps, 4), "count_ms": round(tc / a.steps, 4),
+                print(json.dumps({"set": name, "cfg": cname, "variant": int(v), "env": envset, "reads": soa.n_reads, "prep_ms": round(tp / a.steps, 4), "count_ms": round(tc / a.steps, 4),
                                   "M_aln_s": round(soa.n_reads / ((tp + tc) / a.steps) / 1e3, 1), "calls": st.n_calls, "same_as_first": sig == base}), flush=True)
                 g.free(d); g.close()
         b.close()
