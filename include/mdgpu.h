@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MDGPU_ABI_VERSION 5
+#define MDGPU_ABI_VERSION 6
 
 /* ---- options that reach the hot path: the subset of `Config`
  *      (MethylDackel.h:90-126) read by filter_func / the per-column loop ---- */
@@ -132,6 +132,17 @@ int md_drop_contig(md_ctx *ctx, int32_t tid);
  * contig[localPos..localEnd] (MBias.c:147,170-178), so context at chunk edges depends on
  * the chunk layout.  bounds[0..n] are the n chunks' starts followed by the last end. */
 int md_set_mbias_chunks(md_ctx *ctx, int32_t tid, const uint32_t *bounds, uint32_t n_chunks);
+
+/* -l <BED> (+ --keepStrand): the regions of one loaded contig, sorted the way the reference sorts them (sortBED, bed.c:64-85:
+ * start, end, strand).  Replaces, on the device, the three BED tests of the pileup path:
+ *   - read admission (filter_func -> spanOverlapsBED, common.c:432-439, bed.c:22-41): a read is dropped unless it overlaps a region;
+ *   - column selection (posOverlapsBED, extract.c:402-405 / MBias.c:166, bed.c:46-54): a column counts when the first region
+ *     whose end lies beyond it starts at or before it;
+ *   - strand (readStrandOverlapsBED, extract.c:425 / MBias.c:184, bed.c:57-63): in a '+' region only OT/CTOT reads are looked at,
+ *     in a '-' region only OB/CTOB reads (strand = 0 unless --keepStrand was given).
+ * From the first call on the context is in BED mode: tiles of contigs without regions produce nothing.  Call after md_load_contig. */
+typedef struct md_bed_region { uint32_t start, end; uint32_t strand; /* 0 any, 1 '+', 2 '-' */ } md_bed_region;
+int md_set_bed(md_ctx *ctx, int32_t tid, const md_bed_region *regs, uint32_t n);
 
 /* extract: replaces the chunk body extract.c:379-494 (pileup + per-column counting +
  * variant test).  Writes up to `capacity` md_call records sorted by position into

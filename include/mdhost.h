@@ -46,6 +46,8 @@ typedef struct mdh_backend {
     int   (*bam_mbias_run)(void *s, int run, const md_tile_desc *tile, uint32_t keep_hi, md_tile_stats *st);
     int   (*bam_push_begin)(void *s, const void *comp, uint64_t bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip);   /* optional pair: overlapped push */
     int   (*bam_push_end)(void *s, md_bam_summary *out);
+    /* optional: -l <BED> (md_set_bed); without it the sub-commands refuse -l */
+    int   (*set_bed)(void *be, int32_t tid, const md_bed_region *regs, uint32_t n);
 } mdh_backend;
 
 /* Same argv conventions as the reference: argv[0] is the sub-command name. */

@@ -48,6 +48,10 @@ class MdReadsSoa(C.Structure):
     ]
 
 
+class MdBedRegion(C.Structure):
+    _fields_ = [("start", C.c_uint32), ("end", C.c_uint32), ("strand", C.c_uint32)]
+
+
 class MdTileDesc(C.Structure):
     _fields_ = [("tid", C.c_int32), ("beg", C.c_uint32), ("end", C.c_uint32), ("ce_beg", C.c_uint32), ("ce_end", C.c_uint32)]
 
@@ -102,6 +106,7 @@ BAM_EXTRACT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(MdTileDesc)
 BAM_MBIAS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(MdTileDesc), C.c_uint32, C.POINTER(MdTileStats))
 BAM_PUSH_BEGIN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(MdBgzfBlock), C.c_uint32, C.c_uint32)
 BAM_PUSH_END_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(MdBamSummary))
+SET_BED_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.POINTER(MdBedRegion), C.c_uint32)
 
 
 class MdhBackend(C.Structure):
@@ -112,7 +117,7 @@ class MdhBackend(C.Structure):
                 ("submit_mbias_tile", SUBMIT_FN),
                 ("bam_open", BAM_OPEN_FN), ("bam_close", BAM_CLOSE_FN), ("bam_reset", BAM_CLOSE_FN), ("bam_push", BAM_PUSH_FN),
                 ("bam_get_runs", BAM_RUNS_FN), ("bam_extract_run", BAM_EXTRACT_FN), ("bam_mbias_run", BAM_MBIAS_FN),
-                ("bam_push_begin", BAM_PUSH_BEGIN_FN), ("bam_push_end", BAM_PUSH_END_FN)]
+                ("bam_push_begin", BAM_PUSH_BEGIN_FN), ("bam_push_end", BAM_PUSH_END_FN), ("set_bed", SET_BED_FN)]
 
 
 _host = None
@@ -162,6 +167,7 @@ def load_gpu():
         g.md_load_contig.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint32]
         g.md_drop_contig.argtypes = [C.c_void_p, C.c_int32]
         g.md_set_mbias_chunks.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint32), C.c_uint32]
+        g.md_set_bed.argtypes = [C.c_void_p, C.c_int32, C.POINTER(MdBedRegion), C.c_uint32]
         g.md_extract_tile.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa), C.POINTER(MdCall), C.c_uint64, C.POINTER(MdTileStats)]
         g.md_submit_tile.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa)]
         g.md_submit_mbias_tile.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa)]

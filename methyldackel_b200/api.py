@@ -130,7 +130,8 @@ class _GpuBackend:
                       A.BAM_EXTRACT_FN(lambda s, run, td, kh, c, cap, st: g.md_bam_extract_run(s, run, td, kh, c, cap, st)),
                       A.BAM_MBIAS_FN(lambda s, run, td, kh, st: g.md_bam_mbias_run(s, run, td, kh, st)),
                       A.BAM_PUSH_BEGIN_FN(lambda s, c, n, bl, nb, sk: g.md_bam_push_begin(s, c, n, bl, nb, sk)),
-                      A.BAM_PUSH_END_FN(lambda s, o: g.md_bam_push_end(s, o))]
+                      A.BAM_PUSH_END_FN(lambda s, o: g.md_bam_push_end(s, o)),
+                      A.SET_BED_FN(lambda b, t, r, n: g.md_set_bed(b, t, r, n))]
         self.be = A.MdhBackend(None, *self._keep)
 
 

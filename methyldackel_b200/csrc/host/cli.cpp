@@ -18,6 +18,7 @@
 #include "pardecode.hpp"
 #include "format.hpp"
 #include "mbias_report.hpp"
+#include "bed.hpp"
 #include "../../../include/mdhost.h"
 
 using namespace mdhost;
@@ -73,14 +74,14 @@ static void extract_usage() {
     fprintf(stderr,
 "\nUsage: MethylDackel extract [OPTIONS] <ref.fa> <sorted_alignments.bam>\n\n"
 "B200 build of the extract hot path. Options (same names, defaults and meaning as MethylDackel 0.6.1):\n"
-"  -q INT  -p INT  -d INT  -r STR  -o/--opref STR  -@ INT  --chunkSize INT  -D INT (ignored)\n"
+"  -q INT  -p INT  -d INT  -r STR  -l FILE (BED)  --keepStrand  -o/--opref STR  -@ INT  --chunkSize INT  -D INT (ignored)\n"
 "  --noCpG  --CHG  --CHH  --mergeContext  --fraction  --counts  --logit  --methylKit  --cytosine_report\n"
 "  --keepDupes  --keepSingleton  --keepDiscordant  -F/--ignoreFlags INT  -R/--requireFlags INT  --ignoreNH\n"
 "  --minOppositeDepth INT  --maxVariantFrac FLOAT\n"
 "  --OT/--OB/--CTOT/--CTOB INT,INT,INT,INT   --nOT/--nOB/--nCTOT/--nCTOB INT,INT,INT,INT\n"
 "  -h/--help  -v/--version\n"
 "  --minConversionEfficiency FLOAT\n"
-"Not available in this build yet: -l/--keepStrand (BED), -M/-t/-b/-O/-N/-B (mappability).\n"
+"Not available in this build: -M/-t/-b/-O/-N/-B (mappability).\n"
 "Note that --fraction, --counts, and --logit are mutually exclusive!\n");
 }
 
@@ -88,10 +89,10 @@ static void mbias_usage() {
     fprintf(stderr,
 "\nUsage: MethylDackel mbias [OPTIONS] <ref.fa> <sorted_alignments.bam> <output.prefix>\n\n"
 "B200 build of the mbias hot path. Options (as MethylDackel 0.6.1):\n"
-"  -q INT  -p INT  -r STR  -@ INT  --chunkSize INT  -D INT (ignored)  --noCpG  --CHG  --CHH\n"
+"  -q INT  -p INT  -r STR  -l FILE (BED)  --keepStrand  -@ INT  --chunkSize INT  -D INT (ignored)  --noCpG  --CHG  --CHH\n"
 "  --keepDupes  --keepSingleton  --keepDiscordant  -F INT  -R INT  --ignoreNH  --txt  --noSVG\n"
 "  --nOT/--nOB/--nCTOT/--nCTOB INT,INT,INT,INT  -h/--help  -v/--version\n"
-"Not available in this build yet: -l/--keepStrand (BED), --minConversionEfficiency.\n");
+"Not available in this build yet: --minConversionEfficiency.\n");
 }
 
 static bool load_bai(const std::string &bam, BaiIndex &idx) {
@@ -207,6 +208,17 @@ struct Driver {
     BamHeader own_hdr; uint64_t start_voff = 0;              // device-decode mode: no host decoder, just the header
     std::shared_ptr<Fragment> frag; size_t frag_i = 0;      // decode cursor shared by consecutive FragTilers
     const BamHeader *hdr = nullptr;
+    BedFile bed; bool have_bed = false;                     // -l
+    // a chunk the reference's workers skip because no BED region overlaps it (extract.c:353-367): nothing is written for it
+    bool chunk_skipped(const Chunk &k) const { return have_bed && !bed.chunk_overlaps(k.tid, k.beg, k.end); }
+    // hand the contig's regions to the device (after load_contig)
+    int push_bed(uint32_t tid) {
+        if (!have_bed) return 0;
+        if (!be->set_bed) { fprintf(stderr, "The device back end does not implement -l.\n"); return -20; }
+        const std::vector<md_bed_region> &v = bed.regions(tid);
+        if (be->set_bed(dev, (int32_t) tid, v.data(), (uint32_t) v.size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+        return 0;
+    }
     std::string cur_seq; int cur_seq_tid = -1; bool cur_seq_ok = false;
     std::future<bool> next_ready; std::string next_seq; int next_tid = -1;
     // whole contig for the device and the writer; the one announced with prefetch() was read in the background meanwhile
@@ -357,7 +369,7 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
             auto part = std::make_shared<std::vector<md_call>>(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b);
             const char *cname = d.hdr->names[J.tid].c_str();
             const std::string *rp = ref;
-            out_thread.post(cname, rp, k, part);
+            if (!d.chunk_skipped(k)) out_thread.post(cname, rp, k, part);
             calls_head = b; ++next_chunk;
         }
         if (calls_head > (1u << 20)) { calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
@@ -378,7 +390,7 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
     auto tile = [&](const ContigJob &J, int run, const md_tile_desc &td, bool on_device) -> int {
         if (!ref) return 0;
         if (on_device) {
-            if (!loaded) { if (be->load_contig(d.dev, (int32_t) J.tid, ref->data(), (uint32_t) ref->size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; } loaded = true; }
+            if (!loaded) { if (be->load_contig(d.dev, (int32_t) J.tid, ref->data(), (uint32_t) ref->size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; } if (d.push_bed(J.tid)) return -20; loaded = true; }
             md_tile_desc t = td; if (t.end > ref->size()) t.end = (uint32_t) ref->size(); if (t.beg > t.end) t.beg = t.end;
             const uint64_t cap = (uint64_t)(t.end - t.beg) + 16;
             tile_calls.clear(); tile_calls.grow(cap);
@@ -431,6 +443,7 @@ static int mbias_device_decode(Driver &d, const mdh_backend *be, const char *bam
             std::vector<uint32_t> bounds; bounds.push_back(J.chunks.front().beg); for (auto &k : J.chunks) bounds.push_back(k.end);
             if (be->load_contig(d.dev, (int32_t) J.tid, ref->data(), (uint32_t) ref->size()) != 0 ||
                 be->set_mbias_chunks(d.dev, (int32_t) J.tid, bounds.data(), (uint32_t) bounds.size() - 1) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+            if (d.push_bed(J.tid)) return -20;
             loaded = true;
         }
         md_tile_desc t = td; if (t.end > ref->size()) t.end = (uint32_t) ref->size(); if (t.beg > t.end) t.beg = t.end;
@@ -452,7 +465,6 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     ExtractOptions o;
     char *opref = nullptr; const char *reg = nullptr, *bedName = nullptr, *bwName = nullptr, *bbmName = nullptr;
     int c, nThreads = 1, keepStrand = 0; double minConvEff = 0.0; bool threads_given = false;
-    (void) keepStrand;
     double t_start = now_s(); g_t0 = t_start; g_marks = getenv("MD_TIMING") != nullptr;
     tune_allocator();
     memset(&g_stats, 0, sizeof g_stats);
@@ -522,8 +534,8 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     if (o.cytosine_report + o.merge == 2) { fprintf(stderr, "--mergeContext and --cytosine_report are mutually exclusive.\n"); extract_usage(); return 1; }
     if (!(o.core.keepCpG + o.core.keepCHG + o.core.keepCHH)) {
         fprintf(stderr, "You haven't specified any metrics to output!\nEither don't use the --noCpG option or specify --CHG and/or --CHH.\n"); return -1; }
-    if (bedName || bwName || bbmName) {
-        fprintf(stderr, "This B200 build of the extract path does not implement -l or -M/-B yet.\n"); return 1; }
+    if (bwName || bbmName) {
+        fprintf(stderr, "This B200 build of the extract path does not implement -M/-B.\n"); return 1; }
     o.core.minConversionEfficiency = (float) minConvEff;            // Config.minConversionEfficiency is a float (MethylDackel.h:110)
 
     Driver d; d.be = be;
@@ -581,6 +593,10 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         if (gEnd > d.hdr->lens[gTid]) gEnd = d.hdr->lens[gTid];
     }
 
+    if (bedName) {                                                  // extract.c:1469-1477
+        if (!d.bed.load(bedName, d.hdr->names, d.hdr->lens, keepStrand != 0)) { fprintf(stderr, "There was an error while reading in your BED file!\n"); return 1; }
+        d.have_bed = true;
+    }
     for (int k = 0; k < 3; ++k) if (fp[k] && (k == 0 || fp[k] != fp[0])) setvbuf(fp[k], nullptr, _IOFBF, 4 << 20);
     OrderedFormatter out_thread(format_threads(), o, fp);
     int rc = 0;
@@ -643,6 +659,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             uint32_t rbeg = chunks.front().beg, rend = chunks.back().end;
             if (rend > ref->size()) rend = (uint32_t) ref->size();
             if (be->load_contig(d.dev, (int32_t) tid, ref->data(), (uint32_t) ref->size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+            if ((rc = d.push_bed(tid)) != 0) break;
             g_acc[1] += now_s() - t_ld;
             mark("contig loaded");
             d.seek_to((int) tid, rbeg);
@@ -662,7 +679,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
                     size_t b = a; while (b < calls.size() && calls[b].pos < k.end) ++b;
                     auto part = std::make_shared<std::vector<md_call>>(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b);
                     const char *cname = d.hdr->names[tid].c_str();
-                    out_thread.post(cname, ref, k, part);
+                    if (!d.chunk_skipped(k)) out_thread.post(cname, ref, k, part);
                     calls_head = b; ++next_chunk;
                 }
                 if (calls_head > (1u << 20)) { calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
@@ -749,7 +766,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
     cfg.keepCpG = 1; cfg.minMapq = 10; cfg.minPhred = 5; cfg.ignoreFlags = 0xF00; cfg.noOverlapMerge = 1;   // MBias.c:312-328, :160
     unsigned long chunkSize = 1000000;
     const char *reg = nullptr, *bedName = nullptr; char *opref = nullptr;
-    int c, SVG = 1, txt = 0, nThreads = 1; double minConvEff = 0.0; bool threads_given = false;
+    int c, SVG = 1, txt = 0, nThreads = 1, keepStrand = 0; double minConvEff = 0.0; bool threads_given = false;
     double t_start = now_s(); g_t0 = t_start; g_marks = getenv("MD_TIMING") != nullptr;
     tune_allocator();
     memset(&g_stats, 0, sizeof g_stats);
@@ -778,7 +795,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
         case 8: SVG = 0; txt = 1; break;
         case 9: case 10: case 11: case 12: parse_bounds(optarg, cfg.absoluteBounds, c - 9); break;
         case 13: chunkSize = strtoul(optarg, NULL, 10); if (chunkSize < 1) { fprintf(stderr, "Error: The chunk size must be at least 1!\n"); return 1; } break;
-        case 14: break;
+        case 14: keepStrand = 1; break;
         case 15: minConvEff = atof(optarg); break;
         case 16: cfg.ignoreNH = 1; break;
         case 200: shardRank = atoi(optarg); break;
@@ -800,7 +817,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
     if (cfg.minMapq < 0) { fprintf(stderr, "-q %i is invalid. Resetting to 0, which is the lowest possible value.\n", cfg.minMapq); cfg.minMapq = 0; }
     if (!(cfg.keepCpG + cfg.keepCHG + cfg.keepCHH)) {
         fprintf(stderr, "You haven't specified any metrics to output!\nEither don't use the --noCpG option or specify --CHG and/or --CHH.\n"); return -1; }
-    if (bedName || minConvEff > 0.0) { fprintf(stderr, "This B200 build of the mbias path does not implement -l or --minConversionEfficiency yet.\n"); return 1; }
+    if (minConvEff > 0.0) { fprintf(stderr, "This B200 build of the mbias path does not implement --minConversionEfficiency yet.\n"); return 1; }
     // NB: mbias never applies the 0x400 adjustment of extract.c:1005-1007 (MBias.c has no such line)
 
     Driver d; d.be = be;
@@ -824,6 +841,10 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
         if (s > 0) gPos = (uint32_t) s;
         if (e > 0) gEnd = (uint32_t) e;
         if (gEnd > d.hdr->lens[gTid]) gEnd = d.hdr->lens[gTid];
+    }
+    if (bedName) {                                                  // MBias.c:522-530
+        if (!d.bed.load(bedName, d.hdr->names, d.hdr->lens, keepStrand != 0)) { fprintf(stderr, "There was an error while reading in your BED file!\n"); return 1; }
+        d.have_bed = true;
     }
     // as in extract: the device context comes up while the host opens files and starts decoding
     std::future<void *> dev_future = std::async(std::launch::async, [be, &cfg] { void *p = be->create(be->factory_user, &cfg); mark("device context ready"); return p; });
@@ -889,6 +910,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
             if (rend > ref->size()) rend = (uint32_t) ref->size();
             if (be->load_contig(d.dev, (int32_t) tid, ref->data(), (uint32_t) ref->size()) != 0 ||
                 be->set_mbias_chunks(d.dev, (int32_t) tid, bounds.data(), (uint32_t) bounds.size() - 1) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+            if ((rc = d.push_bed(tid)) != 0) break;
             d.seek_to((int) tid, rbeg);
             FragTiler tiler(*d.bam, d.frag, d.frag_i, (int) tid, rbeg, rend, tile_reads); tiler.set_pack_quals(pack_quals_enabled());
             carry.clear();

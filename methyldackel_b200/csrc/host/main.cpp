@@ -30,6 +30,8 @@ static int be_bam_mbias(void *s, int run, const md_tile_desc *t, uint32_t keep_h
 static int be_bam_push_begin(void *s, const void *comp, uint64_t bytes, const md_bgzf_block *blocks, uint32_t n, uint32_t skip) { return md_bam_push_begin((md_bam_stream *) s, comp, bytes, blocks, n, skip); }
 static int be_bam_push_end(void *s, md_bam_summary *out) { return md_bam_push_end((md_bam_stream *) s, out); }
 
+static int be_set_bed(void *b, int32_t tid, const md_bed_region *r, uint32_t n) { return md_set_bed((md_ctx *) b, tid, r, n); }
+
 static void usage_main() {
     fprintf(stderr, "MethylDackel (B200 build of the extract/mbias hot path): A tool for processing bisulfite sequencing alignments.\n"
                     "Usage: MethylDackel <command> [options]\n\nCommands:\n"
@@ -40,7 +42,7 @@ static void usage_main() {
 
 int main(int argc, char *argv[]) {
     mdh_backend be = {nullptr, be_create, be_destroy, be_load, be_drop, be_extract, be_chunks, be_mbias, be_hist, md_last_error, be_submit, be_collect, md_alloc_pinned, md_free_pinned, be_submit_mbias,
-                      be_bam_open, be_bam_close, be_bam_reset, be_bam_push, be_bam_runs, be_bam_extract, be_bam_mbias, be_bam_push_begin, be_bam_push_end};
+                      be_bam_open, be_bam_close, be_bam_reset, be_bam_push, be_bam_runs, be_bam_extract, be_bam_mbias, be_bam_push_begin, be_bam_push_end, be_set_bed};
     if (argc == 1) { usage_main(); return 0; }
     if (!strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) { usage_main(); return 0; }
     if (!strcmp(argv[1], "-v") || !strcmp(argv[1], "--version")) { printf("0.6.1-b200 (B200 build; no HTSlib)\n"); return 0; }

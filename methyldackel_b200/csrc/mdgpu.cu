@@ -71,6 +71,17 @@ struct KParams {
 // the name itself is checked against frag_key[] of that record, so the table stays small enough to live in L2.
 struct HashTab { uint32_t *tab; uint32_t cap; };
 
+// -l BED regions of one contig (bed.c), sorted as sortBED does: start[], pmax[] = running maximum of end[] (so that the first
+// region whose end lies beyond a position is a binary search), strand[] (0 any, 1 '+', 2 '-').  on = 0: no BED file in play.
+struct BedView { const uint32_t *start, *pmax, *strand; uint32_t n, on; };
+// index of the first region with end > pos — the region posOverlapsBED (bed.c:46-54) settles on for pos, and the first one
+// spanOverlapsBED (bed.c:22-41) does not skip as "before" a read starting at pos
+__device__ __forceinline__ uint32_t bed_first_beyond(const BedView &B, uint32_t pos) {
+    uint32_t lo = 0, hi = B.n;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(B.pmax + mid) > pos) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+
 // counters[]: 0 n_admitted, 1 max reference span, 2 n_pairs, 3 n_multi, 4-5 n_calls (64-bit append cursor), 6 overflow flag, 7 max l_qseq
 enum { C_ADMIT = 0, C_MAXSPAN = 1, C_PAIRED = 2, C_MULTI = 3, C_NCALLS = 4 /* 64-bit: slots 4,5 */, C_OVERFLOW = 6, C_MAXLQ = 7, C_N = 8 };
 
@@ -197,7 +208,7 @@ done:
 }
 
 __global__ void __launch_bounds__(256) prep_kernel(DevReads R, KParams P, int32_t *rend, uint8_t *info, HashTab T, int32_t *mate, uint32_t *counters,
-                                                   const unsigned char *ref, uint32_t ce_beg, uint32_t ce_end) {
+                                                   const unsigned char *ref, uint32_t ce_beg, uint32_t ce_end, BedView B) {
     // grid-stride over the alignments; the five tile-wide statistics are reduced per thread, then per CTA, so the
     // global counters see one atomic per CTA instead of one per warp (same-address L2 atomics serialise)
     uint32_t n_ok = 0, n_paired = 0, n_multi = 0, span_max = 0, lq_max = 0;
@@ -212,6 +223,10 @@ __global__ void __launch_bounds__(256) prep_kernel(DevReads R, KParams P, int32_
         }
         const uint32_t lq = R.l_qseq[i];
         bool ok = dev_admit(P, f, R.mapq[i], a) && strand != 0 && rl > 0 && ql == lq && lq > 0;
+        if (ok && B.on) {                                                       // common.c:432-439: the read must overlap a BED region (strand independent)
+            const uint32_t j = bed_first_beyond(B, (uint32_t) R.pos[i]);
+            ok = j < B.n && (long long) __ldg(B.start + j) < (long long) R.pos[i] + rl;
+        }
         if (ok && P.minCE > 0.0f && dev_conversion_efficiency(R, P, i, strand, ref, ce_beg, ce_end) < P.minCE) ok = false;   // common.c:442-444
         const bool elig = ok && (f & 1u) && !(f & 12u) && !P.noOverlap;      // overlaps.c:128
         rend[i] = R.pos[i] + rl;
@@ -290,6 +305,7 @@ struct CountArgs {
     uint32_t *hist; int32_t *lens;                         // mbias
     uint32_t st_seq, st_qual;                              // per-warp staging capacities in bytes (count_warp)
     uint32_t wide;                                         // 1: 32-bit window counters; 0: 16-bit pairs packed in one word (overflow -> rerun wide)
+    BedView bed;
     uint32_t ablate;                                       // timing experiments only (MD_ABLATE): 1 skip evaluation, 2 skip generation, 4 skip staging copies
     uint32_t okmask;                                       // 2-/4-bit phred tiles: bit c set when code c decodes to a phred >= minPhred
 };
@@ -404,7 +420,7 @@ __device__ __forceinline__ void slow_read(const CountArgs &A, uint32_t i, unsign
             const int j0 = (int) max(0ll, w0 - (long long) p), j1 = (int) min((long long) len, own1 - (long long) p);
             for (int j = j0 + lane; j < j1; j += 32) {
                 const int rp = p + j, qi = q + j;
-                const unsigned cx = ctx(rp - (int) w0);
+                const unsigned cx = ctx(rp - (int) w0, rc.wantG);
                 if (!cx) continue;
                 const bool siteG = (cx & 4u) != 0;
                 if (MODE != 1 && siteG != rc.wantG) continue;   // wrong-strand columns only matter to the variant filter
@@ -463,7 +479,7 @@ __host__ __device__ inline WarpLayout warp_layout(uint32_t W, int mode, uint32_t
     WarpLayout L; const uint32_t NW = W >> 5;
     auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
     L.off_bm = 128;                                              // [0,128): 8 mbarriers + ticket counter
-    L.off_cnt = up(L.off_bm + 4u * (NW + 2u) * 4u);
+    L.off_cnt = up(L.off_bm + (mode == 1 ? 6u : 4u) * (NW + 2u) * 4u);   // bmC, bmG, bmT0, bmT1 (+ bmCo, bmGo with the variant filter)
     const uint32_t ncnt = mode == 2 ? 4u * 2u * MB_SM_Q * 2u : ((mode == 1 ? 4u * W : 2u * W) >> (wide ? 0 : 1));
     L.off_warp = up(L.off_cnt + ncnt * 4u);
     L.off_seq = 0; L.off_qual = up(st_seq + 32u); L.off_ctx = L.off_qual + up(st_qual + 32u);
@@ -486,7 +502,13 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
     const WarpLayout SL = warp_layout(W, MODE, A.wide, A.st_seq, A.st_qual);
     uint64_t *bars = (uint64_t *) smem;                                   // [8]
     uint32_t *ticket = (uint32_t *)(smem + 64);
+    // site bitmaps of the window (bit = position; word w of the window lives at index w + 1, words 0 and NW + 1 are zero pads):
+    //   bmC / bmG   kept-context C / G columns where a call may be made (a '-' / '+' BED region with --keepStrand blanks them)
+    //   bmT0 / bmT1 column is CpG / CHG (neither: CHH)
+    //   bmCo / bmGo (variant filter only) C / G columns where opposite-strand evidence is collected; they differ from bmC / bmG
+    //               only inside strand-specific BED regions (extract.c:425 skips the read before either use)
     uint32_t *bmC = (uint32_t *)(smem + SL.off_bm), *bmG = bmC + NW + 2, *bmT0 = bmG + NW + 2, *bmT1 = bmT0 + NW + 2;
+    uint32_t *bmCo = (MODE == 1) ? bmT1 + NW + 2 : bmC, *bmGo = (MODE == 1) ? bmCo + NW + 2 : bmG;
     uint32_t *cnt = (uint32_t *)(smem + SL.off_cnt);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned char *wbase = smem + SL.off_warp + (size_t) warp * SL.warp_stride;
@@ -512,7 +534,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
     }
     const uint32_t ncnt = (MODE == 2) ? 4u * 2u * MB_SM_Q * 2u : ((MODE == 1 ? 4u * W : 2u * W) >> (A.wide ? 0 : 1));
     for (uint32_t t = tid; t < ncnt; t += WS_WARPS * 32) cnt[t] = 0;
-    if (tid < 8) { uint32_t *g = bmC + (tid >> 1) * (NW + 2); g[(tid & 1) ? NW + 1 : 0] = 0; }
+    if (tid < (MODE == 1 ? 12 : 8)) { uint32_t *g = bmC + (tid >> 1) * (NW + 2); g[(tid & 1) ? NW + 1 : 0] = 0; }
     __syncthreads();
     {
         const uint32_t t16 = 16u * tid;
@@ -548,10 +570,28 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
             t0 = (((cpgC | cpgG) & k0) >> 2) & ownm;
             t1 = (((chgC | chgG) & k1) >> 2) & ownm;
         }
+        // -l: positions outside every BED region drop out; with --keepStrand a '+' region keeps only OT/CTOT reads (which call at C
+        // columns and give evidence at G columns), a '-' region only OB/CTOB reads (extract.c:402-405,425; bed.c:46-63)
+        unsigned oC = sC, oG = sG;                                          // evidence columns
+        if (A.bed.on) {
+            unsigned aO = 0, aE = 0;
+            const long long p0 = w0 + t16;
+            if (p0 < own1) {
+                uint32_t j = bed_first_beyond(A.bed, (uint32_t) p0);
+                for (int jj = 0; jj < 16; ++jj) {
+                    const uint32_t pp = (uint32_t)(p0 + jj);
+                    while (j < A.bed.n && __ldg(A.bed.pmax + j) <= pp) ++j;
+                    if (j < A.bed.n && __ldg(A.bed.start + j) <= pp) { const uint32_t sd = __ldg(A.bed.strand + j); if (sd != 2u) aO |= 1u << jj; if (sd != 1u) aE |= 1u << jj; }
+                }
+            }
+            oC = sC & aE; oG = sG & aO; sC &= aO; sG &= aE; t0 &= aO | aE; t1 &= aO | aE;
+        }
         const unsigned pC = __shfl_down_sync(0xffffffffu, sC, 1), pG = __shfl_down_sync(0xffffffffu, sG, 1), p0 = __shfl_down_sync(0xffffffffu, t0, 1), p1 = __shfl_down_sync(0xffffffffu, t1, 1);
+        const unsigned pCo = __shfl_down_sync(0xffffffffu, oC, 1), pGo = __shfl_down_sync(0xffffffffu, oG, 1);
         if (!(tid & 1)) {
             const uint32_t wi = (t16 >> 5) + 1;
             bmC[wi] = sC | (pC << 16); bmG[wi] = sG | (pG << 16); bmT0[wi] = t0 | (p0 << 16); bmT1[wi] = t1 | (p1 << 16);
+            if (MODE == 1) { bmCo[wi] = oC | (pCo << 16); bmGo[wi] = oG | (pGo << 16); }
         }
     }
     __syncthreads();                                                      // bitmaps complete; refw (overlay) no longer needed
@@ -564,11 +604,12 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
     if (seqb_max) nb = min(nb, (A.st_seq - 32u) / seqb_max);
     if (qualb_max) nb = min(nb, (A.st_qual - 32u) / qualb_max);
     if (maxlq >= (1u << 14)) nb = 0;                                      // query index must fit the queue entry
-    auto ctx_code = [&](int rel) -> unsigned {
+    // context code of a window position for a read of the given orientation: 0 = nothing to do there, else type (1 CpG, 2 CHG, 3 CHH) | 4 if it is a G column
+    auto ctx_code = [&](int rel, bool wantG) -> unsigned {
         const uint32_t wi = ((uint32_t) rel >> 5) + 1, b = 1u << (rel & 31);
-        const bool c = bmC[wi] & b, g = bmG[wi] & b;
-        if (!c && !g) return 0u;
-        return ((bmT0[wi] & b) ? 1u : (bmT1[wi] & b) ? 2u : 3u) | (g ? 4u : 0u);
+        const bool own = (wantG ? bmG[wi] : bmC[wi]) & b, opp = (MODE == 1) && ((wantG ? bmCo[wi] : bmGo[wi]) & b);
+        if (!own && !opp) return 0u;
+        return ((bmT0[wi] & b) ? 1u : (bmT1[wi] & b) ? 2u : 3u) | ((own ? wantG : !wantG) ? 4u : 0u);
     };
     if (nb == 0) {
         for (uint32_t i = rr.x + warp; i < rr.y; i += WS_WARPS) {         // reads too long to stage: whole warp per alignment, from global memory
@@ -660,7 +701,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
                 eval_hit<MODE, true>(A, hc, cnt, W, w0i, w0i + rel, qi, bb, ql, is_opp ? !hc.wantG : hc.wantG);
             };
             // iterator over this lane's candidate bases: current match op [ra,rb) (clipped, window-relative), bitmap word wi, remaining bits cur
-            const uint32_t *own_bm = rc.wantG ? bmG : bmC, *opp_bm = rc.wantG ? bmC : bmG;
+            const uint32_t *own_bm = rc.wantG ? bmG : bmC, *opp_bm = rc.wantG ? bmCo : bmGo;
             uint32_t k = k0; int p = pos, q = 0, ra = 0, rb = 0, wi = 0; unsigned cur = 0, curo = 0; bool in_op = false;
             bool done = !(live && !direct);
             if constexpr (GEN == 1) {
@@ -827,7 +868,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
                     if (op == 0 || op == 7 || op == 8) {
                         const int a = max(max(p2, w0i), p2 + (rc.lo - q2)), bnd = min(min(p2 + len, w0i + own), p2 + (rc.hi - q2));
                         for (int x = a; x < bnd; ++x) {
-                            const unsigned cxc = ctx_code(x - w0i);
+                            const unsigned cxc = ctx_code(x - w0i, rc.wantG);
                             if (!cxc) continue;
                             const bool siteG = (cxc & 4u) != 0;
                             if (MODE != 1 && siteG != rc.wantG) continue;
@@ -857,7 +898,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
     unsigned rep = 0;
     {
         const uint32_t wi = (t16 >> 5) + 1, sh = t16 & 31u;
-        unsigned sites = ((bmC[wi] | bmG[wi]) >> sh) & 0xffffu;
+        unsigned sites = ((bmC[wi] | bmG[wi] | bmCo[wi] | bmGo[wi]) >> sh) & 0xffffu;
         while (sites) {
             const int kbit = __ffs(sites) - 1; sites &= sites - 1;
             const uint32_t t = t16 + kbit;
@@ -888,7 +929,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
     uint32_t o = s_base + s_warp_tot[warp] + (incl - mine);
     {
         const uint32_t wi = (t16 >> 5) + 1, sh = t16 & 31u;
-        const unsigned g16 = (bmG[wi] >> sh) & 0xffffu, a16 = (bmT0[wi] >> sh) & 0xffffu, b16 = (bmT1[wi] >> sh) & 0xffffu;
+        const unsigned g16 = ((bmG[wi] | bmGo[wi]) >> sh) & 0xffffu, a16 = (bmT0[wi] >> sh) & 0xffffu, b16 = (bmT1[wi] >> sh) & 0xffffu;
         unsigned r16 = rep & 0xffffu;
         while (r16) {
             const int kbit = __ffs(r16) - 1; r16 &= r16 - 1;
@@ -932,7 +973,7 @@ __global__ void __launch_bounds__(128) gather_kernel(const md_call *raw, const u
 
 // ------------------------------------------------------------------------------------------------
 // host side of the library
-struct Contig { unsigned char *d_seq = nullptr; uint32_t len = 0; uint32_t *d_bounds = nullptr; uint32_t n_chunks = 0; };
+struct Contig { unsigned char *d_seq = nullptr; uint32_t len = 0; uint32_t *d_bounds = nullptr; uint32_t n_chunks = 0; uint32_t *d_bed = nullptr; uint32_t n_bed = 0; };
 
 struct DevBuf {
     void *p = nullptr; size_t cap = 0;
@@ -973,6 +1014,7 @@ struct md_ctx {
     uint32_t *d_hist = nullptr; int32_t *d_lens = nullptr;
     uint64_t launches = 0;
     uint32_t W = 4096;
+    bool bed_mode = false;               // md_set_bed was called: -l semantics for every tile
     uint32_t ablate = 0;                 // MD_ABLATE: timing experiments (results are wrong when set)
     int gen = 1;                         // count_warp<MODE, GEN>: 1 = segment-at-a-time candidate generator, 0 = one candidate per lane per ballot (kept for A/B runs, MD_GEN=0)
 };
@@ -1024,7 +1066,7 @@ extern "C" void md_destroy(md_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     sync_all(c);
-    for (auto &kv : c->contigs) { cudaFree(kv.second.d_seq); if (kv.second.d_bounds) cudaFree(kv.second.d_bounds); }
+    for (auto &kv : c->contigs) { cudaFree(kv.second.d_seq); if (kv.second.d_bounds) cudaFree(kv.second.d_bounds); if (kv.second.d_bed) cudaFree(kv.second.d_bed); }
     for (int k = 0; k < MD_NLANES; ++k) {
         Lane *L = &c->lanes[k];
         L->staged.arena.release();
@@ -1058,6 +1100,7 @@ extern "C" int md_drop_contig(md_ctx *c, int32_t tid) {
     sync_all(c);
     cudaFree(it->second.d_seq);
     if (it->second.d_bounds) cudaFree(it->second.d_bounds);
+    if (it->second.d_bed) cudaFree(it->second.d_bed);
     c->contigs.erase(it);
     return 0;
 }
@@ -1072,6 +1115,29 @@ extern "C" int md_set_mbias_chunks(md_ctx *c, int32_t tid, const uint32_t *bound
     CK(cudaMemcpyAsync(it->second.d_bounds, bounds, ((size_t) n_chunks + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, L->stream));
     CK(cudaStreamSynchronize(L->stream));
     it->second.n_chunks = n_chunks;
+    return 0;
+}
+
+// -l: the BED regions of one contig.  From the first call on, the context is in BED mode: contigs without regions yield nothing.
+extern "C" int md_set_bed(md_ctx *c, int32_t tid, const md_bed_region *regs, uint32_t n) {
+    c->bed_mode = true;
+    auto it = c->contigs.find(tid);
+    if (it == c->contigs.end()) { g_err = "md_set_bed: contig not loaded"; return -2; }
+    CK(cudaSetDevice(c->device));
+    Lane *L = &c->lanes[0];
+    if (it->second.d_bed) { sync_all(c); cudaFree(it->second.d_bed); it->second.d_bed = nullptr; it->second.n_bed = 0; }
+    if (!n) return 0;
+    for (uint32_t k = 1; k < n; ++k) {
+        const md_bed_region &a = regs[k - 1], &b = regs[k];
+        if (a.start > b.start || (a.start == b.start && (a.end > b.end || (a.end == b.end && a.strand > b.strand)))) { g_err = "md_set_bed: regions must be sorted by start, end, strand"; return -2; }
+    }
+    std::vector<uint32_t> h((size_t) n * 3);
+    uint32_t run = 0;
+    for (uint32_t k = 0; k < n; ++k) { run = std::max(run, regs[k].end); h[k] = regs[k].start; h[(size_t) n + k] = run; h[(size_t) 2 * n + k] = regs[k].strand; }
+    CK(cudaMalloc(&it->second.d_bed, h.size() * sizeof(uint32_t)));
+    CK(cudaMemcpyAsync(it->second.d_bed, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, L->stream));
+    CK(cudaStreamSynchronize(L->stream));
+    it->second.n_bed = n;
     return 0;
 }
 
@@ -1127,6 +1193,7 @@ static int launch_count(md_ctx *c, Lane *L, const Contig &g, const DevReads &R, 
     A.st_seq = WS_SEQ_BYTES; A.st_qual = std::min<uint32_t>(WS_QUAL_BYTES, 32u * (((160u * R.qbits + 63u) >> 6) * 8u) + 32u);
     A.wide = wide ? 1u : 0u;
     A.ablate = c->ablate;
+    A.bed.start = g.d_bed; A.bed.pmax = g.d_bed ? g.d_bed + g.n_bed : nullptr; A.bed.strand = g.d_bed ? g.d_bed + 2 * (size_t) g.n_bed : nullptr; A.bed.n = g.n_bed; A.bed.on = c->bed_mode ? 1u : 0u;
     A.okmask = 0; for (int cde = 0; cde < 16; ++cde) if ((int) R.qlut[cde] >= kp.minPhred) A.okmask |= 1u << cde;
     const size_t sm = warp_layout(W, mode, A.wide, A.st_seq, A.st_qual).total;
     if (c->gen == 1) {
@@ -1176,7 +1243,8 @@ static int run_pipeline(md_ctx *c, Lane *L, const md_tile_desc *t, const DevRead
         const uint32_t gb = std::min<uint32_t>((n + 255) / 256, 148u * 8u);     // 8 CTAs of 256 threads per SM, grid-stride
         uint32_t ce_beg = t->ce_beg, ce_end = (t->ce_end == 0 || t->ce_end > g.len) ? g.len : t->ce_end;
         if (ce_beg > ce_end) ce_beg = ce_end;
-        prep_kernel<<<gb, 256, 0, s>>>(R, kp, (int32_t *) L->rend.p, (uint8_t *) L->info.p, T, (int32_t *) L->mate.p, (uint32_t *) L->counters.p, g.d_seq, ce_beg, ce_end);
+        BedView bv; bv.start = g.d_bed; bv.pmax = g.d_bed ? g.d_bed + g.n_bed : nullptr; bv.strand = g.d_bed ? g.d_bed + 2 * (size_t) g.n_bed : nullptr; bv.n = g.n_bed; bv.on = c->bed_mode ? 1u : 0u;
+        prep_kernel<<<gb, 256, 0, s>>>(R, kp, (int32_t *) L->rend.p, (uint8_t *) L->info.p, T, (int32_t *) L->mate.p, (uint32_t *) L->counters.p, g.d_seq, ce_beg, ce_end, bv);
         c->launches += 1;
     }
     CK(cudaEventRecord(L->ev[2], s));

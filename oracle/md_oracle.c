@@ -125,6 +125,38 @@ done:
 }
 
 /* filter + strand + trimAlignment (common.c:137-172) + trimAbsoluteAlignment (common.c:174-208) */
+/* ---- -l <BED> (bed.c).  The regions of the contig being processed, in sortBED order; on = a BED file is in play ---- */
+static const md_bed_region *g_bed = 0; static uint32_t g_nbed = 0; static int g_bed_on = 0;
+void mdo_set_bed(const md_bed_region *regs, uint32_t n, int on) { g_bed = regs; g_nbed = n; g_bed_on = on; }
+/* compareRegions (bed.c:10-16) of region k, given as [start, end-1] by the callers (bed.c:29,32), against [start1, end1) */
+static int64_t bed_cmp(uint32_t k, int64_t start1, int64_t end1) {
+    int64_t start0 = g_bed[k].start, end0 = (int64_t) g_bed[k].end - 1;
+    if (start0 < start1 && end0 >= start1) return 0;
+    if (start0 >= start1 && start0 < end1) return 0;
+    return start0 - start1;
+}
+/* spanOverlapsBED on a read (common.c:432-439, bed.c:22-41) from a fresh cursor: the first region that is not before the read decides */
+static int bed_read_ok(int64_t pos, int64_t endpos) {
+    for (uint32_t k = 0; k < g_nbed; ++k) { int64_t rv = bed_cmp(k, pos, endpos); if (rv >= 0) return rv == 0; }
+    return 0;
+}
+/* posOverlapsBED (bed.c:46-54) driven as in extract.c:403: regions whose end is <= pos are stepped over, the next one decides.
+ * Returns 1 when pos is inside it and sets *strand to that region's strand */
+static int bed_pos_ok(int64_t pos, int *strand) {
+    for (uint32_t k = 0; k < g_nbed; ++k) {
+        if (pos >= (int64_t) g_bed[k].end) continue;
+        if (pos < (int64_t) g_bed[k].start) return 0;
+        *strand = (int) g_bed[k].strand; return 1;
+    }
+    return 0;
+}
+/* readStrandOverlapsBED (bed.c:57-63) */
+static int bed_strand_ok(int region_strand, int s) {
+    if (region_strand == 1) return s == 1 || s == 3;
+    if (region_strand == 2) return s == 2 || s == 4;
+    return 1;
+}
+
 static int build_work(const md_config *c, const md_reads_soa *r, work_t *w, uint32_t *n_adm, const char *ref, uint32_t ce_beg, uint32_t ce_end) {
     uint32_t n = r->n_reads;
     memset(w, 0, sizeof *w);
@@ -151,6 +183,7 @@ static int build_work(const md_config *c, const md_reads_soa *r, work_t *w, uint
         /* a record whose CIGAR does not describe its SEQ, with no reference span, or with an
          * undeterminable strand (the reference asserts, common.c:122-125) cannot be piled up */
         int ok = mdo_admit(c, r->flag[i], r->mapq[i], r->aux[i]) && s != 0 && rl > 0 && qlen == r->l_qseq[i] && r->l_qseq[i] > 0;
+        if (ok && g_bed_on && !bed_read_ok(r->pos[i], w->rend[i])) ok = 0;                     /* common.c:432-439 */
         if (ok && c->minConversionEfficiency > 0.0f && conversion_efficiency(c, r, i, s, ref, ce_beg, ce_end) < c->minConversionEfficiency) ok = 0;   /* common.c:442-444 */
         w->admit[i] = (uint8_t) ok;
         if (!ok) continue;
@@ -320,6 +353,7 @@ int mdo_extract_tile_ce(const md_config *c, const char *ref, uint32_t reflen, ui
             if (op == 0 || op == 7 || op == 8) {
                 for (uint32_t j = 0; j < len; ++j, ++p, ++qi) {
                     if (p < (int64_t) beg || p >= (int64_t) end) continue;             /* extract.c:400 */
+                    if (g_bed_on) { int sd = 0; if (!bed_pos_ok(p, &sd) || !bed_strand_ok(sd, s)) continue; }   /* extract.c:402-405, 425 */
                     char rb = ref[p];
                     int ctx = mdo_context(ref, (int) p, (int) reflen);               /* extract.c:407-418 */
                     if (ctx == 0) continue;
@@ -383,6 +417,7 @@ int mdo_mbias_tile(const md_config *c, const char *ref, uint32_t reflen, uint32_
             if (op == 0 || op == 7 || op == 8) {
                 for (uint32_t j = 0; j < len; ++j, ++p, ++qi) {
                     if (p < (int64_t) beg || p >= (int64_t) end) continue;             /* MBias.c:163 */
+                    if (g_bed_on) { int sd = 0; if (!bed_pos_ok(p, &sd) || !bed_strand_ok(sd, s)) continue; }   /* MBias.c:165-168, 184 */
                     /* chunk window contig[localPos..localEnd] (MBias.c:147): find the chunk that owns p */
                     uint32_t lo = 0, hi = n_chunks;
                     while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if (bounds[mid] <= (uint32_t) p) lo = mid; else hi = mid; }

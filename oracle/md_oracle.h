@@ -31,6 +31,10 @@ int mdo_mbias_tile(const md_config *cfg, const char *ref, uint32_t reflen, uint3
                    const uint32_t *bounds, uint32_t n_chunks,
                    const md_reads_soa *reads, uint32_t *hist, int32_t lens[4], md_tile_stats *stats);
 
+/* -l <BED>: the regions (sortBED order, bed.c:64-85) of the contig the following mdo_*_tile calls work on; on = 0 switches
+ * the BED tests off.  The array must stay alive while it is set. */
+void mdo_set_bed(const md_bed_region *regs, uint32_t n, int on);
+
 /* Per-read helpers exposed for unit tests */
 int mdo_strand(uint16_t flag, uint8_t aux);                       /* getStrand, common.c:84-116 */
 int mdo_admit(const md_config *cfg, uint16_t flag, uint8_t mapq, uint8_t aux); /* filter_func, common.c:416-430 */

@@ -69,3 +69,36 @@ SYNTH_OPTION_SETS = [
 def slug(opts):
     s = "_".join(o.strip("-").replace(",", ".").replace(":", ".") for o in opts) or "default"
     return s[:60]
+
+
+# -l <BED> (bed.c): regions with overlaps, nesting, strands, a region past the contig end, header/comment lines.
+# "@BED" in an option set stands for the path of this file (written by the bed_file fixture helper below).
+BED_TEXT = """# comment
+track name=foo
+chr1\t1000\t3000\ta\t0\t+
+chr1\t2500\t2600\tb\t0\t-
+chr1\t10000\t10050\tc\t0\t-
+chr1\t20000\t29999\td\t0\t+
+chr1\t20500\t40000\te\t0\t.
+chr1\t59990\t60050
+chr2\t0\t100\tx\t1\t-
+chr2\t7000\t9000\ty\t1\t+
+"""
+BED_OPTION_SETS = [
+    ["-l", "@BED"],
+    ["-l", "@BED", "--keepStrand"],
+    ["-l", "@BED", "--keepStrand", "--CHG", "--CHH", "--mergeContext"],
+    ["-l", "@BED", "--keepStrand", "--cytosine_report", "--CHH", "--chunkSize", "5000"],
+    ["-l", "@BED", "--keepStrand", "--minOppositeDepth", "2", "--maxVariantFrac", "0.1", "--mergeContext", "--CHG"],
+    ["-l", "@BED", "-r", "chr1:2000-25000", "--chunkSize", "700"],
+    ["-l", "@BED", "--keepStrand", "--methylKit", "--CHH", "-F", "0", "--keepDupes"],
+]
+BED_MBIAS_SETS = [["--noSVG", "-l", "@BED"], ["--noSVG", "-l", "@BED", "--keepStrand", "--CHG", "--CHH", "--chunkSize", "2500"]]
+
+
+def with_bed(opts, tmp_path):
+    """Writes BED_TEXT under tmp_path and substitutes its path for "@BED"."""
+    f = os.path.join(str(tmp_path), "regions.bed")
+    if not os.path.exists(f):
+        open(f, "w").write(BED_TEXT)
+    return [f if o == "@BED" else o for o in opts]

@@ -21,6 +21,7 @@ def lib():
                                           C.POINTER(A.MdCall), C.c_uint64, C.POINTER(A.MdTileStats)]
         o.mdo_mbias_tile.argtypes = [C.POINTER(A.MdConfig), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32,
                                      C.POINTER(A.MdReadsSoa), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(A.MdTileStats)]
+        o.mdo_set_bed.argtypes = [C.POINTER(A.MdBedRegion), C.c_uint32, C.c_int]; o.mdo_set_bed.restype = None
         o.mdo_strand.argtypes = [C.c_uint16, C.c_uint8]
         o.mdo_admit.argtypes = [C.POINTER(A.MdConfig), C.c_uint16, C.c_uint8, C.c_uint8]
         o.mdo_context.argtypes = [C.c_char_p, C.c_int, C.c_int]
@@ -80,8 +81,20 @@ class OracleBackend:
             st["contigs"].pop(tid, None)
             return 0
 
+        def set_bed(_b, tid, regs, n):
+            st.setdefault("bed", {})[tid] = (A.MdBedRegion * max(n, 1))(*[regs[i] for i in range(n)]), n
+            return 0
+
+        def use_bed(tid):
+            if "bed" in st:
+                arr, n = st["bed"].get(tid, ((A.MdBedRegion * 1)(), 0))
+                o.mdo_set_bed(arr, n, 1)
+            else:
+                o.mdo_set_bed(None, 0, 0)
+
         def extract_tile(_b, td, reads, calls, cap, stats):
             seq, n = st["contigs"][td.contents.tid]
+            use_bed(td.contents.tid)
             return o.mdo_extract_tile_ce(C.byref(st["cfg"]), seq, n, td.contents.beg, td.contents.end, td.contents.ce_beg, td.contents.ce_end, reads, calls, cap, stats)
 
         def set_chunks(_b, tid, bounds, n):
@@ -91,6 +104,7 @@ class OracleBackend:
         def mbias_tile(_b, td, reads, stats):
             seq, n = st["contigs"][td.contents.tid]
             b = st["chunks"][td.contents.tid]
+            use_bed(td.contents.tid)
             return o.mdo_mbias_tile(C.byref(st["cfg"]), seq, n, td.contents.beg, td.contents.end, b, len(b) - 1, reads, st["hist"], st["lens"], stats)
 
         def mbias_hist(_b, hist, lens):
@@ -106,6 +120,8 @@ class OracleBackend:
                       A.EXTRACT_TILE_FN(extract_tile), A.SET_CHUNKS_FN(set_chunks), A.MBIAS_TILE_FN(mbias_tile), A.MBIAS_HIST_FN(mbias_hist),
                       A.LAST_ERROR_FN(last_error)]
         self.be = A.MdhBackend(None, *self._keep)      # async slots stay NULL: the driver then runs tile by tile
+        self._keep.append(A.SET_BED_FN(set_bed))
+        self.be.set_bed = self._keep[-1]
         if device_decode:
             # md_bam_* emulated on the CPU (tests/native/mdemu.cpp: the kernels' own per-thread bodies in plain loops); the
             # tiles it assembles go to the oracle through the two callbacks above

@@ -22,7 +22,7 @@ def test_libmdgpu_exports_header_symbols(built):
     for n in names:
         assert hasattr(lib, n), n
     lib.md_abi_version.restype = C.c_int
-    assert lib.md_abi_version() == 5
+    assert lib.md_abi_version() == 6
 
 
 def test_libmdhost_exports_header_symbols(built):

@@ -260,3 +260,49 @@ def test_cli_small_tiles_three_in_flight(built, synth, tmp_path, nq, sub):
         n = subprocess.run([NEW_BIN, "mbias"] + opts + ["-@", "3", p + ".fa", p + ".bam"], capture_output=True, text=True, env=env)
         assert r.returncode == 0 and n.returncode == 0, (r.stderr, n.stderr)
         assert n.stdout == r.stdout and len(r.stdout.splitlines()) > 10
+
+
+@pytest.mark.parametrize("opts", cases.BED_OPTION_SETS, ids=[cases.slug(o) for o in cases.BED_OPTION_SETS])
+@pytest.mark.parametrize("decode", ["device_decode", "host_decode"])
+def test_cli_bed_regions(built, synth, tmp_path, opts, decode, monkeypatch):
+    """-l / --keepStrand on the device (md_set_bed: admission in prep_kernel, column/strand masks in count_warp)"""
+    monkeypatch.setenv("MD_DEVICE_DECODE", "1" if decode == "device_decode" else "0")
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    refp, newp = _both(built, tmp_path, "bed", cases.with_bed(opts, tmp_path), p + ".fa", p + ".bam")
+    assert compare_outputs(refp, newp) == []
+
+
+@pytest.mark.parametrize("opts", cases.BED_MBIAS_SETS, ids=["plain", "strand_allctx"])
+def test_cli_bed_mbias(built, synth, tmp_path, opts):
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    o = cases.with_bed(opts, tmp_path)
+    r = subprocess.run([built["ref_bin"], "mbias"] + o + [p + ".fa", p + ".bam"], capture_output=True, text=True)
+    n = subprocess.run([NEW_BIN, "mbias"] + o + [p + ".fa", p + ".bam"], capture_output=True, text=True)
+    assert r.returncode == 0 and n.returncode == 0, (r.stderr, n.stderr)
+    assert n.stdout == r.stdout and len(r.stdout.splitlines()) > 50
+
+
+def test_bed_tile_abi_vs_oracle(built, synth):
+    """md_set_bed through the C ABI: one tile, strand-specific regions, variant filter on (six site bitmaps)"""
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    cfg = A.default_config(keepCHG=1, keepCHH=1, minOppositeDepth=2, maxVariantFrac=0.1)
+    regs = [(1000, 3000, 1), (2500, 2600, 2), (10000, 10050, 2), (20000, 29999, 1), (20500, 40000, 0), (59990, 60001, 0)]
+    arr = (A.MdBedRegion * len(regs))(*[A.MdBedRegion(*r) for r in regs])
+    b = api.BamFile(p + ".bam")
+    ref = api.fetch_contig(p + ".fa", "chr1")
+    soa = b.read_region(0, 0, len(ref))
+    o = ob.lib()
+    cap = len(ref) + 16
+    exp = (A.MdCall * cap)(); est = A.MdTileStats()
+    o.mdo_set_bed(arr, len(regs), 1)
+    try:
+        assert o.mdo_extract_tile(C.byref(cfg), ref, len(ref), 0, len(ref), C.byref(soa), exp, cap, C.byref(est)) == 0
+    finally:
+        o.mdo_set_bed(None, 0, 0)
+    with api.GpuContext(cfg) as g:
+        g.load_contig(0, ref)
+        assert g.g.md_set_bed(g.h, 0, arr, len(regs)) == 0
+        got, gst = g.extract_tile(0, 0, len(ref), soa)
+    assert gst.n_calls == est.n_calls and est.n_calls > 1000 and gst.n_admitted == est.n_admitted
+    assert bytes(C.string_at(got, gst.n_calls * C.sizeof(A.MdCall))) == bytes(C.string_at(exp, est.n_calls * C.sizeof(A.MdCall)))
+    b.close()

@@ -149,3 +149,34 @@ def test_phred_encodings_cpu(built, synth, tmp_path, nq):
     p = synth("q%d" % nq, "--contigs", "chr1:50000", "--depth", "25", "--quals", str(nq))
     refp, newp = _both(built, tmp_path, "q", ["--CHG", "--CHH", "-p", "9"], p + ".fa", p + ".bam")
     assert compare_outputs(refp, newp) == []
+
+
+@pytest.mark.parametrize("opts", cases.BED_OPTION_SETS, ids=[cases.slug(o) for o in cases.BED_OPTION_SETS])
+def test_bed_regions(built, synth, tmp_path, opts):
+    """-l / --keepStrand (bed.c; extract.c:353-367, 402-405, 425; common.c:432-439): host BED parsing + chunk skipping with the port's
+    restatement of the three BED tests, against the reference build"""
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    refp, newp = _both(built, tmp_path, "bed", cases.with_bed(opts, tmp_path), p + ".fa", p + ".bam")
+    assert compare_outputs(refp, newp) == []
+    assert sum(1 for _ in open([f for f in __import__("glob").glob(refp + "*")][0])) > 100
+
+
+@pytest.mark.parametrize("opts", cases.BED_MBIAS_SETS, ids=["plain", "strand_allctx"])
+def test_bed_mbias(built, synth, tmp_path, opts):
+    import subprocess
+    import sys
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    o = cases.with_bed(opts, tmp_path)
+    r = subprocess.run([built["ref_bin"], "mbias"] + o + [p + ".fa", p + ".bam"], capture_output=True, text=True)
+    code = ("import sys; sys.path[:0]=[%r,%r]; import oracle_binding as ob; "
+            "sys.exit(ob.run_host_main('mbias', %r, ob.OracleBackend()))") % (cases.ROOT, os.path.join(cases.ROOT, "tests"), o + [p + ".fa", p + ".bam"])
+    n = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and n.returncode == 0, (r.stderr, n.stderr)
+    assert n.stdout == r.stdout and len(r.stdout.splitlines()) > 50
+
+
+def test_bed_malformed_is_refused(built, synth, tmp_path):
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    bad = str(tmp_path / "bad.bed")
+    open(bad, "w").write("chrUnknown\t1\t2\n")
+    assert ob.run_host_main("extract", ["-l", bad, p + ".fa", p + ".bam", "-o", str(tmp_path / "x")], ob.OracleBackend()) == 1   # extract.c:1473-1476
