@@ -141,6 +141,14 @@ int md_set_mbias_chunks(md_ctx *ctx, int32_t tid, const uint32_t *bounds, uint32
  *   - strand (readStrandOverlapsBED, extract.c:425 / MBias.c:184, bed.c:57-63): in a '+' region only OT/CTOT reads are looked at,
  *     in a '-' region only OB/CTOB reads (strand = 0 unless --keepStrand was given).
  * From the first call on the context is in BED mode: tiles of contigs without regions produce nothing.  Call after md_load_contig. */
+/* perRead (perRead.c): the CpG calls processRead() makes on one alignment.  tile->[beg,end) is the region of the contig being
+ * processed (the whole contig, or the -r interval); chunk_size is --chunkSize (chunks start at tile->beg, perRead.c:118-137) and
+ * matters because the CpG context is evaluated in the reference window of the chunk an alignment starts in (perRead.c:176-181).
+ * out[i] belongs to alignment i of `reads`; nmeth == 0xffffffff marks an alignment the sub-command does not report (it starts
+ * outside [beg,end) or fails -q / -F / -R, perRead.c:186-191).  Uses md_config::minMapq, minPhred, ignoreFlags, requireFlags. */
+typedef struct md_read_meth { uint32_t nmeth, nunmeth; } md_read_meth;
+int md_per_read_tile(md_ctx *ctx, const md_tile_desc *tile, const md_reads_soa *reads, uint32_t chunk_size, md_read_meth *out /* n_reads entries */);
+
 typedef struct md_bed_region { uint32_t start, end; uint32_t strand; /* 0 any, 1 '+', 2 '-' */ } md_bed_region;
 int md_set_bed(md_ctx *ctx, int32_t tid, const md_bed_region *regs, uint32_t n);
 

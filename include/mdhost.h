@@ -48,11 +48,14 @@ typedef struct mdh_backend {
     int   (*bam_push_end)(void *s, md_bam_summary *out);
     /* optional: -l <BED> (md_set_bed); without it the sub-commands refuse -l */
     int   (*set_bed)(void *be, int32_t tid, const md_bed_region *regs, uint32_t n);
+    /* optional: perRead (md_per_read_tile); without it the perRead sub-command refuses to run */
+    int   (*per_read_tile)(void *be, const md_tile_desc *tile, const md_reads_soa *reads, uint32_t chunk_size, md_read_meth *out);
 } mdh_backend;
 
 /* Same argv conventions as the reference: argv[0] is the sub-command name. */
 int mdh_extract_main(int argc, char *argv[], const mdh_backend *be);
 int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be);
+int mdh_perread_main(int argc, char *argv[], const mdh_backend *be);   /* perRead_main, perRead.c:305, main.c:20 */
 
 /* Run statistics of the last mdh_extract_main / mdh_mbias_main call in this process */
 typedef struct mdh_run_stats {

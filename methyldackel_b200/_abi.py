@@ -48,6 +48,10 @@ class MdReadsSoa(C.Structure):
     ]
 
 
+class MdReadMeth(C.Structure):
+    _fields_ = [("nmeth", C.c_uint32), ("nunmeth", C.c_uint32)]
+
+
 class MdBedRegion(C.Structure):
     _fields_ = [("start", C.c_uint32), ("end", C.c_uint32), ("strand", C.c_uint32)]
 
@@ -107,6 +111,7 @@ BAM_MBIAS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(MdTileDesc), 
 BAM_PUSH_BEGIN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(MdBgzfBlock), C.c_uint32, C.c_uint32)
 BAM_PUSH_END_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(MdBamSummary))
 SET_BED_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.POINTER(MdBedRegion), C.c_uint32)
+PER_READ_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa), C.c_uint32, C.POINTER(MdReadMeth))
 
 
 class MdhBackend(C.Structure):
@@ -117,7 +122,7 @@ class MdhBackend(C.Structure):
                 ("submit_mbias_tile", SUBMIT_FN),
                 ("bam_open", BAM_OPEN_FN), ("bam_close", BAM_CLOSE_FN), ("bam_reset", BAM_CLOSE_FN), ("bam_push", BAM_PUSH_FN),
                 ("bam_get_runs", BAM_RUNS_FN), ("bam_extract_run", BAM_EXTRACT_FN), ("bam_mbias_run", BAM_MBIAS_FN),
-                ("bam_push_begin", BAM_PUSH_BEGIN_FN), ("bam_push_end", BAM_PUSH_END_FN), ("set_bed", SET_BED_FN)]
+                ("bam_push_begin", BAM_PUSH_BEGIN_FN), ("bam_push_end", BAM_PUSH_END_FN), ("set_bed", SET_BED_FN), ("per_read_tile", PER_READ_FN)]
 
 
 _host = None
@@ -134,6 +139,7 @@ def load_host():
         h = C.CDLL(p)
         h.mdh_extract_main.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(MdhBackend)]
         h.mdh_mbias_main.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(MdhBackend)]
+        h.mdh_perread_main.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(MdhBackend)]
         h.mdh_last_run_stats.argtypes = [C.POINTER(MdhRunStats)]
         h.mdh_bam_open.restype = C.c_void_p; h.mdh_bam_open.argtypes = [C.c_char_p]
         h.mdh_bam_close.argtypes = [C.c_void_p]
@@ -168,6 +174,7 @@ def load_gpu():
         g.md_drop_contig.argtypes = [C.c_void_p, C.c_int32]
         g.md_set_mbias_chunks.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint32), C.c_uint32]
         g.md_set_bed.argtypes = [C.c_void_p, C.c_int32, C.POINTER(MdBedRegion), C.c_uint32]
+        g.md_per_read_tile.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa), C.c_uint32, C.POINTER(MdReadMeth)]
         g.md_extract_tile.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa), C.POINTER(MdCall), C.c_uint64, C.POINTER(MdTileStats)]
         g.md_submit_tile.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa)]
         g.md_submit_mbias_tile.argtypes = [C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa)]

@@ -131,7 +131,8 @@ class _GpuBackend:
                       A.BAM_MBIAS_FN(lambda s, run, td, kh, st: g.md_bam_mbias_run(s, run, td, kh, st)),
                       A.BAM_PUSH_BEGIN_FN(lambda s, c, n, bl, nb, sk: g.md_bam_push_begin(s, c, n, bl, nb, sk)),
                       A.BAM_PUSH_END_FN(lambda s, o: g.md_bam_push_end(s, o)),
-                      A.SET_BED_FN(lambda b, t, r, n: g.md_set_bed(b, t, r, n))]
+                      A.SET_BED_FN(lambda b, t, r, n: g.md_set_bed(b, t, r, n)),
+                      A.PER_READ_FN(lambda b, td, r, ch, out: g.md_per_read_tile(b, td, r, ch, out))]
         self.be = A.MdhBackend(None, *self._keep)
 
 
@@ -140,11 +141,16 @@ def _run(which, argv, device):
     be = _GpuBackend(device)
     args = [which.encode()] + [a.encode() if isinstance(a, str) else a for a in argv]
     arr = (C.c_char_p * (len(args) + 1))(*args, None)
-    fn = h.mdh_extract_main if which == "extract" else h.mdh_mbias_main
+    fn = {"extract": h.mdh_extract_main, "mbias": h.mdh_mbias_main, "perRead": h.mdh_perread_main}[which]
     rc = fn(len(args), arr, C.byref(be.be))
     st = A.MdhRunStats()
     h.mdh_last_run_stats(C.byref(st))
     return rc, st
+
+
+def perread_main(argv, device=0):
+    """`MethylDackel perRead <argv>` on the GPU. Returns (exit code, run stats)."""
+    return _run("perRead", list(argv), device)
 
 
 def extract_main(argv, device=0):

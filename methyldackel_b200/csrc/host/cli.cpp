@@ -761,6 +761,133 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     return rc;
 }
 
+// ---- perRead ------------------------------------------------------------------------------------------------------------
+// `MethylDackel perRead [opts] <ref.fa> <aln.bam>` (perRead.c:205-464): per-alignment CpG methylation.  The host walks the
+// coordinate-sorted file once, hands batches of alignments (SoA, plain phreds) to md_per_read_tile and prints one line per
+// reported alignment in file order, which is the order the reference's chunk-ordered output amounts to.
+static void perread_usage() {
+    fprintf(stderr,
+"\nUsage: MethylDackel perRead [OPTIONS] <ref.fa> <input>\n\n"
+"B200 build of the perRead path: the average CpG methylation level of every read.\n"
+"Output columns: read name, chromosome, position, CpG methylation (%%), number of informative bases.\n"
+"Options (as MethylDackel 0.6.1): -q INT (10)  -p INT (5)  -r STR  -l FILE  --keepStrand  -o STR  -F/--ignoreFlags INT (0)\n"
+"  -R/--requireFlags INT (0)  -@ INT  --chunkSize INT (1000000)  -h/--help  -v/--version\n"
+"Note that this program will produce incorrect values for alignments spanning more than 10kb.\n");
+}
+
+extern "C" int mdh_perread_main(int argc, char *argv[], const mdh_backend *be) {
+    md_config cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.keepCpG = 1; cfg.minMapq = 10; cfg.minPhred = 5;                    // perRead.c:215-230
+    unsigned long chunkSize = 1000000;
+    const char *reg = nullptr, *bedName = nullptr, *oname = nullptr; int c, keepStrand = 0;
+    static struct option lopts[] = {{"help", 0, NULL, 'h'}, {"version", 0, NULL, 'v'}, {"chunkSize", 1, NULL, 19}, {"keepStrand", 0, NULL, 20},
+                                    {"ignoreFlags", 1, NULL, 'F'}, {"requireFlags", 1, NULL, 'R'}, {0, 0, NULL, 0}};
+    FILE *ofile = stdout;
+    optind = 0;
+    while ((c = getopt_long(argc, argv, "hvq:p:o:@:r:l:F:R:", lopts, NULL)) >= 0) {
+        switch (c) {
+        case 'h': perread_usage(); return 0;
+        case 'v': printf("%s (B200 build; no HTSlib)\n", MD_VERSION); return 0;
+        case 'o': oname = optarg; if ((ofile = fopen(optarg, "w")) == NULL) { fprintf(stderr, "Couldn't open %s for writing\n", optarg); return 2; } break;
+        case 'q': cfg.minMapq = atoi(optarg); break;
+        case 'p': cfg.minPhred = atoi(optarg); break;
+        case '@': break;
+        case 'r': reg = optarg; break;
+        case 'l': bedName = optarg; break;
+        case 'F': cfg.ignoreFlags = atoi(optarg); break;
+        case 'R': cfg.requireFlags = atoi(optarg); break;
+        case 19: chunkSize = strtoul(optarg, NULL, 10); if (chunkSize < 1) { fprintf(stderr, "Error: The chunk size must be at least 1!\n"); return 1; } break;
+        case 20: keepStrand = 1; break;
+        default: fprintf(stderr, "Invalid option '%c'\n", c); perread_usage(); return 1;
+        }
+    }
+    (void) oname;
+    if (argc == 1) { perread_usage(); return 0; }
+    if (argc - optind != 2) { fprintf(stderr, "You must supply a reference genome in fasta format and a BAM or CRAM file\n"); perread_usage(); return -1; }
+    if (cfg.minPhred < 1) { fprintf(stderr, "-p %i is invalid. resetting to 1, which is the lowest possible value.\n", cfg.minPhred); cfg.minPhred = 1; }
+    if (cfg.minMapq < 0) { fprintf(stderr, "-q %i is invalid. Resetting to 0, which is the lowest possible value.\n", cfg.minMapq); cfg.minMapq = 0; }
+    if (!be->per_read_tile) { fprintf(stderr, "The device back end does not implement perRead.\n"); return -20; }
+    const char *fastaName = argv[optind], *bamName = argv[optind + 1];
+    std::unique_ptr<Fasta> fa;
+    try { fa.reset(new Fasta(fastaName)); } catch (std::exception &e) { fprintf(stderr, "Couldn't open the index for %s!\n", fastaName); perread_usage(); return -2; }
+    std::unique_ptr<BamStream> bs;
+    try { bs.reset(new BamStream(bamName)); } catch (std::exception &e) { fprintf(stderr, "Couldn't open %s for reading!\n", bamName); return -4; }
+    const BamHeader &hdr = bs->header();
+    BaiIndex bai; const bool have_bai = load_bai(bamName, bai);
+    uint32_t gTid = 0, gPos = 0, gEnd = 0;
+    if (reg) {                                                              // perRead.c:395-420
+        int s, e, nl = parse_region(reg, &s, &e);
+        if (nl < 0) { fprintf(stderr, "Could not parse the specified region!\n"); return -4; }
+        int tid = hdr.name2tid(std::string(reg, (size_t) nl));
+        if (tid < 0) { fprintf(stderr, "%s did not match a known chromosome/contig name!\n", reg); return -6; }
+        gTid = (uint32_t) tid;
+        if (s > 0) gPos = (uint32_t) s;
+        if (e > 0) gEnd = (uint32_t) e;
+        if (gEnd > hdr.lens[gTid]) gEnd = hdr.lens[gTid];
+    }
+    BedFile bed; bool have_bed = false;
+    if (bedName) {
+        if (!bed.load(bedName, hdr.names, hdr.lens, keepStrand != 0)) { fprintf(stderr, "There was an error while reading in your BED file!\n"); return 1; }
+        have_bed = true;
+    }
+    void *dev = be->create(be->factory_user, &cfg);
+    if (!dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
+    int rc = 0;
+    const size_t batch = tile_reads_default(false);
+    const uint32_t chunk32 = (uint32_t) std::min<unsigned long>(chunkSize, 0x7fffffffUL);
+    SoaTile tile; std::vector<char> names; std::vector<uint32_t> name_off; std::vector<md_read_meth> res; std::string line, seq;
+    if (have_bai) { bool found; uint64_t o = bai.start_offset((int) gTid, gPos, found); if (found && o) bs->seek(o); }
+    BamRec r; bool more = bs->peek(r);
+    // contigs in file order from the region's contig on (all of them without -r; with -r only that one, perRead.c:128-131)
+    for (uint32_t tid = gTid; tid < hdr.names.size() && rc == 0; ++tid) {
+        const uint32_t beg = tid == gTid ? gPos : 0, end = (reg && gEnd) ? gEnd : hdr.lens[tid];
+        while (more && r.tid >= 0 && (uint32_t) r.tid < tid) { bs->pop(); more = bs->peek(r); }
+        bool loaded = false;
+        while (more && r.tid == (int32_t) tid && rc == 0) {
+            tile.clear(); names.clear(); name_off.clear();
+            while (more && r.tid == (int32_t) tid && tile.n() < batch) {
+                if (r.pos >= (int32_t) beg && r.pos < (int64_t) end) {
+                    tile.add(r);
+                    name_off.push_back((uint32_t) names.size());
+                    const size_t nl = strnlen(r.qname, r.l_qname);
+                    names.insert(names.end(), r.qname, r.qname + nl); names.push_back('\0');
+                } else if (r.pos >= (int64_t) end) { while (more && r.tid == (int32_t) tid) { bs->pop(); more = bs->peek(r); } break; }
+                bs->pop(); more = bs->peek(r);
+            }
+            if (!tile.n()) continue;
+            if (!loaded) {
+                if (!fa->fetch(hdr.names[tid], seq)) { fprintf(stderr, "Couldn't fetch the sequence of %s!\n", hdr.names[tid].c_str()); rc = -2; break; }
+                if (be->load_contig(dev, (int32_t) tid, seq.data(), (uint32_t) seq.size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+                loaded = true;
+            }
+            md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, beg, end, 0, 0};
+            res.resize(tile.n());
+            if (be->per_read_tile(dev, &td, &v, chunk32, res.data()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+            g_stats.n_records += tile.n(); g_stats.n_tiles++;
+            line.clear();
+            char buf[64];
+            for (size_t i = 0; i < tile.n(); ++i) {
+                if (res[i].nmeth == 0xffffffffu) continue;
+                if (have_bed) {                                            // a chunk no BED region overlaps is skipped as a whole (perRead.c:159-173)
+                    const uint64_t lp = (uint64_t) beg + ((uint64_t)((uint32_t) tile.pos[i] - beg) / chunk32) * chunk32, le = std::min<uint64_t>(lp + chunk32, end);
+                    if (!bed.chunk_overlaps(tid, (uint32_t) lp, (uint32_t) le)) continue;
+                }
+                const uint32_t nm = res[i].nmeth, nu = res[i].nunmeth;
+                line += names.data() + name_off[i]; line += '\t'; line += hdr.names[tid]; line += '\t';
+                snprintf(buf, sizeof buf, "%" PRId64 "\t", (int64_t) tile.pos[i]); line += buf;
+                if (nm + nu > 0) { snprintf(buf, sizeof buf, "%f\t%" PRIu32 "\n", 100. * ((double) nm) / (nm + nu), nm + nu); line += buf; }   // perRead.c:19-25
+                else { snprintf(buf, sizeof buf, "0.0\t%" PRIu32 "\n", nm + nu); line += buf; }                                              // perRead.c:27-31
+            }
+            if (!line.empty()) fputs(line.c_str(), ofile);
+        }
+        if (loaded) be->drop_contig(dev, (int32_t) tid);
+        if (reg) break;
+    }
+    be->destroy(dev);
+    if (ofile != stdout) fclose(ofile);
+    return rc;
+}
+
 extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
     md_config cfg; memset(&cfg, 0, sizeof cfg);
     cfg.keepCpG = 1; cfg.minMapq = 10; cfg.minPhred = 5; cfg.ignoreFlags = 0xF00; cfg.noOverlapMerge = 1;   // MBias.c:312-328, :160

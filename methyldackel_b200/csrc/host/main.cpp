@@ -32,17 +32,20 @@ static int be_bam_push_end(void *s, md_bam_summary *out) { return md_bam_push_en
 
 static int be_set_bed(void *b, int32_t tid, const md_bed_region *r, uint32_t n) { return md_set_bed((md_ctx *) b, tid, r, n); }
 
+static int be_per_read(void *b, const md_tile_desc *t, const md_reads_soa *r, uint32_t chunk, md_read_meth *out) { return md_per_read_tile((md_ctx *) b, t, r, chunk, out); }
+
 static void usage_main() {
     fprintf(stderr, "MethylDackel (B200 build of the extract/mbias hot path): A tool for processing bisulfite sequencing alignments.\n"
                     "Usage: MethylDackel <command> [options]\n\nCommands:\n"
                     "    mbias    Determine the position-dependent methylation bias in a dataset.\n"
                     "    extract  Extract methylation metrics from an alignment file in BAM format.\n"
-                    "(mergeContext and perRead are not part of this build.)\n");
+                    "    perRead  Generate a per-read methylation summary.\n"
+                    "(mergeContext is not part of this build.)\n");
 }
 
 int main(int argc, char *argv[]) {
     mdh_backend be = {nullptr, be_create, be_destroy, be_load, be_drop, be_extract, be_chunks, be_mbias, be_hist, md_last_error, be_submit, be_collect, md_alloc_pinned, md_free_pinned, be_submit_mbias,
-                      be_bam_open, be_bam_close, be_bam_reset, be_bam_push, be_bam_runs, be_bam_extract, be_bam_mbias, be_bam_push_begin, be_bam_push_end, be_set_bed};
+                      be_bam_open, be_bam_close, be_bam_reset, be_bam_push, be_bam_runs, be_bam_extract, be_bam_mbias, be_bam_push_begin, be_bam_push_end, be_set_bed, be_per_read};
     if (argc == 1) { usage_main(); return 0; }
     if (!strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) { usage_main(); return 0; }
     if (!strcmp(argv[1], "-v") || !strcmp(argv[1], "--version")) { printf("0.6.1-b200 (B200 build; no HTSlib)\n"); return 0; }
@@ -58,7 +61,8 @@ int main(int argc, char *argv[]) {
         }
         return rc;
     }
-    if (!strcmp(argv[1], "mergeContext") || !strcmp(argv[1], "perRead")) { fprintf(stderr, "The %s sub-command is not part of the B200 build.\n", argv[1]); return -1; }
+    if (!strcmp(argv[1], "perRead")) return mdh_perread_main(argc - 1, argv + 1, &be);
+    if (!strcmp(argv[1], "mergeContext")) { fprintf(stderr, "The %s sub-command is not part of the B200 build.\n", argv[1]); return -1; }
     fprintf(stderr, "Unknown command!\n"); usage_main();
     return -1;
 }

@@ -941,6 +941,70 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// perRead (perRead.c:37-94, 183-196): one thread per alignment replays processRead() — a sequential walk that cannot be
+// turned into a pileup because of its quirks, all of which are observable and therefore kept:
+//   * a base below minPhred is stepped over and the NEXT base is then looked at without a phred test of its own, under the
+//     CIGAR op of the skipped base even when that op has just ended (perRead.c:59-63); when the skipped base was the read's
+//     last one, the "next base" is the nibble behind the sequence: the pad nibble for odd lengths, the high nibble of the
+//     first phred for even ones (BAM record layout, bam_seqi on index l_qseq);
+//   * CpG context is looked up in the reference window of the chunk the alignment STARTS in: contig[localPos-2, localEnd+10000]
+//     (perRead.c:176-181), so a C on the window's last base is no CpG and everything beyond it is no context at all;
+//   * the only filters are -R, -F, -q (perRead.c:189-191) — no duplicate / NH / singleton logic; an alignment is reported by
+//     the chunk holding its start (perRead.c:186-187);
+//   * a strand of 0 (paired without read1/read2) is treated as a bottom strand: (strand & 1) == 0 (perRead.c:72).
+__global__ void __launch_bounds__(128) per_read_kernel(DevReads R, KParams P, const unsigned char *ref, uint32_t reflen, uint32_t beg, uint32_t end, uint32_t chunk, md_read_meth *out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R.n; i += gridDim.x * blockDim.x) {
+        const unsigned f = R.flag[i];
+        const long long pos = R.pos[i];
+        md_read_meth res; res.nmeth = 0xffffffffu; res.nunmeth = 0;
+        const bool rep = pos >= (long long) beg && pos < (long long) end && !(P.requireFlags && ((unsigned) P.requireFlags & f) != (unsigned) P.requireFlags) &&
+                         !(P.ignoreFlags && ((unsigned) P.ignoreFlags & f) != 0u) && (int) R.mapq[i] >= P.minMapq;
+        if (!rep) { out[i] = res; continue; }
+        // the chunk this alignment starts in, and its reference window (perRead.c:118-137, 176-181)
+        const unsigned long long lp = (unsigned long long) beg + ((unsigned long long)(pos - beg) / chunk) * chunk;
+        const unsigned long long le = min(lp + (unsigned long long) chunk, (unsigned long long) end);
+        const long long w0 = lp > 1 ? (long long) lp - 2 : 0, w1 = (long long) min(le + 10000ull, (unsigned long long) reflen - 1ull);   // inclusive
+        const long long seqlen = w1 - w0 + 1;
+        const int strand = dev_strand(f, R.aux[i]);
+        const bool top = (strand & 1) == 1;
+        const uint32_t lq = R.l_qseq[i], soff = R.seq_off[i], qoff = R.qual_off[i];
+        const uint32_t k0 = R.cigar_off[i], k1 = R.cigar_off[i + 1];
+        uint32_t rp = 0, k = k0, off = 0, nm = 0, nu = 0;
+        unsigned long long mp = (unsigned long long) pos;
+        while (rp < lq && k < k1) {
+            uint32_t c = __ldg(R.cigar + k);
+            if (off >= (c >> 4)) { off = 0; ++k; if (k >= k1) break; c = __ldg(R.cigar + k); }   // (the reference reads one op past the array here)
+            const unsigned type = (0x3C1A7u >> ((c & 15u) << 1)) & 3u;       // bam_cigar_type: bit0 consumes query, bit1 consumes reference
+            if (type & 2u) {
+                if (type & 1u) {
+                    if ((int) dev_qual(R, qoff, (int) rp) < P.minPhred) { ++mp; ++rp; ++off; }
+                    const long long rel = (long long) mp - w0;
+                    int dir = 0;
+                    if (rel < seqlen) {
+                        const unsigned char b0 = __ldg(ref + mp);
+                        if (d_isC(b0)) { if (rel + 1 != seqlen && d_isG(__ldg(ref + mp + 1))) dir = 1; }
+                        else if (d_isG(b0)) { if (rel != 0 && d_isC(__ldg(ref + mp - 1))) dir = -1; }
+                    }
+                    if (dir) {
+                        unsigned base;
+                        if (rp < lq) base = dev_base(R.seq, soff, (int) rp);
+                        else if (lq & 1u) base = (__ldg(R.seq + soff + (lq >> 3)) >> (((lq >> 1) & 3u) << 3)) & 0xfu;   // pad nibble of the last sequence byte
+                        else base = dev_qual(R, qoff, 0) >> 4;                                                          // first phred byte follows the sequence
+                        if (dir == 1 && top) { if (base == 2u) ++nm; else if (base == 8u) ++nu; }
+                        else if (dir == -1 && !top) { if (base == 4u) ++nm; else if (base == 1u) ++nu; }
+                    }
+                    ++mp; ++rp; ++off;
+                } else { mp += c >> 4; ++k; off = 0; }
+            } else if (type & 1u) { rp += c >> 4; ++k; off = 0; }
+            else { ++k; off = 0; }
+        }
+        res.nmeth = nm; res.nunmeth = nu;
+        out[i] = res;
+    }
+}
+
 // K5/K6: put the per-window segments into position order on the device (exclusive scan of the directory
 // counts by one CTA, then a segment copy), so the D2H transfer lands in the caller's buffer already sorted.
 __global__ void __launch_bounds__(1024) dir_scan_kernel(uint2 *dir, uint32_t n_win, uint32_t *sorted_off) {
@@ -1409,6 +1473,32 @@ extern "C" int md_extract_tile(md_ctx *c, const md_tile_desc *tile, const md_rea
     int t = md_submit_tile(c, tile, reads);
     if (t < 0) return t;
     return md_collect_tile(c, t, calls, capacity, stats);
+}
+
+// perRead: one kernel over the tile's alignments, results copied back in input order (out[i].nmeth == 0xffffffff: not reported)
+extern "C" int md_per_read_tile(md_ctx *c, const md_tile_desc *tile, const md_reads_soa *reads, uint32_t chunk_size, md_read_meth *out) {
+    CK(cudaSetDevice(c->device));
+    auto it = c->contigs.find(tile->tid);
+    if (it == c->contigs.end()) { g_err = "tile refers to a contig that was not loaded (md_load_contig)"; return -2; }
+    if (!chunk_size) { g_err = "md_per_read_tile: chunk_size must be at least 1"; return -2; }
+    const Contig &g = it->second;
+    int ticket = -1;
+    Lane *L = free_lane(c, &ticket);
+    if (!L) { g_err = "md_per_read_tile: all lanes are busy (collect a ticket first)"; return -4; }
+    int rc = stage_reads(c, L, L->staged, reads);
+    if (rc) return rc;
+    const uint32_t n = L->staged.view.n;
+    if (!n || !g.len) return 0;
+    if (L->calls.reserve((size_t) n * sizeof(md_read_meth))) return -100;
+    const uint32_t end = std::min(tile->end, g.len), beg = std::min(tile->beg, end);
+    const uint32_t gb = std::min<uint32_t>((n + 127) / 128, 148u * 16u);
+    per_read_kernel<<<gb, 128, 0, L->stream>>>(L->staged.view, c->kp, g.d_seq, g.len, beg, end, chunk_size, (md_read_meth *) L->calls.p);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, L->calls.p, (size_t) n * sizeof(md_read_meth), cudaMemcpyDeviceToHost, L->stream));
+    CK(cudaStreamSynchronize(L->stream));
+    c->last = L;
+    return 0;
 }
 
 extern "C" int md_extract_tile_device(md_ctx *c, const md_tile_desc *tile, const md_dev_reads *reads, md_tile_stats *stats) {

@@ -448,3 +448,60 @@ int mdo_mbias_tile(const md_config *c, const char *ref, uint32_t reflen, uint32_
     free_work(&w);
     return 0;
 }
+
+
+/* ---- perRead (perRead.c:37-94, 183-196) -------------------------------------------------------------------------------- */
+static int cpg_dir(const char *seq, int64_t pos, int64_t seqlen) {          /* isCpG, common.c:49-62 */
+    if (pos >= seqlen) return 0;
+    if (is_c(seq[pos])) { if (pos + 1 == seqlen) return 0; return is_g(seq[pos + 1]) ? 1 : 0; }
+    if (is_g(seq[pos])) { if (pos == 0) return 0; return is_c(seq[pos - 1]) ? -1 : 0; }
+    return 0;
+}
+int mdo_per_read_tile(const md_config *c, const char *ref, uint32_t reflen, uint32_t beg, uint32_t end, uint32_t chunk,
+                      const md_reads_soa *r, md_read_meth *out) {
+    static const int ctype[16] = {3, 1, 2, 2, 1, 0, 0, 3, 3, 0, 0, 0, 0, 0, 0, 0};   /* bam_cigar_type: MIDNSHP=XB */
+    if (end > reflen) end = reflen;
+    if (beg > end) beg = end;
+    for (uint32_t i = 0; i < r->n_reads; ++i) {
+        out[i].nmeth = 0xffffffffu; out[i].nunmeth = 0;
+        int64_t pos = r->pos[i]; uint16_t f = r->flag[i];
+        if (pos < (int64_t) beg || pos >= (int64_t) end) continue;                                   /* perRead.c:186-187 */
+        if (c->requireFlags && (c->requireFlags & f) != c->requireFlags) continue;                   /* :189 */
+        if (c->ignoreFlags && (c->ignoreFlags & f) != 0) continue;                                   /* :190 */
+        if ((int) r->mapq[i] < c->minMapq) continue;                                                 /* :191 */
+        /* chunk of the alignment's start and its reference window contig[localPos2 .. localEnd+10000] (perRead.c:118-137, 176-181) */
+        uint64_t localPos = (uint64_t) beg + ((uint64_t)(pos - beg) / chunk) * chunk, localEnd = localPos + chunk;
+        if (localEnd > end) localEnd = end;
+        int64_t localPos2 = localPos > 1 ? (int64_t) localPos - 2 : 0;
+        int64_t wend = (int64_t) localEnd + 10000; if (wend > (int64_t) reflen - 1) wend = (int64_t) reflen - 1;
+        const char *seq = ref + localPos2; int64_t seqlen = wend - localPos2 + 1;
+        int strand = mdo_strand(f, r->aux[i]);
+        uint32_t lq = r->l_qseq[i], ncig = r->cigar_off[i + 1] - r->cigar_off[i];
+        const uint32_t *cig = r->cigar + r->cigar_off[i];
+        uint32_t readPosition = 0, op = 0, opOffset = 0, nmethyl = 0, nunmethyl = 0;
+        uint64_t mappedPosition = (uint64_t) pos;
+        while (readPosition < lq && op < ncig) {                                                    /* perRead.c:51 */
+            if (opOffset >= (cig[op] >> 4)) { opOffset = 0; op++; if (op >= ncig) break; }            /* :52-55 (the reference then reads cig[ncig]) */
+            int t = ctype[cig[op] & 15];
+            if (t & 2) {
+                if (t & 1) {
+                    if ((int) qual_at(r, i, readPosition) < c->minPhred) { mappedPosition++; readPosition++; opOffset++; }   /* :59-63 */
+                    int direction = cpg_dir(seq, (int64_t) mappedPosition - localPos2, seqlen);     /* :65 */
+                    if (direction) {
+                        /* bam_seqi(readSeq, readPosition); index l_qseq reads the nibble behind the sequence in the BAM record */
+                        uint8_t base;
+                        if (readPosition < lq) base = seq_nib(r, i, readPosition);
+                        else if (lq & 1) base = (uint8_t)(((const uint8_t *)(r->seq + r->seq_off[i]))[lq >> 1] & 0xf);
+                        else base = (uint8_t)(qual_at(r, i, 0) >> 4);
+                        if (direction == 1 && (strand & 1) == 1) { if (base == 2) nmethyl++; else if (base == 8) nunmethyl++; }        /* :68-70 */
+                        else if (direction == -1 && (strand & 1) == 0) { if (base == 4) nmethyl++; else if (base == 1) nunmethyl++; }  /* :71-74 */
+                    }
+                    mappedPosition++; readPosition++; opOffset++;
+                } else { mappedPosition += cig[op++] >> 4; opOffset = 0; }                           /* :80-83 */
+            } else if (t & 1) { readPosition += cig[op++] >> 4; opOffset = 0; }                      /* :85-88 */
+            else { opOffset = 0; op++; }                                                             /* :89-93 */
+        }
+        out[i].nmeth = nmethyl; out[i].nunmeth = nunmethyl;
+    }
+    return 0;
+}

@@ -31,6 +31,10 @@ int mdo_mbias_tile(const md_config *cfg, const char *ref, uint32_t reflen, uint3
                    const uint32_t *bounds, uint32_t n_chunks,
                    const md_reads_soa *reads, uint32_t *hist, int32_t lens[4], md_tile_stats *stats);
 
+/* perRead: processRead() on every alignment of the tile that the sub-command reports (contract of md_per_read_tile) */
+int mdo_per_read_tile(const md_config *cfg, const char *ref, uint32_t reflen, uint32_t beg, uint32_t end, uint32_t chunk_size,
+                      const md_reads_soa *reads, md_read_meth *out);
+
 /* -l <BED>: the regions (sortBED order, bed.c:64-85) of the contig the following mdo_*_tile calls work on; on = 0 switches
  * the BED tests off.  The array must stay alive while it is set. */
 void mdo_set_bed(const md_bed_region *regs, uint32_t n, int on);

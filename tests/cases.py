@@ -102,3 +102,15 @@ def with_bed(opts, tmp_path):
     if not os.path.exists(f):
         open(f, "w").write(BED_TEXT)
     return [f if o == "@BED" else o for o in opts]
+
+
+# perRead (perRead.c): option sets on the synthetic "noisy" data set and on the reference's fixtures
+PERREAD_SETS = [
+    [],
+    ["-q", "0", "-p", "20", "--chunkSize", "777"],          # many low-phred skips (perRead.c:59-63), chunk windows every 777 bp
+    ["-r", "chr1:5000-20000", "-F", "1024"],
+    ["-l", "@BED", "--chunkSize", "3000", "-R", "64"],      # chunk-level BED skipping (perRead.c:159-173)
+    ["-p", "40", "-q", "60", "-@", "4"],
+]
+PERREAD_FIXTURES = [("cg100.fa", "cg_aln.bam", ["-q", "2"]), ("chgchh.fa", "chgchh_aln.bam", ["-q", "0", "-p", "1"]), ("ct100.fa", "ct_aln.bam", ["-q", "0"]),
+                    ("cg100.fa", "cg_with_variants.bam", ["-q", "0", "-p", "30"]), ("cg100.fa", "NH.bam", ["-q", "0"])]

@@ -21,6 +21,7 @@ def lib():
                                           C.POINTER(A.MdCall), C.c_uint64, C.POINTER(A.MdTileStats)]
         o.mdo_mbias_tile.argtypes = [C.POINTER(A.MdConfig), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32,
                                      C.POINTER(A.MdReadsSoa), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(A.MdTileStats)]
+        o.mdo_per_read_tile.argtypes = [C.POINTER(A.MdConfig), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(A.MdReadsSoa), C.POINTER(A.MdReadMeth)]
         o.mdo_set_bed.argtypes = [C.POINTER(A.MdBedRegion), C.c_uint32, C.c_int]; o.mdo_set_bed.restype = None
         o.mdo_strand.argtypes = [C.c_uint16, C.c_uint8]
         o.mdo_admit.argtypes = [C.POINTER(A.MdConfig), C.c_uint16, C.c_uint8, C.c_uint8]
@@ -92,6 +93,10 @@ class OracleBackend:
             else:
                 o.mdo_set_bed(None, 0, 0)
 
+        def per_read_tile(_b, td, reads, chunk, out):
+            seq, n = st["contigs"][td.contents.tid]
+            return o.mdo_per_read_tile(C.byref(st["cfg"]), seq, n, td.contents.beg, td.contents.end, chunk, reads, out)
+
         def extract_tile(_b, td, reads, calls, cap, stats):
             seq, n = st["contigs"][td.contents.tid]
             use_bed(td.contents.tid)
@@ -122,6 +127,8 @@ class OracleBackend:
         self.be = A.MdhBackend(None, *self._keep)      # async slots stay NULL: the driver then runs tile by tile
         self._keep.append(A.SET_BED_FN(set_bed))
         self.be.set_bed = self._keep[-1]
+        self._keep.append(A.PER_READ_FN(per_read_tile))
+        self.be.per_read_tile = self._keep[-1]
         if device_decode:
             # md_bam_* emulated on the CPU (tests/native/mdemu.cpp: the kernels' own per-thread bodies in plain loops); the
             # tiles it assembles go to the oracle through the two callbacks above
@@ -145,5 +152,5 @@ def run_host_main(which, argv, backend):
     h = A.load_host()
     args = [which.encode()] + [a.encode() if isinstance(a, str) else a for a in argv]
     arr = (C.c_char_p * (len(args) + 1))(*args, None)
-    fn = h.mdh_extract_main if which == "extract" else h.mdh_mbias_main
+    fn = {"extract": h.mdh_extract_main, "mbias": h.mdh_mbias_main, "perRead": h.mdh_perread_main}[which]
     return fn(len(args), arr, C.byref(backend.be))

@@ -306,3 +306,54 @@ def test_bed_tile_abi_vs_oracle(built, synth):
     assert gst.n_calls == est.n_calls and est.n_calls > 1000 and gst.n_admitted == est.n_admitted
     assert bytes(C.string_at(got, gst.n_calls * C.sizeof(A.MdCall))) == bytes(C.string_at(exp, est.n_calls * C.sizeof(A.MdCall)))
     b.close()
+
+
+def _perread_cli(built, tmp_path, args, fa, bam):
+    refp, newp = str(tmp_path / "pr_ref.txt"), str(tmp_path / "pr_new.txt")
+    r = subprocess.run([built["ref_bin"], "perRead"] + list(args) + ["-o", refp, fa, bam], capture_output=True, text=True)
+    n = subprocess.run([NEW_BIN, "perRead"] + list(args) + ["-o", newp, fa, bam], capture_output=True, text=True)
+    assert r.returncode == 0 and n.returncode == 0, (r.stderr, n.stderr)
+    return open(refp).read(), open(newp).read()
+
+
+@pytest.mark.parametrize("opts", cases.PERREAD_SETS, ids=[cases.slug(o) for o in cases.PERREAD_SETS])
+def test_cli_perread_synthetic(built, synth, tmp_path, opts):
+    """perRead through the drop-in binary (per_read_kernel) against the reference build, byte for byte"""
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    a, b = _perread_cli(built, tmp_path, cases.with_bed(opts, tmp_path), p + ".fa", p + ".bam")
+    assert a == b and len(a.splitlines()) > 500
+
+
+@pytest.mark.parametrize("fx", cases.PERREAD_FIXTURES, ids=[f[1] for f in cases.PERREAD_FIXTURES])
+def test_cli_perread_fixtures(built, tmp_path, fx):
+    fa, bam, args = fx
+    a, b = _perread_cli(built, tmp_path, args, cases.fx(fa), cases.fx(bam))
+    assert a == b and a
+
+
+def test_cli_perread_indels_clips_long_reads(built, synth, tmp_path):
+    p = synth("len75", "--contigs", "chr1:50000", "--depth", "25", "--readlen", "75", "--isize-mean", "160", "--isize-sd", "40", "--isize-min", "75", "--isize-max", "400")
+    a, b = _perread_cli(built, tmp_path, ["-p", "12", "-q", "0"], p + ".fa", p + ".bam")
+    assert a == b and len(a.splitlines()) > 500
+
+
+def test_perread_tile_abi_vs_oracle(built, synth):
+    """md_per_read_tile through the C ABI against the port, record for record (packed phred tiles included)"""
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    cfg = A.default_config(minMapq=0, minPhred=12)
+    cfg.ignoreFlags = 0
+    b = api.BamFile(p + ".bam")
+    ref = api.fetch_contig(p + ".fa", "chr1")
+    soa = b.read_region(0, 0, len(ref))
+    n = soa.n_reads
+    exp = (A.MdReadMeth * n)(); got = (A.MdReadMeth * n)()
+    o = ob.lib()
+    for beg, end, chunk in [(0, len(ref), 1000000), (5000, 41234, 999), (0, len(ref), 1)]:
+        assert o.mdo_per_read_tile(C.byref(cfg), ref, len(ref), beg, end, chunk, C.byref(soa), exp) == 0
+        with api.GpuContext(cfg) as g:
+            g.load_contig(0, ref)
+            td = A.MdTileDesc(0, beg, end)
+            assert g.g.md_per_read_tile(g.h, C.byref(td), C.byref(soa), chunk, got) == 0
+        assert bytes(got) == bytes(exp)
+        assert sum(1 for k in range(n) if exp[k].nmeth != 0xffffffff and exp[k].nmeth + exp[k].nunmeth > 0) > 1000
+    b.close()

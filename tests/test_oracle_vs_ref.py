@@ -180,3 +180,34 @@ def test_bed_malformed_is_refused(built, synth, tmp_path):
     bad = str(tmp_path / "bad.bed")
     open(bad, "w").write("chrUnknown\t1\t2\n")
     assert ob.run_host_main("extract", ["-l", bad, p + ".fa", p + ".bam", "-o", str(tmp_path / "x")], ob.OracleBackend()) == 1   # extract.c:1473-1476
+
+
+def _perread_both(built, tmp_path, args, fa, bam):
+    import subprocess
+    refp, newp = str(tmp_path / "pr_ref.txt"), str(tmp_path / "pr_new.txt")
+    r = subprocess.run([built["ref_bin"], "perRead"] + list(args) + ["-o", refp, fa, bam], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert ob.run_host_main("perRead", list(args) + ["-o", newp, fa, bam], ob.OracleBackend()) == 0
+    return open(refp).read(), open(newp).read()
+
+
+@pytest.mark.parametrize("opts", cases.PERREAD_SETS, ids=[cases.slug(o) for o in cases.PERREAD_SETS])
+def test_perread_synthetic(built, synth, tmp_path, opts):
+    """perRead (perRead.c:37-94, 183-196): host driver + the port's restatement of processRead against the reference build"""
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    a, b = _perread_both(built, tmp_path, cases.with_bed(opts, tmp_path), p + ".fa", p + ".bam")
+    assert a == b and len(a.splitlines()) > 500
+
+
+@pytest.mark.parametrize("fx", cases.PERREAD_FIXTURES, ids=[f[1] for f in cases.PERREAD_FIXTURES])
+def test_perread_fixtures(built, tmp_path, fx):
+    fa, bam, args = fx
+    a, b = _perread_both(built, tmp_path, args, cases.fx(fa), cases.fx(bam))
+    assert a == b and a
+
+
+def test_perread_indels_clips_long_reads(built, synth, tmp_path):
+    """odd read length (pad nibble behind the sequence), indels and clips next to low-phred bases: the skipped-base quirk crosses CIGAR op ends"""
+    p = synth("len75", "--contigs", "chr1:50000", "--depth", "25", "--readlen", "75", "--isize-mean", "160", "--isize-sd", "40", "--isize-min", "75", "--isize-max", "400")
+    a, b = _perread_both(built, tmp_path, ["-p", "12", "-q", "0"], p + ".fa", p + ".bam")
+    assert a == b and len(a.splitlines()) > 500
