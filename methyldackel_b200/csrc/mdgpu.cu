@@ -628,17 +628,25 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
             if (s64 >= rr.y) break;
             const uint32_t s = (uint32_t) s64, e = min(s + nb, rr.y), i = s + lane;
             // -- every lane: scalars of its alignment (the first and last lanes' offsets also delimit the batch's byte ranges)
+            // Loads are issued level by level (everything addressed by i first, then what those values address), unconditionally
+            // where a condition would only serialise two round trips to L2/HBM; the values are used further down.
             unsigned inf = 0; bool live = false;
-            int pos = 0, lq = 0, mate = -1; unsigned f = 0; uint32_t soff = 0, qoff = 0, k0 = 0, k1 = 0, c0 = 0;
+            int pos = 0, lq = 0, mate = -1, rend_i = 0; unsigned f = 0; uint32_t soff = 0, qoff = 0, k0 = 0, k1 = 0, c0 = 0;
+            int m_pos = 0, m_end = 0; unsigned m_inf = 0, m_flag = 0; uint32_t m_k0 = 0, m_k1 = 0, m_soff = 0, m_qoff = 0, m_lq = 0, m_c0 = 0;
             if (i < e) {
                 soff = R.seq_off[i]; qoff = R.qual_off[i]; lq = (int) R.l_qseq[i];
-                inf = A.info[i];
-                live = (inf & INFO_ADMIT) && (long long) A.rend[i] > w0;
+                inf = A.info[i]; rend_i = A.rend[i];
+                pos = R.pos[i]; f = R.flag[i];
+                k0 = R.cigar_off[i]; k1 = R.cigar_off[i + 1];
+                mate = (MODE == 2) ? -1 : A.mate[i];
+                live = (inf & INFO_ADMIT) && (long long) rend_i > w0;
                 if (live) {
-                    pos = R.pos[i]; f = R.flag[i];
-                    k0 = R.cigar_off[i]; k1 = R.cigar_off[i + 1];
-                    mate = (MODE == 2) ? -1 : A.mate[i];
                     c0 = __ldg(R.cigar + k0);
+                    if (mate >= 0) {
+                        m_pos = R.pos[mate]; m_end = A.rend[mate]; m_inf = A.info[mate];
+                        m_k0 = R.cigar_off[mate]; m_k1 = R.cigar_off[mate + 1];
+                        m_soff = R.seq_off[mate]; m_qoff = R.qual_off[mate]; m_flag = R.flag[mate]; m_lq = R.l_qseq[mate];
+                    }
                 }
             }
             // -- lane 0 streams the batch's bases and phreds into the warp's staging buffer (TMA, completion on the warp's mbarrier)
@@ -662,7 +670,21 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
                 rc.strand = INFO_STRAND(inf); rc.rd2 = (f & 0x80u) ? 1 : 0; rc.wantG = !(rc.strand & 1);
                 dev_trim(A.P, rc.strand, f, lq, rc.lo, rc.hi);
                 rc.soff = soff; rc.qoff = qoff;
-                load_mate(A, i, mate, rc);
+                // mate descriptor (overlap merge): cust_tweak_overlap_quality bails out when the strands differ in parity (overlaps.c:65);
+                // disjoint spans have nothing to merge
+                rc.mi = mate;
+                if (mate >= 0) {
+                    const int ms = INFO_STRAND(m_inf);
+                    rc.mpos = m_pos; rc.mend = m_end;
+                    if (((rc.strand - ms) & 1) || !(pos < m_end && m_pos < rend_i)) rc.mi = -1;
+                    else {
+                        rc.mk0 = m_k0; rc.mk1 = m_k1; rc.msoff = m_soff; rc.mqoff = m_qoff;
+                        dev_trim(A.P, ms, m_flag, (int) m_lq, rc.mlo, rc.mhi);
+                        rc.is_a = (uint32_t) mate > i;                    // first in file order is `a` (overlaps.c:129-135)
+                        rc.mate_simple = false; rc.mq0 = 0;                // a mate whose CIGAR is a single match op maps reference -> query by subtraction
+                        if (m_k1 - m_k0 == 1) { m_c0 = __ldg(R.cigar + m_k0) & 15u; rc.mate_simple = (m_c0 == 0 || m_c0 == 7 || m_c0 == 8); }
+                    }
+                }
                 const uint32_t sw_need = ((((uint32_t) lq + 1u) >> 1) + 3u) >> 2, qw_need = qual_words_of(R, (uint32_t) lq);
                 staged = soff >= sw0 && soff + sw_need <= sw1 && qoff >= qw0 && qoff + qw_need <= qw1;
                 uint32_t *cx = rctx + WS_CTX_WORDS * lane;
