@@ -306,6 +306,7 @@ struct CountArgs {
     uint32_t st_seq, st_qual;                              // per-warp staging capacities in bytes (count_warp)
     uint32_t wide;                                         // 1: 32-bit window counters; 0: 16-bit pairs packed in one word (overflow -> rerun wide)
     BedView bed;
+    uint32_t split; uint32_t *acc; uint32_t *done;         // deep tiles: `split` CTAs share a window's alignments; their counters meet in acc[] (32-bit layout per window), the last one to arrive (done[]) writes the calls
     uint32_t ablate;                                       // timing experiments only (MD_ABLATE): 1 skip evaluation, 2 skip generation, 4 skip staging copies
     uint32_t okmask;                                       // 2-/4-bit phred tiles: bit c set when code c decodes to a phred >= minPhred
 };
@@ -515,7 +516,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
     unsigned char *sseq = wbase + SL.off_seq, *squal = wbase + SL.off_qual;
     uint32_t *rctx = (uint32_t *)(wbase + SL.off_ctx), *queue = (uint32_t *)(wbase + SL.off_queue);
     unsigned char *refw = smem + SL.off_warp;                             // prologue only: overlays the warps' staging area
-    const uint32_t w = blockIdx.x;
+    const uint32_t S = A.split, w = blockIdx.x / S, part = blockIdx.x - w * S;
     const long long w0 = (long long) A.beg + (long long) w * W;
     const long long own1 = min((long long) A.end, w0 + (long long) W);
     const int own = (int)(own1 - w0), w0i = (int) w0;
@@ -595,7 +596,12 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
         }
     }
     __syncthreads();                                                      // bitmaps complete; refw (overlay) no longer needed
-    const uint2 rr = make_uint2(s_rr[0], max(s_rr[0], s_rr[1]));
+    uint2 rr = make_uint2(s_rr[0], max(s_rr[0], s_rr[1]));
+    if (S > 1) {                                                          // this CTA's share of the window's alignments
+        const unsigned long long len = rr.y - rr.x;
+        const uint32_t lo = rr.x + (uint32_t)(len * part / S), hi = rr.x + (uint32_t)(len * (part + 1) / S);
+        rr = make_uint2(lo, hi);
+    }
 
     // ---- streaming phase: every warp on its own -----------------------------------------------------------
     const uint32_t maxlq = A.counters[C_MAXLQ];
@@ -915,7 +921,31 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
         }
         return;
     }
-    __shared__ uint32_t s_warp_tot[WS_WARPS], s_base;
+    __shared__ uint32_t s_warp_tot[WS_WARPS], s_base, s_last;
+    // deep tiles: add this CTA's counters to the window's accumulators in HBM; whoever arrives last reads the sums back
+    const uint32_t *acc = A.acc + (size_t) w * (MODE == 1 ? 4u : 2u) * W;
+    if (S > 1) {
+        uint32_t *accw = A.acc + (size_t) w * (MODE == 1 ? 4u : 2u) * W;
+        const uint32_t nwords = (MODE == 1 ? 4u * W : 2u * W) >> (A.wide ? 0 : 1);
+        for (uint32_t t = tid; t < nwords; t += WS_WARPS * 32) {
+            const uint32_t v = cnt[t];
+            if (!v) continue;
+            if (A.wide) atomicAdd(accw + t, v);
+            else {                                                          // word t < W: meth | unmeth << 16 of column t; word W + t: nOff | nVariant << 16
+                const uint32_t col = t < W ? t : t - W, base0 = t < W ? 0u : 2u * W;
+                if (v & 0xffffu) atomicAdd(accw + base0 + col, v & 0xffffu);
+                if (v >> 16) atomicAdd(accw + base0 + W + col, v >> 16);
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(A.done + w, 1u) == S - 1u) ? 1u : 0u;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+    }
+    auto c_meth = [&](uint32_t t) -> uint32_t { return S > 1 ? __ldcg(acc + t) : (A.wide ? cnt[t] : (cnt[t] & 0xffffu)); };
+    auto c_unmeth = [&](uint32_t t) -> uint32_t { return S > 1 ? __ldcg(acc + W + t) : (A.wide ? cnt[W + t] : (cnt[t] >> 16)); };
     const uint32_t t16 = 16u * tid;
     unsigned rep = 0;
     {
@@ -926,11 +956,12 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
             const uint32_t t = t16 + kbit;
             bool excl = false;
             if (MODE == 1) {
-                const uint32_t noff = A.wide ? cnt[2 * W + t] : (cnt[W + t] & 0xffffu), nvar = A.wide ? cnt[3 * W + t] : (cnt[W + t] >> 16);
+                const uint32_t noff = S > 1 ? __ldcg(acc + 2 * W + t) : (A.wide ? cnt[2 * W + t] : (cnt[W + t] & 0xffffu));
+                const uint32_t nvar = S > 1 ? __ldcg(acc + 3 * W + t) : (A.wide ? cnt[3 * W + t] : (cnt[W + t] >> 16));
                 excl = A.P.minOppositeDepth > 0 && noff >= (uint32_t) A.P.minOppositeDepth && ((double) nvar) / ((double) noff) >= A.P.maxVariantFrac;
             }
             if (excl) rep |= 0x10000u << kbit;
-            if (excl || (A.wide ? cnt[t] + cnt[W + t] : cnt[t])) rep |= 1u << kbit;
+            if (excl || (c_meth(t) + c_unmeth(t))) rep |= 1u << kbit;
         }
     }
     const uint32_t mine = __popc(rep & 0xffffu);
@@ -956,7 +987,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
         while (r16) {
             const int kbit = __ffs(r16) - 1; r16 &= r16 - 1;
             const uint32_t t = t16 + kbit;
-            md_call c; c.pos = (uint32_t)(w0 + t); c.nmeth = A.wide ? cnt[t] : (cnt[t] & 0xffffu); c.nunmeth = A.wide ? cnt[W + t] : (cnt[t] >> 16);
+            md_call c; c.pos = (uint32_t)(w0 + t); c.nmeth = c_meth(t); c.nunmeth = c_unmeth(t);
             c.info = (((a16 >> kbit) & 1u) ? 0u : ((b16 >> kbit) & 1u) ? 1u : 2u) | (((g16 >> kbit) & 1u) ? 4u : 0u) | (((rep >> (16 + kbit)) & 1u) ? 8u : 0u);
             A.calls[o++] = c;
         }
@@ -1085,7 +1116,7 @@ struct md_dev_reads {
 struct Lane {
     cudaStream_t stream = nullptr;
     md_dev_reads staged;                 // device copy of the host tile
-    DevBuf rend, info, mate, tab, win, dir, calls, counters, sorted, sorted_off;
+    DevBuf rend, info, mate, tab, win, dir, calls, counters, sorted, sorted_off, acc, done;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float timing[5] = {0, 0, 0, 0, 0};
     uint32_t last_nwin = 0; uint64_t last_ncalls = 0; bool pending = false; md_tile_stats last_stats;
@@ -1100,6 +1131,7 @@ struct md_ctx {
     uint32_t *d_hist = nullptr; int32_t *d_lens = nullptr;
     uint64_t launches = 0;
     uint32_t W = 4096;
+    uint32_t split_above = 4096, force_split = 0;   // windows averaging more alignments than this are split across CTAs (MD_SPLIT_ABOVE, MD_FORCE_SPLIT for tests)
     bool bed_mode = false;               // md_set_bed was called: -l semantics for every tile
     uint32_t ablate = 0;                 // MD_ABLATE: timing experiments (results are wrong when set)
     int gen = 1;                         // count_warp<MODE, GEN>: 1 = segment-at-a-time candidate generator, 0 = one candidate per lane per ballot (kept for A/B runs, MD_GEN=0)
@@ -1143,6 +1175,8 @@ extern "C" md_ctx *md_create(const md_config *cfg, int device) {
     cudaFuncSetAttribute(count_warp<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
     cudaFuncSetAttribute(count_warp<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
     if (const char *v = getenv("MD_ABLATE")) c->ablate = (uint32_t) atoi(v);
+    if (const char *v = getenv("MD_SPLIT_ABOVE")) c->split_above = (uint32_t) atol(v);
+    if (const char *v = getenv("MD_FORCE_SPLIT")) { int e = atoi(v); c->force_split = e > 0 && e <= 64 ? (uint32_t) e : 0u; }
     if (const char *v = getenv("MD_GEN")) { int e = atoi(v); if (e == 0 || e == 1) c->gen = e; }
     cudaStreamSynchronize(L->stream);
     return c;
@@ -1156,7 +1190,7 @@ extern "C" void md_destroy(md_ctx *c) {
     for (int k = 0; k < MD_NLANES; ++k) {
         Lane *L = &c->lanes[k];
         L->staged.arena.release();
-        DevBuf *bufs[] = {&L->rend, &L->info, &L->mate, &L->tab, &L->win, &L->dir, &L->calls, &L->counters, &L->sorted, &L->sorted_off};
+        DevBuf *bufs[] = {&L->rend, &L->info, &L->mate, &L->tab, &L->win, &L->dir, &L->calls, &L->counters, &L->sorted, &L->sorted_off, &L->acc, &L->done};
         for (DevBuf *b : bufs) b->release();
         for (int i = 0; i < 5; ++i) if (L->ev[i]) cudaEventDestroy(L->ev[i]);
         if (L->h_counters) cudaFreeHost(L->h_counters);
@@ -1278,18 +1312,36 @@ static int launch_count(md_ctx *c, Lane *L, const Contig &g, const DevReads &R, 
     // 2-bit tiles with packed counters fit three CTAs per SM, everything else two
     A.st_seq = WS_SEQ_BYTES; A.st_qual = std::min<uint32_t>(WS_QUAL_BYTES, 32u * (((160u * R.qbits + 63u) >> 6) * 8u) + 32u);
     A.wide = wide ? 1u : 0u;
+    // deep, narrow tiles (targeted panels: thousands of alignments per position window) would run on a handful of CTAs;
+    // give every window several CTAs, each with ~2048 of its alignments
+    A.split = 1; A.acc = nullptr; A.done = nullptr;
+    {
+        const uint64_t avg = (uint64_t) R.n / n_win;
+        uint32_t S = avg > c->split_above ? (uint32_t) std::min<uint64_t>(48, (avg + 2047) / 2048) : 1u;
+        if (c->force_split) S = c->force_split;
+        if (S > 1) {
+            const size_t acc_bytes = (size_t) n_win * (mode == 1 ? 4u : 2u) * W * 4u;
+            if (mode != 2) {
+                if (L->acc.reserve(acc_bytes) || L->done.reserve((size_t) n_win * 4)) return -100;
+                CK(cudaMemsetAsync(L->acc.p, 0, acc_bytes, s)); CK(cudaMemsetAsync(L->done.p, 0, (size_t) n_win * 4, s));
+                A.acc = (uint32_t *) L->acc.p; A.done = (uint32_t *) L->done.p;
+            }
+            A.split = S;
+        }
+    }
+    const uint32_t n_cta = n_win * A.split;
     A.ablate = c->ablate;
     A.bed.start = g.d_bed; A.bed.pmax = g.d_bed ? g.d_bed + g.n_bed : nullptr; A.bed.strand = g.d_bed ? g.d_bed + 2 * (size_t) g.n_bed : nullptr; A.bed.n = g.n_bed; A.bed.on = c->bed_mode ? 1u : 0u;
     A.okmask = 0; for (int cde = 0; cde < 16; ++cde) if ((int) R.qlut[cde] >= kp.minPhred) A.okmask |= 1u << cde;
     const size_t sm = warp_layout(W, mode, A.wide, A.st_seq, A.st_qual).total;
     if (c->gen == 1) {
-        if (mode == 2) count_warp<2, 1><<<n_win, WS_WARPS * 32, sm, s>>>(A);
-        else if (mode == 1) count_warp<1, 1><<<n_win, WS_WARPS * 32, sm, s>>>(A);
-        else count_warp<0, 1><<<n_win, WS_WARPS * 32, sm, s>>>(A);
+        if (mode == 2) count_warp<2, 1><<<n_cta, WS_WARPS * 32, sm, s>>>(A);
+        else if (mode == 1) count_warp<1, 1><<<n_cta, WS_WARPS * 32, sm, s>>>(A);
+        else count_warp<0, 1><<<n_cta, WS_WARPS * 32, sm, s>>>(A);
     } else {
-        if (mode == 2) count_warp<2, 0><<<n_win, WS_WARPS * 32, sm, s>>>(A);
-        else if (mode == 1) count_warp<1, 0><<<n_win, WS_WARPS * 32, sm, s>>>(A);
-        else count_warp<0, 0><<<n_win, WS_WARPS * 32, sm, s>>>(A);
+        if (mode == 2) count_warp<2, 0><<<n_cta, WS_WARPS * 32, sm, s>>>(A);
+        else if (mode == 1) count_warp<1, 0><<<n_cta, WS_WARPS * 32, sm, s>>>(A);
+        else count_warp<0, 0><<<n_cta, WS_WARPS * 32, sm, s>>>(A);
     }
     c->launches += 1;
     if (!mbias) {

@@ -29,9 +29,15 @@ def test_oracle_accepts_adversarial_tiles(built):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("split", [0, 3, 7], ids=["one_cta_per_window", "split3", "split7"])
 @pytest.mark.parametrize("seed", list(range(24)))
-def test_gpu_equals_oracle_on_random_tiles(built, seed):
+def test_gpu_equals_oracle_on_random_tiles(built, seed, split, monkeypatch):
+    """split > 0 forces the deep-tile path: several CTAs per window, counters summed in HBM, the last CTA writes the calls"""
     from methyldackel_b200 import api
+    if split:
+        if seed % 2:
+            pytest.skip("forced split runs on every other seed")
+        monkeypatch.setenv("MD_FORCE_SPLIT", str(split))
     rng = np.random.default_rng(1000 + seed)
     reflen = int(rng.choice([300, 4096, 4097, 9000, 20000]))
     ref = rt.random_reference(rng, reflen)
@@ -56,8 +62,10 @@ def test_gpu_equals_oracle_on_random_tiles(built, seed):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", list(range(6)))
-def test_gpu_mbias_equals_oracle_on_random_tiles(built, seed):
+def test_gpu_mbias_equals_oracle_on_random_tiles(built, seed, monkeypatch):
     from methyldackel_b200 import api
+    if seed % 2:
+        monkeypatch.setenv("MD_FORCE_SPLIT", "5")
     rng = np.random.default_rng(5000 + seed)
     reflen = int(rng.choice([4096, 9000, 20000]))
     ref = rt.random_reference(rng, reflen)
