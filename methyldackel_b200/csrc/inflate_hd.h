@@ -37,11 +37,14 @@ struct Tables {
 
 struct BitReader {
     const uint32_t *words;   // 4-byte aligned base of the buffer the stream lives in (padded by >= 8 readable bytes)
-    uint64_t next;           // index of the next word to load
+    uint64_t next;           // index of the next word to go into the bit buffer
     uint64_t buf; int cnt;   // LSB-first bit buffer
     uint64_t end_word;       // first word index wholly beyond the stream (reads past it yield zeros)
+    uint32_t pre0, pre1;     // words[next], words[next + 1], loaded ahead of their use: on the device the compressed stream comes
+                             // from L2/HBM, and a load issued only when the buffer runs dry would sit on the decoder's critical path
 };
 
+MD_HD uint32_t br_word(const BitReader &b, uint64_t i) { return i < b.end_word ? b.words[i] : 0u; }
 MD_HD void br_init(BitReader &b, const void *base_aligned, uint64_t byte_off, uint64_t byte_len) {
     b.words = (const uint32_t *) base_aligned;
     b.next = byte_off >> 2;
@@ -49,13 +52,14 @@ MD_HD void br_init(BitReader &b, const void *base_aligned, uint64_t byte_off, ui
     b.buf = 0; b.cnt = 0;
     const int mis = (int)(byte_off & 3);
     if (byte_len) { b.buf = (uint64_t)(b.words[b.next++] >> (8 * mis)); b.cnt = 32 - 8 * mis; }
+    b.pre0 = br_word(b, b.next); b.pre1 = br_word(b, b.next + 1);
 }
 // at least 33 bits available afterwards (zeros once the stream is exhausted)
 MD_HD void br_fill(BitReader &b) {
     if (b.cnt <= 32) {
-        const uint32_t w = b.next < b.end_word ? b.words[b.next] : 0u;
+        b.buf |= (uint64_t) b.pre0 << b.cnt; b.cnt += 32;
         ++b.next;
-        b.buf |= (uint64_t) w << b.cnt; b.cnt += 32;
+        b.pre0 = b.pre1; b.pre1 = br_word(b, b.next + 1);
     }
 }
 MD_HD uint32_t br_peek(const BitReader &b, int n) { return (uint32_t)(b.buf & ((1ull << n) - 1ull)); }
