@@ -31,7 +31,8 @@ struct BedFile {
             std::string line = text.substr(at, nl == std::string::npos ? std::string::npos : nl - at);
             at = nl == std::string::npos ? text.size() : nl + 1;
             ++lnum;
-            if (line.empty() || line[0] == '#') continue;
+            if (line.empty()) break;                           // ks_getuntil() returns the line length and parseBED loops while it is > 0 (bed.c:118): an empty line ends the file
+            if (line[0] == '#') continue;
             const char *s = line.c_str(), *p = s;
             while (*p && !isspace((unsigned char) *p)) ++p;
             const std::string name(s, (size_t)(p - s));

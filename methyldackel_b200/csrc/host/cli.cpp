@@ -92,7 +92,7 @@ static void mbias_usage() {
 "  -q INT  -p INT  -r STR  -l FILE (BED)  --keepStrand  -@ INT  --chunkSize INT  -D INT (ignored)  --noCpG  --CHG  --CHH\n"
 "  --keepDupes  --keepSingleton  --keepDiscordant  -F INT  -R INT  --ignoreNH  --txt  --noSVG\n"
 "  --nOT/--nOB/--nCTOT/--nCTOB INT,INT,INT,INT  -h/--help  -v/--version\n"
-"Not available in this build yet: --minConversionEfficiency.\n");
+"  --minConversionEfficiency FLOAT\n");
 }
 
 static bool load_bai(const std::string &bam, BaiIndex &idx) {
@@ -944,12 +944,12 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
     if (cfg.minMapq < 0) { fprintf(stderr, "-q %i is invalid. Resetting to 0, which is the lowest possible value.\n", cfg.minMapq); cfg.minMapq = 0; }
     if (!(cfg.keepCpG + cfg.keepCHG + cfg.keepCHH)) {
         fprintf(stderr, "You haven't specified any metrics to output!\nEither don't use the --noCpG option or specify --CHG and/or --CHH.\n"); return -1; }
-    if (minConvEff > 0.0) { fprintf(stderr, "This B200 build of the mbias path does not implement --minConversionEfficiency yet.\n"); return 1; }
+    cfg.minConversionEfficiency = (float) minConvEff;               // Config.minConversionEfficiency is a float (MethylDackel.h:110)
     // NB: mbias never applies the 0x400 adjustment of extract.c:1005-1007 (MBias.c has no such line)
 
     Driver d; d.be = be;
     const char *fastaName = argv[optind], *bamName = argv[optind + 1];
-    const bool dev_decode = device_decode_enabled(be) && !(false);
+    const bool dev_decode = device_decode_enabled(be) && !(minConvEff > 0.0);
     try {
         if (dev_decode) { BgzfReader rd(bamName); d.own_hdr = read_bam_header(rd); d.start_voff = rd.tell(); d.hdr = &d.own_hdr; }
         else { const int nt = decode_threads(nThreads, threads_given); d.bam.reset(new ParallelBam(bamName, nt, warm_threads(nt))); d.hdr = &d.bam->header(); }
@@ -1039,7 +1039,17 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
                 be->set_mbias_chunks(d.dev, (int32_t) tid, bounds.data(), (uint32_t) bounds.size() - 1) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
             if ((rc = d.push_bed(tid)) != 0) break;
             d.seek_to((int) tid, rbeg);
-            FragTiler tiler(*d.bam, d.frag, d.frag_i, (int) tid, rbeg, rend, tile_reads); tiler.set_pack_quals(pack_quals_enabled());
+            // With --minConversionEfficiency the verdict on an alignment depends on the chunk it is looked at in: the filter only sees
+            // the chunk's own window contig[localPos, localEnd] (MBias.c:147,154-156; common.c:363,378), so tiles are cut at chunk ends
+            // and carry that window; otherwise the whole run of chunks is one region.
+            const bool per_chunk = cfg.minConversionEfficiency > 0.0f;
+            std::vector<std::pair<uint32_t, uint32_t>> regions;
+            if (per_chunk) for (size_t k = 0; k + 1 < bounds.size(); ++k) regions.emplace_back(bounds[k], std::min<uint32_t>(bounds[k + 1], rend));
+            else regions.emplace_back(rbeg, rend);
+            for (size_t ri = 0; ri < regions.size() && rc == 0; ++ri) {
+            const uint32_t gbeg = regions[ri].first, gend = regions[ri].second;
+            const uint32_t ce_beg = per_chunk ? gbeg : 0, ce_end = per_chunk ? (uint32_t) std::min<uint64_t>((uint64_t) bounds[ri + 1] + 1, ref->size()) : 0;
+            FragTiler tiler(*d.bam, d.frag, d.frag_i, (int) tid, gbeg, gend, tile_reads); tiler.set_pack_quals(pack_quals_enabled());
             carry.clear();
             for (;;) {
                 SoaTile &tile = *ring[rk % ring.size()];
@@ -1050,7 +1060,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
                 g_stats.t_decode_s += now_s() - t0;
                 if (!got) break;
                 if (tile.n() == 0) continue;
-                md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end, 0, 0}; md_tile_stats st;
+                md_reads_soa v = tile.view(); md_tile_desc td{(int32_t) tid, tile.beg, tile.end, ce_beg, ce_end}; md_tile_stats st;
                 g_stats.n_records += tile.n(); g_stats.n_tiles++;
                 t0 = now_s();
                 if (use_async) {
@@ -1064,6 +1074,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
                     if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
                 }
             }
+            }   // regions
             while (rc == 0 && !flight.empty()) rc = collect_one();       // the contig (and its chunk table) is dropped next
             be->drop_contig(d.dev, (int32_t) tid);
         }

@@ -403,9 +403,17 @@ int mdo_extract_tile_ce(const md_config *c, const char *ref, uint32_t reflen, ui
 int mdo_mbias_tile(const md_config *c, const char *ref, uint32_t reflen, uint32_t beg, uint32_t end,
                    const uint32_t *bounds, uint32_t n_chunks,
                    const md_reads_soa *r, uint32_t *hist, int32_t lens[4], md_tile_stats *st) {
+    return mdo_mbias_tile_ce(c, ref, reflen, beg, end, 0, 0, bounds, n_chunks, r, hist, lens, st);
+}
+
+int mdo_mbias_tile_ce(const md_config *c, const char *ref, uint32_t reflen, uint32_t beg, uint32_t end, uint32_t ce_beg, uint32_t ce_end,
+                      const uint32_t *bounds, uint32_t n_chunks,
+                      const md_reads_soa *r, uint32_t *hist, int32_t lens[4], md_tile_stats *st) {
     work_t w; uint32_t n_adm = 0;
     if (end > reflen) end = reflen;
-    if (build_work(c, r, &w, &n_adm, ref, 0, reflen) < 0) { free_work(&w); return -2; }
+    if (ce_end == 0 || ce_end > reflen) ce_end = reflen;
+    if (ce_beg > ce_end) ce_beg = ce_end;
+    if (build_work(c, r, &w, &n_adm, ref, ce_beg, ce_end) < 0) { free_work(&w); return -2; }
     for (uint32_t i = 0; i < r->n_reads; ++i) {
         if (!w.admit[i]) continue;
         int s = w.strand[i];

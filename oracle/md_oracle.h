@@ -39,6 +39,11 @@ int mdo_per_read_tile(const md_config *cfg, const char *ref, uint32_t reflen, ui
  * the BED tests off.  The array must stay alive while it is set. */
 void mdo_set_bed(const md_bed_region *regs, uint32_t n, int on);
 
+/* same with the conversion-efficiency window of the tile's chunk (MBias.c:154-156: contig[localPos, localEnd]; 0,0 = whole contig) */
+int mdo_mbias_tile_ce(const md_config *cfg, const char *ref, uint32_t reflen, uint32_t beg, uint32_t end, uint32_t ce_beg, uint32_t ce_end,
+                      const uint32_t *bounds, uint32_t n_chunks,
+                      const md_reads_soa *reads, uint32_t *hist, int32_t lens[4], md_tile_stats *stats);
+
 /* Per-read helpers exposed for unit tests */
 int mdo_strand(uint16_t flag, uint8_t aux);                       /* getStrand, common.c:84-116 */
 int mdo_admit(const md_config *cfg, uint16_t flag, uint8_t mapq, uint8_t aux); /* filter_func, common.c:416-430 */

@@ -23,6 +23,8 @@ def lib():
                                      C.POINTER(A.MdReadsSoa), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(A.MdTileStats)]
         o.mdo_per_read_tile.argtypes = [C.POINTER(A.MdConfig), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(A.MdReadsSoa), C.POINTER(A.MdReadMeth)]
         o.mdo_set_bed.argtypes = [C.POINTER(A.MdBedRegion), C.c_uint32, C.c_int]; o.mdo_set_bed.restype = None
+        o.mdo_mbias_tile_ce.argtypes = [C.POINTER(A.MdConfig), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32,
+                                        C.POINTER(A.MdReadsSoa), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(A.MdTileStats)]
         o.mdo_strand.argtypes = [C.c_uint16, C.c_uint8]
         o.mdo_admit.argtypes = [C.POINTER(A.MdConfig), C.c_uint16, C.c_uint8, C.c_uint8]
         o.mdo_context.argtypes = [C.c_char_p, C.c_int, C.c_int]
@@ -110,7 +112,7 @@ class OracleBackend:
             seq, n = st["contigs"][td.contents.tid]
             b = st["chunks"][td.contents.tid]
             use_bed(td.contents.tid)
-            return o.mdo_mbias_tile(C.byref(st["cfg"]), seq, n, td.contents.beg, td.contents.end, b, len(b) - 1, reads, st["hist"], st["lens"], stats)
+            return o.mdo_mbias_tile_ce(C.byref(st["cfg"]), seq, n, td.contents.beg, td.contents.end, td.contents.ce_beg, td.contents.ce_end, b, len(b) - 1, reads, st["hist"], st["lens"], stats)
 
         def mbias_hist(_b, hist, lens):
             C.memmove(hist, st["hist"], C.sizeof(st["hist"]))

@@ -357,3 +357,13 @@ def test_perread_tile_abi_vs_oracle(built, synth):
         assert bytes(got) == bytes(exp)
         assert sum(1 for k in range(n) if exp[k].nmeth != 0xffffffff and exp[k].nmeth + exp[k].nunmeth > 0) > 1000
     b.close()
+
+
+@pytest.mark.parametrize("opts", [["--noSVG", "--minConversionEfficiency", "0.97", "--CHH"], ["--noSVG", "--minConversionEfficiency", "0.9", "--CHG", "--nOT", "3,3,3,3"]],
+                         ids=["ce097_chh", "ce09_chg_trim"])
+def test_cli_mbias_conversion_efficiency(built, synth, opts):
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    r = subprocess.run([built["ref_bin"], "mbias"] + opts + [p + ".fa", p + ".bam"], capture_output=True, text=True)
+    n = subprocess.run([NEW_BIN, "mbias"] + opts + [p + ".fa", p + ".bam"], capture_output=True, text=True)
+    assert r.returncode == 0 and n.returncode == 0, (r.stderr, n.stderr)
+    assert n.stdout == r.stdout and len(r.stdout.splitlines()) > 50

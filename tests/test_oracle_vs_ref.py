@@ -211,3 +211,43 @@ def test_perread_indels_clips_long_reads(built, synth, tmp_path):
     p = synth("len75", "--contigs", "chr1:50000", "--depth", "25", "--readlen", "75", "--isize-mean", "160", "--isize-sd", "40", "--isize-min", "75", "--isize-max", "400")
     a, b = _perread_both(built, tmp_path, ["-p", "12", "-q", "0"], p + ".fa", p + ".bam")
     assert a == b and len(a.splitlines()) > 500
+
+
+@pytest.mark.parametrize("opts", [["--noSVG", "--minConversionEfficiency", "0.97", "--CHH"], ["--noSVG", "--minConversionEfficiency", "0.9", "--CHG", "--nOT", "3,3,3,3"]],
+                         ids=["ce097_chh", "ce09_chg_trim"])
+def test_mbias_conversion_efficiency(built, synth, tmp_path, opts):
+    """mbias --minConversionEfficiency: the filter sees the chunk's own window contig[localPos, localEnd] (MBias.c:147,154-156); one
+    chunk per contig keeps every read inside it (see cases.SYNTH_OPTION_SETS)"""
+    import subprocess
+    import sys
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    r = subprocess.run([built["ref_bin"], "mbias"] + opts + [p + ".fa", p + ".bam"], capture_output=True, text=True)
+    r0 = subprocess.run([built["ref_bin"], "mbias", "--noSVG"] + opts[3:] + [p + ".fa", p + ".bam"], capture_output=True, text=True)
+    code = ("import sys; sys.path[:0]=[%r,%r]; import oracle_binding as ob; "
+            "sys.exit(ob.run_host_main('mbias', %r, ob.OracleBackend()))") % (cases.ROOT, os.path.join(cases.ROOT, "tests"), opts + [p + ".fa", p + ".bam"])
+    n = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and n.returncode == 0, (r.stderr, n.stderr)
+    assert n.stdout == r.stdout and len(r.stdout.splitlines()) > 50
+    assert r.stdout != r0.stdout                      # the filter does drop alignments on this data set
+
+
+BED_VARIANTS = {
+    "unsorted_nested": "chr1\t30000\t31000\nchr1\t100\t50000\nchr1\t200\t300\nchr2\t5\t6\nchr1\t100\t200\n",
+    "headers_then_blank_line_ends_file": "browser position chr1\ntrack name=x\n# note\nchr1\t1000\t2000\tn\t0\t-\nchr2\t100\t14000\tm\t0\t+\n\nchr1\t30000\t40000\n",
+    "past_contig_end": "chr1\t59000\t70000\nchr2\t14990\t99999\n",
+    "short_columns_keepstrand": "chr1\t1000\t9000\tname\nchr1\t20000\t29000\tname\t5\nchr2\t0\t15000\tx\t1\t-\textra\n",
+    "adjacent_and_single_base": "chr1\t500\t501\nchr1\t501\t502\nchr1\t502\t600\nchr1\t600\t601\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(BED_VARIANTS))
+@pytest.mark.parametrize("gz", [False, True], ids=["plain", "gzip"])
+def test_bed_file_variants(built, synth, tmp_path, name, gz):
+    """parseBED leniencies (bed.c:91-236): header lines, blank lines, unsorted and nested regions, ends past the contig, missing
+    strand columns under --keepStrand, gzip-compressed input"""
+    import gzip
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    f = str(tmp_path / ("r.bed.gz" if gz else "r.bed"))
+    (gzip.open(f, "wt") if gz else open(f, "w")).write(BED_VARIANTS[name])
+    refp, newp = _both(built, tmp_path, "bv", ["-l", f, "--keepStrand", "--CHH", "--chunkSize", "4000", "--cytosine_report"], p + ".fa", p + ".bam")
+    assert compare_outputs(refp, newp) == []
