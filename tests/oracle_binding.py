@@ -74,6 +74,7 @@ class OracleBackend:
             return 1
 
         def destroy(_b):
+            o.mdo_set_bed(None, 0, 0)          # the port's BED state is global: leave it off for whoever uses the library next
             return None
 
         def load_contig(_b, tid, seq, n):
