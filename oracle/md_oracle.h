@@ -1,5 +1,5 @@
 /* TEST INFRASTRUCTURE — CPU restatement ("port") of the reference's extract / mbias
- * hot path, consuming the same SoA tiles as the CUDA library.  Only tests/,
+ * hot path (plus the -l BED tests and perRead's processRead), consuming the same SoA tiles as the CUDA library.  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline leg may use this; the product
  * (methyldackel_b200/) never links or loads it.
  *

@@ -114,3 +114,16 @@ PERREAD_SETS = [
 ]
 PERREAD_FIXTURES = [("cg100.fa", "cg_aln.bam", ["-q", "2"]), ("chgchh.fa", "chgchh_aln.bam", ["-q", "0", "-p", "1"]), ("ct100.fa", "ct_aln.bam", ["-q", "0"]),
                     ("cg100.fa", "cg_with_variants.bam", ["-q", "0", "-p", "30"]), ("cg100.fa", "NH.bam", ["-q", "0"])]
+
+
+# golden cases on the reference's fixtures for the "next" rows: -l BED (file committed under tests/golden/fixtures) and perRead
+FIXTURE_BED = [
+    ("bed_plain", ["-q", "2", "-l", "@FXBED"], "cg100.fa", "cg_aln.bam"),
+    ("bed_strand_all", ["-q", "2", "-l", "@FXBED", "--keepStrand", "--CHG", "--CHH", "--cytosine_report"], "cg100.fa", "cg_aln.bam"),
+    ("bed_merge_var", ["-p", "1", "-q", "0", "-l", "@FXBED", "--keepStrand", "--mergeContext", "--minOppositeDepth", "1", "--maxVariantFrac", "0.1"], "cg100.fa", "cg_with_variants.bam"),
+]
+FIXTURE_PERREAD = [("pr_" + f[1].split(".")[0], f[2], f[0], f[1]) for f in PERREAD_FIXTURES]
+
+
+def fx_bed(opts):
+    return [fx("cg100.bed") if o == "@FXBED" else o for o in opts]

@@ -36,6 +36,20 @@ def main():
         for f in glob.glob(prefix + "*"):
             txt = open(f).read().replace(prefix, "PREFIX")
             open(f, "w").write(txt)
+    # -l BED and perRead on the fixtures
+    for name, args, fa, bam in cases.FIXTURE_BED:
+        d = os.path.join(out, name)
+        os.makedirs(d)
+        prefix = os.path.join(d, "PREFIX")
+        r = subprocess.run([REF, "extract"] + cases.fx_bed(args) + [cases.fx(fa), cases.fx(bam), "-o", prefix], capture_output=True, text=True, check=True)
+        open(os.path.join(d, "stdout"), "w").write(r.stdout)
+        for f in glob.glob(prefix + "*"):
+            txt = open(f).read().replace(prefix, "PREFIX")
+            open(f, "w").write(txt)
+    for name, args, fa, bam in cases.FIXTURE_PERREAD:
+        d = os.path.join(out, name)
+        os.makedirs(d)
+        subprocess.run([REF, "perRead"] + args + ["-o", os.path.join(d, "perRead.txt"), cases.fx(fa), cases.fx(bam)], capture_output=True, text=True, check=True)
     # mbias on a fixture: --txt table and the suggestion line
     d = os.path.join(out, "mbias_cg")
     os.makedirs(d)

@@ -51,3 +51,41 @@ def test_golden_mbias_gpu(built, tmp_path):
     assert r.stdout == open(os.path.join(EXP, "mbias_cg", "stdout")).read()
     sug = "".join(l + "\n" for l in r.stderr.splitlines() if l.startswith("Suggested inclusion options:"))
     assert sug == open(os.path.join(EXP, "mbias_cg", "suggestion")).read()
+
+
+# ---- -l BED and perRead golden vectors
+@pytest.mark.parametrize("case", cases.FIXTURE_BED, ids=[c[0] for c in cases.FIXTURE_BED])
+def test_golden_bed_cpu(built, tmp_path, case):
+    name, args, fa, bam = case
+    prefix = str(tmp_path / "out")
+    assert ob.run_host_main("extract", cases.fx_bed(args) + [cases.fx(fa), cases.fx(bam), "-o", prefix], ob.OracleBackend()) == 0
+    _check(os.path.join(EXP, name), prefix)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", cases.FIXTURE_BED, ids=[c[0] for c in cases.FIXTURE_BED])
+def test_golden_bed_gpu(built, tmp_path, case):
+    name, args, fa, bam = case
+    prefix = str(tmp_path / "out")
+    r = subprocess.run([NEW_BIN, "extract"] + cases.fx_bed(args) + [cases.fx(fa), cases.fx(bam), "-o", prefix], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == open(os.path.join(EXP, name, "stdout")).read()
+    _check(os.path.join(EXP, name), prefix)
+
+
+@pytest.mark.parametrize("case", cases.FIXTURE_PERREAD, ids=[c[0] for c in cases.FIXTURE_PERREAD])
+def test_golden_perread_cpu(built, tmp_path, case):
+    name, args, fa, bam = case
+    out = str(tmp_path / "pr.txt")
+    assert ob.run_host_main("perRead", list(args) + ["-o", out, cases.fx(fa), cases.fx(bam)], ob.OracleBackend()) == 0
+    assert open(out).read() == open(os.path.join(EXP, name, "perRead.txt")).read()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", cases.FIXTURE_PERREAD, ids=[c[0] for c in cases.FIXTURE_PERREAD])
+def test_golden_perread_gpu(built, tmp_path, case):
+    name, args, fa, bam = case
+    out = str(tmp_path / "pr.txt")
+    r = subprocess.run([NEW_BIN, "perRead"] + list(args) + ["-o", out, cases.fx(fa), cases.fx(bam)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out).read() == open(os.path.join(EXP, name, "perRead.txt")).read()
