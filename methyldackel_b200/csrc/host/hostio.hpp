@@ -47,6 +47,7 @@ public:
         emit(nullptr, 0);  // EOF marker block
         fclose(fp_); fp_ = nullptr;
     }
+    void close_no_eof() { flush_block(); fclose(fp_); fp_ = nullptr; }   // the caller appends more blocks (mdsynth)
 private:
     void emit(const uint8_t *data, size_t n) {
         uint8_t out[65536 + 64];
