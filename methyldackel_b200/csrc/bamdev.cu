@@ -23,17 +23,27 @@
 namespace {
 using mdbam::BlockScan; using mdbam::TileSrc; using mdbam::TileDst; using mdbam::Sz4;
 
-// One warp per BGZF block, INF_WARPS blocks per CTA, decoding tables in shared memory.  Deflate decoding is a serial bit-stream
-// walk; all 32 lanes run it redundantly (see inflate_hd.h:inflate_block) and split the match copies between them.
-constexpr int INF_WARPS = 8;
-__global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const uint8_t *comp, const md_bgzf_block *blk, const unsigned long long *uoff, uint8_t *ubuf, uint32_t n_blocks, int *err) {
-    __shared__ mdinflate::Tables T[INF_WARPS];
-    const uint32_t b = blockIdx.x * INF_WARPS + (threadIdx.x >> 5);
-    if (b >= n_blocks) return;
-    const md_bgzf_block d = blk[b];
-    if (d.isize == 0) return;
-    const int rc = mdinflate::inflate_block(comp, d.comp_off, d.comp_len, ubuf + uoff[b], d.isize, T[threadIdx.x >> 5], (int)(threadIdx.x & 31), 32);
-    if (rc && !(threadIdx.x & 31)) atomicCAS(err, 0, (int)((b << 4) | (uint32_t)(-rc)));
+// One warp per BGZF block at a time, INF_WARPS warps per CTA, three CTAs per SM; every warp owns a mdinflate::Decoder (tables + the
+// ring of its most recent output) in shared memory and pulls block numbers from a global ticket until none are left, so a
+// slow block never holds finished warps hostage.  Deflate decoding is a serial bit-stream walk; all 32 lanes run it
+// redundantly (see inflate_hd.h) and share out the match copies and the flushes of the ring to global memory.
+constexpr int INF_WARPS = 5;
+constexpr size_t INF_SMEM = INF_WARPS * sizeof(mdinflate::Decoder);
+__global__ void __launch_bounds__(INF_WARPS * 32, 3) inflate_kernel(const uint8_t *comp, const md_bgzf_block *blk, const unsigned long long *uoff, uint8_t *ubuf, uint32_t n_blocks, int *err, uint32_t *ticket) {
+    extern __shared__ __align__(16) unsigned char inf_smem[];
+    const int lane = (int)(threadIdx.x & 31);
+    mdinflate::Decoder &D = ((mdinflate::Decoder *) inf_smem)[threadIdx.x >> 5];
+    for (;;) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(ticket, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= n_blocks) break;
+        const md_bgzf_block d = blk[b];
+        if (d.isize == 0) continue;
+        const int rc = mdinflate::inflate_block(comp, d.comp_off, d.comp_len, ubuf + uoff[b], d.isize, D, lane, 32);
+        if (rc && lane == 0) atomicCAS(err, 0, (int)((b << 4) | (uint32_t)(-rc)));
+        __syncwarp();
+    }
 }
 __global__ void scan_blocks_kernel(const uint8_t *u, const unsigned long long *uoff, uint32_t n_blocks, unsigned long long first, unsigned long long U, int32_t n_targets, BlockScan *out) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,6 +126,7 @@ extern "C" md_bam_stream *md_bam_open(md_ctx *c, int32_t n_targets) {
     CKN(cudaSetDevice(c->device));
     md_bam_stream *s = new md_bam_stream();
     s->c = c; s->n_targets = n_targets;
+    cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) INF_SMEM);
     bool ok = cudaStreamCreateWithFlags(&s->sd, cudaStreamNonBlocking) == cudaSuccess && cudaMallocHost((void **) &s->h_tot, 2 * sizeof(Sz4)) == cudaSuccess;
     for (int k = 0; k < 2 && ok; ++k) ok = cudaMallocHost((void **) &s->slot[k].h_small, 64) == cudaSuccess && s->slot[k].small.reserve(256) == 0;
     if (!ok) { g_err = "md_bam_open: allocation failed"; delete s; return nullptr; }
@@ -187,12 +198,13 @@ static int bam_push_impl(md_bam_stream *s, BamSlot &S, const BamSlot *P, const v
     PCK(cudaMemcpyAsync(S.blk.p, blocks, (size_t) n_blocks * sizeof(md_bgzf_block), cudaMemcpyHostToDevice, st));
     PCK(cudaMemcpyAsync(S.uoff.p, uoff.data(), (size_t)(n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
     PCK(cudaMemsetAsync(S.small.p, 0, 256, st));
-    uint32_t *d_small = (uint32_t *) S.small.p;       // [0] n_runs [1] err [2] bad [3] last_pos [4,5] final_exit
+    uint32_t *d_small = (uint32_t *) S.small.p;       // [0] n_runs [1] err [2] bad [3] last_pos [4,5] final_exit [8] inflate ticket
     const uint8_t *u = (const uint8_t *) S.ubuf.p;
     const unsigned long long first = D0 + (carry_in ? 0 : skip);
     tm.tick();
     if (n_blocks) {
-        inflate_kernel<<<(n_blocks + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, 0, st>>>((const uint8_t *) S.comp.p, (const md_bgzf_block *) S.blk.p, (const unsigned long long *) S.uoff.p, (uint8_t *) S.ubuf.p, n_blocks, (int *)(d_small + 1));
+        const uint32_t inf_ctas = std::min<uint32_t>((n_blocks + INF_WARPS - 1) / INF_WARPS, 148u * 3u);
+        inflate_kernel<<<inf_ctas, INF_WARPS * 32, INF_SMEM, st>>>((const uint8_t *) S.comp.p, (const md_bgzf_block *) S.blk.p, (const unsigned long long *) S.uoff.p, (uint8_t *) S.ubuf.p, n_blocks, (int *)(d_small + 1), d_small + 8);
         tm.tick();
         const uint32_t g = (n_blocks + 127) / 128;
         // block 0's slice starts at D0 so that the straddling record is part of its chain

@@ -3,13 +3,21 @@
 // Replaces, on the device, the zlib inflate that runs inside htslib's bgzf_read under sam_itr_next
 // (reference call site common.c:413; BGZF framing per the SAM specification, section 4.1).  A BGZF block is an
 // independent raw-deflate stream of at most 64 KB of output, so blocks decode in parallel: the CUDA kernel gives every
-// warp one block and lets its leader lane run inflate_block() below; the very same function is compiled for the host
-// by tests (checked against zlib on real files), which is what keeps a decoder that cannot be debugged interactively
-// on the GPU honest.
+// warp one block at a time.  The very same function is compiled for the host by tests (lane 0 of 1, checked against zlib
+// on real files), which is what keeps a decoder that cannot be debugged interactively on the GPU honest.
 //
-// Decoding tables (per block decoder, ~3.6 KB; shared memory on the device): a 10-bit primary table for literal/length
-// codes and an 8-bit one for distance codes resolve every code up to that length in one look-up; longer codes (rare by
-// construction: they are the improbable symbols) fall back to the canonical count/offset walk.
+// How a warp decodes (round 2 design; the round-1 decoder copied every match through global memory, one L2 round trip per
+// match, and BAM data is 80 % matches of ~6 bytes):
+//   * The bit-stream walk is serial, so all 32 lanes run it REDUNDANTLY — identical control flow and register state, the warp
+//     never diverges and the walk costs what one lane would cost.  What the lanes share out is the data movement.
+//   * Output goes into a ring of the last WIN bytes in SHARED memory.  A match whose source lies inside the ring (distance
+//     <= WIN - 264: 93 % of the matches of a level-1 BAM, more at higher levels) is a shared-memory load + store by `len`
+//     lanes at once; only the far ones read global memory, from bytes that were flushed long before.
+//   * Every FLUSH bytes the finished part of the ring is written to global memory by all lanes with 16-byte stores.
+//   * Decoding tables hold 32-bit entries with everything a symbol needs (code length, extra-bit count, base value, kind),
+//     so a match costs two table look-ups and no further memory access; codes longer than the primary table (rare by
+//     construction: they are the improbable symbols) fall back to the canonical count/offset walk.
+//   * The tables are built by the warp in parallel: lane l owns the codes of length l + 1.
 #pragma once
 #include <stdint.h>
 
@@ -20,207 +28,304 @@
 #endif
 #if defined(__CUDA_ARCH__)
 #define MD_SYNCWARP() __syncwarp()
+#define MD_ATOMIC_INC(p) atomicAdd((p), 1u)
 #else
 #define MD_SYNCWARP() ((void) 0)
+#define MD_ATOMIC_INC(p) (++*(p))
 #endif
 
 namespace mdinflate {
 
-enum { LIT_ROOT = 10, DIST_ROOT = 8 };
+enum { LIT_ROOT = 10, DIST_ROOT = 8, CL_ROOT = 7, WIN = 8192, WMASK = WIN - 1, FLUSH = 2048, NEAR = WIN - 264 };
 
-struct Tables {
-    uint16_t lit[1 << LIT_ROOT];      // (symbol << 4) | code length, 0 = code longer than LIT_ROOT
-    uint16_t dist[1 << DIST_ROOT];    // same for distance codes
-    uint16_t lit_sorted[288], dist_sorted[32];   // symbols ordered by (length, symbol): canonical walk
-    uint16_t lit_count[16], dist_count[16];
+// entry layout (lit/len and distance tables): bits 0-3 code length (0: not in the primary table), bits 4-7 number of extra
+// bits, bits 8-9 kind (0 literal / distance, 1 length, 2 end of block, 3 invalid symbol), bits 16-31 literal byte or base value
+struct Decoder {                         // one per warp; shared memory on the device (14592 bytes)
+    uint32_t lit[1 << LIT_ROOT];
+    uint32_t dist[1 << DIST_ROOT];       // doubles as the code-length alphabet's table while a dynamic header is read
+    uint16_t lit_sorted[288], dist_sorted[32];   // symbols ordered by (length, symbol): canonical walk for codes beyond the primary table
+    uint32_t lit_limit[16], dist_limit[16];      // per code length l: (first code of length l + number of codes of length l) << (15 - l)
+    int32_t lit_off[16], dist_off[16];           // per code length l: index into sorted[] of its first symbol - its first code
+    uint32_t scratch[16];                // per-length counters while a table is built
+    uint8_t lens[320];                   // code lengths of the block being set up (lit/len at 0, distance at 288)
+    alignas(16) uint8_t win[WIN];        // ring of the most recent output, indexed by (output address & WMASK)
 };
 
 struct BitReader {
-    const uint32_t *words;   // 4-byte aligned base of the buffer the stream lives in (padded by >= 8 readable bytes)
-    uint64_t next;           // index of the next word to go into the bit buffer
-    uint64_t buf; int cnt;   // LSB-first bit buffer
-    uint64_t end_word;       // first word index wholly beyond the stream (reads past it yield zeros)
-    uint32_t pre0, pre1;     // words[next], words[next + 1], loaded ahead of their use: on the device the compressed stream comes
-                             // from L2/HBM, and a load issued only when the buffer runs dry would sit on the decoder's critical path
+    const uint32_t *words;   // 4-byte aligned base of the buffer the stream lives in
+    uint32_t w0, w1;         // the 64-bit window the next bits come from: bit p of w0 is the next one
+    uint32_t pre0, pre1;     // the following words, loaded ahead of their use (the compressed stream comes from L2/HBM)
+    uint32_t p;              // < 32
+    uint32_t idx;            // index of the word in w0 (a pushed segment is far below 16 GB)
+    uint32_t end_word;       // first word index wholly beyond the stream (reads past it yield zeros)
 };
 
-MD_HD uint32_t br_word(const BitReader &b, uint64_t i) { return i < b.end_word ? b.words[i] : 0u; }
-MD_HD void br_init(BitReader &b, const void *base_aligned, uint64_t byte_off, uint64_t byte_len) {
-    b.words = (const uint32_t *) base_aligned;
-    b.next = byte_off >> 2;
-    b.end_word = (byte_off + byte_len + 3) >> 2;
-    b.buf = 0; b.cnt = 0;
-    const int mis = (int)(byte_off & 3);
-    if (byte_len) { b.buf = (uint64_t)(b.words[b.next++] >> (8 * mis)); b.cnt = 32 - 8 * mis; }
-    b.pre0 = br_word(b, b.next); b.pre1 = br_word(b, b.next + 1);
+MD_HD uint32_t br_word(const BitReader &b, uint32_t i) {
+#if defined(__CUDA_ARCH__)
+    return i < b.end_word ? __ldg(b.words + i) : 0u;
+#else
+    return i < b.end_word ? b.words[i] : 0u;
+#endif
 }
-// at least 33 bits available afterwards (zeros once the stream is exhausted)
-MD_HD void br_fill(BitReader &b) {
-    if (b.cnt <= 32) {
-        b.buf |= (uint64_t) b.pre0 << b.cnt; b.cnt += 32;
-        ++b.next;
-        b.pre0 = b.pre1; b.pre1 = br_word(b, b.next + 1);
+MD_HD void br_init(BitReader &b, const void *base_aligned, uint64_t byte_off, uint64_t end_byte) {
+    b.words = (const uint32_t *) base_aligned;
+    b.end_word = (uint32_t)((end_byte + 3) >> 2);
+    b.idx = (uint32_t)(byte_off >> 2); b.p = (uint32_t)(byte_off & 3) * 8u;
+    b.w0 = br_word(b, b.idx); b.w1 = br_word(b, b.idx + 1);
+    b.pre0 = br_word(b, b.idx + 2); b.pre1 = br_word(b, b.idx + 3);
+}
+// the next 32 bits of the stream
+MD_HD uint32_t br_peek(const BitReader &b) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(b.w0, b.w1, b.p);
+#else
+    return (uint32_t)((((uint64_t) b.w1 << 32) | (uint64_t) b.w0) >> b.p);
+#endif
+}
+MD_HD void br_drop(BitReader &b, uint32_t n) {      // n <= 32
+    b.p += n;
+    if (b.p >= 32u) {
+        b.p -= 32u; ++b.idx;
+        b.w0 = b.w1; b.w1 = b.pre0; b.pre0 = b.pre1; b.pre1 = br_word(b, b.idx + 3);
     }
 }
-MD_HD uint32_t br_peek(const BitReader &b, int n) { return (uint32_t)(b.buf & ((1ull << n) - 1ull)); }
-MD_HD void br_drop(BitReader &b, int n) { b.buf >>= n; b.cnt -= n; }
-MD_HD uint32_t br_take(BitReader &b, int n) { uint32_t v = br_peek(b, n); br_drop(b, n); return v; }
-// bytes of the stream consumed so far (for the stored-block path and for diagnostics)
-MD_HD void br_align_byte(BitReader &b) { br_drop(b, b.cnt & 7); }
+MD_HD uint32_t br_take(BitReader &b, uint32_t n) { const uint32_t v = br_peek(b) & ((1u << n) - 1u); br_drop(b, n); return v; }   // n < 32
 
 MD_HD uint32_t bit_reverse(uint32_t v, int n) {
+#if defined(__CUDA_ARCH__)
+    return __brev(v) >> (32 - n);
+#else
     uint32_t r = 0;
     for (int i = 0; i < n; ++i) { r = (r << 1) | (v & 1u); v >>= 1; }
     return r;
+#endif
+}
+
+// table entries from (symbol, code length); base values and extra-bit counts of RFC 1951 3.2.5 in closed form
+MD_HD uint32_t lit_entry(uint32_t sym, uint32_t len) {
+    if (sym < 256u) return (sym << 16) | len;
+    if (sym == 256u) return (2u << 8) | len;
+    if (sym > 285u) return (3u << 8) | len;
+    const uint32_t s = sym - 257u;
+    uint32_t base, xb;
+    if (s < 8u) { base = 3u + s; xb = 0u; }
+    else if (s == 28u) { base = 258u; xb = 0u; }
+    else { xb = (s >> 2) - 1u; base = ((4u + (s & 3u)) << xb) + 3u; }
+    return (base << 16) | (1u << 8) | (xb << 4) | len;
+}
+MD_HD uint32_t dist_entry(uint32_t sym, uint32_t len) {
+    if (sym >= 30u) return (3u << 8) | len;
+    uint32_t base, xb;
+    if (sym < 4u) { base = 1u + sym; xb = 0u; }
+    else { xb = (sym >> 1) - 1u; base = ((2u + (sym & 1u)) << xb) + 1u; }
+    return (base << 16) | (xb << 4) | len;
 }
 
 // Canonical Huffman set from code lengths (RFC 1951 3.2.2).  Returns false for an over-subscribed set.
-// All lanes of a warp run this with the same arguments; only lane 0 stores to the (shared) tables, with a warp barrier
-// between the phases, so no lane reads a table entry another lane is still writing.
-MD_HD bool build_table(const uint8_t *lens, int n, uint16_t *primary, int root, uint16_t *sorted, uint16_t *count, int lane) {
-    uint16_t cnt[16];
-    for (int i = 0; i < 16; ++i) cnt[i] = 0;
-    for (int i = 0; i < n; ++i) cnt[lens[i]]++;
-    cnt[0] = 0;
-    int left = 1;
-    for (int l = 1; l < 16; ++l) { left <<= 1; left -= cnt[l]; if (left < 0) return false; }
-    uint16_t offs[16]; offs[1] = 0;
-    for (int l = 1; l < 15; ++l) offs[l + 1] = (uint16_t)(offs[l] + cnt[l]);
+// kind: 0 lit/len, 1 distance, 2 code-length alphabet.  The warp builds it together: lane l handles the codes of length
+// l + 1 (on the host the single lane loops over the lengths).
+MD_HD bool build_table(Decoder &D, const uint8_t *lens, int n, uint32_t *primary, int root, uint16_t *sorted, uint32_t *limit, int32_t *offv, int kind, int lane, int nl) {
     MD_SYNCWARP();                                       // nobody is still decoding with the previous tables
-    if (lane == 0) {
-        for (int i = 0; i < 16; ++i) count[i] = cnt[i];
-        for (int i = 0; i < n; ++i) if (lens[i]) sorted[offs[lens[i]]++] = (uint16_t) i;
-        if (root) for (int i = 0; i < (1 << root); ++i) primary[i] = 0;
-    }
+    for (int i = lane; i < 16; i += nl) D.scratch[i] = 0;
+    for (int i = lane; i < (1 << root); i += nl) primary[i] = 0;
     MD_SYNCWARP();
-    // assign codes in (length, symbol) order and spread the short ones over the primary table
-    if (root && lane == 0) {
-        uint32_t code = 0; int idx = 0;
-        for (int l = 1; l <= root; ++l) {
-            for (int k = 0; k < cnt[l]; ++k, ++idx, ++code) {
-                const uint32_t rev = bit_reverse(code, l);
-                const uint16_t e = (uint16_t)((sorted[idx] << 4) | l);
-                for (uint32_t x = rev; x < (1u << root); x += (1u << l)) primary[x] = e;
+    for (int i = lane; i < n; i += nl) { const uint32_t l = lens[i]; if (l) MD_ATOMIC_INC(&D.scratch[l]); }
+    MD_SYNCWARP();
+    int left = 1;
+    for (int l = 1; l < 16; ++l) { left <<= 1; left -= (int) D.scratch[l]; if (left < 0) return false; }
+    for (int l = 1 + lane; l < 16; l += nl) {
+        uint32_t off = 0, code = 0;
+        for (int k = 1; k < l; ++k) { const uint32_t c = D.scratch[k]; off += c; code = (code + c) << 1; }
+        const uint32_t c = D.scratch[l];
+        limit[l] = (code + c) << (15 - l);
+        offv[l] = (int32_t) off - (int32_t) code;
+        if (!c) continue;
+        for (int i = 0; i < n; ++i) {
+            if (lens[i] != (uint8_t) l) continue;
+            sorted[off++] = (uint16_t) i;
+            if (l <= root) {
+                const uint32_t e = kind == 0 ? lit_entry((uint32_t) i, (uint32_t) l) : kind == 1 ? dist_entry((uint32_t) i, (uint32_t) l) : (((uint32_t) i << 16) | (uint32_t) l);
+                for (uint32_t x = bit_reverse(code, l); x < (1u << root); x += (1u << l)) primary[x] = e;
             }
-            code <<= 1;
+            ++code;
         }
     }
     MD_SYNCWARP();
     return true;
 }
 
-// canonical walk, one bit at a time (codes longer than the primary table, and the code-length alphabet)
-MD_HD int decode_slow(BitReader &b, const uint16_t *sorted, const uint16_t *count) {
-    int code = 0, first = 0, index = 0;
-    for (int l = 1; l < 16; ++l) {
-        code |= (int) br_take(b, 1);
-        const int c = count[l];
-        if (code - c < first) return sorted[index + (code - first)];
-        index += c; first += c; first <<= 1; code <<= 1;
+// A code longer than the primary table: canonical decode by limits.  With the next 15 bits taken MSB first (x), the code's
+// length is the first l with x < limit[l]; its symbol is sorted[off[l] + (x >> (15 - l))].  Consumes the code's bits.
+MD_HD int decode_slow(BitReader &b, const uint16_t *sorted, const uint32_t *limit, const int32_t *offv, int root) {
+    const uint32_t x = bit_reverse(br_peek(b) & 0x7fffu, 15);
+#if defined(__CUDA_ARCH__)
+    #pragma unroll 1
+#endif
+    for (int l = root + 1; l < 16; ++l) {
+        if (x < limit[l]) { br_drop(b, (uint32_t) l); return sorted[offv[l] + (int32_t)(x >> (15 - l))]; }
     }
     return -1;
 }
 
-MD_HD int decode_sym(BitReader &b, const uint16_t *primary, int root, const uint16_t *sorted, const uint16_t *count) {
-    const uint16_t e = primary[br_peek(b, root)];
-    if (e) { br_drop(b, e & 15); return e >> 4; }
-    return decode_slow(b, sorted, count);
+// ring -> global: bytes [lo, hi) of the output (addresses relative to the 16-byte aligned `outb`)
+MD_HD void flush_ring(const Decoder &D, uint8_t *outb, uint32_t lo, uint32_t hi, int lane, int nl) {
+    MD_SYNCWARP();                                       // everything below `hi` has been stored
+    const uint32_t lo16 = (lo + 15u) & ~15u, hi16 = hi & ~15u;
+    if (lo16 >= hi16) { for (uint32_t x = lo + (uint32_t) lane; x < hi; x += (uint32_t) nl) outb[x] = D.win[x & WMASK]; }
+    else {
+        for (uint32_t x = lo + (uint32_t) lane; x < lo16; x += (uint32_t) nl) outb[x] = D.win[x & WMASK];
+        for (uint32_t x = lo16 + 16u * (uint32_t) lane; x < hi16; x += 16u * (uint32_t) nl) {
+#if defined(__CUDA_ARCH__)
+            *(uint4 *)(outb + x) = *(const uint4 *)(D.win + (x & WMASK));
+#else
+            for (int k = 0; k < 16; ++k) outb[x + (uint32_t) k] = D.win[(x + (uint32_t) k) & WMASK];
+#endif
+        }
+        for (uint32_t x = hi16 + (uint32_t) lane; x < hi; x += (uint32_t) nl) outb[x] = D.win[x & WMASK];
+    }
+    MD_SYNCWARP();                                       // the ring bytes may be overwritten from here on; far matches may read the flushed bytes
 }
 
 // Inflate one raw-deflate stream of `in_len` bytes at base+in_off into out[0..out_len).  The stream must produce exactly
 // out_len bytes.  Returns 0, or a negative code: -1 bad block type / stored length, -2 bad code lengths, -3 bad symbol,
 // -4 output overrun, -5 distance before start, -6 output short.
-//
-// `lane` / `nl`: on the device all 32 lanes of a warp run this function REDUNDANTLY on the same block (identical control
-// flow and register state, so the warp never diverges and the cost is that of one lane); what they share out is the
-// output: lane 0 stores literals, and a match of `len` bytes is copied by all lanes at once (one round of memory latency
-// per 32 bytes instead of one per byte — the byte-serial copy is what bounds a single-lane decoder).  Host: lane 0 of 1.
-MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_len, uint8_t *out, uint32_t out_len, Tables &T, int lane = 0, int nl = 1) {
-    BitReader b; br_init(b, base_aligned, in_off, in_len);
-    uint32_t op = 0;
-    const uint16_t len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-    const uint8_t len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-    const uint16_t dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-    const uint8_t dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+// `lane` / `nl`: on the device all 32 lanes of a warp call this with the same arguments (see the header comment).  Host: lane 0 of 1.
+MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_len, uint8_t *out, uint32_t out_len, Decoder &D, int lane = 0, int nl = 1) {
+    BitReader b; br_init(b, base_aligned, in_off, in_off + in_len);
+    // output addresses are kept relative to the 16-byte aligned address at or below `out`, so that ring index, global
+    // address and the 16-byte flush stores agree in alignment
+    const uint32_t a0 = (uint32_t)((uintptr_t) out & 15u);
+    uint8_t *outb = out - a0;
+    uint32_t op = a0, flushed = a0, next_flush = FLUSH;
+    const uint32_t oend = a0 + out_len;
     const uint8_t cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     for (;;) {
-        br_fill(b);
-        const uint32_t last = br_take(b, 1), type = br_take(b, 2);
+        const uint32_t hdr = br_peek(b);
+        const uint32_t last = hdr & 1u, type = (hdr >> 1) & 3u;
+        br_drop(b, 3);
         if (type == 0) {
-            br_align_byte(b); br_fill(b);
-            const uint32_t len = br_take(b, 16); br_fill(b);
-            const uint32_t nlen = br_take(b, 16);
-            if ((len ^ 0xffffu) != nlen) return -1;
-            if (op + len > out_len) return -4;
-            for (uint32_t i = 0; i < len; ++i) { br_fill(b); const uint8_t v = (uint8_t) br_take(b, 8); if (lane == 0) out[op] = v; ++op; }
+            br_drop(b, (8u - (b.p & 7u)) & 7u);
+            const uint32_t ln = br_peek(b);
+            br_drop(b, 32);
+            const uint32_t len = ln & 0xffffu;
+            if ((len ^ 0xffffu) != (ln >> 16)) return -1;
+            if (op + len > oend) return -4;
+            uint64_t bp = (uint64_t) b.idx * 4u + (b.p >> 3);               // byte position of the stored data in the buffer
+            const uint8_t *src = (const uint8_t *) b.words;
+            uint32_t rem = len;
+            while (rem) {
+                const uint32_t nmax = next_flush - op, c = rem < nmax ? rem : nmax;
+                for (uint32_t k = (uint32_t) lane; k < c; k += (uint32_t) nl) D.win[(op + k) & WMASK] = src[bp + k];
+                op += c; bp += c; rem -= c;
+                if (op >= next_flush) { flush_ring(D, outb, flushed, next_flush, lane, nl); flushed = next_flush; next_flush += FLUSH; }
+            }
+            br_init(b, base_aligned, bp, in_off + in_len);
         } else if (type == 1 || type == 2) {
-            uint8_t lens[320];
             int nlit, ndist;
+            MD_SYNCWARP();
             if (type == 1) {
                 nlit = 288; ndist = 30;
-                for (int i = 0; i < 144; ++i) lens[i] = 8;
-                for (int i = 144; i < 256; ++i) lens[i] = 9;
-                for (int i = 256; i < 280; ++i) lens[i] = 7;
-                for (int i = 280; i < 288; ++i) lens[i] = 8;
-                for (int i = 0; i < 30; ++i) lens[288 + i] = 5;
+                for (int i = lane; i < 320; i += nl) D.lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
             } else {
-                nlit = (int) br_take(b, 5) + 257; ndist = (int) br_take(b, 5) + 1;
-                const int ncl = (int) br_take(b, 4) + 4;
+                const uint32_t h = br_peek(b);
+                nlit = (int)(h & 31u) + 257; ndist = (int)((h >> 5) & 31u) + 1;
+                const int ncl = (int)((h >> 10) & 15u) + 4;
+                br_drop(b, 14);
                 if (nlit > 286 || ndist > 30) return -2;
-                uint8_t cl[19];
-                for (int i = 0; i < 19; ++i) cl[i] = 0;
-                for (int i = 0; i < ncl; ++i) { br_fill(b); cl[cl_order[i]] = (uint8_t) br_take(b, 3); }
-                // the code-length alphabet is decoded with the canonical walk only (19 symbols, <= 7 bits; root 0 = no primary
-                // table); T.dist_sorted / T.dist_count serve as its scratch until the real distance set is built
-                if (!build_table(cl, 19, T.dist, 0, T.dist_sorted, T.dist_count, lane)) return -2;
-                int i = 0;
+                // the code-length alphabet (19 symbols, <= 7 bits) borrows the distance table and its canonical-walk arrays
+                uint8_t *cl = D.lens + 288;
+                for (int i = lane; i < 19; i += nl) cl[i] = 0;
+                MD_SYNCWARP();
+                for (int i = 0; i < ncl; ++i) { const uint32_t v = br_take(b, 3); if (lane == 0) cl[cl_order[i]] = (uint8_t) v; }
+                MD_SYNCWARP();
+                if (!build_table(D, cl, 19, D.dist, CL_ROOT, D.dist_sorted, D.dist_limit, D.dist_off, 2, lane, nl)) return -2;
+                int i = 0; uint32_t prev = 0;
                 while (i < nlit + ndist) {
-                    br_fill(b);
-                    const int sym = decode_slow(b, T.dist_sorted, T.dist_count);
-                    if (sym < 0) return -2;
-                    if (sym < 16) lens[i++] = (uint8_t) sym;
+                    const uint32_t e = D.dist[br_peek(b) & ((1u << CL_ROOT) - 1u)];
+                    if (!(e & 15u)) return -2;                   // code-length codes are at most 7 bits: all of them are in the table
+                    br_drop(b, e & 15u);
+                    const uint32_t sym = e >> 16;
+                    if (sym < 16u) { if (lane == 0) D.lens[i] = (uint8_t) sym; prev = sym; ++i; }
                     else {
-                        int rep; uint8_t v = 0;
-                        br_fill(b);
-                        if (sym == 16) { if (i == 0) return -2; v = lens[i - 1]; rep = 3 + (int) br_take(b, 2); }
-                        else if (sym == 17) rep = 3 + (int) br_take(b, 3);
+                        int rep; uint32_t v = 0;
+                        if (sym == 16u) { if (i == 0) return -2; v = prev; rep = 3 + (int) br_take(b, 2); }
+                        else if (sym == 17u) rep = 3 + (int) br_take(b, 3);
                         else rep = 11 + (int) br_take(b, 7);
                         if (i + rep > nlit + ndist) return -2;
-                        while (rep--) lens[i++] = v;
+                        for (int k = lane; k < rep; k += nl) D.lens[i + k] = (uint8_t) v;
+                        i += rep; prev = v;
                     }
                 }
-                if (lens[256] == 0) return -2;
+                MD_SYNCWARP();
+                if (D.lens[256] == 0) return -2;
                 // distance lengths follow the literal/length ones; move them to a fixed offset
-                for (int k = ndist - 1; k >= 0; --k) lens[288 + k] = lens[nlit + k];
+                uint8_t dl = 0;
+                if (nl == 1) { for (int k = ndist - 1; k >= 0; --k) D.lens[288 + k] = D.lens[nlit + k]; }
+                else { if (lane < ndist) dl = D.lens[nlit + lane]; MD_SYNCWARP(); if (lane < ndist) D.lens[288 + lane] = dl; }
+                MD_SYNCWARP();
             }
-            if (!build_table(lens, nlit, T.lit, LIT_ROOT, T.lit_sorted, T.lit_count, lane)) return -2;
-            if (!build_table(lens + 288, ndist, T.dist, DIST_ROOT, T.dist_sorted, T.dist_count, lane)) return -2;
+            MD_SYNCWARP();
+            if (!build_table(D, D.lens, nlit, D.lit, LIT_ROOT, D.lit_sorted, D.lit_limit, D.lit_off, 0, lane, nl)) return -2;
+            if (!build_table(D, D.lens + 288, ndist, D.dist, DIST_ROOT, D.dist_sorted, D.dist_limit, D.dist_off, 1, lane, nl)) return -2;
             for (;;) {
-                br_fill(b);
-                int sym = decode_sym(b, T.lit, LIT_ROOT, T.lit_sorted, T.lit_count);
-                if (sym < 0) return -3;
-                if (sym < 256) { if (op >= out_len) return -4; if (lane == 0) out[op] = (uint8_t) sym; ++op; continue; }
-                if (sym == 256) break;
-                sym -= 257;
-                if (sym >= 29) return -3;
-                uint32_t len = len_base[sym] + br_take(b, len_extra[sym]);
-                br_fill(b);
-                const int ds = decode_sym(b, T.dist, DIST_ROOT, T.dist_sorted, T.dist_count);
-                if (ds < 0 || ds >= 30) return -3;
-                const uint32_t dist = dist_base[ds] + br_take(b, dist_extra[ds]);
-                if (dist > op) return -5;
-                if (op + len > out_len) return -4;
-                const uint8_t *src = out + op - dist; uint8_t *dst = out + op;
-                MD_SYNCWARP();                                   // the bytes being copied were stored by other lanes
-                if (dist >= len) { for (uint32_t k = (uint32_t) lane; k < len; k += (uint32_t) nl) dst[k] = src[k]; }
-                else if (nl == 1) { for (uint32_t k = 0; k < len; ++k) dst[k] = src[k]; }
-                else { for (uint32_t k = (uint32_t) lane; k < len; k += (uint32_t) nl) dst[k] = src[k % dist]; }   // overlapping match = the last `dist` bytes repeated
-                op += len;
+                uint32_t bits = br_peek(b);
+                uint32_t e = D.lit[bits & ((1u << LIT_ROOT) - 1u)];
+                if (!(e & 15u)) {                                 // a code longer than the primary table
+                    const int sym = decode_slow(b, D.lit_sorted, D.lit_limit, D.lit_off, LIT_ROOT);
+                    if (sym < 0) return -3;
+                    e = lit_entry((uint32_t) sym, 0u);
+                    bits = br_peek(b);
+                }
+                const uint32_t cl = e & 15u;
+                if (e & 0x100u) {                                 // length symbol: a match (kind 1; kind 3 is tested below)
+                    if (e & 0x200u) return -3;
+                    const uint32_t xb = (e >> 4) & 15u;
+                    const uint32_t len = (e >> 16) + ((bits >> cl) & ((1u << xb) - 1u));
+                    br_drop(b, cl + xb);
+                    bits = br_peek(b);
+                    uint32_t d = D.dist[bits & ((1u << DIST_ROOT) - 1u)];
+                    if (!(d & 15u)) {
+                        const int ds = decode_slow(b, D.dist_sorted, D.dist_limit, D.dist_off, DIST_ROOT);
+                        if (ds < 0) return -3;
+                        d = dist_entry((uint32_t) ds, 0u);
+                        bits = br_peek(b);
+                    }
+                    if (d & 0x300u) return -3;
+                    const uint32_t dcl = d & 15u, dxb = (d >> 4) & 15u;
+                    const uint32_t dist = (d >> 16) + ((bits >> dcl) & ((1u << dxb) - 1u));
+                    br_drop(b, dcl + dxb);
+                    if (dist > op - a0) return -5;
+                    if (op + len > oend) return -4;
+                    MD_SYNCWARP();                               // the bytes being copied were stored by other lanes
+                    const uint32_t s0 = op - dist;
+                    if (dist <= (uint32_t) NEAR) {               // source inside the ring
+                        if (dist >= len) { for (uint32_t k = (uint32_t) lane; k < len; k += (uint32_t) nl) D.win[(op + k) & WMASK] = D.win[(s0 + k) & WMASK]; }
+                        else if (nl == 1) { for (uint32_t k = 0; k < len; ++k) D.win[(op + k) & WMASK] = D.win[(s0 + k) & WMASK]; }
+                        else { for (uint32_t k = (uint32_t) lane; k < len; k += (uint32_t) nl) D.win[(op + k) & WMASK] = D.win[(s0 + k % dist) & WMASK]; }   // overlapping match = the last `dist` bytes repeated
+                    } else {                                     // far match: those bytes left the ring, but were flushed long ago (dist - len >= FLUSH)
+                        for (uint32_t k = (uint32_t) lane; k < len; k += (uint32_t) nl) {
+#if defined(__CUDA_ARCH__)
+                            D.win[(op + k) & WMASK] = __ldcg(outb + s0 + k);
+#else
+                            D.win[(op + k) & WMASK] = outb[s0 + k];
+#endif
+                        }
+                    }
+                    op += len;
+                } else if (!(e & 0x200u)) {                       // literal
+                    br_drop(b, cl);
+                    if (op >= oend) return -4;
+                    if (lane == 0) D.win[op & WMASK] = (uint8_t)(e >> 16);
+                    ++op;
+                } else { br_drop(b, cl); break; }                 // end of block
+                if (op >= next_flush) { flush_ring(D, outb, flushed, next_flush, lane, nl); flushed = next_flush; next_flush += FLUSH; }
             }
         } else return -1;
         if (last) break;
     }
-    return op == out_len ? 0 : -6;
+    if (op != oend) return -6;
+    if (op > flushed) flush_ring(D, outb, flushed, op, lane, nl);
+    return 0;
 }
 
 }  // namespace mdinflate

@@ -54,7 +54,7 @@ static int push_impl(Emu *e, Seg *s, const Seg *P, const void *comp, uint64_t co
     if (carry_in) memcpy(s->ubuf.data() + D0, P->ubuf.data() + P->leftover_from, carry_in);
     // 4-byte aligned, padded copy of the compressed bytes (the device buffer is)
     std::vector<uint32_t> cal((comp_bytes + 64 + 3) / 4, 0); memcpy(cal.data(), comp, comp_bytes);
-    mdinflate::Tables T;
+    static thread_local mdinflate::Decoder T;
     for (uint32_t b = 0; b < n_blocks; ++b) {
         if (!blocks[b].isize) continue;
         int rc = mdinflate::inflate_block(cal.data(), blocks[b].comp_off, blocks[b].comp_len, s->ubuf.data() + uoff[b], blocks[b].isize, T);
@@ -159,3 +159,11 @@ extern "C" int emu_bam_mbias_run(void *sv, int run, const md_tile_desc *t, uint3
 }
 // the tile built last (for tests that compare it with the host decoder's)
 extern "C" int emu_bam_tile_view(void *sv, md_reads_soa *out) { Emu *s = (Emu *) sv; if (!s->tile[s->cur].valid) return -1; *out = view_of(s->tile[s->cur]); return 0; }
+
+// the deflate decoder on its own (tests/test_inflate_vs_zlib.py): raw-deflate stream -> out[out_off .. out_off + out_len)
+extern "C" int emu_inflate_raw(const uint8_t *comp, uint64_t comp_len, uint64_t in_off, uint8_t *out, uint32_t out_off, uint32_t out_len) {
+    std::vector<uint32_t> cal((in_off + comp_len + 64 + 3) / 4, 0);
+    memcpy((uint8_t *) cal.data() + in_off, comp, comp_len);
+    static thread_local mdinflate::Decoder T;
+    return mdinflate::inflate_block(cal.data(), in_off, comp_len, out + out_off, out_len, T);
+}
