@@ -259,56 +259,91 @@ def _output_names(argv):
     return out
 
 
+def _default_group():
+    import torch
+    import torch.distributed as dist
+
+    def allreduce_sum(x):
+        t = torch.tensor([x], dtype=torch.int64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(t)
+        return int(t.item())
+    return dist.barrier, allreduce_sum
+
+
 def extract_sharded(argv, rank, world, run_main=None, barrier=None, allreduce_sum=None):
     """`MethylDackel extract <argv>` with the genome split over `world` processes (one per GPU).
 
     ``run_main(argv)`` runs the sub-command main in this process (default: the CUDA library on device
     ``rank``); ``barrier()`` and ``allreduce_sum(int)`` come from the launcher's process group (default:
-    torch.distributed).  Returns the exit code."""
+    torch.distributed).  Returns the exit code: this rank's own when it failed, -20 when another rank failed.
+
+    A failed rank must neither hang the others nor leak into the result: every rank always reaches both collectives
+    (an exception inside run_main counts as a failure), and rank 0 only concatenates the shard files when ALL ranks
+    succeeded and every shard file exists; otherwise the partial shard files and outputs are removed."""
+    import os
     import sys
     if run_main is None:
         run_main = lambda av: extract_main(av, device=rank)[0]  # noqa: E731
     if barrier is None or allreduce_sum is None:
-        import torch
-        import torch.distributed as dist
-
-        def barrier():
-            dist.barrier()
-
-        def allreduce_sum(x):
-            t = torch.tensor([x], dtype=torch.int64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
-            dist.all_reduce(t)
-            return int(t.item())
-    rc = run_main(list(argv) + ["--shardRank", str(rank), "--shardWorld", str(world)])
-    st = A.MdhRunStats()
-    A.load_host().mdh_last_run_stats(C.byref(st))
-    nvar = allreduce_sum(int(st.n_variant_positions))
-    worst = allreduce_sum(1 if rc != 0 else 0)
-    barrier()
+        barrier, allreduce_sum = _default_group()
+    names = []
+    nvar_local = 0
+    try:
+        names = _output_names(argv)
+        rc = run_main(list(argv) + ["--shardRank", str(rank), "--shardWorld", str(world)])
+        st = A.MdhRunStats()
+        A.load_host().mdh_last_run_stats(C.byref(st))
+        nvar_local = int(st.n_variant_positions)
+    except Exception as e:  # noqa: BLE001 - the collectives below must still be reached
+        print("extract_sharded: rank %d failed: %s" % (rank, e), file=sys.stderr)
+        rc = -20
+    nvar = allreduce_sum(nvar_local if rc == 0 else 0)
+    worst = allreduce_sum(1 if rc != 0 else 0)                 # also orders every rank's shard files before rank 0 reads them
+    merged_ok = 1
     if rank == 0:
-        for name in _output_names(argv):
-            with open(name, "wb") as out:
-                for r in range(world):
-                    part = "%s.shard%d" % (name, r)
-                    with open(part, "rb") as f:
-                        while True:
-                            blk = f.read(1 << 24)
-                            if not blk:
-                                break
-                            out.write(blk)
-                    import os
-                    os.unlink(part)
-        if nvar:
-            print("%d positions were excluded due to likely being variants." % nvar)
-            sys.stdout.flush()
-    barrier()
-    return rc if rc != 0 else (-20 if worst else 0)
+        parts = [["%s.shard%d" % (name, r) for r in range(world)] for name in names]
+        try:
+            if worst == 0 and all(os.path.exists(x) for ps in parts for x in ps):
+                for name, ps in zip(names, parts):
+                    with open(name, "wb") as out:
+                        for part in ps:
+                            with open(part, "rb") as f:
+                                while True:
+                                    blk = f.read(1 << 24)
+                                    if not blk:
+                                        break
+                                    out.write(blk)
+                if nvar:
+                    print("%d positions were excluded due to likely being variants." % nvar)
+                    sys.stdout.flush()
+            else:
+                merged_ok = 0
+                if worst == 0:
+                    print("extract_sharded: a shard file is missing; nothing was merged", file=sys.stderr)
+        except OSError as e:
+            merged_ok = 0
+            print("extract_sharded: merging the shards failed: %s" % e, file=sys.stderr)
+        finally:
+            for ps in parts:
+                for part in ps:
+                    if os.path.exists(part):
+                        os.unlink(part)
+            if not merged_ok:
+                for name in names:                             # no normal-looking output from a failed run
+                    if os.path.exists(name):
+                        os.unlink(name)
+    merged_ok = allreduce_sum(merged_ok if rank == 0 else 0)   # doubles as the final barrier; tells every rank the outcome
+    if rc != 0:
+        return rc
+    return 0 if (worst == 0 and merged_ok) else -20
 
 
-def mbias_sharded(argv, rank, world, tmp_prefix, run_main=None, barrier=None):
+def mbias_sharded(argv, rank, world, tmp_prefix, run_main=None, barrier=None, allreduce_sum=None):
     """`MethylDackel mbias <argv>` over `world` processes: every rank histograms its run of chunks, rank 0 sums the
-    (<= 64 KB) histograms on the host (the analogue of mergeStrandMeth, MBias.c:42-55) and prints the report."""
+    (<= 64 KB) histograms on the host (the analogue of mergeStrandMeth, MBias.c:42-55) and prints the report.
+    As in extract_sharded, the report is only produced when every rank succeeded and every histogram file is complete."""
     import os
+    import sys
     import numpy as np
     if run_main is None:
         run_main = lambda av: mbias_main(av, device=rank)[0]  # noqa: E731
@@ -316,19 +351,40 @@ def mbias_sharded(argv, rank, world, tmp_prefix, run_main=None, barrier=None):
         import torch.distributed as dist
         barrier = dist.barrier
     part = "%s.hist%d" % (tmp_prefix, rank)
-    rc = run_main(list(argv) + ["--shardRank", str(rank), "--shardWorld", str(world), "--histOut", part])
+    n = 4 * 2 * A.MD_MBIAS_MAXLEN * 2
+    try:
+        rc = run_main(list(argv) + ["--shardRank", str(rank), "--shardWorld", str(world), "--histOut", part])
+        if rc == 0 and (not os.path.exists(part) or os.path.getsize(part) != 4 * (4 + n)):
+            rc = -3
+    except Exception as e:  # noqa: BLE001
+        print("mbias_sharded: rank %d failed: %s" % (rank, e), file=sys.stderr)
+        rc = -20
+    if allreduce_sum is not None:
+        worst = allreduce_sum(1 if rc != 0 else 0)
+    else:                                                      # no reduction available: a failed rank leaves a marker file next to its histogram
+        if rc != 0:
+            open(part + ".failed", "w").close()
+        barrier()
+        worst = sum(os.path.exists("%s.hist%d.failed" % (tmp_prefix, r)) for r in range(world))
     barrier()
-    if rank == 0 and rc == 0:
-        n = 4 * 2 * A.MD_MBIAS_MAXLEN * 2
-        hist = np.zeros(n, dtype=np.uint32); lens = np.zeros(4, dtype=np.int32)
-        for r in range(world):
-            raw = np.fromfile("%s.hist%d" % (tmp_prefix, r), dtype=np.uint32)
-            lens = np.maximum(lens, raw[:4].view(np.int32))
-            hist += raw[4:4 + n]
-            os.unlink("%s.hist%d" % (tmp_prefix, r))
-        flags = set(argv)
-        svg = 0 if "--noSVG" in flags else 1
-        txt = 1 if ("--txt" in flags or "--noSVG" in flags) else 0
-        A.load_host().mdh_mbias_report(hist.ctypes.data_as(C.POINTER(C.c_uint32)), lens.ctypes.data_as(C.POINTER(C.c_int32)), svg, txt)
+    if rank == 0:
+        try:
+            if worst == 0:
+                hist = np.zeros(n, dtype=np.uint32); lens = np.zeros(4, dtype=np.int32)
+                for r in range(world):
+                    raw = np.fromfile("%s.hist%d" % (tmp_prefix, r), dtype=np.uint32)
+                    lens = np.maximum(lens, raw[:4].view(np.int32))
+                    hist += raw[4:4 + n]
+                flags = set(argv)
+                svg = 0 if "--noSVG" in flags else 1
+                txt = 1 if ("--txt" in flags or "--noSVG" in flags) else 0
+                A.load_host().mdh_mbias_report(hist.ctypes.data_as(C.POINTER(C.c_uint32)), lens.ctypes.data_as(C.POINTER(C.c_int32)), svg, txt)
+        finally:
+            for r in range(world):
+                for x in ("%s.hist%d" % (tmp_prefix, r), "%s.hist%d.failed" % (tmp_prefix, r)):
+                    if os.path.exists(x):
+                        os.unlink(x)
     barrier()
-    return rc
+    if rc != 0:
+        return rc
+    return 0 if worst == 0 else -20

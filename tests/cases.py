@@ -9,8 +9,11 @@ def fx(n):
     return os.path.join(FX, n)
 
 
-# The 15 commands of the reference's tests/test.py (file:line in comments) with the line counts it
-# asserts.  Test 8 asserts 12 upstream; the reference's own code gives 11.
+# The 15 commands of the reference's tests/test.py (file:line in comments) with the line counts it asserts — all 15 exactly
+# as upstream holds them.  Test 8 (12 lines) is not reproduced by the reference's own sources as they lie in /root/reference
+# (11 lines by oracle/_ref, by the oracle port, by the CUDA path and by the independent Python model tests/pymodel.py);
+# DISPUTED records that, tests/test_reference_test8.py holds the derivation, and the upstream number stays in the table as a
+# strict xfail until a real-htslib build says otherwise.
 REFERENCE_TESTS = [
     ("t01", ["-q", "2"], "ct100.fa", "ct_aln.bam", {"_CpG.bedGraph": 1}),                                   # test.py:18
     ("t02", ["-q", "2"], "cg100.fa", "cg_aln.bam", {"_CpG.bedGraph": 49}),                                  # test.py:25 (>1)
@@ -20,7 +23,7 @@ REFERENCE_TESTS = [
     ("t05", ["--minDepth", "2", "-q", "2"], "cg100.fa", "cg_aln.bam", {"_CpG.bedGraph": 1}),                # test.py:60
     ("t06", ["--ignoreFlags", "0xD00", "-q", "2"], "cg100.fa", "cg_aln.bam", {"_CpG.bedGraph": 49}),        # test.py:68
     ("t07", ["--requireFlags", "0xD00", "-q", "2"], "cg100.fa", "cg_aln.bam", {"_CpG.bedGraph": 49}),       # test.py:76
-    ("t08", ["--nOT", "50,50,40,40", "-q", "2"], "cg100.fa", "cg_aln.bam", {"_CpG.bedGraph": 11}),          # test.py:84 (asserts 12)
+    ("t08", ["--nOT", "50,50,40,40", "-q", "2"], "cg100.fa", "cg_aln.bam", {"_CpG.bedGraph": 12}),          # test.py:84-87
     ("t09", ["-p", "1", "-q", "0", "--minOppositeDepth", "3", "--maxVariantFrac", "0.25"], "cg100.fa", "cg_with_variants.bam",
      {"_CpG.bedGraph": 48}),                                                                                  # test.py:92
     ("t10", [], "chgchh.fa", "chgchh_aln.bam", {"_CpG.bedGraph": 2}),                                        # test.py:101
@@ -30,6 +33,14 @@ REFERENCE_TESTS = [
     ("t14", ["-q", "1"], "cg100.fa", "NH.bam", {"_CpG.bedGraph": 1}),                                        # test.py:133
     ("t15", ["--ignoreNH", "-q", "1"], "cg100.fa", "NH.bam", {"_CpG.bedGraph": 49}),                         # test.py:141
 ]
+
+DISPUTED = {"t08": {"_CpG.bedGraph": 11}}
+
+
+def counts_for(case):
+    """line counts every implementation in this repository produces (== upstream's except for DISPUTED)"""
+    return DISPUTED.get(case[0], case[4])
+
 
 FIXTURE_EXTRA = [
     ("x_cyt", ["-q", "2", "--cytosine_report", "--CHG", "--CHH"], "cg100.fa", "cg_aln.bam"),

@@ -20,7 +20,20 @@ dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=ran
 def allsum(x):
     t = torch.tensor([x], dtype=torch.int64); dist.all_reduce(t); return int(t.item())
 mode = sys.argv[1]; argv = sys.argv[2:]
-if mode == "extract":
+fail_rank = int(os.environ.get("MD_TEST_FAIL_RANK", "-1"))
+def maybe_fail(sub):
+    def run(av):
+        if rank == fail_rank:
+            if os.environ.get("MD_TEST_FAIL_HOW") == "raise":
+                raise RuntimeError("injected failure")
+            return -20                                     # failed before any output file was created
+        return ob.run_host_main(sub, av, ob.OracleBackend())
+    return run
+if fail_rank >= 0 and mode == "extract":
+    rc = api.extract_sharded(argv, rank, world, run_main=maybe_fail("extract"), barrier=dist.barrier, allreduce_sum=allsum)
+elif fail_rank >= 0:
+    rc = api.mbias_sharded(argv[1:], rank, world, argv[0], run_main=maybe_fail("mbias"), barrier=dist.barrier, allreduce_sum=allsum if os.environ.get("MD_TEST_ALLSUM") else None)
+elif mode == "extract":
     rc = api.extract_sharded(argv, rank, world, run_main=lambda av: ob.run_host_main("extract", av, ob.OracleBackend()), barrier=dist.barrier, allreduce_sum=allsum)
 else:
     rc = api.mbias_sharded(argv[1:], rank, world, argv[0], run_main=lambda av: ob.run_host_main("mbias", av, ob.OracleBackend()), barrier=dist.barrier)
@@ -29,14 +42,17 @@ sys.exit(rc)
 '''
 
 
-def _launch(mode, argv, port, world=2):
+def _launch(mode, argv, port, world=2, extra_env=None, expect_ok=True):
     code = WORKER % {"root": cases.ROOT, "port": port}
     procs = []
     for r in range(world):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), **(extra_env or {}))
         procs.append(subprocess.Popen([sys.executable, "-c", code, mode] + argv, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
-    outs = [p.communicate(timeout=300) for p in procs]
-    assert all(p.returncode == 0 for p in procs), [o[1][-2000:] for o in outs]
+    outs = [p.communicate(timeout=300) for p in procs]           # a rank left waiting in a collective would hit the timeout
+    if expect_ok:
+        assert all(p.returncode == 0 for p in procs), [o[1][-2000:] for o in outs]
+    else:
+        assert all(p.returncode != 0 for p in procs), [(p.returncode, o[1][-500:]) for p, o in zip(procs, outs)]
     return outs
 
 
@@ -58,3 +74,18 @@ def test_mbias_two_ranks_equals_reference(built, synth, tmp_path):
     r = subprocess.run([built["ref_bin"], "mbias"] + opts + [p + ".fa", p + ".bam"], capture_output=True, text=True)
     outs = _launch("mbias", [str(tmp_path / "mb")] + opts + [p + ".fa", p + ".bam"], 29531)
     assert outs[0][0] == r.stdout and len(r.stdout) > 500
+
+
+def test_a_failed_rank_neither_hangs_nor_leaks_into_the_output(built, synth, tmp_path):
+    """rank 1 fails (by return code, or by raising) before it creates its shard: every rank must come back with a
+    non-zero code, nothing is merged, and no partial shard or output file is left behind."""
+    p = synth("shard", "--contigs", "chr1:70000,chr2:30000,chr3:9000", "--depth", "20")
+    for k, how in enumerate(["rc", "raise"]):
+        newp = str(tmp_path / ("fail%d" % k))
+        _launch("extract", ["--chunkSize", "10000", p + ".fa", p + ".bam", "-o", newp], 29551 + k, extra_env={"MD_TEST_FAIL_RANK": "1", "MD_TEST_FAIL_HOW": how}, expect_ok=False)
+        left = [f for f in os.listdir(str(tmp_path)) if f.startswith("fail%d" % k)]
+        assert left == [], left
+    for k, allsum in enumerate(["", "1"]):
+        outs = _launch("mbias", [str(tmp_path / ("mbf%d" % k)), "--noSVG", p + ".fa", p + ".bam"], 29561 + k, extra_env={"MD_TEST_FAIL_RANK": "1", "MD_TEST_ALLSUM": allsum}, expect_ok=False)
+        assert outs[0][0] == ""                                 # no report from a failed run
+        assert [f for f in os.listdir(str(tmp_path)) if f.startswith("mbf%d" % k)] == []
