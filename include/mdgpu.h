@@ -114,7 +114,8 @@ typedef struct md_tile_stats {
 
 /* mbias histogram layout: hist[((strand*2 + read2)*lmax + qpos)*2 + {0:meth,1:unmeth}],
  * strand 0..3 = OT,OB,CTOT,CTOB (MethylDackel.h:172-176 strandMeth, MBias.c:193-212) */
-#define MD_MBIAS_MAXLEN 1024
+#define MD_MBIAS_MAXLEN 1024   /* the reference grows without bound (MBias.c:16-40); an mbias tile holding a longer read is
+                                  refused with an error (-6) instead of being histogrammed incompletely */
 
 typedef struct md_ctx md_ctx;
 

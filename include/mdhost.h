@@ -3,8 +3,9 @@
  * entry points and the helpers the tests and the benchmark use to decode BAM files into
  * md_reads_soa tiles.
  *
- * extract_main / mbias_main have the signatures the reference exports from libMethylDackel.a
- * (main.c:17-18, extract.c:706, MBias.c:304) and take the same argv.
+ * mdh_extract_main / mdh_mbias_main / mdh_perread_main take the reference's argv (extract.c:706, MBias.c:304,
+ * perRead.c:305) plus the device back end to drive; the entry points with EXACTLY the reference's signatures
+ * (`int extract_main(int, char **)`, main.c:17-20) are in methyldackel.h / lib/libMethylDackel.so, bound to libmdgpu.
  */
 #ifndef MDHOST_H
 #define MDHOST_H
@@ -97,6 +98,9 @@ uint32_t mdh_chunk_bounds(const char *seq, uint32_t len, unsigned long chunk_siz
 
 /* Report stage of mbias on a summed histogram (layout of md_mbias_hist): suggestion line (svg!=0) and/or --txt table. */
 void mdh_mbias_report(const uint32_t *hist, const int32_t lens[4], int svg, int txt);
+/* The same with the M-bias plots (makeSVGs, svg.c:302-437): opref = the SVG prefix (NULL: neither plots nor suggestion line),
+ * which = keepCpG + 2*keepCHG + 4*keepCHH (MBias.c:558).  Returns 0, or -3 when a file could not be written. */
+int mdh_mbias_report_svg(const uint32_t *hist, const int32_t lens[4], const char *opref, int which, int txt);
 
 const char *mdh_last_error(void);
 

@@ -155,6 +155,7 @@ def load_host():
         h.mdh_chunk_bounds.restype = C.c_uint32
         h.mdh_chunk_bounds.argtypes = [C.c_char_p, C.c_uint32, C.c_ulong, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]
         h.mdh_mbias_report.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.c_int, C.c_int]
+        h.mdh_mbias_report_svg.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.c_char_p, C.c_int, C.c_int]
         h.mdh_last_error.restype = C.c_char_p
         _host = h
     return _host

@@ -376,9 +376,23 @@ def mbias_sharded(argv, rank, world, tmp_prefix, run_main=None, barrier=None, al
                     lens = np.maximum(lens, raw[:4].view(np.int32))
                     hist += raw[4:4 + n]
                 flags = set(argv)
-                svg = 0 if "--noSVG" in flags else 1
                 txt = 1 if ("--txt" in flags or "--noSVG" in flags) else 0
-                A.load_host().mdh_mbias_report(hist.ctypes.data_as(C.POINTER(C.c_uint32)), lens.ctypes.data_as(C.POINTER(C.c_int32)), svg, txt)
+                opref = None
+                if "--noSVG" not in flags:                     # the third positional argument is the plot prefix (MBias.c:445-449)
+                    takes = {"-q", "-p", "-r", "-l", "-D", "-F", "-R", "-@", "--nOT", "--nOB", "--nCTOT", "--nCTOB", "--chunkSize", "--minConversionEfficiency",
+                             "--ignoreFlags", "--requireFlags"}
+                    pos, i = [], 0
+                    while i < len(argv):
+                        if argv[i] in takes:
+                            i += 2
+                        elif argv[i].startswith("-"):
+                            i += 1
+                        else:
+                            pos.append(argv[i]); i += 1
+                    opref = pos[2].encode() if len(pos) > 2 else None
+                which = (0 if "--noCpG" in flags else 1) + (2 if "--CHG" in flags else 0) + (4 if "--CHH" in flags else 0)
+                if A.load_host().mdh_mbias_report_svg(hist.ctypes.data_as(C.POINTER(C.c_uint32)), lens.ctypes.data_as(C.POINTER(C.c_int32)), opref, which, txt) != 0:
+                    worst = 1
         finally:
             for r in range(world):
                 for x in ("%s.hist%d" % (tmp_prefix, r), "%s.hist%d.failed" % (tmp_prefix, r)):

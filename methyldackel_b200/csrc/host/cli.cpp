@@ -18,6 +18,7 @@
 #include "pardecode.hpp"
 #include "format.hpp"
 #include "mbias_report.hpp"
+#include "mbias_svg.hpp"
 #include "bed.hpp"
 #include "../../../include/mdhost.h"
 
@@ -1088,9 +1089,8 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
         if (!f || fwrite(lens, sizeof(int32_t), 4, f) != 4 || fwrite(hist.data(), sizeof(uint32_t), hist.size(), f) != hist.size()) rc = -3;
         if (f) fclose(f);
     } else if (rc == 0) {
-        // makeSVGs (svg.c:302-437) is where the reference prints the suggestions; the SVG drawing itself is
-        // host-only plotting outside the accelerated path and is not produced by this build.
-        if (SVG) { (void) opref; mbias_print_suggestions(stderr, hist.data(), lens); }
+        // makeSVGs (svg.c:302-437) draws <prefix>_<strand>.svg and prints the suggestion line; then makeTXT (MBias.c:558-559)
+        if (SVG) mbias_write_svgs(opref, hist.data(), lens, cfg.keepCpG + 2 * cfg.keepCHG + 4 * cfg.keepCHH, stderr);
         if (txt) mbias_print_txt(stdout, hist.data(), lens);
     }
     g_stats.t_total_s = now_s() - t_start;
@@ -1162,4 +1162,12 @@ extern "C" void mdh_mbias_report(const uint32_t *hist, const int32_t lens[4], in
     if (svg) mbias_print_suggestions(stderr, hist, lens);
     if (txt) mbias_print_txt(stdout, hist, lens);
     fflush(stdout); fflush(stderr);
+}
+// The same with the plots: opref = the SVG prefix (NULL: no plots, no suggestion line), which = keepCpG + 2 keepCHG + 4 keepCHH
+extern "C" int mdh_mbias_report_svg(const uint32_t *hist, const int32_t lens[4], const char *opref, int which, int txt) {
+    bool ok = true;
+    if (opref) ok = mbias_write_svgs(opref, hist, lens, which, stderr);
+    if (txt) mbias_print_txt(stdout, hist, lens);
+    fflush(stdout); fflush(stderr);
+    return ok ? 0 : -3;
 }

@@ -139,6 +139,7 @@ static void gen_slab(const Opts &o, size_t tid, const std::string &ref, uint64_t
                 else if (u >= 0.97 && u < 0.99) { indel_len = 1 + (int) r.below(3); ins = r.uni() < 0.5; }
                 else if (u >= 0.99) { if (r.uni() < 0.5) clip5 = 1 + (int) r.below(20); else clip3 = 1 + (int) r.below(20); indel_len = 1 + (int) r.below(3); ins = r.uni() < 0.5; }
                 const int body = L - clip5 - clip3;
+                if (body < 45) indel_len = 0;                       // short reads: no room for an indel away from the ends
                 if (indel_len) indel_at = 10 + (int) r.below((uint32_t)(body - 30));
                 if (clip5) cig.emplace_back(4, clip5);
                 if (indel_len) {

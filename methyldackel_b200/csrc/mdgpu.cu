@@ -1472,6 +1472,12 @@ static int finish_counters(md_ctx *c, Lane *L, md_tile_stats *st) {
         int rc = rerun_count(c, L, true);
         if (rc) return rc;
     }
+    if (L->last_mbias && L->h_counters[C_MAXLQ] > (uint32_t) MD_MBIAS_MAXLEN) {
+        // the reference grows its per-position arrays without bound (MBias.c:16-40); this build's histogram is fixed: refuse
+        // rather than hand back a table that silently lacks the positions beyond it
+        char msg[160]; snprintf(msg, sizeof msg, "mbias: the tile holds a read of %u bases; this build histograms query positions below %d (MD_MBIAS_MAXLEN)", L->h_counters[C_MAXLQ], MD_MBIAS_MAXLEN);
+        g_err = msg; return -6;
+    }
     unsigned long long ncalls; memcpy(&ncalls, &L->h_counters[C_NCALLS], 8);   // C_NCALLS is 8-byte aligned (index 4)
     if (L->h_counters[C_OVERFLOW]) { g_err = L->h_counters[C_OVERFLOW] == 2u ? "internal: staging copy did not complete" : "internal: call buffer overflow"; return -3; }
     L->last_ncalls = ncalls;

@@ -209,6 +209,15 @@ def test_cli_mbias_long_reads(built, synth):
     assert n.stdout == r.stdout and len(r.stdout.splitlines()) > 1000
 
 
+def test_cli_mbias_refuses_reads_longer_than_the_histogram(built, synth):
+    """the reference grows its per-position arrays without bound (MBias.c:16-40); this build's histogram ends at
+    MD_MBIAS_MAXLEN, and a longer read must be an error, not a silently shorter table"""
+    p = synth("len1500", "--contigs", "chr1:120000", "--depth", "8", "--readlen", "1500", "--isize-mean", "2500", "--isize-sd", "200", "--isize-min", "1500", "--isize-max", "4000")
+    for env in ({}, {"MD_DEVICE_DECODE": "0"}):
+        n = subprocess.run([NEW_BIN, "mbias", "--noSVG", p + ".fa", p + ".bam"], capture_output=True, text=True, env=dict(os.environ, **env))
+        assert n.returncode != 0 and "MD_MBIAS_MAXLEN" in n.stderr and n.stdout == "", (n.returncode, n.stderr[-300:])
+
+
 # ---------------------------------------------------------------- phred encodings of the tile (md_reads_soa::qual_bits)
 @pytest.mark.parametrize("nq,env", [(4, {}), (12, {}), (40, {}), (4, {"MD_QUAL_PACK": "0"})], ids=["2bit", "4bit", "8bit_alphabet_too_large", "packing_off"])
 def test_cli_phred_encodings(built, synth, tmp_path, nq, env):

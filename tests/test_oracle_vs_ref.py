@@ -99,6 +99,50 @@ def test_mbias_suggestion_line(built, synth, tmp_path):
     ref_line = [l for l in r.stderr.splitlines() if l.startswith("Suggested inclusion options:")]
     new_line = [l for l in n.stderr.splitlines() if l.startswith("Suggested inclusion options:")]
     assert ref_line and ref_line == new_line
+    _same_svgs(tmp_path, "svgref", "svgnew", expect=["OB", "OT"])
+
+
+def _same_svgs(tmp_path, ref_prefix, new_prefix, expect=None):
+    """the M-bias plots (makeSVGs, svg.c:302-437) byte for byte: same set of <prefix>_<strand>.svg files, same content"""
+    ref_files = sorted(f[len(ref_prefix):] for f in os.listdir(str(tmp_path)) if f.startswith(ref_prefix + "_") and f.endswith(".svg"))
+    new_files = sorted(f[len(new_prefix):] for f in os.listdir(str(tmp_path)) if f.startswith(new_prefix + "_") and f.endswith(".svg"))
+    assert ref_files == new_files and ref_files
+    if expect is not None:
+        assert ref_files == ["_%s.svg" % e for e in expect]
+    for f in ref_files:
+        assert open(str(tmp_path / (ref_prefix + f))).read() == open(str(tmp_path / (new_prefix + f))).read(), f
+
+
+@pytest.mark.parametrize("name,synth_args,opts", [
+    ("nondirectional", ["--contigs", "chrA:40000", "--depth", "40", "--bismark-tags", "--nondirectional", "0.3", "--single-frac", "0.1", "--isize-mean", "200", "--isize-sd", "30", "--read-seed", "99"], ["--CHG", "--CHH"]),
+    ("short_reads", ["--contigs", "chr1:30000", "--depth", "30", "--readlen", "36", "--isize-mean", "120", "--isize-sd", "20", "--isize-min", "40", "--isize-max", "250"], ["--noCpG", "--CHH", "--nOT", "2,2,3,3"]),
+    ("long_reads", ["--contigs", "chr1:60000", "--depth", "20", "--readlen", "251", "--isize-mean", "400", "--isize-sd", "50", "--isize-min", "260", "--isize-max", "700"], ["--CHG"]),
+], ids=["nondirectional_all_four_strands", "short_reads_x5_ticks", "long_reads_x10_ticks"])
+def test_mbias_svgs(built, synth, tmp_path, name, synth_args, opts):
+    import subprocess, sys
+    p = synth("svg_" + name, *synth_args)
+    r = subprocess.run([built["ref_bin"], "mbias"] + opts + [p + ".fa", p + ".bam", str(tmp_path / "svgref")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import oracle_binding as ob; "
+            "sys.exit(ob.run_host_main('mbias', %r, ob.OracleBackend()))") % (cases.ROOT, os.path.join(cases.ROOT, "tests"), opts + [p + ".fa", p + ".bam", str(tmp_path / "svgnew")])
+    n = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert n.returncode == 0, n.stderr
+    assert n.stdout == r.stdout
+    assert [l for l in n.stderr.splitlines() if l.startswith("Suggested")] == [l for l in r.stderr.splitlines() if l.startswith("Suggested")]
+    _same_svgs(tmp_path, "svgref", "svgnew")
+
+
+def test_mbias_svg_fixture(built, tmp_path):
+    """the reference's own fixture (4 records): the plot of a strand with a single read pair"""
+    import subprocess, sys
+    args = ["-q", "2", cases.fx("cg100.fa"), cases.fx("cg_aln.bam")]
+    r = subprocess.run([built["ref_bin"], "mbias"] + args + [str(tmp_path / "svgref")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import oracle_binding as ob; "
+            "sys.exit(ob.run_host_main('mbias', %r, ob.OracleBackend()))") % (cases.ROOT, os.path.join(cases.ROOT, "tests"), args + [str(tmp_path / "svgnew")])
+    n = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert n.returncode == 0, n.stderr
+    _same_svgs(tmp_path, "svgref", "svgnew")
 
 
 def test_parallel_decode_many_small_jobs(built, synth, tmp_path):
