@@ -188,6 +188,17 @@ int md_fetch_calls(md_ctx *ctx, md_call *calls, uint64_t capacity, uint64_t *n_c
 /* CUDA-event timing of the last tile on this context, in milliseconds:
  * out[0]=h2d, out[1]=prep+pair kernels, out[2]=count kernel, out[3]=d2h, out[4]=total. */
 int md_last_timing(md_ctx *ctx, float out[5]);
+/* Device time (CUDA events) and work totals of a context over all the tiles it ran: what a caller that only sees the
+ * sub-command mains (extract_main ...) needs to tell kernel time from end-to-end time.  md_last_totals() returns the
+ * totals of the context destroyed last in this process. */
+typedef struct md_totals {
+    double h2d_ms, prep_ms, count_ms, d2h_ms, tile_ms;   /* summed over tiles (tile_ms: first copy to last read-back of each tile) */
+    double inflate_ms, frame_ms, push_h2d_ms;            /* device decode: BGZF inflate kernel, record framing kernels, segment copies */
+    uint64_t tiles, alignments, cigar_ops, calls, launches;
+    uint64_t comp_bytes, inflated_bytes;                 /* device decode: compressed bytes pushed / bytes they inflated to */
+} md_totals;
+int md_ctx_totals(md_ctx *ctx, md_totals *out);
+int md_last_totals(md_totals *out);
 /* Number of kernel launches issued by this context so far (for bench.py gpu_launches). */
 uint64_t md_launch_count(md_ctx *ctx);
 /* CUDA stream handle (cudaStream_t) the kernels are launched on. */

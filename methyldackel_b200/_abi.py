@@ -69,6 +69,14 @@ class MdTileStats(C.Structure):
                 ("n_multi", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class MdTotals(C.Structure):
+    """md_totals (include/mdgpu.h): device time (CUDA events, ms) and work of one context over all its tiles"""
+    _fields_ = [("h2d_ms", C.c_double), ("prep_ms", C.c_double), ("count_ms", C.c_double), ("d2h_ms", C.c_double), ("tile_ms", C.c_double),
+                ("inflate_ms", C.c_double), ("frame_ms", C.c_double), ("push_h2d_ms", C.c_double),
+                ("tiles", C.c_uint64), ("alignments", C.c_uint64), ("cigar_ops", C.c_uint64), ("calls", C.c_uint64), ("launches", C.c_uint64),
+                ("comp_bytes", C.c_uint64), ("inflated_bytes", C.c_uint64)]
+
+
 class MdhRunStats(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("n_tiles", C.c_uint64), ("n_calls", C.c_uint64),
                 ("t_decode_s", C.c_double), ("t_device_s", C.c_double), ("t_format_s", C.c_double), ("t_total_s", C.c_double),
@@ -208,5 +216,27 @@ def load_gpu():
         g.md_bam_tile_fetch.argtypes = [C.c_void_p, C.POINTER(MdReadsSoa), C.POINTER(C.c_int32)]
         g.md_last_error.restype = C.c_char_p
         g.md_abi_version.restype = C.c_int
+        g.md_ctx_totals.argtypes = [C.c_void_p, C.POINTER(MdTotals)]
+        g.md_last_totals.argtypes = [C.POINTER(MdTotals)]
         _gpu = g
     return _gpu
+
+
+_dropin = None
+
+
+def load_dropin():
+    """libMethylDackel.so: extract_main / mbias_main / perRead_main with the reference's signatures, and the native back-end
+    table bound to libmdgpu (include/methyldackel.h).  Needs libmdgpu.so and libmdhost.so beside it."""
+    global _dropin
+    if _dropin is None:
+        load_host(); load_gpu()
+        p = os.path.join(LIBDIR, "libMethylDackel.so")
+        if not os.path.exists(p):
+            raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % p)
+        d = C.CDLL(p, mode=C.RTLD_GLOBAL)
+        d.mdh_gpu_backend.restype = C.POINTER(MdhBackend); d.mdh_gpu_backend.argtypes = [C.c_int]
+        for f in (d.extract_main, d.mbias_main, d.perRead_main):
+            f.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+        _dropin = d
+    return _dropin

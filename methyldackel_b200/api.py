@@ -99,53 +99,25 @@ class GpuContext:
         return int(self.g.md_launch_count(self.h))
 
 
-class _GpuBackend:
-    """mdh_backend bound to libmdgpu — the only binding the product uses."""
-
-    def __init__(self, device=0):
-        g = A.load_gpu()
-        self.g = g
-
-        def create(_u, cfg):
-            return g.md_create(cfg, device)
-
-        def last_error():
-            return g.md_last_error()
-
-        self._keep = [A.CREATE_FN(create), A.DESTROY_FN(lambda b: g.md_destroy(b)),
-                      A.LOAD_CONTIG_FN(lambda b, t, s, n: g.md_load_contig(b, t, s, n)),
-                      A.DROP_CONTIG_FN(lambda b, t: g.md_drop_contig(b, t)),
-                      A.EXTRACT_TILE_FN(lambda b, td, r, c, cap, st: g.md_extract_tile(b, td, r, c, cap, st)),
-                      A.SET_CHUNKS_FN(lambda b, t, bo, n: g.md_set_mbias_chunks(b, t, bo, n)),
-                      A.MBIAS_TILE_FN(lambda b, td, r, st: g.md_mbias_tile(b, td, r, st)),
-                      A.MBIAS_HIST_FN(lambda b, h, l: g.md_mbias_hist(b, h, l)),
-                      A.LAST_ERROR_FN(last_error),
-                      A.SUBMIT_FN(lambda b, td, r: g.md_submit_tile(b, td, r)),
-                      A.COLLECT_FN(lambda b, t, c, cap, st: g.md_collect_tile(b, t, c, cap, st)),
-                      A.PIN_ALLOC_FN(lambda n: g.md_alloc_pinned(n)), A.PIN_FREE_FN(lambda q: g.md_free_pinned(q)),
-                      A.SUBMIT_FN(lambda b, t, r: g.md_submit_mbias_tile(b, t, r)),
-                      A.BAM_OPEN_FN(lambda b, nt: g.md_bam_open(b, nt)), A.BAM_CLOSE_FN(lambda s: g.md_bam_close(s)), A.BAM_CLOSE_FN(lambda s: g.md_bam_reset(s)),
-                      A.BAM_PUSH_FN(lambda s, c, n, bl, nb, sk, o: g.md_bam_push(s, c, n, bl, nb, sk, o)),
-                      A.BAM_RUNS_FN(lambda s, r, cap: g.md_bam_get_runs(s, r, cap)),
-                      A.BAM_EXTRACT_FN(lambda s, run, td, kh, c, cap, st: g.md_bam_extract_run(s, run, td, kh, c, cap, st)),
-                      A.BAM_MBIAS_FN(lambda s, run, td, kh, st: g.md_bam_mbias_run(s, run, td, kh, st)),
-                      A.BAM_PUSH_BEGIN_FN(lambda s, c, n, bl, nb, sk: g.md_bam_push_begin(s, c, n, bl, nb, sk)),
-                      A.BAM_PUSH_END_FN(lambda s, o: g.md_bam_push_end(s, o)),
-                      A.SET_BED_FN(lambda b, t, r, n: g.md_set_bed(b, t, r, n)),
-                      A.PER_READ_FN(lambda b, td, r, ch, out: g.md_per_read_tile(b, td, r, ch, out))]
-        self.be = A.MdhBackend(None, *self._keep)
-
-
 def _run(which, argv, device):
+    """The sub-command main of libmdhost driven by the NATIVE back-end table of libMethylDackel.so (every slot bound to
+    libmdgpu on `device`): no Python on the data path."""
     h = A.load_host()
-    be = _GpuBackend(device)
+    be = A.load_dropin().mdh_gpu_backend(device)
     args = [which.encode()] + [a.encode() if isinstance(a, str) else a for a in argv]
     arr = (C.c_char_p * (len(args) + 1))(*args, None)
     fn = {"extract": h.mdh_extract_main, "mbias": h.mdh_mbias_main, "perRead": h.mdh_perread_main}[which]
-    rc = fn(len(args), arr, C.byref(be.be))
+    rc = fn(len(args), arr, be)
     st = A.MdhRunStats()
     h.mdh_last_run_stats(C.byref(st))
     return rc, st
+
+
+def last_totals():
+    """md_totals of the device context the last sub-command main used (CUDA-event kernel time, tiles, alignments ...)."""
+    t = A.MdTotals()
+    A.load_gpu().md_last_totals(C.byref(t))
+    return t
 
 
 def perread_main(argv, device=0):

@@ -96,7 +96,7 @@ __global__ void tile_gather_kernel(TileSrc S, const Sz4 *sz, const Sz4 *off, Til
 // ---- host side ------------------------------------------------------------------------------------------------------
 static const size_t BAM_HEADROOM = (size_t) 64 << 20;      // room in front of a segment's bytes for the record that straddles in
 
-struct TileArena { DevBuf buf; DevReads view; int32_t *rend = nullptr; uint32_t n = 0; int32_t tid = -1; uint32_t cut = 0; bool valid = false; };
+struct TileArena { DevBuf buf; DevReads view; int32_t *rend = nullptr; uint32_t n = 0, n_cigar = 0; int32_t tid = -1; uint32_t cut = 0; bool valid = false; };
 
 // One pushed segment: its compressed bytes, inflated stream, record table and the per-contig runs.  Two slots alternate so
 // that segment k+1 is copied and decoded (on its own stream, driven by a helper thread) while the tiles of segment k are
@@ -162,7 +162,7 @@ static const uint32_t BAM_MAX_RUNS = 1u << 16;
 // MD_TIMING=1: per-stage device times of the decode (CUDA events on the stream the work is queued on)
 struct BamTimer {
     bool on; cudaStream_t st; cudaEvent_t ev[8]; int n = 0;
-    explicit BamTimer(cudaStream_t s) : on(getenv("MD_TIMING") != nullptr), st(s) { if (on) for (auto &e : ev) cudaEventCreate(&e); }
+    explicit BamTimer(cudaStream_t s, bool always = false) : on(always || getenv("MD_TIMING") != nullptr), st(s) { if (on) for (auto &e : ev) cudaEventCreate(&e); }
     ~BamTimer() { if (on) for (auto &e : ev) cudaEventDestroy(e); }
     void tick() { if (on && n < 8) cudaEventRecord(ev[n++], st); }
     void add(double *acc) { if (!on || n < 2) return; cudaEventSynchronize(ev[n - 1]); for (int k = 0; k + 1 < n; ++k) { float ms = 0; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); acc[k] += ms; } }
@@ -190,7 +190,7 @@ static int bam_push_impl(md_bam_stream *s, BamSlot &S, const BamSlot *P, const v
     if (S.comp.reserve(comp_bytes + 64) || S.blk.reserve((size_t) n_blocks * sizeof(md_bgzf_block) + 16) || S.uoff.reserve((size_t)(n_blocks + 1) * 8) ||
         S.ubuf.reserve(U + 64) || S.scan.reserve((size_t) n_blocks * sizeof(BlockScan) + 16) || S.cnt.reserve((size_t) n_blocks * 4 + 16) || S.base.reserve((size_t) n_blocks * 4 + 16) ||
         S.runs.reserve((size_t) BAM_MAX_RUNS * sizeof(md_bam_run))) { S.err = "md_bam_push: out of device memory"; return -100; }
-    BamTimer tm(st); tm.tick();
+    BamTimer tm(st, true); tm.tick();
     // the straddling record's first bytes go in front of the new data
     if (carry_in) PCK(cudaMemcpyAsync((uint8_t *) S.ubuf.p + D0, (const uint8_t *) P->ubuf.p + P->leftover_from, carry_in, cudaMemcpyDeviceToDevice, st));
     PCK(cudaMemcpyAsync(S.comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, st));
@@ -282,6 +282,11 @@ extern "C" int md_bam_push_end(md_bam_stream *s, md_bam_summary *out) {
     bam_join(s); s->inflight = false;
     BamSlot &S = s->slot[s->target];
     s->c->launches += S.launches;
+    {   // totals for md_ctx_totals (the helper thread has finished: t_push is quiescent)
+        md_totals &T = s->c->tot;
+        T.push_h2d_ms = s->t_push[0]; T.inflate_ms = s->t_push[1]; T.frame_ms = s->t_push[2] + s->t_push[3];
+        T.comp_bytes = s->comp_total; T.inflated_bytes = s->infl_total;
+    }
     if (S.rc) { g_err = S.err.empty() ? "md_bam_push failed" : S.err; return S.rc; }
     s->cur_slot = s->target; s->have_segment = true;
     if (out) *out = S.sum;
@@ -357,7 +362,7 @@ static int bam_build_tile(md_bam_stream *s, int run, const md_tile_desc *t, uint
     v.pos = D.pos; v.flag = D.flag; v.mapq = D.mapq; v.aux = D.aux; v.l_qseq = D.l_qseq; v.cigar_off = D.cigar_off; v.seq_off = D.seq_off; v.qual_off = D.qual_off;
     v.frag_key = D.frag_key; v.cigar = D.cigar; v.seq = D.seq; v.qual = D.qual;
     tm.tick(); tm.add(s->t_tile); s->n_tiles++;
-    N.rend = D.rend; N.n = (uint32_t) n; N.tid = t->tid; N.cut = t->end; N.valid = true;
+    N.rend = D.rend; N.n = (uint32_t) n; N.n_cigar = tot.y; N.tid = t->tid; N.cut = t->end; N.valid = true;
     s->cur ^= 1;
     CK(cudaGetLastError());
     return 0;
@@ -371,6 +376,7 @@ static int bam_run_tile(md_bam_stream *s, int run, const md_tile_desc *t, uint32
     int rc = bam_build_tile(s, run, t, keep_hi);
     if (rc) return rc;
     TileArena &T = s->tile[s->cur];
+    L->last_ncigar = T.n_cigar;
     rc = run_pipeline(c, L, t, T.view, mbias);
     if (rc) return rc;
     rc = finish_counters(c, L, stats);
@@ -378,7 +384,7 @@ static int bam_run_tile(md_bam_stream *s, int run, const md_tile_desc *t, uint32
     if (!mbias) rc = fetch_sorted(c, L, calls, cap, nullptr);
     CK(cudaEventRecord(L->ev[4], L->stream));
     CK(cudaStreamSynchronize(L->stream));
-    collect_timing(L);
+    collect_timing(c, L);
     c->last = L;
     return rc;
 }

@@ -35,7 +35,18 @@
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
-static thread_local std::string g_err;
+// The last error of the calling thread; a thread that has none of its own (the CLI creates the context on a helper thread
+// and reports from the calling one) sees the most recent error of the process.
+#include <mutex>
+static std::mutex g_err_mu; static std::string g_err_any;
+struct ErrSlot {
+    std::string s;
+    ErrSlot &operator=(const std::string &v) { s = v; std::lock_guard<std::mutex> l(g_err_mu); g_err_any = v; return *this; }
+    ErrSlot &operator=(const char *v) { return *this = std::string(v); }
+    bool empty() const { return s.empty(); }
+    const char *c_str() { if (!s.empty()) return s.c_str(); std::lock_guard<std::mutex> l(g_err_mu); s = g_err_any; return s.c_str(); }
+};
+static thread_local ErrSlot g_err;
 static void set_err(const char *what, cudaError_t e) { g_err = std::string(what) + ": " + cudaGetErrorString(e); }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(#call, e_); return -100; } } while (0)
 #define CKN(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(#call, e_); return nullptr; } } while (0)
@@ -1107,7 +1118,7 @@ struct DevBuf {
 };
 
 struct md_dev_reads {
-    DevBuf arena; DevReads view; uint32_t n = 0;
+    DevBuf arena; DevReads view; uint32_t n = 0, n_cigar = 0;
 };
 
 #define MD_NLANES 3
@@ -1121,7 +1132,7 @@ struct Lane {
     float timing[5] = {0, 0, 0, 0, 0};
     uint32_t last_nwin = 0; uint64_t last_ncalls = 0; bool pending = false; md_tile_stats last_stats;
     uint32_t *h_counters = nullptr;      // page-locked
-    md_tile_desc last_tile; DevReads last_reads; bool last_mbias = false;
+    md_tile_desc last_tile; DevReads last_reads; bool last_mbias = false; uint32_t last_ncigar = 0;
 };
 
 struct md_ctx {
@@ -1134,6 +1145,7 @@ struct md_ctx {
     uint32_t split_above = 4096, force_split = 0;   // windows averaging more alignments than this are split across CTAs (MD_SPLIT_ABOVE, MD_FORCE_SPLIT for tests)
     bool bed_mode = false;               // md_set_bed was called: -l semantics for every tile
     uint32_t ablate = 0;                 // MD_ABLATE: timing experiments (results are wrong when set)
+    md_totals tot;                       // device time and work over all tiles (md_ctx_totals)
     int gen = 1;                         // count_warp<MODE, GEN>: 1 = segment-at-a-time candidate generator, 0 = one candidate per lane per ballot (kept for A/B runs, MD_GEN=0)
 };
 
@@ -1157,7 +1169,7 @@ extern "C" md_ctx *md_create(const md_config *cfg, int device) {
     if (device < 0 || device >= ndev) { g_err = "bad device index"; return nullptr; }
     CKN(cudaSetDevice(device));
     md_ctx *c = new md_ctx();
-    c->device = device; c->cfg = *cfg; fill_kparams(cfg, c->kp);
+    c->device = device; c->cfg = *cfg; fill_kparams(cfg, c->kp); memset(&c->tot, 0, sizeof c->tot);
     for (int k = 0; k < MD_NLANES; ++k) {
         Lane *L = &c->lanes[k];
         if (cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; delete c; return nullptr; }
@@ -1182,10 +1194,15 @@ extern "C" md_ctx *md_create(const md_config *cfg, int device) {
     return c;
 }
 
+static md_totals g_last_totals;
+extern "C" int md_ctx_totals(md_ctx *c, md_totals *out) { if (!c || !out) return -2; *out = c->tot; out->launches = c->launches; return 0; }
+extern "C" int md_last_totals(md_totals *out) { if (!out) return -2; *out = g_last_totals; return 0; }
+
 extern "C" void md_destroy(md_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     sync_all(c);
+    g_last_totals = c->tot; g_last_totals.launches = c->launches;
     for (auto &kv : c->contigs) { cudaFree(kv.second.d_seq); if (kv.second.d_bounds) cudaFree(kv.second.d_bounds); if (kv.second.d_bed) cudaFree(kv.second.d_bed); }
     for (int k = 0; k < MD_NLANES; ++k) {
         Lane *L = &c->lanes[k];
@@ -1282,7 +1299,7 @@ static int stage_reads(md_ctx *c, Lane *L, md_dev_reads &d, const md_reads_soa *
     v.l_qseq = (const uint32_t *)(base + off[4]); v.cigar_off = (const uint32_t *)(base + off[5]); v.seq_off = (const uint32_t *)(base + off[6]);
     v.qual_off = (const uint32_t *)(base + off[7]); v.frag_key = (const uint64_t *)(base + off[8]); v.cigar = (const uint32_t *)(base + off[9]);
     v.seq = (const uint32_t *)(base + off[10]); v.qual = (const uint64_t *)(base + off[11]);
-    d.n = (uint32_t) n;
+    d.n = (uint32_t) n; d.n_cigar = r->n_cigar_ops;
     return 0;
 }
 
@@ -1500,10 +1517,13 @@ static int fetch_sorted(md_ctx *c, Lane *L, md_call *out, uint64_t capacity, uin
     return 0;
 }
 
-static void collect_timing(Lane *L) {
+static void collect_timing(md_ctx *c, Lane *L) {
     float t;
     for (int k = 0; k < 4; ++k) { t = 0; if (cudaEventElapsedTime(&t, L->ev[k], L->ev[k + 1]) == cudaSuccess) L->timing[k] = t; else L->timing[k] = 0; }
     t = 0; if (cudaEventElapsedTime(&t, L->ev[0], L->ev[4]) == cudaSuccess) L->timing[4] = t;
+    md_totals &T = c->tot;
+    T.h2d_ms += L->timing[0]; T.prep_ms += L->timing[1]; T.count_ms += L->timing[2]; T.d2h_ms += L->timing[3]; T.tile_ms += L->timing[4];
+    T.tiles += 1; T.alignments += L->last_reads.n; T.cigar_ops += L->last_ncigar; T.calls += L->last_mbias ? 0 : L->last_ncalls;
 }
 
 // Lane selection: round-robin over the lanes that have nothing in flight.
@@ -1523,6 +1543,7 @@ static int submit_common(md_ctx *c, const md_tile_desc *tile, const md_reads_soa
     CK(cudaEventRecord(L->ev[0], L->stream));
     int rc = stage_reads(c, L, L->staged, reads);
     if (rc) return rc;
+    L->last_ncigar = L->staged.n_cigar;
     rc = run_pipeline(c, L, tile, L->staged.view, mbias);
     if (rc) return rc;
     // queue the small read-backs now so that collect only has to wait
@@ -1544,7 +1565,7 @@ extern "C" int md_collect_tile(md_ctx *c, int ticket, md_call *calls, uint64_t c
     if (!L->last_mbias) rc = fetch_sorted(c, L, calls, capacity, nullptr);
     CK(cudaEventRecord(L->ev[4], L->stream));
     CK(cudaStreamSynchronize(L->stream));
-    collect_timing(L);
+    collect_timing(c, L);
     c->last = L;
     return rc;
 }
@@ -1586,12 +1607,13 @@ extern "C" int md_extract_tile_device(md_ctx *c, const md_tile_desc *tile, const
     Lane *L = &c->lanes[0];
     if (L->pending) { g_err = "md_extract_tile_device: lane 0 has a tile in flight"; return -4; }
     CK(cudaEventRecord(L->ev[0], L->stream));
+    L->last_ncigar = reads->n_cigar;
     int rc = run_pipeline(c, L, tile, reads->view, false);
     if (rc) return rc;
     rc = finish_counters(c, L, stats);
     CK(cudaEventRecord(L->ev[4], L->stream));
     CK(cudaStreamSynchronize(L->stream));
-    collect_timing(L);
+    collect_timing(c, L);
     c->last = L;
     return rc;
 }
@@ -1611,12 +1633,13 @@ extern "C" int md_mbias_tile_device(md_ctx *c, const md_tile_desc *tile, const m
     CK(cudaSetDevice(c->device));
     Lane *L = &c->lanes[0];
     CK(cudaEventRecord(L->ev[0], L->stream));
+    L->last_ncigar = reads->n_cigar;
     int rc = run_pipeline(c, L, tile, reads->view, true);
     if (rc) return rc;
     rc = finish_counters(c, L, stats);
     CK(cudaEventRecord(L->ev[4], L->stream));
     CK(cudaStreamSynchronize(L->stream));
-    collect_timing(L);
+    collect_timing(c, L);
     c->last = L;
     return rc;
 }
