@@ -251,6 +251,9 @@ int md_bam_tile_fetch(md_bam_stream *s, md_reads_soa *dst, int32_t *rend);
 
 const char *md_last_error(void);
 int md_abi_version(void);
+/* first 16 hex digits of the SHA-256 over the CUDA sources this library was built from (`make -C methyldackel_b200/csrc srchash`
+ * prints the tree's): lets a profile be tied to the source it maps to */
+const char *md_source_hash(void);
 
 #ifdef __cplusplus
 }

@@ -216,6 +216,7 @@ def load_gpu():
         g.md_bam_tile_fetch.argtypes = [C.c_void_p, C.POINTER(MdReadsSoa), C.POINTER(C.c_int32)]
         g.md_last_error.restype = C.c_char_p
         g.md_abi_version.restype = C.c_int
+        g.md_source_hash.restype = C.c_char_p
         g.md_ctx_totals.argtypes = [C.c_void_p, C.POINTER(MdTotals)]
         g.md_last_totals.argtypes = [C.POINTER(MdTotals)]
         _gpu = g

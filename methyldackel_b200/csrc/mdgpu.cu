@@ -52,6 +52,10 @@ static void set_err(const char *what, cudaError_t e) { g_err = std::string(what)
 #define CKN(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(#call, e_); return nullptr; } } while (0)
 extern "C" const char *md_last_error(void) { return g_err.c_str(); }
 extern "C" int md_abi_version(void) { return MDGPU_ABI_VERSION; }
+#ifndef MD_SRC_HASH
+#define MD_SRC_HASH "unknown"
+#endif
+extern "C" const char *md_source_hash(void) { return MD_SRC_HASH; }
 
 // ------------------------------------------------------------------------------------------------
 // device-side views
