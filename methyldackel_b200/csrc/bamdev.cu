@@ -23,13 +23,14 @@
 namespace {
 using mdbam::BlockScan; using mdbam::TileSrc; using mdbam::TileDst; using mdbam::Sz4;
 
-// One warp per BGZF block at a time, INF_WARPS warps per CTA, three CTAs per SM; every warp owns a mdinflate::Decoder (tables + the
+// One warp per BGZF block at a time, INF_WARPS warps per CTA, INF_CTAS_PER_SM CTAs per SM; every warp owns a mdinflate::Decoder (tables + the
 // ring of its most recent output) in shared memory and pulls block numbers from a global ticket until none are left, so a
 // slow block never holds finished warps hostage.  Deflate decoding is a serial bit-stream walk; all 32 lanes run it
 // redundantly (see inflate_hd.h) and share out the match copies and the flushes of the ring to global memory.
-constexpr int INF_WARPS = 5;
+constexpr int INF_WARPS = 7, INF_CTAS_PER_SM = 4;                 // 28 warps per SM: 7 KB of shared memory each (4 KB ring)
 constexpr size_t INF_SMEM = INF_WARPS * sizeof(mdinflate::Decoder);
-__global__ void __launch_bounds__(INF_WARPS * 32, 3) inflate_kernel(const uint8_t *comp, const md_bgzf_block *blk, const unsigned long long *uoff, uint8_t *ubuf, uint32_t n_blocks, int *err, uint32_t *ticket) {
+static_assert(INF_CTAS_PER_SM * (INF_SMEM + 1024) <= 228 * 1024, "inflate_kernel: decoders do not fit the SM's shared memory");
+__global__ void __launch_bounds__(INF_WARPS * 32, INF_CTAS_PER_SM) inflate_kernel(const uint8_t *comp, const md_bgzf_block *blk, const unsigned long long *uoff, uint8_t *ubuf, uint32_t n_blocks, int *err, uint32_t *ticket) {
     extern __shared__ __align__(16) unsigned char inf_smem[];
     const int lane = (int)(threadIdx.x & 31);
     mdinflate::Decoder &D = ((mdinflate::Decoder *) inf_smem)[threadIdx.x >> 5];
@@ -187,14 +188,14 @@ static int bam_push_impl(md_bam_stream *s, BamSlot &S, const BamSlot *P, const v
     if (carry_in > BAM_HEADROOM) { S.err = "md_bam_push: a record larger than 64 MB straddles two segments"; return -2; }
     const uint64_t D0 = BAM_HEADROOM - carry_in, U = BAM_HEADROOM + tot;
     if (tot + carry_in >= ((uint64_t) 1 << 32) - BAM_HEADROOM) { S.err = "md_bam_push: segment inflates to more than 4 GB"; return -2; }
-    if (S.comp.reserve(comp_bytes + 64) || S.blk.reserve((size_t) n_blocks * sizeof(md_bgzf_block) + 16) || S.uoff.reserve((size_t)(n_blocks + 1) * 8) ||
+    if (S.comp.reserve(comp_bytes + 1024) || S.blk.reserve((size_t) n_blocks * sizeof(md_bgzf_block) + 16) || S.uoff.reserve((size_t)(n_blocks + 1) * 8) ||
         S.ubuf.reserve(U + 64) || S.scan.reserve((size_t) n_blocks * sizeof(BlockScan) + 16) || S.cnt.reserve((size_t) n_blocks * 4 + 16) || S.base.reserve((size_t) n_blocks * 4 + 16) ||
         S.runs.reserve((size_t) BAM_MAX_RUNS * sizeof(md_bam_run))) { S.err = "md_bam_push: out of device memory"; return -100; }
     BamTimer tm(st, true); tm.tick();
     // the straddling record's first bytes go in front of the new data
     if (carry_in) PCK(cudaMemcpyAsync((uint8_t *) S.ubuf.p + D0, (const uint8_t *) P->ubuf.p + P->leftover_from, carry_in, cudaMemcpyDeviceToDevice, st));
     PCK(cudaMemcpyAsync(S.comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, st));
-    PCK(cudaMemsetAsync((uint8_t *) S.comp.p + comp_bytes, 0, 64, st));
+    PCK(cudaMemsetAsync((uint8_t *) S.comp.p + comp_bytes, 0, 1024, st));     // the decoder stages the stream in 256-byte chunks: it reads up to two chunks past a stream's end
     PCK(cudaMemcpyAsync(S.blk.p, blocks, (size_t) n_blocks * sizeof(md_bgzf_block), cudaMemcpyHostToDevice, st));
     PCK(cudaMemcpyAsync(S.uoff.p, uoff.data(), (size_t)(n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
     PCK(cudaMemsetAsync(S.small.p, 0, 256, st));
@@ -203,7 +204,7 @@ static int bam_push_impl(md_bam_stream *s, BamSlot &S, const BamSlot *P, const v
     const unsigned long long first = D0 + (carry_in ? 0 : skip);
     tm.tick();
     if (n_blocks) {
-        const uint32_t inf_ctas = std::min<uint32_t>((n_blocks + INF_WARPS - 1) / INF_WARPS, 148u * 3u);
+        const uint32_t inf_ctas = std::min<uint32_t>((n_blocks + INF_WARPS - 1) / INF_WARPS, 148u * INF_CTAS_PER_SM);
         inflate_kernel<<<inf_ctas, INF_WARPS * 32, INF_SMEM, st>>>((const uint8_t *) S.comp.p, (const md_bgzf_block *) S.blk.p, (const unsigned long long *) S.uoff.p, (uint8_t *) S.ubuf.p, n_blocks, (int *)(d_small + 1), d_small + 8);
         tm.tick();
         const uint32_t g = (n_blocks + 127) / 128;

@@ -296,7 +296,22 @@ int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamNa
     const bool overlapped = be->bam_push_begin && be->bam_push_end;
     std::vector<md_bgzf_block> blk[2]; int cur = 0;
     const uint8_t *base[2] = {nullptr, nullptr}; size_t bytes[2] = {0, 0};
-    bool have_cur = seg.next(target, base[0], bytes[0], blk[0]);
+    // large files go through page-locked staging buffers filled by a background thread (StagedSegments); small ones are
+    // pushed straight from the file mapping (allocating the buffers would cost more than it saves)
+    std::unique_ptr<StagedSegments> staged;
+    {
+        const char *e = getenv("MD_STAGE");
+        const bool want = e ? e[0] != '0' : seg.remaining() >= ((size_t) 512 << 20);
+        if (want && be->pinned_alloc && be->pinned_free) { staged.reset(new StagedSegments(seg, target, be->pinned_alloc, be->pinned_free)); if (!staged->staged()) staged.reset(); }
+    }
+    auto next_segment = [&](int slot) -> bool {
+        if (!staged) return seg.next(target, base[slot], bytes[slot], blk[slot]);
+        StagedSegments::Seg sg;
+        if (!staged->next(sg)) return false;
+        base[slot] = sg.base; bytes[slot] = sg.bytes; blk[slot].swap(sg.blocks);
+        return true;
+    };
+    bool have_cur = next_segment(0);
     bool pushed = false;
     if (have_cur && overlapped) { if (be->bam_push_begin(bs, base[0], bytes[0], blk[0].data(), (uint32_t) blk[0].size(), skip) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; } pushed = true; }
     bool done = false;
@@ -309,7 +324,7 @@ int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamNa
         if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
         // cut the next segment now: whether the file ends here decides how this segment's last run is closed
         const int nxt = cur ^ 1;
-        const bool have_next = seg.next(target, base[nxt], bytes[nxt], blk[nxt]);
+        const bool have_next = next_segment(nxt);
         const bool file_end = !have_next;
         if (have_next && overlapped) { if (be->bam_push_begin(bs, base[nxt], bytes[nxt], blk[nxt].data(), (uint32_t) blk[nxt].size(), 0) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; } pushed = true; }
         g_stats.n_records += sum.n_records;

@@ -333,6 +333,7 @@ public:
     ~BgzfSegmenter() { if (map_) munmap((void *) map_, size_); if (fd_ >= 0) ::close(fd_); }
     void seek(uint64_t file_off) { off_ = (size_t) file_off; }
     bool eof() const { return off_ + 18 > size_; }
+    size_t remaining() const { return off_ < size_ ? size_ - off_ : 0; }
     // next segment of about `target` compressed bytes: pointer + length, block table with payload offsets relative to it
     bool next(size_t target, const uint8_t *&base, size_t &bytes, std::vector<md_bgzf_block> &blocks) {
         blocks.clear();
@@ -356,6 +357,61 @@ public:
     }
 private:
     int fd_ = -1; const uint8_t *map_ = nullptr; size_t size_ = 0, off_ = 0;
+};
+
+// Segments of the compressed file copied into page-locked buffers ahead of the device: a copy from the file mapping is a
+// pageable transfer (staged by the driver at ~11 GB/s and blocking the stream it is queued on), one from page-locked memory
+// runs at PCIe rate and is asynchronous.  A background thread cuts the next segments and copies them in (several threads
+// per segment); the consumer sees them in file order.  A segment's buffer is recycled `depth - 1` calls of next() later,
+// which is what the overlapped device push needs (segment k counted, k+1 being decoded, k+2 staged).
+class StagedSegments {
+public:
+    struct Seg { const uint8_t *base = nullptr; size_t bytes = 0; std::vector<md_bgzf_block> blocks; };
+    StagedSegments(BgzfSegmenter &seg, size_t target, void *(*alloc)(size_t), void (*release)(void *), int depth = 4, int copy_threads = 4)
+        : seg_(seg), target_(target), release_(release), copy_threads_(copy_threads) {
+        cap_ = target + (1u << 17);                       // a segment ends at the first block boundary at or beyond the target
+        for (int k = 0; k < depth; ++k) { void *p = alloc ? alloc(cap_) : nullptr; if (!p) break; buf_.push_back((uint8_t *) p); }
+        if (buf_.size() >= 3) th_ = std::thread([this] { run(); });
+    }
+    ~StagedSegments() {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; } cv_.notify_all();
+        if (th_.joinable()) th_.join();
+        for (uint8_t *p : buf_) if (release_) release_(p);
+    }
+    bool staged() const { return th_.joinable(); }
+    // next segment in file order; false at the end of the file.  The previous results stay valid for depth - 2 more calls.
+    bool next(Seg &out) {
+        std::unique_lock<std::mutex> l(m_);
+        ++taken_; cv_.notify_all();                        // the buffer handed out depth - 1 calls ago may be refilled now
+        cv_.wait(l, [&] { return !q_.empty() || done_; });
+        if (!err_.empty()) throw std::runtime_error(err_);
+        if (q_.empty()) return false;
+        out = std::move(q_.front()); q_.pop_front();
+        return true;
+    }
+private:
+    void run() {
+        try {
+            for (size_t k = 0;; ++k) {
+                { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return stop_ || k + 1 < taken_ + buf_.size(); }); if (stop_) return; }   // at most depth - 1 segments ahead of the consumer's last call
+                Seg s; const uint8_t *src; size_t bytes;
+                if (!seg_.next(target_, src, bytes, s.blocks)) break;
+                if (bytes > cap_) throw std::runtime_error("BGZF segment larger than its staging buffer");
+                uint8_t *dst = buf_[k % buf_.size()];
+                const int nt = bytes > (8u << 20) ? copy_threads_ : 1;
+                std::vector<std::thread> th;
+                for (int t = 1; t < nt; ++t) th.emplace_back([=] { const size_t a = bytes * (size_t) t / nt, b = bytes * (size_t)(t + 1) / nt; memcpy(dst + a, src + a, b - a); });
+                memcpy(dst, src, bytes / (size_t) nt);
+                for (auto &t : th) t.join();
+                s.base = dst; s.bytes = bytes;
+                { std::lock_guard<std::mutex> g(m_); q_.push_back(std::move(s)); } cv_.notify_all();
+            }
+        } catch (std::exception &e) { std::lock_guard<std::mutex> g(m_); err_ = e.what(); }
+        { std::lock_guard<std::mutex> g(m_); done_ = true; } cv_.notify_all();
+    }
+    BgzfSegmenter &seg_; size_t target_, cap_ = 0; void (*release_)(void *); int copy_threads_;
+    std::vector<uint8_t *> buf_; std::thread th_;
+    std::mutex m_; std::condition_variable cv_; std::deque<Seg> q_; size_t taken_ = 0; bool stop_ = false, done_ = false; std::string err_;
 };
 
 // Same contract as Tiler (tiles.hpp), fed by fragments.  The caller's thread only scans positions to decide which runs of

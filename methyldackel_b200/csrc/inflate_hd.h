@@ -36,28 +36,45 @@
 
 namespace mdinflate {
 
-enum { LIT_ROOT = 10, DIST_ROOT = 8, CL_ROOT = 7, WIN = 8192, WMASK = WIN - 1, FLUSH = 2048, NEAR = WIN - 264 };
+#ifndef MD_INFLATE_WIN
+#define MD_INFLATE_WIN 4096
+#endif
+// Sizes are chosen for occupancy: the walk is one long dependency chain (measured: ~7 cycles from one issued instruction of
+// a warp to its next), so throughput grows with the number of resident warps until the schedulers saturate at ~7 warps each.
+// 8-bit / 6-bit primary tables cover 94 % / 97 % of the codes of a BAM stream; a 4 KB ring holds the source of 5 matches in 6.
+enum { LIT_ROOT = 8, DIST_ROOT = 6, CL_ROOT = 7, WIN = MD_INFLATE_WIN, WMASK = WIN - 1, FLUSH = WIN / 4, NEAR = WIN - 264,
+       IN_CHUNK = 64, IN_WORDS = 2 * IN_CHUNK };   // device: the compressed stream is staged through a ring of two 256-byte chunks
 
 // entry layout (lit/len and distance tables): bits 0-3 code length (0: not in the primary table), bits 4-7 number of extra
-// bits, bits 8-9 kind (0 literal / distance, 1 length, 2 end of block, 3 invalid symbol), bits 16-31 literal byte or base value
-struct Decoder {                         // one per warp; shared memory on the device (14592 bytes)
+// bits, bits 8-9 kind (0 literal / distance, 1 length, 2 end of block, 3 invalid symbol: never stored in a primary table, so the
+// hot loop does not test for it), bits 16-31 literal byte or base value
+struct Decoder {                         // one per warp; shared memory on the device (7 KB with a 4 KB ring)
     uint32_t lit[1 << LIT_ROOT];
-    uint32_t dist[1 << DIST_ROOT];       // doubles as the code-length alphabet's table while a dynamic header is read
+    uint32_t dist[1 << CL_ROOT];         // distance table (1 << DIST_ROOT entries used); holds the code-length alphabet's table while a dynamic header is read
     uint16_t lit_sorted[288], dist_sorted[32];   // symbols ordered by (length, symbol): canonical walk for codes beyond the primary table
     uint32_t lit_limit[16], dist_limit[16];      // per code length l: (first code of length l + number of codes of length l) << (15 - l)
     int32_t lit_off[16], dist_off[16];           // per code length l: index into sorted[] of its first symbol - its first code
     uint32_t scratch[16];                // per-length counters while a table is built
     uint8_t lens[320];                   // code lengths of the block being set up (lit/len at 0, distance at 288)
+    alignas(16) uint32_t in[IN_WORDS];   // device only: word i of the compressed buffer sits at in[i % IN_WORDS] while the reader is near it
     alignas(16) uint8_t win[WIN];        // ring of the most recent output, indexed by (output address & WMASK)
 };
 
+// The compressed stream is read 32 bits at a time.  On the device a load issued when the word is needed — or kept in a
+// register queue that is shifted at every refill, which makes each refill wait for the load of the previous one — puts an
+// L2/HBM round trip on the critical path of a walk that is nothing but a dependency chain.  So the warp stages the stream
+// through shared memory: 256-byte chunks copied with cp.async (LDGSTS, no registers involved) one chunk ahead of the reader,
+// and a refill is a shared-memory load of a word that arrived hundreds of symbols earlier.
 struct BitReader {
-    const uint32_t *words;   // 4-byte aligned base of the buffer the stream lives in
+    const uint32_t *words;   // 4-byte aligned base of the buffer the stream lives in (256-byte aligned on the device)
     uint32_t w0, w1;         // the 64-bit window the next bits come from: bit p of w0 is the next one
-    uint32_t pre0, pre1;     // the following words, loaded ahead of their use (the compressed stream comes from L2/HBM)
+    uint32_t pre0;           // the word after w1, fetched one refill ahead of its use
     uint32_t p;              // < 32
     uint32_t idx;            // index of the word in w0 (a pushed segment is far below 16 GB)
     uint32_t end_word;       // first word index wholly beyond the stream (reads past it yield zeros)
+    uint32_t *ring;          // device: Decoder::in
+    uint32_t nci;            // device: next chunk to be copied into the ring
+    int lane;
 };
 
 MD_HD uint32_t br_word(const BitReader &b, uint32_t i) {
@@ -67,12 +84,46 @@ MD_HD uint32_t br_word(const BitReader &b, uint32_t i) {
     return i < b.end_word ? b.words[i] : 0u;
 #endif
 }
-MD_HD void br_init(BitReader &b, const void *base_aligned, uint64_t byte_off, uint64_t end_byte) {
+#if defined(__CUDA_ARCH__)
+// chunk c of the buffer -> its half of the ring (lanes 0-15, 16 bytes each); chunks wholly beyond the stream are zeros
+__device__ __forceinline__ void br_issue_chunk(BitReader &b, uint32_t c) {
+    if (b.lane < 16) {
+        uint32_t *dst = b.ring + (c & 1u) * IN_CHUNK + (uint32_t) b.lane * 4u;
+        const uint32_t w = c * IN_CHUNK + (uint32_t) b.lane * 4u;
+        if (c * IN_CHUNK < b.end_word + IN_CHUNK) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t) __cvta_generic_to_shared(dst)), "l"(b.words + w) : "memory");
+        } else { dst[0] = 0u; dst[1] = 0u; dst[2] = 0u; dst[3] = 0u; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void br_wait_chunks() { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncwarp(); }
+#endif
+MD_HD void br_init(BitReader &b, const void *base_aligned, uint64_t byte_off, uint64_t end_byte, uint32_t *ring, int lane) {
     b.words = (const uint32_t *) base_aligned;
     b.end_word = (uint32_t)((end_byte + 3) >> 2);
     b.idx = (uint32_t)(byte_off >> 2); b.p = (uint32_t)(byte_off & 3) * 8u;
-    b.w0 = br_word(b, b.idx); b.w1 = br_word(b, b.idx + 1);
-    b.pre0 = br_word(b, b.idx + 2); b.pre1 = br_word(b, b.idx + 3);
+    b.w0 = br_word(b, b.idx); b.w1 = br_word(b, b.idx + 1); b.pre0 = br_word(b, b.idx + 2);
+    b.ring = ring; b.lane = lane; b.nci = 0;
+#if defined(__CUDA_ARCH__)
+    const uint32_t c0 = (b.idx + 3u) / IN_CHUNK;         // the chunk the next fetch falls into
+    __syncwarp();                                        // nobody still reads the ring on behalf of an earlier stream
+    br_issue_chunk(b, c0); br_issue_chunk(b, c0 + 1u);
+    b.nci = c0 + 2u;
+    br_wait_chunks();
+#endif
+}
+// word i of the stream for the refill
+MD_HD uint32_t br_fetch(BitReader &b, uint32_t i) {
+#if defined(__CUDA_ARCH__)
+    if ((i & (IN_CHUNK - 1u)) == 0u && i / IN_CHUNK + 1u == b.nci) {
+        // entering chunk i / IN_CHUNK: it was requested a whole chunk ago; the chunk before it is used up, its half takes the next one
+        br_wait_chunks();
+        br_issue_chunk(b, b.nci); ++b.nci;
+    }
+    return b.ring[i & (IN_WORDS - 1u)];
+#else
+    return br_word(b, i);
+#endif
 }
 // the next 32 bits of the stream
 MD_HD uint32_t br_peek(const BitReader &b) {
@@ -86,7 +137,7 @@ MD_HD void br_drop(BitReader &b, uint32_t n) {      // n <= 32
     b.p += n;
     if (b.p >= 32u) {
         b.p -= 32u; ++b.idx;
-        b.w0 = b.w1; b.w1 = b.pre0; b.pre0 = b.pre1; b.pre1 = br_word(b, b.idx + 3);
+        b.w0 = b.w1; b.w1 = b.pre0; b.pre0 = br_fetch(b, b.idx + 2u);
     }
 }
 MD_HD uint32_t br_take(BitReader &b, uint32_t n) { const uint32_t v = br_peek(b) & ((1u << n) - 1u); br_drop(b, n); return v; }   // n < 32
@@ -145,7 +196,8 @@ MD_HD bool build_table(Decoder &D, const uint8_t *lens, int n, uint32_t *primary
             sorted[off++] = (uint16_t) i;
             if (l <= root) {
                 const uint32_t e = kind == 0 ? lit_entry((uint32_t) i, (uint32_t) l) : kind == 1 ? dist_entry((uint32_t) i, (uint32_t) l) : (((uint32_t) i << 16) | (uint32_t) l);
-                for (uint32_t x = bit_reverse(code, l); x < (1u << root); x += (1u << l)) primary[x] = e;
+                if ((e & 0x300u) != 0x300u)              // an invalid symbol is left to the slow path, which reports it
+                    for (uint32_t x = bit_reverse(code, l); x < (1u << root); x += (1u << l)) primary[x] = e;
             }
             ++code;
         }
@@ -170,6 +222,7 @@ MD_HD int decode_slow(BitReader &b, const uint16_t *sorted, const uint32_t *limi
 // ring -> global: bytes [lo, hi) of the output (addresses relative to the 16-byte aligned `outb`)
 MD_HD void flush_ring(const Decoder &D, uint8_t *outb, uint32_t lo, uint32_t hi, int lane, int nl) {
     MD_SYNCWARP();                                       // everything below `hi` has been stored
+    if (hi <= lo) return;
     const uint32_t lo16 = (lo + 15u) & ~15u, hi16 = hi & ~15u;
     if (lo16 >= hi16) { for (uint32_t x = lo + (uint32_t) lane; x < hi; x += (uint32_t) nl) outb[x] = D.win[x & WMASK]; }
     else {
@@ -191,12 +244,13 @@ MD_HD void flush_ring(const Decoder &D, uint8_t *outb, uint32_t lo, uint32_t hi,
 // -4 output overrun, -5 distance before start, -6 output short.
 // `lane` / `nl`: on the device all 32 lanes of a warp call this with the same arguments (see the header comment).  Host: lane 0 of 1.
 MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_len, uint8_t *out, uint32_t out_len, Decoder &D, int lane = 0, int nl = 1) {
-    BitReader b; br_init(b, base_aligned, in_off, in_off + in_len);
+    BitReader b; br_init(b, base_aligned, in_off, in_off + in_len, D.in, lane);
     // output addresses are kept relative to the 16-byte aligned address at or below `out`, so that ring index, global
     // address and the 16-byte flush stores agree in alignment
     const uint32_t a0 = (uint32_t)((uintptr_t) out & 15u);
     uint8_t *outb = out - a0;
     uint32_t op = a0, flushed = a0, next_flush = FLUSH;
+    bool bad = false;
     const uint32_t oend = a0 + out_len;
     const uint8_t cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     for (;;) {
@@ -219,7 +273,7 @@ MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_l
                 op += c; bp += c; rem -= c;
                 if (op >= next_flush) { flush_ring(D, outb, flushed, next_flush, lane, nl); flushed = next_flush; next_flush += FLUSH; }
             }
-            br_init(b, base_aligned, bp, in_off + in_len);
+            br_init(b, base_aligned, bp, in_off + in_len, D.in, lane);
         } else if (type == 1 || type == 2) {
             int nlit, ndist;
             MD_SYNCWARP();
@@ -267,6 +321,9 @@ MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_l
             MD_SYNCWARP();
             if (!build_table(D, D.lens, nlit, D.lit, LIT_ROOT, D.lit_sorted, D.lit_limit, D.lit_off, 0, lane, nl)) return -2;
             if (!build_table(D, D.lens + 288, ndist, D.dist, DIST_ROOT, D.dist_sorted, D.dist_limit, D.dist_off, 1, lane, nl)) return -2;
+            // The hot loop.  Range violations (a distance reaching before the block, output beyond its announced size) only set
+            // `bad`: the ring absorbs the stray bytes, flushes are clamped to the block, and the flag is looked at when the ring is
+            // flushed and at the end — two compares per symbol instead of two branches.
             for (;;) {
                 uint32_t bits = br_peek(b);
                 uint32_t e = D.lit[bits & ((1u << LIT_ROOT) - 1u)];
@@ -274,36 +331,41 @@ MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_l
                     const int sym = decode_slow(b, D.lit_sorted, D.lit_limit, D.lit_off, LIT_ROOT);
                     if (sym < 0) return -3;
                     e = lit_entry((uint32_t) sym, 0u);
+                    if ((e & 0x300u) == 0x300u) return -3;
                     bits = br_peek(b);
                 }
                 const uint32_t cl = e & 15u;
-                if (e & 0x100u) {                                 // length symbol: a match (kind 1; kind 3 is tested below)
-                    if (e & 0x200u) return -3;
+                if (e & 0x100u) {                                 // length symbol: a match
                     const uint32_t xb = (e >> 4) & 15u;
-                    const uint32_t len = (e >> 16) + ((bits >> cl) & ((1u << xb) - 1u));
-                    br_drop(b, cl + xb);
-                    bits = br_peek(b);
-                    uint32_t d = D.dist[bits & ((1u << DIST_ROOT) - 1u)];
+                    const uint32_t len = (e >> 16) + ((bits >> cl) & ~(0xffffffffu << xb));
+                    uint32_t used = cl + xb;                      // <= 20: the distance code's first DIST_ROOT bits are still in `bits`
+                    uint32_t d = D.dist[(bits >> used) & ((1u << DIST_ROOT) - 1u)];
                     if (!(d & 15u)) {
+                        br_drop(b, used); used = 0;
                         const int ds = decode_slow(b, D.dist_sorted, D.dist_limit, D.dist_off, DIST_ROOT);
                         if (ds < 0) return -3;
                         d = dist_entry((uint32_t) ds, 0u);
+                        if (d & 0x300u) return -3;
                         bits = br_peek(b);
                     }
-                    if (d & 0x300u) return -3;
                     const uint32_t dcl = d & 15u, dxb = (d >> 4) & 15u;
-                    const uint32_t dist = (d >> 16) + ((bits >> dcl) & ((1u << dxb) - 1u));
-                    br_drop(b, dcl + dxb);
-                    if (dist > op - a0) return -5;
-                    if (op + len > oend) return -4;
+                    if (used + dcl + dxb > 32u) { br_drop(b, used); used = 0; bits = br_peek(b); }   // rare: long codes with many extra bits (dcl + dxb <= 28)
+                    const uint32_t dist = (d >> 16) + ((bits >> (used + dcl)) & ~(0xffffffffu << dxb));
+                    br_drop(b, used + dcl + dxb);
+                    const bool viol = dist > op - a0 || op + len > oend;
+                    bad |= viol;
                     MD_SYNCWARP();                               // the bytes being copied were stored by other lanes
                     const uint32_t s0 = op - dist;
                     if (dist <= (uint32_t) NEAR) {               // source inside the ring
-                        if (dist >= len) { for (uint32_t k = (uint32_t) lane; k < len; k += (uint32_t) nl) D.win[(op + k) & WMASK] = D.win[(s0 + k) & WMASK]; }
+                        if (dist >= len) {
+                            if (len <= 32u && nl == 32) { if ((uint32_t) lane < len) D.win[(op + (uint32_t) lane) & WMASK] = D.win[(s0 + (uint32_t) lane) & WMASK]; }
+                            else for (uint32_t k = (uint32_t) lane; k < len; k += (uint32_t) nl) D.win[(op + k) & WMASK] = D.win[(s0 + k) & WMASK];
+                        }
                         else if (nl == 1) { for (uint32_t k = 0; k < len; ++k) D.win[(op + k) & WMASK] = D.win[(s0 + k) & WMASK]; }
                         else { for (uint32_t k = (uint32_t) lane; k < len; k += (uint32_t) nl) D.win[(op + k) & WMASK] = D.win[(s0 + k % dist) & WMASK]; }   // overlapping match = the last `dist` bytes repeated
                     } else {                                     // far match: those bytes left the ring, but were flushed long ago (dist - len >= FLUSH)
-                        for (uint32_t k = (uint32_t) lane; k < len; k += (uint32_t) nl) {
+                        const uint32_t lim = viol ? 0u : len;    // never form an address from a distance that reaches before the block
+                        for (uint32_t k = (uint32_t) lane; k < lim; k += (uint32_t) nl) {
 #if defined(__CUDA_ARCH__)
                             D.win[(op + k) & WMASK] = __ldcg(outb + s0 + k);
 #else
@@ -314,12 +376,16 @@ MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_l
                     op += len;
                 } else if (!(e & 0x200u)) {                       // literal
                     br_drop(b, cl);
-                    if (op >= oend) return -4;
+                    bad |= op >= oend;
                     if (lane == 0) D.win[op & WMASK] = (uint8_t)(e >> 16);
                     ++op;
                 } else { br_drop(b, cl); break; }                 // end of block
-                if (op >= next_flush) { flush_ring(D, outb, flushed, next_flush, lane, nl); flushed = next_flush; next_flush += FLUSH; }
+                if (op >= next_flush) {
+                    if (bad) return -4;
+                    flush_ring(D, outb, flushed, next_flush, lane, nl); flushed = next_flush; next_flush += FLUSH;
+                }
             }
+            if (bad) return -4;
         } else return -1;
         if (last) break;
     }
