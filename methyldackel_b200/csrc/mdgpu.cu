@@ -373,9 +373,10 @@ __device__ __forceinline__ void eval_plain(const CountArgs &A, int strand, int r
         if (rv) {
             if (MODE == 2) {
                 const int s1 = strand - 1;
+                // the per-strand length `l` (MBias.c:212: largest query position with a call, plus one) is read off the finished
+                // histogram by md_mbias_hist; a global atomicMax per call here serialised the whole kernel on four addresses
                 if (qi < MB_SM_Q) atomicAdd(cnt + (((s1 * 2 + rd2) * MB_SM_Q + qi) * 2 + (rv < 0 ? 1 : 0)), 1u);
                 else if (qi < MD_MBIAS_MAXLEN) atomicAdd(A.hist + ((((size_t) s1 * 2 + rd2) * MD_MBIAS_MAXLEN + qi) * 2 + (rv < 0 ? 1 : 0)), 1u);
-                if (qi < MD_MBIAS_MAXLEN) atomicMax(A.lens + s1, qi + 1);
             } else if (A.wide) atomicAdd(cnt + (rv > 0 ? o : W + o), 1u);
             else {                                                // meth in the low half, unmeth in the high half of one word
                 const uint32_t old = atomicAdd(cnt + o, rv > 0 ? 1u : 0x10000u);
@@ -1653,8 +1654,16 @@ extern "C" int md_mbias_hist(md_ctx *c, uint32_t *hist, int32_t lens[4]) {
     sync_all(c);
     Lane *L = &c->lanes[0];
     CK(cudaMemcpyAsync(hist, c->d_hist, (size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, L->stream));
-    CK(cudaMemcpyAsync(lens, c->d_lens, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, L->stream));
     CK(cudaStreamSynchronize(L->stream));
+    // strandMeth::l (MBias.c:212): one past the largest query position that received a call, over both reads of the strand
+    for (int s = 0; s < 4; ++s) {
+        int32_t l = 0;
+        for (int rd = 0; rd < 2; ++rd) {
+            const uint32_t *h = hist + ((size_t) s * 2 + rd) * MD_MBIAS_MAXLEN * 2;
+            for (int q = MD_MBIAS_MAXLEN - 1; q >= l; --q) if (h[2 * q] | h[2 * q + 1]) { l = q + 1; break; }
+        }
+        lens[s] = l;
+    }
     return 0;
 }
 
