@@ -158,50 +158,82 @@ namespace {
 // in chunk order (the analogue of the reference's ordered output bins, extract.c:514-535).  post() applies back-pressure.
 class OrderedFormatter {
 public:
+    // fp[k]: the output files (headers already written through them); lines are appended with pwrite on their descriptors
     OrderedFormatter(int nthreads, const ExtractOptions &o, FILE *fp[3]) : o_(o) {
-        fp_[0] = fp[0]; fp_[1] = fp[1]; fp_[2] = fp[2];
+        one_file_ = fp[0] && fp[1] == fp[0];                      // cytosine_report: the contexts interleave in one file
+        for (int k = 0; k < 3; ++k) {
+            fd_[k] = -1; off_[k] = 0;
+            if (fp[k] && !(one_file_ && k)) { fflush(fp[k]); fd_[k] = fileno(fp[k]); off_[k] = (uint64_t) ftello(fp[k]); }
+        }
         for (int i = 0; i < std::max(1, nthreads); ++i) th_.emplace_back([this] { run(); });
     }
     ~OrderedFormatter() { { std::lock_guard<std::mutex> g(m_); stop_ = true; } cv_.notify_all(); for (auto &t : th_) t.join(); }
-    void post(const char *chrom, const std::string *ref, Chunk k, std::shared_ptr<std::vector<md_call>> part) {
+    void post(const char *chrom, std::shared_ptr<const std::string> ref, Chunk k, std::shared_ptr<std::vector<md_call>> part) {
         std::unique_lock<std::mutex> l(m_);
-        cv_.wait(l, [&] { return next_seq_ - next_write_ < 64; });
-        q_.push_back(Job{next_seq_++, chrom, ref, k, std::move(part)}); cv_.notify_all();
+        cv_.wait(l, [&] { return next_seq_ - written_ < 96; });
+        q_.push_back(Job{next_seq_++, chrom, std::move(ref), k, std::move(part)}); cv_.notify_all();
     }
-    void drain() { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return next_write_ == next_seq_; }); }
+    void drain() { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return written_ == next_seq_; }); }
     double busy_seconds() { std::lock_guard<std::mutex> g(m_); return busy_s_; }
     uint64_t n_variant_positions() { std::lock_guard<std::mutex> g(m_); return n_variant_; }
+    bool failed() { std::lock_guard<std::mutex> g(m_); return failed_; }
 private:
-    struct Job { uint64_t seq; const char *chrom; const std::string *ref; Chunk k; std::shared_ptr<std::vector<md_call>> part; };
-    struct Done { char *buf[3] = {nullptr, nullptr, nullptr}; size_t len[3] = {0, 0, 0}; };
+    struct Job { uint64_t seq; const char *chrom; std::shared_ptr<const std::string> ref; Chunk k; std::shared_ptr<std::vector<md_call>> part; };
+    struct Done { std::shared_ptr<TextBuf> buf[3]; uint64_t at[3] = {0, 0, 0}; };
     void run() {
         for (;;) {
             Job j;
             { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return stop_ || !q_.empty(); }); if (q_.empty()) return; j = std::move(q_.front()); q_.pop_front(); }
             const double t0 = now_s();
-            Done d; FILE *m[3] = {nullptr, nullptr, nullptr};
-            const bool one_file = fp_[0] && fp_[1] == fp_[0];                  // cytosine_report: the contexts interleave in one file
-            for (int k = 0; k < 3; ++k) if (fp_[k]) { if (one_file && k) m[k] = m[0]; else m[k] = open_memstream(&d.buf[k], &d.len[k]); }
+            Done d; TextBuf *m[3] = {nullptr, nullptr, nullptr};
+            for (int k = 0; k < 3; ++k) {
+                if (one_file_) { if (k == 0) d.buf[0].reset(new TextBuf()); m[k] = d.buf[0].get(); }
+                else if (fd_[k] >= 0) { d.buf[k].reset(new TextBuf()); m[k] = d.buf[k].get(); }
+            }
             uint64_t nvar;
             { ExtractWriter w(o_, m); w.process_chunk(j.chrom, *j.ref, j.k.beg, j.k.end, j.part->data(), j.part->size()); nvar = w.n_variant_positions(); }
-            for (int k = 0; k < 3; ++k) if (m[k] && !(one_file && k)) fclose(m[k]);
-            j.part.reset();
-            std::lock_guard<std::mutex> g(m_);
-            busy_s_ += now_s() - t0; n_variant_ += nvar;
-            ready_.emplace(j.seq, d);
-            for (auto it = ready_.find(next_write_); it != ready_.end(); it = ready_.find(next_write_)) {
-                for (int k = 0; k < 3; ++k) if (it->second.buf[k]) { if (it->second.len[k]) fwrite(it->second.buf[k], 1, it->second.len[k], fp_[k]); free(it->second.buf[k]); }
-                ready_.erase(it); ++next_write_;
+            j.part.reset(); j.ref.reset();
+            // Chunks finish out of order; file offsets are handed out strictly in chunk order (the analogue of the reference's
+            // ordered output bins, extract.c:514-535), after which the bytes can land in any order: every thread writes the
+            // chunks IT released, with pwrite, outside the lock.
+            std::vector<Done> mine;
+            {
+                std::lock_guard<std::mutex> g(m_);
+                busy_s_ += now_s() - t0; n_variant_ += nvar;
+                ready_.emplace(j.seq, std::move(d));
+                for (auto it = ready_.find(next_assign_); it != ready_.end(); it = ready_.find(next_assign_)) {
+                    for (int k = 0; k < 3; ++k) if (it->second.buf[k]) { it->second.at[k] = off_[k]; off_[k] += it->second.buf[k]->n; }
+                    mine.push_back(std::move(it->second));
+                    ready_.erase(it); ++next_assign_;
+                }
+            }
+            bool ok = true;
+            const double t1 = now_s();
+            for (Done &w : mine)
+                for (int k = 0; k < 3; ++k) if (w.buf[k]) {
+                    const char *p = w.buf[k]->v.data(); size_t left = w.buf[k]->n; uint64_t at = w.at[k];
+                    while (left) { ssize_t r = pwrite(fd_[k], p, left, (off_t) at); if (r <= 0) { ok = false; break; } p += r; left -= (size_t) r; at += (uint64_t) r; }
+                    w.buf[k].reset();
+                }
+            {
+                std::lock_guard<std::mutex> g(m_);
+                written_ += mine.size(); write_s_ += now_s() - t1;
+                if (!ok) failed_ = true;
             }
             cv_.notify_all();
         }
     }
-    const ExtractOptions &o_; FILE *fp_[3];
-    std::deque<Job> q_; std::map<uint64_t, Done> ready_; uint64_t next_seq_ = 0, next_write_ = 0, n_variant_ = 0;
-    std::mutex m_; std::condition_variable cv_; bool stop_ = false; double busy_s_ = 0;
+    const ExtractOptions &o_; int fd_[3]; uint64_t off_[3]; bool one_file_ = false;
+    std::deque<Job> q_; std::map<uint64_t, Done> ready_; uint64_t next_seq_ = 0, next_assign_ = 0, written_ = 0, n_variant_ = 0;
+    std::mutex m_; std::condition_variable cv_; bool stop_ = false, failed_ = false; double busy_s_ = 0, write_s_ = 0;
     std::vector<std::thread> th_;
 };
-static int format_threads() { if (const char *e = getenv("MD_FORMAT_THREADS")) { int v = atoi(e); if (v > 0) return v; } unsigned hw = std::thread::hardware_concurrency(); return (int) std::max(1u, std::min(8u, hw / 4)); }
+// threads for the text stage: with the file decoded on the device the host cores have nothing else to do
+static int format_threads(bool device_decode) {
+    if (const char *e = getenv("MD_FORMAT_THREADS")) { int v = atoi(e); if (v > 0) return v; }
+    unsigned hw = std::thread::hardware_concurrency();
+    return (int) (device_decode ? std::max(2u, std::min(24u, hw > 4 ? hw - 3 : 2u)) : std::max(1u, std::min(8u, hw / 4)));
+}
 
 struct Driver {
     const mdh_backend *be; void *dev = nullptr;
@@ -220,21 +252,26 @@ struct Driver {
         if (be->set_bed(dev, (int32_t) tid, v.data(), (uint32_t) v.size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
         return 0;
     }
-    std::string cur_seq; int cur_seq_tid = -1; bool cur_seq_ok = false;
-    std::future<bool> next_ready; std::string next_seq; int next_tid = -1;
+    // contig sequences are shared with the text stage, which may still be formatting a contig's last chunks when the next
+    // contig is loaded (no drain between contigs)
+    std::shared_ptr<std::string> cur_seq = std::make_shared<std::string>(); int cur_seq_tid = -1; bool cur_seq_ok = false;
+    std::future<bool> next_ready; std::shared_ptr<std::string> next_seq; int next_tid = -1;
     // whole contig for the device and the writer; the one announced with prefetch() was read in the background meanwhile
     const std::string *fetch(uint32_t tid) {
         if ((int) tid != cur_seq_tid) {
             cur_seq_tid = (int) tid;
-            if (next_ready.valid() && next_tid == (int) tid) { cur_seq_ok = next_ready.get(); cur_seq.swap(next_seq); }
-            else { if (next_ready.valid()) next_ready.get(); cur_seq.clear(); cur_seq_ok = tid < hdr->names.size() && fa->fetch(hdr->names[tid], cur_seq); }
+            if (next_ready.valid() && next_tid == (int) tid) { cur_seq_ok = next_ready.get(); cur_seq = next_seq; next_seq.reset(); }
+            else { if (next_ready.valid()) next_ready.get(); cur_seq = std::make_shared<std::string>(); cur_seq_ok = tid < hdr->names.size() && fa->fetch(hdr->names[tid], *cur_seq); }
         }
-        return cur_seq_ok ? &cur_seq : nullptr;
+        return cur_seq_ok ? cur_seq.get() : nullptr;
     }
+    std::shared_ptr<const std::string> shared_ref() const { return cur_seq; }
     void prefetch(uint32_t tid) {
         if (next_ready.valid() || (int) tid == cur_seq_tid || tid >= hdr->names.size()) return;
         next_tid = (int) tid;
-        next_ready = std::async(std::launch::async, [this, tid] { return fa->fetch(hdr->names[tid], next_seq); });
+        next_seq = std::make_shared<std::string>();
+        std::shared_ptr<std::string> dst = next_seq;
+        next_ready = std::async(std::launch::async, [this, tid, dst] { return fa->fetch(hdr->names[tid], *dst); });
     }
     ~Driver() { if (next_ready.valid()) next_ready.wait(); }
     // a few bases around a chunk end (adjustBounds, common.c:477) without loading the contig; returns the contig's length
@@ -384,8 +421,7 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
             size_t b = a; while (b < calls.size() && calls[b].pos < k.end) ++b;
             auto part = std::make_shared<std::vector<md_call>>(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b);
             const char *cname = d.hdr->names[J.tid].c_str();
-            const std::string *rp = ref;
-            if (!d.chunk_skipped(k)) out_thread.post(cname, rp, k, part);
+            if (!d.chunk_skipped(k)) out_thread.post(cname, d.shared_ref(), k, part);
             calls_head = b; ++next_chunk;
         }
         if (calls_head > (1u << 20)) { calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
@@ -423,7 +459,6 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
     };
     auto close_contig = [&](const ContigJob &J) -> int {
         if (ref) absorb(J, J.rend, true);
-        out_thread.drain();                                     // the next contig replaces *ref
         if (loaded) be->drop_contig(d.dev, (int32_t) J.tid);
         loaded = false;
         return 0;
@@ -614,7 +649,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         d.have_bed = true;
     }
     for (int k = 0; k < 3; ++k) if (fp[k] && (k == 0 || fp[k] != fp[0])) setvbuf(fp[k], nullptr, _IOFBF, 4 << 20);
-    OrderedFormatter out_thread(format_threads(), o, fp);
+    OrderedFormatter out_thread(format_threads(dev_decode), o, fp);
     int rc = 0;
     {
         // the reference's chunk list (extract.c:325-350), enumerated up front; a shard takes a contiguous,
@@ -695,7 +730,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
                     size_t b = a; while (b < calls.size() && calls[b].pos < k.end) ++b;
                     auto part = std::make_shared<std::vector<md_call>>(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b);
                     const char *cname = d.hdr->names[tid].c_str();
-                    if (!d.chunk_skipped(k)) out_thread.post(cname, ref, k, part);
+                    if (!d.chunk_skipped(k)) out_thread.post(cname, d.shared_ref(), k, part);
                     calls_head = b; ++next_chunk;
                 }
                 if (calls_head > (1u << 20)) { calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
@@ -756,13 +791,13 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             mark("last tile submitted");
             while (rc == 0 && !flight.empty()) rc = collect_one();
             if (rc == 0) absorb(rend, true);
-            { Acc a_(3); out_thread.drain(); }                      // the next contig replaces *ref
             mark("contig written");
             be->drop_contig(d.dev, (int32_t) tid);
         }
         }   // host decode
     }
     out_thread.drain();
+    if (out_thread.failed()) { fprintf(stderr, "Couldn't write the output file(s)! Disk full?\n"); if (rc == 0) rc = -3; }
     g_stats.t_format_s = out_thread.busy_seconds();
     if (g_marks) fprintf(stderr, "[md-timing] calling thread: phred packing %.3f, contig load %.3f, call hand-over %.3f, writer drain %.3f, result buffer %.3f\n", g_acc[0], g_acc[1], g_acc[2], g_acc[3], g_acc[4]);
     if (g_marks && d.bam) fprintf(stderr, "[md-timing] record chains: %zu jobs adopted from the inflating worker, %zu walked by the stitcher\n", d.bam->jobs_adopted(), d.bam->jobs_walked());

@@ -10,6 +10,7 @@
 //   * the variant-exclusion side effects on a pending merged call (extract.c:444-459).
 #pragma once
 #include <cstdio>
+#include <cstdarg>
 #include <cstdint>
 #include <cmath>
 #include <string>
@@ -97,9 +98,26 @@ private:
     uint32_t gTid_, gPos_, gEnd_;
 };
 
+// Output text of one chunk for one file: a plain growable byte buffer (a FILE* costs a locked call per line, and this
+// stage writes ~10^9 lines on a genome).
+struct TextBuf {
+    std::vector<char> v; size_t n = 0;
+    char *room(size_t k) { if (n + k > v.size()) v.resize(std::max(v.size() * 2, n + k + (1u << 16))); return v.data() + n; }
+    void put(const char *p, size_t k) { memcpy(room(k), p, k); n += k; }
+    void printf_(const char *fmt, ...) __attribute__((format(printf, 2, 3))) {
+        va_list ap; va_start(ap, fmt);
+        char *w = room(1024);
+        int k = vsnprintf(w, 1024, fmt, ap);
+        va_end(ap);
+        if (k >= 1024) { va_start(ap, fmt); w = room((size_t) k + 1); vsnprintf(w, (size_t) k + 1, fmt, ap); va_end(ap); }
+        if (k > 0) n += (size_t) k;
+    }
+};
+
 class ExtractWriter {
 public:
-    ExtractWriter(const ExtractOptions &o, FILE *fp[3]) : o_(o) { fp_[0] = fp[0]; fp_[1] = fp[1]; fp_[2] = fp[2]; }
+    // out[k]: where the lines of context k (CpG, CHG, CHH) go; the three may be the same buffer (cytosine_report), or null
+    ExtractWriter(const ExtractOptions &o, TextBuf *out[3]) : o_(o) { fp_[0] = out[0]; fp_[1] = out[1]; fp_[2] = out[2]; }
     uint64_t n_variant_positions() const { return nVariant_; }
 
     // printHeader, extract.c:562-569
@@ -177,32 +195,31 @@ private:
     static char *put_int(char *w, int32_t v) { if (v < 0) { *w++ = '-'; return put_uint(w, (uint32_t)(-(int64_t) v)); } return put_uint(w, (uint32_t) v); }
 
     // writeCall, extract.c:39-99
-    void write_call(FILE *f, const char *chrom, int32_t pos, int32_t width, uint32_t nm, uint32_t nu, char base, const char *context, const char *tnc) {
+    void write_call(TextBuf *f, const char *chrom, int32_t pos, int32_t width, uint32_t nm, uint32_t nu, char base, const char *context, const char *tnc) {
         char strand = (base == 'C' || base == 'c') ? 'F' : 'R';
         if ((nm + nu) < (uint32_t) o_.minDepth && !o_.cytosine_report) return;   // unsigned compare, as in C
         if (!o_.fraction && !o_.logit && !o_.counts && !o_.methylKit && !o_.cytosine_report) {
             // "%s\t%i\t%i\t%i\t%u\t%u\n" (extract.c:45-52) assembled by hand: this line is written ~10^9 times on a genome
-            char buf[512]; char *w = buf;
-            size_t cl = strlen(chrom);
-            if (cl > 400) { fprintf(f, "%s\t%i\t%i\t%i\t%" PRIu32 "\t%" PRIu32 "\n", chrom, pos, pos + width, (int)(100.0 * ((double) nm) / (nm + nu)), nm, nu); return; }
-            memcpy(w, chrom, cl); w += cl; *w++ = '\t';
+            if (chrom != chrom_) { chrom_ = chrom; chrom_len_ = strlen(chrom); }
+            char *w0 = f->room(chrom_len_ + 80), *w = w0;
+            memcpy(w, chrom, chrom_len_); w += chrom_len_; *w++ = '\t';
             w = put_int(w, pos); *w++ = '\t'; w = put_int(w, pos + width); *w++ = '\t';
             w = put_int(w, (int)(100.0 * ((double) nm) / (nm + nu))); *w++ = '\t';
             w = put_uint(w, nm); *w++ = '\t'; w = put_uint(w, nu); *w++ = '\n';
-            fwrite(buf, 1, (size_t)(w - buf), f);
+            f->n += (size_t)(w - w0);
         }
-        else if (o_.fraction) fprintf(f, "%s\t%i\t%i\t%f\n", chrom, pos, pos + width, ((double) nm) / (nm + nu));
-        else if (o_.counts) fprintf(f, "%s\t%i\t%i\t%i\n", chrom, pos, pos + width, nm + nu);
-        else if (o_.logit) fprintf(f, "%s\t%i\t%i\t%f\n", chrom, pos, pos + width, logit(((double) nm) / (nm + nu)));
+        else if (o_.fraction) f->printf_("%s\t%i\t%i\t%f\n", chrom, pos, pos + width, ((double) nm) / (nm + nu));
+        else if (o_.counts) f->printf_("%s\t%i\t%i\t%i\n", chrom, pos, pos + width, nm + nu);
+        else if (o_.logit) f->printf_("%s\t%i\t%i\t%f\n", chrom, pos, pos + width, logit(((double) nm) / (nm + nu)));
         else if (o_.methylKit)
-            fprintf(f, "%s.%i\t%s\t%i\t%c\t%i\t%6.2f\t%6.2f\n", chrom, pos + 1, chrom, pos + 1, strand, nm + nu, 100.0 * ((double) nm) / (nm + nu), 100.0 * ((double) nu) / (nm + nu));
+            f->printf_("%s.%i\t%s\t%i\t%c\t%i\t%6.2f\t%6.2f\n", chrom, pos + 1, chrom, pos + 1, strand, nm + nu, 100.0 * ((double) nm) / (nm + nu), 100.0 * ((double) nu) / (nm + nu));
         else if (o_.cytosine_report) {
             strand = (base == 'C' || base == 'c') ? '+' : '-';
-            fprintf(f, "%s\t%i\t%c\t%" PRIu32 "\t%" PRIu32 "\tC%s\t%s\n", chrom, pos + 1, strand, nm, nu, context, tnc);
+            f->printf_("%s\t%i\t%c\t%" PRIu32 "\t%" PRIu32 "\tC%s\t%s\n", chrom, pos + 1, strand, nm, nu, context, tnc);
         }
     }
     // processLast, extract.c:207-222
-    void process_last(FILE *f, const char *chrom, Last &last, int32_t pos, int width, uint32_t nm, uint32_t nu, char base) {
+    void process_last(TextBuf *f, const char *chrom, Last &last, int32_t pos, int width, uint32_t nm, uint32_t nu, char base) {
         if (last.live && last.pos == pos) {
             write_call(f, chrom, pos, width, nm + last.nm, nu + last.nu, base, nullptr, nullptr);
             last.live = false;
@@ -224,7 +241,8 @@ private:
         }
     }
     ExtractOptions o_;
-    FILE *fp_[3];
+    TextBuf *fp_[3];
+    const char *chrom_ = nullptr; size_t chrom_len_ = 0;
     uint64_t nVariant_ = 0;
 };
 
