@@ -49,7 +49,8 @@ def check_against_tree(agg):
         if f not in files:
             files[f] = open(f, errors="replace").read().splitlines()
         disk = files[f][line - 1].strip() if line - 1 < len(files[f]) else "<beyond end of file>"
-        if disk != a["src"]:
+        norm = lambda t: t.replace('"', "").replace(" ", "")            # the CSV export drops / doubles quotes inside source text  # noqa: E731
+        if norm(disk) != norm(a["src"]):
             bad.append((f, line, a["src"][:80], disk[:80]))
     return bad
 
