@@ -324,6 +324,7 @@ struct CountArgs {
     uint32_t split; uint32_t *acc; uint32_t *done;         // deep tiles: `split` CTAs share a window's alignments; their counters meet in acc[] (32-bit layout per window), the last one to arrive (done[]) writes the calls
     uint32_t ablate;                                       // timing experiments only (MD_ABLATE): 1 skip evaluation, 2 skip generation, 4 skip staging copies
     uint32_t okmask;                                       // 2-/4-bit phred tiles: bit c set when code c decodes to a phred >= minPhred
+    uint16_t *sites;                                       // GEN 2: per CTA 2 * W entries of scratch in HBM (L1-resident): the window's kept C-sites, then its kept G-sites, ascending
 };
 
 #define MB_SM_Q 256   // mbias: query positions < this are histogrammed in shared memory
@@ -553,6 +554,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
     for (uint32_t t = tid; t < ncnt; t += WS_WARPS * 32) cnt[t] = 0;
     if (tid < (MODE == 1 ? 12 : 8)) { uint32_t *g = bmC + (tid >> 1) * (NW + 2); g[(tid & 1) ? NW + 1 : 0] = 0; }
     __syncthreads();
+    unsigned site16C = 0, site16G = 0;                                     // this thread's 16 positions: kept C / G sites (GEN 2 builds the site lists from them)
     {
         const uint32_t t16 = 16u * tid;
         unsigned sC = 0, sG = 0, t0 = 0, t1 = 0;
@@ -603,6 +605,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
             }
             oC = sC & aE; oG = sG & aO; sC &= aO; sG &= aE; t0 &= aO | aE; t1 &= aO | aE;
         }
+        site16C = sC; site16G = sG;
         const unsigned pC = __shfl_down_sync(0xffffffffu, sC, 1), pG = __shfl_down_sync(0xffffffffu, sG, 1), p0 = __shfl_down_sync(0xffffffffu, t0, 1), p1 = __shfl_down_sync(0xffffffffu, t1, 1);
         const unsigned pCo = __shfl_down_sync(0xffffffffu, oC, 1), pGo = __shfl_down_sync(0xffffffffu, oG, 1);
         if (!(tid & 1)) {
@@ -611,7 +614,29 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
             if (MODE == 1) { bmCo[wi] = oC | (pCo << 16); bmGo[wi] = oG | (pGo << 16); }
         }
     }
-    __syncthreads();                                                      // bitmaps complete; refw (overlay) no longer needed
+    // GEN 2: the window's kept sites as sorted lists (C-sites at sites[0..nC), G-sites at sites[W..W+nG), window-relative) and, per
+    // bitmap word, the number of sites below it: rank(x) = prefix[x >> 5] + popc(word & below(x)) turns "the kept sites of a
+    // reference interval" into an index range of the list, and the list turns an index back into a position.
+    __shared__ uint16_t s_prefC[(4096 >> 5) + 1], s_prefG[(4096 >> 5) + 1];
+    __shared__ uint32_t s_scan[WS_WARPS];
+    uint16_t *siteC = A.sites ? A.sites + (size_t) blockIdx.x * 2u * W : nullptr, *siteG = siteC ? siteC + W : nullptr;
+    if (GEN == 2) {
+        const uint32_t v = (uint32_t) __popc(site16C) | ((uint32_t) __popc(site16G) << 16);
+        uint32_t inc = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_scan[warp] = inc;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int k = 0; k < warp; ++k) base += s_scan[k];
+        const uint32_t ex = base + inc - v;
+        if (!(tid & 1)) { s_prefC[tid >> 1] = (uint16_t)(ex & 0xffffu); s_prefG[tid >> 1] = (uint16_t)(ex >> 16); }
+        if (tid == WS_WARPS * 32 - 1) { s_prefC[NW] = (uint16_t)((ex + v) & 0xffffu); s_prefG[NW] = (uint16_t)((ex + v) >> 16); }
+        uint32_t oc = ex & 0xffffu, og = ex >> 16;
+        for (unsigned m = site16C; m; m &= m - 1u) siteC[oc++] = (uint16_t)(16u * tid + (uint32_t)(__ffs(m) - 1));
+        for (unsigned m = site16G; m; m &= m - 1u) siteG[og++] = (uint16_t)(16u * tid + (uint32_t)(__ffs(m) - 1));
+    }
+    __syncthreads();                                                      // bitmaps (and site lists) complete; refw (overlay) no longer needed
     uint2 rr = make_uint2(s_rr[0], max(s_rr[0], s_rr[1]));
     if (S > 1) {                                                          // this CTA's share of the window's alignments
         const unsigned long long len = rr.y - rr.x;
@@ -841,63 +866,75 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
                     if (all_done) break;
                 }
             } else {
-                int opq = 0, opp_ = 0;
-                uint32_t qa = 0, qb2 = 0;                                   // queued candidates: plain / inside the mate's span (warp-uniform)
-                uint32_t *queueB = queue + WS_QUEUE / 2;
+                // GEN 2: list generator (MODE 0 and 2).  The kept sites of a lane's match op are an index range of its strand's site
+                // list: two rank look-ups instead of a walk over bitmap words, and writing the candidates out is a counted loop
+                // over list entries — every lane runs the same few iterations — instead of a find-first-set loop whose trip count
+                // differs from lane to lane (that loop and the per-word counting were 42 % of the kernel's instructions at 17 of 32
+                // lanes in round 1's generator, which stays as GEN 1 for the variant filter).  A match op is cut where the mate's
+                // span begins and ends, in list-index space: phase 0 = sites before the mate's span, 1 = inside it, 2 = beyond it.
+                const uint16_t *lst = rc.wantG ? siteG : siteC, *pref = rc.wantG ? s_prefG : s_prefC;
+                auto rank = [&](int x) -> uint32_t {                    // kept sites of this lane's strand below window-relative position x, 0 <= x <= W
+                    const uint32_t w = (uint32_t) x >> 5;
+                    return (uint32_t) pref[w] + (uint32_t) __popc(own_bm[w + 1] & ((1u << (x & 31)) - 1u));
+                };
+                int qrel = 0;
+                uint32_t qa = 0, qb2 = 0;
+                const bool has_mate = rc.mi >= 0;
+                const int mrel0 = has_mate ? rc.mpos - w0i : 0, mrel1 = has_mate ? rc.mend - w0i : 0;
+                uint32_t j0 = 0, j1 = 0, j2 = 0, j3 = 0;                 // list indices of the current op: [j0, j1) before the mate, [j1, j2) inside, [j2, j3) beyond
+                uint32_t jc = 0, je = 0; int ph = 3;   // cursor and end of the current phase's index range
+                if (A.ablate & 2u) done = true;
                 for (;;) {
-                    // advance to the next candidate (divergent, cheap)
-                    bool has = false; uint32_t ent = 0; bool inmate = false;
-                    while (!done) {
-                        if (cur | curo) {
-                            const unsigned any = cur | curo; const int bit = __ffs(any) - 1;
-                            const bool is_own = (cur >> bit) & 1u;
-                            cur &= ~(1u << bit); curo &= ~(1u << bit);
-                            const int rel = (wi << 5) + bit, qi = opq + (w0i + rel - opp_);
-                            ent = (uint32_t) lane | ((uint32_t) rel << 5) | ((uint32_t) qi << 17) | (is_own ? 0u : 0x80000000u);
-                            inmate = rc.mi >= 0 && (w0i + rel) >= rc.mpos && (w0i + rel) < rc.mend;
-                            has = true; break;
-                        }
-                        if (in_op && wi < ((rb - 1) >> 5)) {
-                            ++wi;
-                            unsigned keep = 0xffffffffu;
-                            if (wi == ((rb - 1) >> 5)) keep &= 0xffffffffu >> (31 - ((rb - 1) & 31));
-                            cur = own_bm[wi + 1] & keep; curo = (MODE == 1) ? (opp_bm[wi + 1] & keep) : 0u;
-                            continue;
-                        }
-                        in_op = false;
+                    while (!done && jc >= je) {
+                        if (ph < 2) { ++ph; jc = ph == 1 ? j1 : j2; je = ph == 1 ? j2 : j3; continue; }
                         if (k >= k1) { done = true; break; }
                         const uint32_t c = (k == k0) ? c0 : __ldg(R.cigar + k), op = c & 15u; const int len = (int)(c >> 4);
                         ++k;
                         if (op == 0 || op == 7 || op == 8) {
                             const int a = max(max(p, w0i), p + (rc.lo - q)), bnd = min(min(p + len, w0i + own), p + (rc.hi - q));
                             if (bnd > a) {
-                                ra = a - w0i; rb = bnd - w0i; wi = ra >> 5; in_op = true; opq = q; opp_ = p;
-                                unsigned keep = 0xffffffffu << (ra & 31);
-                                if (wi == ((rb - 1) >> 5)) keep &= 0xffffffffu >> (31 - ((rb - 1) & 31));
-                                cur = own_bm[wi + 1] & keep; curo = (MODE == 1) ? (opp_bm[wi + 1] & keep) : 0u;
+                                const int ra = a - w0i, rb = bnd - w0i;
+                                qrel = q - (p - w0i);
+                                j0 = rank(ra); j3 = rank(rb);
+                                if (has_mate) { j1 = rank(min(max(mrel0, ra), rb)); j2 = rank(min(max(mrel1, ra), rb)); }
+                                else { j1 = j3; j2 = j3; }
+                                ph = 0; jc = j0; je = j1;
                             }
                             p += len; q += len;
                         } else if (op == 1 || op == 4) q += len;
                         else if (op == 2 || op == 3) p += len;
                     }
-                    // candidates that need the mate's base/phred (global-memory look-ups) are queued apart, so that their latency
-                    // is paid once per 32 look-ups instead of once per round
-                    const unsigned hmA = __ballot_sync(0xffffffffu, has && !inmate), hmB = __ballot_sync(0xffffffffu, has && inmate);
-                    if (has) { if (inmate) queueB[qb2 + __popc(hmB & ((1u << lane) - 1u))] = ent; else queue[qa + __popc(hmA & ((1u << lane) - 1u))] = ent; }
-                    qa += __popc(hmA); qb2 += __popc(hmB);
-                    const bool all_done = (hmA | hmB) == 0u;                  // no lane produced anything: every iterator is exhausted
+                    const bool busy = jc < je;
+                    const bool all_done = !__any_sync(0xffffffffu, busy);     // every lane ran out of match ops: the batch is exhausted
+                    const bool tB = ph == 1;
+                    const uint32_t room = WS_QUEUE - qa - qb2, cap = room >> 5;   // the queues are drained below 64 entries each: cap >= 10
+                    const uint32_t n = busy ? min(je - jc, cap) : 0u;
+                    const uint32_t v = tB ? (n << 16) : n;
+                    uint32_t inc = v;
+                    #pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                    const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+                    if (n) {
+                        const uint32_t ex = inc - v;
+                        uint32_t *dst = tB ? queue + (WS_QUEUE - 1u - (qb2 + (ex >> 16))) : queue + (qa + (ex & 0xffffu));
+                        const int dir = tB ? -1 : 1;
+                        const uint32_t base = (uint32_t) lane + ((uint32_t) qrel << 17);
+                        for (uint32_t r = 0; r < n; ++r) { *dst = base + (uint32_t) lst[jc + r] * 0x20020u; dst += dir; }
+                        jc += n;
+                    }
+                    qa += tot & 0xffffu; qb2 += tot >> 16;
                     __syncwarp();
                     while (qa >= 32u * EV || (all_done && qa > 0u)) {
                         const uint32_t take = min(qa, 32u * EV);
                         #pragma unroll
-                        for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take) eval_entry(queue[qa - take + lane + 32 * r], false);
+                        for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take && !(A.ablate & 1u)) eval_entry(queue[qa - take + lane + 32 * r], false);
                         qa -= take;
                         __syncwarp();
                     }
                     while (qb2 >= 32u * EV || (all_done && qb2 > 0u)) {
                         const uint32_t take = min(qb2, 32u * EV);
                         #pragma unroll
-                        for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take) eval_entry(queueB[qb2 - take + lane + 32 * r], true);
+                        for (int r = 0; r < EV; ++r) if ((uint32_t)(lane + 32 * r) < take && !(A.ablate & 1u)) eval_entry(queue[WS_QUEUE - qb2 + lane + 32 * r], true);
                         qb2 -= take;
                         __syncwarp();
                     }
@@ -1132,7 +1169,7 @@ struct md_dev_reads {
 struct Lane {
     cudaStream_t stream = nullptr;
     md_dev_reads staged;                 // device copy of the host tile
-    DevBuf rend, info, mate, tab, win, dir, calls, counters, sorted, sorted_off, acc, done;
+    DevBuf rend, info, mate, tab, win, dir, calls, counters, sorted, sorted_off, acc, done, sites;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float timing[5] = {0, 0, 0, 0, 0};
     uint32_t last_nwin = 0; uint64_t last_ncalls = 0; bool pending = false; md_tile_stats last_stats;
@@ -1151,7 +1188,7 @@ struct md_ctx {
     bool bed_mode = false;               // md_set_bed was called: -l semantics for every tile
     uint32_t ablate = 0;                 // MD_ABLATE: timing experiments (results are wrong when set)
     md_totals tot;                       // device time and work over all tiles (md_ctx_totals)
-    int gen = 1;                         // count_warp<MODE, GEN>: 1 = segment-at-a-time candidate generator, 0 = one candidate per lane per ballot (kept for A/B runs, MD_GEN=0)
+    int gen = 2;                         // count_warp<MODE, GEN>: 2 = list generator (site lists + rank look-ups), 1 = bitmap generator (always used with the variant filter; MD_GEN=1 forces it)
 };
 
 static void sync_all(md_ctx *c) { for (int k = 0; k < MD_NLANES; ++k) if (c->lanes[k].stream) cudaStreamSynchronize(c->lanes[k].stream); }
@@ -1188,13 +1225,12 @@ extern "C" md_ctx *md_create(const md_config *cfg, int device) {
     cudaFuncSetAttribute(count_warp<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
     cudaFuncSetAttribute(count_warp<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
     cudaFuncSetAttribute(count_warp<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
-    cudaFuncSetAttribute(count_warp<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
-    cudaFuncSetAttribute(count_warp<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 1, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
-    cudaFuncSetAttribute(count_warp<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
+    cudaFuncSetAttribute(count_warp<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 0, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
+    cudaFuncSetAttribute(count_warp<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_layout(4096, 2, 1, WS_SEQ_BYTES, WS_QUAL_BYTES).total);
     if (const char *v = getenv("MD_ABLATE")) c->ablate = (uint32_t) atoi(v);
     if (const char *v = getenv("MD_SPLIT_ABOVE")) c->split_above = (uint32_t) atol(v);
     if (const char *v = getenv("MD_FORCE_SPLIT")) { int e = atoi(v); c->force_split = e > 0 && e <= 64 ? (uint32_t) e : 0u; }
-    if (const char *v = getenv("MD_GEN")) { int e = atoi(v); if (e == 0 || e == 1) c->gen = e; }
+    if (const char *v = getenv("MD_GEN")) { int e = atoi(v); if (e == 1 || e == 2) c->gen = e; }
     cudaStreamSynchronize(L->stream);
     return c;
 }
@@ -1212,7 +1248,7 @@ extern "C" void md_destroy(md_ctx *c) {
     for (int k = 0; k < MD_NLANES; ++k) {
         Lane *L = &c->lanes[k];
         L->staged.arena.release();
-        DevBuf *bufs[] = {&L->rend, &L->info, &L->mate, &L->tab, &L->win, &L->dir, &L->calls, &L->counters, &L->sorted, &L->sorted_off, &L->acc, &L->done};
+        DevBuf *bufs[] = {&L->rend, &L->info, &L->mate, &L->tab, &L->win, &L->dir, &L->calls, &L->counters, &L->sorted, &L->sorted_off, &L->acc, &L->done, &L->sites};
         for (DevBuf *b : bufs) b->release();
         for (int i = 0; i < 5; ++i) if (L->ev[i]) cudaEventDestroy(L->ev[i]);
         if (L->h_counters) cudaFreeHost(L->h_counters);
@@ -1356,14 +1392,16 @@ static int launch_count(md_ctx *c, Lane *L, const Contig &g, const DevReads &R, 
     A.bed.start = g.d_bed; A.bed.pmax = g.d_bed ? g.d_bed + g.n_bed : nullptr; A.bed.strand = g.d_bed ? g.d_bed + 2 * (size_t) g.n_bed : nullptr; A.bed.n = g.n_bed; A.bed.on = c->bed_mode ? 1u : 0u;
     A.okmask = 0; for (int cde = 0; cde < 16; ++cde) if ((int) R.qlut[cde] >= kp.minPhred) A.okmask |= 1u << cde;
     const size_t sm = warp_layout(W, mode, A.wide, A.st_seq, A.st_qual).total;
-    if (c->gen == 1) {
+    A.sites = nullptr;
+    if (c->gen == 2 && mode != 1) {                              // list generator: 2 * W site slots per CTA (the variant filter keeps the bitmap generator)
+        if (L->sites.reserve((size_t) n_cta * 2u * W * sizeof(uint16_t))) return -100;
+        A.sites = (uint16_t *) L->sites.p;
+        if (mode == 2) count_warp<2, 2><<<n_cta, WS_WARPS * 32, sm, s>>>(A);
+        else count_warp<0, 2><<<n_cta, WS_WARPS * 32, sm, s>>>(A);
+    } else {
         if (mode == 2) count_warp<2, 1><<<n_cta, WS_WARPS * 32, sm, s>>>(A);
         else if (mode == 1) count_warp<1, 1><<<n_cta, WS_WARPS * 32, sm, s>>>(A);
         else count_warp<0, 1><<<n_cta, WS_WARPS * 32, sm, s>>>(A);
-    } else {
-        if (mode == 2) count_warp<2, 0><<<n_cta, WS_WARPS * 32, sm, s>>>(A);
-        else if (mode == 1) count_warp<1, 0><<<n_cta, WS_WARPS * 32, sm, s>>>(A);
-        else count_warp<0, 0><<<n_cta, WS_WARPS * 32, sm, s>>>(A);
     }
     c->launches += 1;
     if (!mbias) {
