@@ -512,6 +512,31 @@ static int mbias_device_decode(Driver &d, const mdh_backend *be, const char *bam
     return rc;
 }
 
+// One process per GPU: shard `rank` of `world` takes a contiguous run [c0, c1) of the reference's chunks.  The runs are
+// balanced by the amount of ALIGNMENT DATA they hold — compressed file bytes between the chunks' positions in the BAM
+// index's linear index — not by base pairs: a targeted panel or an unevenly covered genome otherwise leaves most GPUs
+// idle (the reference's dynamic chunk cursor, extract.c:327-350, balances itself the same way).  Without an
+// index, or when it shows no data at all, the split falls back to base pairs.
+static void shard_chunks(const std::vector<Chunk> &all, const BaiIndex *bai, int rank, int world, size_t &c0, size_t &c1) {
+    std::vector<uint64_t> w(all.size());
+    uint64_t total = 0;
+    if (bai) {
+        for (size_t k = 0; k < all.size(); ++k) {
+            const uint64_t a = bai->file_pos((int) all[k].tid, all[k].beg);
+            uint64_t b = bai->file_pos((int) all[k].tid, all[k].end);
+            if (k + 1 < all.size() && all[k + 1].tid != all[k].tid) { const uint64_t nb = bai->file_pos((int) all[k + 1].tid, all[k + 1].beg); if (nb > a) b = std::max(b, nb); }   // a contig's last chunk reaches to the next contig's data
+            w[k] = (a && b > a) ? b - a : 0; total += w[k];
+        }
+    }
+    if (total == 0) { for (size_t k = 0; k < all.size(); ++k) { w[k] = all[k].end - all[k].beg; total += w[k]; } }
+    else for (size_t k = 0; k < all.size(); ++k) { w[k] += 1; total += 1; }     // empty chunks still cost something, and every prefix sum moves
+    const uint64_t lo = total * (uint64_t) rank / (uint64_t) world, hi = total * (uint64_t)(rank + 1) / (uint64_t) world;
+    uint64_t acc = 0;
+    c0 = c1 = all.size();
+    for (size_t k = 0; k < all.size(); ++k) { if (acc >= lo && c0 == all.size()) c0 = k; if (acc >= hi) { c1 = k; break; } acc += w[k]; }
+    if (c0 > c1) c0 = c1;
+}
+
 extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     ExtractOptions o;
     char *opref = nullptr; const char *reg = nullptr, *bedName = nullptr, *bwName = nullptr, *bbmName = nullptr;
@@ -591,7 +616,12 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
 
     Driver d; d.be = be;
     const char *fastaName = argv[optind], *bamName = argv[optind + 1];
-    const bool dev_decode = device_decode_enabled(be) && !(minConvEff > 0.0);
+    // A query name that occurs more than twice among the admitted records (secondary / supplementary alignments let in by -F)
+    // pairs up alternately in file order WITHIN each of the reference's chunks (a fresh hash per chunk, extract.c:393,536), so
+    // which records merge depends on the chunk grid.  Tiles then follow the chunks exactly (one tile per chunk, host decoder);
+    // with the default -F 0xF00 names occur at most twice and the tiling is free.
+    const bool chunk_exact = (o.core.ignoreFlags & 0x900) != 0x900;
+    const bool dev_decode = device_decode_enabled(be) && !(minConvEff > 0.0) && !chunk_exact;
     try {
         if (dev_decode) { BgzfReader rd(bamName); d.own_hdr = read_bam_header(rd); d.start_voff = rd.tell(); d.hdr = &d.own_hdr; }
         else { const int nt = decode_threads(nThreads, threads_given); d.bam.reset(new ParallelBam(bamName, nt, warm_threads(nt))); d.hdr = &d.bam->header(); }
@@ -662,13 +692,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             while (cursor.next(ch, fetch)) all.push_back(ch);
         }
         size_t c0 = 0, c1 = all.size();
-        if (shardWorld > 1) {
-            uint64_t total = 0; for (auto &k : all) total += k.end - k.beg;
-            uint64_t lo = total * (uint64_t) shardRank / (uint64_t) shardWorld, hi = total * (uint64_t)(shardRank + 1) / (uint64_t) shardWorld, acc = 0;
-            c0 = c1 = all.size();
-            for (size_t k = 0; k < all.size(); ++k) { if (acc >= lo && c0 == all.size()) c0 = k; if (acc >= hi) { c1 = k; break; } acc += all[k].end - all[k].beg; }
-            if (c0 > c1) c0 = c1;
-        }
+        if (shardWorld > 1) shard_chunks(all, d.have_bai ? &d.bai : nullptr, shardRank, shardWorld, c0, c1);
         if (dev_decode) {
             d.dev = dev_future.get(); dev_join.taken = true;
             mark("device joined");
@@ -681,8 +705,8 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         TileAlloc pin; if (use_async && be->pinned_alloc && be->pinned_free) { pin.alloc = be->pinned_alloc; pin.release = be->pinned_free; }
         std::vector<std::unique_ptr<SoaTile>> ring;
         for (int k = 0; k < (use_async ? 3 : 1); ++k) ring.emplace_back(new SoaTile(use_async ? &pin : nullptr));
-        const size_t tile_reads = tile_reads_default(use_async);
-        if (use_async) for (auto &t : ring) t->reserve_for(tile_reads + tile_reads / 8, 160);
+        const size_t tile_reads = chunk_exact ? (size_t) 1 << 40 : tile_reads_default(use_async);
+        if (use_async && !chunk_exact) for (auto &t : ring) t->reserve_for(tile_reads + tile_reads / 8, 160);
         // phred column re-encoded as 2/4-bit codes when the tile's alphabet allows (md_reads_soa::qual_bits)
         const bool pack_q = pack_quals_enabled();
         SoaTile carry;
@@ -719,7 +743,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
             // With --minConversionEfficiency the verdict on an alignment depends on the reference chunk it is looked at in
             // (computeConversionEfficiency only sees that chunk's window, common.c:363,378), so tiles are cut at chunk ends
             // and carry the chunk window; otherwise the whole run of chunks is one region.
-            const bool per_chunk = o.core.minConversionEfficiency > 0.0f;
+            const bool per_chunk = o.core.minConversionEfficiency > 0.0f || chunk_exact;
             std::vector<Chunk> regions;
             if (per_chunk) regions = chunks; else regions.push_back(Chunk{tid, rbeg, rend});
             // completed tiles arrive in order; hand every finished reference chunk to the writer
@@ -1037,13 +1061,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
             while (cursor.next(ch, fetch)) all.push_back(ch);
         }
         size_t c0 = 0, c1 = all.size();
-        if (shardWorld > 1) {
-            uint64_t total = 0; for (auto &k : all) total += k.end - k.beg;
-            uint64_t lo = total * (uint64_t) shardRank / (uint64_t) shardWorld, hi = total * (uint64_t)(shardRank + 1) / (uint64_t) shardWorld, acc = 0;
-            c0 = c1 = all.size();
-            for (size_t k = 0; k < all.size(); ++k) { if (acc >= lo && c0 == all.size()) c0 = k; if (acc >= hi) { c1 = k; break; } acc += all[k].end - all[k].beg; }
-            if (c0 > c1) c0 = c1;
-        }
+        if (shardWorld > 1) shard_chunks(all, d.have_bai ? &d.bai : nullptr, shardRank, shardWorld, c0, c1);
         if (dev_decode) {
             d.dev = dev_future.get(); dev_join.taken = true;
             if (!d.dev) { fprintf(stderr, "Could not initialise the device back end: %s\n", be->last_error ? be->last_error() : "?"); return -20; }

@@ -350,6 +350,15 @@ struct BaiIndex {
         fclose(f);
         return ok;
     }
+    // Compressed file position (bytes) near which the alignments at `pos` of contig `tid` are stored, from the linear index
+    // (one entry per 16 kb); used to weigh genome intervals by the amount of alignment data they hold.  0 when unknown.
+    uint64_t file_pos(int tid, int64_t pos) const {
+        if (tid < 0 || (size_t) tid >= refs.size()) return 0;
+        const Ref &R = refs[(size_t) tid];
+        if (R.ioff.empty()) return 0;
+        const size_t w = (size_t)(pos >> 14);
+        return (w < R.ioff.size() ? R.ioff[w] : R.ioff.back()) >> 16;
+    }
     // Smallest virtual offset at which an alignment overlapping [beg, ...) on tid can start; 0 if unknown.
     // found=false when the index proves there is no alignment on tid at all.
     uint64_t start_offset(int tid, int64_t beg, bool &found) const {
