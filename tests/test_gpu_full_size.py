@@ -85,3 +85,87 @@ def test_config1_region_equals_reference_build(built, c2, tmp_path):
     assert r.returncode == 0 and n.returncode == 0, (r.stderr, n.stderr)
     a = open(rp + "_CpG.bedGraph").read().replace(rp, "X"); bb = open(np_ + "_CpG.bedGraph").read().replace(np_, "X")
     assert a == bb and a.count("\n") > 20000
+
+
+def _cmp_extract(built, tmp_path, prefix, opts, tag):
+    rp, np_ = str(tmp_path / (tag + "_ref")), str(tmp_path / (tag + "_new"))
+    r = subprocess.run([built["ref_bin"], "extract", "-@", str(os.cpu_count() or 1)] + opts + [prefix + ".fa", prefix + ".bam", "-o", rp], capture_output=True, text=True)
+    n = subprocess.run([NEW_BIN, "extract"] + opts + [prefix + ".fa", prefix + ".bam", "-o", np_], capture_output=True, text=True)
+    assert r.returncode == 0 and n.returncode == 0, (r.stderr[-500:], n.stderr[-500:])
+    assert r.stdout == n.stdout
+    total = 0
+    for ctx in ("CpG", "CHG", "CHH"):
+        fr, fn = "%s_%s.bedGraph" % (rp, ctx), "%s_%s.bedGraph" % (np_, ctx)
+        assert os.path.exists(fr) == os.path.exists(fn)
+        if os.path.exists(fr):
+            a = open(fr, "rb").read().replace(rp.encode(), b"X"); bb = open(fn, "rb").read().replace(np_.encode(), b"X")
+            assert a == bb, "%s %s differs" % (tag, ctx)
+            total += len(a)
+    return total
+
+
+def test_config1_whole_file_equals_reference_build(built, c2, tmp_path):
+    """the binary's WHOLE config[1] output against oracle/_ref's, byte for byte (not a hash against itself): the
+    default CpG bedGraph, the merged all-context files of config[2]'s option set, and the mbias table + suggestion line"""
+    assert _cmp_extract(built, tmp_path, c2, [], "cpg") > 25_000_000
+    assert _cmp_extract(built, tmp_path, c2, ["--CHG", "--CHH", "--mergeContext"], "all") > 60_000_000
+    r = subprocess.run([built["ref_bin"], "mbias", "-@", str(os.cpu_count() or 1), "--txt", c2 + ".fa", c2 + ".bam", str(tmp_path / "mb_ref")], capture_output=True, text=True)
+    n = subprocess.run([NEW_BIN, "mbias", "--txt", c2 + ".fa", c2 + ".bam", str(tmp_path / "mb_new")], capture_output=True, text=True)
+    assert r.returncode == 0 and n.returncode == 0, (r.stderr[-500:], n.stderr[-500:])
+    assert r.stdout == n.stdout and len(r.stdout) > 5000
+    assert [l for l in r.stderr.splitlines() if l.startswith("Suggested")] == [l for l in n.stderr.splitlines() if l.startswith("Suggested")]
+    for s_ in ("OT", "OB"):
+        assert open(str(tmp_path / ("mb_ref_%s.svg" % s_))).read() == open(str(tmp_path / ("mb_new_%s.svg" % s_))).read()
+
+
+def test_config3_panel_fraction_equals_reference_build(built, synth, tmp_path):
+    """BASELINE.json configs[3] (5 Mbp at 2000x, insert 180+-25: nearly every pair overlaps) at 1/20 of its length — 250 kbp,
+    3.3 M alignments, ~13 000 per 4096-position window, so every window is split over several CTAs — whole file against oracle/_ref"""
+    p = synth("c4_frac", "--contigs", "panel:250000", "--depth", "2000", "--isize-mean", "180", "--isize-sd", "25", "--isize-min", "150", "--isize-max", "300", "--read-seed", "4242")
+    assert _cmp_extract(built, tmp_path, p, [], "panel") > 500_000
+    assert _cmp_extract(built, tmp_path, p, ["--CHG", "--CHH", "--minOppositeDepth", "50", "--maxVariantFrac", "0.1"], "panel_var") > 1_000_000
+
+
+SHARD_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+from methyldackel_b200 import api
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=world)
+def allsum(x):
+    t = torch.tensor([x], dtype=torch.int64); dist.all_reduce(t); return int(t.item())
+dev = rank %% max(1, torch.cuda.device_count())
+mode, argv = sys.argv[1], sys.argv[2:]
+if mode == "extract":
+    rc = api.extract_sharded(argv, rank, world, run_main=lambda av: api.extract_main(av, device=dev)[0], barrier=dist.barrier, allreduce_sum=allsum)
+else:
+    rc = api.mbias_sharded(argv[1:], rank, world, argv[0], run_main=lambda av: api.mbias_main(av, device=dev)[0], barrier=dist.barrier, allreduce_sum=allsum)
+dist.destroy_process_group()
+sys.exit(rc)
+'''
+
+
+def test_sharded_product_path_on_the_device(built, synth, tmp_path):
+    """VERDICT r1 #6: the sharded drivers (api.extract_sharded / mbias_sharded: one process per shard, shards balanced by the BAM
+    index) with libmdgpu as the back end — three processes sharing whatever devices the box has — against the one-process run"""
+    import sys
+    p = synth("shard_gpu", "--human", "6000000", "--depth", "20", "--read-seed", "31")
+    opts = ["--CHG", "--CHH", "--mergeContext"]
+    one, many = str(tmp_path / "one"), str(tmp_path / "many")
+    assert subprocess.run([NEW_BIN, "extract"] + opts + [p + ".fa", p + ".bam", "-o", one], capture_output=True).returncode == 0
+    code = SHARD_WORKER % {"root": cases.ROOT, "port": 29611}
+    procs = [subprocess.Popen([sys.executable, "-c", code, "extract"] + opts + [p + ".fa", p + ".bam", "-o", many],
+                              env=dict(os.environ, RANK=str(r), WORLD_SIZE="3"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(3)]
+    outs = [q.communicate(timeout=600) for q in procs]
+    assert all(q.returncode == 0 for q in procs), [o[1][-1500:] for o in outs]
+    for ctx in ("CpG", "CHG", "CHH"):
+        a = open("%s_%s.bedGraph" % (one, ctx)).read().replace(one, "X"); bb = open("%s_%s.bedGraph" % (many, ctx)).read().replace(many, "X")
+        assert a == bb and a.count("\n") > 10000
+    r1 = subprocess.run([NEW_BIN, "mbias", "--noSVG", p + ".fa", p + ".bam"], capture_output=True, text=True)
+    code = SHARD_WORKER % {"root": cases.ROOT, "port": 29612}
+    procs = [subprocess.Popen([sys.executable, "-c", code, "mbias", str(tmp_path / "mbh"), "--noSVG", p + ".fa", p + ".bam"],
+                              env=dict(os.environ, RANK=str(r), WORLD_SIZE="3"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(3)]
+    outs = [q.communicate(timeout=600) for q in procs]
+    assert all(q.returncode == 0 for q in procs), [o[1][-1500:] for o in outs]
+    assert outs[0][0] == r1.stdout and len(r1.stdout) > 2000
