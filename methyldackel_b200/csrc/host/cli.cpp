@@ -156,6 +156,18 @@ namespace {
 // Text formatting: reference chunks are independent (extract.c:496-507 flushes the merge state at every chunk end), so a few
 // threads format chunks concurrently, each into memory, and the finished texts are appended to the output files strictly
 // in chunk order (the analogue of the reference's ordered output bins, extract.c:514-535).  post() applies back-pressure.
+// Buffers that cycle between the calling thread and the text stage.  A whole-genome run pushes tens of gigabytes through these
+// (md_call records in, text out); allocating each one afresh means faulting in that many zeroed pages — on a cold process
+// that was most of the wall clock.  A pool keeps the working set at what is in flight.
+template <class T> class BufPool {
+public:
+    std::unique_ptr<T> get() { std::lock_guard<std::mutex> g(m_); if (free_.empty()) return std::unique_ptr<T>(new T()); std::unique_ptr<T> p = std::move(free_.back()); free_.pop_back(); return p; }
+    void put(std::unique_ptr<T> p) { if (!p) return; std::lock_guard<std::mutex> g(m_); if (free_.size() < 256) free_.push_back(std::move(p)); }
+private:
+    std::mutex m_; std::vector<std::unique_ptr<T>> free_;
+};
+typedef std::vector<md_call> CallVec;
+
 class OrderedFormatter {
 public:
     // fp[k]: the output files (headers already written through them); lines are appended with pwrite on their descriptors
@@ -165,21 +177,25 @@ public:
             fd_[k] = -1; off_[k] = 0;
             if (fp[k] && !(one_file_ && k)) { fflush(fp[k]); fd_[k] = fileno(fp[k]); off_[k] = (uint64_t) ftello(fp[k]); }
         }
+        max_inflight_ = (uint64_t) std::max(8, 3 * std::max(1, nthreads));
         for (int i = 0; i < std::max(1, nthreads); ++i) th_.emplace_back([this] { run(); });
     }
     ~OrderedFormatter() { { std::lock_guard<std::mutex> g(m_); stop_ = true; } cv_.notify_all(); for (auto &t : th_) t.join(); }
-    void post(const char *chrom, std::shared_ptr<const std::string> ref, Chunk k, std::shared_ptr<std::vector<md_call>> part) {
+    // a vector for the next chunk's records (recycled)
+    std::unique_ptr<CallVec> call_buffer() { std::unique_ptr<CallVec> p = calls_.get(); p->clear(); return p; }
+    void post(const char *chrom, std::shared_ptr<const std::string> ref, Chunk k, std::unique_ptr<CallVec> part) {
         std::unique_lock<std::mutex> l(m_);
-        cv_.wait(l, [&] { return next_seq_ - written_ < 96; });
+        cv_.wait(l, [&] { return next_seq_ - written_ < max_inflight_; });
         q_.push_back(Job{next_seq_++, chrom, std::move(ref), k, std::move(part)}); cv_.notify_all();
     }
     void drain() { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return written_ == next_seq_; }); }
     double busy_seconds() { std::lock_guard<std::mutex> g(m_); return busy_s_; }
+    double write_seconds() { std::lock_guard<std::mutex> g(m_); return write_s_; }
     uint64_t n_variant_positions() { std::lock_guard<std::mutex> g(m_); return n_variant_; }
     bool failed() { std::lock_guard<std::mutex> g(m_); return failed_; }
 private:
-    struct Job { uint64_t seq; const char *chrom; std::shared_ptr<const std::string> ref; Chunk k; std::shared_ptr<std::vector<md_call>> part; };
-    struct Done { std::shared_ptr<TextBuf> buf[3]; uint64_t at[3] = {0, 0, 0}; };
+    struct Job { uint64_t seq; const char *chrom; std::shared_ptr<const std::string> ref; Chunk k; std::unique_ptr<CallVec> part; };
+    struct Done { std::unique_ptr<TextBuf> buf[3]; uint64_t at[3] = {0, 0, 0}; };
     void run() {
         for (;;) {
             Job j;
@@ -187,12 +203,12 @@ private:
             const double t0 = now_s();
             Done d; TextBuf *m[3] = {nullptr, nullptr, nullptr};
             for (int k = 0; k < 3; ++k) {
-                if (one_file_) { if (k == 0) d.buf[0].reset(new TextBuf()); m[k] = d.buf[0].get(); }
-                else if (fd_[k] >= 0) { d.buf[k].reset(new TextBuf()); m[k] = d.buf[k].get(); }
+                if (one_file_) { if (k == 0) { d.buf[0] = text_.get(); d.buf[0]->n = 0; } m[k] = d.buf[0].get(); }
+                else if (fd_[k] >= 0) { d.buf[k] = text_.get(); d.buf[k]->n = 0; m[k] = d.buf[k].get(); }
             }
             uint64_t nvar;
             { ExtractWriter w(o_, m); w.process_chunk(j.chrom, *j.ref, j.k.beg, j.k.end, j.part->data(), j.part->size()); nvar = w.n_variant_positions(); }
-            j.part.reset(); j.ref.reset();
+            calls_.put(std::move(j.part)); j.ref.reset();
             // Chunks finish out of order; file offsets are handed out strictly in chunk order (the analogue of the reference's
             // ordered output bins, extract.c:514-535), after which the bytes can land in any order: every thread writes the
             // chunks IT released, with pwrite, outside the lock.
@@ -213,7 +229,7 @@ private:
                 for (int k = 0; k < 3; ++k) if (w.buf[k]) {
                     const char *p = w.buf[k]->v.data(); size_t left = w.buf[k]->n; uint64_t at = w.at[k];
                     while (left) { ssize_t r = pwrite(fd_[k], p, left, (off_t) at); if (r <= 0) { ok = false; break; } p += r; left -= (size_t) r; at += (uint64_t) r; }
-                    w.buf[k].reset();
+                    text_.put(std::move(w.buf[k]));
                 }
             {
                 std::lock_guard<std::mutex> g(m_);
@@ -223,7 +239,8 @@ private:
             cv_.notify_all();
         }
     }
-    const ExtractOptions &o_; int fd_[3]; uint64_t off_[3]; bool one_file_ = false;
+    const ExtractOptions &o_; int fd_[3]; uint64_t off_[3]; bool one_file_ = false; uint64_t max_inflight_ = 32;
+    BufPool<TextBuf> text_; BufPool<CallVec> calls_;
     std::deque<Job> q_; std::map<uint64_t, Done> ready_; uint64_t next_seq_ = 0, next_assign_ = 0, written_ = 0, n_variant_ = 0;
     std::mutex m_; std::condition_variable cv_; bool stop_ = false, failed_ = false; double busy_s_ = 0, write_s_ = 0;
     std::vector<std::thread> th_;
@@ -413,15 +430,14 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
     std::vector<ContigJob> jobs = contig_jobs(all, c0, c1);
     const std::string *ref = nullptr; bool loaded = false;
     std::vector<md_call> calls; size_t calls_head = 0, next_chunk = 0;
-    PodVec<md_call> tile_calls;
+    PodVec<md_call> tile_calls; md_call *pin_calls = nullptr; uint64_t pin_cap = 0;
     auto absorb = [&](const ContigJob &J, uint32_t done_upto, bool last) {
         while (next_chunk < J.chunks.size() && (J.chunks[next_chunk].end <= done_upto || last)) {
             const Chunk k = J.chunks[next_chunk];
             size_t a = calls_head; while (a < calls.size() && calls[a].pos < k.beg) ++a;
             size_t b = a; while (b < calls.size() && calls[b].pos < k.end) ++b;
-            auto part = std::make_shared<std::vector<md_call>>(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b);
             const char *cname = d.hdr->names[J.tid].c_str();
-            if (!d.chunk_skipped(k)) out_thread.post(cname, d.shared_ref(), k, part);
+            if (!d.chunk_skipped(k)) { std::unique_ptr<CallVec> part = out_thread.call_buffer(); part->assign(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b); out_thread.post(cname, d.shared_ref(), k, std::move(part)); }
             calls_head = b; ++next_chunk;
         }
         if (calls_head > (1u << 20)) { calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
@@ -445,13 +461,20 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
             if (!loaded) { if (be->load_contig(d.dev, (int32_t) J.tid, ref->data(), (uint32_t) ref->size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; } if (d.push_bed(J.tid)) return -20; loaded = true; }
             md_tile_desc t = td; if (t.end > ref->size()) t.end = (uint32_t) ref->size(); if (t.beg > t.end) t.beg = t.end;
             const uint64_t cap = (uint64_t)(t.end - t.beg) + 16;
-            tile_calls.clear(); tile_calls.grow(cap);
+            // the records come back into page-locked memory when the back end offers it (a pageable target halves the D2H rate and
+            // makes the copy synchronous); the buffer only ever grows
+            md_call *dst = nullptr;
+            if (be->pinned_alloc && be->pinned_free) {
+                if (cap > pin_cap) { if (pin_calls) be->pinned_free(pin_calls); pin_cap = cap + cap / 4; pin_calls = (md_call *) be->pinned_alloc(pin_cap * sizeof(md_call)); if (!pin_calls) pin_cap = 0; }
+                dst = pin_calls;
+            }
+            if (!dst) { tile_calls.clear(); tile_calls.grow(cap); dst = tile_calls.data(); }
             md_tile_stats st;
             double t0 = now_s();
-            int r = be->bam_extract_run(bs, run, &t, J.rend, tile_calls.data(), cap, &st);
+            int r = be->bam_extract_run(bs, run, &t, J.rend, dst, cap, &st);
             g_stats.t_device_s += now_s() - t0;
             if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
-            calls.insert(calls.end(), tile_calls.data(), tile_calls.data() + (ptrdiff_t) st.n_calls);
+            calls.insert(calls.end(), dst, dst + (ptrdiff_t) st.n_calls);
             g_stats.n_calls += st.n_calls; g_stats.n_tiles++;
         }
         absorb(J, td.end, false);
@@ -465,6 +488,7 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
     };
     int rc = drive_segments(d, be, bs, bamName, jobs, open_contig, tile, close_contig);
     be->bam_close(bs);
+    if (pin_calls) be->pinned_free(pin_calls);
     return rc;
 }
 
@@ -752,9 +776,8 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
                     const Chunk k = chunks[next_chunk];
                     size_t a = calls_head; while (a < calls.size() && calls[a].pos < k.beg) ++a;
                     size_t b = a; while (b < calls.size() && calls[b].pos < k.end) ++b;
-                    auto part = std::make_shared<std::vector<md_call>>(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b);
                     const char *cname = d.hdr->names[tid].c_str();
-                    if (!d.chunk_skipped(k)) out_thread.post(cname, d.shared_ref(), k, part);
+                    if (!d.chunk_skipped(k)) { std::unique_ptr<CallVec> part = out_thread.call_buffer(); part->assign(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b); out_thread.post(cname, d.shared_ref(), k, std::move(part)); }
                     calls_head = b; ++next_chunk;
                 }
                 if (calls_head > (1u << 20)) { calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
@@ -823,6 +846,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     out_thread.drain();
     if (out_thread.failed()) { fprintf(stderr, "Couldn't write the output file(s)! Disk full?\n"); if (rc == 0) rc = -3; }
     g_stats.t_format_s = out_thread.busy_seconds();
+    if (g_marks) fprintf(stderr, "[md-timing] text stage: formatting %.3f s, pwrite %.3f s (summed over its threads)\n", out_thread.busy_seconds(), out_thread.write_seconds());
     if (g_marks) fprintf(stderr, "[md-timing] calling thread: phred packing %.3f, contig load %.3f, call hand-over %.3f, writer drain %.3f, result buffer %.3f\n", g_acc[0], g_acc[1], g_acc[2], g_acc[3], g_acc[4]);
     if (g_marks && d.bam) fprintf(stderr, "[md-timing] record chains: %zu jobs adopted from the inflating worker, %zu walked by the stitcher\n", d.bam->jobs_adopted(), d.bam->jobs_walked());
     be->destroy(d.dev);
