@@ -23,8 +23,10 @@
 
 #if defined(__CUDACC__)
 #define MD_HD __host__ __device__ __forceinline__
+#define MD_HD_COLD __host__ __device__ __noinline__      /* rare paths: kept out of the hot loop's instruction stream */
 #else
 #define MD_HD inline
+#define MD_HD_COLD inline
 #endif
 #if defined(__CUDA_ARCH__)
 #define MD_SYNCWARP() __syncwarp()
@@ -112,14 +114,19 @@ MD_HD void br_init(BitReader &b, const void *base_aligned, uint64_t byte_off, ui
     br_wait_chunks();
 #endif
 }
+#if defined(__CUDA_ARCH__)
+// entering a new chunk: it was requested a whole chunk ago; the chunk before it is used up, its half of the ring takes the next one
+__device__ __noinline__ uint32_t br_next_chunk(const uint32_t *words, uint32_t *ring, uint32_t end_word, uint32_t nci, int lane) {
+    BitReader t; t.words = words; t.ring = ring; t.end_word = end_word; t.lane = lane;
+    br_wait_chunks();
+    br_issue_chunk(t, nci);
+    return nci + 1u;
+}
+#endif
 // word i of the stream for the refill
 MD_HD uint32_t br_fetch(BitReader &b, uint32_t i) {
 #if defined(__CUDA_ARCH__)
-    if ((i & (IN_CHUNK - 1u)) == 0u && i / IN_CHUNK + 1u == b.nci) {
-        // entering chunk i / IN_CHUNK: it was requested a whole chunk ago; the chunk before it is used up, its half takes the next one
-        br_wait_chunks();
-        br_issue_chunk(b, b.nci); ++b.nci;
-    }
+    if ((i & (IN_CHUNK - 1u)) == 0u && i / IN_CHUNK + 1u == b.nci) b.nci = br_next_chunk(b.words, b.ring, b.end_word, b.nci, b.lane);
     return b.ring[i & (IN_WORDS - 1u)];
 #else
     return br_word(b, i);
@@ -207,20 +214,21 @@ MD_HD bool build_table(Decoder &D, const uint8_t *lens, int n, uint32_t *primary
 }
 
 // A code longer than the primary table: canonical decode by limits.  With the next 15 bits taken MSB first (x), the code's
-// length is the first l with x < limit[l]; its symbol is sorted[off[l] + (x >> (15 - l))].  Consumes the code's bits.
-MD_HD int decode_slow(BitReader &b, const uint16_t *sorted, const uint32_t *limit, const int32_t *offv, int root) {
-    const uint32_t x = bit_reverse(br_peek(b) & 0x7fffu, 15);
+// length is the first l with x < limit[l]; its symbol is sorted[off[l] + (x >> (15 - l))].  `bits` = the next bits of the stream;
+// returns symbol | code length << 16 (the caller drops the bits), or -1.
+MD_HD_COLD int decode_slow(uint32_t bits, const uint16_t *sorted, const uint32_t *limit, const int32_t *offv, int root) {
+    const uint32_t x = bit_reverse(bits & 0x7fffu, 15);
 #if defined(__CUDA_ARCH__)
     #pragma unroll 1
 #endif
     for (int l = root + 1; l < 16; ++l) {
-        if (x < limit[l]) { br_drop(b, (uint32_t) l); return sorted[offv[l] + (int32_t)(x >> (15 - l))]; }
+        if (x < limit[l]) return (int) sorted[offv[l] + (int32_t)(x >> (15 - l))] | (l << 16);
     }
     return -1;
 }
 
 // ring -> global: bytes [lo, hi) of the output (addresses relative to the 16-byte aligned `outb`)
-MD_HD void flush_ring(const Decoder &D, uint8_t *outb, uint32_t lo, uint32_t hi, int lane, int nl) {
+MD_HD_COLD void flush_ring(const Decoder &D, uint8_t *outb, uint32_t lo, uint32_t hi, int lane, int nl) {
     MD_SYNCWARP();                                       // everything below `hi` has been stored
     if (hi <= lo) return;
     const uint32_t lo16 = (lo + 15u) & ~15u, hi16 = hi & ~15u;
@@ -328,9 +336,10 @@ MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_l
                 uint32_t bits = br_peek(b);
                 uint32_t e = D.lit[bits & ((1u << LIT_ROOT) - 1u)];
                 if (!(e & 15u)) {                                 // a code longer than the primary table
-                    const int sym = decode_slow(b, D.lit_sorted, D.lit_limit, D.lit_off, LIT_ROOT);
+                    const int sym = decode_slow(bits, D.lit_sorted, D.lit_limit, D.lit_off, LIT_ROOT);
                     if (sym < 0) return -3;
-                    e = lit_entry((uint32_t) sym, 0u);
+                    br_drop(b, (uint32_t) sym >> 16);
+                    e = lit_entry((uint32_t) sym & 0xffffu, 0u);
                     if ((e & 0x300u) == 0x300u) return -3;
                     bits = br_peek(b);
                 }
@@ -342,9 +351,10 @@ MD_HD int inflate_block(const void *base_aligned, uint64_t in_off, uint64_t in_l
                     uint32_t d = D.dist[(bits >> used) & ((1u << DIST_ROOT) - 1u)];
                     if (!(d & 15u)) {
                         br_drop(b, used); used = 0;
-                        const int ds = decode_slow(b, D.dist_sorted, D.dist_limit, D.dist_off, DIST_ROOT);
+                        const int ds = decode_slow(br_peek(b), D.dist_sorted, D.dist_limit, D.dist_off, DIST_ROOT);
                         if (ds < 0) return -3;
-                        d = dist_entry((uint32_t) ds, 0u);
+                        br_drop(b, (uint32_t) ds >> 16);
+                        d = dist_entry((uint32_t) ds & 0xffffu, 0u);
                         if (d & 0x300u) return -3;
                         bits = br_peek(b);
                     }

@@ -222,7 +222,7 @@ done:
     return __fdiv_rn((float) nU, (float)(nM + nU));
 }
 
-__global__ void __launch_bounds__(256) prep_kernel(DevReads R, KParams P, int32_t *rend, uint8_t *info, HashTab T, int32_t *mate, uint32_t *counters,
+__global__ void __launch_bounds__(256, 8) prep_kernel(DevReads R, KParams P, int32_t *rend, uint8_t *info, HashTab T, int32_t *mate, uint32_t *counters,
                                                    const unsigned char *ref, uint32_t ce_beg, uint32_t ce_end, BedView B) {
     // grid-stride over the alignments; the five tile-wide statistics are reduced per thread, then per CTA, so the
     // global counters see one atomic per CTA instead of one per warp (same-address L2 atomics serialise)
