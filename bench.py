@@ -591,6 +591,8 @@ def run_big(args, rank, local_rank, world, cores):
     calls = grp.sumr(float(tot.calls)); cig = grp.sumr(float(tot.cigar_ops))
     comp = grp.sumr(float(tot.comp_bytes)); infl_b = grp.sumr(float(tot.inflated_bytes))
     c_ms_max = grp.maxr(c_ms / steps); infl_ms_max = grp.maxr(infl_ms / steps); p_ms_max = grp.maxr(p_ms / steps)
+    h2d_rate = tot.comp_bytes / (tot.push_h2d_ms * 1e-3) / 1e9 if tot.push_h2d_ms else 0.0      # this rank's segment copies (page-locked staging -> HBM)
+    h2d_min = -grp.maxr(-h2d_rate); h2d_max = grp.maxr(h2d_rate)
     if rank != 0:
         grp.close()
         return 0
@@ -605,6 +607,7 @@ def run_big(args, rank, local_rank, world, cores):
                 "algorithmic_bytes_per_step": int(alg), "kernel_ms_per_step": round(c_ms_max, 3), "launches_of_kernel_per_step": int(tot.tiles), "prep_ms_per_step": round(p_ms_max, 3),
                 "traffic": traffic, "traffic_source": traffic_src,
                 "note": "summed over the %d tiles of one pass (CUDA events around every tile's kernels); traffic is per launch of a typical tile" % tot.tiles}
+    h2d = {"GBps_slowest_rank": round(h2d_min, 1), "GBps_fastest_rank": round(h2d_max, 1), "what": "compressed segments, page-locked staging buffers -> HBM, CUDA events on the decode stream"}
     inflate = {"kernel": "inflate_kernel", "ms_per_step": round(infl_ms_max, 2), "compressed_GBps": round(comp / world / (infl_ms_max * 1e-3) / 1e9, 2) if infl_ms_max else None,
                "inflated_GBps": round(infl_b / world / (infl_ms_max * 1e-3) / 1e9, 2) if infl_ms_max else None}
 
@@ -656,7 +659,7 @@ def run_big(args, rank, local_rank, world, cores):
                    "d2h_bytes_per_step": int(calls * 16) if sub == "extract" else 4 * 2 * 1024 * 2 * 4,
                    "path": "%s_main(argv) of lib/libMethylDackel.so: BAM + FASTA files in -> device-side BGZF inflate + decode -> prep/count kernels -> %s" % (
                        sub, "md_call records -> host formatter -> bedGraph files (in %s)" % out_dir() if sub == "extract" else "histogram -> --txt table")},
-           "gpu_launches": launches, "roofline": roofline, "inflate": inflate, "clocks": sampler.summary(), "calls_per_step": int(calls), "tiles_per_step": int(tot.tiles)}
+           "gpu_launches": launches, "roofline": roofline, "inflate": inflate, "segment_h2d": h2d, "clocks": sampler.summary(), "calls_per_step": int(calls), "tiles_per_step": int(tot.tiles)}
     if cli is not None:
         out["cli_from_bam"] = cli
     if parity is not None:
