@@ -173,7 +173,7 @@ def load_gpu():
     """libmdgpu.so: the CUDA library. Fails loudly if it has not been built — there is no CPU fallback."""
     global _gpu
     if _gpu is None:
-        p = os.path.join(LIBDIR, "libmdgpu.so")
+        p = os.environ.get("MD_LIBMDGPU") or os.path.join(LIBDIR, "libmdgpu.so")      # MD_LIBMDGPU: an experimental build of the same ABI (A/B runs)
         if not os.path.exists(p):
             raise RuntimeError("%s is missing: the CUDA extension must be built (make -C methyldackel_b200/csrc gpu); there is no CPU fallback" % p)
         g = C.CDLL(p, mode=C.RTLD_GLOBAL)

@@ -368,13 +368,15 @@ int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamNa
     bool have_cur = next_segment(0);
     bool pushed = false;
     if (have_cur && overlapped) { if (be->bam_push_begin(bs, base[0], bytes[0], blk[0].data(), (uint32_t) blk[0].size(), skip) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; } pushed = true; }
-    bool done = false;
+    bool done = false; size_t n_seg = 0;
     while (have_cur && !done && rc == 0) {
         double t0 = now_s();
         md_bam_summary sum;
         int r = overlapped ? be->bam_push_end(bs, &sum) : be->bam_push(bs, base[cur], bytes[cur], blk[cur].data(), (uint32_t) blk[cur].size(), skip, &sum);
         pushed = false; skip = 0;
         g_stats.t_decode_s += now_s() - t0;
+        if (g_marks && (n_seg < 4 || n_seg % 10 == 0)) { char m[64]; snprintf(m, sizeof m, "segment %zu decoded", n_seg); mark(m); }
+        ++n_seg;
         if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
         // cut the next segment now: whether the file ends here decides how this segment's last run is closed
         const int nxt = cur ^ 1;
@@ -437,14 +439,14 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
             size_t a = calls_head; while (a < calls.size() && calls[a].pos < k.beg) ++a;
             size_t b = a; while (b < calls.size() && calls[b].pos < k.end) ++b;
             const char *cname = d.hdr->names[J.tid].c_str();
-            if (!d.chunk_skipped(k)) { std::unique_ptr<CallVec> part = out_thread.call_buffer(); part->assign(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b); out_thread.post(cname, d.shared_ref(), k, std::move(part)); }
+            if (!d.chunk_skipped(k)) { std::unique_ptr<CallVec> part; { Acc a_(2); part = out_thread.call_buffer(); part->assign(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b); } { Acc a_(3); out_thread.post(cname, d.shared_ref(), k, std::move(part)); } }
             calls_head = b; ++next_chunk;
         }
-        if (calls_head > (1u << 20)) { calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
+        if (calls_head > (1u << 20)) { Acc a_(4); calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
     };
     size_t job_i = 0;
     auto open_contig = [&](const ContigJob &J) -> int {
-        ref = d.fetch(J.tid);
+        { Acc a_(1); ref = d.fetch(J.tid); }
         while (job_i < jobs.size() && jobs[job_i].tid != J.tid) ++job_i;
         if (job_i + 1 < jobs.size()) d.prefetch(jobs[job_i + 1].tid);
         calls.clear(); calls_head = 0; next_chunk = 0; loaded = false;
@@ -474,7 +476,7 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
             int r = be->bam_extract_run(bs, run, &t, J.rend, dst, cap, &st);
             g_stats.t_device_s += now_s() - t0;
             if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
-            calls.insert(calls.end(), dst, dst + (ptrdiff_t) st.n_calls);
+            { Acc a_(0); calls.insert(calls.end(), dst, dst + (ptrdiff_t) st.n_calls); }
             g_stats.n_calls += st.n_calls; g_stats.n_tiles++;
         }
         absorb(J, td.end, false);
@@ -847,7 +849,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     if (out_thread.failed()) { fprintf(stderr, "Couldn't write the output file(s)! Disk full?\n"); if (rc == 0) rc = -3; }
     g_stats.t_format_s = out_thread.busy_seconds();
     if (g_marks) fprintf(stderr, "[md-timing] text stage: formatting %.3f s, pwrite %.3f s (summed over its threads)\n", out_thread.busy_seconds(), out_thread.write_seconds());
-    if (g_marks) fprintf(stderr, "[md-timing] calling thread: phred packing %.3f, contig load %.3f, call hand-over %.3f, writer drain %.3f, result buffer %.3f\n", g_acc[0], g_acc[1], g_acc[2], g_acc[3], g_acc[4]);
+    if (g_marks) fprintf(stderr, "[md-timing] calling thread: record append / phred packing %.3f, contig load %.3f, chunk copy %.3f, waiting for the text stage %.3f, buffer upkeep %.3f\n", g_acc[0], g_acc[1], g_acc[2], g_acc[3], g_acc[4]);
     if (g_marks && d.bam) fprintf(stderr, "[md-timing] record chains: %zu jobs adopted from the inflating worker, %zu walked by the stitcher\n", d.bam->jobs_adopted(), d.bam->jobs_walked());
     be->destroy(d.dev);
     mark("device destroyed");
