@@ -28,9 +28,9 @@ using mdbam::BlockScan; using mdbam::TileSrc; using mdbam::TileDst; using mdbam:
 // slow block never holds finished warps hostage.  Deflate decoding is a serial bit-stream walk; all 32 lanes run it
 // redundantly (see inflate_hd.h) and share out the match copies and the flushes of the ring to global memory.
 #ifndef MD_INFLATE_WARPS
-#define MD_INFLATE_WARPS 7
+#define MD_INFLATE_WARPS 8
 #endif
-constexpr int INF_WARPS = MD_INFLATE_WARPS, INF_CTAS_PER_SM = 4;  // 28 warps per SM: 7 KB of shared memory each (4 KB ring)
+constexpr int INF_WARPS = MD_INFLATE_WARPS, INF_CTAS_PER_SM = 4;  // 32 warps per SM: 5.25 KB of shared memory each (2 KB ring), 64 registers per thread
 constexpr size_t INF_SMEM = INF_WARPS * sizeof(mdinflate::Decoder);
 static_assert(INF_CTAS_PER_SM * (INF_SMEM + 1024) <= 228 * 1024, "inflate_kernel: decoders do not fit the SM's shared memory");
 __global__ void __launch_bounds__(INF_WARPS * 32, INF_CTAS_PER_SM) inflate_kernel(const uint8_t *comp, const md_bgzf_block *blk, const unsigned long long *uoff, uint8_t *ubuf, uint32_t n_blocks, int *err, uint32_t *ticket) {

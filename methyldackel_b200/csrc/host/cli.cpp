@@ -350,13 +350,13 @@ int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamNa
     const bool overlapped = be->bam_push_begin && be->bam_push_end;
     std::vector<md_bgzf_block> blk[2]; int cur = 0;
     const uint8_t *base[2] = {nullptr, nullptr}; size_t bytes[2] = {0, 0};
-    // large files go through page-locked staging buffers filled by a background thread (StagedSegments); small ones are
+    // large files go through page-locked staging buffers filled by a background reader (StagedSegments); small ones are
     // pushed straight from the file mapping (allocating the buffers would cost more than it saves)
     std::unique_ptr<StagedSegments> staged;
     {
         const char *e = getenv("MD_STAGE");
         const bool want = e ? e[0] != '0' : seg.remaining() >= ((size_t) 512 << 20);
-        if (want && be->pinned_alloc && be->pinned_free) { staged.reset(new StagedSegments(seg, target, be->pinned_alloc, be->pinned_free)); if (!staged->staged()) staged.reset(); }
+        if (want && be->pinned_alloc && be->pinned_free) { staged.reset(new StagedSegments(bamName, seg.tell(), target, be->pinned_alloc, be->pinned_free)); if (!staged->staged()) staged.reset(); }
     }
     auto next_segment = [&](int slot) -> bool {
         if (!staged) return seg.next(target, base[slot], bytes[slot], blk[slot]);

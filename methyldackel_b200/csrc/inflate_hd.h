@@ -11,7 +11,7 @@
 //   * The bit-stream walk is serial, so all 32 lanes run it REDUNDANTLY — identical control flow and register state, the warp
 //     never diverges and the walk costs what one lane would cost.  What the lanes share out is the data movement.
 //   * Output goes into a ring of the last WIN bytes in SHARED memory.  A match whose source lies inside the ring (distance
-//     <= WIN - 264: 93 % of the matches of a level-1 BAM, more at higher levels) is a shared-memory load + store by `len`
+//     <= WIN - 264) is a shared-memory load + store by `len`
 //     lanes at once; only the far ones read global memory, from bytes that were flushed long before.
 //   * Every FLUSH bytes the finished part of the ring is written to global memory by all lanes with 16-byte stores.
 //   * Decoding tables hold 32-bit entries with everything a symbol needs (code length, extra-bit count, base value, kind),
@@ -39,18 +39,19 @@
 namespace mdinflate {
 
 #ifndef MD_INFLATE_WIN
-#define MD_INFLATE_WIN 4096
+#define MD_INFLATE_WIN 2048
 #endif
 // Sizes are chosen for occupancy: the walk is one long dependency chain (measured: ~7 cycles from one issued instruction of
 // a warp to its next), so throughput grows with the number of resident warps until the schedulers saturate at ~7 warps each.
-// 8-bit / 6-bit primary tables cover 94 % / 97 % of the codes of a BAM stream; a 4 KB ring holds the source of 5 matches in 6.
+// 8-bit / 6-bit primary tables cover 94 % / 97 % of the codes of a BAM stream; a 2 KB ring holds the source of 3 matches in 4
+// (measured on the config[1] file: 32 warps per SM with a 2 KB ring beat 28 with 4 KB by 6 %, and 15 with 8 KB by 13 %).
 enum { LIT_ROOT = 8, DIST_ROOT = 6, CL_ROOT = 7, WIN = MD_INFLATE_WIN, WMASK = WIN - 1, FLUSH = WIN / 4, NEAR = WIN - 264,
        IN_CHUNK = 64, IN_WORDS = 2 * IN_CHUNK };   // device: the compressed stream is staged through a ring of two 256-byte chunks
 
 // entry layout (lit/len and distance tables): bits 0-3 code length (0: not in the primary table), bits 4-7 number of extra
 // bits, bits 8-9 kind (0 literal / distance, 1 length, 2 end of block, 3 invalid symbol: never stored in a primary table, so the
 // hot loop does not test for it), bits 16-31 literal byte or base value
-struct Decoder {                         // one per warp; shared memory on the device (7 KB with a 4 KB ring)
+struct Decoder {                         // one per warp; shared memory on the device (5.25 KB with a 2 KB ring)
     uint32_t lit[1 << LIT_ROOT];
     uint32_t dist[1 << CL_ROOT];         // distance table (1 << DIST_ROOT entries used); holds the code-length alphabet's table while a dynamic header is read
     uint16_t lit_sorted[288], dist_sorted[32];   // symbols ordered by (length, symbol): canonical walk for codes beyond the primary table

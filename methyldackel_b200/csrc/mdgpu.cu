@@ -881,12 +881,12 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
                 uint32_t qa = 0, qb2 = 0;
                 const bool has_mate = rc.mi >= 0;
                 const int mrel0 = has_mate ? rc.mpos - w0i : 0, mrel1 = has_mate ? rc.mend - w0i : 0;
-                uint32_t j0 = 0, j1 = 0, j2 = 0, j3 = 0;                 // list indices of the current op: [j0, j1) before the mate, [j1, j2) inside, [j2, j3) beyond
-                uint32_t jc = 0, je = 0; int ph = 3;   // cursor and end of the current phase's index range
+                // cursors into the site list for the current match op: plain candidates [a1, b1) (before the mate's span) and [a2, b2)
+                // (beyond it), in-mate-span candidates [m1, m2); a round takes from all three, so one round per op is the rule
+                uint32_t a1 = 0, b1 = 0, m1 = 0, m2 = 0, a2 = 0, b2 = 0;
                 if (A.ablate & 2u) done = true;
                 for (;;) {
-                    while (!done && jc >= je) {
-                        if (ph < 2) { ++ph; jc = ph == 1 ? j1 : j2; je = ph == 1 ? j2 : j3; continue; }
+                    while (!done && a1 >= b1 && m1 >= m2 && a2 >= b2) {
                         if (k >= k1) { done = true; break; }
                         const uint32_t c = (k == k0) ? c0 : __ldg(R.cigar + k), op = c & 15u; const int len = (int)(c >> 4);
                         ++k;
@@ -895,32 +895,36 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 3) count_warp(CountArgs A) {
                             if (bnd > a) {
                                 const int ra = a - w0i, rb = bnd - w0i;
                                 qrel = q - (p - w0i);
-                                j0 = rank(ra); j3 = rank(rb);
-                                if (has_mate) { j1 = rank(min(max(mrel0, ra), rb)); j2 = rank(min(max(mrel1, ra), rb)); }
-                                else { j1 = j3; j2 = j3; }
-                                ph = 0; jc = j0; je = j1;
+                                a1 = rank(ra); b2 = rank(rb);
+                                if (has_mate) { b1 = rank(min(max(mrel0, ra), rb)); a2 = rank(min(max(mrel1, ra), rb)); }
+                                else { b1 = b2; a2 = b2; }
+                                m1 = b1; m2 = a2;
                             }
                             p += len; q += len;
                         } else if (op == 1 || op == 4) q += len;
                         else if (op == 2 || op == 3) p += len;
                     }
-                    const bool busy = jc < je;
+                    const uint32_t lA1 = b1 - a1, lA = lA1 + (b2 - a2), lB = m2 - m1;
+                    const bool busy = (lA | lB) != 0u;
                     const bool all_done = !__any_sync(0xffffffffu, busy);     // every lane ran out of match ops: the batch is exhausted
-                    const bool tB = ph == 1;
                     const uint32_t room = WS_QUEUE - qa - qb2, cap = room >> 5;   // the queues are drained below 64 entries each: cap >= 10
-                    const uint32_t n = busy ? min(je - jc, cap) : 0u;
-                    const uint32_t v = tB ? (n << 16) : n;
+                    const uint32_t nB = min(lB, cap >> 1), nA = min(lA, cap - nB);
+                    const uint32_t v = nA | (nB << 16);
                     uint32_t inc = v;
                     #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
                     const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
-                    if (n) {
-                        const uint32_t ex = inc - v;
-                        uint32_t *dst = tB ? queue + (WS_QUEUE - 1u - (qb2 + (ex >> 16))) : queue + (qa + (ex & 0xffffu));
-                        const int dir = tB ? -1 : 1;
-                        const uint32_t base = (uint32_t) lane + ((uint32_t) qrel << 17);
-                        for (uint32_t r = 0; r < n; ++r) { *dst = base + (uint32_t) lst[jc + r] * 0x20020u; dst += dir; }
-                        jc += n;
+                    const uint32_t ex = inc - v;
+                    const uint32_t base = (uint32_t) lane + ((uint32_t) qrel << 17);
+                    if (nA) {
+                        uint32_t *dst = queue + (qa + (ex & 0xffffu));
+                        for (uint32_t r = 0; r < nA; ++r) { const uint32_t jj = r < lA1 ? a1 + r : a2 + (r - lA1); dst[r] = base + (uint32_t) lst[jj] * 0x20020u; }
+                        const uint32_t t1 = min(nA, lA1); a1 += t1; a2 += nA - t1;
+                    }
+                    if (nB) {
+                        uint32_t *dst = queue + (WS_QUEUE - 1u - (qb2 + (ex >> 16)));
+                        for (uint32_t r = 0; r < nB; ++r) *(dst - r) = base + (uint32_t) lst[m1 + r] * 0x20020u;
+                        m1 += nB;
                     }
                     qa += tot & 0xffffu; qb2 += tot >> 16;
                     __syncwarp();

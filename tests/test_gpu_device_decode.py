@@ -175,3 +175,15 @@ def test_cli_device_decode_mbias(built, synth, seg):
     n = subprocess.run([NEW_BIN, "mbias"] + opts + [p + ".fa", p + ".bam"], capture_output=True, text=True, env=dict(os.environ, MD_DEVICE_DECODE="1", MD_SEGMENT_BYTES=seg))
     assert r.returncode == 0 and n.returncode == 0, (r.stderr, n.stderr)
     assert n.stdout == r.stdout and len(r.stdout.splitlines()) > 50
+
+
+@pytest.mark.parametrize("seg", ["1", "70000", "3000000"], ids=["block_per_segment", "70kB_segments", "3MB_segments"])
+def test_cli_device_decode_through_staging_buffers(built, synth, tmp_path, seg):
+    """large files reach the device through page-locked staging buffers filled by a background reader (StagedSegments, forced
+    here with MD_STAGE=1): same bytes out, whatever the segment size, with regions (index seek) and several contigs"""
+    p = synth("stage", "--contigs", "chr1:400000,chr2:150000,chr3:30000", "--depth", "25", "--read-seed", "12")
+    for opts in (["--CHG", "--CHH", "--mergeContext"], ["-r", "chr2:20000-90000", "--CHG"], ["-r", "chr3"]):
+        assert _cli_both(built, tmp_path, opts, p + ".fa", p + ".bam", {"MD_SEGMENT_BYTES": seg, "MD_STAGE": "1"}) == []
+    r = subprocess.run([built["ref_bin"], "mbias", "--noSVG", "--CHG", p + ".fa", p + ".bam"], capture_output=True, text=True)
+    n = subprocess.run([NEW_BIN, "mbias", "--noSVG", "--CHG", p + ".fa", p + ".bam"], capture_output=True, text=True, env=dict(os.environ, MD_SEGMENT_BYTES=seg, MD_STAGE="1"))
+    assert r.returncode == 0 and n.returncode == 0 and n.stdout == r.stdout and len(r.stdout) > 1000
