@@ -431,25 +431,31 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
     if (!bs) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
     std::vector<ContigJob> jobs = contig_jobs(all, c0, c1);
     const std::string *ref = nullptr; bool loaded = false;
-    std::vector<md_call> calls; size_t calls_head = 0, next_chunk = 0;
+    size_t next_chunk = 0;
     PodVec<md_call> tile_calls; md_call *pin_calls = nullptr; uint64_t pin_cap = 0;
-    auto absorb = [&](const ContigJob &J, uint32_t done_upto, bool last) {
-        while (next_chunk < J.chunks.size() && (J.chunks[next_chunk].end <= done_upto || last)) {
+    // The records of a tile go straight from the read-back buffer into the vectors of the reference chunks they belong to (one
+    // copy, located by binary search; a chunk that straddles a tile cut keeps collecting in `pending`), and every chunk that is
+    // complete — its end lies at or before `done_upto`, or the contig is being closed — is handed to the text stage.
+    std::unique_ptr<CallVec> pending;
+    auto feed = [&](const ContigJob &J, const md_call *rec, size_t n, uint32_t done_upto, bool last) {
+        const char *cname = d.hdr->names[J.tid].c_str();
+        size_t i = 0;
+        while (next_chunk < J.chunks.size()) {
             const Chunk k = J.chunks[next_chunk];
-            size_t a = calls_head; while (a < calls.size() && calls[a].pos < k.beg) ++a;
-            size_t b = a; while (b < calls.size() && calls[b].pos < k.end) ++b;
-            const char *cname = d.hdr->names[J.tid].c_str();
-            if (!d.chunk_skipped(k)) { std::unique_ptr<CallVec> part; { Acc a_(2); part = out_thread.call_buffer(); part->assign(calls.begin() + (ptrdiff_t) a, calls.begin() + (ptrdiff_t) b); } { Acc a_(3); out_thread.post(cname, d.shared_ref(), k, std::move(part)); } }
-            calls_head = b; ++next_chunk;
+            const md_call *e = std::lower_bound(rec + i, rec + n, k.end, [](const md_call &c, uint32_t v) { return c.pos < v; });
+            if (e != rec + i) { Acc a_(2); if (!pending) pending = out_thread.call_buffer(); pending->insert(pending->end(), rec + i, e); i = (size_t)(e - rec); }
+            if (!(k.end <= done_upto || last)) break;                       // the chunk continues in the next tile
+            if (!pending) pending = out_thread.call_buffer();
+            if (!d.chunk_skipped(k)) { Acc a_(3); out_thread.post(cname, d.shared_ref(), k, std::move(pending)); }
+            pending.reset(); ++next_chunk;
         }
-        if (calls_head > (1u << 20)) { Acc a_(4); calls.erase(calls.begin(), calls.begin() + (ptrdiff_t) calls_head); calls_head = 0; }
     };
     size_t job_i = 0;
     auto open_contig = [&](const ContigJob &J) -> int {
         { Acc a_(1); ref = d.fetch(J.tid); }
         while (job_i < jobs.size() && jobs[job_i].tid != J.tid) ++job_i;
         if (job_i + 1 < jobs.size()) d.prefetch(jobs[job_i + 1].tid);
-        calls.clear(); calls_head = 0; next_chunk = 0; loaded = false;
+        pending.reset(); next_chunk = 0; loaded = false;
         if (!ref) {
             fprintf(stderr, "faidx_fetch_seq returned %i while trying to fetch the sequence for tid %s:%" PRIu32 "-%" PRIu32 "!\n", -2, d.hdr->names[J.tid].c_str(), J.chunks.front().beg, J.chunks.front().end);
             fprintf(stderr, "Note that the output will be truncated!\n");
@@ -459,6 +465,7 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
     };
     auto tile = [&](const ContigJob &J, int run, const md_tile_desc &td, bool on_device) -> int {
         if (!ref) return 0;
+        const md_call *got = nullptr; size_t n_got = 0;
         if (on_device) {
             if (!loaded) { if (be->load_contig(d.dev, (int32_t) J.tid, ref->data(), (uint32_t) ref->size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; } if (d.push_bed(J.tid)) return -20; loaded = true; }
             md_tile_desc t = td; if (t.end > ref->size()) t.end = (uint32_t) ref->size(); if (t.beg > t.end) t.beg = t.end;
@@ -476,14 +483,14 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
             int r = be->bam_extract_run(bs, run, &t, J.rend, dst, cap, &st);
             g_stats.t_device_s += now_s() - t0;
             if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; }
-            { Acc a_(0); calls.insert(calls.end(), dst, dst + (ptrdiff_t) st.n_calls); }
+            got = dst; n_got = (size_t) st.n_calls;
             g_stats.n_calls += st.n_calls; g_stats.n_tiles++;
         }
-        absorb(J, td.end, false);
+        feed(J, got, n_got, td.end, false);
         return 0;
     };
     auto close_contig = [&](const ContigJob &J) -> int {
-        if (ref) absorb(J, J.rend, true);
+        if (ref) feed(J, nullptr, 0, J.rend, true);
         if (loaded) be->drop_contig(d.dev, (int32_t) J.tid);
         loaded = false;
         return 0;
