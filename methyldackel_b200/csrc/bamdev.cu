@@ -23,9 +23,8 @@
 namespace {
 using mdbam::BlockScan; using mdbam::TileSrc; using mdbam::TileDst; using mdbam::Sz4;
 
-// One warp per BGZF block at a time, INF_WARPS warps per CTA, INF_CTAS_PER_SM CTAs per SM; every warp owns a mdinflate::Decoder (tables + the
-// ring of its most recent output) in shared memory and pulls block numbers from a global ticket until none are left, so a
-// slow block never holds finished warps hostage.  Deflate decoding is a serial bit-stream walk; all 32 lanes run it
+// One warp per BGZF block, INF_WARPS warps per CTA, INF_CTAS_PER_SM CTAs per SM; every warp owns a mdinflate::Decoder (tables + the
+// ring of its most recent output) in shared memory.  Deflate decoding is a serial bit-stream walk; all 32 lanes run it
 // redundantly (see inflate_hd.h) and share out the match copies and the flushes of the ring to global memory.
 #ifndef MD_INFLATE_WARPS
 #define MD_INFLATE_WARPS 8
@@ -33,21 +32,18 @@ using mdbam::BlockScan; using mdbam::TileSrc; using mdbam::TileDst; using mdbam:
 constexpr int INF_WARPS = MD_INFLATE_WARPS, INF_CTAS_PER_SM = 4;  // 32 warps per SM: 5.25 KB of shared memory each (2 KB ring), 64 registers per thread
 constexpr size_t INF_SMEM = INF_WARPS * sizeof(mdinflate::Decoder);
 static_assert(INF_CTAS_PER_SM * (INF_SMEM + 1024) <= 228 * 1024, "inflate_kernel: decoders do not fit the SM's shared memory");
-__global__ void __launch_bounds__(INF_WARPS * 32, INF_CTAS_PER_SM) inflate_kernel(const uint8_t *comp, const md_bgzf_block *blk, const unsigned long long *uoff, uint8_t *ubuf, uint32_t n_blocks, int *err, uint32_t *ticket) {
+__global__ void __launch_bounds__(INF_WARPS * 32, INF_CTAS_PER_SM) inflate_kernel(const uint8_t *comp, const md_bgzf_block *blk, const unsigned long long *uoff, uint8_t *ubuf, uint32_t n_blocks, int *err) {
     extern __shared__ __align__(16) unsigned char inf_smem[];
     const int lane = (int)(threadIdx.x & 31);
     mdinflate::Decoder &D = ((mdinflate::Decoder *) inf_smem)[threadIdx.x >> 5];
-    for (;;) {
-        uint32_t b = 0;
-        if (lane == 0) b = atomicAdd(ticket, 1u);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= n_blocks) break;
-        const md_bgzf_block d = blk[b];
-        if (d.isize == 0) continue;
-        const int rc = mdinflate::inflate_block(comp, d.comp_off, d.comp_len, ubuf + uoff[b], d.isize, D, lane, 32);
-        if (rc && lane == 0) atomicCAS(err, 0, (int)((b << 4) | (uint32_t)(-rc)));
-        __syncwarp();
-    }
+    // one block per warp and the CTA retires: the decode stream has the lowest priority, so the slots that free up go to the
+    // count / prep kernels of the tile in flight first (persistent decoder CTAs would hold every SM until the segment is done)
+    const uint32_t b = blockIdx.x * INF_WARPS + (threadIdx.x >> 5);
+    if (b >= n_blocks) return;
+    const md_bgzf_block d = blk[b];
+    if (d.isize == 0) return;
+    const int rc = mdinflate::inflate_block(comp, d.comp_off, d.comp_len, ubuf + uoff[b], d.isize, D, lane, 32);
+    if (rc && lane == 0) atomicCAS(err, 0, (int)((b << 4) | (uint32_t)(-rc)));
 }
 __global__ void scan_blocks_kernel(const uint8_t *u, const unsigned long long *uoff, uint32_t n_blocks, unsigned long long first, unsigned long long U, int32_t n_targets, BlockScan *out) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,7 +127,8 @@ extern "C" md_bam_stream *md_bam_open(md_ctx *c, int32_t n_targets) {
     md_bam_stream *s = new md_bam_stream();
     s->c = c; s->n_targets = n_targets;
     cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) INF_SMEM);
-    bool ok = cudaStreamCreateWithFlags(&s->sd, cudaStreamNonBlocking) == cudaSuccess && cudaMallocHost((void **) &s->h_tot, 2 * sizeof(Sz4)) == cudaSuccess;
+    int prio_lo = 0, prio_hi = 0; cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);      // numerically: lowest priority, greatest priority
+    bool ok = cudaStreamCreateWithPriority(&s->sd, cudaStreamNonBlocking, prio_lo) == cudaSuccess && cudaMallocHost((void **) &s->h_tot, 2 * sizeof(Sz4)) == cudaSuccess;
     for (int k = 0; k < 2 && ok; ++k) ok = cudaMallocHost((void **) &s->slot[k].h_small, 64) == cudaSuccess && s->slot[k].small.reserve(256) == 0;
     if (!ok) { g_err = "md_bam_open: allocation failed"; delete s; return nullptr; }
     return s;
@@ -202,13 +199,12 @@ static int bam_push_impl(md_bam_stream *s, BamSlot &S, const BamSlot *P, const v
     PCK(cudaMemcpyAsync(S.blk.p, blocks, (size_t) n_blocks * sizeof(md_bgzf_block), cudaMemcpyHostToDevice, st));
     PCK(cudaMemcpyAsync(S.uoff.p, uoff.data(), (size_t)(n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
     PCK(cudaMemsetAsync(S.small.p, 0, 256, st));
-    uint32_t *d_small = (uint32_t *) S.small.p;       // [0] n_runs [1] err [2] bad [3] last_pos [4,5] final_exit [8] inflate ticket
+    uint32_t *d_small = (uint32_t *) S.small.p;       // [0] n_runs [1] err [2] bad [3] last_pos [4,5] final_exit
     const uint8_t *u = (const uint8_t *) S.ubuf.p;
     const unsigned long long first = D0 + (carry_in ? 0 : skip);
     tm.tick();
     if (n_blocks) {
-        const uint32_t inf_ctas = std::min<uint32_t>((n_blocks + INF_WARPS - 1) / INF_WARPS, 148u * INF_CTAS_PER_SM);
-        inflate_kernel<<<inf_ctas, INF_WARPS * 32, INF_SMEM, st>>>((const uint8_t *) S.comp.p, (const md_bgzf_block *) S.blk.p, (const unsigned long long *) S.uoff.p, (uint8_t *) S.ubuf.p, n_blocks, (int *)(d_small + 1), d_small + 8);
+        inflate_kernel<<<(n_blocks + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, INF_SMEM, st>>>((const uint8_t *) S.comp.p, (const md_bgzf_block *) S.blk.p, (const unsigned long long *) S.uoff.p, (uint8_t *) S.ubuf.p, n_blocks, (int *)(d_small + 1));
         tm.tick();
         const uint32_t g = (n_blocks + 127) / 128;
         // block 0's slice starts at D0 so that the straddling record is part of its chain

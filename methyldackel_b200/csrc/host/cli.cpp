@@ -359,6 +359,7 @@ int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamNa
         if (want && be->pinned_alloc && be->pinned_free) { staged.reset(new StagedSegments(bamName, seg.tell(), target, be->pinned_alloc, be->pinned_free)); if (!staged->staged()) staged.reset(); }
     }
     auto next_segment = [&](int slot) -> bool {
+        Acc a_(5);
         if (!staged) return seg.next(target, base[slot], bytes[slot], blk[slot]);
         StagedSegments::Seg sg;
         if (!staged->next(sg)) return false;
@@ -467,7 +468,7 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
         if (!ref) return 0;
         const md_call *got = nullptr; size_t n_got = 0;
         if (on_device) {
-            if (!loaded) { if (be->load_contig(d.dev, (int32_t) J.tid, ref->data(), (uint32_t) ref->size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; } if (d.push_bed(J.tid)) return -20; loaded = true; }
+            if (!loaded) { Acc a_(6); if (be->load_contig(d.dev, (int32_t) J.tid, ref->data(), (uint32_t) ref->size()) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; } if (d.push_bed(J.tid)) return -20; loaded = true; }
             md_tile_desc t = td; if (t.end > ref->size()) t.end = (uint32_t) ref->size(); if (t.beg > t.end) t.beg = t.end;
             const uint64_t cap = (uint64_t)(t.end - t.beg) + 16;
             // the records come back into page-locked memory when the back end offers it (a pageable target halves the D2H rate and
@@ -491,7 +492,7 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
     };
     auto close_contig = [&](const ContigJob &J) -> int {
         if (ref) feed(J, nullptr, 0, J.rend, true);
-        if (loaded) be->drop_contig(d.dev, (int32_t) J.tid);
+        if (loaded) { Acc a_(6); be->drop_contig(d.dev, (int32_t) J.tid); }
         loaded = false;
         return 0;
     };
@@ -576,7 +577,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     int c, nThreads = 1, keepStrand = 0; double minConvEff = 0.0; bool threads_given = false;
     double t_start = now_s(); g_t0 = t_start; g_marks = getenv("MD_TIMING") != nullptr;
     tune_allocator();
-    memset(&g_stats, 0, sizeof g_stats);
+    memset(&g_stats, 0, sizeof g_stats); memset(g_acc, 0, sizeof g_acc);
 
     static struct option lopts[] = {
         {"opref", 1, NULL, 'o'}, {"fraction", 0, NULL, 'f'}, {"counts", 0, NULL, 'c'}, {"logit", 0, NULL, 'm'}, {"minDepth", 1, NULL, 'd'},
@@ -856,7 +857,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     if (out_thread.failed()) { fprintf(stderr, "Couldn't write the output file(s)! Disk full?\n"); if (rc == 0) rc = -3; }
     g_stats.t_format_s = out_thread.busy_seconds();
     if (g_marks) fprintf(stderr, "[md-timing] text stage: formatting %.3f s, pwrite %.3f s (summed over its threads)\n", out_thread.busy_seconds(), out_thread.write_seconds());
-    if (g_marks) fprintf(stderr, "[md-timing] calling thread: record append / phred packing %.3f, contig load %.3f, chunk copy %.3f, waiting for the text stage %.3f, buffer upkeep %.3f\n", g_acc[0], g_acc[1], g_acc[2], g_acc[3], g_acc[4]);
+    if (g_marks) fprintf(stderr, "[md-timing] calling thread: record append / phred packing %.3f, contig load %.3f, chunk copy %.3f, waiting for the text stage %.3f, buffer upkeep %.3f, waiting for the next file segment %.3f, contig to / from the device %.3f\n", g_acc[0], g_acc[1], g_acc[2], g_acc[3], g_acc[4], g_acc[5], g_acc[6]);
     if (g_marks && d.bam) fprintf(stderr, "[md-timing] record chains: %zu jobs adopted from the inflating worker, %zu walked by the stitcher\n", d.bam->jobs_adopted(), d.bam->jobs_walked());
     be->destroy(d.dev);
     mark("device destroyed");

@@ -1218,7 +1218,8 @@ extern "C" md_ctx *md_create(const md_config *cfg, int device) {
     c->device = device; c->cfg = *cfg; fill_kparams(cfg, c->kp); memset(&c->tot, 0, sizeof c->tot);
     for (int k = 0; k < MD_NLANES; ++k) {
         Lane *L = &c->lanes[k];
-        if (cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; delete c; return nullptr; }
+        int prio_lo = 0, prio_hi = 0; cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&L->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { g_err = "cudaStreamCreate failed"; delete c; return nullptr; }   // the tile kernels go ahead of the device decoder's
         for (int i = 0; i < 5; ++i) cudaEventCreate(&L->ev[i]);
         if (cudaMallocHost((void **) &L->h_counters, C_N * 4) != cudaSuccess) { g_err = "cudaMallocHost failed"; delete c; return nullptr; }
     }
