@@ -644,7 +644,7 @@ def run_big(args, rank, local_rank, world, cores):
         for _ in range(2):
             t0 = time.perf_counter()
             with open(outp + ".cli.stdout", "w") as so:
-                subprocess.run([os.path.join(LIB, "MethylDackel"), sub] + list(opts) + [prefix + ".fa", prefix + ".bam"] + (["-o", outp + "_cli"] if sub == "extract" else ["--noSVG"]),
+                subprocess.run([os.path.join(LIB, "MethylDackel"), sub] + list(opts) + [prefix + ".fa", prefix + ".bam"] + (["-o", outp] if sub == "extract" else ["--noSVG"]),   # same files as the library call: one copy of the output at a time
                                check=True, stdout=so, stderr=subprocess.DEVNULL)
             ts.append(time.perf_counter() - t0)
         cli = {"value": round(n_aln / min(ts) / 1e6, 3), "unit": UNIT, "seconds": round(min(ts), 3), "what": "lib/MethylDackel %s ... as a fresh process, best of 2" % sub}
