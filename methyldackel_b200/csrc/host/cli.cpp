@@ -433,7 +433,11 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
     std::vector<ContigJob> jobs = contig_jobs(all, c0, c1);
     const std::string *ref = nullptr; bool loaded = false;
     size_t next_chunk = 0;
-    PodVec<md_call> tile_calls; md_call *pin_calls = nullptr; uint64_t pin_cap = 0;
+    PodVec<md_call> tile_calls; md_call *pin_calls[2] = {nullptr, nullptr}; uint64_t pin_cap[2] = {0, 0}; uint64_t n_dev_tiles = 0;
+    // The hand-over below (a copy of every record + the hand-off to the text stage) runs on a helper thread, one tile behind the
+    // calling thread, which meanwhile has the device build and count the next tile; two read-back buffers alternate.
+    struct FeedJob { const ContigJob *J; const md_call *rec; size_t n; uint32_t upto; bool last; };
+    std::mutex fm; std::condition_variable fcv; std::deque<FeedJob> fq; bool fstop = false; uint64_t f_submitted = 0, f_done = 0;
     // The records of a tile go straight from the read-back buffer into the vectors of the reference chunks they belong to (one
     // copy, located by binary search; a chunk that straddles a tile cut keeps collecting in `pending`), and every chunk that is
     // complete — its end lies at or before `done_upto`, or the contig is being closed — is handed to the text stage.
@@ -451,8 +455,19 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
             pending.reset(); ++next_chunk;
         }
     };
+    std::thread feeder([&] {
+        for (;;) {
+            FeedJob j;
+            { std::unique_lock<std::mutex> l(fm); fcv.wait(l, [&] { return fstop || !fq.empty(); }); if (fq.empty()) return; j = fq.front(); fq.pop_front(); }
+            feed(*j.J, j.rec, j.n, j.upto, j.last);
+            { std::lock_guard<std::mutex> g(fm); ++f_done; } fcv.notify_all();
+        }
+    });
+    auto feed_async = [&](const ContigJob &J, const md_call *rec, size_t n, uint32_t upto, bool last) { { std::lock_guard<std::mutex> g(fm); fq.push_back(FeedJob{&J, rec, n, upto, last}); ++f_submitted; } fcv.notify_all(); };
+    auto feed_wait = [&](uint64_t outstanding) { std::unique_lock<std::mutex> l(fm); fcv.wait(l, [&] { return f_submitted - f_done <= outstanding; }); };
     size_t job_i = 0;
     auto open_contig = [&](const ContigJob &J) -> int {
+        feed_wait(0);                                           // the hand-over thread is done with the previous contig's state
         { Acc a_(1); ref = d.fetch(J.tid); }
         while (job_i < jobs.size() && jobs[job_i].tid != J.tid) ++job_i;
         if (job_i + 1 < jobs.size()) d.prefetch(jobs[job_i + 1].tid);
@@ -474,11 +489,13 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
             // the records come back into page-locked memory when the back end offers it (a pageable target halves the D2H rate and
             // makes the copy synchronous); the buffer only ever grows
             md_call *dst = nullptr;
+            const int pb = (int)(n_dev_tiles++ & 1);
+            feed_wait(1);                                       // the tile before last has left this buffer
             if (be->pinned_alloc && be->pinned_free) {
-                if (cap > pin_cap) { if (pin_calls) be->pinned_free(pin_calls); pin_cap = cap + cap / 4; pin_calls = (md_call *) be->pinned_alloc(pin_cap * sizeof(md_call)); if (!pin_calls) pin_cap = 0; }
-                dst = pin_calls;
+                if (cap > pin_cap[pb]) { if (pin_calls[pb]) be->pinned_free(pin_calls[pb]); pin_cap[pb] = cap + cap / 4; pin_calls[pb] = (md_call *) be->pinned_alloc(pin_cap[pb] * sizeof(md_call)); if (!pin_calls[pb]) pin_cap[pb] = 0; }
+                dst = pin_calls[pb];
             }
-            if (!dst) { tile_calls.clear(); tile_calls.grow(cap); dst = tile_calls.data(); }
+            if (!dst) { feed_wait(0); tile_calls.clear(); tile_calls.grow(cap); dst = tile_calls.data(); }
             md_tile_stats st;
             double t0 = now_s();
             int r = be->bam_extract_run(bs, run, &t, J.rend, dst, cap, &st);
@@ -487,18 +504,22 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
             got = dst; n_got = (size_t) st.n_calls;
             g_stats.n_calls += st.n_calls; g_stats.n_tiles++;
         }
-        feed(J, got, n_got, td.end, false);
+        feed_async(J, got, n_got, td.end, false);
         return 0;
     };
     auto close_contig = [&](const ContigJob &J) -> int {
-        if (ref) feed(J, nullptr, 0, J.rend, true);
+        if (ref) feed_async(J, nullptr, 0, J.rend, true);
+        feed_wait(0);
         if (loaded) { Acc a_(6); be->drop_contig(d.dev, (int32_t) J.tid); }
         loaded = false;
         return 0;
     };
     int rc = drive_segments(d, be, bs, bamName, jobs, open_contig, tile, close_contig);
+    feed_wait(0);
+    { std::lock_guard<std::mutex> g(fm); fstop = true; } fcv.notify_all();
+    feeder.join();
     be->bam_close(bs);
-    if (pin_calls) be->pinned_free(pin_calls);
+    for (int k = 0; k < 2; ++k) if (pin_calls[k]) be->pinned_free(pin_calls[k]);
     return rc;
 }
 

@@ -72,6 +72,7 @@ struct KParams {
     int keepMask;              // bit0 CpG, bit1 CHG, bit2 CHH
     int minOppositeDepth; double maxVariantFrac;
     int bounds[16], abounds[16];
+    int anyTrim;               // some --OT/.../--nOT/... bound is set (none: every read keeps [0, l_qseq), and the table look-ups are skipped)
     int noOverlap;
     float minCE;               // --minConversionEfficiency (common.c:442-444); 0 = off
     unsigned char boost[256];  // (uint8_t)(q + 0.2*q), overlaps.c:103,106, tabulated on the host in double
@@ -134,6 +135,7 @@ __device__ __forceinline__ bool dev_admit(const KParams &P, unsigned f, unsigned
 // kept query range [lo,hi) after trimAlignment + trimAbsoluteAlignment (common.c:137-208);
 // bases outside read as N with phred 0.
 __device__ __forceinline__ void dev_trim(const KParams &P, int strand, unsigned f, int l, int &lo, int &hi) {
+    if (!P.anyTrim) { lo = 0; hi = l; return; }
     int b = 4 * (strand - 1) + ((f & 0x80u) ? 2 : 0);
     int lb = min(P.bounds[b], l), rb = P.bounds[b + 1];
     lo = lb; hi = rb ? min(rb, l) : l;
@@ -1203,7 +1205,7 @@ static void fill_kparams(const md_config *c, KParams &k) {
     k.keepDiscordant = c->keepDiscordant; k.ignoreFlags = c->ignoreFlags; k.requireFlags = c->requireFlags; k.ignoreNH = c->ignoreNH;
     k.keepMask = (c->keepCpG ? 1 : 0) | (c->keepCHG ? 2 : 0) | (c->keepCHH ? 4 : 0);
     k.minOppositeDepth = c->minOppositeDepth; k.maxVariantFrac = c->maxVariantFrac;
-    for (int i = 0; i < 16; ++i) { k.bounds[i] = c->bounds[i] < 0 ? 0 : c->bounds[i]; k.abounds[i] = c->absoluteBounds[i] < 0 ? 0 : c->absoluteBounds[i]; }
+    for (int i = 0; i < 16; ++i) { k.bounds[i] = c->bounds[i] < 0 ? 0 : c->bounds[i]; k.abounds[i] = c->absoluteBounds[i] < 0 ? 0 : c->absoluteBounds[i]; if (k.bounds[i] | k.abounds[i]) k.anyTrim = 1; }
     k.noOverlap = c->noOverlapMerge; k.minCE = c->minConversionEfficiency;
     for (int q = 0; q < 256; ++q) { volatile double v = (double) q; volatile double t = 0.2 * v; volatile double s = v + t; k.boost[q] = (unsigned char)(int) s; }
 }
