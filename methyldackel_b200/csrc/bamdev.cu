@@ -322,7 +322,7 @@ static int bam_build_tile(md_bam_stream *s, int run, const md_tile_desc *t, uint
     if (carry) {
         const DevReads &V = P.view;
         S.prev.pos = V.pos; S.prev.flag = V.flag; S.prev.mapq = V.mapq; S.prev.aux = V.aux; S.prev.l_qseq = V.l_qseq; S.prev.cigar_off = V.cigar_off; S.prev.seq_off = V.seq_off;
-        S.prev.qual_off = V.qual_off; S.prev.frag_key = V.frag_key; S.prev.cigar = V.cigar; S.prev.seq = V.seq; S.prev.qual = V.qual;
+        S.prev.qual_off = V.qual_off; S.prev.frag_key = V.frag_key; S.prev.cigar = V.cigar; S.prev.seq = V.seq; S.prev.qual = V.qual; S.prev.name_chk = V.name_chk;
         S.prev_rend = P.rend; S.n_prev = P.n;
     }
     S.keep_lo = t->beg; S.keep_hi = keep_hi;
@@ -346,21 +346,21 @@ static int bam_build_tile(md_bam_stream *s, int run, const md_tile_desc *t, uint
     }
     tm.tick();
     const size_t n = tot.x;
-    size_t szs[13] = {n * 4, n * 2, n, n, n * 4, (n + 1) * 4, n * 4, n * 4, n * 8, n * 4, (size_t) tot.y * 4, (size_t) tot.z * 4, (size_t) tot.w * 8};
-    size_t offs[13], total = 0;
-    for (int k = 0; k < 13; ++k) { offs[k] = total; total += al256(szs[k] + 16); }
+    size_t szs[14] = {n * 4, n * 2, n, n, n * 4, (n + 1) * 4, n * 4, n * 4, n * 8, n * 4, (size_t) tot.y * 4, (size_t) tot.z * 4, (size_t) tot.w * 8, n * 4};
+    size_t offs[14], total = 0;
+    for (int k = 0; k < 14; ++k) { offs[k] = total; total += al256(szs[k] + 16); }
     if (N.buf.reserve(total)) return -100;
     unsigned char *base = (unsigned char *) N.buf.p;
     TileDst D;
     D.pos = (int32_t *)(base + offs[0]); D.flag = (uint16_t *)(base + offs[1]); D.mapq = base + offs[2]; D.aux = base + offs[3]; D.l_qseq = (uint32_t *)(base + offs[4]);
     D.cigar_off = (uint32_t *)(base + offs[5]); D.seq_off = (uint32_t *)(base + offs[6]); D.qual_off = (uint32_t *)(base + offs[7]); D.frag_key = (uint64_t *)(base + offs[8]);
-    D.rend = (int32_t *)(base + offs[9]); D.cigar = (uint32_t *)(base + offs[10]); D.seq = (uint32_t *)(base + offs[11]); D.qual = (uint64_t *)(base + offs[12]);
+    D.rend = (int32_t *)(base + offs[9]); D.cigar = (uint32_t *)(base + offs[10]); D.seq = (uint32_t *)(base + offs[11]); D.qual = (uint64_t *)(base + offs[12]); D.name_chk = (uint32_t *)(base + offs[13]);
     if (m) { tile_gather_kernel<<<(m + 255) / 256, 256, 0, st>>>(S, (const Sz4 *) s->sz.p, (const Sz4 *) s->off.p, D); c->launches += 1; }
     else CK(cudaMemsetAsync(D.cigar_off, 0, 4, st));
     DevReads &v = N.view; memset(&v, 0, sizeof v);
     v.n = (uint32_t) n; v.seq_words = tot.z; v.qual_words = tot.w; v.qbits = 8;
     v.pos = D.pos; v.flag = D.flag; v.mapq = D.mapq; v.aux = D.aux; v.l_qseq = D.l_qseq; v.cigar_off = D.cigar_off; v.seq_off = D.seq_off; v.qual_off = D.qual_off;
-    v.frag_key = D.frag_key; v.cigar = D.cigar; v.seq = D.seq; v.qual = D.qual;
+    v.frag_key = D.frag_key; v.cigar = D.cigar; v.seq = D.seq; v.qual = D.qual; v.name_chk = D.name_chk;
     tm.tick(); tm.add(s->t_tile); s->n_tiles++;
     N.rend = D.rend; N.n = (uint32_t) n; N.n_cigar = tot.y; N.tid = t->tid; N.cut = t->end; N.valid = true;
     s->cur ^= 1;

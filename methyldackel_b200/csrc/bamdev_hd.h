@@ -70,6 +70,7 @@ MD_HD bool head_body(uint32_t i, const uint8_t *u, const unsigned long long *rec
 struct SoaView {            // device (or host) arrays of a tile, as md_reads_soa
     const int32_t *pos; const uint16_t *flag; const uint8_t *mapq; const uint8_t *aux; const uint32_t *l_qseq;
     const uint32_t *cigar_off, *seq_off, *qual_off; const uint64_t *frag_key; const uint32_t *cigar, *seq; const uint64_t *qual;
+    const uint32_t *name_chk;   // second hash of the query name (device-built tiles)
 };
 struct TileSrc {
     const uint8_t *u; const unsigned long long *rec_off; const int32_t *pos, *rend;   // own records [r0, r0+n_own) of the segment
@@ -80,6 +81,7 @@ struct TileSrc {
 struct TileDst {
     int32_t *pos; uint16_t *flag; uint8_t *mapq, *aux; uint32_t *l_qseq, *cigar_off, *seq_off, *qual_off; uint64_t *frag_key; int32_t *rend;
     uint32_t *cigar, *seq; uint64_t *qual;
+    uint32_t *name_chk;
 };
 struct Sz4 { uint32_t x, y, z, w; };     // reads, cigar words, seq words, qual words
 
@@ -110,7 +112,7 @@ MD_HD void tile_gather_body(uint32_t e, const TileSrc &S, const Sz4 &v, const Sz
     D.cigar_off[k] = o.y; D.seq_off[k] = o.z; D.qual_off[k] = o.w;
     if (e < S.n_prev) {
         const SoaView &P = S.prev;
-        D.pos[k] = P.pos[e]; D.flag[k] = P.flag[e]; D.mapq[k] = P.mapq[e]; D.aux[k] = P.aux[e]; D.l_qseq[k] = P.l_qseq[e]; D.frag_key[k] = P.frag_key[e]; D.rend[k] = S.prev_rend[e];
+        D.pos[k] = P.pos[e]; D.flag[k] = P.flag[e]; D.mapq[k] = P.mapq[e]; D.aux[k] = P.aux[e]; D.l_qseq[k] = P.l_qseq[e]; D.frag_key[k] = P.frag_key[e]; D.name_chk[k] = P.name_chk[e]; D.rend[k] = S.prev_rend[e];
         const uint32_t c0 = P.cigar_off[e], s0 = P.seq_off[e], q0 = P.qual_off[e];
         for (uint32_t j = 0; j < v.y; ++j) D.cigar[o.y + j] = P.cigar[c0 + j];
         for (uint32_t j = 0; j < v.z; ++j) D.seq[o.z + j] = P.seq[s0 + j];
@@ -120,7 +122,7 @@ MD_HD void tile_gather_body(uint32_t e, const TileSrc &S, const Sz4 &v, const Sz
         const uint8_t *r = S.u + S.rec_off[i];
         const Head h = head_of(r);
         D.pos[k] = h.pos; D.flag[k] = (uint16_t) h.flag; D.mapq[k] = (uint8_t) h.mapq; D.aux[k] = aux_bits(r, h); D.l_qseq[k] = h.l_seq;
-        D.frag_key[k] = name_key(r, h); D.rend[k] = S.rend[i];
+        D.frag_key[k] = name_key(r, h); D.name_chk[k] = name_check(r, h); D.rend[k] = S.rend[i];
         const uint8_t *c = cigar_of(r, h);
         for (uint32_t j = 0; j < h.n_cigar; ++j) D.cigar[o.y + j] = ld32(c + 4 * j);
         bytes_to_words32(D.seq + o.z, seq_of(r, h), (h.l_seq + 1u) >> 1);

@@ -126,6 +126,16 @@ MD_HD uint64_t name_key(const uint8_t *r, const Head &h) {
     if (k == 0) k = 1;
     return k;
 }
+// A second, independent 32-bit hash of the same name (different multiplier, bytes taken back to front).  Two names are taken
+// for the same fragment only when both the 64-bit key and this check agree: 96 bits instead of 64.
+MD_HD uint32_t name_check(const uint8_t *r, const Head &h) {
+    const uint8_t *s = qname_of(r); uint32_t n = 0;
+    while (n < h.l_qname && s[n]) ++n;
+    uint32_t k = 0x811c9dc5u ^ (n * 0x85ebca6bu);
+    for (uint32_t i = n; i-- > 0;) { k = (k ^ s[i]) * 0x01000193u; k ^= k >> 15; }
+    k ^= k >> 16; k *= 0x7feb352du; k ^= k >> 15; k *= 0x846ca68bu; k ^= k >> 16;
+    return k;
+}
 MD_HD uint32_t seq_words(uint32_t l) { return (((l + 1u) >> 1) + 3u) >> 2; }
 MD_HD uint32_t qual_words8(uint32_t l) { return (l + 7u) >> 3; }
 

@@ -65,6 +65,7 @@ struct DevReads {
     const int32_t *pos; const uint16_t *flag; const uint8_t *mapq; const uint8_t *aux; const uint32_t *l_qseq;
     const uint32_t *cigar_off, *seq_off, *qual_off; const uint64_t *frag_key;
     const uint32_t *cigar, *seq; const uint64_t *qual;
+    const uint32_t *name_chk;                       // second hash of the query name, or null (host-supplied tiles carry the 64-bit key only)
 };
 
 struct KParams {
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(256, 8) prep_kernel(DevReads R, KParams P, int
             for (uint32_t probe = 0; probe < T.cap; ++probe) {
                 const uint32_t old = atomicCAS(T.tab + h, 0xffffffffu, i);
                 if (old == 0xffffffffu) break;                                 // first record of this name
-                if (R.frag_key[old] == key) {                                  // same name: pair up, or detect a third record
+                if (R.frag_key[old] == key && (!R.name_chk || R.name_chk[old] == R.name_chk[i])) {   // same name (64-bit key, and the 32-bit check where the tile carries it): pair up, or detect a third record
                     if (atomicCAS((int *) mate + old, -1, (int) i) == -1) { mate[i] = (int32_t) old; ++n_paired; }
                     else ++n_multi;
                     break;
@@ -1346,7 +1347,7 @@ static int stage_reads(md_ctx *c, Lane *L, md_dev_reads &d, const md_reads_soa *
     v.pos = (const int32_t *)(base + off[0]); v.flag = (const uint16_t *)(base + off[1]); v.mapq = base + off[2]; v.aux = base + off[3];
     v.l_qseq = (const uint32_t *)(base + off[4]); v.cigar_off = (const uint32_t *)(base + off[5]); v.seq_off = (const uint32_t *)(base + off[6]);
     v.qual_off = (const uint32_t *)(base + off[7]); v.frag_key = (const uint64_t *)(base + off[8]); v.cigar = (const uint32_t *)(base + off[9]);
-    v.seq = (const uint32_t *)(base + off[10]); v.qual = (const uint64_t *)(base + off[11]);
+    v.seq = (const uint32_t *)(base + off[10]); v.qual = (const uint64_t *)(base + off[11]); v.name_chk = nullptr;
     d.n = (uint32_t) n; d.n_cigar = r->n_cigar_ops;
     return 0;
 }
@@ -1475,14 +1476,16 @@ static int run_pipeline(md_ctx *c, Lane *L, const md_tile_desc *t, const DevRead
 static int resolve_duplicates_on_host(md_ctx *c, Lane *L) {
     const DevReads &R = L->last_reads;
     const uint32_t n = R.n;
-    std::vector<int32_t> pos(n), rend(n), mate(n, -1); std::vector<uint16_t> flag(n); std::vector<uint8_t> info(n); std::vector<uint64_t> key(n);
+    std::vector<int32_t> pos(n), rend(n), mate(n, -1); std::vector<uint16_t> flag(n); std::vector<uint8_t> info(n); std::vector<uint64_t> key(n); std::vector<uint32_t> chk(R.name_chk ? n : 0);
     cudaStream_t s = L->stream;
     CK(cudaMemcpyAsync(pos.data(), R.pos, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(rend.data(), L->rend.p, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(flag.data(), R.flag, (size_t) n * 2, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(info.data(), L->info.p, (size_t) n, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(key.data(), R.frag_key, (size_t) n * 8, cudaMemcpyDeviceToHost, s));
+    if (R.name_chk) CK(cudaMemcpyAsync(chk.data(), R.name_chk, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (R.name_chk) for (uint32_t i = 0; i < n; ++i) key[i] ^= (uint64_t) chk[i] * 0x9e3779b97f4a7c15ull;      // one map key from both hashes
     std::vector<std::pair<int32_t, uint32_t>> by_end;
     for (uint32_t i = 0; i < n; ++i) if (info[i] & INFO_ADMIT) by_end.emplace_back(rend[i], i);
     std::sort(by_end.begin(), by_end.end());

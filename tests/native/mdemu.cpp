@@ -19,7 +19,7 @@ namespace {
 const size_t HEADROOM = 1 << 20;
 struct Tile {
     std::vector<int32_t> pos, rend; std::vector<uint16_t> flag; std::vector<uint8_t> mapq, aux; std::vector<uint32_t> l_qseq, cigar_off, seq_off, qual_off, cigar, seq;
-    std::vector<uint64_t> frag_key, qual; uint32_t n = 0; int32_t tid = -1; uint32_t cut = 0; bool valid = false;
+    std::vector<uint64_t> frag_key, qual; std::vector<uint32_t> name_chk; uint32_t n = 0; int32_t tid = -1; uint32_t cut = 0; bool valid = false;
 };
 struct Seg {
     std::vector<uint8_t> ubuf; uint64_t U = 0, D0 = 0, leftover_from = 0, leftover = 0;
@@ -121,7 +121,7 @@ static int build(Emu *s, int run, const md_tile_desc *t, uint32_t keep_hi) {
     }
     if (P.valid && P.tid == t->tid && P.cut == t->beg) {
         S.prev.pos = P.pos.data(); S.prev.flag = P.flag.data(); S.prev.mapq = P.mapq.data(); S.prev.aux = P.aux.data(); S.prev.l_qseq = P.l_qseq.data(); S.prev.cigar_off = P.cigar_off.data();
-        S.prev.seq_off = P.seq_off.data(); S.prev.qual_off = P.qual_off.data(); S.prev.frag_key = P.frag_key.data(); S.prev.cigar = P.cigar.data(); S.prev.seq = P.seq.data(); S.prev.qual = P.qual.data();
+        S.prev.seq_off = P.seq_off.data(); S.prev.qual_off = P.qual_off.data(); S.prev.frag_key = P.frag_key.data(); S.prev.cigar = P.cigar.data(); S.prev.seq = P.seq.data(); S.prev.qual = P.qual.data(); S.prev.name_chk = P.name_chk.data();
         S.prev_rend = P.rend.data(); S.n_prev = P.n;
     }
     S.keep_lo = t->beg; S.keep_hi = keep_hi;
@@ -131,9 +131,9 @@ static int build(Emu *s, int run, const md_tile_desc *t, uint32_t keep_hi) {
     for (uint32_t e = 0; e < m; ++e) { sz[e] = mdbam::tile_sizes_body(e, S); off[e] = acc; acc.x += sz[e].x; acc.y += sz[e].y; acc.z += sz[e].z; acc.w += sz[e].w; }
     const size_t n = acc.x;
     N.pos.assign(n, 0); N.rend.assign(n, 0); N.flag.assign(n, 0); N.mapq.assign(n, 0); N.aux.assign(n, 0); N.l_qseq.assign(n, 0); N.cigar_off.assign(n + 1, 0); N.seq_off.assign(n, 0); N.qual_off.assign(n, 0);
-    N.frag_key.assign(n, 0); N.cigar.assign(acc.y + 4, 0); N.seq.assign(acc.z + 4, 0); N.qual.assign(acc.w + 4, 0);
+    N.frag_key.assign(n, 0); N.name_chk.assign(n + 1, 0); N.cigar.assign(acc.y + 4, 0); N.seq.assign(acc.z + 4, 0); N.qual.assign(acc.w + 4, 0);
     mdbam::TileDst D; D.pos = N.pos.data(); D.flag = N.flag.data(); D.mapq = N.mapq.data(); D.aux = N.aux.data(); D.l_qseq = N.l_qseq.data(); D.cigar_off = N.cigar_off.data(); D.seq_off = N.seq_off.data();
-    D.qual_off = N.qual_off.data(); D.frag_key = N.frag_key.data(); D.rend = N.rend.data(); D.cigar = N.cigar.data(); D.seq = N.seq.data(); D.qual = N.qual.data();
+    D.qual_off = N.qual_off.data(); D.frag_key = N.frag_key.data(); D.name_chk = N.name_chk.data(); D.rend = N.rend.data(); D.cigar = N.cigar.data(); D.seq = N.seq.data(); D.qual = N.qual.data();
     for (uint32_t e = 0; e < m; ++e) mdbam::tile_gather_body(e, S, sz[e], off[e], D);
     N.cigar.resize(acc.y); N.seq.resize(acc.z); N.qual.resize(acc.w);
     N.n = (uint32_t) n; N.tid = t->tid; N.cut = t->end; N.valid = true;
