@@ -270,44 +270,79 @@ def extract_sharded(argv, rank, world, run_main=None, barrier=None, allreduce_su
         print("extract_sharded: rank %d failed: %s" % (rank, e), file=sys.stderr)
         rc = -20
     nvar = allreduce_sum(nvar_local if rc == 0 else 0)
-    worst = allreduce_sum(1 if rc != 0 else 0)                 # also orders every rank's shard files before rank 0 reads them
+    worst = allreduce_sum(1 if rc != 0 else 0)                 # also orders every rank's shard files before anyone reads them
+    # Merge: every rank copies ITS shard into the final file at the offset the lower ranks' sizes give it — world copies in
+    # parallel, done by the kernel (copy_file_range), instead of one process reading and rewriting the whole output.
+    parts = [["%s.shard%d" % (name, r) for r in range(world)] for name in names]
+    mine_ok = 1 if (worst == 0 and all(os.path.exists(ps[rank]) for ps in parts)) else 0
+    all_ok = allreduce_sum(mine_ok) == world
     merged_ok = 1
-    if rank == 0:
-        parts = [["%s.shard%d" % (name, r) for r in range(world)] for name in names]
-        try:
-            if worst == 0 and all(os.path.exists(x) for ps in parts for x in ps):
-                for name, ps in zip(names, parts):
+    if all_ok:                                                 # every rank takes the same branch: the collectives below stay matched
+        sizes = [[allreduce_sum(os.path.getsize(ps[r]) if r == rank else 0) for r in range(world)] for ps in parts]
+        if rank == 0:
+            try:
+                for name, sz in zip(names, sizes):
                     with open(name, "wb") as out:
-                        for part in ps:
-                            with open(part, "rb") as f:
-                                while True:
-                                    blk = f.read(1 << 24)
-                                    if not blk:
-                                        break
-                                    out.write(blk)
-                if nvar:
-                    print("%d positions were excluded due to likely being variants." % nvar)
-                    sys.stdout.flush()
-            else:
+                        out.truncate(sum(sz))
+            except OSError as e:
                 merged_ok = 0
-                if worst == 0:
-                    print("extract_sharded: a shard file is missing; nothing was merged", file=sys.stderr)
+                print("extract_sharded: cannot create the output files: %s" % e, file=sys.stderr)
+        barrier()
+        try:
+            for name, ps, sz in zip(names, parts, sizes):
+                if os.path.exists(name):
+                    _copy_into(ps[rank], name, sum(sz[:rank]))
+                else:
+                    merged_ok = 0
         except OSError as e:
             merged_ok = 0
-            print("extract_sharded: merging the shards failed: %s" % e, file=sys.stderr)
-        finally:
-            for ps in parts:
+            print("extract_sharded: merging the shards failed on rank %d: %s" % (rank, e), file=sys.stderr)
+    else:
+        merged_ok = 0
+        if rank == 0 and worst == 0:
+            print("extract_sharded: a shard file is missing; nothing was merged", file=sys.stderr)
+    merged_ok = 1 if allreduce_sum(merged_ok) == world else 0   # doubles as the barrier after the copies; tells every rank the outcome
+    for ps in parts:
+        if os.path.exists(ps[rank]):
+            os.unlink(ps[rank])
+    if rank == 0:
+        if merged_ok:
+            if nvar:
+                print("%d positions were excluded due to likely being variants." % nvar)
+                sys.stdout.flush()
+        else:
+            for ps in parts:                                   # a rank that died before this point leaves its shard behind
                 for part in ps:
                     if os.path.exists(part):
                         os.unlink(part)
-            if not merged_ok:
-                for name in names:                             # no normal-looking output from a failed run
-                    if os.path.exists(name):
-                        os.unlink(name)
-    merged_ok = allreduce_sum(merged_ok if rank == 0 else 0)   # doubles as the final barrier; tells every rank the outcome
+            for name in names:                                 # no normal-looking output from a failed run
+                if os.path.exists(name):
+                    os.unlink(name)
+    barrier()
     if rc != 0:
         return rc
     return 0 if (worst == 0 and merged_ok) else -20
+
+
+def _copy_into(src, dst, offset):
+    """src -> dst[offset:], in the kernel where the file system allows it"""
+    import os
+    n = os.path.getsize(src)
+    with open(src, "rb") as fi, open(dst, "r+b") as fo:
+        done = 0
+        try:
+            while done < n:
+                k = os.copy_file_range(fi.fileno(), fo.fileno(), min(n - done, 1 << 30), done, offset + done)
+                if k <= 0:
+                    raise OSError("copy_file_range made no progress")
+                done += k
+        except (OSError, AttributeError):
+            fi.seek(done); fo.seek(offset + done)
+            while True:
+                blk = fi.read(1 << 24)
+                if not blk:
+                    break
+                fo.write(blk)
 
 
 def mbias_sharded(argv, rank, world, tmp_prefix, run_main=None, barrier=None, allreduce_sum=None):
