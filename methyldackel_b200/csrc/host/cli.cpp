@@ -734,7 +734,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
         d.have_bed = true;
     }
     for (int k = 0; k < 3; ++k) if (fp[k] && (k == 0 || fp[k] != fp[0])) setvbuf(fp[k], nullptr, _IOFBF, 4 << 20);
-    OrderedFormatter out_thread(format_threads(dev_decode), o, fp);
+    OrderedFormatter out_thread(std::max(2, format_threads(dev_decode) / shardWorld), o, fp);     // shards of one job share the host's cores
     int rc = 0;
     {
         // the reference's chunk list (extract.c:325-350), enumerated up front; a shard takes a contiguous,
