@@ -380,7 +380,7 @@ def run_c2(args, rank, local_rank, world, cores):
     hbuf = g.g.md_alloc_pinned(len(raw) + 64)
     C.memmove(hbuf, raw, len(raw))
     segs, cur_blocks, seg_start, off = [], [], 0, 0
-    SEG = int(os.environ.get("MD_SEGMENT_BYTES", 128 << 20))      # the sub-command driver's default segment size (host/cli.cpp: device_segment_bytes)
+    SEG = int(os.environ.get("MD_SEGMENT_BYTES", 96 << 20))      # the sub-command driver's default segment size (host/cli.cpp: device_segment_bytes)
     while off + 18 <= len(raw):
         xlen = struct.unpack_from("<H", raw, off + 10)[0]
         bs = struct.unpack_from("<H", raw, off + 16)[0] + 1          # BC subfield first, as every BGZF writer lays it out (checked below)

@@ -139,7 +139,9 @@ static bool device_decode_enabled(const mdh_backend *be) {
     const char *e = getenv("MD_DEVICE_DECODE");
     return !(e && e[0] == '0');
 }
-static size_t device_segment_bytes() { if (const char *e = getenv("MD_SEGMENT_BYTES")) { long v = atol(e); if (v > 0) return (size_t) v; } return (size_t) 128 << 20; }
+// Segment size of the device decoder.  One warp decodes one BGZF block and 148 SMs x 32 warps are resident at a time, so a
+// segment of about one such wave (4 736 blocks of ~20 KB) keeps every decoder slot busy without a nearly empty second round.
+static size_t device_segment_bytes() { if (const char *e = getenv("MD_SEGMENT_BYTES")) { long v = atol(e); if (v > 0) return (size_t) v; } return (size_t) 96 << 20; }
 
 static bool pack_quals_enabled() { const char *e = getenv("MD_QUAL_PACK"); return !(e && e[0] == '0'); }
 
