@@ -260,9 +260,13 @@ def extract_sharded(argv, rank, world, run_main=None, barrier=None, allreduce_su
         barrier, allreduce_sum = _default_group()
     names = []
     nvar_local = 0
+    import time
+    t0 = time.time()
+    marks = []                                                 # MD_TIMING=1: where a sharded run spends its wall time, per rank
     try:
         names = _output_names(argv)
         rc = run_main(list(argv) + ["--shardRank", str(rank), "--shardWorld", str(world)])
+        marks.append(("shard done", time.time() - t0))
         st = A.MdhRunStats()
         A.load_host().mdh_last_run_stats(C.byref(st))
         nvar_local = int(st.n_variant_positions)
@@ -276,6 +280,7 @@ def extract_sharded(argv, rank, world, run_main=None, barrier=None, allreduce_su
     parts = [["%s.shard%d" % (name, r) for r in range(world)] for name in names]
     mine_ok = 1 if (worst == 0 and all(os.path.exists(ps[rank]) for ps in parts)) else 0
     all_ok = allreduce_sum(mine_ok) == world
+    marks.append(("all shards done", time.time() - t0))
     merged_ok = 1
     if all_ok:                                                 # every rank takes the same branch: the collectives below stay matched
         sizes = [[allreduce_sum(os.path.getsize(ps[r]) if r == rank else 0) for r in range(world)] for ps in parts]
@@ -301,7 +306,9 @@ def extract_sharded(argv, rank, world, run_main=None, barrier=None, allreduce_su
         merged_ok = 0
         if rank == 0 and worst == 0:
             print("extract_sharded: a shard file is missing; nothing was merged", file=sys.stderr)
+    marks.append(("own shard copied", time.time() - t0))
     merged_ok = 1 if allreduce_sum(merged_ok) == world else 0   # doubles as the barrier after the copies; tells every rank the outcome
+    marks.append(("all copied", time.time() - t0))
     for ps in parts:
         if os.path.exists(ps[rank]):
             os.unlink(ps[rank])
@@ -319,6 +326,9 @@ def extract_sharded(argv, rank, world, run_main=None, barrier=None, allreduce_su
                 if os.path.exists(name):
                     os.unlink(name)
     barrier()
+    if os.environ.get("MD_TIMING"):
+        marks.append(("cleaned up", time.time() - t0))
+        print("[md-timing] extract_sharded rank %d: %s" % (rank, ", ".join("%s %.3f" % m for m in marks)), file=sys.stderr)
     if rc != 0:
         return rc
     return 0 if (worst == 0 and merged_ok) else -20

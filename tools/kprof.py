@@ -30,7 +30,8 @@ ref = api.fetch_contig(p + ".fa", "chr1")
 soa = b.read_region(0)
 reps = int(os.environ.get("KPROF_REPS", "2"))
 
-for name, cfg, mb in (("cpg", A.default_config(), False), ("var", A.default_config(minOppositeDepth=5, maxVariantFrac=0.25), False), ("mbias", A.default_config(noOverlapMerge=1), True)):
+only_decode = os.environ.get("KPROF_ONLY") == "decode"       # variant sweeps of the inflate kernel (tools/gpu_r2_groups.sh)
+for name, cfg, mb in () if only_decode else (("cpg", A.default_config(), False), ("var", A.default_config(minOppositeDepth=5, maxVariantFrac=0.25), False), ("mbias", A.default_config(noOverlapMerge=1), True)):
     g = api.GpuContext(cfg)
     g.load_contig(0, ref)
     if mb:
@@ -48,7 +49,7 @@ g.load_contig(0, ref)
 tiles = b.make_tiles(0, 0, len(ref), 1 << 19)
 td, s0 = tiles[0]
 out = (A.MdReadMeth * s0.n_reads)()
-for _ in range(reps):
+for _ in range(0 if only_decode else reps):
     assert g.g.md_per_read_tile(g.h, C.byref(A.MdTileDesc(0, 0, len(ref), 0, 0)), C.byref(s0), 1000000, out) == 0, g.g.md_last_error()
 print("perRead: %d alignments" % s0.n_reads, flush=True)
 
