@@ -34,7 +34,7 @@ extern "C" void mdh_last_run_stats(mdh_run_stats *out) { if (out) *out = g_stats
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 // MD_TIMING=1: phase marks on stderr (seconds since the sub-command started)
 static double g_t0 = 0; static bool g_marks = false;
-static double g_acc[8];   // pack, contig load, absorb, drain, ring wait
+static double g_acc[16];  // 0-6: see the [md-timing] calling-thread line; 7-12: device-decode driver (push_end, push_begin, runs, waits for the hand-over thread, read-back buffer growth, tile call)
 struct Acc { int k; double t0; explicit Acc(int k_) : k(k_), t0(now_s()) {} ~Acc() { g_acc[k] += now_s() - t0; } };
 static void mark(const char *what) { if (g_marks) fprintf(stderr, "[md-timing] %8.3f  %s\n", now_s() - g_t0, what); }
 
@@ -375,7 +375,7 @@ int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamNa
     while (have_cur && !done && rc == 0) {
         double t0 = now_s();
         md_bam_summary sum;
-        int r = overlapped ? be->bam_push_end(bs, &sum) : be->bam_push(bs, base[cur], bytes[cur], blk[cur].data(), (uint32_t) blk[cur].size(), skip, &sum);
+        int r; { Acc a_(7); r = overlapped ? be->bam_push_end(bs, &sum) : be->bam_push(bs, base[cur], bytes[cur], blk[cur].data(), (uint32_t) blk[cur].size(), skip, &sum); }
         pushed = false; skip = 0;
         g_stats.t_decode_s += now_s() - t0;
         if (g_marks && (n_seg < 4 || n_seg % 10 == 0)) { char m[64]; snprintf(m, sizeof m, "segment %zu decoded", n_seg); mark(m); }
@@ -385,10 +385,10 @@ int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamNa
         const int nxt = cur ^ 1;
         const bool have_next = next_segment(nxt);
         const bool file_end = !have_next;
-        if (have_next && overlapped) { if (be->bam_push_begin(bs, base[nxt], bytes[nxt], blk[nxt].data(), (uint32_t) blk[nxt].size(), 0) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; } pushed = true; }
+        if (have_next && overlapped) { Acc a_(8); if (be->bam_push_begin(bs, base[nxt], bytes[nxt], blk[nxt].data(), (uint32_t) blk[nxt].size(), 0) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; } pushed = true; }
         g_stats.n_records += sum.n_records;
         runs.resize(sum.n_runs);
-        if (sum.n_runs) be->bam_get_runs(bs, runs.data(), sum.n_runs);
+        if (sum.n_runs) { Acc a_(9); be->bam_get_runs(bs, runs.data(), sum.n_runs); }
         for (size_t k = 0; k < runs.size() && !done && rc == 0; ++k) {
             const md_bam_run &run = runs[k];
             if (run.tid < 0) { done = true; break; }                                   // unmapped records close a sorted file
@@ -469,7 +469,7 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
     auto feed_wait = [&](uint64_t outstanding) { std::unique_lock<std::mutex> l(fm); fcv.wait(l, [&] { return f_submitted - f_done <= outstanding; }); };
     size_t job_i = 0;
     auto open_contig = [&](const ContigJob &J) -> int {
-        feed_wait(0);                                           // the hand-over thread is done with the previous contig's state
+        { Acc a_(10); feed_wait(0); }                           // the hand-over thread is done with the previous contig's state
         { Acc a_(1); ref = d.fetch(J.tid); }
         while (job_i < jobs.size() && jobs[job_i].tid != J.tid) ++job_i;
         if (job_i + 1 < jobs.size()) d.prefetch(jobs[job_i + 1].tid);
@@ -492,8 +492,9 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
             // makes the copy synchronous); the buffer only ever grows
             md_call *dst = nullptr;
             const int pb = (int)(n_dev_tiles++ & 1);
-            feed_wait(1);                                       // the tile before last has left this buffer
+            { Acc a_(10); feed_wait(1); }                       // the tile before last has left this buffer
             if (be->pinned_alloc && be->pinned_free) {
+                Acc a_(11);
                 if (cap > pin_cap[pb]) { if (pin_calls[pb]) be->pinned_free(pin_calls[pb]); pin_cap[pb] = cap + cap / 4; pin_calls[pb] = (md_call *) be->pinned_alloc(pin_cap[pb] * sizeof(md_call)); if (!pin_calls[pb]) pin_cap[pb] = 0; }
                 dst = pin_calls[pb];
             }
@@ -511,7 +512,7 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
     };
     auto close_contig = [&](const ContigJob &J) -> int {
         if (ref) feed_async(J, nullptr, 0, J.rend, true);
-        feed_wait(0);
+        { Acc a_(10); feed_wait(0); }
         if (loaded) { Acc a_(6); be->drop_contig(d.dev, (int32_t) J.tid); }
         loaded = false;
         return 0;
@@ -881,6 +882,7 @@ extern "C" int mdh_extract_main(int argc, char *argv[], const mdh_backend *be) {
     g_stats.t_format_s = out_thread.busy_seconds();
     if (g_marks) fprintf(stderr, "[md-timing] text stage: formatting %.3f s, pwrite %.3f s (summed over its threads)\n", out_thread.busy_seconds(), out_thread.write_seconds());
     if (g_marks) fprintf(stderr, "[md-timing] calling thread: record append / phred packing %.3f, contig load %.3f, chunk copy %.3f, waiting for the text stage %.3f, buffer upkeep %.3f, waiting for the next file segment %.3f, contig to / from the device %.3f\n", g_acc[0], g_acc[1], g_acc[2], g_acc[3], g_acc[4], g_acc[5], g_acc[6]);
+    if (g_marks && dev_decode) fprintf(stderr, "[md-timing] device-decode driver (calling thread): waiting for a segment's decode %.3f, handing over the next segment %.3f, run table %.3f, waiting for the hand-over thread %.3f, growing the read-back buffers %.3f\n", g_acc[7], g_acc[8], g_acc[9], g_acc[10], g_acc[11]);
     if (g_marks && d.bam) fprintf(stderr, "[md-timing] record chains: %zu jobs adopted from the inflating worker, %zu walked by the stitcher\n", d.bam->jobs_adopted(), d.bam->jobs_walked());
     be->destroy(d.dev);
     mark("device destroyed");
@@ -1208,6 +1210,7 @@ extern "C" int mdh_mbias_main(int argc, char *argv[], const mdh_backend *be) {
     }
     std::vector<uint32_t> hist((size_t) 4 * 2 * MD_MBIAS_MAXLEN * 2, 0); int32_t lens[4] = {0, 0, 0, 0};
     if (rc == 0 && be->mbias_hist(d.dev, hist.data(), lens) != 0) rc = -20;
+    if (g_marks && dev_decode) fprintf(stderr, "[md-timing] device-decode driver (calling thread): waiting for a segment's decode %.3f, handing over the next segment %.3f, run table %.3f, contig load %.3f, waiting for the next file segment %.3f\n", g_acc[7], g_acc[8], g_acc[9], g_acc[1], g_acc[5]);
     be->destroy(d.dev);
     if (rc == 0 && histOut) {                                  // shard: hand the raw histogram to the caller, who sums the shards
         FILE *f = fopen(histOut, "wb");
