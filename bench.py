@@ -690,7 +690,7 @@ def main():
         args.mbp = int(args.mbp or 10)
         return run_c2(args, rank, local_rank, world, cores)
     args.steps = 2 if args.steps is None else args.steps
-    args.warmup = 1 if args.warmup is None else args.warmup
+    args.warmup = 3 if args.warmup is None else args.warmup
     if args.mbp is not None and args.config != "c4":
         args.mbp = int(args.mbp)
     return run_big(args, rank, local_rank, world, cores)

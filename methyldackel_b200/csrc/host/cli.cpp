@@ -435,7 +435,7 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
     std::vector<ContigJob> jobs = contig_jobs(all, c0, c1);
     const std::string *ref = nullptr; bool loaded = false;
     size_t next_chunk = 0;
-    PodVec<md_call> tile_calls; md_call *pin_calls[2] = {nullptr, nullptr}; uint64_t pin_cap[2] = {0, 0}; uint64_t n_dev_tiles = 0;
+    PodVec<md_call> tile_calls; md_call *pin_calls[2] = {nullptr, nullptr}; uint64_t pin_cap[2] = {0, 0}; uint64_t n_dev_tiles = 0; std::vector<md_call *> old_pins;
     // The hand-over below (a copy of every record + the hand-off to the text stage) runs on a helper thread, one tile behind the
     // calling thread, which meanwhile has the device build and count the next tile; two read-back buffers alternate.
     struct FeedJob { const ContigJob *J; const md_call *rec; size_t n; uint32_t upto; bool last; };
@@ -495,7 +495,8 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
             { Acc a_(10); feed_wait(1); }                       // the tile before last has left this buffer
             if (be->pinned_alloc && be->pinned_free) {
                 Acc a_(11);
-                if (cap > pin_cap[pb]) { if (pin_calls[pb]) be->pinned_free(pin_calls[pb]); pin_cap[pb] = cap + cap / 4; pin_calls[pb] = (md_call *) be->pinned_alloc(pin_cap[pb] * sizeof(md_call)); if (!pin_calls[pb]) pin_cap[pb] = 0; }
+                // (an outgrown buffer is released at the end of the run: freeing page-locked memory waits for the device, i.e. for the segment being decoded)
+                if (cap > pin_cap[pb]) { if (pin_calls[pb]) old_pins.push_back(pin_calls[pb]); pin_cap[pb] = 2 * cap; pin_calls[pb] = (md_call *) be->pinned_alloc(pin_cap[pb] * sizeof(md_call)); if (!pin_calls[pb]) pin_cap[pb] = 0; }
                 dst = pin_calls[pb];
             }
             if (!dst) { feed_wait(0); tile_calls.clear(); tile_calls.grow(cap); dst = tile_calls.data(); }
@@ -523,6 +524,7 @@ static int extract_device_decode(Driver &d, const mdh_backend *be, const char *b
     feeder.join();
     be->bam_close(bs);
     for (int k = 0; k < 2; ++k) if (pin_calls[k]) be->pinned_free(pin_calls[k]);
+    for (md_call *p : old_pins) be->pinned_free(p);
     return rc;
 }
 

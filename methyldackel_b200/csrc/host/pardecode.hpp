@@ -370,19 +370,22 @@ class StagedSegments {
 public:
     struct Seg { const uint8_t *base = nullptr; size_t bytes = 0; std::vector<md_bgzf_block> blocks; };
     StagedSegments(const std::string &path, uint64_t file_off, size_t target, void *(*alloc)(size_t), void (*release)(void *), int depth = 4, int io_threads = 6)
-        : target_(target), release_(release), io_threads_(io_threads), off_(file_off) {
+        : target_(target), alloc_(alloc), release_(release), io_threads_(io_threads), off_(file_off) {
         fd_ = ::open(path.c_str(), O_RDONLY);
         struct stat st;
         if (fd_ < 0 || fstat(fd_, &st) != 0) { if (fd_ >= 0) ::close(fd_); fd_ = -1; return; }
         size_ = (uint64_t) st.st_size;
         cap_ = target + (1u << 17);                       // a segment ends at the first block boundary at or beyond the target
-        for (int k = 0; k < depth; ++k) { void *p = alloc ? alloc(cap_) : nullptr; if (!p) break; buf_.push_back((uint8_t *) p); }
-        if (buf_.size() >= 3) th_ = std::thread([this] { run(); });
+        // the first buffer now (it also tells whether page-locked memory can be had at all); the others are allocated by the reader
+        // when it first needs them, so the consumer gets segment 0 after one allocation instead of `depth`
+        buf_.assign((size_t) std::max(depth, 3), nullptr);
+        buf_[0] = alloc ? (uint8_t *) alloc(cap_) : nullptr;
+        if (buf_[0]) th_ = std::thread([this] { run(); });
     }
     ~StagedSegments() {
         { std::lock_guard<std::mutex> g(m_); stop_ = true; } cv_.notify_all();
         if (th_.joinable()) th_.join();
-        for (uint8_t *p : buf_) if (release_) release_(p);
+        for (uint8_t *p : buf_) if (p && release_) release_(p);
         if (fd_ >= 0) ::close(fd_);
     }
     bool staged() const { return th_.joinable(); }
@@ -401,7 +404,9 @@ private:
         try {
             for (size_t k = 0; off_ + 18 <= size_; ++k) {
                 { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return stop_ || k + 1 < taken_ + buf_.size(); }); if (stop_) return; }   // at most depth - 1 segments ahead of the consumer's last call
-                uint8_t *dst = buf_[k % buf_.size()];
+                uint8_t *&slot = buf_[k % buf_.size()];
+                if (!slot) { slot = (uint8_t *) alloc_(cap_); if (!slot) throw std::runtime_error("out of page-locked memory for the staging buffers"); }
+                uint8_t *dst = slot;
                 const size_t want = (size_t) std::min<uint64_t>(cap_, size_ - off_);
                 const int nt = want > (8u << 20) ? io_threads_ : 1;
                 std::atomic<bool> ok{true};
@@ -438,7 +443,7 @@ private:
         } catch (std::exception &e) { std::lock_guard<std::mutex> g(m_); err_ = e.what(); }
         { std::lock_guard<std::mutex> g(m_); done_ = true; } cv_.notify_all();
     }
-    size_t target_, cap_ = 0; void (*release_)(void *); int io_threads_; int fd_ = -1; uint64_t off_ = 0, size_ = 0;
+    size_t target_, cap_ = 0; void *(*alloc_)(size_t); void (*release_)(void *); int io_threads_; int fd_ = -1; uint64_t off_ = 0, size_ = 0;
     std::vector<uint8_t *> buf_; std::thread th_;
     std::mutex m_; std::condition_variable cv_; std::deque<Seg> q_; size_t taken_ = 0; bool stop_ = false, done_ = false; std::string err_;
 };

@@ -1150,20 +1150,50 @@ __global__ void __launch_bounds__(128) gather_kernel(const md_call *raw, const u
 
 // ------------------------------------------------------------------------------------------------
 // host side of the library
-struct Contig { unsigned char *d_seq = nullptr; uint32_t len = 0; uint32_t *d_bounds = nullptr; uint32_t n_chunks = 0; uint32_t *d_bed = nullptr; uint32_t n_bed = 0; };
+struct Contig { unsigned char *d_seq = nullptr; uint32_t len = 0; uint32_t *d_bounds = nullptr; uint32_t n_chunks = 0; uint32_t *d_bed = nullptr; uint32_t n_bed = 0;
+                size_t cap_seq = 0, cap_bounds = 0, cap_bed = 0; };   // capacities of the pool blocks behind the three pointers
+
+// cudaFree waits for EVERYTHING in flight on the device — during a run that is the next segment's inflate (10-15 ms), and a
+// genome's worth of growing buffers and contig swaps added up to 0.4 - 1.6 s of a 2 - 3 s run (MD_TIMING, round 2).  Buffers
+// that are outgrown or dropped while a context is alive therefore go to a graveyard that is emptied when a context is destroyed
+// (their total stays below ~3x the final sizes: buffers grow by 1.5x), and contig-sized blocks are recycled (DevPool).
+static std::mutex g_grave_m;
+static std::vector<void *> g_grave;
+static void dev_free_later(void *p) { if (!p) return; std::lock_guard<std::mutex> g(g_grave_m); g_grave.push_back(p); }
+static void dev_free_graveyard() {                        // the caller has synchronised its streams
+    std::vector<void *> dead;
+    { std::lock_guard<std::mutex> g(g_grave_m); dead.swap(g_grave); }
+    for (void *p : dead) cudaFree(p);
+}
 
 struct DevBuf {
     void *p = nullptr; size_t cap = 0;
     int reserve(size_t n) {
         if (n <= cap) return 0;
-        if (p) cudaFree(p);
+        dev_free_later(p);
         p = nullptr; cap = 0;
-        size_t want = n + n / 4 + 256;
+        size_t want = n + n / 2 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { set_err("cudaMalloc", e); return -100; }
         cap = want; return 0;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// Blocks handed back by md_drop_contig, reused by the next md_load_contig / md_set_* (contigs come largest first in the usual
+// genome order, so after the first few every request is served from here); freed with the context.
+struct DevPool {
+    std::vector<std::pair<void *, size_t>> free_;
+    void *get(size_t n, size_t *cap_out) {
+        size_t best = free_.size();
+        for (size_t k = 0; k < free_.size(); ++k) if (free_[k].second >= n && (best == free_.size() || free_[k].second < free_[best].second)) best = k;
+        if (best != free_.size() && free_[best].second <= 4 * n + (1u << 20)) { void *p = free_[best].first; *cap_out = free_[best].second; free_.erase(free_.begin() + (ptrdiff_t) best); return p; }
+        void *p = nullptr; const size_t want = n + n / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) return nullptr;
+        *cap_out = want; return p;
+    }
+    void put(void *p, size_t cap) { if (p) free_.emplace_back(p, cap); }
+    void release() { for (auto &b : free_) cudaFree(b.first); free_.clear(); }
 };
 
 struct md_dev_reads {
@@ -1187,6 +1217,7 @@ struct Lane {
 struct md_ctx {
     int device = 0; md_config cfg; KParams kp;
     std::map<int32_t, Contig> contigs;
+    DevPool pool;
     Lane lanes[MD_NLANES]; int rr = 0; Lane *last = nullptr;
     uint32_t *d_hist = nullptr; int32_t *d_lens = nullptr;
     uint64_t launches = 0;
@@ -1253,6 +1284,8 @@ extern "C" void md_destroy(md_ctx *c) {
     sync_all(c);
     g_last_totals = c->tot; g_last_totals.launches = c->launches;
     for (auto &kv : c->contigs) { cudaFree(kv.second.d_seq); if (kv.second.d_bounds) cudaFree(kv.second.d_bounds); if (kv.second.d_bed) cudaFree(kv.second.d_bed); }
+    c->pool.release();
+    dev_free_graveyard();
     for (int k = 0; k < MD_NLANES; ++k) {
         Lane *L = &c->lanes[k];
         L->staged.arena.release();
@@ -1272,7 +1305,8 @@ extern "C" int md_load_contig(md_ctx *c, int32_t tid, const char *seq, uint32_t 
     md_drop_contig(c, tid);
     Lane *L = &c->lanes[0];
     Contig g; g.len = len;
-    CK(cudaMalloc(&g.d_seq, (size_t) len + 16));
+    g.d_seq = (unsigned char *) c->pool.get((size_t) len + 16, &g.cap_seq);
+    if (!g.d_seq) { g_err = "md_load_contig: out of device memory"; return -100; }
     CK(cudaMemcpyAsync(g.d_seq, seq, len, cudaMemcpyHostToDevice, L->stream));
     CK(cudaStreamSynchronize(L->stream));
     c->contigs[tid] = g;
@@ -1283,10 +1317,10 @@ extern "C" int md_drop_contig(md_ctx *c, int32_t tid) {
     auto it = c->contigs.find(tid);
     if (it == c->contigs.end()) return 0;
     cudaSetDevice(c->device);
-    sync_all(c);
-    cudaFree(it->second.d_seq);
-    if (it->second.d_bounds) cudaFree(it->second.d_bounds);
-    if (it->second.d_bed) cudaFree(it->second.d_bed);
+    sync_all(c);                                              // the lanes' kernels are done with it (the decode stream never reads contigs)
+    c->pool.put(it->second.d_seq, it->second.cap_seq);
+    c->pool.put(it->second.d_bounds, it->second.cap_bounds);
+    c->pool.put(it->second.d_bed, it->second.cap_bed);
     c->contigs.erase(it);
     return 0;
 }
@@ -1296,8 +1330,9 @@ extern "C" int md_set_mbias_chunks(md_ctx *c, int32_t tid, const uint32_t *bound
     if (it == c->contigs.end()) { g_err = "md_set_mbias_chunks: contig not loaded"; return -2; }
     CK(cudaSetDevice(c->device));
     Lane *L = &c->lanes[0];
-    if (it->second.d_bounds) { sync_all(c); cudaFree(it->second.d_bounds); it->second.d_bounds = nullptr; }
-    CK(cudaMalloc(&it->second.d_bounds, ((size_t) n_chunks + 1) * sizeof(uint32_t)));
+    if (it->second.d_bounds) { sync_all(c); c->pool.put(it->second.d_bounds, it->second.cap_bounds); it->second.d_bounds = nullptr; }
+    it->second.d_bounds = (uint32_t *) c->pool.get(((size_t) n_chunks + 1) * sizeof(uint32_t), &it->second.cap_bounds);
+    if (!it->second.d_bounds) { g_err = "md_set_mbias_chunks: out of device memory"; return -100; }
     CK(cudaMemcpyAsync(it->second.d_bounds, bounds, ((size_t) n_chunks + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, L->stream));
     CK(cudaStreamSynchronize(L->stream));
     it->second.n_chunks = n_chunks;
@@ -1311,7 +1346,7 @@ extern "C" int md_set_bed(md_ctx *c, int32_t tid, const md_bed_region *regs, uin
     if (it == c->contigs.end()) { g_err = "md_set_bed: contig not loaded"; return -2; }
     CK(cudaSetDevice(c->device));
     Lane *L = &c->lanes[0];
-    if (it->second.d_bed) { sync_all(c); cudaFree(it->second.d_bed); it->second.d_bed = nullptr; it->second.n_bed = 0; }
+    if (it->second.d_bed) { sync_all(c); c->pool.put(it->second.d_bed, it->second.cap_bed); it->second.d_bed = nullptr; it->second.n_bed = 0; }
     if (!n) return 0;
     for (uint32_t k = 1; k < n; ++k) {
         const md_bed_region &a = regs[k - 1], &b = regs[k];
@@ -1320,7 +1355,8 @@ extern "C" int md_set_bed(md_ctx *c, int32_t tid, const md_bed_region *regs, uin
     std::vector<uint32_t> h((size_t) n * 3);
     uint32_t run = 0;
     for (uint32_t k = 0; k < n; ++k) { run = std::max(run, regs[k].end); h[k] = regs[k].start; h[(size_t) n + k] = run; h[(size_t) 2 * n + k] = regs[k].strand; }
-    CK(cudaMalloc(&it->second.d_bed, h.size() * sizeof(uint32_t)));
+    it->second.d_bed = (uint32_t *) c->pool.get(h.size() * sizeof(uint32_t), &it->second.cap_bed);
+    if (!it->second.d_bed) { g_err = "md_set_bed: out of device memory"; return -100; }
     CK(cudaMemcpyAsync(it->second.d_bed, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, L->stream));
     CK(cudaStreamSynchronize(L->stream));
     it->second.n_bed = n;
