@@ -147,16 +147,13 @@ def peak_hbm():
 
 
 def traffic_of(kernel_key):
-    """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/r2_traffic.json, else round 1's)"""
-    for name in ("r2_traffic.json", "r1_traffic.json"):
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", name)))
-            if kernel_key in tj:
-                tj = tj[kernel_key]
-            return int(tj["dram_bytes_read"] + tj["dram_bytes_write"]), tj.get("source")
-        except Exception:
-            continue
-    return None, None
+    """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/r2_traffic.json); None when that
+    kernel / configuration has no capture"""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[kernel_key]
+        return int(tj["dram_bytes_read"] + tj["dram_bytes_write"]), tj.get("source")
+    except Exception:
+        return None, None
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm

@@ -32,13 +32,13 @@ using mdbam::BlockScan; using mdbam::TileSrc; using mdbam::TileDst; using mdbam:
 constexpr int INF_WARPS = MD_INFLATE_WARPS, INF_CTAS_PER_SM = 4;  // 32 warps per SM: 5.25 KB of shared memory each (2 KB ring), 64 registers per thread
 constexpr size_t INF_SMEM = INF_WARPS * sizeof(mdinflate::Decoder);
 static_assert(INF_CTAS_PER_SM * (INF_SMEM + 1024) <= 228 * 1024, "inflate_kernel: decoders do not fit the SM's shared memory");
-__global__ void __launch_bounds__(INF_WARPS * 32, INF_CTAS_PER_SM) inflate_kernel(const uint8_t *comp, const md_bgzf_block *blk, const unsigned long long *uoff, uint8_t *ubuf, uint32_t n_blocks, int *err) {
+__global__ void __launch_bounds__(INF_WARPS * 32, INF_CTAS_PER_SM) inflate_kernel(const uint8_t *comp, const md_bgzf_block *blk, const unsigned long long *uoff, uint8_t *ubuf, uint32_t b0, uint32_t n_blocks, int *err) {
     extern __shared__ __align__(16) unsigned char inf_smem[];
     const int lane = (int)(threadIdx.x & 31);
     mdinflate::Decoder &D = ((mdinflate::Decoder *) inf_smem)[threadIdx.x >> 5];
     // one block per warp and the CTA retires: the decode stream has the lowest priority, so the slots that free up go to the
     // count / prep kernels of the tile in flight first (persistent decoder CTAs would hold every SM until the segment is done)
-    const uint32_t b = blockIdx.x * INF_WARPS + (threadIdx.x >> 5);
+    const uint32_t b = b0 + blockIdx.x * INF_WARPS + (threadIdx.x >> 5);      // this launch covers blocks [b0, n_blocks)
     if (b >= n_blocks) return;
     const md_bgzf_block d = blk[b];
     if (d.isize == 0) return;
@@ -114,6 +114,12 @@ struct md_bam_stream {
     md_ctx *c = nullptr; int32_t n_targets = 0;
     BamSlot slot[2]; int cur_slot = 0; bool have_segment = false;
     cudaStream_t sd = nullptr;          // decode stream
+    // a large segment is copied in PUSH_PARTS pieces on `sc`, and every piece is inflated (its own launch, on its own stream)
+    // as soon as it has arrived, so that only the first piece's copy is exposed instead of the whole segment's
+    enum { PUSH_PARTS = 4 };
+    cudaStream_t sc = nullptr, si[PUSH_PARTS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_pre = nullptr, ev_c0 = nullptr, ev_i0 = nullptr, ev_copy[PUSH_PARTS] = {nullptr, nullptr, nullptr, nullptr}, ev_inf[PUSH_PARTS] = {nullptr, nullptr, nullptr, nullptr};
+    bool parts_ok = false;
     std::thread worker; bool inflight = false; int target = 0;
     DevBuf cub_tmp, sz, off;
     TileArena tile[2]; int cur = 0;
@@ -131,6 +137,14 @@ extern "C" md_bam_stream *md_bam_open(md_ctx *c, int32_t n_targets) {
     bool ok = cudaStreamCreateWithPriority(&s->sd, cudaStreamNonBlocking, prio_lo) == cudaSuccess && cudaMallocHost((void **) &s->h_tot, 2 * sizeof(Sz4)) == cudaSuccess;
     for (int k = 0; k < 2 && ok; ++k) ok = cudaMallocHost((void **) &s->slot[k].h_small, 64) == cudaSuccess && s->slot[k].small.reserve(256) == 0;
     if (!ok) { g_err = "md_bam_open: allocation failed"; delete s; return nullptr; }
+    {   // optional: without these the segment is copied and inflated in one piece
+        const char *e = getenv("MD_PUSH_PARTS");
+        bool po = !(e && e[0] == '1' && e[1] == 0) && cudaStreamCreateWithFlags(&s->sc, cudaStreamNonBlocking) == cudaSuccess;
+        po = po && cudaEventCreate(&s->ev_pre) == cudaSuccess && cudaEventCreate(&s->ev_c0) == cudaSuccess && cudaEventCreate(&s->ev_i0) == cudaSuccess;
+        for (int k = 0; k < md_bam_stream::PUSH_PARTS && po; ++k)
+            po = cudaStreamCreateWithPriority(&s->si[k], cudaStreamNonBlocking, prio_lo) == cudaSuccess && cudaEventCreate(&s->ev_copy[k]) == cudaSuccess && cudaEventCreate(&s->ev_inf[k]) == cudaSuccess;
+        s->parts_ok = po;
+    }
     return s;
 }
 static void bam_join(md_bam_stream *s) { if (s->worker.joinable()) s->worker.join(); }
@@ -151,6 +165,11 @@ extern "C" void md_bam_close(md_bam_stream *s) {
     for (DevBuf *b : bufs) b->release();
     if (s->h_tot) cudaFreeHost(s->h_tot);
     if (s->sd) cudaStreamDestroy(s->sd);
+    if (s->sc) cudaStreamDestroy(s->sc);
+    for (int k = 0; k < md_bam_stream::PUSH_PARTS; ++k) { if (s->si[k]) cudaStreamDestroy(s->si[k]); if (s->ev_copy[k]) cudaEventDestroy(s->ev_copy[k]); if (s->ev_inf[k]) cudaEventDestroy(s->ev_inf[k]); }
+    if (s->ev_pre) cudaEventDestroy(s->ev_pre);
+    if (s->ev_c0) cudaEventDestroy(s->ev_c0);
+    if (s->ev_i0) cudaEventDestroy(s->ev_i0);
     delete s;
 }
 extern "C" void md_bam_reset(md_bam_stream *s) {       // after a seek: forget the straddling record and the carried reads
@@ -192,20 +211,57 @@ static int bam_push_impl(md_bam_stream *s, BamSlot &S, const BamSlot *P, const v
         S.ubuf.reserve(U + 64) || S.scan.reserve((size_t) n_blocks * sizeof(BlockScan) + 16) || S.cnt.reserve((size_t) n_blocks * 4 + 16) || S.base.reserve((size_t) n_blocks * 4 + 16) ||
         S.runs.reserve((size_t) BAM_MAX_RUNS * sizeof(md_bam_run))) { S.err = "md_bam_push: out of device memory"; return -100; }
     BamTimer tm(st, true); tm.tick();
-    // the straddling record's first bytes go in front of the new data
-    if (carry_in) PCK(cudaMemcpyAsync((uint8_t *) S.ubuf.p + D0, (const uint8_t *) P->ubuf.p + P->leftover_from, carry_in, cudaMemcpyDeviceToDevice, st));
-    PCK(cudaMemcpyAsync(S.comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, st));
-    PCK(cudaMemsetAsync((uint8_t *) S.comp.p + comp_bytes, 0, 1024, st));     // the decoder stages the stream in 256-byte chunks: it reads up to two chunks past a stream's end
-    PCK(cudaMemcpyAsync(S.blk.p, blocks, (size_t) n_blocks * sizeof(md_bgzf_block), cudaMemcpyHostToDevice, st));
-    PCK(cudaMemcpyAsync(S.uoff.p, uoff.data(), (size_t)(n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
-    PCK(cudaMemsetAsync(S.small.p, 0, 256, st));
     uint32_t *d_small = (uint32_t *) S.small.p;       // [0] n_runs [1] err [2] bad [3] last_pos [4,5] final_exit
     const uint8_t *u = (const uint8_t *) S.ubuf.p;
     const unsigned long long first = D0 + (carry_in ? 0 : skip);
-    tm.tick();
-    if (n_blocks) {
-        inflate_kernel<<<(n_blocks + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, INF_SMEM, st>>>((const uint8_t *) S.comp.p, (const md_bgzf_block *) S.blk.p, (const unsigned long long *) S.uoff.p, (uint8_t *) S.ubuf.p, n_blocks, (int *)(d_small + 1));
+    // the straddling record's first bytes go in front of the new data
+    if (carry_in) PCK(cudaMemcpyAsync((uint8_t *) S.ubuf.p + D0, (const uint8_t *) P->ubuf.p + P->leftover_from, carry_in, cudaMemcpyDeviceToDevice, st));
+    PCK(cudaMemsetAsync(S.small.p, 0, 256, st));
+    const int NP = md_bam_stream::PUSH_PARTS;
+    const bool in_parts = s->parts_ok && n_blocks >= 1024;
+    if (!in_parts) {
+        PCK(cudaMemcpyAsync(S.comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, st));
+        PCK(cudaMemsetAsync((uint8_t *) S.comp.p + comp_bytes, 0, 1024, st));     // the decoder stages the stream in 256-byte chunks: it reads up to two chunks past a stream's end
+        PCK(cudaMemcpyAsync(S.blk.p, blocks, (size_t) n_blocks * sizeof(md_bgzf_block), cudaMemcpyHostToDevice, st));
+        PCK(cudaMemcpyAsync(S.uoff.p, uoff.data(), (size_t)(n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
         tm.tick();
+        if (n_blocks) inflate_kernel<<<(n_blocks + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, INF_SMEM, st>>>((const uint8_t *) S.comp.p, (const md_bgzf_block *) S.blk.p, (const unsigned long long *) S.uoff.p, (uint8_t *) S.ubuf.p, 0u, n_blocks, (int *)(d_small + 1));
+        tm.tick();
+    } else {
+        // piece p = blocks [bp[p], bp[p+1]) and the bytes [lo[p], lo[p+1]) of the buffer, cut where a block's stream begins.  A decoder
+        // reads up to 3 chunks of 256 bytes beyond its stream's end (never using them), so every copy runs 1 KB into the next
+        // piece: the bytes a launch touches have all arrived when its event fires (copies are in order on `sc`).
+        uint32_t bp[md_bam_stream::PUSH_PARTS + 1]; uint64_t lo[md_bam_stream::PUSH_PARTS + 1];
+        bp[0] = 0; lo[0] = 0; bp[NP] = n_blocks; lo[NP] = comp_bytes;
+        for (int q = 1; q < NP; ++q) {
+            const uint64_t want = comp_bytes * (uint64_t) q / NP;
+            uint32_t a = bp[q - 1], z = n_blocks;                  // first block whose stream starts at or beyond `want`
+            while (a < z) { const uint32_t m = (a + z) / 2; if (blocks[m].comp_off < want) a = m + 1; else z = m; }
+            bp[q] = a; lo[q] = a < n_blocks ? blocks[a].comp_off : comp_bytes;
+        }
+        PCK(cudaEventRecord(s->ev_pre, st));                       // the error flag is cleared, the carried bytes are queued
+        PCK(cudaEventRecord(s->ev_c0, s->sc));
+        PCK(cudaMemsetAsync((uint8_t *) S.comp.p + comp_bytes, 0, 1024, s->sc));
+        PCK(cudaMemcpyAsync(S.blk.p, blocks, (size_t) n_blocks * sizeof(md_bgzf_block), cudaMemcpyHostToDevice, s->sc));
+        PCK(cudaMemcpyAsync(S.uoff.p, uoff.data(), (size_t)(n_blocks + 1) * 8, cudaMemcpyHostToDevice, s->sc));
+        for (int q = 0; q < NP; ++q) {
+            const uint64_t hi = std::min<uint64_t>(comp_bytes, lo[q + 1] + 1024);
+            if (hi > lo[q]) PCK(cudaMemcpyAsync((uint8_t *) S.comp.p + lo[q], (const uint8_t *) comp + lo[q], hi - lo[q], cudaMemcpyHostToDevice, s->sc));
+            PCK(cudaEventRecord(s->ev_copy[q], s->sc));
+        }
+        for (int q = 0; q < NP; ++q) {
+            PCK(cudaStreamWaitEvent(s->si[q], s->ev_pre, 0));
+            PCK(cudaStreamWaitEvent(s->si[q], s->ev_copy[q], 0));
+            if (q == 0) PCK(cudaEventRecord(s->ev_i0, s->si[0]));
+            if (bp[q + 1] > bp[q])
+                inflate_kernel<<<(bp[q + 1] - bp[q] + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, INF_SMEM, s->si[q]>>>((const uint8_t *) S.comp.p, (const md_bgzf_block *) S.blk.p, (const unsigned long long *) S.uoff.p, (uint8_t *) S.ubuf.p, bp[q], bp[q + 1], (int *)(d_small + 1));
+            PCK(cudaEventRecord(s->ev_inf[q], s->si[q]));
+            S.launches += 1;
+        }
+        for (int q = 0; q < NP; ++q) PCK(cudaStreamWaitEvent(st, s->ev_inf[q], 0));
+        tm.tick(); tm.tick();                                      // (copy and inflate are timed by their own events below)
+    }
+    if (n_blocks) {
         const uint32_t g = (n_blocks + 127) / 128;
         // block 0's slice starts at D0 so that the straddling record is part of its chain
         unsigned long long d0 = D0;
@@ -218,8 +274,8 @@ static int bam_push_impl(md_bam_stream *s, BamSlot &S, const BamSlot *P, const v
         cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const uint32_t *) S.cnt.p, (uint32_t *) S.base.p, (int) n_blocks, st);
         if (S.cub_tmp.reserve(tmp + 256)) { S.err = "md_bam_push: out of device memory"; return -100; }
         cub::DeviceScan::ExclusiveSum(S.cub_tmp.p, tmp, (const uint32_t *) S.cnt.p, (uint32_t *) S.base.p, (int) n_blocks, st);
-        S.launches += 6;
-    } else tm.tick();
+        S.launches += in_parts ? 5 : 6;
+    }
     tm.tick();
     // number of records = base[last] + cnt[last]
     uint32_t last2[2] = {0, 0};
@@ -259,7 +315,18 @@ static int bam_push_impl(md_bam_stream *s, BamSlot &S, const BamSlot *P, const v
             r.last_pos = k + 1 < nr ? S.runs_host[k + 1].prev_last_pos : (int32_t) S.h_small[3];
         }
     }
-    tm.add(s->t_push); s->n_push++; s->comp_total += comp_bytes; s->infl_total += tot; s->rec_total += n;
+    {
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        tm.add(acc);
+        if (in_parts) {                                            // everything has completed: the stream was synchronised above
+            float h = 0, f = 0;
+            cudaEventElapsedTime(&h, s->ev_c0, s->ev_copy[NP - 1]);
+            cudaEventElapsedTime(&f, s->ev_i0, tm.ev[1]);          // first launch's start -> all pieces inflated
+            acc[0] = h; acc[1] = f;
+        }
+        for (int k = 0; k < 8; ++k) s->t_push[k] += acc[k];
+    }
+    s->n_push++; s->comp_total += comp_bytes; s->infl_total += tot; s->rec_total += n;
     PCK(cudaGetLastError());
     S.sum.n_records = n; S.sum.n_runs = (uint32_t) S.runs_host.size(); S.sum.inflated_bytes = tot; S.sum.leftover_bytes = S.leftover;
     return 0;
