@@ -191,7 +191,15 @@ private:
         return rv;
     }
     static double logit(double p) { return log(p) - log(1 - p); }
-    static char *put_uint(char *w, uint32_t v) { char t[12]; int n = 0; do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) *w++ = t[--n]; return w; }
+    // decimal digits of v; two at a time from a table, written back to front into their final place
+    static char *put_uint(char *w, uint32_t v) {
+        static const char D2[201] = "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+        const int n = v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+        char *e = w + n, *q = e;
+        while (v >= 100u) { const uint32_t r = v % 100u; v /= 100u; q -= 2; memcpy(q, D2 + 2 * r, 2); }
+        if (v >= 10u) { q -= 2; memcpy(q, D2 + 2 * v, 2); } else *--q = (char)('0' + v);
+        return e;
+    }
     static char *put_int(char *w, int32_t v) { if (v < 0) { *w++ = '-'; return put_uint(w, (uint32_t)(-(int64_t) v)); } return put_uint(w, (uint32_t) v); }
 
     // writeCall, extract.c:39-99
@@ -204,7 +212,10 @@ private:
             char *w0 = f->room(chrom_len_ + 80), *w = w0;
             memcpy(w, chrom, chrom_len_); w += chrom_len_; *w++ = '\t';
             w = put_int(w, pos); *w++ = '\t'; w = put_int(w, pos + width); *w++ = '\t';
-            w = put_int(w, (int)(100.0 * ((double) nm) / (nm + nu))); *w++ = '\t';
+            // (int)(100.0 * nm / (nm + nu)) of extract.c:50 in integers: the double quotient of two 32-bit counts is never close
+            // enough to an integer it does not equal for the truncation to differ (gap >= 2^-32, rounding error <= 2^-46)
+            const uint32_t tot = nm + nu;                                   // 32-bit sum, as in the reference
+            w = put_int(w, tot ? (int)(100ull * nm / tot) : (int)(100.0 * ((double) nm) / tot)); *w++ = '\t';
             w = put_uint(w, nm); *w++ = '\t'; w = put_uint(w, nu); *w++ = '\n';
             f->n += (size_t)(w - w0);
         }
