@@ -404,16 +404,22 @@ def run_c2(args, rank, local_rank, world, cores):
     assert bs_, g.g.md_last_error()
     summ = A.MdBamSummary(); runs1 = (A.MdBamRun * 8)()
 
+    PREFETCH = not os.environ.get("MD_NO_PREFETCH")
+
     def bam_step():
         g.g.md_bam_reset(bs_)
         so, sl, arr, nb = seg_arr[0]
         assert g.g.md_bam_push_begin(bs_, hbuf + so, sl, arr, nb, hoff) == 0, g.g.md_last_error()
+        if len(seg_arr) > 1 and PREFETCH:                               # the next segment's bytes travel while this one is inflated
+            assert g.g.md_bam_prefetch(bs_, hbuf + seg_arr[1][0], seg_arr[1][1]) == 0, g.g.md_last_error()
         out_off, open_beg = 0, 0
         for k in range(len(seg_arr)):
             assert g.g.md_bam_push_end(bs_, C.byref(summ)) == 0, g.g.md_last_error()
             if k + 1 < len(seg_arr):
                 so, sl, arr, nb = seg_arr[k + 1]
                 assert g.g.md_bam_push_begin(bs_, hbuf + so, sl, arr, nb, 0) == 0, g.g.md_last_error()
+                if k + 2 < len(seg_arr) and PREFETCH:
+                    assert g.g.md_bam_prefetch(bs_, hbuf + seg_arr[k + 2][0], seg_arr[k + 2][1]) == 0, g.g.md_last_error()
             nr = g.g.md_bam_get_runs(bs_, runs1, 8)
             assert nr == 1 and runs1[0].tid == 0
             cut = reflen if k + 1 == len(seg_arr) else max(runs1[0].last_pos, open_beg)
@@ -489,7 +495,7 @@ def run_c2(args, rank, local_rank, world, cores):
                       "parallelism": "contig interval per GPU, no collective", "l2": "inputs (%.0f MB SoA / %.0f MB compressed BAM per GPU) larger than the 126 MB L2" % (soa_bytes(soa) / 1e6, len(raw) / 1e6)},
            "e2e": {"value": round(total_aln / bam_s / 1e6, 3), "unit": UNIT, "ms_per_step": round(bam_s * 1e3, 3), "h2d_bytes_per_step": len(raw), "d2h_bytes_per_step": int(n_bam_calls * 16),
                    "segments_per_step": len(seg_arr), "launches_per_step": int(bam_launches // max(args.steps, 1)),
-                   "path": "compressed BAM bytes (page-locked) -> md_bam_push_begin/_end (H2D, BGZF inflate, record framing on the device; segment k+1 overlaps the tiles of segment k) -> md_bam_extract_run (tile assembly in HBM + prep + count) -> D2H md_call records"},
+                   "path": "compressed BAM bytes (page-locked) -> md_bam_push_begin/_end + md_bam_prefetch (H2D of segment k+2 under the inflate of k+1; BGZF inflate, record framing on the device; segment k+1 overlaps the tiles of segment k) -> md_bam_extract_run (tile assembly in HBM + prep + count) -> D2H md_call records"},
            "e2e_soa": {"value": round(total_aln / soa_s / 1e6, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(n_soa_calls * 16 + 32 * len(tiles)),
                        "ms_per_step": round(soa_s * 1e3, 3), "tiles_per_step": len(tiles), "lanes": NL,
                        "last_tile_ms": {"h2d": round(soa_t[0], 3), "prep": round(soa_t[1], 3), "count": round(soa_t[2], 3), "d2h": round(soa_t[3], 3)},

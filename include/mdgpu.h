@@ -239,6 +239,11 @@ int md_bam_push(md_bam_stream *s, const void *comp, uint64_t comp_bytes, const m
  * compressed bytes and the block table must stay valid until _end(). */
 int md_bam_push_begin(md_bam_stream *s, const void *comp, uint64_t comp_bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip);
 int md_bam_push_end(md_bam_stream *s, md_bam_summary *out);
+/* Optional, between md_bam_push_begin() and md_bam_push_end(): start the host-to-device copy of the segment that will be pushed
+ * next (same `comp` / `comp_bytes` as that later md_bam_push_begin(), which then skips its copy), so that it overlaps the decode in
+ * flight.  The buffer must stay valid until that later push has ended.  comp == NULL waits for outstanding prefetches and drops
+ * them.  A no-op (0) when no push is in flight. */
+int md_bam_prefetch(md_bam_stream *s, const void *comp, uint64_t comp_bytes);
 int md_bam_get_runs(md_bam_stream *s, md_bam_run *runs, uint32_t cap);
 /* One tile = reads carried from the previous tile of this contig (if that tile ended where this one begins) + run `run`
  * of the last segment (run < 0: carried reads only, to close a contig), restricted to records with pos < keep_hi; then

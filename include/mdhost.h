@@ -51,6 +51,8 @@ typedef struct mdh_backend {
     int   (*set_bed)(void *be, int32_t tid, const md_bed_region *regs, uint32_t n);
     /* optional: perRead (md_per_read_tile); without it the perRead sub-command refuses to run */
     int   (*per_read_tile)(void *be, const md_tile_desc *tile, const md_reads_soa *reads, uint32_t chunk_size, md_read_meth *out);
+    /* optional: md_bam_prefetch — copy of the next segment overlapped with the decode in flight */
+    int   (*bam_prefetch)(void *s, const void *comp, uint64_t bytes);
 } mdh_backend;
 
 /* Same argv conventions as the reference: argv[0] is the sub-command name. */

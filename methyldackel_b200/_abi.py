@@ -118,6 +118,7 @@ BAM_EXTRACT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(MdTileDesc)
 BAM_MBIAS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(MdTileDesc), C.c_uint32, C.POINTER(MdTileStats))
 BAM_PUSH_BEGIN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(MdBgzfBlock), C.c_uint32, C.c_uint32)
 BAM_PUSH_END_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(MdBamSummary))
+BAM_PREFETCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)
 SET_BED_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.POINTER(MdBedRegion), C.c_uint32)
 PER_READ_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(MdTileDesc), C.POINTER(MdReadsSoa), C.c_uint32, C.POINTER(MdReadMeth))
 
@@ -130,7 +131,8 @@ class MdhBackend(C.Structure):
                 ("submit_mbias_tile", SUBMIT_FN),
                 ("bam_open", BAM_OPEN_FN), ("bam_close", BAM_CLOSE_FN), ("bam_reset", BAM_CLOSE_FN), ("bam_push", BAM_PUSH_FN),
                 ("bam_get_runs", BAM_RUNS_FN), ("bam_extract_run", BAM_EXTRACT_FN), ("bam_mbias_run", BAM_MBIAS_FN),
-                ("bam_push_begin", BAM_PUSH_BEGIN_FN), ("bam_push_end", BAM_PUSH_END_FN), ("set_bed", SET_BED_FN), ("per_read_tile", PER_READ_FN)]
+                ("bam_push_begin", BAM_PUSH_BEGIN_FN), ("bam_push_end", BAM_PUSH_END_FN), ("set_bed", SET_BED_FN), ("per_read_tile", PER_READ_FN),
+                ("bam_prefetch", BAM_PREFETCH_FN)]
 
 
 _host = None
@@ -210,6 +212,7 @@ def load_gpu():
         g.md_bam_get_runs.argtypes = [C.c_void_p, C.POINTER(MdBamRun), C.c_uint32]
         g.md_bam_push_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(MdBgzfBlock), C.c_uint32, C.c_uint32]
         g.md_bam_push_end.argtypes = [C.c_void_p, C.POINTER(MdBamSummary)]
+        g.md_bam_prefetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         g.md_bam_extract_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(MdTileDesc), C.c_uint32, C.POINTER(MdCall), C.c_uint64, C.POINTER(MdTileStats)]
         g.md_bam_mbias_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(MdTileDesc), C.c_uint32, C.POINTER(MdTileStats)]
         g.md_bam_tile_shape.argtypes = [C.c_void_p, C.POINTER(MdReadsSoa)]

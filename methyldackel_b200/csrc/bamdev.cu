@@ -108,6 +108,8 @@ struct BamSlot {
     uint32_t n_records = 0;
     std::vector<md_bam_run> runs_host;
     md_bam_summary sum; int rc = 0; std::string err; uint64_t launches = 0;
+    // md_bam_prefetch: the compressed bytes of the segment this slot will decode next are already on their way (copy stream)
+    const void *pref_ptr = nullptr; uint64_t pref_bytes = 0; cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
 };
 
 struct md_bam_stream {
@@ -119,7 +121,7 @@ struct md_bam_stream {
     enum { PUSH_PARTS = 4 };
     cudaStream_t sc = nullptr, si[PUSH_PARTS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_pre = nullptr, ev_c0 = nullptr, ev_i0 = nullptr, ev_copy[PUSH_PARTS] = {nullptr, nullptr, nullptr, nullptr}, ev_inf[PUSH_PARTS] = {nullptr, nullptr, nullptr, nullptr};
-    bool parts_ok = false;
+    bool parts_ok = false, use_parts = false, prefetch_ok = false;
     std::thread worker; bool inflight = false; int target = 0;
     DevBuf cub_tmp, sz, off;
     TileArena tile[2]; int cur = 0;
@@ -138,8 +140,14 @@ extern "C" md_bam_stream *md_bam_open(md_ctx *c, int32_t n_targets) {
     for (int k = 0; k < 2 && ok; ++k) ok = cudaMallocHost((void **) &s->slot[k].h_small, 64) == cudaSuccess && s->slot[k].small.reserve(256) == 0;
     if (!ok) { g_err = "md_bam_open: allocation failed"; delete s; return nullptr; }
     {   // optional: without these the segment is copied and inflated in one piece
+        // (measured: for 96 MB segments — one wave of decoder warps — the staggered quarter waves cost more than the hidden copy
+        //  saves, 9.8 against 9.1 ms per segment; for a 183 MB segment they gain 1 ms of 17.6.  Off unless MD_PUSH_PARTS=4; what
+        //  hides the copy by default is md_bam_prefetch.)
         const char *e = getenv("MD_PUSH_PARTS");
-        bool po = !(e && e[0] == '1' && e[1] == 0) && cudaStreamCreateWithFlags(&s->sc, cudaStreamNonBlocking) == cudaSuccess;
+        s->use_parts = e && atoi(e) == md_bam_stream::PUSH_PARTS;
+        bool po = cudaStreamCreateWithFlags(&s->sc, cudaStreamNonBlocking) == cudaSuccess;
+        s->prefetch_ok = po && cudaEventCreate(&s->slot[0].ev_p0) == cudaSuccess && cudaEventCreate(&s->slot[0].ev_p1) == cudaSuccess &&
+                         cudaEventCreate(&s->slot[1].ev_p0) == cudaSuccess && cudaEventCreate(&s->slot[1].ev_p1) == cudaSuccess;
         po = po && cudaEventCreate(&s->ev_pre) == cudaSuccess && cudaEventCreate(&s->ev_c0) == cudaSuccess && cudaEventCreate(&s->ev_i0) == cudaSuccess;
         for (int k = 0; k < md_bam_stream::PUSH_PARTS && po; ++k)
             po = cudaStreamCreateWithPriority(&s->si[k], cudaStreamNonBlocking, prio_lo) == cudaSuccess && cudaEventCreate(&s->ev_copy[k]) == cudaSuccess && cudaEventCreate(&s->ev_inf[k]) == cudaSuccess;
@@ -165,7 +173,8 @@ extern "C" void md_bam_close(md_bam_stream *s) {
     for (DevBuf *b : bufs) b->release();
     if (s->h_tot) cudaFreeHost(s->h_tot);
     if (s->sd) cudaStreamDestroy(s->sd);
-    if (s->sc) cudaStreamDestroy(s->sc);
+    if (s->sc) { cudaStreamSynchronize(s->sc); cudaStreamDestroy(s->sc); }
+    for (int k = 0; k < 2; ++k) { if (s->slot[k].ev_p0) cudaEventDestroy(s->slot[k].ev_p0); if (s->slot[k].ev_p1) cudaEventDestroy(s->slot[k].ev_p1); }
     for (int k = 0; k < md_bam_stream::PUSH_PARTS; ++k) { if (s->si[k]) cudaStreamDestroy(s->si[k]); if (s->ev_copy[k]) cudaEventDestroy(s->ev_copy[k]); if (s->ev_inf[k]) cudaEventDestroy(s->ev_inf[k]); }
     if (s->ev_pre) cudaEventDestroy(s->ev_pre);
     if (s->ev_c0) cudaEventDestroy(s->ev_c0);
@@ -174,6 +183,8 @@ extern "C" void md_bam_close(md_bam_stream *s) {
 }
 extern "C" void md_bam_reset(md_bam_stream *s) {       // after a seek: forget the straddling record and the carried reads
     bam_join(s); s->inflight = false;
+    if (s->sc) { cudaSetDevice(s->c->device); cudaStreamSynchronize(s->sc); }
+    s->slot[0].pref_ptr = s->slot[1].pref_ptr = nullptr;
     s->have_segment = false; s->slot[0].leftover = s->slot[1].leftover = 0; s->tile[0].valid = s->tile[1].valid = false;
 }
 
@@ -218,10 +229,17 @@ static int bam_push_impl(md_bam_stream *s, BamSlot &S, const BamSlot *P, const v
     if (carry_in) PCK(cudaMemcpyAsync((uint8_t *) S.ubuf.p + D0, (const uint8_t *) P->ubuf.p + P->leftover_from, carry_in, cudaMemcpyDeviceToDevice, st));
     PCK(cudaMemsetAsync(S.small.p, 0, 256, st));
     const int NP = md_bam_stream::PUSH_PARTS;
-    const bool in_parts = s->parts_ok && n_blocks >= 1024;
+    // the compressed bytes may already be here (md_bam_prefetch with the same buffer); a prefetch of something else is waited out
+    const bool prefetched = S.pref_ptr && S.pref_ptr == comp && S.pref_bytes == comp_bytes;
+    if (S.pref_ptr) PCK(cudaStreamWaitEvent(st, S.ev_p1, 0));
+    const bool had_prefetch = S.pref_ptr != nullptr;
+    S.pref_ptr = nullptr; S.pref_bytes = 0;
+    const bool in_parts = s->parts_ok && s->use_parts && !prefetched && n_blocks >= 1024;
     if (!in_parts) {
-        PCK(cudaMemcpyAsync(S.comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, st));
-        PCK(cudaMemsetAsync((uint8_t *) S.comp.p + comp_bytes, 0, 1024, st));     // the decoder stages the stream in 256-byte chunks: it reads up to two chunks past a stream's end
+        if (!prefetched) {
+            PCK(cudaMemcpyAsync(S.comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, st));
+            PCK(cudaMemsetAsync((uint8_t *) S.comp.p + comp_bytes, 0, 1024, st));     // the decoder stages the stream in 256-byte chunks: it reads up to two chunks past a stream's end
+        }
         PCK(cudaMemcpyAsync(S.blk.p, blocks, (size_t) n_blocks * sizeof(md_bgzf_block), cudaMemcpyHostToDevice, st));
         PCK(cudaMemcpyAsync(S.uoff.p, uoff.data(), (size_t)(n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
         tm.tick();
@@ -318,6 +336,8 @@ static int bam_push_impl(md_bam_stream *s, BamSlot &S, const BamSlot *P, const v
     {
         double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         tm.add(acc);
+        if (prefetched) { float h = 0; cudaEventElapsedTime(&h, S.ev_p0, S.ev_p1); acc[0] = h; }      // the copy ran on the copy stream, earlier
+        (void) had_prefetch;
         if (in_parts) {                                            // everything has completed: the stream was synchronised above
             float h = 0, f = 0;
             cudaEventElapsedTime(&h, s->ev_c0, s->ev_copy[NP - 1]);
@@ -329,6 +349,31 @@ static int bam_push_impl(md_bam_stream *s, BamSlot &S, const BamSlot *P, const v
     s->n_push++; s->comp_total += comp_bytes; s->infl_total += tot; s->rec_total += n;
     PCK(cudaGetLastError());
     S.sum.n_records = n; S.sum.n_runs = (uint32_t) S.runs_host.size(); S.sum.inflated_bytes = tot; S.sum.leftover_bytes = S.leftover;
+    return 0;
+}
+
+// While a push is in flight: start copying the compressed bytes of the segment that will be pushed AFTER it (on the copy stream,
+// into the slot that push will use — its previous contents were inflated two pushes ago).  md_bam_push_begin() with the same
+// buffer and size then skips its copy, so the host-to-device transfer of segment k+2 hides behind the inflate of segment k+1.
+// comp == NULL: wait for outstanding prefetches and forget them (before the caller releases its buffers).
+extern "C" int md_bam_prefetch(md_bam_stream *s, const void *comp, uint64_t comp_bytes) {
+    if (!s || !s->prefetch_ok) return 0;
+    cudaSetDevice(s->c->device);
+    if (!comp) {
+        cudaStreamSynchronize(s->sc);
+        if (!s->inflight) { s->slot[0].pref_ptr = s->slot[1].pref_ptr = nullptr; }
+        else s->slot[s->target ^ 1].pref_ptr = nullptr;
+        return 0;
+    }
+    if (!s->inflight) return 0;                                    // only defined relative to a push in flight; otherwise a no-op
+    BamSlot &S = s->slot[s->target ^ 1];
+    if (S.pref_ptr) return 0;
+    if (S.comp.reserve(comp_bytes + 1024)) { g_err = "md_bam_prefetch: out of device memory"; return -100; }
+    if (cudaEventRecord(S.ev_p0, s->sc) != cudaSuccess ||
+        cudaMemcpyAsync(S.comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, s->sc) != cudaSuccess ||
+        cudaMemsetAsync((uint8_t *) S.comp.p + comp_bytes, 0, 1024, s->sc) != cudaSuccess ||
+        cudaEventRecord(S.ev_p1, s->sc) != cudaSuccess) { g_err = "md_bam_prefetch: copy failed"; return -100; }
+    S.pref_ptr = comp; S.pref_bytes = comp_bytes;
     return 0;
 }
 

@@ -348,10 +348,10 @@ int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamNa
         return r;
     };
     // Segment k+1 is handed to the device (copy + inflate + record tables, on a helper thread and its own stream) before
-    // the tiles of segment k are requested, when the back end offers the two-phase push.
+    // the tiles of segment k are requested, when the back end offers the two-phase push; and when it offers the prefetch, the
+    // compressed bytes of segment k+2 start travelling as soon as segment k+1 is being decoded.
     const bool overlapped = be->bam_push_begin && be->bam_push_end;
-    std::vector<md_bgzf_block> blk[2]; int cur = 0;
-    const uint8_t *base[2] = {nullptr, nullptr}; size_t bytes[2] = {0, 0};
+    const bool prefetching = overlapped && be->bam_prefetch && !getenv("MD_NO_PREFETCH");
     // large files go through page-locked staging buffers filled by a background reader (StagedSegments); small ones are
     // pushed straight from the file mapping (allocating the buffers would cost more than it saves)
     std::unique_ptr<StagedSegments> staged;
@@ -360,32 +360,44 @@ int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamNa
         const bool want = e ? e[0] != '0' : seg.remaining() >= ((size_t) 512 << 20);
         if (want && be->pinned_alloc && be->pinned_free) { staged.reset(new StagedSegments(bamName, seg.tell(), target, be->pinned_alloc, be->pinned_free)); if (!staged->staged()) staged.reset(); }
     }
-    auto next_segment = [&](int slot) -> bool {
+    // three segments are alive at a time: k (its tiles), k+1 (being decoded), k+2 (being copied)
+    struct HostSeg { const uint8_t *base = nullptr; size_t bytes = 0; std::vector<md_bgzf_block> blk; bool have = false; } hs[3];
+    auto next_segment = [&](HostSeg &h) {
         Acc a_(5);
-        if (!staged) return seg.next(target, base[slot], bytes[slot], blk[slot]);
+        if (!staged) { h.have = seg.next(target, h.base, h.bytes, h.blk); return; }
         StagedSegments::Seg sg;
-        if (!staged->next(sg)) return false;
-        base[slot] = sg.base; bytes[slot] = sg.bytes; blk[slot].swap(sg.blocks);
-        return true;
+        h.have = staged->next(sg);
+        if (h.have) { h.base = sg.base; h.bytes = sg.bytes; h.blk.swap(sg.blocks); }
     };
-    bool have_cur = next_segment(0);
-    bool pushed = false;
-    if (have_cur && overlapped) { if (be->bam_push_begin(bs, base[0], bytes[0], blk[0].data(), (uint32_t) blk[0].size(), skip) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; } pushed = true; }
-    bool done = false; size_t n_seg = 0;
-    while (have_cur && !done && rc == 0) {
+    auto dev_fail = [&]() { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); return -20; };
+    size_t n_seg = 0;                                      // index of the segment whose tiles are being requested: lives in hs[n_seg % 3]
+    next_segment(hs[0]);
+    bool pushed = false, fetched_ahead = false;            // fetched_ahead: hs[(n_seg + 1) % 3] already holds (or was asked for) segment n_seg + 1
+    if (hs[0].have && overlapped) {
+        if (be->bam_push_begin(bs, hs[0].base, hs[0].bytes, hs[0].blk.data(), (uint32_t) hs[0].blk.size(), skip) != 0) return dev_fail();
+        pushed = true;
+        if (prefetching) { next_segment(hs[1]); fetched_ahead = true; if (hs[1].have && be->bam_prefetch(bs, hs[1].base, hs[1].bytes) != 0) return dev_fail(); }
+    }
+    bool done = false;
+    while (hs[n_seg % 3].have && !done && rc == 0) {
+        HostSeg &cur = hs[n_seg % 3], &nxt = hs[(n_seg + 1) % 3], &nxt2 = hs[(n_seg + 2) % 3];
         double t0 = now_s();
         md_bam_summary sum;
-        int r; { Acc a_(7); r = overlapped ? be->bam_push_end(bs, &sum) : be->bam_push(bs, base[cur], bytes[cur], blk[cur].data(), (uint32_t) blk[cur].size(), skip, &sum); }
+        int r; { Acc a_(7); r = overlapped ? be->bam_push_end(bs, &sum) : be->bam_push(bs, cur.base, cur.bytes, cur.blk.data(), (uint32_t) cur.blk.size(), skip, &sum); }
         pushed = false; skip = 0;
         g_stats.t_decode_s += now_s() - t0;
         if (g_marks && (n_seg < 4 || n_seg % 10 == 0)) { char m[64]; snprintf(m, sizeof m, "segment %zu decoded", n_seg); mark(m); }
-        ++n_seg;
-        if (r != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; }
+        if (r != 0) { rc = dev_fail(); break; }
         // cut the next segment now: whether the file ends here decides how this segment's last run is closed
-        const int nxt = cur ^ 1;
-        const bool have_next = next_segment(nxt);
+        if (!fetched_ahead) next_segment(nxt);
+        fetched_ahead = false;
+        const bool have_next = nxt.have;
         const bool file_end = !have_next;
-        if (have_next && overlapped) { Acc a_(8); if (be->bam_push_begin(bs, base[nxt], bytes[nxt], blk[nxt].data(), (uint32_t) blk[nxt].size(), 0) != 0) { fprintf(stderr, "device error: %s\n", be->last_error ? be->last_error() : "?"); rc = -20; break; } pushed = true; }
+        if (have_next && overlapped) {
+            { Acc a_(8); if (be->bam_push_begin(bs, nxt.base, nxt.bytes, nxt.blk.data(), (uint32_t) nxt.blk.size(), 0) != 0) { rc = dev_fail(); break; } }
+            pushed = true;
+            if (prefetching) { next_segment(nxt2); fetched_ahead = true; if (nxt2.have && be->bam_prefetch(bs, nxt2.base, nxt2.bytes) != 0) { rc = dev_fail(); break; } }
+        }
         g_stats.n_records += sum.n_records;
         runs.resize(sum.n_runs);
         if (sum.n_runs) { Acc a_(9); be->bam_get_runs(bs, runs.data(), sum.n_runs); }
@@ -412,9 +424,10 @@ int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamNa
                 if (cj >= jobs.size()) done = true;
             }
         }
-        have_cur = have_next; cur = nxt;
+        ++n_seg;
     }
     if (pushed) { md_bam_summary dummy; be->bam_push_end(bs, &dummy); }            // a segment beyond the region was already on its way
+    if (prefetching) be->bam_prefetch(bs, nullptr, 0);                             // ... and so may be a copy: it must not outlive the staging buffers
     while (rc == 0 && cj < jobs.size()) rc = finish();
     return rc;
 }

@@ -26,11 +26,12 @@ int be_bam_extract(void *s, int run, const md_tile_desc *t, uint32_t keep_hi, md
 int be_bam_mbias(void *s, int run, const md_tile_desc *t, uint32_t keep_hi, md_tile_stats *st) { return md_bam_mbias_run((md_bam_stream *) s, run, t, keep_hi, st); }
 int be_bam_push_begin(void *s, const void *comp, uint64_t bytes, const md_bgzf_block *blocks, uint32_t n, uint32_t skip) { return md_bam_push_begin((md_bam_stream *) s, comp, bytes, blocks, n, skip); }
 int be_bam_push_end(void *s, md_bam_summary *out) { return md_bam_push_end((md_bam_stream *) s, out); }
+int be_bam_prefetch(void *s, const void *comp, uint64_t bytes) { return md_bam_prefetch((md_bam_stream *) s, comp, bytes); }
 int be_set_bed(void *b, int32_t tid, const md_bed_region *r, uint32_t n) { return md_set_bed((md_ctx *) b, tid, r, n); }
 int be_per_read(void *b, const md_tile_desc *t, const md_reads_soa *r, uint32_t chunk, md_read_meth *out) { return md_per_read_tile((md_ctx *) b, t, r, chunk, out); }
 
 const mdh_backend g_backend = {nullptr, be_create, be_destroy, be_load, be_drop, be_extract, be_chunks, be_mbias, be_hist, md_last_error, be_submit, be_collect, md_alloc_pinned, md_free_pinned, be_submit_mbias,
-                               be_bam_open, be_bam_close, be_bam_reset, be_bam_push, be_bam_runs, be_bam_extract, be_bam_mbias, be_bam_push_begin, be_bam_push_end, be_set_bed, be_per_read};
+                               be_bam_open, be_bam_close, be_bam_reset, be_bam_push, be_bam_runs, be_bam_extract, be_bam_mbias, be_bam_push_begin, be_bam_push_end, be_set_bed, be_per_read, be_bam_prefetch};
 int env_device() { const char *e = getenv("MD_DEVICE"); return e ? atoi(e) : 0; }
 }  // namespace
 

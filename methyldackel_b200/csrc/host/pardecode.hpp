@@ -369,7 +369,7 @@ private:
 class StagedSegments {
 public:
     struct Seg { const uint8_t *base = nullptr; size_t bytes = 0; std::vector<md_bgzf_block> blocks; };
-    StagedSegments(const std::string &path, uint64_t file_off, size_t target, void *(*alloc)(size_t), void (*release)(void *), int depth = 4, int io_threads = 6)
+    StagedSegments(const std::string &path, uint64_t file_off, size_t target, void *(*alloc)(size_t), void (*release)(void *), int depth = 5, int io_threads = 6)
         : target_(target), alloc_(alloc), release_(release), io_threads_(io_threads), off_(file_off) {
         fd_ = ::open(path.c_str(), O_RDONLY);
         struct stat st;
@@ -378,7 +378,7 @@ public:
         cap_ = target + (1u << 17);                       // a segment ends at the first block boundary at or beyond the target
         // the first buffer now (it also tells whether page-locked memory can be had at all); the others are allocated by the reader
         // when it first needs them, so the consumer gets segment 0 after one allocation instead of `depth`
-        buf_.assign((size_t) std::max(depth, 3), nullptr);
+        buf_.assign((size_t) std::max(depth, 4), nullptr);
         buf_[0] = alloc ? (uint8_t *) alloc(cap_) : nullptr;
         if (buf_[0]) th_ = std::thread([this] { run(); });
     }
@@ -389,7 +389,8 @@ public:
         if (fd_ >= 0) ::close(fd_);
     }
     bool staged() const { return th_.joinable(); }
-    // next segment in file order; false at the end of the file.  The previous result stays valid until the call after the next.
+    // next segment in file order; false at the end of the file.  A result stays valid until the SECOND call after the one that
+    // returned it (the driver holds two at a time: one being decoded, one being copied ahead — md_bam_prefetch).
     bool next(Seg &out) {
         std::unique_lock<std::mutex> l(m_);
         ++taken_; cv_.notify_all();
@@ -403,7 +404,7 @@ private:
     void run() {
         try {
             for (size_t k = 0; off_ + 18 <= size_; ++k) {
-                { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return stop_ || k + 1 < taken_ + buf_.size(); }); if (stop_) return; }   // at most depth - 1 segments ahead of the consumer's last call
+                { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return stop_ || k + 2 < taken_ + buf_.size(); }); if (stop_) return; }   // segment k reuses the buffer of segment k - depth, which must have been returned at least three calls ago
                 uint8_t *&slot = buf_[k % buf_.size()];
                 if (!slot) { slot = (uint8_t *) alloc_(cap_); if (!slot) throw std::runtime_error("out of page-locked memory for the staging buffers"); }
                 uint8_t *dst = slot;

@@ -1,9 +1,9 @@
 # after a host/driver change: GPU test tier, the bench lines of all configurations (no reference arms), CLI timelines
 L=${1:-chk}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_device_decode.py -x -q > gpurun_out/pytest_dd_$L.log 2>&1 || { echo "device-decode tests FAILED with the piecewise push: falling back to MD_PUSH_PARTS=1"; tail -15 gpurun_out/pytest_dd_$L.log; export MD_PUSH_PARTS=1; }
+timeout 600 python -m pytest tests/test_gpu_device_decode.py -x -q > gpurun_out/pytest_dd_$L.log 2>&1 || { echo "device-decode tests FAILED with the prefetch: falling back to MD_NO_PREFETCH=1"; tail -15 gpurun_out/pytest_dd_$L.log; export MD_NO_PREFETCH=1; }
 tail -2 gpurun_out/pytest_dd_$L.log
-echo "A/B of the piecewise push (tools/kprof.py, one 183 MB segment):"; KPROF_ONLY=decode KPROF_REPS=6 python tools/kprof.py 2>&1 | tail -1; MD_PUSH_PARTS=1 KPROF_ONLY=decode KPROF_REPS=6 python tools/kprof.py 2>&1 | tail -1
+echo "A/B of the prefetch (bench.py c2, e2e ms per step):"; for v in "" 1; do MD_NO_PREFETCH=$v python bench.py --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('MD_NO_PREFETCH=$v', d['e2e']['value'], d['e2e']['ms_per_step'], d['inflate'])"; done
 ( time timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_device_decode.py ) > gpurun_out/pytest_$L.log 2>&1; tail -4 gpurun_out/pytest_$L.log
 python bench.py --no-cpu-baseline > gpurun_out/bench_c2_$L.json 2> gpurun_out/bench_c2_$L.err; tail -c 600 gpurun_out/bench_c2_$L.json; tail -2 gpurun_out/bench_c2_$L.err
 for C in c3 c5 c4; do
