@@ -89,3 +89,23 @@ def test_a_failed_rank_neither_hangs_nor_leaks_into_the_output(built, synth, tmp
         outs = _launch("mbias", [str(tmp_path / ("mbf%d" % k)), "--noSVG", p + ".fa", p + ".bam"], 29561 + k, extra_env={"MD_TEST_FAIL_RANK": "1", "MD_TEST_ALLSUM": allsum}, expect_ok=False)
         assert outs[0][0] == ""                                 # no report from a failed run
         assert [f for f in os.listdir(str(tmp_path)) if f.startswith("mbf%d" % k)] == []
+
+
+def test_copy_into_pieces_offsets_and_fallback(tmp_path, monkeypatch):
+    """the shard merge: many pieces on several threads land at the right offsets; without copy_file_range it reads and writes"""
+    import os
+    from methyldackel_b200 import api
+    data = os.urandom(3 * 1000 * 1000 + 17)
+    src, dst = tmp_path / "shard", tmp_path / "final"
+    src.write_bytes(data)
+    for threads, piece in ((8, 256 * 1024), (1, 1 << 20), (4, 1 << 30)):
+        dst.write_bytes(b"H" * 100 + b"\0" * len(data) + b"T" * 50)
+        api._copy_into(str(src), str(dst), 100, threads=threads, piece=piece)
+        assert dst.read_bytes() == b"H" * 100 + data + b"T" * 50
+    monkeypatch.delattr(os, "copy_file_range", raising=False)          # e.g. a file system that does not offer it
+    dst.write_bytes(b"H" * 100 + b"\0" * len(data) + b"T" * 50)
+    api._copy_into(str(src), str(dst), 100, threads=3, piece=700 * 1000)
+    assert dst.read_bytes() == b"H" * 100 + data + b"T" * 50
+    (tmp_path / "empty").write_bytes(b"")
+    api._copy_into(str(tmp_path / "empty"), str(dst), 100)
+    assert dst.read_bytes() == b"H" * 100 + data + b"T" * 50
