@@ -376,7 +376,7 @@ int drive_segments(Driver &d, const mdh_backend *be, void *bs, const char *bamNa
     if (hs[0].have && overlapped) {
         if (be->bam_push_begin(bs, hs[0].base, hs[0].bytes, hs[0].blk.data(), (uint32_t) hs[0].blk.size(), skip) != 0) return dev_fail();
         pushed = true;
-        if (prefetching) { next_segment(hs[1]); fetched_ahead = true; if (hs[1].have && be->bam_prefetch(bs, hs[1].base, hs[1].bytes) != 0) return dev_fail(); }
+        if (prefetching) { next_segment(hs[1]); fetched_ahead = true; if (hs[1].have && be->bam_prefetch(bs, hs[1].base, hs[1].bytes) != 0) rc = dev_fail(); }   // (the push in flight is waited for below)
     }
     bool done = false;
     while (hs[n_seg % 3].have && !done && rc == 0) {
