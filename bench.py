@@ -8,7 +8,7 @@ Contract (see the task brief): `python bench.py --gpus N --steps K --warmup W` p
 path over that batch.  With N GPUs every rank owns its own 10 Mbp contig interval (weak scaling, no data-path collective).
   * value     : alignments / s with the SoA batch already resident in HBM (prep + count kernels, CUDA-event timed, max over ranks).
   * e2e       : the same work through the C ABI from HOST buffers holding what the reference starts from — the COMPRESSED BAM
-                (page-locked): md_bam_push_begin/_end (H2D, BGZF inflate and record framing on the device) + md_bam_extract_run
+                (page-locked): md_bam_push_begin/_end + md_bam_prefetch (H2D, BGZF inflate and record framing on the device) + md_bam_extract_run
                 (tile assembly, prep, count) + D2H of the md_call records, every step.  This is the like-for-like counterpart of
                 the reference arm (inflate + decode + pileup), minus its text formatting.
   * e2e_soa   : the round-1 `e2e`: pre-decoded SoA tiles in page-locked memory through md_submit_tile()/md_collect_tile().
