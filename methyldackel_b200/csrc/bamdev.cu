@@ -5,7 +5,7 @@
 // which the CLI otherwise does on host cores (host/pardecode.hpp).  The caller hands over SEGMENTS of the compressed file
 // (whole BGZF blocks, cut by scanning the 18-byte block headers); everything downstream happens in HBM:
 //
-//   inflate_kernel     one warp per BGZF block; the leader lane runs inflate_hd.h:inflate_block with its tables in shared memory
+//   inflate_kernel     one warp per BGZF block: inflate_hd.h:inflate_block, tables + input ring + output ring in shared memory
 //   scan_blocks_kernel one thread per block: first plausible record start inside the block + walk of the record chain from it
 //   check/fix_chain    adopt the per-block chains whose start equals the predecessor's exit (a parallel check); a serial
 //                      walk repairs the blocks where the guess was wrong, so results never depend on the guess
