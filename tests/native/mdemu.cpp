@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <vector>
 #include <string>
+#include <map>
+#include <mutex>
 #include <algorithm>
 #include "../../include/mdgpu.h"
 #include "../../methyldackel_b200/csrc/bamdev_hd.h"
@@ -29,6 +31,12 @@ struct Emu {
     int32_t n_targets; emu_extract_cb ex; emu_mbias_cb mb; void *be;
     Seg seg[2]; int cur_seg = 0; bool have = false;          // two slots, as the device library: tiles read seg[cur_seg]
     bool pending = false; int pending_rc = 0, target = 0; md_bam_summary pending_sum;
+    // The device reads the caller's buffers until md_bam_push_end() returns, so the emulation reads them as LATE as it may: the
+    // decode of a two-phase push happens in emu_bam_push_end().  A caller that recycles a buffer too early is then seen.
+    const void *p_comp = nullptr; uint64_t p_bytes = 0; const md_bgzf_block *p_blocks = nullptr; uint32_t p_nblocks = 0, p_skip = 0;
+    // md_bam_prefetch: the bytes may be copied at any time between the prefetch and the end of the push that uses them, so they
+    // must read the same at both ends
+    const void *pf_ptr = nullptr; uint64_t pf_bytes = 0, pf_sum = 0, n_prefetch_used = 0;
     Tile tile[2]; int cur = 0; std::string err;
     uint64_t n_fix = 0;
 };
@@ -85,11 +93,13 @@ static int push_impl(Emu *e, Seg *s, const Seg *P, const void *comp, uint64_t co
     out->n_records = n; out->n_runs = (uint32_t) s->runs.size(); out->inflated_bytes = tot; out->leftover_bytes = s->leftover;
     return 0;
 }
+static uint64_t fnv64(const void *p, uint64_t n) { const uint8_t *b = (const uint8_t *) p; uint64_t h = 1469598103934665603ull; for (uint64_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull; return h; }
 extern "C" int emu_bam_push_begin(void *sv, const void *comp, uint64_t comp_bytes, const md_bgzf_block *blocks, uint32_t n_blocks, uint32_t skip) {
     Emu *e = (Emu *) sv;
     if (e->pending) { g_emu_err = "a push is already in flight"; return -4; }
     e->target = e->have ? (e->cur_seg ^ 1) : 0;
-    e->pending_rc = push_impl(e, &e->seg[e->target], e->have ? &e->seg[e->cur_seg] : nullptr, comp, comp_bytes, blocks, n_blocks, skip, &e->pending_sum);
+    e->p_comp = comp; e->p_bytes = comp_bytes; e->p_blocks = blocks; e->p_nblocks = n_blocks; e->p_skip = skip;
+    if (e->pf_ptr && (e->pf_ptr != comp || e->pf_bytes != comp_bytes)) e->pf_ptr = nullptr;       // a prefetch is for the very next push
     e->pending = true;
     return 0;
 }
@@ -97,6 +107,12 @@ extern "C" int emu_bam_push_end(void *sv, md_bam_summary *out) {
     Emu *e = (Emu *) sv;
     if (!e->pending) { g_emu_err = "nothing in flight"; return -4; }
     e->pending = false;
+    if (e->pf_ptr && e->pf_ptr == e->p_comp && e->pf_bytes == e->p_bytes) {
+        if (fnv64(e->p_comp, e->p_bytes) != e->pf_sum) { g_emu_err = "a prefetched buffer changed before the push that uses it ended"; return -9; }
+        ++e->n_prefetch_used;
+        e->pf_ptr = nullptr;
+    }
+    e->pending_rc = push_impl(e, &e->seg[e->target], e->have ? &e->seg[e->cur_seg] : nullptr, e->p_comp, e->p_bytes, e->p_blocks, e->p_nblocks, e->p_skip, &e->pending_sum);
     if (e->pending_rc) return e->pending_rc;
     e->cur_seg = e->target; e->have = true;
     if (out) *out = e->pending_sum;
@@ -106,6 +122,20 @@ extern "C" int emu_bam_push(void *sv, const void *comp, uint64_t comp_bytes, con
     int rc = emu_bam_push_begin(sv, comp, comp_bytes, blocks, n_blocks, skip);
     return rc ? rc : emu_bam_push_end(sv, out);
 }
+// md_bam_prefetch: only between push_begin and push_end; comp == NULL drops an outstanding prefetch
+extern "C" int emu_bam_prefetch(void *sv, const void *comp, uint64_t comp_bytes) {
+    Emu *e = (Emu *) sv;
+    if (!comp) { e->pf_ptr = nullptr; return 0; }
+    if (!e->pending || e->pf_ptr) return 0;
+    e->pf_ptr = comp; e->pf_bytes = comp_bytes; e->pf_sum = fnv64(comp, comp_bytes);
+    return 0;
+}
+extern "C" uint64_t emu_bam_prefetch_used(void *sv) { return ((Emu *) sv)->n_prefetch_used; }
+// stand-ins for the page-locked allocator: freed memory is overwritten first, so that a reader of a released buffer sees garbage
+static std::map<void *, size_t> g_pins; static std::mutex g_pins_m; static uint64_t g_pins_total = 0;
+extern "C" void *emu_alloc_pinned(size_t n) { void *p = malloc(n ? n : 1); if (p) { memset(p, 0xA5, n); std::lock_guard<std::mutex> g(g_pins_m); g_pins[p] = n; ++g_pins_total; } return p; }
+extern "C" void emu_free_pinned(void *p) { if (!p) return; size_t n = 0; { std::lock_guard<std::mutex> g(g_pins_m); auto it = g_pins.find(p); if (it != g_pins.end()) { n = it->second; g_pins.erase(it); } } memset(p, 0xDD, n); free(p); }
+extern "C" uint64_t emu_pinned_stats(uint64_t *live) { std::lock_guard<std::mutex> g(g_pins_m); if (live) *live = g_pins.size(); return g_pins_total; }
 extern "C" int emu_bam_get_runs(void *sv, md_bam_run *runs, uint32_t cap) { Emu *e = (Emu *) sv; if (!e->have) return 0; const Seg &s = e->seg[e->cur_seg]; for (size_t k = 0; k < s.runs.size() && k < cap; ++k) runs[k] = s.runs[k]; return (int) s.runs.size(); }
 
 static int build(Emu *s, int run, const md_tile_desc *t, uint32_t keep_hi) {

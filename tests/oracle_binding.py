@@ -53,6 +53,11 @@ def emu():
         e.emu_bam_tile_view.argtypes = [C.c_void_p, C.POINTER(A.MdReadsSoa)]
         e.emu_bam_fixups.restype = C.c_uint64; e.emu_bam_fixups.argtypes = [C.c_void_p]
         e.emu_last_error.restype = C.c_char_p
+        e.emu_bam_prefetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        e.emu_bam_prefetch_used.restype = C.c_uint64; e.emu_bam_prefetch_used.argtypes = [C.c_void_p]
+        e.emu_alloc_pinned.restype = C.c_void_p; e.emu_alloc_pinned.argtypes = [C.c_size_t]
+        e.emu_free_pinned.restype = None; e.emu_free_pinned.argtypes = [C.c_void_p]
+        e.emu_pinned_stats.restype = C.c_uint64; e.emu_pinned_stats.argtypes = [C.POINTER(C.c_uint64)]
         _emu = e
     return _emu
 
@@ -60,7 +65,7 @@ def emu():
 class OracleBackend:
     """mdh_backend whose slots call the oracle port. Keeps the callbacks alive."""
 
-    def __init__(self, device_decode=False, overlapped=True):
+    def __init__(self, device_decode=False, overlapped=True, staging=False):
         o = lib()
         self.state = {}
         st = self.state
@@ -148,6 +153,26 @@ class OracleBackend:
                 two = [A.BAM_PUSH_BEGIN_FN(lambda s_, c, n, bl, nb, sk: e.emu_bam_push_begin(s_, c, n, bl, nb, sk)), A.BAM_PUSH_END_FN(lambda s_, o_: e.emu_bam_push_end(s_, o_))]
                 self._keep += two
                 self.be.bam_push_begin, self.be.bam_push_end = two
+                # md_bam_prefetch: the emulation checks the protocol (same bytes when prefetched and when the push ends)
+                st["bam_streams"] = []
+
+                def bam_open_tracked(b, nt):
+                    h = e.emu_bam_open(nt, ex_cb, mb_cb, b)
+                    st["bam_streams"].append(h)
+                    return h
+
+                def bam_close_tracked(s_):
+                    st["prefetch_used"] = st.get("prefetch_used", 0) + int(e.emu_bam_prefetch_used(s_))
+                    e.emu_bam_close(s_)
+                more = [A.BAM_PREFETCH_FN(lambda s_, c, n: e.emu_bam_prefetch(s_, c, n)), A.BAM_OPEN_FN(bam_open_tracked), A.BAM_CLOSE_FN(bam_close_tracked)]
+                self._keep += more
+                self.be.bam_prefetch, self.be.bam_open, self.be.bam_close = more
+            if staging:
+                # "page-locked" memory: plain memory that is overwritten when it is released (a reader of a recycled staging
+                # buffer then decodes garbage); with it the driver's StagedSegments path runs on the CPU
+                pins = [A.PIN_ALLOC_FN(lambda n: e.emu_alloc_pinned(n)), A.PIN_FREE_FN(lambda p_: e.emu_free_pinned(p_))]
+                self._keep += pins
+                self.be.pinned_alloc, self.be.pinned_free = pins
 
 
 def run_host_main(which, argv, backend):

@@ -16,9 +16,16 @@ from util import run_ref, compare_outputs
 
 def _host_main(sub, argv, env):
     overlapped = env.pop("OVERLAPPED", "1") == "1"           # two-phase push (segment k+1 decoded while segment k's tiles are built) or the plain one
+    staging = env.pop("STAGING", "0") == "1"                 # page-locked staging buffers (stand-ins that are poisoned on release) + md_bam_prefetch
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import oracle_binding as ob; "
-            "sys.exit(ob.run_host_main(%r, %r, ob.OracleBackend(device_decode=True, overlapped=%r)))") % (cases.ROOT, os.path.join(cases.ROOT, "tests"), sub, argv, overlapped)
+            "b = ob.OracleBackend(device_decode=True, overlapped=%r, staging=%r); rc = ob.run_host_main(%r, %r, b); "
+            "sys.stderr.write('\\nPREFETCH_USED %%d\\n' %% b.state.get('prefetch_used', 0)); sys.exit(rc)") % (
+                cases.ROOT, os.path.join(cases.ROOT, "tests"), overlapped, staging, sub, argv)
     return subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, MD_DEVICE_DECODE="1", **env))
+
+
+def _prefetch_used(proc):
+    return int([ln for ln in proc.stderr.splitlines() if ln.startswith("PREFETCH_USED")][-1].split()[1])
 
 
 def _extract_both(built, tmp_path, opts, fa, bam, env):
@@ -37,6 +44,33 @@ def _extract_both(built, tmp_path, opts, fa, bam, env):
 def test_extract_noisy(built, synth, tmp_path, opts, seg):
     p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
     assert _extract_both(built, tmp_path, opts, p + ".fa", p + ".bam", {"MD_SEGMENT_BYTES": seg}) == []
+
+
+@pytest.mark.parametrize("seg", ["1", "30000", "70000"], ids=["block_per_segment", "30kB_segments", "70kB_segments"])
+@pytest.mark.parametrize("opts", [["--CHG", "--CHH", "--mergeContext"], ["-r", "chr1:5000-20000"], ["-r", "chr2", "--methylKit"]], ids=["merge", "region", "contig2"])
+def test_extract_through_staging_buffers_with_prefetch(built, synth, tmp_path, opts, seg):
+    """the round-2 driver on the CPU: segments are read into recycled staging buffers by the background reader, three host
+    segments are alive at a time, the bytes of segment k+2 are prefetched while k+1 is decoded.  The emulation reads the caller's
+    buffers as late as the device may, its "page-locked" memory is poisoned on release, and it refuses a prefetched buffer whose
+    bytes changed before the push that uses it ended — so a buffer recycled too early shows as an error or as different output."""
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    refp, newp = str(tmp_path / "ref"), str(tmp_path / "new")
+    r = run_ref(built["ref_bin"], "extract", opts, p + ".fa", p + ".bam", refp)
+    assert r.returncode == 0, r.stderr
+    n = _host_main("extract", list(opts) + [p + ".fa", p + ".bam", "-o", newp], {"MD_SEGMENT_BYTES": seg, "MD_STAGE": "1", "STAGING": "1"})
+    assert n.returncode == 0, n.stderr
+    assert compare_outputs(refp, newp) == []
+    if opts[0] != "-r":
+        assert _prefetch_used(n) >= 3                        # whole file: every segment from the third on arrives by prefetch
+
+
+def test_mbias_through_staging_buffers_with_prefetch(built, synth, tmp_path):
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    r = subprocess.run([built["ref_bin"], "mbias", "--noSVG", "--CHH", p + ".fa", p + ".bam"], capture_output=True, text=True)
+    n = _host_main("mbias", ["--noSVG", "--CHH", p + ".fa", p + ".bam"], {"MD_SEGMENT_BYTES": "40000", "MD_STAGE": "1", "STAGING": "1"})
+    assert n.returncode == 0, n.stderr
+    assert n.stdout == r.stdout and len(r.stdout) > 500
+    assert _prefetch_used(n) >= 3
 
 
 def test_plain_push(built, synth, tmp_path):
