@@ -126,6 +126,7 @@ extern "C" int emu_bam_push(void *sv, const void *comp, uint64_t comp_bytes, con
 extern "C" int emu_bam_prefetch(void *sv, const void *comp, uint64_t comp_bytes) {
     Emu *e = (Emu *) sv;
     if (!comp) { e->pf_ptr = nullptr; return 0; }
+    if (const char *f = getenv("MDEMU_FAIL_PREFETCH")) { static int calls = 0; if (++calls == atoi(f)) { g_emu_err = "injected prefetch failure"; return -100; } }
     if (!e->pending || e->pf_ptr) return 0;
     e->pf_ptr = comp; e->pf_bytes = comp_bytes; e->pf_sum = fnv64(comp, comp_bytes);
     return 0;

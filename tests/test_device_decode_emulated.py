@@ -73,6 +73,15 @@ def test_mbias_through_staging_buffers_with_prefetch(built, synth, tmp_path):
     assert _prefetch_used(n) >= 3
 
 
+@pytest.mark.parametrize("nth", ["1", "3"])
+def test_a_failing_prefetch_ends_the_run_cleanly(built, synth, tmp_path, nth):
+    """the first / a later md_bam_prefetch fails while a push is in flight: the driver reports the device error and returns
+    (it must wait for the push before it lets go of the staging buffers — the emulation reads them in push_end)"""
+    p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
+    n = _host_main("extract", [p + ".fa", p + ".bam", "-o", str(tmp_path / "x")], {"MD_SEGMENT_BYTES": "30000", "MD_STAGE": "1", "STAGING": "1", "MDEMU_FAIL_PREFETCH": nth})
+    assert n.returncode != 0 and "device error" in n.stderr, (n.returncode, n.stderr[-500:])
+
+
 def test_plain_push(built, synth, tmp_path):
     """back ends without the two-phase push are driven segment by segment"""
     p = synth("noisy", "--contigs", "chr1:60000,chr2:15000", "--depth", "25", "--lower-frac", "0.02", "--n-frac", "0.01")
