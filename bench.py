@@ -156,6 +156,25 @@ def traffic_of(kernel_key):
         return None, None
 
 
+def inflate_summary(file_bytes, segs_per_step, infl_ms, inflated_total, comp_total, frame_ms, h2d_ms, hbm_peak_gbs, e2e_ms_per_step):
+    """The decode kernel that bounds `e2e` (cumulative CUDA-event times over every push of the stream, warm-up included, per
+    segment).  Its algorithmic bytes are compressed bytes in + inflated bytes out; `hbm_frac` only shows how far from memory
+    bound it is — the kernel is bound by instruction issue / its dependency chain."""
+    if not infl_ms or not segs_per_step:
+        return {"kernel": "inflate_kernel", "ms_per_segment": None}
+    comp_seg = file_bytes / segs_per_step
+    ratio = inflated_total / max(1, comp_total)
+    comp_gbs = comp_seg / (infl_ms * 1e-3) / 1e9
+    out = {"kernel": "inflate_kernel", "ms_per_segment": round(infl_ms, 3), "compressed_GBps": round(comp_gbs, 2), "inflated_GBps": round(comp_gbs * ratio, 2),
+           "segments_per_step": segs_per_step, "frame_ms_per_segment": round(frame_ms, 3), "h2d_ms_per_segment": round(h2d_ms, 3),
+           "bound": "instruction issue / dependency chain (not hbm)", "algorithmic_GBps": round(comp_gbs * (1.0 + ratio), 1)}
+    if hbm_peak_gbs:
+        out["hbm_frac"] = round(comp_gbs * (1.0 + ratio) / hbm_peak_gbs, 4)
+    if e2e_ms_per_step:
+        out["share_of_e2e_step"] = round(infl_ms * segs_per_step / e2e_ms_per_step, 3)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ CPU reference arm
 def chunks_for(cores, region_bp):
     """--chunkSize giving every core at least 4 chunks (None: the default 1 Mbp already does)"""
@@ -467,10 +486,7 @@ def run_c2(args, rank, local_rank, world, cores):
                 "traffic": traffic, "traffic_source": traffic_src}
     # the decode kernel that bounds `e2e`: compressed bytes in + inflated bytes out per segment, against the same peak
     nseg = max(1, len(seg_arr) * (args.steps + warm))
-    infl_ms = tot2.inflate_ms / nseg                                   # cumulative over every push of this stream (warm-up included)
-    inflate = {"kernel": "inflate_kernel", "ms_per_segment": round(infl_ms, 3), "compressed_GBps": round(len(raw) / len(seg_arr) / (infl_ms * 1e-3) / 1e9, 2) if infl_ms else None,
-               "inflated_GBps": round(tot2.inflated_bytes / max(1, tot2.comp_bytes) * len(raw) / len(seg_arr) / (infl_ms * 1e-3) / 1e9, 2) if infl_ms else None,
-               "segments_per_step": len(seg_arr), "frame_ms_per_segment": round(tot2.frame_ms / nseg, 3), "h2d_ms_per_segment": round(tot2.push_h2d_ms / nseg, 3)}
+    inflate = inflate_summary(len(raw), len(seg_arr), tot2.inflate_ms / nseg, tot2.inflated_bytes, tot2.comp_bytes, tot2.frame_ms / nseg, tot2.push_h2d_ms / nseg, peak, bam_s * 1e3)
 
     # ------------------------------------------------------------ the drop-in binary from the BAM file (informational)
     cli = None
